@@ -1,0 +1,328 @@
+/*
+ * apex_gpu.h — C ABI of the B200-native bundle-adjustment Levenberg–Marquardt path.
+ *
+ * This is the drop-in boundary a Rust shim in apex-solver's reserved module
+ * `src/linearizer/gpu/mod.rs:1-5` (and a new `linalg::gpu`) would bind with
+ * `extern "C"`; INTEGRATION.md shows that shim. Every entry point cites the
+ * reference interface it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - plain pointers + sizes, `repr(C)`-compatible PODs, no callbacks, no C++ or
+ *     torch types; never throws across the boundary.
+ *   - every function returns an apex_status: 0 = ok, negative = error (mapped 1:1
+ *     on the reference's error enums, see below). apex_last_error() gives the text.
+ *   - a context is single-threaded (`&mut self` semantics of `LinearSolver`,
+ *     src/linalg/mod.rs:143-180); one context per GPU / rank.
+ *   - all arithmetic is FP64; indices are u32 (the reference uses usize).
+ *   - THERE IS NO CPU FALLBACK: without a CUDA device every compute entry point
+ *     returns APEX_ERR_NO_DEVICE.
+ *
+ * The same declarations (with the prefix `oracle_` instead of `apex_`) are
+ * implemented on the CPU by oracle/apex_oracle.cpp, the test oracle.
+ */
+#ifndef APEX_GPU_H
+#define APEX_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t apex_status;
+
+/* ---- status codes ------------------------------------------------------- */
+#define APEX_OK 0
+/* LinAlgError (src/linalg/mod.rs:77-101) */
+#define APEX_ERR_FACTORIZATION_FAILED (-1) /* LinAlgError::FactorizationFailed  */
+#define APEX_ERR_SINGULAR_MATRIX (-2)      /* LinAlgError::SingularMatrix       */
+#define APEX_ERR_INVALID_INPUT (-5)        /* LinAlgError::InvalidInput / LinearizerError::InvalidInput (src/linearizer/mod.rs:65-85) */
+#define APEX_ERR_INVALID_STATE (-6)        /* LinAlgError::InvalidState         */
+/* OptimizerError (src/optimizer/mod.rs:66-141) */
+#define APEX_ERR_LINEAR_SOLVE_FAILED (-10) /* OptimizerError::LinearSolveFailed */
+#define APEX_ERR_INVALID_PARAMETERS (-11)  /* OptimizerError::InvalidParameters */
+#define APEX_ERR_NUMERICAL_INSTABILITY (-12)
+#define APEX_ERR_EMPTY_PROBLEM (-13)       /* OptimizerError::EmptyProblem      */
+#define APEX_ERR_NO_RESIDUAL_BLOCKS (-14)  /* OptimizerError::NoResidualBlocks  */
+/* boundary-only */
+#define APEX_ERR_CUDA (-20)        /* CUDA runtime error                         */
+#define APEX_ERR_NCCL (-21)        /* NCCL error                                 */
+#define APEX_ERR_NO_DEVICE (-22)   /* no CUDA device / library built without one */
+#define APEX_ERR_UNSUPPORTED (-23) /* valid in the reference, not on this path   */
+
+/* ---- enums ---------------------------------------------------------------- */
+
+/* Camera model of the projection factor (crates/apex-camera-models/src/, one file per model).
+ * Intrinsic vector layouts follow the reference's `From<&Camera> for DVector`. */
+enum apex_camera_model {
+  APEX_CAM_BAL = 0,            /* BALPinholeCameraStrict [f,k1,k2]             bal_pinhole.rs:242 */
+  APEX_CAM_PINHOLE = 1,        /* PinholeCamera [fx,fy,cx,cy]                   pinhole.rs:202     */
+  APEX_CAM_KANNALA_BRANDT = 2, /* [fx,fy,cx,cy,k1,k2,k3,k4]                     kannala_brandt.rs:358 */
+  APEX_CAM_DOUBLE_SPHERE = 3,  /* [fx,fy,cx,cy,xi,alpha]                        double_sphere.rs:332 */
+  APEX_CAM_RADTAN = 4,         /* [fx,fy,cx,cy,k1,k2,p1,p2,k3]                  rad_tan.rs:333     */
+  APEX_CAM_UCM = 5,            /* [fx,fy,cx,cy,alpha]                           ucm.rs:300         */
+  APEX_CAM_EUCM = 6,           /* [fx,fy,cx,cy,alpha,beta]                      eucm.rs:320        */
+  APEX_CAM_FOV = 7,            /* [fx,fy,cx,cy,w]                               fov.rs:291         */
+  APEX_CAM_FTHETA = 8          /* [cx,cy,k1..k4]                                ftheta.rs:224      */
+};
+
+/* OptimizeParams<POSE,LANDMARK,INTRINSIC> (src/factors/mod.rs:83-101). Only the two
+ * modes that are live in bin/bundle_adjustment.rs are supported:
+ * BundleAdjustment = POSE|LANDMARK, SelfCalibration = POSE|LANDMARK|INTRINSIC. */
+#define APEX_OPT_POSE 1u
+#define APEX_OPT_LANDMARK 2u
+#define APEX_OPT_INTRINSIC 4u
+
+/* LossFunction implementations (src/core/loss_functions.rs). params[] meaning per id. */
+enum apex_loss {
+  APEX_LOSS_NONE = 0,          /* residual block without a loss (loss_func = None)             */
+  APEX_LOSS_L2 = 1,            /* L2Loss                        :174                            */
+  APEX_LOSS_L1 = 2,            /* L1Loss                        :236                            */
+  APEX_LOSS_HUBER = 3,         /* HuberLoss{scale=p0}           :353                            */
+  APEX_LOSS_CAUCHY = 4,        /* CauchyLoss{scale=p0}          :486                            */
+  APEX_LOSS_FAIR = 5,          /* FairLoss{scale=p0}            :585                            */
+  APEX_LOSS_GEMAN_MCCLURE = 6, /* GemanMcClureLoss{scale=p0}    :674                            */
+  APEX_LOSS_WELSCH = 7,        /* WelschLoss{scale=p0}          :759                            */
+  APEX_LOSS_TUKEY = 8,         /* TukeyBiweightLoss{scale=p0}   :848                            */
+  APEX_LOSS_ANDREWS = 9,       /* AndrewsWaveLoss{scale=p0}     :949                            */
+  APEX_LOSS_RAMSAY_EA = 10,    /* RamsayEaLoss{scale=p0}        :1037                           */
+  APEX_LOSS_TRIMMED_MEAN = 11, /* TrimmedMeanLoss{scale=p0}     :1132                           */
+  APEX_LOSS_LP_NORM = 12,      /* LpNormLoss{p=p0}              :1207                           */
+  APEX_LOSS_BARRON = 13,       /* BarronGeneralLoss{alpha=p0,scale=p1} :1316 (AdaptiveBarron delegates, :1569) */
+  APEX_LOSS_T_DISTRIBUTION = 14 /* TDistributionLoss{nu=p0}     :1445                           */
+};
+
+/* LinearSolverType::{ExplicitSchur, ImplicitSchur} as spelled in README.md:256-257;
+ * today's code spells them SparseSchurComplement + SchurVariant::{Sparse,Iterative}
+ * (src/linalg/sparse/explicit_schur.rs:58-65). */
+enum apex_schur_variant {
+  /* SchurVariant::Sparse: explicit S, direct Cholesky (explicit_schur.rs:539-634). */
+  APEX_SCHUR_EXPLICIT = 0,
+  /* Matrix-free PCG with block preconditioner = the math of IterativeSchurSolver
+   * (src/linalg/sparse/implicit_schur.rs:163-946), wired with the +J^T r gradient. */
+  APEX_SCHUR_IMPLICIT = 1,
+  /* SchurVariant::Iterative exactly as dispatched today: explicit S + scalar-Jacobi PCG
+   * (explicit_schur.rs:639-756, reached from :1224-1225). */
+  APEX_SCHUR_EXPLICIT_PCG = 2
+};
+
+/* SchurPreconditioner (explicit_schur.rs:67-78); used by APEX_SCHUR_IMPLICIT only. */
+enum apex_schur_preconditioner {
+  APEX_PRECOND_NONE = 0,
+  APEX_PRECOND_BLOCK_DIAGONAL = 1,
+  APEX_PRECOND_SCHUR_JACOBI = 2
+};
+
+/* OptimizationStatus (src/optimizer/mod.rs:189-216), same order. */
+enum apex_optimization_status {
+  APEX_STATUS_CONVERGED = 0,
+  APEX_STATUS_MAX_ITERATIONS_REACHED = 1,
+  APEX_STATUS_COST_TOLERANCE_REACHED = 2,
+  APEX_STATUS_PARAMETER_TOLERANCE_REACHED = 3,
+  APEX_STATUS_GRADIENT_TOLERANCE_REACHED = 4,
+  APEX_STATUS_NUMERICAL_FAILURE = 5,
+  APEX_STATUS_USER_TERMINATED = 6,
+  APEX_STATUS_TIMEOUT = 7,
+  APEX_STATUS_TRUST_REGION_RADIUS_TOO_SMALL = 8,
+  APEX_STATUS_MIN_COST_THRESHOLD_REACHED = 9,
+  APEX_STATUS_ILL_CONDITIONED_JACOBIAN = 10,
+  APEX_STATUS_INVALID_NUMERICAL_VALUES = 11,
+  APEX_STATUS_FAILED = 12
+};
+
+/* ---- PODs ------------------------------------------------------------------ */
+
+typedef struct apex_ctx apex_ctx; /* opaque */
+
+typedef struct apex_ctx_desc {
+  int32_t device;           /* CUDA device ordinal                                       */
+  int32_t rank;             /* 0..nranks-1                                               */
+  int32_t nranks;           /* 1 = single GPU                                            */
+  int32_t reserved;
+  const void* nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks, or NULL when nranks==1 */
+} apex_ctx_desc;
+
+/* The factor graph bin/bundle_adjustment.rs:212-441 builds (one ProjectionFactor with a single
+ * 2x1 observation per residual block, Problem::add_residual_block src/core/problem.rs:575-598),
+ * flattened to SoA. Host pointers, caller-owned, copied by apex_problem_upload. With nranks>1
+ * every rank passes the SAME full problem; the library keeps its own shard of points. */
+typedef struct apex_problem_desc {
+  int32_t camera_model;  /* enum apex_camera_model                                        */
+  uint32_t opt_flags;    /* APEX_OPT_*                                                    */
+  int32_t intr_dim;      /* K = CameraModel::INTRINSIC_DIM of camera_model                */
+  /* 1 if an "intr_XXXX" variable exists per camera even though no factor references it
+   * (bin/bundle_adjustment.rs:243-246 always inserts them): they then own K all-zero columns
+   * (diagonal = lambda) and enter the parameter norm. Ignored when APEX_OPT_INTRINSIC is set. */
+  int32_t intr_vars_present;
+  uint32_t ncam;
+  uint32_t npts;
+  uint64_t nobs;
+  const double* pose;       /* [ncam][7] = tx,ty,tz,qw,qx,qy,qz (se3.rs:200-222), world->camera */
+  const double* intr;       /* [ncam][K]                                                 */
+  const double* pt;         /* [npts][3]                                                 */
+  const uint32_t* obs_cam;  /* [nobs] camera index of each residual block, insertion order */
+  const uint32_t* obs_pt;   /* [nobs] landmark index                                     */
+  const double* obs_uv;     /* [nobs][2] measured pixel                                  */
+  int32_t loss_id;          /* enum apex_loss, uniform over blocks                       */
+  int32_t reserved0;
+  double loss_params[4];
+  /* Problem::fix_variable (src/core/problem.rs:609-616): bit d set = tangent DOF d is fixed
+   * (step zeroed at update time only, src/core/problem.rs:185-289). NULL = nothing fixed. */
+  const uint8_t* pose_fixed;  /* [ncam] bits 0..5                                        */
+  const uint16_t* intr_fixed; /* [ncam] bits 0..K-1                                      */
+  const uint8_t* pt_fixed;    /* [npts] bits 0..2                                        */
+} apex_problem_desc;
+
+/* LevenbergMarquardtConfig (src/optimizer/levenberg_marquardt.rs:213-317), field for field, plus the
+ * Schur solver's CG parameters (explicit_schur.rs:211-212). Dead fields of the reference
+ * (damping_increase_factor ... min_relative_decrease) are carried but unused. */
+typedef struct apex_lm_config {
+  int32_t schur_variant;        /* enum apex_schur_variant                                */
+  int32_t schur_preconditioner; /* enum apex_schur_preconditioner                         */
+  int32_t max_iterations;       /* default 50; for_bundle_adjustment(): 20 (:519-530)     */
+  int32_t cg_max_iterations;    /* 200                                                    */
+  double cost_tolerance;        /* 1e-6  */
+  double parameter_tolerance;   /* 1e-8  */
+  double gradient_tolerance;    /* 1e-10 */
+  double timeout_seconds;       /* <= 0: None */
+  double damping;               /* 1e-3  */
+  double damping_min;           /* 1e-12 */
+  double damping_max;           /* 1e12  */
+  double damping_increase_factor; /* dead */
+  double damping_decrease_factor; /* dead */
+  double damping_nu;            /* 2.0   */
+  double trust_region_radius;   /* 1e4 (only forwarded to check_convergence) */
+  double min_step_quality;      /* dead */
+  double good_step_quality;     /* dead */
+  double min_diagonal;          /* dead */
+  double max_diagonal;          /* dead */
+  double min_cost_threshold;    /* NaN: None */
+  double min_trust_region_radius; /* 1e-32 */
+  double max_condition_number;  /* dead; NaN: None */
+  double min_relative_decrease; /* dead */
+  double cg_tolerance;          /* 1e-6  */
+  int32_t use_jacobi_scaling;   /* must be 0 on this path (default false, :352)            */
+  int32_t compute_covariances;  /* must be 0 on this path                                  */
+} apex_lm_config;
+
+/* SolverResult + ConvergenceInfo (src/optimizer/mod.rs:163-172,250-273). */
+typedef struct apex_lm_result {
+  int32_t status;     /* enum apex_optimization_status                                    */
+  int32_t iterations; /* = iteration + 1 at termination (levenberg_marquardt.rs:1015)     */
+  double initial_cost;
+  double final_cost;
+  double elapsed_seconds;
+  double final_gradient_norm;
+  double final_parameter_update_norm;
+  int32_t cost_evaluations;
+  int32_t jacobian_evaluations;
+  int32_t successful_steps;
+  int32_t unsuccessful_steps;
+  double final_damping;     /* config.damping is mutated by a solve (:706-714)             */
+  double final_damping_nu;
+  int64_t linear_iterations; /* total PCG iterations (0 for the direct variant)            */
+} apex_lm_result;
+
+/* IterationStats (src/optimizer/mod.rs:375-398) + linear-solver iterations. */
+typedef struct apex_iter_trace {
+  int32_t iteration;
+  int32_t accepted;
+  int32_t ls_iter; /* PCG iterations of this LM iteration                                  */
+  int32_t reserved;
+  double cost;          /* state.current_cost after accept/reject                          */
+  double cost_change;
+  double gradient_norm;
+  double step_norm;
+  double tr_ratio;      /* rho                                                             */
+  double tr_radius;     /* damping after update_damping                                    */
+  double new_cost;      /* cost at the trial point                                         */
+  double predicted_reduction;
+  double parameter_norm;
+  double iter_time_ms;
+} apex_iter_trace;
+
+/* Sizes of the current problem as seen by the solver. */
+typedef struct apex_dims {
+  uint32_t ncam, npts;
+  uint64_t nobs;
+  int32_t intr_dim;    /* K                                                               */
+  int32_t dc;          /* camera-side DOF per camera inside the reduced system (6 or 6+K)  */
+  uint64_t cam_dof;    /* rows of S in the reference layout (includes unreferenced intr columns) */
+  uint64_t lm_dof;     /* 3*npts                                                          */
+  uint32_t npts_local; /* points owned by this rank                                        */
+  uint32_t reserved;
+  uint64_t nobs_local;
+} apex_dims;
+
+/* ---- entry points ---------------------------------------------------------- */
+
+/* Library/ABI version (major*100+minor) and whether a CUDA device is usable. */
+int32_t apex_abi_version(void);
+int32_t apex_device_count(void);
+
+/* Fill `cfg` with LevenbergMarquardtConfig::default() (levenberg_marquardt.rs:319-359) or the
+ * for_bundle_adjustment() preset (:519-530). */
+void apex_lm_config_default(apex_lm_config* cfg);
+void apex_lm_config_for_bundle_adjustment(apex_lm_config* cfg);
+
+/* ncclGetUniqueId for the host to broadcast (128 bytes). */
+apex_status apex_nccl_unique_id(void* out128);
+
+apex_status apex_ctx_create(const apex_ctx_desc* desc, apex_ctx** out);
+void apex_ctx_destroy(apex_ctx* ctx);
+const char* apex_last_error(const apex_ctx* ctx);
+
+/* Replaces Problem construction + initialize_optimization_state (src/optimizer/mod.rs:522-563):
+ * copies the SoA problem to HBM, builds the point-major and camera-major observation orders,
+ * normalises pose quaternions as SE3::from(DVector) does (se3.rs:200-206). */
+apex_status apex_problem_upload(apex_ctx* ctx, const apex_problem_desc* desc);
+apex_status apex_get_dims(const apex_ctx* ctx, apex_dims* out);
+/* Overwrite / read back the current variable values (host arrays, full problem layout). */
+apex_status apex_params_upload(apex_ctx* ctx, const double* pose, const double* intr, const double* pt);
+apex_status apex_params_download(apex_ctx* ctx, double* pose, double* intr, double* pt);
+
+/* AssemblyBackend::assemble (src/linearizer/mod.rs:191-227 -> cpu/sparse.rs:119-184) followed by the
+ * block J^T J / J^T r accumulation that solve_augmented_equation starts with
+ * (explicit_schur.rs:1146-1166): residuals, loss-corrected Jacobian blocks, H_cc/H_pp blocks, g.
+ * Results stay on the device. `lambda` is the LM damping used for the point-block inverses. */
+apex_status apex_linearize(apex_ctx* ctx, double lambda);
+/* compute_residual_sparse + compute_cost (src/core/problem.rs:864-899, src/optimizer/mod.rs:358-361):
+ * 0.5*||r~||^2 at the current values. */
+apex_status apex_cost(apex_ctx* ctx, double* cost);
+
+/* Debug / parity read-backs of the last apex_linearize, in the caller's observation order.
+ * Any pointer may be NULL. r[nobs][2]; jc[nobs][2][dc] (columns: pose 6 then intrinsics K);
+ * jp[nobs][2][3]. Single-rank contexts only. */
+apex_status apex_get_linearization(apex_ctx* ctx, double* r, double* jc, double* jp);
+/* hcc[ncam][dc][dc] (undamped), gc[ncam][dc], hpp[npts][9] (undamped), gp[npts][3],
+ * hpp_inv[npts][9] (of the damped, guarded block: explicit_schur.rs:365-442 / implicit_schur.rs:685-778). */
+apex_status apex_get_blocks(apex_ctx* ctx, double* hcc, double* gc, double* hpp, double* gp, double* hpp_inv);
+
+/* apply_schur_operator_fast (implicit_schur.rs:163-251): y = (H_cc + lambda I - H_cp H_pp^-1 H_cp^T) x for
+ * the last linearization. x, y are HOST vectors of ncam*dc doubles in camera-major order
+ * [cam0: pose6, intrK | cam1: ...]. For parity tests. */
+apex_status apex_schur_matvec(apex_ctx* ctx, const double* x, double* y);
+/* Same operator on device-resident vectors, `reps` back-to-back launches, for roofline timing;
+ * returns the mean CUDA-event duration of one application in milliseconds. */
+apex_status apex_schur_matvec_bench(apex_ctx* ctx, int32_t reps, int32_t flush_l2, double* ms_per_call);
+
+/* LinearSolver::solve_augmented_equation (src/linalg/mod.rs:143-180; explicit_schur.rs:1129-1234 /
+ * implicit_schur.rs:1035-1085) on the last linearization. Outputs (host, may be NULL):
+ * step_cam[ncam][dc], step_intr_unref[ncam][K] is implicit zero, step_pt[npts][3];
+ * grad_norm = ||J^T r||_2 (get_gradient, +J^T r convention); pcg_iters. */
+apex_status apex_solve_augmented(apex_ctx* ctx, int32_t schur_variant, int32_t preconditioner,
+                                 int32_t cg_max_iterations, double cg_tolerance, double lambda,
+                                 double* step_cam, double* step_pt, double* grad_norm, int32_t* pcg_iters);
+
+/* LevenbergMarquardt::optimize (levenberg_marquardt.rs:1034-1083 -> optimize_with_mode :823-1028):
+ * the whole loop, device resident. `trace` (may be NULL) receives up to trace_cap rows. */
+apex_status apex_lm_solve(apex_ctx* ctx, const apex_lm_config* cfg, apex_lm_result* result,
+                          apex_iter_trace* trace, int32_t trace_cap);
+
+/* Number of kernel launches issued by this context since creation (bench bookkeeping). */
+int64_t apex_kernel_launches(const apex_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APEX_GPU_H */

@@ -1,0 +1,1764 @@
+// apex_oracle.cpp — TEST ORACLE. CPU restatement (C++17 + OpenMP) of apex-solver's bundle-adjustment
+// Levenberg–Marquardt path. This file is test infrastructure, NOT product code: only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+//
+// PARITY PINNING: the unit-level functions below are pinned against the reference's own
+// known-answer tests (tests/test_oracle_kat.py ports them). End-to-end LM numbers
+// (per-iteration cost, iteration count, status) are pinned by NO reference test and no shipped
+// fixture, and the reference (Rust; faer 0.24 / nalgebra 0.33 un-vendored, no toolchain here) cannot be
+// built in this container => for the LM-level targets: "parity unpinned".
+//
+// Every function cites the reference file:line it follows (paths relative to the reference repo).
+// nalgebra / faer semantics (sources not under /root/reference) are restated from the crates'
+// documented behaviour: UnitQuaternion*v, to_rotation_matrix, from_scaled_axis, Matrix3::try_inverse
+// (closed form, None iff det==0), DMatrix::try_inverse (closed form n<=3, LU partial pivoting above),
+// symmetric_eigenvalues (only min/max are used), faer sparse J^T J / norm_l2 (summation order
+// unspecified => tolerance-based parity, never bitwise).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "../include/apex_gpu.h"
+
+namespace {
+
+constexpr double F64_EPS = 2.220446049250313e-16;
+constexpr double F64_MIN = -1.7976931348623157e308;  // Rust f64::MIN (most negative finite)
+
+// ------------------------------------------------------------------------------------------------
+// Quaternion / SO3 / SE3  (crates/apex-manifolds/src/{so3,se3}.rs + nalgebra semantics)
+// ------------------------------------------------------------------------------------------------
+struct Quat { double w, i, j, k; };
+struct V3 { double x, y, z; };
+
+inline V3 cross(const V3& a, const V3& b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+// Quaternion::normalize then UnitQuaternion::from_quaternion (= Unit::new_normalize): se3.rs:107-113
+// normalises twice when a pose is built from a DVector (se3.rs:200-206).
+inline Quat quat_normalize(Quat q) {
+  double n = std::sqrt(q.w * q.w + q.i * q.i + q.j * q.j + q.k * q.k);
+  return {q.w / n, q.i / n, q.j / n, q.k / n};
+}
+
+// nalgebra UnitQuaternion * Vector3: t = 2 (qv x v); v' = t*w + qv x t + v.   (so3.rs:359-378)
+inline V3 quat_rotate(const Quat& q, const V3& v) {
+  V3 qv{q.i, q.j, q.k};
+  V3 t = cross(qv, v);
+  t = {t.x * 2.0, t.y * 2.0, t.z * 2.0};
+  V3 c = cross(qv, t);
+  return {t.x * q.w + c.x + v.x, t.y * q.w + c.y + v.y, t.z * q.w + c.z + v.z};
+}
+
+// UnitQuaternion::to_rotation_matrix (so3.rs:193-195). Row-major R[9].
+inline void quat_to_matrix(const Quat& q, double R[9]) {
+  double i = q.i, j = q.j, k = q.k, w = q.w;
+  double ww = w * w, ii = i * i, jj = j * j, kk = k * k;
+  double ij = i * j * 2.0, wk = w * k * 2.0, wj = w * j * 2.0, ik = i * k * 2.0, jk = j * k * 2.0, wi = w * i * 2.0;
+  R[0] = ww + ii - jj - kk; R[1] = ij - wk;           R[2] = wj + ik;
+  R[3] = wk + ij;           R[4] = ww - ii + jj - kk; R[5] = jk - wi;
+  R[6] = ik - wj;           R[7] = wi + jk;           R[8] = ww - ii - jj + kk;
+}
+
+// Hamilton product; nalgebra does not renormalise the product of two unit quaternions (so3.rs:270-290).
+inline Quat quat_mul(const Quat& a, const Quat& b) {
+  return {a.w * b.w - a.i * b.i - a.j * b.j - a.k * b.k,
+          a.w * b.i + a.i * b.w + a.j * b.k - a.k * b.j,
+          a.w * b.j - a.i * b.k + a.j * b.w + a.k * b.i,
+          a.w * b.k + a.i * b.j - a.j * b.i + a.k * b.w};
+}
+
+constexpr double SMALL_ANGLE_THRESHOLD = 1e-10;  // crates/apex-manifolds/src/lib.rs:61
+
+// SO3Tangent::exp (so3.rs:558-577).
+inline Quat so3_exp(const V3& th) {
+  double t2 = th.x * th.x + th.y * th.y + th.z * th.z;
+  if (t2 > SMALL_ANGLE_THRESHOLD) {
+    // UnitQuaternion::from_scaled_axis: Quaternion::from_imag(theta/2).exp()
+    V3 h{th.x / 2.0, th.y / 2.0, th.z / 2.0};
+    double nn = h.x * h.x + h.y * h.y + h.z * h.z;
+    double n = std::sqrt(nn);
+    double s = std::sin(n) / n;  // w_exp = exp(0) = 1
+    return {std::cos(n), h.x * s, h.y * s, h.z * s};
+  }
+  return quat_normalize({1.0, th.x / 2.0, th.y / 2.0, th.z / 2.0});
+}
+
+// SO3Tangent::left_jacobian (so3.rs:595-611), row-major 3x3.
+inline void so3_left_jacobian(const V3& th, double J[9]) {
+  double angle = th.x * th.x + th.y * th.y + th.z * th.z;  // squared norm
+  double K[9] = {0, -th.z, th.y, th.z, 0, -th.x, -th.y, th.x, 0};
+  for (int a = 0; a < 9; ++a) J[a] = 0.0;
+  J[0] = J[4] = J[8] = 1.0;
+  if (angle <= SMALL_ANGLE_THRESHOLD) {
+    for (int a = 0; a < 9; ++a) J[a] += 0.5 * K[a];
+    return;
+  }
+  double theta = std::sqrt(angle), s = std::sin(theta), c = std::cos(theta);
+  double a1 = (1.0 - c) / angle, a2 = (theta - s) / (angle * theta);
+  double K2[9];
+  for (int r = 0; r < 3; ++r)
+    for (int cc = 0; cc < 3; ++cc) {
+      double v = 0;
+      for (int m = 0; m < 3; ++m) v += K[r * 3 + m] * K[m * 3 + cc];
+      K2[r * 3 + cc] = v;
+    }
+  for (int a = 0; a < 9; ++a) J[a] += a1 * K[a] + a2 * K2[a];
+}
+
+struct Pose { V3 t; Quat q; };
+
+// SE3::from(DVector) (se3.rs:200-206)
+inline Pose pose_from7(const double* d) {
+  Pose p;
+  p.t = {d[0], d[1], d[2]};
+  p.q = quat_normalize(quat_normalize({d[3], d[4], d[5], d[6]}));
+  return p;
+}
+inline void pose_to7(const Pose& p, double* d) {
+  d[0] = p.t.x; d[1] = p.t.y; d[2] = p.t.z; d[3] = p.q.w; d[4] = p.q.i; d[5] = p.q.j; d[6] = p.q.k;
+}
+// SE3::act (se3.rs:322-345): R p + t
+inline V3 pose_act(const Pose& p, const V3& v) {
+  V3 r = quat_rotate(p.q, v);
+  return {r.x + p.t.x, r.y + p.t.y, r.z + p.t.z};
+}
+// right_plus (lib.rs:269-282) = compose(self, exp(tau)) ; SE3Tangent::exp (se3.rs:569-586);
+// compose (se3.rs:272-297). tau = [rho, theta].
+inline Pose pose_plus(const Pose& p, const double* tau) {
+  V3 rho{tau[0], tau[1], tau[2]}, th{tau[3], tau[4], tau[5]};
+  Quat qe = so3_exp(th);
+  double Jl[9];
+  so3_left_jacobian(th, Jl);
+  V3 te{Jl[0] * rho.x + Jl[1] * rho.y + Jl[2] * rho.z, Jl[3] * rho.x + Jl[4] * rho.y + Jl[5] * rho.z,
+        Jl[6] * rho.x + Jl[7] * rho.y + Jl[8] * rho.z};
+  Pose out;
+  out.q = quat_mul(p.q, qe);
+  V3 rt = quat_rotate(p.q, te);
+  out.t = {rt.x + p.t.x, rt.y + p.t.y, rt.z + p.t.z};
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Camera models  (crates/apex-camera-models/src/*.rs)
+// ------------------------------------------------------------------------------------------------
+constexpr double GEOMETRIC_PRECISION = 1e-6;  // lib.rs:56
+constexpr double MIN_DEPTH = 1e-6;            // lib.rs:80
+
+int model_intr_dim(int model) {
+  switch (model) {
+    case APEX_CAM_BAL: return 3;
+    case APEX_CAM_PINHOLE: return 4;
+    case APEX_CAM_KANNALA_BRANDT: return 8;
+    case APEX_CAM_DOUBLE_SPHERE: return 6;
+    default: return -1;
+  }
+}
+
+// project(): returns false on Err (the factor then zeroes residual and Jacobian rows,
+// src/factors/projection_factor.rs:227-239).
+bool cam_project(int model, const double* in, const V3& p, double uv[2]) {
+  switch (model) {
+    case APEX_CAM_BAL: {  // bal_pinhole.rs:273-296, validity :154-156
+      if (!(p.z < -MIN_DEPTH)) return false;
+      double inv_neg_z = -1.0 / p.z;
+      double xn = p.x * inv_neg_z, yn = p.y * inv_neg_z;
+      double r2 = xn * xn + yn * yn, r4 = r2 * r2;
+      double d = 1.0 + in[1] * r2 + in[2] * r4;
+      uv[0] = in[0] * (xn * d);
+      uv[1] = in[0] * (yn * d);
+      return true;
+    }
+    case APEX_CAM_PINHOLE: {  // pinhole.rs:226-238, validity :105-107
+      if (!(p.z >= 1e-6)) return false;
+      double inv_z = 1.0 / p.z;
+      uv[0] = in[0] * p.x * inv_z + in[2];
+      uv[1] = in[1] * p.y * inv_z + in[3];
+      return true;
+    }
+    case APEX_CAM_KANNALA_BRANDT: {  // kannala_brandt.rs:385-450, validity :103-105
+      if (!(p.z > F64_EPS)) return false;
+      double r2 = p.x * p.x + p.y * p.y, r = std::sqrt(r2);
+      double th = std::atan2(r, p.z);
+      double t2 = th * th, t3 = t2 * th, t5 = t3 * t2, t7 = t5 * t2, t9 = t7 * t2;
+      double thd = th + in[4] * t3 + in[5] * t5 + in[6] * t7 + in[7] * t9;
+      if (r < GEOMETRIC_PRECISION) {
+        double inv_z = 1.0 / p.z;
+        uv[0] = in[0] * p.x * inv_z + in[2];
+        uv[1] = in[1] * p.y * inv_z + in[3];
+        return true;
+      }
+      double inv_r = 1.0 / r;
+      uv[0] = in[0] * thd * p.x * inv_r + in[2];
+      uv[1] = in[1] * thd * p.y * inv_r + in[3];
+      return true;
+    }
+    case APEX_CAM_DOUBLE_SPHERE: {  // double_sphere.rs:361-392, validity :118-127
+      double xi = in[4], alpha = in[5];
+      double r2 = p.x * p.x + p.y * p.y;
+      double d1 = std::sqrt(r2 + p.z * p.z);
+      double w1 = alpha > 0.5 ? (1.0 - alpha) / alpha : alpha / (1.0 - alpha);
+      double w2 = (w1 + xi) / std::sqrt(2.0 * w1 * xi + xi * xi + 1.0);
+      if (!(p.z > -w2 * d1)) return false;
+      double xdz = xi * d1 + p.z;
+      double d2 = std::sqrt(r2 + xdz * xdz);
+      double denom = alpha * d2 + (1.0 - alpha) * xdz;
+      if (denom < GEOMETRIC_PRECISION) return false;
+      uv[0] = in[0] * p.x / denom + in[2];
+      uv[1] = in[1] * p.y / denom + in[3];
+      return true;
+    }
+  }
+  return false;
+}
+
+// jacobian_point(): J[6] row-major 2x3 = d(u,v)/d(p_cam).
+void cam_jacobian_point(int model, const double* in, const V3& p, double J[6]) {
+  switch (model) {
+    case APEX_CAM_BAL: {  // bal_pinhole.rs:400-435
+      double f = in[0], k1 = in[1], k2 = in[2];
+      double inv_neg_z = -1.0 / p.z;
+      double xn = p.x * inv_neg_z, yn = p.y * inv_neg_z;
+      double r2 = xn * xn + yn * yn, r4 = r2 * r2;
+      double dist = 1.0 + k1 * r2 + k2 * r4;
+      double dd = k1 + 2.0 * k2 * r2;
+      double dxn_dz = xn * inv_neg_z, dyn_dz = yn * inv_neg_z;
+      double dxd_dxn = dist + xn * dd * 2.0 * xn;
+      double dxd_dyn = xn * dd * 2.0 * yn;
+      double dyd_dxn = yn * dd * 2.0 * xn;
+      double dyd_dyn = dist + yn * dd * 2.0 * yn;
+      J[0] = f * (dxd_dxn * inv_neg_z);
+      J[1] = f * (dxd_dyn * inv_neg_z);
+      J[2] = f * (dxd_dxn * dxn_dz + dxd_dyn * dyn_dz);
+      J[3] = f * (dyd_dxn * inv_neg_z);
+      J[4] = f * (dyd_dyn * inv_neg_z);
+      J[5] = f * (dyd_dxn * dxn_dz + dyd_dyn * dyn_dz);
+      return;
+    }
+    case APEX_CAM_PINHOLE: {  // pinhole.rs:315-330
+      double inv_z = 1.0 / p.z, xn = p.x * inv_z, yn = p.y * inv_z;
+      J[0] = in[0] * inv_z; J[1] = 0.0; J[2] = -in[0] * xn * inv_z;
+      J[3] = 0.0; J[4] = in[1] * inv_z; J[5] = -in[1] * yn * inv_z;
+      return;
+    }
+    case APEX_CAM_KANNALA_BRANDT: {  // kannala_brandt.rs:609-675
+      double fx = in[0], fy = in[1], k1 = in[4], k2 = in[5], k3 = in[6], k4 = in[7];
+      double x = p.x, y = p.y, z = p.z;
+      double r = std::sqrt(x * x + y * y);
+      double th = std::atan2(r, z);
+      double t2 = th * th, t3 = t2 * th, t5 = t3 * t2, t7 = t5 * t2, t9 = t7 * t2;
+      double thd = th + k1 * t3 + k2 * t5 + k3 * t7 + k4 * t9;
+      double dthd = 1.0 + 3.0 * k1 * t2 + 5.0 * k2 * t2 * t2 + 7.0 * k3 * t2 * t2 * t2 + 9.0 * k4 * t2 * t2 * t2 * t2;
+      if (r < GEOMETRIC_PRECISION) {
+        J[0] = fx * dthd / z; J[1] = 0; J[2] = 0; J[3] = 0; J[4] = fy * dthd / z; J[5] = 0;
+        return;
+      }
+      double inv_r = 1.0 / r, r2 = r * r, rz2 = r2 + z * z;
+      double dth_dx = z * x / (r * rz2), dth_dy = z * y / (r * rz2), dth_dz = -r / rz2;
+      double inv_r2 = inv_r * inv_r;
+      J[0] = fx * (dthd * dth_dx * x * inv_r + thd * (inv_r - x * x * inv_r2 * inv_r));
+      J[1] = fx * (dthd * dth_dy * x * inv_r - thd * x * y * inv_r2 * inv_r);
+      J[2] = fx * dthd * dth_dz * x * inv_r;
+      J[3] = fy * (dthd * dth_dx * y * inv_r - thd * x * y * inv_r2 * inv_r);
+      J[4] = fy * (dthd * dth_dy * y * inv_r + thd * (inv_r - y * y * inv_r2 * inv_r));
+      J[5] = fy * dthd * dth_dz * y * inv_r;
+      return;
+    }
+    case APEX_CAM_DOUBLE_SPHERE: {  // double_sphere.rs:532-583
+      double fx = in[0], fy = in[1], xi = in[4], alpha = in[5];
+      double x = p.x, y = p.y, z = p.z;
+      double r2 = x * x + y * y;
+      double d1 = std::sqrt(r2 + z * z);
+      double xdz = xi * d1 + z;
+      double d2 = std::sqrt(r2 + xdz * xdz);
+      double denom = alpha * d2 + (1.0 - alpha) * xdz;
+      double inv_d1 = 1.0 / d1, inv_d2 = 1.0 / d2;
+      double dd1_dx = x * inv_d1, dd1_dy = y * inv_d1, dd1_dz = z * inv_d1;
+      double dx_dx = xi * dd1_dx, dx_dy = xi * dd1_dy, dx_dz = xi * dd1_dz + 1.0;
+      double dd2_dx = (x + xdz * dx_dx) * inv_d2, dd2_dy = (y + xdz * dx_dy) * inv_d2, dd2_dz = (xdz * dx_dz) * inv_d2;
+      double dn_dx = alpha * dd2_dx + (1.0 - alpha) * dx_dx;
+      double dn_dy = alpha * dd2_dy + (1.0 - alpha) * dx_dy;
+      double dn_dz = alpha * dd2_dz + (1.0 - alpha) * dx_dz;
+      double denom2 = denom * denom;
+      J[0] = fx * (denom - x * dn_dx) / denom2;
+      J[1] = fx * (-x * dn_dy) / denom2;
+      J[2] = fx * (-x * dn_dz) / denom2;
+      J[3] = fy * (-y * dn_dx) / denom2;
+      J[4] = fy * (denom - y * dn_dy) / denom2;
+      J[5] = fy * (-y * dn_dz) / denom2;
+      return;
+    }
+  }
+}
+
+// jacobian_intrinsics(): J[2*K] row-major 2xK.
+void cam_jacobian_intrinsics(int model, const double* in, const V3& p, double* J) {
+  switch (model) {
+    case APEX_CAM_BAL: {  // bal_pinhole.rs:649-672
+      double f = in[0], k1 = in[1], k2 = in[2];
+      double inv_neg_z = -1.0 / p.z;
+      double xn = p.x * inv_neg_z, yn = p.y * inv_neg_z;
+      double r2 = xn * xn + yn * yn, r4 = r2 * r2;
+      double dist = 1.0 + k1 * r2 + k2 * r4;
+      J[0] = xn * dist; J[1] = f * xn * r2; J[2] = f * xn * r4;
+      J[3] = yn * dist; J[4] = f * yn * r2; J[5] = f * yn * r4;
+      return;
+    }
+    case APEX_CAM_PINHOLE: {  // pinhole.rs:385-393
+      double inv_z = 1.0 / p.z;
+      J[0] = p.x * inv_z; J[1] = 0; J[2] = 1; J[3] = 0;
+      J[4] = 0; J[5] = p.y * inv_z; J[6] = 0; J[7] = 1;
+      return;
+    }
+    case APEX_CAM_KANNALA_BRANDT: {  // kannala_brandt.rs:767-836
+      double fx = in[0], fy = in[1], k1 = in[4], k2 = in[5], k3 = in[6], k4 = in[7];
+      double x = p.x, y = p.y, z = p.z;
+      double r = std::sqrt(x * x + y * y);
+      double th = std::atan2(r, z);
+      double t2 = th * th, t3 = t2 * th, t5 = t3 * t2, t7 = t5 * t2, t9 = t7 * t2;
+      double thd = th + k1 * t3 + k2 * t5 + k3 * t7 + k4 * t9;
+      if (r < GEOMETRIC_PRECISION) {
+        for (int a = 0; a < 16; ++a) J[a] = 0.0;
+        return;
+      }
+      double inv_r = 1.0 / r;
+      J[0] = x * thd * inv_r; J[1] = 0; J[2] = 1; J[3] = 0;
+      J[4] = fx * t3 * x * inv_r; J[5] = fx * t5 * x * inv_r; J[6] = fx * t7 * x * inv_r; J[7] = fx * t9 * x * inv_r;
+      J[8] = 0; J[9] = y * thd * inv_r; J[10] = 0; J[11] = 1;
+      J[12] = fy * t3 * y * inv_r; J[13] = fy * t5 * y * inv_r; J[14] = fy * t7 * y * inv_r; J[15] = fy * t9 * y * inv_r;
+      return;
+    }
+    case APEX_CAM_DOUBLE_SPHERE: {  // double_sphere.rs:691-731
+      double fx = in[0], fy = in[1], xi = in[4], alpha = in[5];
+      double x = p.x, y = p.y, z = p.z;
+      double r2 = x * x + y * y;
+      double d1 = std::sqrt(r2 + z * z);
+      double xdz = xi * d1 + z;
+      double d2 = std::sqrt(r2 + xdz * xdz);
+      double denom = alpha * d2 + (1.0 - alpha) * xdz;
+      double inv_denom = 1.0 / denom, inv_d2 = 1.0 / d2;
+      double dd2_dxi = (xdz * d1) * inv_d2;
+      double dn_dxi = alpha * dd2_dxi + (1.0 - alpha) * d1;
+      double dn_dalpha = d2 - xdz;
+      double inv_denom2 = inv_denom * inv_denom;
+      J[0] = x * inv_denom; J[1] = 0; J[2] = 1; J[3] = 0;
+      J[4] = -fx * x * dn_dxi * inv_denom2; J[5] = -fx * x * dn_dalpha * inv_denom2;
+      J[6] = 0; J[7] = y * inv_denom; J[8] = 0; J[9] = 1;
+      J[10] = -fy * y * dn_dxi * inv_denom2; J[11] = -fy * y * dn_dalpha * inv_denom2;
+      return;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Loss functions (src/core/loss_functions.rs) and Corrector (src/core/corrector.rs)
+// ------------------------------------------------------------------------------------------------
+void loss_evaluate(int id, const double* prm, double s, double rho[3]) {
+  switch (id) {
+    case APEX_LOSS_L2:  // :174-179
+      rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; return;
+    case APEX_LOSS_L1: {  // :236-250
+      if (s < F64_EPS) { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; return; }
+      double q = std::sqrt(s);
+      rho[0] = 2.0 * q; rho[1] = 1.0 / q; rho[2] = -1.0 / (2.0 * s * q); return;
+    }
+    case APEX_LOSS_HUBER: {  // :353-381
+      double scale = prm[0], scale2 = scale * scale;
+      if (s > scale2) {
+        double r = std::sqrt(s);
+        double rho1 = std::max(scale / r, F64_MIN);
+        rho[0] = 2.0 * scale * r - scale2; rho[1] = rho1; rho[2] = -rho1 / (2.0 * s);
+      } else { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; }
+      return;
+    }
+    case APEX_LOSS_CAUCHY: {  // :486-508
+      double scale2 = prm[0] * prm[0], c = 1.0 / scale2;
+      double sum = 1.0 + s * c, inv = 1.0 / sum;
+      rho[0] = scale2 * std::log(sum) / 2.0; rho[1] = std::max(inv, F64_MIN); rho[2] = -c * (inv * inv);
+      return;
+    }
+    case APEX_LOSS_FAIR: {  // :585-607
+      if (s < F64_EPS) { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; return; }
+      double sc = prm[0];
+      double x = std::sqrt(s), ax = std::fabs(x), cpx = sc + ax;
+      rho[0] = sc * sc * (ax / sc - std::log(1.0 + ax / sc));
+      rho[1] = 0.5 / cpx;
+      rho[2] = -1.0 / (4.0 * s * cpx * cpx);
+      return;
+    }
+    case APEX_LOSS_GEMAN_MCCLURE: {  // :674-687
+      double c = 1.0 / (prm[0] * prm[0]);
+      double denom = 1.0 + s * c, inv = 1.0 / denom, inv2 = inv * inv;
+      rho[0] = s * inv; rho[1] = inv2; rho[2] = -2.0 * c * inv2 * inv; return;
+    }
+    case APEX_LOSS_WELSCH: {  // :759-770
+      double scale2 = prm[0] * prm[0], inv_scale2 = 1.0 / scale2;
+      double e = std::exp(-s * inv_scale2);
+      rho[0] = (scale2 / 2.0) * (1.0 - e); rho[1] = 0.5 * e; rho[2] = -0.5 * inv_scale2 * e; return;
+    }
+    case APEX_LOSS_TUKEY: {  // :848-869
+      double sc = prm[0], sc2 = sc * sc;
+      double x = std::sqrt(s);
+      if (x > sc) { rho[0] = sc2 / 6.0; rho[1] = 0.0; rho[2] = 0.0; return; }
+      double ratio = x / sc, ratio2 = ratio * ratio, om = 1.0 - ratio2, om2 = om * om;
+      rho[0] = (sc2 / 6.0) * (1.0 - om * om2); rho[1] = 0.5 * om2; rho[2] = -(ratio / sc2) * om; return;
+    }
+    case APEX_LOSS_ANDREWS: {  // :949-969
+      double sc = prm[0], sc2 = sc * sc, thr = 3.14159265358979323846 * sc;
+      double x = std::sqrt(s);
+      if (x > thr) { rho[0] = 2.0 * sc2; rho[1] = 0.0; rho[2] = 0.0; return; }
+      double arg = x / sc, sv = std::sin(arg), cv = std::cos(arg);
+      rho[0] = sc2 * (1.0 - cv); rho[1] = 0.5 * sv; rho[2] = (0.25 / sc) * cv / std::max(x, F64_EPS); return;
+    }
+    case APEX_LOSS_RAMSAY_EA: {  // :1037-1055
+      double sc = prm[0], inv_sc2 = 1.0 / (sc * sc);
+      double x = std::sqrt(s), ax = sc * x, e = std::exp(-ax);
+      rho[0] = inv_sc2 * (1.0 - e * (1.0 + ax)); rho[1] = 0.5 * e; rho[2] = -(sc / (4.0 * std::max(x, F64_EPS))) * e; return;
+    }
+    case APEX_LOSS_TRIMMED_MEAN: {  // :1132-1141
+      double sc2 = prm[0] * prm[0];
+      if (s <= sc2) { rho[0] = s / 2.0; rho[1] = 0.5; rho[2] = 0.0; }
+      else { rho[0] = sc2 / 2.0; rho[1] = 0.0; rho[2] = 0.0; }
+      return;
+    }
+    case APEX_LOSS_LP_NORM: {  // :1207-1224
+      if (s < F64_EPS) { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; return; }
+      double e0 = prm[0] / 2.0, e1 = e0 - 1.0, e2 = e1 - 1.0;
+      rho[0] = std::pow(s, e0); rho[1] = e0 * std::pow(s, e1); rho[2] = e0 * e1 * std::pow(s, e2); return;
+    }
+    case APEX_LOSS_BARRON: {  // :1316-1355
+      double alpha = prm[0], sc = prm[1], sc2 = sc * sc;
+      if (std::fabs(alpha) < 1e-6) {
+        double denom = 1.0 + s / sc2, inv = 1.0 / denom;
+        rho[0] = (sc2 / 2.0) * std::log(denom); rho[1] = std::max(inv, F64_MIN); rho[2] = -inv * inv / sc2; return;
+      }
+      if (std::fabs(alpha - 2.0) < 1e-6) { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; return; }
+      double x = std::sqrt(s), nz = x / sc, nz2 = nz * nz;
+      double inner = std::fabs(alpha) / 2.0 * nz2 + 1.0;
+      double power = std::pow(inner, alpha / 2.0);
+      rho[0] = (std::fabs(alpha) / sc2) * (power - 1.0);
+      rho[1] = 0.5 * std::pow(inner, alpha / 2.0 - 1.0);
+      rho[2] = (alpha - 2.0) / (4.0 * sc2) * std::pow(inner, alpha / 2.0 - 2.0);
+      return;
+    }
+    case APEX_LOSS_T_DISTRIBUTION: {  // :1445-1461
+      double nu = prm[0], h = (nu + 1.0) / 2.0;
+      double inner = 1.0 + s / nu, denom = nu + s;
+      rho[0] = h * std::log(inner); rho[1] = h / denom; rho[2] = -h / (denom * denom); return;
+    }
+  }
+  rho[0] = s; rho[1] = 1.0; rho[2] = 0.0;
+}
+
+struct Corrector { double sqrt_rho1, residual_scaling, alpha_sq_norm; };
+// Corrector::new (corrector.rs:143-181)
+Corrector corrector_new(int loss_id, const double* prm, double sq_norm) {
+  double rho[3];
+  loss_evaluate(loss_id, prm, sq_norm, rho);
+  double sqrt_rho1 = std::sqrt(rho[1]);
+  if (sq_norm == 0.0 || rho[2] <= 0.0) return {sqrt_rho1, sqrt_rho1, 0.0};
+  double d = std::max(1.0 + 2.0 * sq_norm * rho[2] / rho[1], 0.0);
+  double alpha = 1.0 - std::sqrt(d);
+  return {sqrt_rho1, sqrt_rho1 / (1.0 - alpha), alpha / sq_norm};
+}
+
+// ------------------------------------------------------------------------------------------------
+// ProjectionFactor::linearize + linearize_block
+// ------------------------------------------------------------------------------------------------
+constexpr int MAXK = 9;
+struct BlockLin {
+  double r[2];
+  double jpose[12];     // 2x6
+  double jpt[6];        // 2x3
+  double jintr[2 * MAXK];  // 2xK
+};
+
+// evaluate_internal (src/factors/projection_factor.rs:184-296) for n = 1 observation, followed by the
+// loss correction of linearize_block (src/linearizer/mod.rs:143-149). Jacobian columns are kept per
+// variable: pose (6) | landmark (3) | intrinsics (K).
+void linearize_obs(int model, int K, bool opt_intr, int loss_id, const double* loss_prm, const Pose& pose,
+                   const double* intr, const V3& pw, const double* uv_obs, bool want_jac, BlockLin& out) {
+  std::memset(&out, 0, sizeof(out));
+  V3 pc = pose_act(pose, pw);  // :224
+  double uv[2];
+  if (cam_project(model, intr, pc, uv)) {  // :227-239 (Err => zero residual, zero Jacobian rows)
+    out.r[0] = uv[0] - uv_obs[0];  // :242-243
+    out.r[1] = uv[1] - uv_obs[1];
+    if (want_jac) {
+      double A[6];  // d_uv_d_pcam
+      cam_jacobian_point(model, intr, pc, A);
+      double R[9];
+      quat_to_matrix(pose.q, R);
+      // jacobian_pose (lib.rs:560-589 / bal_pinhole.rs:528-556): [R | -R [p_w]x]
+      double S[9] = {0, -pw.z, pw.y, pw.z, 0, -pw.x, -pw.y, pw.x, 0};
+      double D[18];  // 3x6
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 6; ++c) {
+          if (c < 3) D[r * 6 + c] = R[r * 3 + c];
+          else {
+            double v = 0;
+            for (int k = 0; k < 3; ++k) v += R[r * 3 + k] * S[k * 3 + (c - 3)];
+            D[r * 6 + c] = -v;
+          }
+        }
+      for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 6; ++c) {
+          double v = 0;
+          for (int k = 0; k < 3; ++k) v += A[r * 3 + k] * D[k * 6 + c];
+          out.jpose[r * 6 + c] = v;  // :250-259
+        }
+      for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 3; ++c) {
+          double v = 0;
+          for (int k = 0; k < 3; ++k) v += A[r * 3 + k] * R[k * 3 + c];
+          out.jpt[r * 3 + c] = v;  // :262-276
+        }
+      if (opt_intr) cam_jacobian_intrinsics(model, intr, pc, out.jintr);  // :284-291
+    }
+  }
+  if (loss_id != APEX_LOSS_NONE) {
+    double sq = out.r[0] * out.r[0] + out.r[1] * out.r[1];
+    Corrector c = corrector_new(loss_id, loss_prm, sq);
+    if (want_jac) {
+      // correct_jacobian (corrector.rs:233-254)
+      if (c.alpha_sq_norm == 0.0) {
+        for (double& v : out.jpose) v *= c.sqrt_rho1;
+        for (double& v : out.jpt) v *= c.sqrt_rho1;
+        for (int a = 0; a < 2 * K; ++a) out.jintr[a] *= c.sqrt_rho1;
+      } else {
+        auto fix = [&](double* J, int ncol) {
+          for (int col = 0; col < ncol; ++col) {
+            double j0 = J[col], j1 = J[ncol + col];
+            double rtj = out.r[0] * j0 + out.r[1] * j1;
+            J[col] = (j0 - out.r[0] * rtj * c.alpha_sq_norm) * c.sqrt_rho1;
+            J[ncol + col] = (j1 - out.r[1] * rtj * c.alpha_sq_norm) * c.sqrt_rho1;
+          }
+        };
+        fix(out.jpose, 6);
+        fix(out.jpt, 3);
+        if (opt_intr) fix(out.jintr, K);
+      }
+    }
+    out.r[0] *= c.residual_scaling;  // correct_residuals (corrector.rs:292-298)
+    out.r[1] *= c.residual_scaling;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small dense helpers
+// ------------------------------------------------------------------------------------------------
+// nalgebra Matrix3::try_inverse: closed form, fails iff determinant == 0. Row-major.
+bool inverse3(const double* m, double* o) {
+  double m11 = m[0], m12 = m[1], m13 = m[2], m21 = m[3], m22 = m[4], m23 = m[5], m31 = m[6], m32 = m[7], m33 = m[8];
+  double a = m22 * m33 - m32 * m23, b = m21 * m33 - m31 * m23, c = m21 * m32 - m31 * m22;
+  double det = m11 * a - m12 * b + m13 * c;
+  if (det == 0.0) return false;
+  o[0] = a / det; o[1] = (m13 * m32 - m33 * m12) / det; o[2] = (m12 * m23 - m22 * m13) / det;
+  o[3] = -b / det; o[4] = (m11 * m33 - m31 * m13) / det; o[5] = (m13 * m21 - m23 * m11) / det;
+  o[6] = c / det; o[7] = (m12 * m31 - m32 * m11) / det; o[8] = (m11 * m22 - m21 * m12) / det;
+  return true;
+}
+
+// DMatrix::try_inverse: n<=3 closed form, otherwise LU with partial pivoting; fails on an exactly zero pivot.
+bool inverse_n(int n, const double* m, double* o) {
+  if (n == 1) { if (m[0] == 0.0) return false; o[0] = 1.0 / m[0]; return true; }
+  if (n == 2) {
+    double det = m[0] * m[3] - m[2] * m[1];
+    if (det == 0.0) return false;
+    o[0] = m[3] / det; o[1] = -m[1] / det; o[2] = -m[2] / det; o[3] = m[0] / det; return true;
+  }
+  if (n == 3) return inverse3(m, o);
+  std::vector<double> a(m, m + n * n);
+  std::vector<int> piv(n);
+  for (int i = 0; i < n * n; ++i) o[i] = 0.0;
+  for (int i = 0; i < n; ++i) o[i * n + i] = 1.0;
+  for (int c = 0; c < n; ++c) {
+    int p = c; double best = std::fabs(a[c * n + c]);
+    for (int r = c + 1; r < n; ++r) if (std::fabs(a[r * n + c]) > best) { best = std::fabs(a[r * n + c]); p = r; }
+    if (a[p * n + c] == 0.0 || !(best == best)) return false;
+    if (p != c) for (int k = 0; k < n; ++k) { std::swap(a[p * n + k], a[c * n + k]); std::swap(o[p * n + k], o[c * n + k]); }
+    double d = a[c * n + c];
+    for (int r = c + 1; r < n; ++r) {
+      double f = a[r * n + c] / d;
+      if (f == 0.0) continue;
+      for (int k = c; k < n; ++k) a[r * n + k] -= f * a[c * n + k];
+      for (int k = 0; k < n; ++k) o[r * n + k] -= f * o[c * n + k];
+    }
+  }
+  for (int c = n - 1; c >= 0; --c) {
+    double d = a[c * n + c];
+    for (int k = 0; k < n; ++k) o[c * n + k] /= d;
+    for (int r = 0; r < c; ++r) {
+      double f = a[r * n + c];
+      if (f == 0.0) continue;
+      for (int k = 0; k < n; ++k) o[r * n + k] -= f * o[c * n + k];
+    }
+  }
+  return true;
+}
+
+// Eigenvalues of a symmetric 3x3 (cyclic Jacobi). Stands in for nalgebra symmetric_eigenvalues();
+// only min/max feed the guards of invert_landmark_blocks.
+void sym_eig3_minmax(const double* m, double& mn, double& mx) {
+  double a[9];
+  for (int i = 0; i < 9; ++i) a[i] = m[i];
+  // use the lower/upper average to be safe against tiny asymmetry
+  a[1] = a[3] = 0.5 * (m[1] + m[3]); a[2] = a[6] = 0.5 * (m[2] + m[6]); a[5] = a[7] = 0.5 * (m[5] + m[7]);
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = a[1] * a[1] + a[2] * a[2] + a[5] * a[5];
+    double diag = a[0] * a[0] + a[4] * a[4] + a[8] * a[8];
+    if (off <= 1e-40 * diag || off == 0.0) break;
+    const int P[3] = {0, 0, 1}, Q[3] = {1, 2, 2};
+    for (int t = 0; t < 3; ++t) {
+      int p = P[t], q = Q[t];
+      double apq = a[p * 3 + q];
+      if (apq == 0.0) continue;
+      double app = a[p * 3 + p], aqq = a[q * 3 + q];
+      double tau = (aqq - app) / (2.0 * apq);
+      double tt = (tau >= 0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
+      double c = 1.0 / std::sqrt(1.0 + tt * tt), s = tt * c;
+      for (int k = 0; k < 3; ++k) {  // rotate columns p,q
+        double akp = a[k * 3 + p], akq = a[k * 3 + q];
+        a[k * 3 + p] = c * akp - s * akq;
+        a[k * 3 + q] = s * akp + c * akq;
+      }
+      for (int k = 0; k < 3; ++k) {  // rotate rows p,q
+        double apk = a[p * 3 + k], aqk = a[q * 3 + k];
+        a[p * 3 + k] = c * apk - s * aqk;
+        a[q * 3 + k] = s * apk + c * aqk;
+      }
+    }
+  }
+  mn = std::min(a[0], std::min(a[4], a[8]));
+  mx = std::max(a[0], std::max(a[4], a[8]));
+}
+
+// invert_landmark_blocks_with_lambda (explicit_schur.rs:377-442; called with lambda_arg = 0 from :365-367)
+// and IterativeSchurSolver::invert_landmark_blocks (implicit_schur.rs:724-759, reg = 1e-6 + max_ev*1e-6).
+// `block` is already damped. Returns false => LinAlgError::SingularMatrix.
+bool invert_landmark_block(const double* block, double lambda_arg, bool implicit_flavour, double* inv) {
+  const double CONDITION_THRESHOLD = 1e10, MIN_EIGENVALUE_THRESHOLD = 1e-12, REGULARIZATION_SCALE = 1e-6;
+  double mn, mx;
+  sym_eig3_minmax(block, mn, mx);
+  double b[9];
+  for (int i = 0; i < 9; ++i) b[i] = block[i];
+  if (mn < MIN_EIGENVALUE_THRESHOLD) {
+    double reg = implicit_flavour ? (REGULARIZATION_SCALE + mx * REGULARIZATION_SCALE)
+                                  : (std::max(lambda_arg, REGULARIZATION_SCALE) + mx * REGULARIZATION_SCALE);
+    b[0] += reg; b[4] += reg; b[8] += reg;
+  } else if (mx / mn > CONDITION_THRESHOLD) {
+    double reg = mx * REGULARIZATION_SCALE;
+    b[0] += reg; b[4] += reg; b[8] += reg;
+  }
+  return inverse3(b, inv);
+}
+
+// faer Mat::norm_l2 of a vector (src/optimizer/mod.rs:359, levenberg_marquardt.rs:746,888).
+double norm_l2(const double* v, size_t n) {
+  double s = 0;
+  for (size_t i = 0; i < n; ++i) s += v[i] * v[i];
+  return std::sqrt(s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sparse symmetric matrix in CSC (the Schur complement after the 1e-12 filter)
+// ------------------------------------------------------------------------------------------------
+struct Csc {
+  size_t n = 0;
+  std::vector<size_t> colptr;
+  std::vector<uint32_t> row;
+  std::vector<double> val;
+};
+
+// Dense blocked Cholesky (lower, row-major, in place) standing in for faer's sparse Llt
+// (explicit_schur.rs:544-550). Returns false when a pivot is not positive.
+bool dense_cholesky(double* A, size_t n) {
+  const size_t NB = 64;
+  for (size_t k0 = 0; k0 < n; k0 += NB) {
+    size_t kb = std::min(NB, n - k0);
+    // factor diagonal block
+    for (size_t j = k0; j < k0 + kb; ++j) {
+      double d = A[j * n + j];
+      for (size_t k = k0; k < j; ++k) d -= A[j * n + k] * A[j * n + k];
+      if (!(d > 0.0)) return false;
+      d = std::sqrt(d);
+      A[j * n + j] = d;
+      for (size_t i = j + 1; i < k0 + kb; ++i) {
+        double s = A[i * n + j];
+        for (size_t k = k0; k < j; ++k) s -= A[i * n + k] * A[j * n + k];
+        A[i * n + j] = s / d;
+      }
+    }
+    size_t r0 = k0 + kb;
+    if (r0 >= n) break;
+    // panel: rows below, solve L21 L11^T = A21
+#pragma omp parallel for schedule(static)
+    for (size_t i = r0; i < n; ++i) {
+      for (size_t j = k0; j < k0 + kb; ++j) {
+        double s = A[i * n + j];
+        for (size_t k = k0; k < j; ++k) s -= A[i * n + k] * A[j * n + k];
+        A[i * n + j] = s / A[j * n + j];
+      }
+    }
+    // trailing update (lower part): A22 -= L21 L21^T
+#pragma omp parallel for schedule(dynamic, 8)
+    for (size_t i = r0; i < n; ++i) {
+      const double* li = A + i * n + k0;
+      for (size_t j = r0; j <= i; ++j) {
+        const double* lj = A + j * n + k0;
+        double s = 0;
+        for (size_t k = 0; k < kb; ++k) s += li[k] * lj[k];
+        A[i * n + j] -= s;
+      }
+    }
+  }
+  return true;
+}
+
+void cholesky_solve(const double* L, size_t n, const double* b, double* x) {
+  std::vector<double> y(n);
+  for (size_t i = 0; i < n; ++i) {
+    double s = b[i];
+    for (size_t k = 0; k < i; ++k) s -= L[i * n + k] * y[k];
+    y[i] = s / L[i * n + i];
+  }
+  for (size_t ii = n; ii-- > 0;) {
+    double s = y[ii];
+    for (size_t k = ii + 1; k < n; ++k) s -= L[k * n + ii] * x[k];
+    x[ii] = s / L[ii * n + ii];
+  }
+}
+
+// solve_with_cholesky (explicit_schur.rs:539-634): factor; on failure retry with
+// reg = max(trace/n, max|diag|, 1) * 10^(attempt-4), attempt = 0..4.
+apex_status solve_with_cholesky(const Csc& a, const double* b, double* x, std::string& err) {
+  size_t n = a.n;
+  std::vector<double> dense(n * n);
+  auto fill = [&](double reg) {
+    std::fill(dense.begin(), dense.end(), 0.0);
+    for (size_t c = 0; c < n; ++c)
+      for (size_t p = a.colptr[c]; p < a.colptr[c + 1]; ++p) dense[(size_t)a.row[p] * n + c] = a.val[p];  // lower used
+    if (reg != 0.0) for (size_t i = 0; i < n; ++i) dense[i * n + i] += reg;
+  };
+  fill(0.0);
+  if (dense_cholesky(dense.data(), n)) { cholesky_solve(dense.data(), n, b, x); return APEX_OK; }
+  double trace = 0.0, max_diag = 0.0;
+  for (size_t c = 0; c < n; ++c)
+    for (size_t p = a.colptr[c]; p < a.colptr[c + 1]; ++p)
+      if (a.row[p] == c) { trace += a.val[p]; max_diag = std::max(max_diag, std::fabs(a.val[p])); }
+  double base = std::max(std::max(trace / (double)n, max_diag), 1.0);
+  for (int attempt = 0; attempt < 5; ++attempt) {
+    double reg = base * std::pow(10.0, attempt - 4);
+    fill(reg);
+    if (dense_cholesky(dense.data(), n)) { cholesky_solve(dense.data(), n, b, x); return APEX_OK; }
+  }
+  err = "Schur complement singular after 5 regularization attempts";
+  return APEX_ERR_SINGULAR_MATRIX;
+}
+
+// solve_with_pcg (explicit_schur.rs:639-756): scalar-Jacobi PCG on the explicit sparse S.
+int solve_with_pcg(const Csc& a, const double* b, double* x, int max_iterations, double tolerance) {
+  size_t n = a.n;
+  std::vector<double> precond(n, 1.0), r(b, b + n), z(n), p(n), ap(n);
+  for (size_t c = 0; c < n; ++c)
+    for (size_t q = a.colptr[c]; q < a.colptr[c + 1]; ++q)
+      if (a.row[q] == c) { double d = a.val[q]; precond[c] = std::fabs(d) > 1e-12 ? 1.0 / d : 1.0; break; }
+  for (size_t i = 0; i < n; ++i) x[i] = 0.0;
+  for (size_t i = 0; i < n; ++i) z[i] = precond[i] * r[i];
+  p = z;
+  double rz_old = 0.0;
+  for (size_t i = 0; i < n; ++i) rz_old += r[i] * z[i];
+  double r_norm_init = 0.0;
+  for (size_t i = 0; i < n; ++i) r_norm_init += r[i] * r[i];
+  r_norm_init = std::sqrt(r_norm_init);
+  double abs_tol = tolerance * std::max(r_norm_init, 1.0);
+  int iters = 0;
+  for (int it = 0; it < max_iterations; ++it) {
+    iters = it + 1;
+    std::fill(ap.begin(), ap.end(), 0.0);
+    for (size_t c = 0; c < n; ++c) {
+      double pc = p[c];
+      for (size_t q = a.colptr[c]; q < a.colptr[c + 1]; ++q) ap[a.row[q]] += a.val[q] * pc;
+    }
+    double p_ap = 0.0;
+    for (size_t i = 0; i < n; ++i) p_ap += p[i] * ap[i];
+    if (std::fabs(p_ap) < 1e-30) break;
+    double alpha = rz_old / p_ap;
+    for (size_t i = 0; i < n; ++i) x[i] += alpha * p[i];
+    for (size_t i = 0; i < n; ++i) r[i] -= alpha * ap[i];
+    double r_norm = 0.0;
+    for (size_t i = 0; i < n; ++i) r_norm += r[i] * r[i];
+    r_norm = std::sqrt(r_norm);
+    if (r_norm < abs_tol) break;
+    for (size_t i = 0; i < n; ++i) z[i] = precond[i] * r[i];
+    double rz_new = 0.0;
+    for (size_t i = 0; i < n; ++i) rz_new += r[i] * z[i];
+    if (std::fabs(rz_old) < 1e-30) break;
+    double beta = rz_new / rz_old;
+    for (size_t i = 0; i < n; ++i) p[i] = z[i] + beta * p[i];
+    rz_old = rz_new;
+  }
+  return iters;
+}
+
+// One landmark's H_cp rows: (camera row of S, [v0,v1,v2]) sorted by row, as produced by the 3-way
+// merge of explicit_schur.rs:811-865.
+struct CpRow { uint32_t row; double v[3]; };
+
+// compute_schur_complement (explicit_schur.rs:771-925). s_dense (row-major cam_size^2) must already
+// hold the damped H_cc. Landmarks are processed sequentially in block order.
+void schur_accumulate_landmark(double* s_dense, size_t cam_size, const CpRow* rows, size_t nrows, const double* hinv /*row-major 3x3*/) {
+  if (nrows == 0) return;
+  std::vector<double> contrib(nrows * 3);
+  for (size_t i = 0; i < nrows; ++i) {
+    const double* h = rows[i].v;
+    contrib[i * 3 + 0] = h[0] * hinv[0] + h[1] * hinv[3] + h[2] * hinv[6];
+    contrib[i * 3 + 1] = h[0] * hinv[1] + h[1] * hinv[4] + h[2] * hinv[7];
+    contrib[i * 3 + 2] = h[0] * hinv[2] + h[1] * hinv[5] + h[2] * hinv[8];
+  }
+  for (size_t i = 0; i < nrows; ++i) {
+    double* srow = s_dense + (size_t)rows[i].row * cam_size;
+    const double* ci = &contrib[i * 3];
+    for (size_t j = 0; j < nrows; ++j) {
+      const double* hj = rows[j].v;
+      srow[rows[j].row] -= ci[0] * hj[0] + ci[1] * hj[1] + ci[2] * hj[2];
+    }
+  }
+}
+
+void schur_symmetrize_and_sparsify(double* s_dense, size_t n, Csc& out) {
+  for (size_t i = 0; i < n; ++i)  // :903-909
+    for (size_t j = i + 1; j < n; ++j) {
+      double avg = (s_dense[i * n + j] + s_dense[j * n + i]) * 0.5;
+      s_dense[i * n + j] = avg;
+      s_dense[j * n + i] = avg;
+    }
+  out.n = n;
+  out.colptr.assign(n + 1, 0);
+  out.row.clear();
+  out.val.clear();
+  for (size_t col = 0; col < n; ++col) {  // :913-921 (|val| > 1e-12 kept)
+    for (size_t row = 0; row < n; ++row) {
+      double v = s_dense[row * n + col];
+      if (std::fabs(v) > 1e-12) { out.row.push_back((uint32_t)row); out.val.push_back(v); }
+    }
+    out.colptr[col + 1] = out.row.size();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LM bookkeeping
+// ------------------------------------------------------------------------------------------------
+// compute_cost (src/optimizer/mod.rs:358-361)
+double compute_cost(const double* r, size_t n) { double c = norm_l2(r, n); return 0.5 * c * c; }
+
+// compute_step_quality (src/optimizer/mod.rs:668-675)
+double compute_step_quality(double current_cost, double new_cost, double predicted_reduction) {
+  double actual = current_cost - new_cost;
+  if (std::fabs(predicted_reduction) < 1e-15) return actual > 0.0 ? 1.0 : 0.0;
+  return actual / predicted_reduction;
+}
+
+// update_damping (levenberg_marquardt.rs:702-717)
+bool update_damping(double& damping, double& nu, double dmin, double dmax, double rho) {
+  if (rho > 0.0) {
+    double coff = 2.0 * rho - 1.0;
+    damping *= std::max(1.0 / 3.0, 1.0 - coff * coff * coff);
+    damping = std::max(damping, dmin);
+    nu = 2.0;
+    return true;
+  }
+  damping *= nu;
+  nu *= 2.0;
+  damping = std::min(damping, dmax);
+  return false;
+}
+
+struct ConvergenceParams {
+  int iteration; double current_cost, new_cost, parameter_norm, parameter_update_norm, gradient_norm, elapsed;
+  bool step_accepted; int max_iterations; double gradient_tolerance, parameter_tolerance, cost_tolerance;
+  double min_cost_threshold /*NaN none*/, timeout /*<=0 none*/, trust_region_radius, min_trust_region_radius;
+};
+// check_convergence (src/optimizer/mod.rs:591-658). Returns -1 for None.
+int check_convergence(const ConvergenceParams& p) {
+  if (!std::isfinite(p.new_cost) || !std::isfinite(p.parameter_update_norm) || !std::isfinite(p.gradient_norm))
+    return APEX_STATUS_INVALID_NUMERICAL_VALUES;
+  if (p.timeout > 0.0 && p.elapsed >= p.timeout) return APEX_STATUS_TIMEOUT;
+  if (p.iteration >= p.max_iterations) return APEX_STATUS_MAX_ITERATIONS_REACHED;
+  if (!p.step_accepted) return -1;
+  if (p.gradient_norm < p.gradient_tolerance) return APEX_STATUS_GRADIENT_TOLERANCE_REACHED;
+  if (p.iteration > 0) {
+    double rel_step_tol = p.parameter_tolerance * (p.parameter_norm + p.parameter_tolerance);
+    if (p.parameter_update_norm <= rel_step_tol) return APEX_STATUS_PARAMETER_TOLERANCE_REACHED;
+    double cost_change = std::fabs(p.current_cost - p.new_cost);
+    double rel = cost_change / std::max(p.current_cost, 1e-10);
+    if (rel < p.cost_tolerance) return APEX_STATUS_COST_TOLERANCE_REACHED;
+  }
+  if (!std::isnan(p.min_cost_threshold) && p.new_cost < p.min_cost_threshold) return APEX_STATUS_MIN_COST_THRESHOLD_REACHED;
+  if (p.trust_region_radius < p.min_trust_region_radius) return APEX_STATUS_TRUST_REGION_RADIUS_TOO_SMALL;
+  return -1;
+}
+
+void lm_config_default(apex_lm_config* c) {  // levenberg_marquardt.rs:319-359
+  std::memset(c, 0, sizeof(*c));
+  c->schur_variant = APEX_SCHUR_EXPLICIT;          // SchurVariant::default() = Sparse
+  c->schur_preconditioner = APEX_PRECOND_SCHUR_JACOBI;
+  c->max_iterations = 50;
+  c->cg_max_iterations = 200;  // explicit_schur.rs:211
+  c->cost_tolerance = 1e-6; c->parameter_tolerance = 1e-8; c->gradient_tolerance = 1e-10;
+  c->timeout_seconds = 0.0;
+  c->damping = 1e-3; c->damping_min = 1e-12; c->damping_max = 1e12;
+  c->damping_increase_factor = 10.0; c->damping_decrease_factor = 0.3; c->damping_nu = 2.0;
+  c->trust_region_radius = 1e4; c->min_step_quality = 0.0; c->good_step_quality = 0.75;
+  c->min_diagonal = 1e-6; c->max_diagonal = 1e32;
+  c->min_cost_threshold = std::numeric_limits<double>::quiet_NaN();
+  c->min_trust_region_radius = 1e-32;
+  c->max_condition_number = std::numeric_limits<double>::quiet_NaN();
+  c->min_relative_decrease = 1e-3;
+  c->cg_tolerance = 1e-6;  // explicit_schur.rs:212
+  c->use_jacobi_scaling = 0; c->compute_covariances = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Problem state
+// ------------------------------------------------------------------------------------------------
+struct Ctx {
+  std::string err;
+  // problem
+  int model = 0, K = 0; uint32_t opt = 0; bool intr_vars = false;
+  uint32_t ncam = 0, npts = 0; uint64_t nobs = 0;
+  std::vector<double> pose, intr, pt;  // current variable values
+  std::vector<uint32_t> obs_cam, obs_pt; std::vector<double> uv;
+  int loss_id = 0; double loss_prm[4] = {0, 0, 0, 0};
+  std::vector<uint8_t> pose_fixed, pt_fixed; std::vector<uint16_t> intr_fixed;
+  // derived structure
+  bool opt_intr = false;
+  int dc = 6;                          // camera DOF inside the reduced system (pose6 [+K])
+  size_t cam_dof = 0, lm_dof = 0;      // reference layout sizes
+  std::vector<size_t> col_intr, col_pose, col_pt;  // reference (sorted-name) column offsets; cameras start at 0
+  std::vector<uint32_t> lm_order;      // landmark indices in landmark-block (column) order
+  std::vector<size_t> pt_obs_start; std::vector<uint32_t> pt_obs;   // observations of each point (insertion order)
+  // linearization
+  bool linearized = false; double lin_lambda = 0;
+  std::vector<BlockLin> lin;
+  std::vector<double> hcc, gc, hpp, gp, hpp_inv_exp, hpp_inv_imp;  // per camera dc*dc, dc; per point 9,3,9,9
+  bool inv_exp_ok = true, inv_imp_ok = true;
+  int64_t last_pcg_iters = 0;
+};
+
+std::string var_name(const char* prefix, int width, uint32_t idx) {
+  char buf[48];
+  std::snprintf(buf, sizeof(buf), "%s%0*u", prefix, width, idx);
+  return buf;
+}
+
+// initialize_optimization_state (src/optimizer/mod.rs:522-563): variables sorted by name;
+// bin/bundle_adjustment.rs:240-253 names them pose_%04d / intr_%04d / pt_%05d.
+void build_structure(Ctx& c) {
+  c.opt_intr = (c.opt & APEX_OPT_INTRINSIC) != 0;
+  c.dc = 6 + (c.opt_intr ? c.K : 0);
+  bool have_intr_vars = c.opt_intr || c.intr_vars;
+  struct Var { std::string name; int kind; uint32_t idx; int size; };
+  std::vector<Var> cams;
+  cams.reserve(2 * (size_t)c.ncam);
+  for (uint32_t i = 0; i < c.ncam; ++i) {
+    cams.push_back({var_name("pose_", 4, i), 0, i, 6});
+    if (have_intr_vars) cams.push_back({var_name("intr_", 4, i), 1, i, c.K});
+  }
+  std::sort(cams.begin(), cams.end(), [](const Var& a, const Var& b) { return a.name < b.name; });
+  c.col_intr.assign(c.ncam, (size_t)-1);
+  c.col_pose.assign(c.ncam, 0);
+  size_t off = 0;
+  for (auto& v : cams) {
+    if (v.kind == 0) c.col_pose[v.idx] = off; else c.col_intr[v.idx] = off;
+    off += v.size;
+  }
+  c.cam_dof = off;
+  // landmarks: lexicographic order of pt_%05d equals numeric order while npts <= 100000
+  c.lm_order.resize(c.npts);
+  for (uint32_t i = 0; i < c.npts; ++i) c.lm_order[i] = i;
+  if (c.npts > 100000) {
+    std::vector<std::string> names(c.npts);
+    for (uint32_t i = 0; i < c.npts; ++i) names[i] = var_name("pt_", 5, i);
+    std::sort(c.lm_order.begin(), c.lm_order.end(), [&](uint32_t a, uint32_t b) { return names[a] < names[b]; });
+  }
+  c.col_pt.assign(c.npts, 0);
+  for (uint32_t k = 0; k < c.npts; ++k) c.col_pt[c.lm_order[k]] = 3 * (size_t)k;
+  c.lm_dof = 3 * (size_t)c.npts;
+  // observations per point
+  c.pt_obs_start.assign((size_t)c.npts + 1, 0);
+  for (uint64_t o = 0; o < c.nobs; ++o) c.pt_obs_start[c.obs_pt[o] + 1]++;
+  for (uint32_t p = 0; p < c.npts; ++p) c.pt_obs_start[p + 1] += c.pt_obs_start[p];
+  c.pt_obs.resize(c.nobs);
+  std::vector<size_t> cur(c.pt_obs_start.begin(), c.pt_obs_start.end() - 1);
+  for (uint64_t o = 0; o < c.nobs; ++o) c.pt_obs[cur[c.obs_pt[o]]++] = (uint32_t)o;
+}
+
+// row of S (reference layout) for local camera dof d of camera cam (local order: pose 6, then intr K)
+inline size_t cam_row(const Ctx& c, uint32_t cam, int d) { return d < 6 ? c.col_pose[cam] + d : c.col_intr[cam] + (d - 6); }
+
+// Jc (2 x dc, local order pose|intr) of an observation
+inline void obs_jc(const Ctx& c, const BlockLin& b, double* jc) {
+  for (int r = 0; r < 2; ++r) {
+    for (int k = 0; k < 6; ++k) jc[r * c.dc + k] = b.jpose[r * 6 + k];
+    if (c.opt_intr) for (int k = 0; k < c.K; ++k) jc[r * c.dc + 6 + k] = b.jintr[r * c.K + k];
+  }
+}
+
+// AssemblyBackend::assemble (src/linearizer/mod.rs:216-227 -> cpu/sparse.rs:119-184): every residual block
+// in parallel (rayon par_iter :132-145), then H = J^T J and g = J^T r (explicit_schur.rs:1146-1160) kept
+// block-wise: H_cc[c] (dc x dc), H_pp[p] (3x3); H_cp[c,p] = Jc^T Jp is formed on demand per observation.
+void linearize(Ctx& c, double lambda) {
+  c.lin.resize(c.nobs);
+#pragma omp parallel for schedule(static)
+  for (int64_t o = 0; o < (int64_t)c.nobs; ++o) {
+    uint32_t cam = c.obs_cam[o], p = c.obs_pt[o];
+    Pose pose = pose_from7(&c.pose[7 * (size_t)cam]);
+    V3 pw{c.pt[3 * (size_t)p], c.pt[3 * (size_t)p + 1], c.pt[3 * (size_t)p + 2]};
+    linearize_obs(c.model, c.K, c.opt_intr, c.loss_id, c.loss_prm, pose, &c.intr[(size_t)c.K * cam], pw, &c.uv[2 * o], true, c.lin[o]);
+  }
+  const int dc = c.dc;
+  c.hcc.assign((size_t)c.ncam * dc * dc, 0.0);
+  c.gc.assign((size_t)c.ncam * dc, 0.0);
+  c.hpp.assign((size_t)c.npts * 9, 0.0);
+  c.gp.assign((size_t)c.npts * 3, 0.0);
+  // camera side: sequential over observations in insertion order (deterministic)
+  for (uint64_t o = 0; o < c.nobs; ++o) {
+    const BlockLin& b = c.lin[o];
+    double jc[2 * (6 + MAXK)];
+    obs_jc(c, b, jc);
+    double* H = &c.hcc[(size_t)c.obs_cam[o] * dc * dc];
+    double* g = &c.gc[(size_t)c.obs_cam[o] * dc];
+    for (int a = 0; a < dc; ++a) {
+      for (int bb = 0; bb < dc; ++bb) H[a * dc + bb] += jc[a] * jc[bb] + jc[dc + a] * jc[dc + bb];
+      g[a] += jc[a] * b.r[0] + jc[dc + a] * b.r[1];
+    }
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t p = 0; p < (int64_t)c.npts; ++p) {
+    double* H = &c.hpp[(size_t)p * 9];
+    double* g = &c.gp[(size_t)p * 3];
+    for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
+      const BlockLin& b = c.lin[c.pt_obs[q]];
+      for (int a = 0; a < 3; ++a) {
+        for (int bb = 0; bb < 3; ++bb) H[a * 3 + bb] += b.jpt[a] * b.jpt[bb] + b.jpt[3 + a] * b.jpt[3 + bb];
+        g[a] += b.jpt[a] * b.r[0] + b.jpt[3 + a] * b.r[1];
+      }
+    }
+  }
+  // damped point-block inverses, both flavours
+  c.hpp_inv_exp.assign((size_t)c.npts * 9, 0.0);
+  c.hpp_inv_imp.assign((size_t)c.npts * 9, 0.0);
+  int ok_exp = 1, ok_imp = 1;
+#pragma omp parallel for schedule(static) reduction(&& : ok_exp, ok_imp)
+  for (int64_t p = 0; p < (int64_t)c.npts; ++p) {
+    double blk[9];
+    for (int a = 0; a < 9; ++a) blk[a] = c.hpp[(size_t)p * 9 + a];
+    blk[0] += lambda; blk[4] += lambda; blk[8] += lambda;  // explicit_schur.rs:1208-1212 / implicit_schur.rs:1053-1068
+    ok_exp = ok_exp && invert_landmark_block(blk, 0.0, false, &c.hpp_inv_exp[(size_t)p * 9]);
+    ok_imp = ok_imp && invert_landmark_block(blk, 0.0, true, &c.hpp_inv_imp[(size_t)p * 9]);
+  }
+  c.inv_exp_ok = ok_exp; c.inv_imp_ok = ok_imp;
+  c.linearized = true;
+  c.lin_lambda = lambda;
+}
+
+// compute_residual_sparse + compute_cost (src/core/problem.rs:864-899,985-1024; src/optimizer/mod.rs:358-361)
+double cost_at(const Ctx& c, const std::vector<double>& pose, const std::vector<double>& intr, const std::vector<double>& pt) {
+  std::vector<double> r(2 * c.nobs);
+#pragma omp parallel for schedule(static)
+  for (int64_t o = 0; o < (int64_t)c.nobs; ++o) {
+    uint32_t cam = c.obs_cam[o], p = c.obs_pt[o];
+    Pose ps = pose_from7(&pose[7 * (size_t)cam]);
+    V3 pw{pt[3 * (size_t)p], pt[3 * (size_t)p + 1], pt[3 * (size_t)p + 2]};
+    BlockLin b;
+    linearize_obs(c.model, c.K, c.opt_intr, c.loss_id, c.loss_prm, ps, &intr[(size_t)c.K * cam], pw, &c.uv[2 * o], false, b);
+    r[2 * o] = b.r[0]; r[2 * o + 1] = b.r[1];
+  }
+  return compute_cost(r.data(), r.size());
+}
+
+// E = Jc^T Jp (dc x 3) = the H_cp block of one observation
+inline void obs_E(const Ctx& c, const BlockLin& b, double* E) {
+  double jc[2 * (6 + MAXK)];
+  obs_jc(c, b, jc);
+  for (int a = 0; a < c.dc; ++a)
+    for (int k = 0; k < 3; ++k) E[a * 3 + k] = jc[a] * b.jpt[k] + jc[c.dc + a] * b.jpt[3 + k];
+}
+
+// apply_schur_operator_fast (implicit_schur.rs:163-251) restricted to points [p0,p1): y (camera-major local layout
+// ncam*dc, pose|intr) += [H_cc x + lambda x if add_hcc] - H_cp Hpp^-1 H_cp^T x.
+void schur_matvec_local(const Ctx& c, const double* x, double* y, double lambda, uint32_t p0, uint32_t p1, bool add_hcc, const std::vector<double>& hinv) {
+  const int dc = c.dc;
+  if (add_hcc) {
+    for (uint32_t cam = 0; cam < c.ncam; ++cam) {
+      const double* H = &c.hcc[(size_t)cam * dc * dc];
+      for (int a = 0; a < dc; ++a) {
+        double s = lambda * x[(size_t)cam * dc + a];
+        for (int b = 0; b < dc; ++b) s += H[a * dc + b] * x[(size_t)cam * dc + b];
+        y[(size_t)cam * dc + a] += s;
+      }
+    }
+  }
+  double E[(6 + MAXK) * 3];
+  for (uint32_t p = p0; p < p1; ++p) {
+    double t[3] = {0, 0, 0};
+    for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
+      uint32_t o = c.pt_obs[q];
+      obs_E(c, c.lin[o], E);
+      const double* xc = &x[(size_t)c.obs_cam[o] * dc];
+      for (int a = 0; a < dc; ++a) for (int k = 0; k < 3; ++k) t[k] += E[a * 3 + k] * xc[a];
+    }
+    const double* hi = &hinv[(size_t)p * 9];
+    double w[3] = {hi[0] * t[0] + hi[1] * t[1] + hi[2] * t[2], hi[3] * t[0] + hi[4] * t[1] + hi[5] * t[2], hi[6] * t[0] + hi[7] * t[1] + hi[8] * t[2]};
+    for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
+      uint32_t o = c.pt_obs[q];
+      obs_E(c, c.lin[o], E);
+      double* yc = &y[(size_t)c.obs_cam[o] * dc];
+      for (int a = 0; a < dc; ++a) yc[a] -= E[a * 3] * w[0] + E[a * 3 + 1] * w[1] + E[a * 3 + 2] * w[2];
+    }
+  }
+}
+
+// Camera "variable" blocks of the implicit solver: per camera a 6x6 pose block and (if present) a KxK
+// intrinsics block (structure.camera_blocks is per VARIABLE, implicit_schur.rs:955-1008).
+// compute_schur_jacobi_preconditioner (:456-573) / compute_block_preconditioner (:352-404) / None (:895-905).
+// Output: per camera, inverse blocks pinv_pose[36], pinv_intr[K*K] (row-major).
+void build_preconditioner(const Ctx& c, int kind, double lambda, const std::vector<double>& hinv, uint32_t p0, uint32_t p1,
+                          std::vector<double>& pinv_pose, std::vector<double>& pinv_intr) {
+  const int dc = c.dc, K = c.K;
+  bool have_intr_vars = c.opt_intr || c.intr_vars;
+  std::vector<double> spose((size_t)c.ncam * 36, 0.0), sintr(have_intr_vars ? (size_t)c.ncam * K * K : 0, 0.0);
+  for (uint32_t cam = 0; cam < c.ncam; ++cam) {
+    const double* H = &c.hcc[(size_t)cam * dc * dc];
+    for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) spose[(size_t)cam * 36 + a * 6 + b] = H[a * dc + b] + (a == b ? lambda : 0.0);
+    if (have_intr_vars)
+      for (int a = 0; a < K; ++a) for (int b = 0; b < K; ++b)
+        sintr[(size_t)cam * K * K + a * K + b] = (c.opt_intr ? H[(6 + a) * dc + 6 + b] : 0.0) + (a == b ? lambda : 0.0);
+  }
+  if (kind == APEX_PRECOND_SCHUR_JACOBI) {
+    double E[(6 + MAXK) * 3], T[(6 + MAXK) * 3];
+    // visibility lists are in landmark-block order (build_visibility_index :784-831)
+    for (uint32_t k = 0; k < c.npts; ++k) {
+      uint32_t p = c.lm_order[k];
+      if (p < p0 || p >= p1) continue;
+      const double* hi = &hinv[(size_t)p * 9];
+      for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
+        uint32_t o = c.pt_obs[q], cam = c.obs_cam[o];
+        obs_E(c, c.lin[o], E);
+        for (int a = 0; a < dc; ++a) for (int j = 0; j < 3; ++j) T[a * 3 + j] = E[a * 3] * hi[j] + E[a * 3 + 1] * hi[3 + j] + E[a * 3 + 2] * hi[6 + j];
+        for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b)
+          spose[(size_t)cam * 36 + a * 6 + b] -= T[a * 3] * E[b * 3] + T[a * 3 + 1] * E[b * 3 + 1] + T[a * 3 + 2] * E[b * 3 + 2];
+        if (c.opt_intr)
+          for (int a = 0; a < K; ++a) for (int b = 0; b < K; ++b)
+            sintr[(size_t)cam * K * K + a * K + b] -= T[(6 + a) * 3] * E[(6 + b) * 3] + T[(6 + a) * 3 + 1] * E[(6 + b) * 3 + 1] + T[(6 + a) * 3 + 2] * E[(6 + b) * 3 + 2];
+      }
+    }
+  }
+  pinv_pose.assign((size_t)c.ncam * 36, 0.0);
+  pinv_intr.assign(sintr.size(), 0.0);
+  auto invert_block = [&](double* blk, int n, double* out) {
+    if (kind == APEX_PRECOND_NONE) { for (int a = 0; a < n * n; ++a) out[a] = 0.0; for (int a = 0; a < n; ++a) out[a * n + a] = 1.0; return; }
+    if (inverse_n(n, blk, out)) return;
+    double trace = 0.0;
+    for (int a = 0; a < n; ++a) trace += blk[a * n + a];
+    double reg = std::max(1e-6 * std::fabs(trace) / (double)n, 1e-8);
+    for (int a = 0; a < n; ++a) blk[a * n + a] += reg;
+    if (inverse_n(n, blk, out)) return;
+    for (int a = 0; a < n * n; ++a) out[a] = 0.0;
+    for (int a = 0; a < n; ++a) out[a * n + a] = 1.0;
+  };
+  for (uint32_t cam = 0; cam < c.ncam; ++cam) {
+    invert_block(&spose[(size_t)cam * 36], 6, &pinv_pose[(size_t)cam * 36]);
+    if (have_intr_vars) invert_block(&sintr[(size_t)cam * K * K], K, &pinv_intr[(size_t)cam * K * K]);
+  }
+}
+
+// Solution of one augmented system, in the structured layout of the C ABI.
+struct StepOut {
+  std::vector<double> cam;        // ncam*dc (pose|intr)
+  std::vector<double> intr_unref; // ncam*K zeros when intr variables exist but are not optimised
+  std::vector<double> pt;         // npts*3
+  double grad_norm = 0;           // || J^T r ||
+  double step_norm = 0;           // || step || over the full reference vector
+  double step_dot_grad = 0;       // step . (J^T r)
+  int pcg_iters = 0;
+};
+
+// SparseSchurComplementSolver::solve_augmented_equation (explicit_schur.rs:1129-1234), variants Sparse
+// (Cholesky) and Iterative-as-dispatched (scalar-Jacobi PCG on explicit S).
+apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol, double lambda, StepOut& out) {
+  if (!c.inv_exp_ok) { c.err = "Landmark block singular"; return APEX_ERR_SINGULAR_MATRIX; }
+  const int dc = c.dc;
+  const size_t n = c.cam_dof;
+  std::vector<double> s_dense(n * n, 0.0);
+  // damped H_cc into S (:1186-1205, :784-792); unreferenced intr columns only get lambda
+  for (uint32_t cam = 0; cam < c.ncam; ++cam) {
+    const double* H = &c.hcc[(size_t)cam * dc * dc];
+    for (int a = 0; a < dc; ++a)
+      for (int b = 0; b < dc; ++b) s_dense[cam_row(c, cam, a) * n + cam_row(c, cam, b)] += H[a * dc + b];
+  }
+  for (size_t i = 0; i < n; ++i) s_dense[i * n + i] += lambda;
+  // landmarks sequentially in block order (:800-898)
+  std::vector<CpRow> rows;
+  double E[(6 + MAXK) * 3];
+  std::vector<double> g_red(n);
+  // -g (:1152-1155, :1166): g_c, g_p are blocks of neg_gradient
+  for (uint32_t cam = 0; cam < c.ncam; ++cam)
+    for (int a = 0; a < dc; ++a) g_red[cam_row(c, cam, a)] = -c.gc[(size_t)cam * dc + a];
+
+  for (uint32_t k = 0; k < c.npts; ++k) {
+    uint32_t p = c.lm_order[k];
+    rows.clear();
+    for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
+      uint32_t o = c.pt_obs[q], cam = c.obs_cam[o];
+      obs_E(c, c.lin[o], E);
+      for (int a = 0; a < dc; ++a) rows.push_back({(uint32_t)cam_row(c, cam, a), {E[a * 3], E[a * 3 + 1], E[a * 3 + 2]}});
+    }
+    std::sort(rows.begin(), rows.end(), [](const CpRow& a, const CpRow& b) { return a.row < b.row; });
+    // merge duplicate rows (the sparse product J^T J sums duplicates)
+    size_t w = 0;
+    for (size_t i = 0; i < rows.size(); ++i) {
+      if (w > 0 && rows[w - 1].row == rows[i].row) { for (int t = 0; t < 3; ++t) rows[w - 1].v[t] += rows[i].v[t]; }
+      else rows[w++] = rows[i];
+    }
+    rows.resize(w);
+    const double* hi = &c.hpp_inv_exp[(size_t)p * 9];
+    schur_accumulate_landmark(s_dense.data(), n, rows.data(), rows.size(), hi);
+    // compute_reduced_gradient (:928-977): g_red = g_c - H_cp (Hpp^-1 g_p), with g = -J^T r
+    double gpn[3] = {-c.gp[(size_t)p * 3], -c.gp[(size_t)p * 3 + 1], -c.gp[(size_t)p * 3 + 2]};
+    double hg[3] = {hi[0] * gpn[0] + hi[1] * gpn[1] + hi[2] * gpn[2], hi[3] * gpn[0] + hi[4] * gpn[1] + hi[5] * gpn[2], hi[6] * gpn[0] + hi[7] * gpn[1] + hi[8] * gpn[2]};
+    for (auto& r : rows) g_red[r.row] -= r.v[0] * hg[0] + r.v[1] * hg[1] + r.v[2] * hg[2];
+  }
+  Csc S;
+  schur_symmetrize_and_sparsify(s_dense.data(), n, S);
+  std::vector<double>().swap(s_dense);
+  std::vector<double> delta_c(n, 0.0);
+  if (use_pcg) out.pcg_iters = solve_with_pcg(S, g_red.data(), delta_c.data(), cg_max_it, cg_tol);
+  else {
+    apex_status st = solve_with_cholesky(S, g_red.data(), delta_c.data(), c.err);
+    if (st != APEX_OK) return st;
+  }
+  // back_substitute (:980-1029): dp = Hpp^-1 (g_p - H_cp^T dc), g_p = -(J^T r)_p
+  out.cam.assign((size_t)c.ncam * dc, 0.0);
+  out.pt.assign((size_t)c.npts * 3, 0.0);
+  for (uint32_t cam = 0; cam < c.ncam; ++cam) for (int a = 0; a < dc; ++a) out.cam[(size_t)cam * dc + a] = delta_c[cam_row(c, cam, a)];
+  out.intr_unref.clear();
+  if (!c.opt_intr && c.intr_vars) {
+    out.intr_unref.assign((size_t)c.ncam * c.K, 0.0);
+    for (uint32_t cam = 0; cam < c.ncam; ++cam) for (int a = 0; a < c.K; ++a) out.intr_unref[(size_t)cam * c.K + a] = delta_c[c.col_intr[cam] + a];
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t p = 0; p < (int64_t)c.npts; ++p) {
+    double t[3] = {0, 0, 0};
+    double Eo[(6 + MAXK) * 3];
+    for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
+      uint32_t o = c.pt_obs[q];
+      obs_E(c, c.lin[o], Eo);
+      const double* xc = &out.cam[(size_t)c.obs_cam[o] * dc];
+      for (int a = 0; a < dc; ++a) for (int k2 = 0; k2 < 3; ++k2) t[k2] += Eo[a * 3 + k2] * xc[a];
+    }
+    double rhs[3] = {-c.gp[(size_t)p * 3] - t[0], -c.gp[(size_t)p * 3 + 1] - t[1], -c.gp[(size_t)p * 3 + 2] - t[2]};
+    const double* hi = &c.hpp_inv_exp[(size_t)p * 9];
+    for (int a = 0; a < 3; ++a) out.pt[(size_t)p * 3 + a] = hi[a * 3] * rhs[0] + hi[a * 3 + 1] * rhs[1] + hi[a * 3 + 2] * rhs[2];
+  }
+  return APEX_OK;
+}
+
+// IterativeSchurSolver::solve_augmented_equation -> solve_with_cached_hessian (implicit_schur.rs:1035-1085, 835-946)
+// wired with the +J^T r gradient convention LM expects: internally g = -J^T r.
+apex_status solve_implicit(Ctx& c, int precond_kind, int cg_max_it, double cg_tol, double lambda, StepOut& out) {
+  if (!c.inv_imp_ok) { c.err = "Landmark block singular"; return APEX_ERR_SINGULAR_MATRIX; }
+  const int dc = c.dc, K = c.K;
+  const size_t n = (size_t)c.ncam * dc;
+  const std::vector<double>& hinv = c.hpp_inv_imp;
+  // g_red = g_c - H_cp Hpp^-1 g_p (:863-880) in local camera-major layout
+  std::vector<double> b(n);
+  for (size_t i = 0; i < n; ++i) b[i] = -c.gc[i];
+  double E[(6 + MAXK) * 3];
+  for (uint32_t p = 0; p < c.npts; ++p) {
+    const double* hi = &hinv[(size_t)p * 9];
+    double g[3] = {-c.gp[(size_t)p * 3], -c.gp[(size_t)p * 3 + 1], -c.gp[(size_t)p * 3 + 2]};
+    double t[3] = {hi[0] * g[0] + hi[1] * g[1] + hi[2] * g[2], hi[3] * g[0] + hi[4] * g[1] + hi[5] * g[2], hi[6] * g[0] + hi[7] * g[1] + hi[8] * g[2]};
+    for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
+      uint32_t o = c.pt_obs[q];
+      obs_E(c, c.lin[o], E);
+      double* bc = &b[(size_t)c.obs_cam[o] * dc];
+      for (int a = 0; a < dc; ++a) bc[a] -= E[a * 3] * t[0] + E[a * 3 + 1] * t[1] + E[a * 3 + 2] * t[2];
+    }
+  }
+  std::vector<double> pinv_pose, pinv_intr;
+  build_preconditioner(c, precond_kind, lambda, hinv, 0, c.npts, pinv_pose, pinv_intr);
+  auto apply_precond = [&](const std::vector<double>& r, std::vector<double>& z) {  // :409-443
+    for (uint32_t cam = 0; cam < c.ncam; ++cam) {
+      const double* P = &pinv_pose[(size_t)cam * 36];
+      for (int a = 0; a < 6; ++a) {
+        double s = 0;
+        for (int bb = 0; bb < 6; ++bb) s += P[a * 6 + bb] * r[(size_t)cam * dc + bb];
+        z[(size_t)cam * dc + a] = s;
+      }
+      if (c.opt_intr) {
+        const double* Q = &pinv_intr[(size_t)cam * K * K];
+        for (int a = 0; a < K; ++a) {
+          double s = 0;
+          for (int bb = 0; bb < K; ++bb) s += Q[a * K + bb] * r[(size_t)cam * dc + 6 + bb];
+          z[(size_t)cam * dc + 6 + a] = s;
+        }
+      }
+    }
+  };
+  // solve_pcg_block (:577-679)
+  std::vector<double> x(n, 0.0), r(b), z(n), pvec(n), ap(n);
+  apply_precond(r, z);
+  pvec = z;
+  double rz_old = 0.0;
+  for (size_t i = 0; i < n; ++i) rz_old += r[i] * z[i];
+  double b_norm = 0.0;
+  for (size_t i = 0; i < n; ++i) b_norm += b[i] * b[i];
+  b_norm = std::sqrt(b_norm);
+  double tol = cg_tol * std::max(b_norm, 1.0);
+  int iters = 0;
+  for (int it = 0; it < cg_max_it; ++it) {
+    iters = it + 1;
+    std::fill(ap.begin(), ap.end(), 0.0);
+    schur_matvec_local(c, pvec.data(), ap.data(), lambda, 0, c.npts, true, hinv);
+    double p_ap = 0.0;
+    for (size_t i = 0; i < n; ++i) p_ap += pvec[i] * ap[i];
+    if (std::fabs(p_ap) < 1e-20) break;
+    double alpha = rz_old / p_ap;
+    for (size_t i = 0; i < n; ++i) x[i] += alpha * pvec[i];
+    for (size_t i = 0; i < n; ++i) r[i] -= alpha * ap[i];
+    double r_norm = 0.0;
+    for (size_t i = 0; i < n; ++i) r_norm += r[i] * r[i];
+    r_norm = std::sqrt(r_norm);
+    if (r_norm < tol) break;
+    apply_precond(r, z);
+    double rz_new = 0.0;
+    for (size_t i = 0; i < n; ++i) rz_new += r[i] * z[i];
+    if (std::fabs(rz_old) < 1e-30) break;
+    double beta = rz_new / rz_old;
+    for (size_t i = 0; i < n; ++i) pvec[i] = z[i] + beta * pvec[i];
+    rz_old = rz_new;
+  }
+  out.pcg_iters = iters;
+  out.cam = x;
+  out.intr_unref.clear();
+  if (!c.opt_intr && c.intr_vars) out.intr_unref.assign((size_t)c.ncam * K, 0.0);  // b = 0, x0 = 0 => stays 0
+  // back-substitution (:923-932)
+  out.pt.assign((size_t)c.npts * 3, 0.0);
+#pragma omp parallel for schedule(static)
+  for (int64_t p = 0; p < (int64_t)c.npts; ++p) {
+    double t[3] = {0, 0, 0};
+    double Eo[(6 + MAXK) * 3];
+    for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
+      uint32_t o = c.pt_obs[q];
+      obs_E(c, c.lin[o], Eo);
+      const double* xc = &x[(size_t)c.obs_cam[o] * dc];
+      for (int a = 0; a < dc; ++a) for (int k2 = 0; k2 < 3; ++k2) t[k2] += Eo[a * 3 + k2] * xc[a];
+    }
+    double rhs[3] = {-c.gp[(size_t)p * 3] - t[0], -c.gp[(size_t)p * 3 + 1] - t[1], -c.gp[(size_t)p * 3 + 2] - t[2]};
+    const double* hi = &hinv[(size_t)p * 9];
+    for (int a = 0; a < 3; ++a) out.pt[(size_t)p * 3 + a] = hi[a * 3] * rhs[0] + hi[a * 3 + 1] * rhs[1] + hi[a * 3 + 2] * rhs[2];
+  }
+  return APEX_OK;
+}
+
+apex_status solve_augmented(Ctx& c, int variant, int precond, int cg_max_it, double cg_tol, double lambda, StepOut& out) {
+  if (!c.linearized || c.lin_lambda != lambda) linearize(c, lambda);
+  apex_status st;
+  if (variant == APEX_SCHUR_IMPLICIT) st = solve_implicit(c, precond, cg_max_it, cg_tol, lambda, out);
+  else st = solve_explicit(c, variant == APEX_SCHUR_EXPLICIT_PCG, cg_max_it, cg_tol, lambda, out);
+  if (st != APEX_OK) return st;
+  // gradient = +J^T r (get_gradient, explicit_schur.rs:1158-1160); norms over the full vector
+  double g2 = 0, s2 = 0, sg = 0;
+  for (size_t i = 0; i < out.cam.size(); ++i) { g2 += c.gc[i] * c.gc[i]; s2 += out.cam[i] * out.cam[i]; sg += out.cam[i] * c.gc[i]; }
+  for (double v : out.intr_unref) s2 += v * v;
+  for (size_t i = 0; i < out.pt.size(); ++i) { g2 += c.gp[i] * c.gp[i]; s2 += out.pt[i] * out.pt[i]; sg += out.pt[i] * c.gp[i]; }
+  out.grad_norm = std::sqrt(g2);
+  out.step_norm = std::sqrt(s2);
+  out.step_dot_grad = sg;
+  c.last_pcg_iters = out.pcg_iters;
+  return APEX_OK;
+}
+
+// apply_parameter_step (src/optimizer/mod.rs:309-331) -> apply_tangent_step (src/core/problem.rs:185-289):
+// fixed tangent indices are zeroed here only; sign = -1 implements apply_negative_parameter_step (:343-356).
+void apply_step(Ctx& c, const StepOut& s, double sign) {
+  const int dc = c.dc, K = c.K;
+#pragma omp parallel for schedule(static)
+  for (int64_t cam = 0; cam < (int64_t)c.ncam; ++cam) {
+    double tau[6];
+    uint8_t fx = c.pose_fixed.empty() ? 0 : c.pose_fixed[cam];
+    for (int a = 0; a < 6; ++a) tau[a] = (fx >> a) & 1 ? 0.0 : sign * s.cam[(size_t)cam * dc + a];
+    Pose p;  // the variable holds an SE3 value; its quaternion is NOT renormalised between updates
+    p.t = {c.pose[7 * cam], c.pose[7 * cam + 1], c.pose[7 * cam + 2]};
+    p.q = {c.pose[7 * cam + 3], c.pose[7 * cam + 4], c.pose[7 * cam + 5], c.pose[7 * cam + 6]};
+    Pose np = pose_plus(p, tau);
+    pose_to7(np, &c.pose[7 * cam]);
+    if (c.opt_intr) {
+      uint16_t fi = c.intr_fixed.empty() ? 0 : c.intr_fixed[cam];
+      for (int a = 0; a < K; ++a) {
+        double d = (fi >> a) & 1 ? 0.0 : sign * s.cam[(size_t)cam * dc + 6 + a];
+        c.intr[(size_t)cam * K + a] += d;
+      }
+    } else if (!s.intr_unref.empty()) {
+      uint16_t fi = c.intr_fixed.empty() ? 0 : c.intr_fixed[cam];
+      for (int a = 0; a < K; ++a) {
+        double d = (fi >> a) & 1 ? 0.0 : sign * s.intr_unref[(size_t)cam * K + a];
+        c.intr[(size_t)cam * K + a] += d;
+      }
+    }
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t p = 0; p < (int64_t)c.npts; ++p) {
+    uint8_t fx = c.pt_fixed.empty() ? 0 : c.pt_fixed[p];
+    for (int a = 0; a < 3; ++a) {
+      double d = (fx >> a) & 1 ? 0.0 : sign * s.pt[(size_t)p * 3 + a];
+      c.pt[(size_t)p * 3 + a] += d;
+    }
+  }
+}
+
+// compute_parameter_norm (src/optimizer/mod.rs:458-467): SE3 contributes its 7-vector.
+double parameter_norm(const Ctx& c) {
+  double s = 0;
+  for (double v : c.pose) s += v * v;
+  if (c.opt_intr || c.intr_vars) for (double v : c.intr) s += v * v;
+  for (double v : c.pt) s += v * v;
+  return std::sqrt(s);
+}
+
+double now_seconds() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// LevenbergMarquardt::optimize -> optimize_with_mode (levenberg_marquardt.rs:1034-1083, 823-1028)
+apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, apex_iter_trace* trace, int trace_cap) {
+  if (c.nobs == 0) { c.err = "no residual blocks"; return APEX_ERR_NO_RESIDUAL_BLOCKS; }
+  double t0 = now_seconds();
+  double damping = cfg->damping, nu = cfg->damping_nu;
+  int iteration = 0, cost_evals = 1, jac_evals = 0, ok_steps = 0, bad_steps = 0;
+  int64_t lin_iters = 0;
+  // Variable::new(SE3::from(DVector)) normalises the initial quaternions (src/core/problem.rs:743-757)
+  for (uint32_t cam = 0; cam < c.ncam; ++cam) { Pose p = pose_from7(&c.pose[7 * (size_t)cam]); pose_to7(p, &c.pose[7 * (size_t)cam]); }
+  double current_cost = cost_at(c, c.pose, c.intr, c.pt);  // mod.rs:550-552
+  double initial_cost = current_cost, previous_cost = current_cost;
+  double final_gnorm = 0, final_snorm = 0;
+  for (;;) {
+    double it0 = now_seconds();
+    linearize(c, damping);
+    jac_evals++;
+    StepOut step;
+    apex_status st = solve_augmented(c, cfg->schur_variant, cfg->schur_preconditioner, cfg->cg_max_iterations, cfg->cg_tolerance, damping, step);
+    if (st != APEX_OK) return st == APEX_ERR_SINGULAR_MATRIX || st == APEX_ERR_FACTORIZATION_FAILED ? APEX_ERR_LINEAR_SOLVE_FAILED : st;
+    lin_iters += step.pcg_iters;
+    // compute_predicted_reduction (:721-727): 0.5 * step^T (damping*step - gradient)
+    double predicted = 0.5 * (damping * step.step_norm * step.step_norm - step.step_dot_grad);
+    final_gnorm = step.grad_norm;
+    final_snorm = step.step_norm;
+    // evaluate_and_apply_step (:770-817)
+    apply_step(c, step, +1.0);
+    double new_cost = cost_at(c, c.pose, c.intr, c.pt);
+    cost_evals++;
+    double rho = compute_step_quality(current_cost, new_cost, predicted);
+    bool accepted = update_damping(damping, nu, cfg->damping_min, cfg->damping_max, rho);
+    double cost_reduction = 0.0;
+    if (accepted) { cost_reduction = current_cost - new_cost; current_cost = new_cost; ok_steps++; }
+    else { apply_step(c, step, -1.0); bad_steps++; }
+    double elapsed = now_seconds() - t0;
+    double pnorm = parameter_norm(c);
+    if (trace && iteration < trace_cap) {
+      apex_iter_trace& t = trace[iteration];
+      t.iteration = iteration; t.accepted = accepted; t.ls_iter = step.pcg_iters; t.reserved = 0;
+      t.cost = current_cost; t.cost_change = previous_cost - current_cost; t.gradient_norm = step.grad_norm;
+      t.step_norm = step.step_norm; t.tr_ratio = rho; t.tr_radius = damping; t.new_cost = new_cost;
+      t.predicted_reduction = predicted; t.parameter_norm = pnorm; t.iter_time_ms = (now_seconds() - it0) * 1e3;
+    }
+    previous_cost = current_cost;
+    double cost_before = accepted ? current_cost + cost_reduction : current_cost;  // :946-950
+    ConvergenceParams cp{iteration, cost_before, current_cost, pnorm, step.step_norm, step.grad_norm, elapsed, accepted,
+                         cfg->max_iterations, cfg->gradient_tolerance, cfg->parameter_tolerance, cfg->cost_tolerance,
+                         cfg->min_cost_threshold, cfg->timeout_seconds, cfg->trust_region_radius, cfg->min_trust_region_radius};
+    int status = check_convergence(cp);
+    if (status >= 0) {
+      res->status = status; res->iterations = iteration + 1; res->initial_cost = initial_cost; res->final_cost = current_cost;
+      res->elapsed_seconds = elapsed; res->final_gradient_norm = final_gnorm; res->final_parameter_update_norm = final_snorm;
+      res->cost_evaluations = cost_evals; res->jacobian_evaluations = jac_evals; res->successful_steps = ok_steps;
+      res->unsuccessful_steps = bad_steps; res->final_damping = damping; res->final_damping_nu = nu; res->linear_iterations = lin_iters;
+      return APEX_OK;
+    }
+    iteration++;
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI (mirrors include/apex_gpu.h with the prefix oracle_) + unit-level entry points for the KATs
+// ================================================================================================
+extern "C" {
+
+struct oracle_ctx { Ctx c; };
+
+int32_t oracle_abi_version(void) { return 100; }
+int32_t oracle_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void oracle_set_num_threads(int32_t n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+void oracle_lm_config_default(apex_lm_config* cfg) { lm_config_default(cfg); }
+void oracle_lm_config_for_bundle_adjustment(apex_lm_config* cfg) {  // levenberg_marquardt.rs:519-530
+  lm_config_default(cfg);
+  cfg->schur_variant = APEX_SCHUR_EXPLICIT_PCG;  // SchurVariant::Iterative as dispatched today
+  cfg->schur_preconditioner = APEX_PRECOND_SCHUR_JACOBI;
+  cfg->damping = 1e-3; cfg->max_iterations = 20; cfg->cost_tolerance = 1e-6; cfg->parameter_tolerance = 1e-8; cfg->gradient_tolerance = 1e-10;
+}
+
+apex_status oracle_ctx_create(const apex_ctx_desc*, oracle_ctx** out) { *out = new oracle_ctx(); return APEX_OK; }
+void oracle_ctx_destroy(oracle_ctx* ctx) { delete ctx; }
+const char* oracle_last_error(const oracle_ctx* ctx) { return ctx->c.err.c_str(); }
+
+apex_status oracle_problem_upload(oracle_ctx* ctx, const apex_problem_desc* d) {
+  Ctx& c = ctx->c;
+  int K = model_intr_dim(d->camera_model);
+  if (K < 0) { c.err = "camera model not supported by the oracle"; return APEX_ERR_UNSUPPORTED; }
+  if (d->intr_dim != K) { c.err = "intr_dim does not match camera model"; return APEX_ERR_INVALID_INPUT; }
+  if ((d->opt_flags & (APEX_OPT_POSE | APEX_OPT_LANDMARK)) != (APEX_OPT_POSE | APEX_OPT_LANDMARK)) {
+    c.err = "only BundleAdjustment / SelfCalibration OptimizeParams are live (SURVEY §7)"; return APEX_ERR_UNSUPPORTED; }
+  if (d->ncam == 0) { c.err = "No camera variables found"; return APEX_ERR_INVALID_INPUT; }   // explicit_schur.rs:278-282
+  if (d->npts == 0) { c.err = "No landmark variables found"; return APEX_ERR_INVALID_INPUT; } // :283-287
+  c.model = d->camera_model; c.K = K; c.opt = d->opt_flags; c.intr_vars = d->intr_vars_present != 0;
+  c.ncam = d->ncam; c.npts = d->npts; c.nobs = d->nobs;
+  c.pose.assign(d->pose, d->pose + 7 * (size_t)c.ncam);
+  c.intr.assign(d->intr, d->intr + (size_t)K * c.ncam);
+  c.pt.assign(d->pt, d->pt + 3 * (size_t)c.npts);
+  c.obs_cam.assign(d->obs_cam, d->obs_cam + c.nobs);
+  c.obs_pt.assign(d->obs_pt, d->obs_pt + c.nobs);
+  c.uv.assign(d->obs_uv, d->obs_uv + 2 * c.nobs);
+  for (uint64_t o = 0; o < c.nobs; ++o)
+    if (c.obs_cam[o] >= c.ncam || c.obs_pt[o] >= c.npts) { c.err = "observation index out of range"; return APEX_ERR_INVALID_INPUT; }
+  c.loss_id = d->loss_id;
+  for (int i = 0; i < 4; ++i) c.loss_prm[i] = d->loss_params[i];
+  c.pose_fixed.clear(); c.intr_fixed.clear(); c.pt_fixed.clear();
+  if (d->pose_fixed) c.pose_fixed.assign(d->pose_fixed, d->pose_fixed + c.ncam);
+  if (d->intr_fixed) c.intr_fixed.assign(d->intr_fixed, d->intr_fixed + c.ncam);
+  if (d->pt_fixed) c.pt_fixed.assign(d->pt_fixed, d->pt_fixed + c.npts);
+  build_structure(c);
+  c.linearized = false;
+  return APEX_OK;
+}
+
+apex_status oracle_get_dims(const oracle_ctx* ctx, apex_dims* out) {
+  const Ctx& c = ctx->c;
+  out->ncam = c.ncam; out->npts = c.npts; out->nobs = c.nobs; out->intr_dim = c.K; out->dc = c.dc;
+  out->cam_dof = c.cam_dof; out->lm_dof = c.lm_dof; out->npts_local = c.npts; out->reserved = 0; out->nobs_local = c.nobs;
+  return APEX_OK;
+}
+
+apex_status oracle_params_upload(oracle_ctx* ctx, const double* pose, const double* intr, const double* pt) {
+  Ctx& c = ctx->c;
+  if (pose) c.pose.assign(pose, pose + 7 * (size_t)c.ncam);
+  if (intr) c.intr.assign(intr, intr + (size_t)c.K * c.ncam);
+  if (pt) c.pt.assign(pt, pt + 3 * (size_t)c.npts);
+  c.linearized = false;
+  return APEX_OK;
+}
+apex_status oracle_params_download(oracle_ctx* ctx, double* pose, double* intr, double* pt) {
+  Ctx& c = ctx->c;
+  if (pose) std::copy(c.pose.begin(), c.pose.end(), pose);
+  if (intr) std::copy(c.intr.begin(), c.intr.end(), intr);
+  if (pt) std::copy(c.pt.begin(), c.pt.end(), pt);
+  return APEX_OK;
+}
+
+apex_status oracle_linearize(oracle_ctx* ctx, double lambda) { linearize(ctx->c, lambda); return APEX_OK; }
+apex_status oracle_cost(oracle_ctx* ctx, double* cost) { *cost = cost_at(ctx->c, ctx->c.pose, ctx->c.intr, ctx->c.pt); return APEX_OK; }
+
+apex_status oracle_get_linearization(oracle_ctx* ctx, double* r, double* jc, double* jp) {
+  Ctx& c = ctx->c;
+  if (!c.linearized) { c.err = "not linearized"; return APEX_ERR_INVALID_STATE; }
+  for (uint64_t o = 0; o < c.nobs; ++o) {
+    const BlockLin& b = c.lin[o];
+    if (r) { r[2 * o] = b.r[0]; r[2 * o + 1] = b.r[1]; }
+    if (jc) obs_jc(c, b, &jc[o * 2 * c.dc]);
+    if (jp) for (int a = 0; a < 6; ++a) jp[o * 6 + a] = b.jpt[a];
+  }
+  return APEX_OK;
+}
+apex_status oracle_get_blocks(oracle_ctx* ctx, double* hcc, double* gc, double* hpp, double* gp, double* hpp_inv, int32_t implicit_flavour) {
+  Ctx& c = ctx->c;
+  if (!c.linearized) { c.err = "not linearized"; return APEX_ERR_INVALID_STATE; }
+  if (hcc) std::copy(c.hcc.begin(), c.hcc.end(), hcc);
+  if (gc) std::copy(c.gc.begin(), c.gc.end(), gc);
+  if (hpp) std::copy(c.hpp.begin(), c.hpp.end(), hpp);
+  if (gp) std::copy(c.gp.begin(), c.gp.end(), gp);
+  if (hpp_inv) { auto& v = implicit_flavour ? c.hpp_inv_imp : c.hpp_inv_exp; std::copy(v.begin(), v.end(), hpp_inv); }
+  return APEX_OK;
+}
+
+apex_status oracle_schur_matvec(oracle_ctx* ctx, const double* x, double* y) {
+  Ctx& c = ctx->c;
+  if (!c.linearized) { c.err = "not linearized"; return APEX_ERR_INVALID_STATE; }
+  size_t n = (size_t)c.ncam * c.dc;
+  for (size_t i = 0; i < n; ++i) y[i] = 0.0;
+  schur_matvec_local(c, x, y, c.lin_lambda, 0, c.npts, true, c.hpp_inv_imp);
+  return APEX_OK;
+}
+// Partial operator over the points [p0,p1) only — what one rank of the sharded path computes before the
+// all-reduce; the H_cc term is added by the caller exactly once (add_hcc).
+apex_status oracle_schur_matvec_partial(oracle_ctx* ctx, const double* x, double* y, uint32_t p0, uint32_t p1, int32_t add_hcc) {
+  Ctx& c = ctx->c;
+  if (!c.linearized) { c.err = "not linearized"; return APEX_ERR_INVALID_STATE; }
+  size_t n = (size_t)c.ncam * c.dc;
+  for (size_t i = 0; i < n; ++i) y[i] = 0.0;
+  schur_matvec_local(c, x, y, c.lin_lambda, p0, std::min(p1, c.npts), add_hcc != 0, c.hpp_inv_imp);
+  return APEX_OK;
+}
+
+apex_status oracle_solve_augmented(oracle_ctx* ctx, int32_t variant, int32_t precond, int32_t cg_max_it, double cg_tol, double lambda,
+                                   double* step_cam, double* step_pt, double* grad_norm, int32_t* pcg_iters) {
+  Ctx& c = ctx->c;
+  StepOut s;
+  apex_status st = solve_augmented(c, variant, precond, cg_max_it, cg_tol, lambda, s);
+  if (st != APEX_OK) return st;
+  if (step_cam) std::copy(s.cam.begin(), s.cam.end(), step_cam);
+  if (step_pt) std::copy(s.pt.begin(), s.pt.end(), step_pt);
+  if (grad_norm) *grad_norm = s.grad_norm;
+  if (pcg_iters) *pcg_iters = s.pcg_iters;
+  return APEX_OK;
+}
+
+apex_status oracle_lm_solve(oracle_ctx* ctx, const apex_lm_config* cfg, apex_lm_result* result, apex_iter_trace* trace, int32_t trace_cap) {
+  return lm_solve(ctx->c, cfg, result, trace, trace_cap);
+}
+
+// Reference-layout column offsets (sorted variable names), for tests of the ordering quirk.
+apex_status oracle_get_column_layout(const oracle_ctx* ctx, uint64_t* col_pose, uint64_t* col_intr, uint64_t* col_pt) {
+  const Ctx& c = ctx->c;
+  for (uint32_t i = 0; i < c.ncam; ++i) { if (col_pose) col_pose[i] = c.col_pose[i]; if (col_intr) col_intr[i] = c.col_intr[i]; }
+  if (col_pt) for (uint32_t i = 0; i < c.npts; ++i) col_pt[i] = c.cam_dof + c.col_pt[i];
+  return APEX_OK;
+}
+
+// ---- unit-level entry points (ported reference KATs call these) --------------------------------
+void oracle_loss_evaluate(int32_t id, const double* prm, double s, double* rho3) { loss_evaluate(id, prm, s, rho3); }
+void oracle_corrector(int32_t id, const double* prm, double sq_norm, double* out3) {
+  Corrector c = corrector_new(id, prm, sq_norm);
+  out3[0] = c.sqrt_rho1; out3[1] = c.residual_scaling; out3[2] = c.alpha_sq_norm;
+}
+int32_t oracle_camera_intr_dim(int32_t model) { return model_intr_dim(model); }
+int32_t oracle_project(int32_t model, const double* intr, const double* p, double* uv) { return cam_project(model, intr, {p[0], p[1], p[2]}, uv) ? 1 : 0; }
+void oracle_jacobian_point(int32_t model, const double* intr, const double* p, double* J6) { cam_jacobian_point(model, intr, {p[0], p[1], p[2]}, J6); }
+void oracle_jacobian_intrinsics(int32_t model, const double* intr, const double* p, double* J) { cam_jacobian_intrinsics(model, intr, {p[0], p[1], p[2]}, J); }
+void oracle_se3_normalize(const double* pose7, double* out7) { Pose p = pose_from7(pose7); pose_to7(p, out7); }
+void oracle_se3_act(const double* pose7, const double* p, double* out3) {
+  Pose ps = pose_from7(pose7); V3 r = pose_act(ps, {p[0], p[1], p[2]}); out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+void oracle_se3_plus(const double* pose7, const double* tau6, double* out7) { Pose ps = pose_from7(pose7); pose_to7(pose_plus(ps, tau6), out7); }
+void oracle_rotation_matrix(const double* q4_wxyz, double* R9) { quat_to_matrix(quat_normalize({q4_wxyz[0], q4_wxyz[1], q4_wxyz[2], q4_wxyz[3]}), R9); }
+// One residual block: r[2], J row-major 2 x (6+3+K) in the factor's column order [pose | landmark | intrinsics]
+// (projection_factor.rs:197-207); loss_id = APEX_LOSS_NONE gives the raw factor output.
+void oracle_linearize_block(int32_t model, uint32_t opt_flags, int32_t loss_id, const double* loss_prm, const double* pose7, const double* pt3,
+                            const double* intr, const double* uv, double* r2, double* J) {
+  int K = model_intr_dim(model);
+  bool oi = (opt_flags & APEX_OPT_INTRINSIC) != 0;
+  BlockLin b;
+  linearize_obs(model, K, oi, loss_id, loss_prm, pose_from7(pose7), intr, {pt3[0], pt3[1], pt3[2]}, uv, true, b);
+  r2[0] = b.r[0]; r2[1] = b.r[1];
+  int nc = 9 + (oi ? K : 0);
+  for (int r = 0; r < 2; ++r) {
+    for (int k = 0; k < 6; ++k) J[r * nc + k] = b.jpose[r * 6 + k];
+    for (int k = 0; k < 3; ++k) J[r * nc + 6 + k] = b.jpt[r * 3 + k];
+    if (oi) for (int k = 0; k < K; ++k) J[r * nc + 9 + k] = b.jintr[r * K + k];
+  }
+}
+int32_t oracle_invert_landmark_block(const double* block9, double lambda_arg, int32_t implicit_flavour, double* inv9) {
+  return invert_landmark_block(block9, lambda_arg, implicit_flavour != 0, inv9) ? 1 : 0;
+}
+int32_t oracle_inverse_n(int32_t n, const double* m, double* out) { return inverse_n(n, m, out) ? 1 : 0; }
+// compute_schur_complement / compute_reduced_gradient / back_substitute on DENSE inputs:
+// hcc[cam^2] row-major, hcp[cam x 3*nlm] row-major, hpp_inv[nlm][9], g_c[cam], g_p[3*nlm].
+void oracle_schur_complement_dense(uint32_t cam, uint32_t nlm, const double* hcc, const double* hcp, const double* hpp_inv, double* s_out) {
+  std::vector<double> s(hcc, hcc + (size_t)cam * cam);
+  std::vector<CpRow> rows;
+  for (uint32_t l = 0; l < nlm; ++l) {
+    rows.clear();
+    for (uint32_t r = 0; r < cam; ++r) {
+      const double* v = &hcp[(size_t)r * 3 * nlm + 3 * l];
+      if (v[0] != 0.0 || v[1] != 0.0 || v[2] != 0.0) rows.push_back({r, {v[0], v[1], v[2]}});
+    }
+    schur_accumulate_landmark(s.data(), cam, rows.data(), rows.size(), &hpp_inv[9 * (size_t)l]);
+  }
+  Csc S;
+  schur_symmetrize_and_sparsify(s.data(), cam, S);
+  std::fill(s_out, s_out + (size_t)cam * cam, 0.0);
+  for (size_t c = 0; c < cam; ++c) for (size_t p = S.colptr[c]; p < S.colptr[c + 1]; ++p) s_out[(size_t)S.row[p] * cam + c] = S.val[p];
+}
+void oracle_reduced_gradient_dense(uint32_t cam, uint32_t nlm, const double* g_c, const double* g_p, const double* hcp, const double* hpp_inv, double* out) {
+  std::vector<double> t(3 * (size_t)nlm);
+  for (uint32_t l = 0; l < nlm; ++l) {
+    const double* hi = &hpp_inv[9 * (size_t)l];
+    for (int a = 0; a < 3; ++a) t[3 * l + a] = hi[a * 3] * g_p[3 * l] + hi[a * 3 + 1] * g_p[3 * l + 1] + hi[a * 3 + 2] * g_p[3 * l + 2];
+  }
+  for (uint32_t r = 0; r < cam; ++r) {
+    double s = 0;
+    for (size_t k = 0; k < 3 * (size_t)nlm; ++k) s += hcp[(size_t)r * 3 * nlm + k] * t[k];
+    out[r] = g_c[r] - s;
+  }
+}
+void oracle_back_substitute_dense(uint32_t cam, uint32_t nlm, const double* delta_c, const double* g_p, const double* hcp, const double* hpp_inv, double* delta_p) {
+  for (uint32_t l = 0; l < nlm; ++l) {
+    double rhs[3];
+    for (int a = 0; a < 3; ++a) {
+      double s = 0;
+      for (uint32_t r = 0; r < cam; ++r) s += hcp[(size_t)r * 3 * nlm + 3 * l + a] * delta_c[r];
+      rhs[a] = g_p[3 * l + a] - s;
+    }
+    const double* hi = &hpp_inv[9 * (size_t)l];
+    for (int a = 0; a < 3; ++a) delta_p[3 * l + a] = hi[a * 3] * rhs[0] + hi[a * 3 + 1] * rhs[1] + hi[a * 3 + 2] * rhs[2];
+  }
+}
+static void dense_to_csc(uint32_t n, const double* a, Csc& S) {
+  S.n = n; S.colptr.assign(n + 1, 0); S.row.clear(); S.val.clear();
+  for (uint32_t c = 0; c < n; ++c) {
+    for (uint32_t r = 0; r < n; ++r) if (a[(size_t)r * n + c] != 0.0) { S.row.push_back(r); S.val.push_back(a[(size_t)r * n + c]); }
+    S.colptr[c + 1] = S.row.size();
+  }
+}
+apex_status oracle_solve_cholesky_dense(uint32_t n, const double* a, const double* b, double* x) {
+  Csc S; dense_to_csc(n, a, S); std::string err; return solve_with_cholesky(S, b, x, err);
+}
+int32_t oracle_solve_pcg_dense(uint32_t n, const double* a, const double* b, double* x, int32_t max_it, double tol) {
+  Csc S; dense_to_csc(n, a, S); return solve_with_pcg(S, b, x, max_it, tol);
+}
+double oracle_compute_cost(const double* r, uint64_t n) { return compute_cost(r, n); }
+double oracle_compute_step_quality(double cur, double nw, double pred) { return compute_step_quality(cur, nw, pred); }
+int32_t oracle_update_damping(double* damping, double* nu, double dmin, double dmax, double rho) { return update_damping(*damping, *nu, dmin, dmax, rho) ? 1 : 0; }
+// check_convergence with the fields of ConvergenceParams; returns -1 for None.
+int32_t oracle_check_convergence(int32_t iteration, double current_cost, double new_cost, double parameter_norm, double parameter_update_norm,
+                                 double gradient_norm, double elapsed, int32_t step_accepted, int32_t max_iterations, double gradient_tolerance,
+                                 double parameter_tolerance, double cost_tolerance, double min_cost_threshold, double timeout,
+                                 double trust_region_radius, double min_trust_region_radius) {
+  ConvergenceParams p{iteration, current_cost, new_cost, parameter_norm, parameter_update_norm, gradient_norm, elapsed, step_accepted != 0,
+                      max_iterations, gradient_tolerance, parameter_tolerance, cost_tolerance, min_cost_threshold, timeout, trust_region_radius,
+                      min_trust_region_radius};
+  return check_convergence(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,512 @@
+"""Pins the TEST ORACLE against the reference's own known-answer tests.
+
+Each test names the reference test it ports (file:line, relative to the reference repo) and uses the same
+inputs, expected values and tolerances.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from apex_solver_b200 import _ffi as F
+from oracle_backend import oracle_lib
+
+L = oracle_lib()
+NAN = float("nan")
+
+
+def arr(*v):
+    return np.array(v, dtype=np.float64)
+
+
+def loss_eval(lid, prm, s):
+    p = arr(*(list(prm) + [0.0] * (4 - len(prm))))
+    out = np.zeros(3)
+    L.oracle_loss_evaluate(lid, F.ptr(p), float(s), F.ptr(out))
+    return out
+
+
+def corrector(lid, prm, s):
+    p = arr(*(list(prm) + [0.0] * (4 - len(prm))))
+    out = np.zeros(3)
+    L.oracle_corrector(lid, F.ptr(p), float(s), F.ptr(out))
+    return out  # sqrt_rho1, residual_scaling, alpha_sq_norm
+
+
+def project(model, intr, p):
+    intr, p = arr(*intr), arr(*p)
+    uv = np.zeros(2)
+    ok = L.oracle_project(model, F.ptr(intr), F.ptr(p), F.ptr(uv))
+    return ok, uv
+
+
+def jac_point(model, intr, p):
+    intr, p = arr(*intr), arr(*p)
+    J = np.zeros(6)
+    L.oracle_jacobian_point(model, F.ptr(intr), F.ptr(p), F.ptr(J))
+    return J.reshape(2, 3)
+
+
+def jac_intr(model, intr, p):
+    intr, p = arr(*intr), arr(*p)
+    K = F.CAM_INTR_DIM[model]
+    J = np.zeros(2 * K)
+    L.oracle_jacobian_intrinsics(model, F.ptr(intr), F.ptr(p), F.ptr(J))
+    return J.reshape(2, K)
+
+
+def se3_plus(pose, tau):
+    pose, tau = arr(*pose), arr(*tau)
+    out = np.zeros(7)
+    L.oracle_se3_plus(F.ptr(pose), F.ptr(tau), F.ptr(out))
+    return out
+
+
+def se3_act(pose, p):
+    pose, p = arr(*pose), arr(*p)
+    out = np.zeros(3)
+    L.oracle_se3_act(F.ptr(pose), F.ptr(p), F.ptr(out))
+    return out
+
+
+def linearize_block(model, opt, loss, pose, pt, intr, uv):
+    lid, prm = loss
+    prm = arr(*(list(prm) + [0.0] * (4 - len(prm))))
+    pose, pt, intr, uv = arr(*pose), arr(*pt), arr(*intr), arr(*uv)
+    K = F.CAM_INTR_DIM[model]
+    nc = 9 + (K if opt & F.OPT_INTRINSIC else 0)
+    r = np.zeros(2)
+    J = np.zeros(2 * nc)
+    L.oracle_linearize_block(model, opt, lid, F.ptr(prm), F.ptr(pose), F.ptr(pt), F.ptr(intr), F.ptr(uv), F.ptr(r), F.ptr(J))
+    return r, J.reshape(2, nc)
+
+
+# ---------------------------------------------------------------------------------------------
+# optimizer/mod.rs
+# ---------------------------------------------------------------------------------------------
+def test_compute_cost():  # src/optimizer/mod.rs:992-1000: compute_cost([1,2]) = 2.5
+    r = arr(1.0, 2.0)
+    assert abs(L.oracle_compute_cost(F.ptr(r), 2) - 2.5) < 1e-15
+
+
+def test_compute_step_quality():  # src/optimizer/mod.rs:1003-1035
+    assert abs(L.oracle_compute_step_quality(10.0, 8.0, 4.0) - 0.5) < 1e-12
+    assert L.oracle_compute_step_quality(10.0, 8.0, 1e-20) == 1.0   # near-zero predicted, cost decreased
+    assert L.oracle_compute_step_quality(10.0, 12.0, 1e-20) == 0.0  # near-zero predicted, cost increased
+    assert abs(L.oracle_compute_step_quality(10.0, 12.0, 2.0) - (-1.0)) < 1e-12
+
+
+def conv(**kw):
+    d = dict(iteration=5, current_cost=1.0, new_cost=0.5, parameter_norm=10.0, parameter_update_norm=1.0, gradient_norm=1.0,
+             elapsed=0.0, step_accepted=1, max_iterations=100, gradient_tolerance=1e-10, parameter_tolerance=1e-8,
+             cost_tolerance=1e-6, min_cost_threshold=NAN, timeout=0.0, trust_region_radius=1e4, min_trust_region_radius=1e-32)
+    d.update(kw)
+    return L.oracle_check_convergence(d["iteration"], d["current_cost"], d["new_cost"], d["parameter_norm"], d["parameter_update_norm"],
+                                      d["gradient_norm"], d["elapsed"], d["step_accepted"], d["max_iterations"], d["gradient_tolerance"],
+                                      d["parameter_tolerance"], d["cost_tolerance"], d["min_cost_threshold"], d["timeout"],
+                                      d["trust_region_radius"], d["min_trust_region_radius"])
+
+
+def test_check_convergence_branches():  # src/optimizer/mod.rs:1184-1332, one case per branch
+    assert conv() == -1                                                     # nothing met
+    assert conv(new_cost=NAN) == 11                                         # InvalidNumericalValues
+    assert conv(parameter_update_norm=float("inf")) == 11
+    assert conv(gradient_norm=NAN) == 11
+    assert conv(timeout=1.0, elapsed=2.0) == 7                              # Timeout
+    assert conv(iteration=100) == 1                                         # MaxIterationsReached
+    assert conv(gradient_norm=1e-12) == 4                                   # GradientToleranceReached
+    assert conv(gradient_norm=1e-12, step_accepted=0) == -1                 # not accepted => criteria skipped
+    assert conv(parameter_update_norm=1e-12) == 3                           # ParameterToleranceReached
+    assert conv(parameter_update_norm=1e-12, iteration=0) == -1             # only after the first iteration
+    assert conv(current_cost=1.0, new_cost=1.0 - 1e-9) == 2                 # CostToleranceReached
+    assert conv(min_cost_threshold=0.6) == 9                                # MinCostThresholdReached
+    assert conv(trust_region_radius=1e-40) == 8                             # TrustRegionRadiusTooSmall
+    # order: non-finite beats max-iterations, max-iterations beats gradient
+    assert conv(iteration=100, new_cost=NAN) == 11
+    assert conv(iteration=100, gradient_norm=0.0) == 1
+
+
+def test_update_damping():  # src/optimizer/levenberg_marquardt.rs:1566-1618
+    lam, nu = C.c_double(1e-3), C.c_double(4.0)
+    assert L.oracle_update_damping(C.byref(lam), C.byref(nu), 1e-12, 1e12, 0.8) == 1
+    assert lam.value < 1e-3 and nu.value == 2.0
+    assert abs(lam.value - 1e-3 * max(1 / 3, 1 - 0.6 ** 3)) < 1e-18
+    lam, nu = C.c_double(1e-3), C.c_double(2.0)
+    assert L.oracle_update_damping(C.byref(lam), C.byref(nu), 1e-12, 1e12, -0.5) == 0
+    assert lam.value == 2e-3 and nu.value == 4.0
+    lam, nu = C.c_double(1e-12), C.c_double(2.0)   # clamp at damping_min
+    L.oracle_update_damping(C.byref(lam), C.byref(nu), 1e-12, 1e12, 0.5)
+    assert lam.value == 1e-12
+    lam, nu = C.c_double(9e11), C.c_double(8.0)    # clamp at damping_max
+    L.oracle_update_damping(C.byref(lam), C.byref(nu), 1e-12, 1e12, -1.0)
+    assert lam.value == 1e12 and nu.value == 16.0
+    # rho == 0 is a rejection (acceptance is strictly rho > 0, :703)
+    lam, nu = C.c_double(1.0), C.c_double(2.0)
+    assert L.oracle_update_damping(C.byref(lam), C.byref(nu), 1e-12, 1e12, 0.0) == 0
+
+
+def test_lm_for_bundle_adjustment_preset():  # src/optimizer/levenberg_marquardt.rs:1339-1347, :319-359, :519-530
+    cfg = F.LmConfig()
+    L.oracle_lm_config_for_bundle_adjustment(C.byref(cfg))
+    assert cfg.max_iterations == 20 and cfg.damping == 1e-3
+    assert cfg.cost_tolerance == 1e-6 and cfg.parameter_tolerance == 1e-8 and cfg.gradient_tolerance == 1e-10
+    assert cfg.schur_preconditioner == F.PRECOND_SCHUR_JACOBI
+    assert cfg.cg_max_iterations == 200 and cfg.cg_tolerance == 1e-6
+    L.oracle_lm_config_default(C.byref(cfg))
+    assert cfg.max_iterations == 50 and cfg.damping_min == 1e-12 and cfg.damping_max == 1e12 and cfg.damping_nu == 2.0
+    assert cfg.trust_region_radius == 1e4 and cfg.min_trust_region_radius == 1e-32 and math.isnan(cfg.min_cost_threshold)
+    assert cfg.schur_variant == F.SCHUR_EXPLICIT and cfg.use_jacobi_scaling == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# core/loss_functions.rs, core/corrector.rs
+# ---------------------------------------------------------------------------------------------
+def test_corrector_huber_inlier_outlier():  # src/core/corrector.rs:309-391
+    c = corrector(F.LOSS_HUBER, [1.0], 0.25)        # inlier: sqrt(rho')=1, alpha=0
+    assert abs(c[0] - 1.0) < 1e-10 and abs(c[1] - 1.0) < 1e-10 and c[2] == 0.0
+    c = corrector(F.LOSS_HUBER, [1.0], 100.0)       # outlier: 0 < sqrt(rho') < 1
+    assert 0.0 < c[0] < 1.0 and c[2] == 0.0 and c[1] == c[0]
+    assert abs(c[0] - math.sqrt(1.0 / 10.0)) < 1e-15
+    c = corrector(F.LOSS_CAUCHY, [1.0], 4.0)
+    assert 0.0 < c[0] < 1.0 and abs(c[0] - math.sqrt(1 / 5.0)) < 1e-15
+    c = corrector(F.LOSS_HUBER, [1.0], 0.0)         # s == 0 short-circuit
+    assert c[0] == 1.0 and c[2] == 0.0
+
+
+def test_loss_weight_ordering():  # src/core/loss_functions.rs:1901-1921
+    s = 100.0
+    w_l2 = loss_eval(F.LOSS_L2, [], s)[1]
+    w_h = loss_eval(F.LOSS_HUBER, [1.345], s)[1]
+    w_c = loss_eval(F.LOSS_CAUCHY, [2.3849], s)[1]
+    assert w_l2 > w_h > w_c and w_c < 0.1
+
+
+LOSS_CASES = [
+    (F.LOSS_L2, []), (F.LOSS_L1, []), (F.LOSS_HUBER, [1.3]), (F.LOSS_CAUCHY, [2.0]), (F.LOSS_FAIR, [1.4]),
+    (F.LOSS_GEMAN_MCCLURE, [2.0]), (F.LOSS_WELSCH, [2.5]), (F.LOSS_TUKEY, [4.0]), (F.LOSS_ANDREWS, [1.5]),
+    (F.LOSS_RAMSAY_EA, [0.3]), (F.LOSS_LP_NORM, [1.5]), (F.LOSS_BARRON, [1.0, 1.5]), (F.LOSS_BARRON, [0.0, 2.0]),
+    (F.LOSS_BARRON, [-2.0, 1.0]), (F.LOSS_T_DISTRIBUTION, [5.0]),
+]
+
+
+# The reference's own rho''(s) differs from d(rho')/ds for these (FairLoss :603 uses 4s instead of 4*sqrt(s);
+# TukeyBiweightLoss :865 carries an extra `ratio`; BarronGeneralLoss :1350-1351 lacks |alpha|/2). The oracle
+# restates the reference AS WRITTEN - the corrector only looks at the sign of rho'' for them anyway.
+REFERENCE_INCONSISTENT = {(F.LOSS_FAIR, (1.4,)), (F.LOSS_TUKEY, (4.0,)), (F.LOSS_BARRON, (1.0, 1.5)), (F.LOSS_BARRON, (-2.0, 1.0))}
+
+
+def test_loss_reference_formulas_as_written():
+    s = 0.5
+    x = math.sqrt(s)
+    assert np.allclose(loss_eval(F.LOSS_FAIR, [1.4], s), [1.4 ** 2 * (x / 1.4 - math.log(1 + x / 1.4)), 0.5 / (1.4 + x), -1 / (4 * s * (1.4 + x) ** 2)], rtol=1e-14)
+    ratio = x / 4.0
+    om = 1 - ratio * ratio
+    assert np.allclose(loss_eval(F.LOSS_TUKEY, [4.0], s), [(16 / 6) * (1 - om ** 3), 0.5 * om * om, -(ratio / 16) * om], rtol=1e-14)
+    inner = 0.5 * (x / 1.5) ** 2 + 1
+    assert np.allclose(loss_eval(F.LOSS_BARRON, [1.0, 1.5], s), [(1 / 2.25) * (inner ** 0.5 - 1), 0.5 * inner ** -0.5, (-1 / 9.0) * inner ** -1.5], rtol=1e-14)
+
+
+@pytest.mark.parametrize("lid,prm", LOSS_CASES)
+def test_loss_second_derivative_matches_numerical_derivative_of_first(lid, prm):
+    # same idea as numerical_derivative (src/core/loss_functions.rs:1592-1604), applied to rho' -> rho''
+    # (several reference losses scale rho differently from rho', so only rho'/rho'' are mutually consistent)
+    if (lid, tuple(prm)) in REFERENCE_INCONSISTENT:
+        pytest.skip("the reference's rho'' is not d(rho')/ds for this loss; restated as written, see test_loss_reference_formulas_as_written")
+    for s in (0.5, 2.0, 7.0):
+        h = 1e-6 * s
+        r0, rp, rm = loss_eval(lid, prm, s), loss_eval(lid, prm, s + h), loss_eval(lid, prm, s - h)
+        num = (rp[1] - rm[1]) / (2 * h)
+        if lid == F.LOSS_HUBER and abs(s - prm[0] ** 2) < 1e-3:
+            continue
+        assert abs(num - r0[2]) <= 1e-5 * max(1.0, abs(r0[2])), (lid, s, num, r0[2])
+
+
+def test_loss_exact_values():
+    # closed forms straight from the reference bodies (loss_functions.rs:364-383, 497-509, 1132-1141, 848-869)
+    assert np.allclose(loss_eval(F.LOSS_HUBER, [2.0], 9.0), [2 * 2 * 3 - 4, 2 / 3, -(2 / 3) / 18], rtol=0, atol=1e-15)
+    assert np.allclose(loss_eval(F.LOSS_HUBER, [2.0], 4.0), [4.0, 1.0, 0.0])  # s == delta^2 is an inlier
+    assert np.allclose(loss_eval(F.LOSS_CAUCHY, [2.0], 4.0), [4 * math.log(2.0) / 2, 0.5, -0.25 * 0.25], atol=1e-15)
+    assert np.allclose(loss_eval(F.LOSS_TRIMMED_MEAN, [2.0], 3.0), [1.5, 0.5, 0.0])
+    assert np.allclose(loss_eval(F.LOSS_TRIMMED_MEAN, [2.0], 5.0), [2.0, 0.0, 0.0])
+    assert np.allclose(loss_eval(F.LOSS_TUKEY, [2.0], 9.0), [4 / 6, 0.0, 0.0])
+    c = corrector(F.LOSS_TUKEY, [2.0], 9.0)   # rho' = 0 => residual and Jacobian are zeroed
+    assert c[0] == 0.0 and c[1] == 0.0 and c[2] == 0.0
+
+
+def test_corrector_second_branch_andrews():
+    # Andrews has rho'' > 0 (loss_functions.rs:951-970) => Corrector::new takes the alpha branch (corrector.rs:164-181)
+    s = 1.0
+    rho = loss_eval(F.LOSS_ANDREWS, [1.5], s)
+    assert rho[2] > 0
+    c = corrector(F.LOSS_ANDREWS, [1.5], s)
+    d = max(1 + 2 * s * rho[2] / rho[1], 0.0)
+    alpha = 1 - math.sqrt(d)
+    assert abs(c[0] - math.sqrt(rho[1])) < 1e-15
+    assert abs(c[1] - math.sqrt(rho[1]) / (1 - alpha)) < 1e-15
+    assert abs(c[2] - alpha / s) < 1e-15 and c[2] != 0.0
+    # full Jacobian correction: J~ = sqrt(rho') (J - alpha/s r r^T J)
+    r0, J0 = linearize_block(F.CAM_PINHOLE, 7, (F.LOSS_NONE, []), [0, 0, 0, 1, 0, 0, 0], [0.1, 0.2, 1.0], [500, 500, 320, 240], [369.6, 340.8])
+    s = float(r0 @ r0)
+    cc = corrector(F.LOSS_ANDREWS, [1.5], s)
+    r1, J1 = linearize_block(F.CAM_PINHOLE, 7, (F.LOSS_ANDREWS, [1.5]), [0, 0, 0, 1, 0, 0, 0], [0.1, 0.2, 1.0], [500, 500, 320, 240], [369.6, 340.8])
+    assert cc[2] != 0.0
+    assert np.allclose(J1, cc[0] * (J0 - cc[2] * np.outer(r0, r0) @ J0), rtol=1e-13, atol=1e-13)
+    assert np.allclose(r1, cc[1] * r0, rtol=1e-14)
+
+
+# ---------------------------------------------------------------------------------------------
+# camera models
+# ---------------------------------------------------------------------------------------------
+def test_bal_projection_kats():  # crates/apex-camera-models/src/bal_pinhole.rs:818-844, 957-962
+    ok, uv = project(F.CAM_BAL, [500.0, 0.0, 0.0], [0.0, 0.0, -1.0])
+    assert ok and np.allclose(uv, [0.0, 0.0], atol=1e-10)
+    ok, uv = project(F.CAM_BAL, [500.0, 0.0, 0.0], [0.1, 0.2, -1.0])
+    assert ok and np.allclose(uv, [50.0, 100.0], atol=1e-10)
+    ok, _ = project(F.CAM_BAL, [500.0, 0.0, 0.0], [0.0, 0.0, 1.0])   # behind camera => Err
+    assert not ok
+    ok, _ = project(F.CAM_BAL, [500.0, 0.0, 0.0], [0.0, 0.0, -1e-7])  # z >= -MIN_DEPTH => Err
+    assert not ok
+
+
+def test_kb_ds_pinhole_center_projection():  # kannala_brandt.rs:900-917, double_sphere.rs:808-823, pinhole tests
+    ok, uv = project(F.CAM_KANNALA_BRANDT, [300, 300, 320, 240, 0.1, 0.01, 0.001, 0.0001], [0, 0, 1.0])
+    assert ok and np.allclose(uv, [320, 240], atol=1e-10)
+    ok, uv = project(F.CAM_DOUBLE_SPHERE, [300, 300, 320, 240, -0.2, 0.6], [0, 0, 1.0])
+    assert ok and np.allclose(uv, [320, 240], atol=1e-10)
+    ok, uv = project(F.CAM_PINHOLE, [500, 500, 320, 240], [0.1, 0.2, 1.0])
+    assert ok and np.allclose(uv, [370.0, 340.0], atol=1e-10)
+    assert not project(F.CAM_PINHOLE, [500, 500, 320, 240], [0.1, 0.2, -1.0])[0]
+    assert not project(F.CAM_KANNALA_BRANDT, [300, 300, 320, 240, 0.1, 0.01, 0.001, 0.0001], [0, 0, -1.0])[0]
+
+
+CAMS = [
+    (F.CAM_BAL, [500.0, 1e-3, -2e-4], [0.1, 0.2, -1.0]),
+    (F.CAM_BAL, [800.0, -0.05, 0.01], [-0.7, 0.4, -2.5]),
+    (F.CAM_PINHOLE, [500.0, 510.0, 320.0, 240.0], [0.1, 0.2, 1.0]),
+    (F.CAM_KANNALA_BRANDT, [300.0, 300.0, 320.0, 240.0, 0.1, 0.01, 0.001, 0.0001], [0.1, 0.2, 1.0]),
+    (F.CAM_DOUBLE_SPHERE, [300.0, 300.0, 320.0, 240.0, -0.2, 0.6], [0.1, 0.2, 1.0]),
+    (F.CAM_DOUBLE_SPHERE, [200.0, 200.0, 300.0, 200.0, 0.5, 0.5], [-0.4, 0.3, 1.5]),
+]
+
+
+@pytest.mark.parametrize("model,intr,p", CAMS)
+def test_jacobian_point_vs_central_differences(model, intr, p):
+    # bal_pinhole.rs:904-954, kannala_brandt.rs:919-1005, double_sphere.rs:825-907: eps 1e-7, tol 1e-5 (lib.rs:56-80)
+    J = jac_point(model, intr, p)
+    eps = 1e-7
+    for k in range(3):
+        d = np.zeros(3); d[k] = eps
+        up = project(model, intr, np.array(p) + d)[1]
+        um = project(model, intr, np.array(p) - d)[1]
+        num = (up - um) / (2 * eps)
+        assert np.allclose(J[:, k], num, rtol=1e-5, atol=1e-5), (k, J[:, k], num)
+
+
+@pytest.mark.parametrize("model,intr,p", CAMS)
+def test_jacobian_intrinsics_vs_central_differences(model, intr, p):
+    J = jac_intr(model, intr, p)
+    for k in range(len(intr)):
+        eps = 1e-7 * max(1.0, abs(intr[k]))
+        ip, im = list(intr), list(intr)
+        ip[k] += eps; im[k] -= eps
+        num = (project(model, ip, p)[1] - project(model, im, p)[1]) / (2 * eps)
+        assert np.allclose(J[:, k], num, rtol=1e-5, atol=1e-5), (k, J[:, k], num)
+
+
+def test_kb_near_axis_branch():  # kannala_brandt.rs:424-437, 640-650, 786-788
+    intr = [300.0, 310.0, 320.0, 240.0, 0.1, 0.01, 0.001, 0.0001]
+    p = [1e-8, -2e-8, 2.0]
+    ok, uv = project(F.CAM_KANNALA_BRANDT, intr, p)
+    assert ok and np.allclose(uv, [300 * 1e-8 / 2 + 320, 310 * -2e-8 / 2 + 240], atol=1e-12)
+    assert np.all(jac_intr(F.CAM_KANNALA_BRANDT, intr, p) == 0.0)
+    J = jac_point(F.CAM_KANNALA_BRANDT, intr, p)
+    assert J[0, 1] == 0 and J[0, 2] == 0 and J[1, 0] == 0 and J[1, 2] == 0 and abs(J[0, 0] - 150.0) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# manifolds + projection factor
+# ---------------------------------------------------------------------------------------------
+def rand_pose(rng):
+    q = rng.standard_normal(4); q /= np.linalg.norm(q)
+    return np.concatenate([rng.standard_normal(3), q])
+
+
+def test_se3_plus_and_act_conventions():
+    # se3.rs:272-297,322-345,569-586; so3.rs:558-611: T (+) tau = T o Exp(tau), Exp(tau) = (J_l(theta) rho, Exp(theta))
+    rng = np.random.default_rng(1)
+    pose = rand_pose(rng)
+    R = np.zeros(9); q = pose[3:].copy()
+    L.oracle_rotation_matrix(F.ptr(q), F.ptr(R)); R = R.reshape(3, 3)
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-14) and abs(np.linalg.det(R) - 1) < 1e-14
+    p = rng.standard_normal(3)
+    assert np.allclose(se3_act(pose, p), R @ p + pose[:3], atol=1e-14)
+    # pure translation step moves t by R rho
+    rho = np.array([0.1, -0.2, 0.3])
+    out = se3_plus(pose, np.concatenate([rho, np.zeros(3)]))
+    assert np.allclose(out[:3], pose[:3] + R @ rho, atol=1e-14) and np.allclose(out[3:], pose[3:], atol=1e-15)
+    # rotation step: R' = R Exp(theta)
+    th = np.array([0.3, -0.1, 0.2])
+    out = se3_plus(pose, np.concatenate([np.zeros(3), th]))
+    R2 = np.zeros(9); q2 = out[3:].copy(); L.oracle_rotation_matrix(F.ptr(q2), F.ptr(R2)); R2 = R2.reshape(3, 3)
+    a = np.linalg.norm(th); k = th / a
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    E = np.eye(3) + math.sin(a) * Kx + (1 - math.cos(a)) * Kx @ Kx
+    assert np.allclose(R2, R @ E, atol=1e-14)
+    # plus followed by minus-step returns (x (+) d) (+) (-d) ~ x  (apply_negative_parameter_step, optimizer/mod.rs:343-356)
+    tau = np.array([0.01, 0.02, -0.03, 0.004, -0.002, 0.001])
+    back = se3_plus(se3_plus(pose, tau), -tau)
+    assert np.allclose(back, pose, atol=1e-4) and not np.array_equal(back, pose)
+    # small-angle branch (theta^2 <= 1e-10): normalised (1, theta/2)
+    th = np.array([1e-6, -2e-6, 3e-6])
+    out = se3_plus([0, 0, 0, 1, 0, 0, 0], np.concatenate([np.zeros(3), th]))
+    qn = np.concatenate([[1.0], th / 2]); qn /= np.linalg.norm(qn)
+    assert np.allclose(out[3:], qn, atol=1e-18)
+
+
+@pytest.mark.parametrize("model,intr,z", [(F.CAM_BAL, [500.0, 1e-2, 1e-3], -1), (F.CAM_KANNALA_BRANDT, [300.0, 300.0, 320.0, 240.0, 0.1, 0.01, 0.001, 0.0001], 1),
+                                          (F.CAM_DOUBLE_SPHERE, [300.0, 300.0, 320.0, 240.0, -0.2, 0.6], 1), (F.CAM_PINHOLE, [500.0, 500.0, 320.0, 240.0], 1)])
+def test_projection_factor_jacobians_vs_central_differences_of_plus(model, intr, z):
+    # bal_pinhole.rs:904-954 / lib.rs:732-772: jacobian_pose vs central differences of pose.plus(delta).act(p)
+    # (eps 1e-7, rel tol 1e-5) — fixes the right-perturbation, [rho, theta] tangent order.
+    rng = np.random.default_rng(7)
+    pose = rand_pose(rng)
+    pose_n = np.zeros(7); L.oracle_se3_normalize(F.ptr(pose), F.ptr(pose_n))
+    # a world point that lands in front of the camera
+    R = np.zeros(9); q = pose_n[3:].copy(); L.oracle_rotation_matrix(F.ptr(q), F.ptr(R)); R = R.reshape(3, 3)
+    pc = np.array([0.3, -0.2, 2.0 * z])
+    pw = R.T @ (pc - pose_n[:3])
+    uv_obs = [1.0, -2.0]
+    opt = F.OPT_POSE | F.OPT_LANDMARK | F.OPT_INTRINSIC
+    r0, J = linearize_block(model, opt, (F.LOSS_NONE, []), pose_n, pw, intr, uv_obs)
+    K = len(intr)
+    assert J.shape == (2, 9 + K)
+    eps = 1e-7
+
+    def resid(pose_, pw_, intr_):
+        return linearize_block(model, opt, (F.LOSS_NONE, []), pose_, pw_, intr_, uv_obs)[0]
+
+    for k in range(6):
+        d = np.zeros(6); d[k] = eps
+        num = (resid(se3_plus(pose_n, d), pw, intr) - resid(se3_plus(pose_n, -d), pw, intr)) / (2 * eps)
+        assert np.allclose(J[:, k], num, rtol=1e-5, atol=1e-4), ("pose", k, J[:, k], num)
+    for k in range(3):
+        d = np.zeros(3); d[k] = eps
+        num = (resid(pose_n, pw + d, intr) - resid(pose_n, pw - d, intr)) / (2 * eps)
+        assert np.allclose(J[:, 6 + k], num, rtol=1e-5, atol=1e-4), ("pt", k)
+    for k in range(K):
+        e = 1e-7 * max(1.0, abs(intr[k]))
+        ip, im = list(intr), list(intr); ip[k] += e; im[k] -= e
+        num = (resid(pose_n, pw, ip) - resid(pose_n, pw, im)) / (2 * e)
+        assert np.allclose(J[:, 9 + k], num, rtol=1e-5, atol=1e-4), ("intr", k)
+
+
+def test_projection_factor_reference_cases():  # src/factors/projection_factor.rs:396-522
+    ident = [0, 0, 0, 1, 0, 0, 0]
+    cam = [500.0, 500.0, 320.0, 240.0]
+    # identity pose, (0.1,0.2,1) seen at its exact projection => residual < 1e-10
+    r, J = linearize_block(F.CAM_PINHOLE, F.OPT_POSE | F.OPT_LANDMARK, (F.LOSS_NONE, []), ident, [0.1, 0.2, 1.0], cam, [370.0, 340.0])
+    assert np.all(np.abs(r) < 1e-10) and J.shape == (2, 9)          # BundleAdjustment: 2 x (6+3)
+    r, J = linearize_block(F.CAM_PINHOLE, 7, (F.LOSS_NONE, []), ident, [0.1, 0.2, 1.0], cam, [370.0, 340.0])
+    assert J.shape == (2, 13)                                       # SelfCalibration: 2 x (6+3+4)
+    assert np.allclose(J[:, 9:], [[0.1, 0, 1, 0], [0, 0.2, 0, 1]])
+    # behind camera => residual 0, Jacobian rows 0 (Ceres convention, :227-239)
+    r, J = linearize_block(F.CAM_PINHOLE, 7, (F.LOSS_HUBER, [1.0]), ident, [0.1, 0.2, -1.0], cam, [370.0, 340.0])
+    assert np.all(r == 0.0) and np.all(J == 0.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# linalg/sparse/explicit_schur.rs
+# ---------------------------------------------------------------------------------------------
+def test_invert_landmark_blocks():  # explicit_schur.rs:1454-1459, 1647-1663: diag(2,3,4)^-1, unchanged by the lambda argument
+    blk = np.diag([2.0, 3.0, 4.0])
+    for lam_arg in (0.0, 0.1, 10.0):
+        for flavour in (0, 1):
+            inv = np.zeros((3, 3))
+            assert L.oracle_invert_landmark_block(F.ptr(blk), C.c_double(lam_arg), flavour, F.ptr(inv)) == 1
+            assert np.allclose(inv, np.diag([0.5, 1 / 3, 0.25]), atol=1e-15)
+    # guards: singular block gets (max(lambda,1e-6) + max_ev*1e-6) I (explicit) / (1e-6 + max_ev*1e-6) I (implicit)
+    blk = np.diag([4.0, 1.0, 0.0])
+    inv = np.zeros((3, 3))
+    assert L.oracle_invert_landmark_block(F.ptr(blk), C.c_double(1e-3), 0, F.ptr(inv)) == 1
+    reg = 1e-3 + 4e-6
+    assert np.allclose(np.diag(inv), 1 / (np.diag(blk) + reg), rtol=1e-12)
+    assert L.oracle_invert_landmark_block(F.ptr(blk), C.c_double(1e-3), 1, F.ptr(inv)) == 1
+    reg = 1e-6 + 4e-6
+    assert np.allclose(np.diag(inv), 1 / (np.diag(blk) + reg), rtol=1e-12)
+    # ill-conditioned (cond > 1e10) but not singular: + max_ev*1e-6
+    blk = np.diag([1e6, 1.0, 1e-5])
+    assert L.oracle_invert_landmark_block(F.ptr(blk), C.c_double(0.0), 0, F.ptr(inv)) == 1
+    assert np.allclose(np.diag(inv), 1 / (np.diag(blk) + 1.0), rtol=1e-12)
+    # a rotated SPD block is inverted exactly
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((3, 3)); blk = A @ A.T + 0.5 * np.eye(3)
+    assert L.oracle_invert_landmark_block(F.ptr(blk), C.c_double(0.0), 0, F.ptr(inv)) == 1
+    assert np.allclose(inv @ blk, np.eye(3), atol=1e-12)
+
+
+def test_compute_schur_complement_known_matrix():  # explicit_schur.rs:1473-1515
+    hcc = np.diag([4.0, 5.0])
+    hcp = np.zeros((2, 3)); hcp[0, 0] = 1.0; hcp[1, 1] = 2.0
+    hinv = (0.5 * np.eye(3)).reshape(1, 9)
+    S = np.zeros((2, 2))
+    L.oracle_schur_complement_dense(2, 1, F.ptr(hcc), F.ptr(hcp), F.ptr(hinv), F.ptr(S))
+    assert abs(S[0, 0] - 3.5) < 1e-10 and abs(S[1, 1] - 3.0) < 1e-10
+    assert S[0, 1] == 0.0 and S[1, 0] == 0.0
+
+
+def test_schur_complement_drops_tiny_entries_and_symmetrises():  # explicit_schur.rs:903-921
+    hcc = np.array([[2.0, 5e-13], [3e-13, 2.0]])
+    hcp = np.zeros((2, 3)); hinv = np.eye(3).reshape(1, 9)
+    S = np.zeros((2, 2))
+    L.oracle_schur_complement_dense(2, 1, F.ptr(hcc), F.ptr(hcp), F.ptr(hinv), F.ptr(S))
+    assert S[0, 1] == 0.0 and S[1, 0] == 0.0 and S[0, 0] == 2.0     # avg 4e-13 <= 1e-12 is dropped
+    hcc = np.array([[2.0, 1.0], [3.0, 2.0]])
+    L.oracle_schur_complement_dense(2, 1, F.ptr(hcc), F.ptr(hcp), F.ptr(hinv), F.ptr(S))
+    assert S[0, 1] == 2.0 and S[1, 0] == 2.0
+
+
+def test_back_substitute():  # explicit_schur.rs:1518-1546: dc=[1,2], g_p=[1,2,3], H_cp=e00+e11, Hpp^-1=I => dp=[0,0,3]
+    hcp = np.zeros((2, 3)); hcp[0, 0] = 1.0; hcp[1, 1] = 1.0
+    hinv = np.eye(3).reshape(1, 9)
+    dp = np.zeros(3)
+    L.oracle_back_substitute_dense(2, 1, F.ptr(arr(1.0, 2.0)), F.ptr(arr(1.0, 2.0, 3.0)), F.ptr(hcp), F.ptr(hinv), F.ptr(dp))
+    assert np.allclose(dp, [0.0, 0.0, 3.0], atol=1e-12)
+
+
+def test_compute_reduced_gradient():  # explicit_schur.rs:1549-1576: g_c=[1,2], g_p=[1,2,3], Hpp^-1=2I => [-1,-2]
+    hcp = np.zeros((2, 3)); hcp[0, 0] = 1.0; hcp[1, 1] = 1.0
+    hinv = (2 * np.eye(3)).reshape(1, 9)
+    out = np.zeros(2)
+    L.oracle_reduced_gradient_dense(2, 1, F.ptr(arr(1.0, 2.0)), F.ptr(arr(1.0, 2.0, 3.0)), F.ptr(hcp), F.ptr(hinv), F.ptr(out))
+    assert np.allclose(out, [-1.0, -2.0], atol=1e-12)
+
+
+def test_solve_with_cholesky_and_pcg():  # explicit_schur.rs:1914-1938, 1942-1959
+    A = np.array([[4.0, 1.0], [1.0, 3.0]]); b = arr(1.0, 2.0); x = np.zeros(2)
+    assert L.oracle_solve_cholesky_dense(2, F.ptr(A), F.ptr(b), F.ptr(x)) == 0
+    assert np.allclose(A @ x, b, atol=1e-8)
+    A = np.diag([2.0, 3.0]); b = arr(1.0, 2.0)
+    L.oracle_solve_pcg_dense(2, F.ptr(A), F.ptr(b), F.ptr(x), 200, C.c_double(1e-6))
+    assert np.allclose(x, [0.5, 2 / 3], atol=1e-6)
+    # indefinite matrix: Cholesky is retried with growing diagonal regularisation (explicit_schur.rs:559-633)
+    A = np.array([[1.0, 2.0], [2.0, 1.0]]); b = arr(1.0, 1.0)
+    assert L.oracle_solve_cholesky_dense(2, F.ptr(A), F.ptr(b), F.ptr(x)) == 0
+    reg = 1.0 * 10.0 ** 0  # first level that makes it PD is base*1e0 = 2 ... accept any of the five levels
+    assert np.all(np.isfinite(x))
+    # larger SPD system against numpy
+    rng = np.random.default_rng(0)
+    M = rng.standard_normal((150, 150)); A = M @ M.T + 150 * np.eye(150); b = rng.standard_normal(150); x = np.zeros(150)
+    assert L.oracle_solve_cholesky_dense(150, F.ptr(A), F.ptr(b), F.ptr(x)) == 0
+    assert np.allclose(x, np.linalg.solve(A, b), rtol=1e-10, atol=1e-12)
+
+
+def test_inverse_n_matches_numpy():
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 3, 4, 6, 8):
+        M = rng.standard_normal((n, n)); A = M @ M.T + n * np.eye(n)
+        out = np.zeros((n, n))
+        assert L.oracle_inverse_n(n, F.ptr(A), F.ptr(out)) == 1
+        assert np.allclose(out, np.linalg.inv(A), rtol=1e-10, atol=1e-12)
+    Z = np.zeros((6, 6)); out = np.zeros((6, 6))
+    assert L.oracle_inverse_n(6, F.ptr(Z), F.ptr(out)) == 0
