@@ -1,0 +1,195 @@
+// apex_ctx.h — host-side context of the B200 bundle-adjustment path: device buffers, the static
+// observation structure built at upload, and the launchers of every kernel group.
+//
+// Data layout in HBM (all FP64, indices u32):
+//   * Observations are sharded with their landmark (points [p0,p1) of this rank) and stored POINT-MAJOR
+//     in "slots". Slots are grouped in chunks of TILE=256; a tile is one chunk holding a run of whole
+//     landmarks (<=256 observations, <=256 landmarks), or, for a landmark with more than 256
+//     observations, several consecutive chunks holding only that landmark. One CTA processes one tile;
+//     per-landmark sums (H_pp, g_p, H_cp^T x) are segmented sums inside the CTA and never cross CTAs.
+//   * Per slot: camera index, landmark index local to the tile, measured pixel, and after linearization
+//     the loss-corrected residual (2 planes) and Jacobian (2*(dc+3) planes), chunk-blocked:
+//     J[(chunk*NP + plane)*TILE + lane] so a chunk's Jacobians are one contiguous 8*NP*256-byte run
+//     and every warp access is a full 256-byte line pair.
+//   * Per landmark (SoA planes over local landmarks): H_pp (6, symmetric), g_p (3), (H_pp+lambda I)^-1 (6).
+//   * Camera side (replicated on every rank): pose[ncam][7], intr[ncam][K], H_cc[ncam][dc][dc], g_c[ncam][dc],
+//     preconditioner blocks, PCG vectors of ncam*dc doubles.
+//   * A CAMERA-MAJOR copy of (pixel, landmark index) feeds the camera-side accumulation kernels, which
+//     re-evaluate the projection instead of gathering Jacobians (cheaper than a strided re-read).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/apex_gpu.h"
+
+namespace apex {
+
+constexpr int TILE = 256;            // slots per chunk = threads per CTA of the tile kernels
+constexpr uint32_t PAD_CAM = 0xFFFFFFFFu;
+constexpr int CAM_THREADS = 128;     // CTA size of the camera-major accumulation kernels
+constexpr int CAM_CHUNK = 2048;      // observations per camera work item
+constexpr int MAX_DC = 14;
+constexpr int MAX_K = 8;
+
+struct TileDesc {
+  uint32_t pt0;      // first local landmark
+  uint32_t npt;      // landmarks in the tile
+  uint32_t chunk0;   // first chunk
+  uint32_t nchunks;  // 1 for a normal tile; >1 only when npt == 1
+};
+
+struct CamItem { uint32_t cam, begin, end, pad; };  // [begin,end) in the camera-major arrays
+
+// Scalars that live on the device (LM bookkeeping, PCG control, norms, error flags).
+struct DevState {
+  // LM state (update_damping / compute_step_quality / check_convergence)
+  double damping, nu;
+  double current_cost, new_cost, previous_cost;
+  double predicted, rho;
+  double grad_norm, step_norm, step_dot_grad, param_norm;
+  int32_t accepted, status, iteration, pad0;
+  // partial norms
+  double g2_cam, s2_cam, sg_cam;          // camera side (replicated)
+  double g2_pt, s2_pt, sg_pt;             // landmark side (rank-local, all-reduced)
+  double pn2_cam, pn2_pt;
+  double cost2_local;                     // sum r~^2 of the local observations
+  // PCG
+  double rz_old, pcg_tol, b_norm, r_norm;
+  int32_t pcg_iters, pcg_done, pcg_max, pad1;
+  // errors
+  int32_t singular_landmark;              // a landmark block could not be inverted
+  int32_t chol_fail;                      // first failing column + 1 of the dense Cholesky
+  int32_t pad2[2];
+};
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count; else p = nullptr;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct NcclApi;  // nccl_dyn.h
+
+struct Ctx {
+  std::string err;
+  int device = 0, rank = 0, nranks = 1;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  int num_sms = 148;
+  void* nccl_comm = nullptr;
+
+  // ---- problem (host copies of what the host needs) ----
+  bool have_problem = false;
+  int model = 0, K = 0, dc = 6, np = 18;  // np = 2*(dc+3) Jacobian planes
+  uint32_t opt = 0;
+  bool opt_intr = false, intr_vars = false;
+  uint32_t ncam = 0, npts = 0;
+  uint64_t nobs = 0;
+  uint64_t cam_dof_ref = 0;  // reference-layout camera dof (includes unreferenced intr columns)
+  int loss_id = 0;
+  double loss_p[4] = {0, 0, 0, 0};
+  uint32_t p0 = 0, p1 = 0, npl = 0;  // local landmark range
+  uint64_t nobs_local = 0;
+  uint32_t nchunks = 0, ntiles = 0, nitems = 0;
+  size_t nslots = 0;
+  std::vector<uint64_t> slot_obs;  // slot -> caller's observation index (UINT64_MAX for padding)
+  std::vector<uint32_t> h_pt_cnt;
+
+  // ---- device: static structure ----
+  DevBuf<TileDesc> tiles;
+  DevBuf<uint32_t> slot_cam;
+  DevBuf<uint16_t> slot_lp;
+  DevBuf<double> slot_uv;            // [chunk][2][TILE]
+  DevBuf<uint32_t> pt_slot0, pt_cnt; // per local landmark
+  DevBuf<CamItem> items;
+  DevBuf<uint32_t> cam_item_start;   // [ncam+1]
+  DevBuf<double> cm_uv;              // [2][nobs_local] camera-major
+  DevBuf<uint32_t> cm_lp;            // [nobs_local] local landmark index
+  DevBuf<uint8_t> pose_fixed, pt_fixed;
+  DevBuf<uint16_t> intr_fixed;
+
+  // ---- device: variables ----
+  DevBuf<double> pose, intr, pt;     // pose[ncam][7], intr[ncam][K], pt[npl][3] (local landmarks only)
+  DevBuf<double> pt_full;            // scratch for params_download with nranks > 1
+
+  // ---- device: linearization ----
+  DevBuf<double> J;                  // [chunk][np][TILE]
+  DevBuf<double> R;                  // [chunk][2][TILE]
+  DevBuf<double> hpp, gp, hinv;      // [6][npl], [3][npl], [6][npl]
+  DevBuf<double> hcc;                // [ncam][dc][dc] followed by g_c [ncam][dc] (one all-reduce)
+  double* gc = nullptr;              // = hcc.p + ncam*dc*dc
+  DevBuf<double> partial;            // [nitems][nacc] camera work-item partial sums
+  DevBuf<double> sj;                 // [ncam][36 + K*K] Schur-Jacobi subtrahends
+  DevBuf<double> pinv;               // [ncam][36 + K*K] preconditioner block inverses
+  bool linearized = false;
+  double lin_lambda = 0.0;
+
+  // ---- device: solve ----
+  DevBuf<double> vb, vx, vr, vz, vp, vy;  // PCG vectors, ncam*dc each
+  DevBuf<double> step_cam, step_pt;       // [ncam][dc], [npl][3]
+  DevBuf<double> red_scratch;             // block partials of the deterministic reductions
+  DevBuf<double> S;                       // dense reduced camera system (explicit variants), n*n row-major
+  DevBuf<double> E;                       // [chunk][3*dc][TILE] H_cp blocks for S formation
+  DevBuf<double> dvec;                    // dense-solver work vectors
+  DevBuf<double> l2flush;                 // > L2 buffer for apex_schur_matvec_bench
+  DevBuf<DevState> state;
+  DevState* h_state = nullptr;            // pinned mirror
+  DevBuf<apex_iter_trace> trace;
+  int64_t last_pcg_iters = 0;
+};
+
+// ---- error helpers --------------------------------------------------------------------------------
+#define APEX_CUDA_TRY(ctx, expr)                                                                    \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      (ctx).err = std::string(#expr) + ": " + cudaGetErrorString(_e);                               \
+      return APEX_ERR_CUDA;                                                                         \
+    }                                                                                               \
+  } while (0)
+
+#define APEX_TRY(expr)                    \
+  do {                                    \
+    apex_status _s = (expr);              \
+    if (_s != APEX_OK) return _s;         \
+  } while (0)
+
+// ---- launchers (one per kernel group; defined in the .cu files) --------------------------------------
+// problem.cu
+apex_status problem_upload(Ctx& c, const apex_problem_desc* d);
+// linearize.cu
+apex_status launch_normalize_poses(Ctx& c);
+apex_status launch_linearize(Ctx& c);                       // K1 + K2 + K3 (lambda from state->damping)
+apex_status launch_cost(Ctx& c, double* d_cost2_out);       // K1': writes sum r~^2 (local) to state->cost2_local
+apex_status launch_schur_jacobi_blocks(Ctx& c, int kind);   // K5 build: fills pinv for preconditioner `kind`
+// schur.cu
+enum TileMode { MODE_MATVEC = 0, MODE_RHS = 1, MODE_BACKSUB = 2 };
+apex_status launch_schur_tiles(Ctx& c, int mode, const double* x, double* y, int check_done);
+apex_status launch_hcc_apply(Ctx& c, const double* x, double* y, int check_done);  // y = (H_cc + lambda I) x on rank 0, else 0
+apex_status schur_operator(Ctx& c, const double* x, double* y, int check_done);    // y = S x, all-reduced
+apex_status launch_reduced_gradient(Ctx& c, double* b);
+apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol);
+// explicit.cu
+apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol);
+// lm.cu
+apex_status launch_step_norms(Ctx& c);
+apex_status launch_apply_step(Ctx& c, double sign, bool only_if_rejected);
+apex_status launch_param_norm(Ctx& c);
+apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, apex_iter_trace* trace, int trace_cap);
+// comm (apex_gpu.cu)
+apex_status allreduce_sum(Ctx& c, double* dev, size_t count);
+apex_status sync_state(Ctx& c);  // copy DevState to the pinned mirror and wait
+
+}  // namespace apex

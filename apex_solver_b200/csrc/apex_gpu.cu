@@ -1,0 +1,351 @@
+// apex_gpu.cu — the C ABI of include/apex_gpu.h over the sm_100a kernels. No CPU fallback: without a CUDA
+// device every compute entry point returns APEX_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <new>
+
+#include "apex_ctx.h"
+#include "ba_device.cuh"
+#include "nccl_dyn.h"
+
+struct apex_ctx { apex::Ctx c; };
+
+namespace apex {
+
+apex_status allreduce_sum(Ctx& c, double* dev, size_t count) {
+  if (c.nranks <= 1 || count == 0) return APEX_OK;
+  NcclApi& api = nccl_api();
+  int r = api.AllReduce(dev, dev, count, NCCL_DOUBLE, NCCL_SUM, (NcclComm)c.nccl_comm, c.stream);
+  if (r != 0) { c.err = std::string("ncclAllReduce: ") + (api.GetErrorString ? api.GetErrorString(r) : "error"); return APEX_ERR_NCCL; }
+  return APEX_OK;
+}
+
+apex_status sync_state(Ctx& c) {
+  APEX_CUDA_TRY(c, cudaMemcpyAsync(c.h_state, c.state.p, sizeof(DevState), cudaMemcpyDeviceToHost, c.stream));
+  APEX_CUDA_TRY(c, cudaStreamSynchronize(c.stream));
+  return APEX_OK;
+}
+
+static apex_status set_damping(Ctx& c, double lambda) {
+  APEX_CUDA_TRY(c, cudaMemcpyAsync(&c.state.p->damping, &lambda, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  APEX_CUDA_TRY(c, cudaStreamSynchronize(c.stream));  // `lambda` is a stack variable
+  return APEX_OK;
+}
+
+static apex_status do_linearize(Ctx& c, double lambda) {
+  APEX_TRY(set_damping(c, lambda));
+  APEX_CUDA_TRY(c, cudaMemsetAsync(&c.state.p->singular_landmark, 0, sizeof(int32_t), c.stream));
+  APEX_TRY(launch_linearize(c));
+  c.linearized = true;
+  c.lin_lambda = lambda;
+  return APEX_OK;
+}
+
+static void lm_config_default(apex_lm_config* c) {  // levenberg_marquardt.rs:319-359
+  std::memset(c, 0, sizeof(*c));
+  c->schur_variant = APEX_SCHUR_EXPLICIT;  // SchurVariant::default() = Sparse
+  c->schur_preconditioner = APEX_PRECOND_SCHUR_JACOBI;
+  c->max_iterations = 50;
+  c->cg_max_iterations = 200;  // explicit_schur.rs:211
+  c->cost_tolerance = 1e-6; c->parameter_tolerance = 1e-8; c->gradient_tolerance = 1e-10;
+  c->timeout_seconds = 0.0;
+  c->damping = 1e-3; c->damping_min = 1e-12; c->damping_max = 1e12;
+  c->damping_increase_factor = 10.0; c->damping_decrease_factor = 0.3; c->damping_nu = 2.0;
+  c->trust_region_radius = 1e4; c->min_step_quality = 0.0; c->good_step_quality = 0.75;
+  c->min_diagonal = 1e-6; c->max_diagonal = 1e32;
+  c->min_cost_threshold = std::numeric_limits<double>::quiet_NaN();
+  c->min_trust_region_radius = 1e-32;
+  c->max_condition_number = std::numeric_limits<double>::quiet_NaN();
+  c->min_relative_decrease = 1e-3;
+  c->cg_tolerance = 1e-6;  // explicit_schur.rs:212
+  c->use_jacobi_scaling = 0; c->compute_covariances = 0;
+}
+
+}  // namespace apex
+
+using namespace apex;
+
+#define CTX_OR_FAIL(ctx)                 \
+  if (!(ctx)) return APEX_ERR_INVALID_STATE; \
+  Ctx& c = (ctx)->c;                     \
+  c.err.clear();                         \
+  if (cudaSetDevice(c.device) != cudaSuccess) { c.err = "cudaSetDevice failed"; return APEX_ERR_CUDA; }
+
+#define NEED_PROBLEM() \
+  if (!c.have_problem) { c.err = "no problem uploaded"; return APEX_ERR_INVALID_STATE; }
+
+extern "C" {
+
+int32_t apex_abi_version(void) { return 100; }
+
+int32_t apex_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void apex_lm_config_default(apex_lm_config* cfg) { lm_config_default(cfg); }
+
+void apex_lm_config_for_bundle_adjustment(apex_lm_config* cfg) {  // levenberg_marquardt.rs:519-530
+  lm_config_default(cfg);
+  cfg->schur_variant = APEX_SCHUR_EXPLICIT_PCG;  // SchurVariant::Iterative as dispatched today
+  cfg->schur_preconditioner = APEX_PRECOND_SCHUR_JACOBI;
+  cfg->damping = 1e-3; cfg->max_iterations = 20;
+  cfg->cost_tolerance = 1e-6; cfg->parameter_tolerance = 1e-8; cfg->gradient_tolerance = 1e-10;
+}
+
+apex_status apex_nccl_unique_id(void* out128) {
+  NcclApi& api = nccl_api();
+  if (!api.ok()) return APEX_ERR_NCCL;
+  NcclUniqueId id;
+  if (api.GetUniqueId(&id) != 0) return APEX_ERR_NCCL;
+  std::memcpy(out128, id.internal, 128);
+  return APEX_OK;
+}
+
+apex_status apex_ctx_create(const apex_ctx_desc* desc, apex_ctx** out) {
+  if (!desc || !out) return APEX_ERR_INVALID_INPUT;
+  *out = nullptr;
+  if (apex_device_count() <= 0) return APEX_ERR_NO_DEVICE;
+  if (desc->nranks < 1 || desc->rank < 0 || desc->rank >= desc->nranks) return APEX_ERR_INVALID_INPUT;
+  if (cudaSetDevice(desc->device) != cudaSuccess) { cudaGetLastError(); return APEX_ERR_CUDA; }
+  apex_ctx* h = new (std::nothrow) apex_ctx();
+  if (!h) return APEX_ERR_CUDA;
+  Ctx& c = h->c;
+  c.device = desc->device; c.rank = desc->rank; c.nranks = desc->nranks;
+  bool ok = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && c.state.alloc(1) == cudaSuccess;
+  ok = ok && cudaMemset(c.state.p, 0, sizeof(DevState)) == cudaSuccess;
+  ok = ok && cudaHostAlloc((void**)&c.h_state, sizeof(DevState), cudaHostAllocDefault) == cudaSuccess;
+  cudaDeviceProp prop;
+  if (ok && cudaGetDeviceProperties(&prop, c.device) == cudaSuccess) c.num_sms = prop.multiProcessorCount;
+  if (!ok) { cudaGetLastError(); delete h; return APEX_ERR_CUDA; }
+  std::memset(c.h_state, 0, sizeof(DevState));
+  if (c.nranks > 1) {
+    NcclApi& api = nccl_api();
+    if (!api.ok() || !desc->nccl_unique_id) { delete h; return APEX_ERR_NCCL; }
+    NcclUniqueId id;
+    std::memcpy(id.internal, desc->nccl_unique_id, 128);
+    NcclComm comm = nullptr;
+    if (api.CommInitRank(&comm, c.nranks, id, c.rank) != 0) { delete h; return APEX_ERR_NCCL; }
+    c.nccl_comm = comm;
+  }
+  *out = h;
+  return APEX_OK;
+}
+
+void apex_ctx_destroy(apex_ctx* ctx) {
+  if (!ctx) return;
+  Ctx& c = ctx->c;
+  cudaSetDevice(c.device);
+  if (c.stream) cudaStreamSynchronize(c.stream);
+  if (c.nccl_comm) nccl_api().CommDestroy((NcclComm)c.nccl_comm);
+  DevBuf<double>* dbl[] = {&c.slot_uv, &c.cm_uv, &c.pose, &c.intr, &c.pt, &c.pt_full, &c.J, &c.R, &c.hpp, &c.gp, &c.hinv, &c.hcc, &c.partial,
+                           &c.sj, &c.pinv, &c.vb, &c.vx, &c.vr, &c.vz, &c.vp, &c.vy, &c.step_cam, &c.step_pt, &c.red_scratch, &c.S, &c.E,
+                           &c.dvec, &c.l2flush};
+  for (auto* b : dbl) b->release();
+  c.tiles.release(); c.slot_cam.release(); c.slot_lp.release(); c.pt_slot0.release(); c.pt_cnt.release(); c.items.release();
+  c.cam_item_start.release(); c.cm_lp.release(); c.pose_fixed.release(); c.pt_fixed.release(); c.intr_fixed.release();
+  c.state.release(); c.trace.release();
+  if (c.h_state) cudaFreeHost(c.h_state);
+  if (c.stream) cudaStreamDestroy(c.stream);
+  delete ctx;
+}
+
+const char* apex_last_error(const apex_ctx* ctx) { return ctx ? ctx->c.err.c_str() : "null context"; }
+
+apex_status apex_problem_upload(apex_ctx* ctx, const apex_problem_desc* desc) {
+  CTX_OR_FAIL(ctx);
+  if (!desc) { c.err = "null problem"; return APEX_ERR_INVALID_INPUT; }
+  return problem_upload(c, desc);
+}
+
+apex_status apex_get_dims(const apex_ctx* ctx, apex_dims* out) {
+  if (!ctx || !out) return APEX_ERR_INVALID_INPUT;
+  const Ctx& c = ctx->c;
+  out->ncam = c.ncam; out->npts = c.npts; out->nobs = c.nobs; out->intr_dim = c.K; out->dc = c.dc;
+  out->cam_dof = c.cam_dof_ref; out->lm_dof = 3 * (uint64_t)c.npts; out->npts_local = c.npl; out->reserved = 0; out->nobs_local = c.nobs_local;
+  return APEX_OK;
+}
+
+apex_status apex_params_upload(apex_ctx* ctx, const double* pose, const double* intr, const double* pt) {
+  CTX_OR_FAIL(ctx);
+  NEED_PROBLEM();
+  cudaStream_t s = c.stream;
+  if (pose) APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pose.p, pose, 7 * (size_t)c.ncam * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (intr) APEX_CUDA_TRY(c, cudaMemcpyAsync(c.intr.p, intr, (size_t)c.K * c.ncam * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (pt && c.npl) APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pt.p, pt + 3 * (size_t)c.p0, 3 * (size_t)c.npl * sizeof(double), cudaMemcpyHostToDevice, s));
+  APEX_CUDA_TRY(c, cudaStreamSynchronize(s));
+  c.linearized = false;
+  return APEX_OK;
+}
+
+// landmark-indexed device array of local rows [npl][w] -> host array of all rows [npts][w]
+static apex_status gather_point_rows(Ctx& c, const double* dev_local, int w, double* host_full) {
+  cudaStream_t s = c.stream;
+  if (c.nranks == 1) {
+    APEX_CUDA_TRY(c, cudaMemcpyAsync(host_full, dev_local, (size_t)w * c.npts * sizeof(double), cudaMemcpyDeviceToHost, s));
+  } else {
+    const size_t total = (size_t)w * c.npts;
+    APEX_CUDA_TRY(c, c.pt_full.alloc(total));
+    APEX_CUDA_TRY(c, cudaMemsetAsync(c.pt_full.p, 0, total * sizeof(double), s));
+    if (c.npl)
+      APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pt_full.p + (size_t)w * c.p0, dev_local, (size_t)w * c.npl * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    APEX_TRY(allreduce_sum(c, c.pt_full.p, total));
+    APEX_CUDA_TRY(c, cudaMemcpyAsync(host_full, c.pt_full.p, total * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
+  APEX_CUDA_TRY(c, cudaStreamSynchronize(s));
+  return APEX_OK;
+}
+
+apex_status apex_params_download(apex_ctx* ctx, double* pose, double* intr, double* pt) {
+  CTX_OR_FAIL(ctx);
+  NEED_PROBLEM();
+  cudaStream_t s = c.stream;
+  if (pose) APEX_CUDA_TRY(c, cudaMemcpyAsync(pose, c.pose.p, 7 * (size_t)c.ncam * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (intr) APEX_CUDA_TRY(c, cudaMemcpyAsync(intr, c.intr.p, (size_t)c.K * c.ncam * sizeof(double), cudaMemcpyDeviceToHost, s));
+  APEX_CUDA_TRY(c, cudaStreamSynchronize(s));
+  if (pt) APEX_TRY(gather_point_rows(c, c.pt.p, 3, pt));
+  return APEX_OK;
+}
+
+apex_status apex_linearize(apex_ctx* ctx, double lambda) {
+  CTX_OR_FAIL(ctx);
+  NEED_PROBLEM();
+  APEX_TRY(do_linearize(c, lambda));
+  APEX_TRY(sync_state(c));
+  return APEX_OK;
+}
+
+apex_status apex_cost(apex_ctx* ctx, double* cost) {
+  CTX_OR_FAIL(ctx);
+  NEED_PROBLEM();
+  APEX_TRY(launch_cost(c, nullptr));
+  APEX_TRY(sync_state(c));
+  const double cn = std::sqrt(c.h_state->cost2_local);
+  if (cost) *cost = 0.5 * cn * cn;
+  return APEX_OK;
+}
+
+apex_status apex_get_linearization(apex_ctx* ctx, double* r, double* jc, double* jp) {
+  CTX_OR_FAIL(ctx);
+  NEED_PROBLEM();
+  if (!c.linearized) { c.err = "not linearized"; return APEX_ERR_INVALID_STATE; }
+  if (c.nranks != 1) { c.err = "get_linearization is single-rank only"; return APEX_ERR_UNSUPPORTED; }
+  const int dc = c.dc, np = c.np;
+  std::vector<double> hJ((size_t)c.nchunks * np * TILE), hR((size_t)c.nchunks * 2 * TILE);
+  APEX_CUDA_TRY(c, cudaMemcpyAsync(hJ.data(), c.J.p, hJ.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  APEX_CUDA_TRY(c, cudaMemcpyAsync(hR.data(), c.R.p, hR.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  APEX_CUDA_TRY(c, cudaStreamSynchronize(c.stream));
+  for (size_t slot = 0; slot < c.nslots; ++slot) {
+    const uint64_t o = c.slot_obs[slot];
+    if (o == UINT64_MAX) continue;
+    const size_t ch = slot / TILE, lane = slot % TILE;
+    if (r) { r[2 * o] = hR[(ch * 2 + 0) * TILE + lane]; r[2 * o + 1] = hR[(ch * 2 + 1) * TILE + lane]; }
+    if (jc) for (int k = 0; k < 2 * dc; ++k) jc[o * 2 * dc + k] = hJ[(ch * np + k) * TILE + lane];
+    if (jp) for (int k = 0; k < 6; ++k) jp[o * 6 + k] = hJ[(ch * np + 2 * dc + k) * TILE + lane];
+  }
+  return APEX_OK;
+}
+
+apex_status apex_get_blocks(apex_ctx* ctx, double* hcc, double* gc, double* hpp, double* gp, double* hpp_inv) {
+  CTX_OR_FAIL(ctx);
+  NEED_PROBLEM();
+  if (!c.linearized) { c.err = "not linearized"; return APEX_ERR_INVALID_STATE; }
+  if (c.nranks != 1) { c.err = "get_blocks is single-rank only"; return APEX_ERR_UNSUPPORTED; }
+  cudaStream_t s = c.stream;
+  const size_t ncd = (size_t)c.ncam * c.dc, n = c.npl;
+  if (hcc) APEX_CUDA_TRY(c, cudaMemcpyAsync(hcc, c.hcc.p, ncd * c.dc * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (gc) APEX_CUDA_TRY(c, cudaMemcpyAsync(gc, c.gc, ncd * sizeof(double), cudaMemcpyDeviceToHost, s));
+  std::vector<double> h6(6 * n), g3(3 * n), i6(6 * n);
+  APEX_CUDA_TRY(c, cudaMemcpyAsync(h6.data(), c.hpp.p, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  APEX_CUDA_TRY(c, cudaMemcpyAsync(g3.data(), c.gp.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  APEX_CUDA_TRY(c, cudaMemcpyAsync(i6.data(), c.hinv.p, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  APEX_CUDA_TRY(c, cudaStreamSynchronize(s));
+  static const int sym[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
+  for (size_t p = 0; p < n; ++p) {
+    if (hpp) for (int k = 0; k < 9; ++k) hpp[9 * p + k] = h6[sym[k] * n + p];
+    if (hpp_inv) for (int k = 0; k < 9; ++k) hpp_inv[9 * p + k] = i6[sym[k] * n + p];
+    if (gp) for (int k = 0; k < 3; ++k) gp[3 * p + k] = g3[k * n + p];
+  }
+  return APEX_OK;
+}
+
+apex_status apex_schur_matvec(apex_ctx* ctx, const double* x, double* y) {
+  CTX_OR_FAIL(ctx);
+  NEED_PROBLEM();
+  if (!c.linearized) { c.err = "not linearized"; return APEX_ERR_INVALID_STATE; }
+  if (!x || !y) { c.err = "null vector"; return APEX_ERR_INVALID_INPUT; }
+  const size_t n = (size_t)c.ncam * c.dc;
+  APEX_CUDA_TRY(c, cudaMemcpyAsync(c.vp.p, x, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  APEX_TRY(schur_operator(c, c.vp.p, c.vy.p, 0));
+  APEX_CUDA_TRY(c, cudaMemcpyAsync(y, c.vy.p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  APEX_CUDA_TRY(c, cudaStreamSynchronize(c.stream));
+  return APEX_OK;
+}
+
+apex_status apex_schur_matvec_bench(apex_ctx* ctx, int32_t reps, int32_t flush_l2, double* ms_per_call) {
+  CTX_OR_FAIL(ctx);
+  NEED_PROBLEM();
+  if (!c.linearized) { c.err = "not linearized"; return APEX_ERR_INVALID_STATE; }
+  if (reps < 1) reps = 1;
+  const size_t n = (size_t)c.ncam * c.dc;
+  const size_t flush_n = (size_t)256 << 20 >> 3;  // 256 MiB > 126 MB L2
+  if (flush_l2) APEX_CUDA_TRY(c, c.l2flush.alloc(flush_n));
+  std::vector<double> ones(n, 1.0);
+  APEX_CUDA_TRY(c, cudaMemcpyAsync(c.vp.p, ones.data(), n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  cudaEvent_t e0, e1;
+  APEX_CUDA_TRY(c, cudaEventCreate(&e0));
+  APEX_CUDA_TRY(c, cudaEventCreate(&e1));
+  double total_ms = 0.0;
+  for (int i = -3; i < reps; ++i) {  // 3 warm-up applications
+    if (flush_l2) APEX_CUDA_TRY(c, cudaMemsetAsync(c.l2flush.p, i & 1, flush_n * sizeof(double), c.stream));
+    APEX_CUDA_TRY(c, cudaEventRecord(e0, c.stream));
+    APEX_TRY(launch_hcc_apply(c, c.vp.p, c.vy.p, 0));
+    APEX_TRY(launch_schur_tiles(c, MODE_MATVEC, c.vp.p, c.vy.p, 0));
+    APEX_CUDA_TRY(c, cudaEventRecord(e1, c.stream));
+    APEX_CUDA_TRY(c, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    APEX_CUDA_TRY(c, cudaEventElapsedTime(&ms, e0, e1));
+    if (i >= 0) total_ms += ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms_per_call) *ms_per_call = total_ms / reps;
+  return APEX_OK;
+}
+
+apex_status apex_solve_augmented(apex_ctx* ctx, int32_t schur_variant, int32_t preconditioner, int32_t cg_max_iterations, double cg_tolerance,
+                                 double lambda, double* step_cam, double* step_pt, double* grad_norm, int32_t* pcg_iters) {
+  CTX_OR_FAIL(ctx);
+  NEED_PROBLEM();
+  if (schur_variant < APEX_SCHUR_EXPLICIT || schur_variant > APEX_SCHUR_EXPLICIT_PCG) { c.err = "bad schur_variant"; return APEX_ERR_INVALID_PARAMETERS; }
+  if (!c.linearized || c.lin_lambda != lambda) APEX_TRY(do_linearize(c, lambda));
+  apex_status st;
+  if (schur_variant == APEX_SCHUR_IMPLICIT) st = solve_implicit(c, preconditioner, cg_max_iterations, cg_tolerance);
+  else st = solve_explicit(c, schur_variant == APEX_SCHUR_EXPLICIT_PCG, cg_max_iterations, cg_tolerance);
+  if (st != APEX_OK) return st;
+  APEX_TRY(launch_step_norms(c));
+  APEX_TRY(sync_state(c));
+  if (c.h_state->singular_landmark) { c.err = "Landmark block singular"; return APEX_ERR_SINGULAR_MATRIX; }
+  if (grad_norm) *grad_norm = std::sqrt(c.h_state->g2_cam + c.h_state->g2_pt);
+  if (pcg_iters) *pcg_iters = (int32_t)c.last_pcg_iters;
+  if (step_cam) {
+    APEX_CUDA_TRY(c, cudaMemcpyAsync(step_cam, c.step_cam.p, (size_t)c.ncam * c.dc * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    APEX_CUDA_TRY(c, cudaStreamSynchronize(c.stream));
+  }
+  if (step_pt) APEX_TRY(gather_point_rows(c, c.step_pt.p, 3, step_pt));
+  return APEX_OK;
+}
+
+apex_status apex_lm_solve(apex_ctx* ctx, const apex_lm_config* cfg, apex_lm_result* result, apex_iter_trace* trace, int32_t trace_cap) {
+  CTX_OR_FAIL(ctx);
+  if (!cfg || !result) { c.err = "null config/result"; return APEX_ERR_INVALID_INPUT; }
+  return lm_solve(c, cfg, result, trace, trace_cap);
+}
+
+int64_t apex_kernel_launches(const apex_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,560 @@
+// explicit.cu — K7 formation of the reduced camera system S and K8 its dense FP64 solve.
+//
+// sm_100a equivalents of SparseSchurComplementSolver (src/linalg/sparse/explicit_schur.rs):
+//   compute_schur_complement :771-925  -> schur_form_kernel (+ diag / symmetrize_drop kernels)
+//   solve_with_cholesky      :539-634  -> blocked right-looking Cholesky; the trailing update is the only
+//                                          dense contraction of the path and runs on the FP64 tensor pipe
+//                                          (mma.sync.m8n8k4.f64 = DMMA.8x8x4; tcgen05 has no FP64 kind)
+//   solve_with_pcg           :639-756  -> scalar-Jacobi PCG on the dense S (what SchurVariant::Iterative
+//                                          dispatches to today, explicit_schur.rs:1224-1225)
+// S is stored dense, row-major, in the camera-major local layout (row = cam*dc + dof), padded to a multiple
+// of 64 with an identity tail so no kernel needs edge handling.
+#include <algorithm>
+#include <cmath>
+
+#include "apex_ctx.h"
+#include "ba_device.cuh"
+#include "kernels_common.cuh"
+
+namespace apex {
+
+constexpr int NB = 64;        // Cholesky block size
+constexpr int PLD = NB + 4;   // padded leading dimension of the shared-memory panels (bank-conflict free)
+
+// ----------------------------------------------------------------------------------------------------
+// K7: S -= sum_p sum_{i,j in obs(p)} (Jc_i^T Jp_i) Hpp_p^-1 (Jp_j^T Jc_j), lower block triangle
+// ----------------------------------------------------------------------------------------------------
+struct FormArgs {
+  const TileDesc* tiles;
+  const uint32_t* slot_cam;
+  const uint16_t* slot_lp;
+  const uint32_t* pt_slot0;
+  const uint32_t* pt_cnt;
+  const double* J;
+  const double* hinv;
+  double* S;
+  size_t ld;
+  uint32_t npl;
+};
+
+template <int DC>
+__global__ void __launch_bounds__(TILE) schur_form_kernel(FormArgs a) {
+  constexpr int NP = 2 * (DC + 3);
+  const TileDesc td = a.tiles[blockIdx.x];
+  const int tid = threadIdx.x;
+  for (uint32_t ch = 0; ch < td.nchunks; ++ch) {
+    const size_t chunk = (size_t)td.chunk0 + ch;
+    const size_t slot = chunk * TILE + tid;
+    const uint32_t cam_i = a.slot_cam[slot];
+    if (cam_i == PAD_CAM) continue;
+    const uint32_t lp = td.pt0 + a.slot_lp[slot];
+    const uint32_t s0 = a.pt_slot0[lp], cnt = a.pt_cnt[lp];
+    double jc[2 * DC], jp[6];
+    const double* Jt = a.J + chunk * NP * TILE + tid;
+#pragma unroll
+    for (int k = 0; k < 2 * DC; ++k) jc[k] = Jt[(size_t)k * TILE];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) jp[k] = Jt[(size_t)(2 * DC + k) * TILE];
+    const size_t n = a.npl;
+    const double h00 = a.hinv[0 * n + lp], h01 = a.hinv[1 * n + lp], h02 = a.hinv[2 * n + lp];
+    const double h11 = a.hinv[3 * n + lp], h12 = a.hinv[4 * n + lp], h22 = a.hinv[5 * n + lp];
+    double G[2][3];  // Jp_i Hpp^-1
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      G[r][0] = jp[r * 3] * h00 + jp[r * 3 + 1] * h01 + jp[r * 3 + 2] * h02;
+      G[r][1] = jp[r * 3] * h01 + jp[r * 3 + 1] * h11 + jp[r * 3 + 2] * h12;
+      G[r][2] = jp[r * 3] * h02 + jp[r * 3 + 1] * h12 + jp[r * 3 + 2] * h22;
+    }
+    for (uint32_t j = s0; j < s0 + cnt; ++j) {
+      const uint32_t cam_j = a.slot_cam[j];
+      if (cam_j > cam_i) continue;
+      const double* Jj = a.J + ((size_t)(j / TILE) * NP) * TILE + (j % TILE);
+      double pj[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) pj[k] = Jj[(size_t)(2 * DC + k) * TILE];
+      double M[2][2];  // Jp_i Hpp^-1 Jp_j^T
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) M[r][cc] = G[r][0] * pj[cc * 3] + G[r][1] * pj[cc * 3 + 1] + G[r][2] * pj[cc * 3 + 2];
+      double cj[2 * DC];
+#pragma unroll
+      for (int k = 0; k < 2 * DC; ++k) cj[k] = Jj[(size_t)k * TILE];
+      double* Srow = a.S + ((size_t)cam_i * DC) * a.ld + (size_t)cam_j * DC;
+#pragma unroll
+      for (int p = 0; p < DC; ++p) {
+        const double a0 = jc[p] * M[0][0] + jc[DC + p] * M[1][0];
+        const double a1 = jc[p] * M[0][1] + jc[DC + p] * M[1][1];
+#pragma unroll
+        for (int q = 0; q < DC; ++q) red_add(Srow + (size_t)p * a.ld + q, -fma(a0, cj[q], a1 * cj[DC + q]));
+      }
+    }
+  }
+}
+
+// S diagonal blocks += H_cc + lambda I (explicit_schur.rs:1186-1205, :784-792); identity on the padded tail
+__global__ void schur_diag_kernel(double* S, size_t ld, const double* hcc, const DevState* st, uint32_t ncam, int dc, uint32_t n, uint32_t npad,
+                                  int add_hcc) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nblk = (size_t)ncam * dc * dc;
+  if (gid < nblk) {
+    if (!add_hcc) return;
+    const uint32_t cam = (uint32_t)(gid / (dc * dc));
+    const int a = (int)((gid / dc) % dc), b = (int)(gid % dc);
+    S[((size_t)cam * dc + a) * ld + (size_t)cam * dc + b] += hcc[gid] + (a == b ? st->damping : 0.0);
+  } else if (gid < nblk + (npad - n)) {
+    const size_t i = n + (gid - nblk);
+    S[i * ld + i] = add_hcc ? 1.0 : 0.0;
+  }
+}
+
+// explicit_schur.rs:903-921: symmetrise and drop |S_ij| <= 1e-12. Only the lower triangle was accumulated
+// (the reference accumulates both and averages them); mirror it into the upper triangle.
+__global__ void symmetrize_drop_kernel(double* S, size_t ld, uint32_t nt) {
+  __shared__ double tile[32][33];
+  // linear index -> (bi >= bj)
+  const uint32_t t = blockIdx.x;
+  uint32_t bi = (uint32_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((uint64_t)bi * (bi + 1) / 2 > t) --bi;
+  while ((uint64_t)(bi + 1) * (bi + 2) / 2 <= t) ++bi;
+  const uint32_t bj = t - (uint32_t)((uint64_t)bi * (bi + 1) / 2);
+  (void)nt;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int r = ty; r < 32; r += 8) {
+    const size_t row = (size_t)bi * 32 + r, col = (size_t)bj * 32 + tx;
+    double v = S[row * ld + col];
+    if (bi == bj && tx > r) v = 0.0;  // upper part of a diagonal tile: filled from the mirror below
+    if (fabs(v) <= 1e-12) v = 0.0;
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const size_t row = (size_t)bi * 32 + r, col = (size_t)bj * 32 + tx;
+    double v = tile[r][tx];
+    if (bi == bj && tx > r) v = tile[tx][r];
+    S[row * ld + col] = v;
+    if (bi != bj) {
+      const size_t mrow = (size_t)bj * 32 + r, mcol = (size_t)bi * 32 + tx;
+      S[mrow * ld + mcol] = tile[tx][r];
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// K8: blocked right-looking Cholesky, lower, in place
+// ----------------------------------------------------------------------------------------------------
+// factor the NB x NB diagonal block at k0 (one CTA, 256 threads)
+__global__ void __launch_bounds__(256) chol_potrf_kernel(double* A, size_t ld, uint32_t k0, DevState* st) {
+  __shared__ double a[NB][NB + 1];
+  __shared__ int bad;
+  if (st->chol_fail) return;
+  const int tid = threadIdx.x;
+  if (tid == 0) bad = 0;
+  for (int e = tid; e < NB * NB; e += 256) { const int r = e / NB, cidx = e % NB; a[r][cidx] = A[((size_t)k0 + r) * ld + k0 + cidx]; }
+  __syncthreads();
+  for (int j = 0; j < NB; ++j) {
+    if (tid == 0) {
+      const double d = a[j][j];
+      if (!(d > 0.0)) { bad = j + 1; a[j][j] = 1.0; } else a[j][j] = sqrt(d);
+    }
+    __syncthreads();
+    const double d = a[j][j];
+    if (tid > j && tid < NB) a[tid][j] /= d;
+    __syncthreads();
+    // trailing update of the lower triangle: rows i > j, cols j < k <= i
+    const int m = NB - 1 - j;
+    for (int e = tid; e < m * m; e += 256) {
+      const int i = j + 1 + e / m, k = j + 1 + e % m;
+      if (k <= i) a[i][k] -= a[i][j] * a[k][j];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < NB * NB; e += 256) { const int r = e / NB, cidx = e % NB; if (cidx <= r) A[((size_t)k0 + r) * ld + k0 + cidx] = a[r][cidx]; }
+  if (tid == 0 && bad) atomicCAS(&st->chol_fail, 0, (int)k0 + bad);
+}
+
+// panel: rows [r0 + 64*blockIdx.x, +64): X <- X * L11^-T, one thread per row (forward substitution)
+__global__ void __launch_bounds__(256) chol_trsm_kernel(double* A, size_t ld, uint32_t k0) {
+  extern __shared__ double trsm_smem[];
+  double (*l)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(trsm_smem);
+  double (*x)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(trsm_smem + NB * (NB + 1));
+  const int tid = threadIdx.x;
+  const size_t r0 = (size_t)k0 + NB + (size_t)blockIdx.x * NB;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e / NB, cidx = e % NB;
+    l[r][cidx] = A[((size_t)k0 + r) * ld + k0 + cidx];
+    x[r][cidx] = A[(r0 + r) * ld + k0 + cidx];
+  }
+  __syncthreads();
+  if (tid < NB) {
+    for (int j = 0; j < NB; ++j) {
+      double s = x[tid][j];
+      for (int k = 0; k < j; ++k) s = fma(-x[tid][k], l[j][k], s);
+      x[tid][j] = s / l[j][j];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < NB * NB; e += 256) { const int r = e / NB, cidx = e % NB; A[(r0 + r) * ld + k0 + cidx] = x[r][cidx]; }
+}
+
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// trailing update A22 -= L21 L21^T on 64x64 tiles of the lower block triangle; 4 warps, each a 32x32
+// sub-tile = 4x4 DMMA.8x8x4 accumulators; the two 64x64 panel tiles are staged in shared memory.
+__global__ void __launch_bounds__(128) chol_syrk_kernel(double* A, size_t ld, uint32_t k0) {
+  extern __shared__ double smem[];
+  double* Pa = smem;
+  double* Pb = smem + NB * PLD;
+  const uint32_t t = blockIdx.x;
+  uint32_t bi = (uint32_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((uint64_t)bi * (bi + 1) / 2 > t) --bi;
+  while ((uint64_t)(bi + 1) * (bi + 2) / 2 <= t) ++bi;
+  const uint32_t bj = t - (uint32_t)((uint64_t)bi * (bi + 1) / 2);
+  const size_t ri = (size_t)k0 + NB + (size_t)bi * NB, rj = (size_t)k0 + NB + (size_t)bj * NB;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB / 2; e += 128) {
+    const int r = e / (NB / 2), c2 = (e % (NB / 2)) * 2;
+    const double2 va = *reinterpret_cast<const double2*>(A + (ri + r) * ld + k0 + c2);
+    Pa[r * PLD + c2] = va.x; Pa[r * PLD + c2 + 1] = va.y;
+    const double2 vb = *reinterpret_cast<const double2*>(A + (rj + r) * ld + k0 + c2);
+    Pb[r * PLD + c2] = vb.x; Pb[r * PLD + c2 + 1] = vb.y;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int lr = lane >> 2, lc = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+#pragma unroll 4
+  for (int kk = 0; kk < NB; kk += 4) {
+    double af[4], bf[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) af[mi] = Pa[(wm + mi * 8 + lr) * PLD + kk + lc];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) bf[ni] = Pb[(wn + ni * 8 + lr) * PLD + kk + lc];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+  }
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      double2* p = reinterpret_cast<double2*>(A + (ri + wm + mi * 8 + lr) * ld + rj + wn + ni * 8 + lc * 2);
+      double2 v = *p;
+      v.x -= acc[mi][ni][0];
+      v.y -= acc[mi][ni][1];
+      *p = v;
+    }
+}
+
+// triangular solves with the factor: forward L y = b, backward L^T x = y, 64-row blocks
+__global__ void __launch_bounds__(NB) trsv_diag_kernel(const double* A, size_t ld, uint32_t k0, double* v, int transpose) {
+  __shared__ double l[NB][NB + 1];
+  __shared__ double y[NB];
+  const int tid = threadIdx.x;
+  for (int r = 0; r < NB; ++r) l[r][tid] = A[((size_t)k0 + r) * ld + k0 + tid];
+  y[tid] = v[k0 + tid];
+  __syncthreads();
+  if (!transpose) {
+    for (int j = 0; j < NB; ++j) {
+      if (tid == j) y[j] /= l[j][j];
+      __syncthreads();
+      if (tid > j) y[tid] -= l[tid][j] * y[j];
+      __syncthreads();
+    }
+  } else {
+    for (int j = NB - 1; j >= 0; --j) {
+      if (tid == j) y[j] /= l[j][j];
+      __syncthreads();
+      if (tid < j) y[tid] -= l[j][tid] * y[j];
+      __syncthreads();
+    }
+  }
+  v[k0 + tid] = y[tid];
+}
+
+// forward: v[i] -= sum_c L[i][k0+c] y[k0+c] for rows i >= k0+64 ; 8 threads per row
+__global__ void __launch_bounds__(256) trsv_update_fwd_kernel(const double* A, size_t ld, uint32_t k0, double* v, uint32_t npad) {
+  __shared__ double y[NB];
+  const int tid = threadIdx.x;
+  if (tid < NB) y[tid] = v[k0 + tid];
+  __syncthreads();
+  const size_t row = (size_t)k0 + NB + (size_t)blockIdx.x * 32 + (tid >> 3);
+  const int sub = tid & 7;
+  double s = 0.0;
+  if (row < npad) {
+    const double* Lr = A + row * ld + k0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s = fma(Lr[sub + 8 * c], y[sub + 8 * c], s);
+  }
+  s += __shfl_down_sync(0xffffffffu, s, 4, 8);
+  s += __shfl_down_sync(0xffffffffu, s, 2, 8);
+  s += __shfl_down_sync(0xffffffffu, s, 1, 8);
+  if (sub == 0 && row < npad) v[row] -= s;
+}
+
+// backward: v[j] -= sum_r L[k0+r][j] x[k0+r] for columns j < k0 ; one thread per column
+__global__ void __launch_bounds__(256) trsv_update_bwd_kernel(const double* A, size_t ld, uint32_t k0, double* v) {
+  __shared__ double x[NB];
+  const int tid = threadIdx.x;
+  if (tid < NB) x[tid] = v[k0 + tid];
+  __syncthreads();
+  const size_t col = (size_t)blockIdx.x * 256 + tid;
+  if (col >= k0) return;
+  double s = 0.0;
+#pragma unroll 8
+  for (int r = 0; r < NB; ++r) s = fma(A[((size_t)k0 + r) * ld + col], x[r], s);
+  v[col] -= s;
+}
+
+__global__ void add_diag_kernel(double* A, size_t ld, uint32_t n, double reg) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) A[(size_t)i * ld + i] += reg;
+}
+
+// trace and max |diag| of S (solve_with_cholesky's regularisation base, explicit_schur.rs:575-590)
+__global__ void __launch_bounds__(1024) diag_stats_kernel(const double* A, size_t ld, uint32_t n, double* out2) {
+  __shared__ double sh[1024];
+  double tr = 0.0, mx = 0.0;
+  for (uint32_t i = threadIdx.x; i < n; i += 1024) { const double d = A[(size_t)i * ld + i]; tr += d; mx = dmax(mx, fabs(d)); }
+  tr = block_reduce_sum(tr, sh);
+  sh[threadIdx.x] = mx;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) { if ((int)threadIdx.x < s) sh[threadIdx.x] = dmax(sh[threadIdx.x], sh[threadIdx.x + s]); __syncthreads(); }
+  if (threadIdx.x == 0) { out2[0] = tr; out2[1] = sh[0]; }
+}
+
+// ---- dense PCG pieces (solve_with_pcg, explicit_schur.rs:639-756) -----------------------------------
+// y = S p, one warp per row of the full symmetric matrix
+__global__ void __launch_bounds__(256) dense_symv_kernel(const double* __restrict__ S, size_t ld, const double* __restrict__ p, double* __restrict__ y,
+                                                         uint32_t n, const DevState* st) {
+  if (st->pcg_done) return;
+  const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const double* Sr = S + (size_t)row * ld;
+  double s = 0.0;
+  for (uint32_t c = lane; c < n; c += 32) s = fma(Sr[c], p[c], s);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+  if (lane == 0) y[row] = s;
+}
+
+// scalar Jacobi preconditioner: 1/d if |d| > 1e-12 else 1 (explicit_schur.rs:655-668)
+__global__ void jacobi_diag_kernel(const double* S, size_t ld, uint32_t n, double* pinv) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double d = S[(size_t)i * ld + i];
+  pinv[i] = fabs(d) > 1e-12 ? 1.0 / d : 1.0;
+}
+
+__global__ void __launch_bounds__(1024) dense_pcg_init_kernel(const double* __restrict__ b, const double* __restrict__ pinv, double* x, double* r,
+                                                              double* z, double* p, DevState* st, uint32_t n, int max_it, double cg_tol) {
+  __shared__ double sh[1024];
+  double bb = 0.0, rz = 0.0;
+  for (uint32_t i = threadIdx.x; i < n; i += 1024) {
+    const double v = b[i], zv = pinv[i] * v;
+    r[i] = v; x[i] = 0.0; z[i] = zv; p[i] = zv;
+    bb += v * v; rz += v * zv;
+  }
+  bb = block_reduce_sum(bb, sh);
+  rz = block_reduce_sum(rz, sh);
+  if (threadIdx.x == 0) {
+    const double b_norm = sqrt(bb);
+    st->b_norm = b_norm; st->pcg_tol = cg_tol * dmax(b_norm, 1.0); st->rz_old = rz; st->r_norm = b_norm;
+    st->pcg_iters = 0; st->pcg_max = max_it; st->pcg_done = max_it <= 0 ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(1024) dense_pcg_step_kernel(const double* __restrict__ ap, const double* __restrict__ pinv, double* x, double* r,
+                                                              double* z, double* p, DevState* st, uint32_t n) {
+  __shared__ double sh[1024];
+  if (st->pcg_done) return;
+  const int iters = st->pcg_iters + 1;
+  const double rz_old = st->rz_old, tol = st->pcg_tol;
+  const int max_it = st->pcg_max;
+  double v = 0.0;
+  for (uint32_t i = threadIdx.x; i < n; i += 1024) v = fma(p[i], ap[i], v);
+  const double p_ap = block_reduce_sum(v, sh);
+  if (fabs(p_ap) < 1e-30) { if (threadIdx.x == 0) { st->pcg_iters = iters; st->pcg_done = 1; } return; }
+  const double alpha = rz_old / p_ap;
+  v = 0.0;
+  double w = 0.0;
+  for (uint32_t i = threadIdx.x; i < n; i += 1024) {
+    x[i] += alpha * p[i];
+    const double rv = r[i] - alpha * ap[i];
+    r[i] = rv;
+    v = fma(rv, rv, v);
+    const double zv = pinv[i] * rv;
+    z[i] = zv;
+    w = fma(rv, zv, w);
+  }
+  const double r_norm = sqrt(block_reduce_sum(v, sh));
+  const double rz_new = block_reduce_sum(w, sh);
+  if (r_norm < tol || fabs(rz_old) < 1e-30) { if (threadIdx.x == 0) { st->pcg_iters = iters; st->pcg_done = 1; st->r_norm = r_norm; } return; }
+  const double beta = rz_new / rz_old;
+  for (uint32_t i = threadIdx.x; i < n; i += 1024) p[i] = z[i] + beta * p[i];
+  if (threadIdx.x == 0) { st->rz_old = rz_new; st->r_norm = r_norm; st->pcg_iters = iters; if (iters >= max_it) st->pcg_done = 1; }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------------
+static uint32_t tri_count(uint32_t nb) { return (uint32_t)((uint64_t)nb * (nb + 1) / 2); }
+
+// in-place Cholesky of the npad x npad matrix at L; returns through st->chol_fail
+static apex_status dense_cholesky(Ctx& c, double* L, uint32_t npad) {
+  cudaStream_t s = c.stream;
+  const size_t ld = npad;
+  static bool attr_set = false;
+  const int smem = 2 * NB * PLD * (int)sizeof(double);
+  const int trsm_smem_bytes = 2 * NB * (NB + 1) * (int)sizeof(double);
+  if (!attr_set) {
+    APEX_CUDA_TRY(c, cudaFuncSetAttribute(chol_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    APEX_CUDA_TRY(c, cudaFuncSetAttribute(chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_smem_bytes));
+    attr_set = true;
+  }
+  const uint32_t nblk = npad / NB;
+  for (uint32_t kb = 0; kb < nblk; ++kb) {
+    const uint32_t k0 = kb * NB;
+    chol_potrf_kernel<<<1, 256, 0, s>>>(L, ld, k0, c.state.p);
+    c.launches++;
+    const uint32_t rem = nblk - kb - 1;
+    if (rem == 0) break;
+    chol_trsm_kernel<<<rem, 256, trsm_smem_bytes, s>>>(L, ld, k0);
+    chol_syrk_kernel<<<tri_count(rem), 128, smem, s>>>(L, ld, k0);
+    c.launches += 2;
+  }
+  APEX_CUDA_TRY(c, cudaGetLastError());
+  return APEX_OK;
+}
+
+static apex_status dense_cholesky_solve(Ctx& c, const double* L, uint32_t npad, double* v) {
+  cudaStream_t s = c.stream;
+  const size_t ld = npad;
+  const uint32_t nblk = npad / NB;
+  for (uint32_t kb = 0; kb < nblk; ++kb) {
+    const uint32_t k0 = kb * NB;
+    trsv_diag_kernel<<<1, NB, 0, s>>>(L, ld, k0, v, 0);
+    c.launches++;
+    const uint32_t rows = npad - k0 - NB;
+    if (rows) { trsv_update_fwd_kernel<<<(rows + 31) / 32, 256, 0, s>>>(L, ld, k0, v, npad); c.launches++; }
+  }
+  for (uint32_t kb = nblk; kb-- > 0;) {
+    const uint32_t k0 = kb * NB;
+    trsv_diag_kernel<<<1, NB, 0, s>>>(L, ld, k0, v, 1);
+    c.launches++;
+    if (k0) { trsv_update_bwd_kernel<<<(k0 + 255) / 256, 256, 0, s>>>(L, ld, k0, v); c.launches++; }
+  }
+  APEX_CUDA_TRY(c, cudaGetLastError());
+  return APEX_OK;
+}
+
+// SparseSchurComplementSolver::solve_augmented_equation steps 2-8 (explicit_schur.rs:1162-1234) on the current
+// linearization. Leaves the camera step in c.step_cam and the landmark step in c.step_pt.
+apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol) {
+  cudaStream_t s = c.stream;
+  const uint32_t n = c.ncam * c.dc;
+  const uint32_t npad = (n + NB - 1) / NB * NB;
+  const size_t ld = npad;
+  const size_t nn = (size_t)npad * npad;
+  APEX_CUDA_TRY(c, c.S.alloc(nn * (use_pcg ? 1 : 2)));  // [S | factor workspace]
+  APEX_CUDA_TRY(c, c.dvec.alloc((size_t)npad * 2 + 8));
+  double* S = c.S.p;
+  APEX_CUDA_TRY(c, cudaMemsetAsync(S, 0, nn * sizeof(double), s));
+  // --- S ---
+  if (c.ntiles) {
+    FormArgs fa{c.tiles.p, c.slot_cam.p, c.slot_lp.p, c.pt_slot0.p, c.pt_cnt.p, c.J.p, c.hinv.p, S, ld, c.npl};
+    switch (c.dc) {
+      case 6: schur_form_kernel<6><<<c.ntiles, TILE, 0, s>>>(fa); break;
+      case 9: schur_form_kernel<9><<<c.ntiles, TILE, 0, s>>>(fa); break;
+      case 10: schur_form_kernel<10><<<c.ntiles, TILE, 0, s>>>(fa); break;
+      case 12: schur_form_kernel<12><<<c.ntiles, TILE, 0, s>>>(fa); break;
+      case 14: schur_form_kernel<14><<<c.ntiles, TILE, 0, s>>>(fa); break;
+      default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
+    }
+    c.launches++;
+  }
+  {
+    const size_t total = (size_t)c.ncam * c.dc * c.dc + (npad - n);
+    schur_diag_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(S, ld, c.hcc.p, c.state.p, c.ncam, c.dc, n, npad, c.rank == 0 ? 1 : 0);
+    c.launches++;
+  }
+  APEX_CUDA_TRY(c, cudaGetLastError());
+  APEX_TRY(allreduce_sum(c, S, nn));
+  {
+    const uint32_t nt = npad / 32;
+    symmetrize_drop_kernel<<<tri_count(nt), dim3(32, 8), 0, s>>>(S, ld, nt);
+    c.launches++;
+  }
+  // --- reduced gradient ---
+  APEX_TRY(launch_reduced_gradient(c, c.vb.p));
+  APEX_CUDA_TRY(c, cudaGetLastError());
+
+  if (!use_pcg) {
+    double* L = S + nn;
+    double* v = c.dvec.p;
+    double reg = 0.0, base = 0.0;
+    bool solved = false;
+    for (int attempt = -1; attempt < 5 && !solved; ++attempt) {
+      if (attempt >= 0) {
+        if (attempt == 0) {
+          diag_stats_kernel<<<1, 1024, 0, s>>>(S, ld, n, v + npad);
+          c.launches++;
+          double h2[2];
+          APEX_CUDA_TRY(c, cudaMemcpyAsync(h2, v + npad, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+          APEX_CUDA_TRY(c, cudaStreamSynchronize(s));
+          base = std::max(std::max(h2[0] / (double)n, h2[1]), 1.0);
+        }
+        reg = base * std::pow(10.0, attempt - 4);
+      }
+      APEX_CUDA_TRY(c, cudaMemcpyAsync(L, S, nn * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      if (reg != 0.0) { add_diag_kernel<<<(n + 255) / 256, 256, 0, s>>>(L, ld, n, reg); c.launches++; }
+      APEX_CUDA_TRY(c, cudaMemsetAsync(&c.state.p->chol_fail, 0, sizeof(int32_t), s));
+      APEX_TRY(dense_cholesky(c, L, npad));
+      APEX_TRY(sync_state(c));
+      if (c.h_state->singular_landmark) { c.err = "Landmark block singular"; return APEX_ERR_SINGULAR_MATRIX; }
+      solved = c.h_state->chol_fail == 0;
+    }
+    if (!solved) { c.err = "Schur complement singular after 5 regularization attempts"; return APEX_ERR_SINGULAR_MATRIX; }
+    APEX_CUDA_TRY(c, cudaMemsetAsync(v, 0, (size_t)npad * sizeof(double), s));
+    APEX_CUDA_TRY(c, cudaMemcpyAsync(v, c.vb.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    APEX_TRY(dense_cholesky_solve(c, L, npad, v));
+    APEX_CUDA_TRY(c, cudaMemcpyAsync(c.step_cam.p, v, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    c.last_pcg_iters = 0;
+  } else {
+    double* dinv = c.dvec.p;
+    jacobi_diag_kernel<<<(n + 255) / 256, 256, 0, s>>>(S, ld, n, dinv);
+    dense_pcg_init_kernel<<<1, 1024, 0, s>>>(c.vb.p, dinv, c.step_cam.p, c.vr.p, c.vz.p, c.vp.p, c.state.p, n, cg_max_it, cg_tol);
+    c.launches += 2;
+    const int BATCH = 10;
+    int enq = 0;
+    while (enq < cg_max_it) {
+      const int nb = std::min(BATCH, cg_max_it - enq);
+      for (int i = 0; i < nb; ++i) {
+        dense_symv_kernel<<<(n + 7) / 8, 256, 0, s>>>(S, ld, c.vp.p, c.vy.p, n, c.state.p);
+        dense_pcg_step_kernel<<<1, 1024, 0, s>>>(c.vy.p, dinv, c.step_cam.p, c.vr.p, c.vz.p, c.vp.p, c.state.p, n);
+        c.launches += 2;
+      }
+      APEX_CUDA_TRY(c, cudaGetLastError());
+      enq += nb;
+      APEX_TRY(sync_state(c));
+      if (c.h_state->pcg_done) break;
+    }
+    if (cg_max_it <= 0) APEX_TRY(sync_state(c));
+    c.last_pcg_iters = c.h_state->pcg_iters;
+    if (c.h_state->singular_landmark) { c.err = "Landmark block singular"; return APEX_ERR_SINGULAR_MATRIX; }
+  }
+  // --- back-substitution (explicit_schur.rs:980-1029) ---
+  APEX_TRY(launch_schur_tiles(c, MODE_BACKSUB, c.step_cam.p, nullptr, 0));
+  return APEX_OK;
+}
+
+}  // namespace apex

@@ -1,0 +1,44 @@
+// kernels_common.cuh — small shared device helpers: deterministic block reductions, cache-hinted loads,
+// FP64 reduction to global memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace apex {
+
+// Fixed-order block reduction (blockDim.x a power of two <= 1024); result valid in thread 0.
+__device__ __forceinline__ double block_reduce_sum(double v, double* sh /*[blockDim.x]*/) {
+  const int tid = threadIdx.x;
+  sh[tid] = v;
+  __syncthreads();
+  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if (tid < s) sh[tid] += sh[tid + s];
+    __syncthreads();
+  }
+  double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// out = sum(in[0..n)) with one CTA; the summation tree depends only on n => run-to-run deterministic.
+static __global__ void __launch_bounds__(1024) reduce_sum_kernel(const double* __restrict__ in, size_t n, double* __restrict__ out) {
+  __shared__ double sh[1024];
+  double v = 0.0;
+  for (size_t i = threadIdx.x; i < n; i += 1024) v += in[i];
+  v = block_reduce_sum(v, sh);
+  if (threadIdx.x == 0) *out = v;
+}
+
+// streaming 8-byte load that does not allocate in L1 (Jacobian planes are read exactly once per kernel)
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
+// fire-and-forget FP64 add into L2 (REDG.E.ADD.F64)
+__device__ __forceinline__ void red_add(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+}  // namespace apex

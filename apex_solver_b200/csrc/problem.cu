@@ -1,0 +1,227 @@
+// problem.cu — apex_problem_upload: replaces Problem construction + initialize_optimization_state
+// (src/core/problem.rs:518-808, src/optimizer/mod.rs:522-563) for the SoA factor graph of
+// bin/bundle_adjustment.rs:212-441. Builds the static observation structure described in apex_ctx.h:
+// landmark sharding across ranks, point-major tiles, camera-major work items.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "apex_ctx.h"
+#include "ba_device.cuh"
+
+namespace apex {
+
+template <typename T>
+static cudaError_t upload_vec(DevBuf<T>& buf, const std::vector<T>& v, cudaStream_t s) {
+  cudaError_t e = buf.alloc(v.size());
+  if (e != cudaSuccess) return e;
+  if (v.empty()) return cudaSuccess;
+  return cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
+  // ---- validation (same failures as the reference / oracle) ----
+  int K = model_intr_dim(d->camera_model);
+  if (K < 0) { c.err = "camera model not supported on the GPU path"; return APEX_ERR_UNSUPPORTED; }
+  if (d->intr_dim != K) { c.err = "intr_dim does not match camera model"; return APEX_ERR_INVALID_INPUT; }
+  if ((d->opt_flags & (APEX_OPT_POSE | APEX_OPT_LANDMARK)) != (APEX_OPT_POSE | APEX_OPT_LANDMARK)) {
+    c.err = "only BundleAdjustment / SelfCalibration OptimizeParams are live (bin/bundle_adjustment.rs)";
+    return APEX_ERR_UNSUPPORTED;
+  }
+  if (d->ncam == 0) { c.err = "No camera variables found"; return APEX_ERR_INVALID_INPUT; }    // explicit_schur.rs:278-282
+  if (d->npts == 0) { c.err = "No landmark variables found"; return APEX_ERR_INVALID_INPUT; }  // explicit_schur.rs:283-287
+  if (d->nobs > 0xFFFFFFF0ull) { c.err = "too many observations for u32 slots"; return APEX_ERR_UNSUPPORTED; }
+  if (d->loss_id < APEX_LOSS_NONE || d->loss_id > APEX_LOSS_T_DISTRIBUTION) { c.err = "unknown loss id"; return APEX_ERR_INVALID_INPUT; }
+  const uint64_t nobs = d->nobs;
+  for (uint64_t o = 0; o < nobs; ++o)
+    if (d->obs_cam[o] >= d->ncam || d->obs_pt[o] >= d->npts) { c.err = "observation index out of range"; return APEX_ERR_INVALID_INPUT; }
+
+  c.have_problem = false;
+  c.linearized = false;
+  c.model = d->camera_model; c.K = K; c.opt = d->opt_flags;
+  c.opt_intr = (d->opt_flags & APEX_OPT_INTRINSIC) != 0;
+  c.intr_vars = d->intr_vars_present != 0;
+  c.dc = 6 + (c.opt_intr ? K : 0);
+  c.np = 2 * (c.dc + 3);
+  c.ncam = d->ncam; c.npts = d->npts; c.nobs = nobs;
+  c.cam_dof_ref = (uint64_t)c.ncam * (6 + ((c.opt_intr || c.intr_vars) ? K : 0));
+  c.loss_id = d->loss_id;
+  for (int i = 0; i < 4; ++i) c.loss_p[i] = d->loss_params[i];
+
+  // ---- landmark sharding: contiguous ranges balanced by observation count ----
+  std::vector<uint64_t> pt_start((size_t)c.npts + 1, 0);
+  for (uint64_t o = 0; o < nobs; ++o) pt_start[d->obs_pt[o] + 1]++;
+  for (uint32_t p = 0; p < c.npts; ++p) pt_start[p + 1] += pt_start[p];
+  auto boundary = [&](int r) -> uint32_t {
+    if (r <= 0) return 0;
+    if (r >= c.nranks) return c.npts;
+    if (nobs == 0) return (uint32_t)((uint64_t)c.npts * r / c.nranks);
+    uint64_t target = nobs * (uint64_t)r / (uint64_t)c.nranks;
+    return (uint32_t)(std::lower_bound(pt_start.begin(), pt_start.begin() + c.npts, target) - pt_start.begin());
+  };
+  c.p0 = boundary(c.rank);
+  c.p1 = boundary(c.rank + 1);
+  c.npl = c.p1 - c.p0;
+  c.nobs_local = pt_start[c.p1] - pt_start[c.p0];
+
+  // ---- point-major order of the local observations (stable in the caller's insertion order) ----
+  std::vector<uint64_t> pm(c.nobs_local);
+  {
+    std::vector<uint64_t> cur(pt_start.begin() + c.p0, pt_start.begin() + c.p1);
+    const uint64_t base = pt_start[c.p0];
+    for (uint64_t o = 0; o < nobs; ++o) {
+      uint32_t p = d->obs_pt[o];
+      if (p >= c.p0 && p < c.p1) pm[cur[p - c.p0]++ - base] = o;
+    }
+  }
+
+  // ---- tiles ----
+  std::vector<TileDesc> tiles;
+  std::vector<uint32_t> pt_slot0(c.npl), pt_cnt(c.npl);
+  uint32_t chunk = 0;
+  {
+    uint32_t cur_pt0 = 0, cur_npt = 0, cur_obs = 0;
+    auto flush = [&]() {
+      if (cur_npt == 0) return;
+      tiles.push_back({cur_pt0, cur_npt, chunk, 1});
+      chunk += 1;
+      cur_npt = 0; cur_obs = 0;
+    };
+    for (uint32_t lp = 0; lp < c.npl; ++lp) {
+      uint64_t k64 = pt_start[c.p0 + lp + 1] - pt_start[c.p0 + lp];
+      uint32_t k = (uint32_t)k64;
+      pt_cnt[lp] = k;
+      if (k > (uint32_t)TILE) {
+        flush();
+        uint32_t nch = (k + TILE - 1) / TILE;
+        tiles.push_back({lp, 1, chunk, nch});
+        pt_slot0[lp] = chunk * TILE;
+        chunk += nch;
+        continue;
+      }
+      if (cur_npt > 0 && (cur_obs + k > (uint32_t)TILE || cur_npt >= (uint32_t)TILE)) flush();
+      if (cur_npt == 0) cur_pt0 = lp;
+      pt_slot0[lp] = chunk * TILE + cur_obs;
+      cur_npt++;
+      cur_obs += k;
+    }
+    flush();
+  }
+  c.ntiles = (uint32_t)tiles.size();
+  c.nchunks = chunk;
+  c.nslots = (size_t)chunk * TILE;
+  c.h_pt_cnt = pt_cnt;
+
+  // ---- slot arrays ----
+  std::vector<uint32_t> slot_cam(c.nslots, PAD_CAM);
+  std::vector<uint16_t> slot_lp(c.nslots, 0);
+  std::vector<double> slot_uv(c.nslots * 2, 0.0);
+  c.slot_obs.assign(c.nslots, UINT64_MAX);
+  {
+    uint64_t q = 0;
+    for (const TileDesc& t : tiles) {
+      for (uint32_t i = 0; i < t.npt; ++i) {
+        uint32_t lp = t.pt0 + i;
+        for (uint32_t k = 0; k < pt_cnt[lp]; ++k, ++q) {
+          size_t slot = (size_t)pt_slot0[lp] + k;
+          uint64_t o = pm[q];
+          slot_cam[slot] = d->obs_cam[o];
+          slot_lp[slot] = (uint16_t)i;
+          size_t ch = slot / TILE, lane = slot % TILE;
+          slot_uv[(ch * 2 + 0) * TILE + lane] = d->obs_uv[2 * o];
+          slot_uv[(ch * 2 + 1) * TILE + lane] = d->obs_uv[2 * o + 1];
+          c.slot_obs[slot] = o;
+        }
+      }
+    }
+  }
+
+  // ---- camera-major copy of the local observations + work items ----
+  std::vector<uint32_t> cam_start((size_t)c.ncam + 1, 0);
+  for (uint64_t q = 0; q < c.nobs_local; ++q) cam_start[d->obs_cam[pm[q]] + 1]++;
+  for (uint32_t k = 0; k < c.ncam; ++k) cam_start[k + 1] += cam_start[k];
+  std::vector<double> cm_uv(2 * (size_t)c.nobs_local);
+  std::vector<uint32_t> cm_lp(c.nobs_local);
+  {
+    std::vector<uint32_t> cur(cam_start.begin(), cam_start.end() - 1);
+    uint64_t q = 0;
+    for (uint32_t lp = 0; lp < c.npl; ++lp)
+      for (uint32_t k = 0; k < pt_cnt[lp]; ++k, ++q) {
+        uint64_t o = pm[q];
+        uint32_t pos = cur[d->obs_cam[o]]++;
+        cm_uv[pos] = d->obs_uv[2 * o];
+        cm_uv[(size_t)c.nobs_local + pos] = d->obs_uv[2 * o + 1];
+        cm_lp[pos] = lp;
+      }
+  }
+  std::vector<CamItem> items;
+  std::vector<uint32_t> cam_item_start((size_t)c.ncam + 1, 0);
+  for (uint32_t k = 0; k < c.ncam; ++k) {
+    cam_item_start[k] = (uint32_t)items.size();
+    for (uint32_t b = cam_start[k]; b < cam_start[k + 1]; b += CAM_CHUNK)
+      items.push_back({k, b, std::min<uint32_t>(b + CAM_CHUNK, cam_start[k + 1]), 0});
+  }
+  cam_item_start[c.ncam] = (uint32_t)items.size();
+  c.nitems = (uint32_t)items.size();
+
+  // ---- fixed masks ----
+  std::vector<uint8_t> pose_fixed(c.ncam, 0), pt_fixed(c.npl, 0);
+  std::vector<uint16_t> intr_fixed(c.ncam, 0);
+  if (d->pose_fixed) std::copy(d->pose_fixed, d->pose_fixed + c.ncam, pose_fixed.begin());
+  if (d->intr_fixed) std::copy(d->intr_fixed, d->intr_fixed + c.ncam, intr_fixed.begin());
+  if (d->pt_fixed) std::copy(d->pt_fixed + c.p0, d->pt_fixed + c.p1, pt_fixed.begin());
+
+  // ---- to the device ----
+  cudaStream_t s = c.stream;
+  APEX_CUDA_TRY(c, upload_vec(c.tiles, tiles, s));
+  APEX_CUDA_TRY(c, upload_vec(c.slot_cam, slot_cam, s));
+  APEX_CUDA_TRY(c, upload_vec(c.slot_lp, slot_lp, s));
+  APEX_CUDA_TRY(c, upload_vec(c.slot_uv, slot_uv, s));
+  APEX_CUDA_TRY(c, upload_vec(c.pt_slot0, pt_slot0, s));
+  APEX_CUDA_TRY(c, upload_vec(c.pt_cnt, pt_cnt, s));
+  APEX_CUDA_TRY(c, upload_vec(c.items, items, s));
+  APEX_CUDA_TRY(c, upload_vec(c.cam_item_start, cam_item_start, s));
+  APEX_CUDA_TRY(c, upload_vec(c.cm_uv, cm_uv, s));
+  APEX_CUDA_TRY(c, upload_vec(c.cm_lp, cm_lp, s));
+  APEX_CUDA_TRY(c, upload_vec(c.pose_fixed, pose_fixed, s));
+  APEX_CUDA_TRY(c, upload_vec(c.intr_fixed, intr_fixed, s));
+  APEX_CUDA_TRY(c, upload_vec(c.pt_fixed, pt_fixed, s));
+
+  const size_t ncd = (size_t)c.ncam * c.dc;
+  const int pb = 36 + K * K;
+  APEX_CUDA_TRY(c, c.pose.alloc((size_t)c.ncam * 7));
+  APEX_CUDA_TRY(c, c.intr.alloc((size_t)c.ncam * K));
+  APEX_CUDA_TRY(c, c.pt.alloc((size_t)c.npl * 3));
+  APEX_CUDA_TRY(c, c.J.alloc((size_t)c.nchunks * c.np * TILE));
+  APEX_CUDA_TRY(c, c.R.alloc((size_t)c.nchunks * 2 * TILE));
+  APEX_CUDA_TRY(c, c.hpp.alloc((size_t)c.npl * 6));
+  APEX_CUDA_TRY(c, c.gp.alloc((size_t)c.npl * 3));
+  APEX_CUDA_TRY(c, c.hinv.alloc((size_t)c.npl * 6));
+  APEX_CUDA_TRY(c, c.hcc.alloc(ncd * c.dc + ncd));
+  c.gc = c.hcc.p + ncd * c.dc;
+  const size_t nacc_max = (size_t)c.dc * (c.dc + 1) / 2 + c.dc + 64;
+  APEX_CUDA_TRY(c, c.partial.alloc((size_t)std::max<uint32_t>(c.nitems, 1) * nacc_max));
+  APEX_CUDA_TRY(c, c.sj.alloc((size_t)c.ncam * pb));
+  APEX_CUDA_TRY(c, c.pinv.alloc((size_t)c.ncam * pb));
+  APEX_CUDA_TRY(c, c.vb.alloc(ncd));
+  APEX_CUDA_TRY(c, c.vx.alloc(ncd));
+  APEX_CUDA_TRY(c, c.vr.alloc(ncd));
+  APEX_CUDA_TRY(c, c.vz.alloc(ncd));
+  APEX_CUDA_TRY(c, c.vp.alloc(ncd));
+  APEX_CUDA_TRY(c, c.vy.alloc(ncd));
+  APEX_CUDA_TRY(c, c.step_cam.alloc(ncd));
+  APEX_CUDA_TRY(c, c.step_pt.alloc((size_t)c.npl * 3));
+  APEX_CUDA_TRY(c, c.red_scratch.alloc(8 * (size_t)std::max<uint32_t>(std::max<uint32_t>(c.nchunks, c.ncam), 1024u) + 64));
+  APEX_CUDA_TRY(c, cudaMemsetAsync(c.step_cam.p, 0, ncd * sizeof(double), s));
+  APEX_CUDA_TRY(c, cudaMemsetAsync(c.step_pt.p, 0, std::max<size_t>((size_t)c.npl * 3, 1) * sizeof(double), s));
+
+  APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pose.p, d->pose, (size_t)c.ncam * 7 * sizeof(double), cudaMemcpyHostToDevice, s));
+  APEX_CUDA_TRY(c, cudaMemcpyAsync(c.intr.p, d->intr, (size_t)c.ncam * K * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (c.npl)
+    APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pt.p, d->pt + 3 * (size_t)c.p0, (size_t)c.npl * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+  APEX_CUDA_TRY(c, cudaStreamSynchronize(s));  // the host vectors above die with this scope
+  c.have_problem = true;
+  return APEX_OK;
+}
+
+}  // namespace apex

@@ -1,0 +1,291 @@
+"""Parity of the sm_100a path (through the C ABI of include/apex_gpu.h) against the TEST ORACLE on the same
+seeded inputs. `-m gpu` only. Tolerances follow BASELINE.json north_star: per-iteration cost <= 1e-9
+relative, final cost / parameters <= 1e-6 relative, identical LM iteration count and termination status;
+unit stages are held much tighter (element-wise FP64 work is compiled without FMA contraction, so it
+differs from the CPU only through libm and summation order).
+"""
+import numpy as np
+import pytest
+
+from apex_solver_b200 import _ffi as F, synth
+from apex_solver_b200.context import GpuContext
+from oracle_backend import OracleContext
+
+pytestmark = pytest.mark.gpu
+
+COST_ITER_RTOL = 1e-9   # north_star: per-iteration cost
+FINAL_RTOL = 1e-6       # north_star: final cost and parameters
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = max(np.abs(b).max(initial=0.0), 1e-300)
+    return float(np.abs(a - b).max(initial=0.0) / scale)
+
+
+def small_problem(model=F.CAM_BAL, self_cal=True, loss=(F.LOSS_HUBER, 1.0), ncam=12, npts=400, track=4.0, seed=7, **kw):
+    return synth.make_problem(ncam, npts, track, camera_model=model, loss=loss, seed=seed, self_calibration=self_cal, **kw)
+
+
+def pair(prob):
+    return GpuContext().upload(prob), OracleContext().upload(prob)
+
+
+CASES = [
+    ("bal_selfcal_huber", dict(model=F.CAM_BAL, self_cal=True, loss=(F.LOSS_HUBER, 1.0))),
+    ("bal_ba_huber", dict(model=F.CAM_BAL, self_cal=False, loss=(F.LOSS_HUBER, 1.0))),
+    ("bal_selfcal_l2", dict(model=F.CAM_BAL, self_cal=True, loss=(F.LOSS_L2,))),
+    ("bal_selfcal_noloss", dict(model=F.CAM_BAL, self_cal=True, loss=(F.LOSS_NONE,))),
+    ("pinhole_selfcal_cauchy", dict(model=F.CAM_PINHOLE, self_cal=True, loss=(F.LOSS_CAUCHY, 1.0))),
+    ("kb_selfcal_cauchy", dict(model=F.CAM_KANNALA_BRANDT, self_cal=True, loss=(F.LOSS_CAUCHY, 1.0))),
+    ("ds_selfcal_cauchy", dict(model=F.CAM_DOUBLE_SPHERE, self_cal=True, loss=(F.LOSS_CAUCHY, 1.0))),
+    ("kb_ba_huber", dict(model=F.CAM_KANNALA_BRANDT, self_cal=False, loss=(F.LOSS_HUBER, 2.0))),
+    ("bal_selfcal_andrews", dict(model=F.CAM_BAL, self_cal=True, loss=(F.LOSS_ANDREWS, 3.0))),  # rho'' > 0: corrector 2nd branch
+    ("bal_selfcal_tukey", dict(model=F.CAM_BAL, self_cal=True, loss=(F.LOSS_TUKEY, 4.0))),
+    ("bal_shuffled", dict(model=F.CAM_BAL, self_cal=True, shuffle_obs=True)),
+]
+
+
+@pytest.mark.parametrize("name,kw", CASES, ids=[c[0] for c in CASES])
+def test_linearize_blocks_cost_matvec(name, kw):
+    prob = small_problem(**kw)
+    g, o = pair(prob)
+    lam = 1e-3
+    assert abs(g.cost() - o.cost()) <= 1e-13 * abs(o.cost())
+    g.linearize(lam); o.linearize(lam)
+    rg, jcg, jpg = g.get_linearization()
+    ro, jco, jpo = o.get_linearization()
+    assert relerr(rg, ro) < 1e-13, "residuals"
+    assert relerr(jcg, jco) < 1e-12, "camera Jacobian blocks"
+    assert relerr(jpg, jpo) < 1e-12, "landmark Jacobian blocks"
+    hg = g.get_blocks(); ho = o.get_blocks()
+    for a, b, what in zip(hg, ho, ("H_cc", "g_c", "H_pp", "g_p", "H_pp^-1")):
+        assert relerr(a, b) < 1e-11, what
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(prob.ncam * prob.dc)
+    yg, yo = g.schur_matvec(x), o.schur_matvec(x)
+    assert relerr(yg, yo) < 1e-11, "Schur operator"
+
+
+@pytest.mark.parametrize("variant", [F.SCHUR_EXPLICIT, F.SCHUR_IMPLICIT, F.SCHUR_EXPLICIT_PCG], ids=["explicit", "implicit", "explicit_pcg"])
+@pytest.mark.parametrize("self_cal", [True, False], ids=["selfcal", "ba"])
+def test_solve_augmented(variant, self_cal):
+    prob = small_problem(self_cal=self_cal, ncam=10, npts=300)
+    g, o = pair(prob)
+    lam = 1e-2
+    sg = g.solve_augmented(variant, lam, cg_max_iterations=500, cg_tolerance=1e-12)
+    so = o.solve_augmented(variant, lam, cg_max_iterations=500, cg_tolerance=1e-12)
+    assert abs(sg[2] - so[2]) <= 1e-12 * so[2], "gradient norm"
+    # both solve the same SPD system to 1e-12: steps agree to solver accuracy
+    assert relerr(sg[0], so[0]) < 1e-7, "camera step"
+    assert relerr(sg[1], so[1]) < 1e-7, "landmark step"
+    if variant == F.SCHUR_EXPLICIT:
+        assert relerr(sg[0], so[0]) < 1e-9
+
+
+@pytest.mark.parametrize("precond", [F.PRECOND_NONE, F.PRECOND_BLOCK_DIAGONAL, F.PRECOND_SCHUR_JACOBI], ids=["none", "blockdiag", "schurjacobi"])
+def test_pcg_iteration_counts_match(precond):
+    prob = small_problem(ncam=10, npts=300)
+    g, o = pair(prob)
+    sg = g.solve_augmented(F.SCHUR_IMPLICIT, 1e-2, precond=precond, cg_max_iterations=30, cg_tolerance=1e-6)
+    so = o.solve_augmented(F.SCHUR_IMPLICIT, 1e-2, precond=precond, cg_max_iterations=30, cg_tolerance=1e-6)
+    assert sg[3] == so[3], "PCG iterations"
+    assert relerr(sg[0], so[0]) < 1e-8
+    assert relerr(sg[1], so[1]) < 1e-8
+
+
+def run_lm(ctx, variant, max_it=8, cg_it=200, **cfgkw):
+    cfg = ctx.default_config(True)
+    cfg.schur_variant = variant
+    cfg.max_iterations = max_it
+    cfg.cg_max_iterations = cg_it
+    for k, v in cfgkw.items():
+        setattr(cfg, k, v)
+    return ctx.lm_solve(cfg)
+
+
+LM_CASES = [
+    ("bal_selfcal_explicit", dict(model=F.CAM_BAL, self_cal=True), F.SCHUR_EXPLICIT),
+    ("bal_selfcal_implicit", dict(model=F.CAM_BAL, self_cal=True), F.SCHUR_IMPLICIT),
+    ("bal_selfcal_explicit_pcg", dict(model=F.CAM_BAL, self_cal=True), F.SCHUR_EXPLICIT_PCG),
+    ("bal_ba_implicit", dict(model=F.CAM_BAL, self_cal=False), F.SCHUR_IMPLICIT),
+    ("bal_ba_explicit", dict(model=F.CAM_BAL, self_cal=False), F.SCHUR_EXPLICIT),
+    ("kb_selfcal_explicit", dict(model=F.CAM_KANNALA_BRANDT, self_cal=True, loss=(F.LOSS_CAUCHY, 1.0)), F.SCHUR_EXPLICIT),
+    ("ds_selfcal_explicit", dict(model=F.CAM_DOUBLE_SPHERE, self_cal=True, loss=(F.LOSS_CAUCHY, 1.0)), F.SCHUR_EXPLICIT),
+    ("ds_selfcal_implicit", dict(model=F.CAM_DOUBLE_SPHERE, self_cal=True, loss=(F.LOSS_CAUCHY, 1.0)), F.SCHUR_IMPLICIT),
+    ("pinhole_selfcal_implicit", dict(model=F.CAM_PINHOLE, self_cal=True), F.SCHUR_IMPLICIT),
+]
+
+
+@pytest.mark.parametrize("name,kw,variant", LM_CASES, ids=[c[0] for c in LM_CASES])
+def test_lm_solve_parity(name, kw, variant):
+    prob = small_problem(ncam=16, npts=600, **kw)
+    g, o = pair(prob)
+    rg, tg = run_lm(g, variant)
+    ro, to = run_lm(o, variant)
+    assert rg.status == ro.status, "termination status"
+    assert rg.iterations == ro.iterations, "LM iteration count"
+    assert abs(rg.initial_cost - ro.initial_cost) <= 1e-13 * ro.initial_cost
+    for a, b in zip(tg, to):
+        assert a.accepted == b.accepted, f"accept/reject at iteration {b.iteration}"
+        assert abs(a.cost - b.cost) <= COST_ITER_RTOL * abs(b.cost), f"cost at iteration {b.iteration}: {a.cost} vs {b.cost}"
+        assert abs(a.tr_radius - b.tr_radius) <= 1e-6 * abs(b.tr_radius), "damping"
+    assert abs(rg.final_cost - ro.final_cost) <= FINAL_RTOL * abs(ro.final_cost)
+    pg, po = g.params_download(), o.params_download()
+    for a, b, what in zip(pg, po, ("poses", "intrinsics", "landmarks")):
+        assert relerr(a, b) < FINAL_RTOL, what
+    assert rg.successful_steps == ro.successful_steps and rg.unsuccessful_steps == ro.unsuccessful_steps
+    assert rg.cost_evaluations == ro.cost_evaluations and rg.jacobian_evaluations == ro.jacobian_evaluations
+
+
+def test_lm_ladybug49_shape_explicit():
+    """BASELINE.json configs[0]: Ladybug problem-49-7776 shape, LM + explicit Schur (direct), full size."""
+    prob = synth.make_shape("ladybug49")
+    g, o = pair(prob)
+    rg, tg = run_lm(g, F.SCHUR_EXPLICIT, max_it=20)
+    ro, to = run_lm(o, F.SCHUR_EXPLICIT, max_it=20)
+    assert (rg.status, rg.iterations) == (ro.status, ro.iterations)
+    for a, b in zip(tg, to):
+        assert a.accepted == b.accepted
+        assert abs(a.cost - b.cost) <= COST_ITER_RTOL * abs(b.cost), f"iteration {b.iteration}"
+    assert abs(rg.final_cost - ro.final_cost) <= FINAL_RTOL * ro.final_cost
+
+
+def test_lm_trafalgar_shape_implicit_scaled():
+    """BASELINE.json configs[1] shape at 1/4 scale (the oracle's single-threaded operator bounds the size)."""
+    prob = synth.make_shape("trafalgar257", scale=0.25)
+    g, o = pair(prob)
+    rg, tg = run_lm(g, F.SCHUR_IMPLICIT, max_it=6)
+    ro, to = run_lm(o, F.SCHUR_IMPLICIT, max_it=6)
+    assert (rg.status, rg.iterations) == (ro.status, ro.iterations)
+    for a, b in zip(tg, to):
+        assert a.accepted == b.accepted
+        assert a.ls_iter == b.ls_iter, f"PCG iterations at LM iteration {b.iteration}"
+        assert abs(a.cost - b.cost) <= COST_ITER_RTOL * abs(b.cost), f"iteration {b.iteration}"
+    assert abs(rg.final_cost - ro.final_cost) <= FINAL_RTOL * ro.final_cost
+
+
+# ---- edge cases the reference's tests cover -------------------------------------------
+def test_long_tracks_span_several_chunks():
+    """A landmark seen by more cameras than one 256-slot tile holds."""
+    prob = synth.make_problem(700, 40, 5.0, seed=11, window_frac=0.5)
+    # give landmark 3 an observation in every camera
+    rng = np.random.default_rng(0)
+    extra_cam = np.arange(prob.ncam, dtype=np.uint32)
+    keep = prob.obs_pt != 3
+    obs_cam = np.concatenate([prob.obs_cam[keep], extra_cam])
+    obs_pt = np.concatenate([prob.obs_pt[keep], np.full(prob.ncam, 3, np.uint32)])
+    uv = np.concatenate([prob.obs_uv[keep], rng.uniform(-300, 300, (prob.ncam, 2))])
+    prob2 = synth.BAProblem(camera_model=prob.camera_model, opt_flags=prob.opt_flags, pose=prob.pose, intr=prob.intr, pt=prob.pt,
+                            obs_cam=obs_cam, obs_pt=obs_pt, obs_uv=uv, loss_id=prob.loss_id, loss_params=prob.loss_params,
+                            pose_fixed=prob.pose_fixed, intr_fixed=prob.intr_fixed)
+    g, o = pair(prob2)
+    g.linearize(1e-3); o.linearize(1e-3)
+    for a, b, what in zip(g.get_blocks(), o.get_blocks(), ("H_cc", "g_c", "H_pp", "g_p", "H_pp^-1")):
+        assert relerr(a, b) < 1e-10, what
+    x = rng.standard_normal(prob2.ncam * prob2.dc)
+    assert relerr(g.schur_matvec(x), o.schur_matvec(x)) < 1e-10
+    for variant in (F.SCHUR_EXPLICIT, F.SCHUR_IMPLICIT):
+        sg = g.solve_augmented(variant, 1e-3, cg_max_iterations=400, cg_tolerance=1e-12)
+        so = o.solve_augmented(variant, 1e-3, cg_max_iterations=400, cg_tolerance=1e-12)
+        assert relerr(sg[0], so[0]) < 1e-6 and relerr(sg[1], so[1]) < 1e-6
+
+
+def test_unobserved_landmarks_and_invalid_projections():
+    """Landmarks without observations (H_pp = lambda I) and points behind the camera (zero rows, Ceres convention,
+    projection_factor.rs:227-239, :498-522)."""
+    prob = small_problem(ncam=8, npts=200)
+    # move a few landmarks behind every camera (BAL looks down -z: in front means p_cam.z < 0) by pushing them far away
+    prob.pt[5] = prob.pt[5] * 1e3
+    prob.pt[17] = -prob.pt[17] * 1e3
+    # drop all observations of landmarks 0..3
+    keep = prob.obs_pt >= 4
+    prob2 = synth.BAProblem(camera_model=prob.camera_model, opt_flags=prob.opt_flags, pose=prob.pose, intr=prob.intr, pt=prob.pt,
+                            obs_cam=prob.obs_cam[keep], obs_pt=prob.obs_pt[keep], obs_uv=prob.obs_uv[keep], loss_id=prob.loss_id,
+                            loss_params=prob.loss_params, pose_fixed=prob.pose_fixed, intr_fixed=prob.intr_fixed)
+    g, o = pair(prob2)
+    assert abs(g.cost() - o.cost()) <= 1e-13 * abs(o.cost())
+    g.linearize(1e-3); o.linearize(1e-3)
+    rg, jcg, jpg = g.get_linearization(); ro, jco, jpo = o.get_linearization()
+    assert np.array_equal(rg == 0.0, ro == 0.0), "zeroed residual rows"
+    assert (ro == 0.0).all(axis=1).any(), "the case must contain invalid projections"
+    for a, b, what in zip(g.get_blocks(), o.get_blocks(), ("H_cc", "g_c", "H_pp", "g_p", "H_pp^-1")):
+        assert relerr(a, b) < 1e-11, what
+    sg = g.solve_augmented(F.SCHUR_IMPLICIT, 1e-3, cg_max_iterations=300, cg_tolerance=1e-12)
+    so = o.solve_augmented(F.SCHUR_IMPLICIT, 1e-3, cg_max_iterations=300, cg_tolerance=1e-12)
+    assert relerr(sg[0], so[0]) < 1e-6 and relerr(sg[1], so[1]) < 1e-6
+    assert np.abs(sg[1][:4]).max() == 0.0, "unobserved landmarks do not move"
+
+
+def test_fixed_variables_are_zeroed_at_update_only():
+    """Problem::fix_variable: the step still contains the fixed DOF (norms include them); only the update masks them
+    (src/core/problem.rs:185-289)."""
+    prob = small_problem(ncam=8, npts=200, fix_first_intr=True)
+    prob.pt_fixed = np.zeros(prob.npts, np.uint8)
+    prob.pt_fixed[:10] = 0b101
+    g, o = pair(prob)
+    rg, tg = run_lm(g, F.SCHUR_EXPLICIT, max_it=3)
+    ro, to = run_lm(o, F.SCHUR_EXPLICIT, max_it=3)
+    assert (rg.status, rg.iterations) == (ro.status, ro.iterations)
+    for a, b in zip(tg, to):
+        assert abs(a.step_norm - b.step_norm) <= 1e-8 * b.step_norm
+        assert abs(a.cost - b.cost) <= COST_ITER_RTOL * b.cost
+    pg, po = g.params_download(), o.params_download()
+    assert relerr(pg[0][0], po[0][0]) < 1e-15, "fixed pose stays put"
+    assert np.array_equal(pg[1][0], prob.intr[0]), "fixed intrinsics stay put"
+    assert np.array_equal(pg[2][:10, 0], prob.pt[:10, 0]) and np.array_equal(pg[2][:10, 2], prob.pt[:10, 2])
+
+
+def test_error_behaviour():
+    g = GpuContext()
+    with pytest.raises(F.ApexError) as e:
+        g.cost()
+    assert e.value.status == F.ERR_INVALID_STATE
+    prob = small_problem(ncam=6, npts=60)
+    g.upload(prob)
+    with pytest.raises(F.ApexError) as e:
+        g.schur_matvec(np.zeros(prob.ncam * prob.dc))
+    assert e.value.status == F.ERR_INVALID_STATE  # not linearized
+    bad = small_problem(ncam=6, npts=60)
+    bad.obs_cam = bad.obs_cam.copy(); bad.obs_cam[0] = 99
+    with pytest.raises(F.ApexError) as e:
+        GpuContext().upload(bad)
+    assert e.value.status == F.ERR_INVALID_INPUT
+    cfg = g.default_config(True)
+    cfg.use_jacobi_scaling = 1
+    with pytest.raises(F.ApexError) as e:
+        g.lm_solve(cfg)
+    assert e.value.status == F.ERR_UNSUPPORTED
+
+
+def test_kernels_ran_on_the_device():
+    prob = small_problem(ncam=6, npts=60)
+    g = GpuContext().upload(prob)
+    n0 = g.kernel_launches()
+    g.linearize(1e-3)
+    g.solve_augmented(F.SCHUR_IMPLICIT, 1e-3)
+    assert g.kernel_launches() > n0 + 5
+
+
+# ---- size-independent properties at the full BASELINE.json shape -----------------------------------------
+def test_schur_operator_properties_trafalgar_full():
+    """configs[1] at full size (257 cams / 65k pts / ~226k obs): S is symmetric positive definite and linear;
+    S x = b solved by PCG reproduces b; the oracle agrees on the operator."""
+    prob = synth.make_shape("trafalgar257")
+    g = GpuContext().upload(prob)
+    lam = 1e-3
+    g.linearize(lam)
+    n = prob.ncam * prob.dc
+    rng = np.random.default_rng(5)
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    Sx, Sy = g.schur_matvec(x), g.schur_matvec(y)
+    assert abs(y @ Sx - x @ Sy) <= 1e-10 * abs(y @ Sx), "symmetry"
+    assert x @ Sx > 0 and y @ Sy > 0, "positive definite"
+    assert relerr(g.schur_matvec(2.0 * x - 3.0 * y), 2.0 * Sx - 3.0 * Sy) < 1e-11, "linearity"
+    o = OracleContext().upload(prob)
+    o.linearize(lam)
+    assert relerr(Sx, o.schur_matvec(x)) < 1e-10
+    # explicit and implicit variants solve the same system
+    s_imp = g.solve_augmented(F.SCHUR_IMPLICIT, lam, cg_max_iterations=2000, cg_tolerance=1e-13)
+    s_exp = g.solve_augmented(F.SCHUR_EXPLICIT, lam)
+    assert relerr(s_imp[0], s_exp[0]) < 1e-5 and relerr(s_imp[1], s_exp[1]) < 1e-5
