@@ -41,6 +41,17 @@ struct TileDesc {
   uint32_t nchunks;  // 1 for a normal tile; >1 only when npt == 1
 };
 
+// Two consecutive normal tiles (chunks 2s, 2s+1) processed together by the persistent Schur-operator kernel.
+struct SuperDesc {
+  uint32_t ptA0, nptA;   // landmarks of chunk 2s
+  uint32_t ptB0, nptB;   // landmarks of chunk 2s+1 (nptB = 0 and validB = 0 when there is none)
+  uint32_t nseg;         // distinct cameras among the <=512 observations
+  uint32_t validB;
+  uint32_t pad[2];
+};
+constexpr int STILE = 2 * TILE;       // slots per supertile
+constexpr int MAX_TILE_PTS = 128;     // landmarks per normal tile (so a supertile stages <= 256 landmark inverses)
+
 struct CamItem { uint32_t cam, begin, end, pad; };  // [begin,end) in the camera-major arrays
 
 // Scalars that live on the device (LM bookkeeping, PCG control, norms, error flags).
@@ -103,6 +114,7 @@ struct Ctx {
   uint32_t p0 = 0, p1 = 0, npl = 0;  // local landmark range
   uint64_t nobs_local = 0;
   uint32_t nchunks = 0, ntiles = 0, nitems = 0;
+  uint32_t nsuper = 0, ngiant = 0, nnormal_chunks = 0;
   size_t nslots = 0;
   std::vector<uint64_t> slot_obs;  // slot -> caller's observation index (UINT64_MAX for padding)
   std::vector<uint32_t> h_pt_cnt;
@@ -111,6 +123,14 @@ struct Ctx {
   DevBuf<TileDesc> tiles;
   DevBuf<uint32_t> slot_cam;
   DevBuf<uint16_t> slot_lp;
+  DevBuf<TileDesc> giant_tiles;      // the tiles with nchunks > 1 (a landmark with more than 256 observations)
+  DevBuf<SuperDesc> supers;
+  DevBuf<uint2> slot_meta;           // per slot: {camera, supertile-local landmark | camera-sorted position << 16}
+  DevBuf<uint32_t> pt_meta;          // per landmark: supertile-local first slot | count << 16
+  DevBuf<uint32_t> seg_cam;          // [nsuper][512] camera of each camera-segment
+  DevBuf<uint16_t> seg_begin;        // [nsuper][514] first sorted position of each segment (+ sentinel)
+  DevBuf<double> xpad;               // operator input at an even per-camera stride
+  DevBuf<double> ypart;              // [grid][ncam*dc] per-CTA private results of the persistent operator kernel
   DevBuf<double> slot_uv;            // [chunk][2][TILE]
   DevBuf<uint32_t> pt_slot0, pt_cnt; // per local landmark
   DevBuf<CamItem> items;
@@ -179,6 +199,7 @@ enum TileMode { MODE_MATVEC = 0, MODE_RHS = 1, MODE_BACKSUB = 2 };
 apex_status launch_schur_tiles(Ctx& c, int mode, const double* x, double* y, int check_done);
 apex_status launch_hcc_apply(Ctx& c, const double* x, double* y, int check_done);  // y = (H_cc + lambda I) x on rank 0, else 0
 apex_status schur_operator(Ctx& c, const double* x, double* y, int check_done);    // y = S x, all-reduced
+apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_done);  // this rank's part
 apex_status launch_reduced_gradient(Ctx& c, double* b);
 apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol);
 // explicit.cu

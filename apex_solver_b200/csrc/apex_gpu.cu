@@ -8,6 +8,7 @@
 
 #include "apex_ctx.h"
 #include "ba_device.cuh"
+#include "kernels_common.cuh"
 #include "nccl_dyn.h"
 
 struct apex_ctx { apex::Ctx c; };
@@ -146,6 +147,7 @@ void apex_ctx_destroy(apex_ctx* ctx) {
                            &c.sj, &c.pinv, &c.vb, &c.vx, &c.vr, &c.vz, &c.vp, &c.vy, &c.step_cam, &c.step_pt, &c.red_scratch, &c.S, &c.E,
                            &c.dvec, &c.l2flush};
   for (auto* b : dbl) b->release();
+  c.giant_tiles.release(); c.supers.release(); c.slot_meta.release(); c.pt_meta.release(); c.seg_cam.release(); c.seg_begin.release(); c.ypart.release(); c.xpad.release();
   c.tiles.release(); c.slot_cam.release(); c.slot_lp.release(); c.pt_slot0.release(); c.pt_cnt.release(); c.items.release();
   c.cam_item_start.release(); c.cm_lp.release(); c.pose_fixed.release(); c.pt_fixed.release(); c.intr_fixed.release();
   c.state.release(); c.trace.release();
@@ -244,8 +246,8 @@ apex_status apex_get_linearization(apex_ctx* ctx, double* r, double* jc, double*
     if (o == UINT64_MAX) continue;
     const size_t ch = slot / TILE, lane = slot % TILE;
     if (r) { r[2 * o] = hR[(ch * 2 + 0) * TILE + lane]; r[2 * o + 1] = hR[(ch * 2 + 1) * TILE + lane]; }
-    if (jc) for (int k = 0; k < 2 * dc; ++k) jc[o * 2 * dc + k] = hJ[(ch * np + k) * TILE + lane];
-    if (jp) for (int k = 0; k < 6; ++k) jp[o * 6 + k] = hJ[(ch * np + 2 * dc + k) * TILE + lane];
+    if (jc) for (int k = 0; k < 2 * dc; ++k) jc[o * 2 * dc + k] = hJ[jplane_index(ch, np, k, lane)];
+    if (jp) for (int k = 0; k < 6; ++k) jp[o * 6 + k] = hJ[jplane_index(ch, np, 2 * dc + k, lane)];
   }
   return APEX_OK;
 }
@@ -303,8 +305,7 @@ apex_status apex_schur_matvec_bench(apex_ctx* ctx, int32_t reps, int32_t flush_l
   for (int i = -3; i < reps; ++i) {  // 3 warm-up applications
     if (flush_l2) APEX_CUDA_TRY(c, cudaMemsetAsync(c.l2flush.p, i & 1, flush_n * sizeof(double), c.stream));
     APEX_CUDA_TRY(c, cudaEventRecord(e0, c.stream));
-    APEX_TRY(launch_hcc_apply(c, c.vp.p, c.vy.p, 0));
-    APEX_TRY(launch_schur_tiles(c, MODE_MATVEC, c.vp.p, c.vy.p, 0));
+    APEX_TRY(schur_operator_local(c, c.vp.p, c.vy.p, 0));
     APEX_CUDA_TRY(c, cudaEventRecord(e1, c.stream));
     APEX_CUDA_TRY(c, cudaEventSynchronize(e1));
     float ms = 0.f;

@@ -49,12 +49,10 @@ __global__ void __launch_bounds__(TILE) schur_form_kernel(FormArgs a) {
     if (cam_i == PAD_CAM) continue;
     const uint32_t lp = td.pt0 + a.slot_lp[slot];
     const uint32_t s0 = a.pt_slot0[lp], cnt = a.pt_cnt[lp];
-    double jc[2 * DC], jp[6];
-    const double* Jt = a.J + chunk * NP * TILE + tid;
-#pragma unroll
-    for (int k = 0; k < 2 * DC; ++k) jc[k] = Jt[(size_t)k * TILE];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) jp[k] = Jt[(size_t)(2 * DC + k) * TILE];
+    double jall[NP];
+    load_jacobian_planes<NP>(a.J, chunk, tid, jall);
+    const double* jc = jall;
+    const double* jp = jall + 2 * DC;
     const size_t n = a.npl;
     const double h00 = a.hinv[0 * n + lp], h01 = a.hinv[1 * n + lp], h02 = a.hinv[2 * n + lp];
     const double h11 = a.hinv[3 * n + lp], h12 = a.hinv[4 * n + lp], h22 = a.hinv[5 * n + lp];
@@ -68,10 +66,10 @@ __global__ void __launch_bounds__(TILE) schur_form_kernel(FormArgs a) {
     for (uint32_t j = s0; j < s0 + cnt; ++j) {
       const uint32_t cam_j = a.slot_cam[j];
       if (cam_j > cam_i) continue;
-      const double* Jj = a.J + ((size_t)(j / TILE) * NP) * TILE + (j % TILE);
+      const double2* Jj = reinterpret_cast<const double2*>(a.J) + (size_t)(j / TILE) * (NP / 2) * TILE + (j % TILE);
       double pj[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) pj[k] = Jj[(size_t)(2 * DC + k) * TILE];
+      for (int m = 0; m < 3; ++m) { const double2 v = Jj[(size_t)(DC + m) * TILE]; pj[2 * m] = v.x; pj[2 * m + 1] = v.y; }
       double M[2][2];  // Jp_i Hpp^-1 Jp_j^T
 #pragma unroll
       for (int r = 0; r < 2; ++r)
@@ -79,7 +77,7 @@ __global__ void __launch_bounds__(TILE) schur_form_kernel(FormArgs a) {
         for (int cc = 0; cc < 2; ++cc) M[r][cc] = G[r][0] * pj[cc * 3] + G[r][1] * pj[cc * 3 + 1] + G[r][2] * pj[cc * 3 + 2];
       double cj[2 * DC];
 #pragma unroll
-      for (int k = 0; k < 2 * DC; ++k) cj[k] = Jj[(size_t)k * TILE];
+      for (int m = 0; m < DC; ++m) { const double2 v = Jj[(size_t)m * TILE]; cj[2 * m] = v.x; cj[2 * m + 1] = v.y; }
       double* Srow = a.S + ((size_t)cam_i * DC) * a.ld + (size_t)cam_j * DC;
 #pragma unroll
       for (int p = 0; p < DC; ++p) {

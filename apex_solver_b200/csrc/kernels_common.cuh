@@ -36,6 +36,35 @@ __device__ __forceinline__ double ld_stream(const double* p) {
   return v;
 }
 
+__device__ __forceinline__ double2 ld_stream2(const double2* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+// Jacobian planes of one 256-slot chunk are stored as NP/2 planes of double2 {plane 2m, plane 2m+1}:
+// element (chunk, plane k, lane) lives at ((chunk*NP/2 + k/2)*256 + lane)*2 + (k&1), so a thread moves its
+// 2*(dc+3) doubles with NP/2 128-bit accesses and a warp access is 512 contiguous bytes.
+__host__ __device__ __forceinline__ size_t jplane_index(size_t chunk, int np, int k, size_t lane) {
+  return ((chunk * (size_t)(np / 2) + (size_t)(k >> 1)) * 256 + lane) * 2 + (size_t)(k & 1);
+}
+template <int NP>
+__device__ __forceinline__ void load_jacobian_planes(const double* J, size_t chunk, int lane, double* j) {
+  const double2* p = reinterpret_cast<const double2*>(J) + chunk * (NP / 2) * 256 + lane;
+#pragma unroll
+  for (int m = 0; m < NP / 2; ++m) {
+    const double2 v = ld_stream2(p + (size_t)m * 256);
+    j[2 * m] = v.x;
+    j[2 * m + 1] = v.y;
+  }
+}
+template <int NP>
+__device__ __forceinline__ void store_jacobian_planes(double* J, size_t chunk, int lane, const double* j) {
+  double2* p = reinterpret_cast<double2*>(J) + chunk * (NP / 2) * 256 + lane;
+#pragma unroll
+  for (int m = 0; m < NP / 2; ++m) p[(size_t)m * 256] = make_double2(j[2 * m], j[2 * m + 1]);
+}
+
 // fire-and-forget FP64 add into L2 (REDG.E.ADD.F64)
 __device__ __forceinline__ void red_add(double* p, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");

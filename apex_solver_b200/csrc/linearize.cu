@@ -89,7 +89,9 @@ __global__ void __launch_bounds__(TILE) linearize_tile_kernel(LinArgs a) {
     const size_t chunk = (size_t)td.chunk0 + ch;
     const size_t slot = chunk * TILE + tid;
     const uint32_t cam = a.slot_cam[slot];
-    double r[2] = {0.0, 0.0}, jc[2 * DC], jp[6];
+    double r[2] = {0.0, 0.0}, jall[NP];
+    double* jc = jall;
+    double* jp = jall + 2 * DC;
     if (cam != PAD_CAM) {
       const uint32_t lp = td.pt0 + a.slot_lp[slot];
       const Pose pose = pose_from7(a.pose + 7 * (size_t)cam);
@@ -105,11 +107,7 @@ __global__ void __launch_bounds__(TILE) linearize_tile_kernel(LinArgs a) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) jp[k] = 0.0;
     }
-    double* Jt = a.J + chunk * NP * TILE + tid;
-#pragma unroll
-    for (int k = 0; k < 2 * DC; ++k) Jt[(size_t)k * TILE] = jc[k];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) Jt[(size_t)(2 * DC + k) * TILE] = jp[k];
+    store_jacobian_planes<NP>(a.J, chunk, tid, jall);
     a.R[(chunk * 2 + 0) * TILE + tid] = r[0];
     a.R[(chunk * 2 + 1) * TILE + tid] = r[1];
     // landmark-side contributions: upper triangle of Jp^T Jp, then Jp^T r

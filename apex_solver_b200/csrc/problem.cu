@@ -76,6 +76,9 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   }
 
   // ---- tiles ----
+  // Normal tiles (<=256 observations, <=128 landmarks) get chunk ids 0..nn-1 in landmark order so that the
+  // persistent operator kernel can pair chunks (2s, 2s+1); landmarks with more than 256 observations get
+  // their chunks after those.
   std::vector<TileDesc> tiles;
   std::vector<uint32_t> pt_slot0(c.npl), pt_cnt(c.npl);
   uint32_t chunk = 0;
@@ -93,13 +96,10 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
       pt_cnt[lp] = k;
       if (k > (uint32_t)TILE) {
         flush();
-        uint32_t nch = (k + TILE - 1) / TILE;
-        tiles.push_back({lp, 1, chunk, nch});
-        pt_slot0[lp] = chunk * TILE;
-        chunk += nch;
+        tiles.push_back({lp, 1, 0xFFFFFFFFu, (k + TILE - 1) / TILE});  // chunk0 assigned below
         continue;
       }
-      if (cur_npt > 0 && (cur_obs + k > (uint32_t)TILE || cur_npt >= (uint32_t)TILE)) flush();
+      if (cur_npt > 0 && (cur_obs + k > (uint32_t)TILE || cur_npt >= (uint32_t)MAX_TILE_PTS)) flush();
       if (cur_npt == 0) cur_pt0 = lp;
       pt_slot0[lp] = chunk * TILE + cur_obs;
       cur_npt++;
@@ -107,6 +107,16 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
     }
     flush();
   }
+  c.nnormal_chunks = chunk;
+  std::vector<TileDesc> giant_tiles;
+  for (TileDesc& t : tiles)
+    if (t.nchunks > 1) {
+      t.chunk0 = chunk;
+      pt_slot0[t.pt0] = chunk * TILE;
+      chunk += t.nchunks;
+      giant_tiles.push_back(t);
+    }
+  c.ngiant = (uint32_t)giant_tiles.size();
   c.ntiles = (uint32_t)tiles.size();
   c.nchunks = chunk;
   c.nslots = (size_t)chunk * TILE;
@@ -133,6 +143,56 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
           c.slot_obs[slot] = o;
         }
       }
+    }
+  }
+
+  // ---- supertiles: camera-sorted segment structure over chunk pairs (2s, 2s+1) ----
+  c.nsuper = (c.nnormal_chunks + 1) / 2;
+  std::vector<SuperDesc> supers(c.nsuper);
+  std::vector<uint2> slot_meta(c.nslots, make_uint2(PAD_CAM, 0));
+  std::vector<uint32_t> pt_meta(c.npl, 0);
+  std::vector<uint32_t> seg_cam((size_t)c.nsuper * STILE, 0);
+  std::vector<uint16_t> seg_begin((size_t)c.nsuper * (STILE + 2), 0);
+  {
+    std::vector<const TileDesc*> by_chunk(c.nnormal_chunks, nullptr);
+    for (const TileDesc& t : tiles) if (t.nchunks == 1) by_chunk[t.chunk0] = &t;
+    std::vector<std::pair<uint32_t, uint32_t>> order;  // (camera, supertile-local slot)
+    for (uint32_t st = 0; st < c.nsuper; ++st) {
+      SuperDesc& d = supers[st];
+      const TileDesc* ta = by_chunk[2 * st];
+      const TileDesc* tb = 2 * st + 1 < c.nnormal_chunks ? by_chunk[2 * st + 1] : nullptr;
+      d = SuperDesc{ta->pt0, ta->npt, tb ? tb->pt0 : 0u, tb ? tb->npt : 0u, 0u, tb ? 1u : 0u, {0u, 0u}};
+      order.clear();
+      for (int h = 0; h < 2; ++h) {
+        const TileDesc* t = h == 0 ? ta : tb;
+        if (!t) continue;
+        const uint32_t spt0 = h == 0 ? 0 : ta->npt;
+        for (uint32_t i = 0; i < t->npt; ++i) {
+          const uint32_t lp = t->pt0 + i;
+          const uint32_t off = h * TILE + (pt_slot0[lp] - t->chunk0 * TILE);
+          pt_meta[lp] = off | (pt_cnt[lp] << 16);
+          for (uint32_t k = 0; k < pt_cnt[lp]; ++k) {
+            const size_t slot = (size_t)pt_slot0[lp] + k;
+            slot_meta[slot].x = slot_cam[slot];
+            slot_meta[slot].y = spt0 + i;  // position filled below
+            order.push_back({slot_cam[slot], off + k});
+          }
+        }
+      }
+      std::sort(order.begin(), order.end());
+      uint32_t nseg = 0;
+      for (size_t pos = 0; pos < order.size(); ++pos) {
+        if (pos == 0 || order[pos].first != order[pos - 1].first) {
+          seg_cam[(size_t)st * STILE + nseg] = order[pos].first;
+          seg_begin[(size_t)st * (STILE + 2) + nseg] = (uint16_t)pos;
+          ++nseg;
+        }
+        const uint32_t sl = order[pos].second;
+        const size_t slot = (size_t)(2 * st + sl / TILE) * TILE + sl % TILE;
+        slot_meta[slot].y |= (uint32_t)pos << 16;
+      }
+      seg_begin[(size_t)st * (STILE + 2) + nseg] = (uint16_t)order.size();
+      d.nseg = nseg;
     }
   }
 
@@ -176,6 +236,12 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   APEX_CUDA_TRY(c, upload_vec(c.tiles, tiles, s));
   APEX_CUDA_TRY(c, upload_vec(c.slot_cam, slot_cam, s));
   APEX_CUDA_TRY(c, upload_vec(c.slot_lp, slot_lp, s));
+  APEX_CUDA_TRY(c, upload_vec(c.giant_tiles, giant_tiles, s));
+  APEX_CUDA_TRY(c, upload_vec(c.supers, supers, s));
+  APEX_CUDA_TRY(c, upload_vec(c.slot_meta, slot_meta, s));
+  APEX_CUDA_TRY(c, upload_vec(c.pt_meta, pt_meta, s));
+  APEX_CUDA_TRY(c, upload_vec(c.seg_cam, seg_cam, s));
+  APEX_CUDA_TRY(c, upload_vec(c.seg_begin, seg_begin, s));
   APEX_CUDA_TRY(c, upload_vec(c.slot_uv, slot_uv, s));
   APEX_CUDA_TRY(c, upload_vec(c.pt_slot0, pt_slot0, s));
   APEX_CUDA_TRY(c, upload_vec(c.pt_cnt, pt_cnt, s));
@@ -209,6 +275,8 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   APEX_CUDA_TRY(c, c.vz.alloc(ncd));
   APEX_CUDA_TRY(c, c.vp.alloc(ncd));
   APEX_CUDA_TRY(c, c.vy.alloc(ncd));
+  APEX_CUDA_TRY(c, c.ypart.alloc((size_t)c.num_sms * ncd));
+  APEX_CUDA_TRY(c, c.xpad.alloc((size_t)c.ncam * (c.dc + 2)));
   APEX_CUDA_TRY(c, c.step_cam.alloc(ncd));
   APEX_CUDA_TRY(c, c.step_pt.alloc((size_t)c.npl * 3));
   APEX_CUDA_TRY(c, c.red_scratch.alloc(8 * (size_t)std::max<uint32_t>(std::max<uint32_t>(c.nchunks, c.ncam), 1024u) + 64));

@@ -30,6 +30,11 @@
 
 namespace {
 
+// Test aid: 1 = accumulate every block sum / operator sweep in REVERSE observation/landmark order. Same
+// arithmetic, different rounding: oracle-vs-reversed-oracle is the floor any reordered (parallel)
+// implementation of the reference, including rayon with another thread count, can be held to.
+int g_reverse_order = 0;
+
 constexpr double F64_EPS = 2.220446049250313e-16;
 constexpr double F64_MIN = -1.7976931348623157e308;  // Rust f64::MIN (most negative finite)
 
@@ -1030,7 +1035,8 @@ void linearize(Ctx& c, double lambda) {
   c.hpp.assign((size_t)c.npts * 9, 0.0);
   c.gp.assign((size_t)c.npts * 3, 0.0);
   // camera side: sequential over observations in insertion order (deterministic)
-  for (uint64_t o = 0; o < c.nobs; ++o) {
+  for (uint64_t oo = 0; oo < c.nobs; ++oo) {
+    const uint64_t o = g_reverse_order ? c.nobs - 1 - oo : oo;
     const BlockLin& b = c.lin[o];
     double jc[2 * (6 + MAXK)];
     obs_jc(c, b, jc);
@@ -1045,7 +1051,8 @@ void linearize(Ctx& c, double lambda) {
   for (int64_t p = 0; p < (int64_t)c.npts; ++p) {
     double* H = &c.hpp[(size_t)p * 9];
     double* g = &c.gp[(size_t)p * 3];
-    for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
+    for (size_t qq = c.pt_obs_start[p]; qq < c.pt_obs_start[p + 1]; ++qq) {
+      const size_t q = g_reverse_order ? c.pt_obs_start[p] + (c.pt_obs_start[p + 1] - 1 - qq) : qq;
       const BlockLin& b = c.lin[c.pt_obs[q]];
       for (int a = 0; a < 3; ++a) {
         for (int bb = 0; bb < 3; ++bb) H[a * 3 + bb] += b.jpt[a] * b.jpt[bb] + b.jpt[3 + a] * b.jpt[3 + bb];
@@ -1108,7 +1115,8 @@ void schur_matvec_local(const Ctx& c, const double* x, double* y, double lambda,
     }
   }
   double E[(6 + MAXK) * 3];
-  for (uint32_t p = p0; p < p1; ++p) {
+  for (uint32_t pp = p0; pp < p1; ++pp) {
+    const uint32_t p = g_reverse_order ? p0 + (p1 - 1 - pp) : pp;
     double t[3] = {0, 0, 0};
     for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
       uint32_t o = c.pt_obs[q];
@@ -1214,7 +1222,8 @@ apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol, d
   for (uint32_t cam = 0; cam < c.ncam; ++cam)
     for (int a = 0; a < dc; ++a) g_red[cam_row(c, cam, a)] = -c.gc[(size_t)cam * dc + a];
 
-  for (uint32_t k = 0; k < c.npts; ++k) {
+  for (uint32_t kk = 0; kk < c.npts; ++kk) {
+    const uint32_t k = g_reverse_order ? c.npts - 1 - kk : kk;
     uint32_t p = c.lm_order[k];
     rows.clear();
     for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
@@ -1283,7 +1292,8 @@ apex_status solve_implicit(Ctx& c, int precond_kind, int cg_max_it, double cg_to
   std::vector<double> b(n);
   for (size_t i = 0; i < n; ++i) b[i] = -c.gc[i];
   double E[(6 + MAXK) * 3];
-  for (uint32_t p = 0; p < c.npts; ++p) {
+  for (uint32_t pp = 0; pp < c.npts; ++pp) {
+    const uint32_t p = g_reverse_order ? c.npts - 1 - pp : pp;
     const double* hi = &hinv[(size_t)p * 9];
     double g[3] = {-c.gp[(size_t)p * 3], -c.gp[(size_t)p * 3 + 1], -c.gp[(size_t)p * 3 + 2]};
     double t[3] = {hi[0] * g[0] + hi[1] * g[1] + hi[2] * g[2], hi[3] * g[0] + hi[4] * g[1] + hi[5] * g[2], hi[6] * g[0] + hi[7] * g[1] + hi[8] * g[2]};
@@ -1515,6 +1525,7 @@ int32_t oracle_num_threads(void) {
   return 1;
 #endif
 }
+void oracle_set_reverse_order(int32_t on) { g_reverse_order = on ? 1 : 0; }
 void oracle_set_num_threads(int32_t n) {
 #ifdef _OPENMP
   if (n > 0) omp_set_num_threads(n);

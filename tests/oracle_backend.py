@@ -60,6 +60,7 @@ def oracle_lib():
             "oracle_solve_pcg_dense": (I32, [U32, VP, VP, VP, I32, DBL]),
             "oracle_get_column_layout": (I32, [VP, VP, VP, VP]),
             "oracle_set_num_threads": (None, [I32]),
+            "oracle_set_reverse_order": (None, [I32]),
         }
         for name, (res, args) in sigs.items():
             fn = getattr(lib, name)
