@@ -116,6 +116,11 @@ class IterTrace(C.Structure):
     ]
 
 
+class Profile(C.Structure):
+    _fields_ = [("lm_device_ms", C.c_double), ("matvec_ms", C.c_double), ("matvec_launches", C.c_int64),
+                ("linearize_ms", C.c_double), ("linearize_launches", C.c_int64)]
+
+
 class Dims(C.Structure):
     _fields_ = [("ncam", C.c_uint32), ("npts", C.c_uint32), ("nobs", C.c_uint64), ("intr_dim", C.c_int32), ("dc", C.c_int32),
                 ("cam_dof", C.c_uint64), ("lm_dof", C.c_uint64), ("npts_local", C.c_uint32), ("reserved", C.c_uint32),
@@ -148,9 +153,12 @@ SYMBOLS = {
                                     P(C.c_double), P(C.c_int32)]),
     "lm_solve": (C.c_int32, [C.c_void_p, P(LmConfig), P(LmResult), P(IterTrace), C.c_int32]),
     "kernel_launches": (C.c_int64, [C.c_void_p]),
+    "profile_enable": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "profile_read": (C.c_int32, [C.c_void_p, P(Profile)]),
+    "shard_range": (C.c_int32, [C.c_uint32, C.c_uint64, C.c_void_p, C.c_int32, C.c_int32, P(C.c_uint32), P(C.c_uint32), P(C.c_uint64)]),
 }
 # entry points the oracle does not implement (GPU-only plumbing)
-GPU_ONLY = {"device_count", "nccl_unique_id", "schur_matvec_bench", "kernel_launches"}
+GPU_ONLY = {"device_count", "nccl_unique_id", "schur_matvec_bench", "kernel_launches", "profile_enable", "profile_read", "shard_range"}
 
 
 def bind(lib: C.CDLL, prefix: str, skip=()) -> None:

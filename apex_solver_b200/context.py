@@ -193,6 +193,25 @@ class Context:
     def kernel_launches(self) -> int:
         return int(self._fn("kernel_launches")(self._h))
 
+    def profile_enable(self, on: bool = True):
+        self._check(self._fn("profile_enable")(self._h, 1 if on else 0))
+
+    def profile_read(self) -> F.Profile:
+        p = F.Profile()
+        self._check(self._fn("profile_read")(self._h, C.byref(p)))
+        return p
+
+
+def shard_range(obs_pt, npts: int, nranks: int, rank: int):
+    """Landmark range [p0,p1) and observation count owned by `rank` (host-only entry point of the product library)."""
+    lib = F.load_library()
+    obs_pt = np.ascontiguousarray(obs_pt, dtype=np.uint32)
+    p0, p1, n = C.c_uint32(), C.c_uint32(), C.c_uint64()
+    st = lib.apex_shard_range(int(npts), int(obs_pt.shape[0]), F.ptr(obs_pt), int(nranks), int(rank), C.byref(p0), C.byref(p1), C.byref(n))
+    if st != F.OK:
+        raise F.ApexError(st, "shard_range")
+    return p0.value, p1.value, n.value
+
 
 class GpuContext(Context):
     """Context on the product library csrc/libapex_gpu.so (sm_100a kernels). No CPU fallback."""

@@ -168,7 +168,22 @@ struct Ctx {
   DevState* h_state = nullptr;            // pinned mirror
   DevBuf<apex_iter_trace> trace;
   int64_t last_pcg_iters = 0;
+
+  // ---- profiling (apex_profile_*) ----
+  bool prof = false;
+  std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
+  size_t ev_mv_used = 0;              // event pairs used by operator launches since the last read
+  std::vector<cudaEvent_t> ev_lin;    // pairs around launch_linearize
+  size_t ev_lin_used = 0;
+  cudaEvent_t ev_lm0 = nullptr, ev_lm1 = nullptr;
+  bool lm_timed = false;
 };
+
+// event pair `idx` of a pool, created on demand
+inline cudaEvent_t* prof_pair(std::vector<cudaEvent_t>& pool, size_t idx) {
+  while (pool.size() < 2 * (idx + 1)) { cudaEvent_t e = nullptr; cudaEventCreate(&e); pool.push_back(e); }
+  return &pool[2 * idx];
+}
 
 // ---- error helpers --------------------------------------------------------------------------------
 #define APEX_CUDA_TRY(ctx, expr)                                                                    \
@@ -189,6 +204,7 @@ struct Ctx {
 // ---- launchers (one per kernel group; defined in the .cu files) --------------------------------------
 // problem.cu
 apex_status problem_upload(Ctx& c, const apex_problem_desc* d);
+void shard_range(uint32_t npts, uint64_t nobs, const uint32_t* obs_pt, int nranks, int rank, std::vector<uint64_t>& pt_start, uint32_t& p0, uint32_t& p1);
 // linearize.cu
 apex_status launch_normalize_poses(Ctx& c);
 apex_status launch_linearize(Ctx& c);                       // K1 + K2 + K3 (lambda from state->damping)

@@ -151,6 +151,9 @@ void apex_ctx_destroy(apex_ctx* ctx) {
   c.tiles.release(); c.slot_cam.release(); c.slot_lp.release(); c.pt_slot0.release(); c.pt_cnt.release(); c.items.release();
   c.cam_item_start.release(); c.cm_lp.release(); c.pose_fixed.release(); c.pt_fixed.release(); c.intr_fixed.release();
   c.state.release(); c.trace.release();
+  for (cudaEvent_t e : c.ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : c.ev_lin) cudaEventDestroy(e);
+  if (c.ev_lm0) { cudaEventDestroy(c.ev_lm0); cudaEventDestroy(c.ev_lm1); }
   if (c.h_state) cudaFreeHost(c.h_state);
   if (c.stream) cudaStreamDestroy(c.stream);
   delete ctx;
@@ -348,5 +351,49 @@ apex_status apex_lm_solve(apex_ctx* ctx, const apex_lm_config* cfg, apex_lm_resu
 }
 
 int64_t apex_kernel_launches(const apex_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+apex_status apex_profile_enable(apex_ctx* ctx, int32_t on) {
+  CTX_OR_FAIL(ctx);
+  c.prof = on != 0;
+  c.ev_mv_used = 0;
+  c.ev_lin_used = 0;
+  return APEX_OK;
+}
+
+apex_status apex_profile_read(apex_ctx* ctx, apex_profile* out) {
+  CTX_OR_FAIL(ctx);
+  if (!out) { c.err = "null profile"; return APEX_ERR_INVALID_INPUT; }
+  APEX_CUDA_TRY(c, cudaStreamSynchronize(c.stream));
+  std::memset(out, 0, sizeof(*out));
+  auto total = [&](std::vector<cudaEvent_t>& pool, size_t used, double& ms, int64_t& n) {
+    for (size_t i = 0; i < used; ++i) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, pool[2 * i], pool[2 * i + 1]) == cudaSuccess) { ms += t; ++n; } else cudaGetLastError();
+    }
+  };
+  total(c.ev_pool, c.ev_mv_used, out->matvec_ms, out->matvec_launches);
+  total(c.ev_lin, c.ev_lin_used, out->linearize_ms, out->linearize_launches);
+  c.ev_mv_used = 0;
+  c.ev_lin_used = 0;
+  if (c.lm_timed) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, c.ev_lm0, c.ev_lm1) == cudaSuccess) out->lm_device_ms = t; else cudaGetLastError();
+  }
+  return APEX_OK;
+}
+
+apex_status apex_shard_range(uint32_t npts, uint64_t nobs, const uint32_t* obs_pt, int32_t nranks, int32_t rank, uint32_t* p0, uint32_t* p1,
+                             uint64_t* nobs_local) {
+  if (!obs_pt && nobs) return APEX_ERR_INVALID_INPUT;
+  if (nranks < 1 || rank < 0 || rank >= nranks) return APEX_ERR_INVALID_INPUT;
+  for (uint64_t o = 0; o < nobs; ++o) if (obs_pt[o] >= npts) return APEX_ERR_INVALID_INPUT;
+  std::vector<uint64_t> pt_start;
+  uint32_t a = 0, b = 0;
+  shard_range(npts, nobs, obs_pt, nranks, rank, pt_start, a, b);
+  if (p0) *p0 = a;
+  if (p1) *p1 = b;
+  if (nobs_local) *nobs_local = pt_start[b] - pt_start[a];
+  return APEX_OK;
+}
 
 }  // extern "C"

@@ -430,6 +430,8 @@ static CamArgs make_cam_args(Ctx& c) {
 
 apex_status launch_linearize(Ctx& c) {
   cudaStream_t s = c.stream;
+  cudaEvent_t* evp = c.prof ? prof_pair(c.ev_lin, c.ev_lin_used++) : nullptr;
+  if (evp) cudaEventRecord(evp[0], s);
   LinArgs la = make_lin_args(c);
   CamArgs ca = make_cam_args(c);
   if (c.ntiles) {
@@ -458,6 +460,7 @@ apex_status launch_linearize(Ctx& c) {
     }
     c.launches++;
   }
+  if (evp) cudaEventRecord(evp[1], s);
   APEX_CUDA_TRY(c, cudaGetLastError());
   // camera-side blocks are sums over all ranks' observations
   APEX_TRY(allreduce_sum(c, c.hcc.p, (size_t)c.ncam * c.dc * (c.dc + 1)));

@@ -255,6 +255,9 @@ apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, ape
   APEX_CUDA_TRY(c, c.trace.alloc((size_t)std::max(trace_cap, 1)));
   std::vector<double> iter_ms;
 
+  if (!c.ev_lm0) { cudaEventCreate(&c.ev_lm0); cudaEventCreate(&c.ev_lm1); }
+  cudaEventRecord(c.ev_lm0, s);
+  c.lm_timed = false;
   // Variable::new(SE3::from(DVector)) normalises the initial quaternions (src/core/problem.rs:743-757)
   APEX_TRY(launch_normalize_poses(c));
   APEX_TRY(launch_cost(c, nullptr));  // initial cost (mod.rs:550-552)
@@ -293,6 +296,8 @@ apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, ape
     iter_ms.push_back((now_seconds() - it0) * 1e3);
     if (c.h_state->accepted) ok_steps++; else bad_steps++;
     if (c.h_state->status >= 0) {
+      cudaEventRecord(c.ev_lm1, s);
+      c.lm_timed = true;
       res->status = c.h_state->status;
       res->iterations = iteration + 1;
       res->initial_cost = initial_cost;

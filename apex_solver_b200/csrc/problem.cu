@@ -19,6 +19,24 @@ static cudaError_t upload_vec(DevBuf<T>& buf, const std::vector<T>& v, cudaStrea
   return cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
 }
 
+// Contiguous landmark ranges balanced by observation count; identical on every rank. pt_start receives the
+// exclusive prefix sum of the per-landmark observation counts.
+void shard_range(uint32_t npts, uint64_t nobs, const uint32_t* obs_pt, int nranks, int rank, std::vector<uint64_t>& pt_start, uint32_t& p0,
+                 uint32_t& p1) {
+  pt_start.assign((size_t)npts + 1, 0);
+  for (uint64_t o = 0; o < nobs; ++o) pt_start[obs_pt[o] + 1]++;
+  for (uint32_t p = 0; p < npts; ++p) pt_start[p + 1] += pt_start[p];
+  auto boundary = [&](int r) -> uint32_t {
+    if (r <= 0) return 0;
+    if (r >= nranks) return npts;
+    if (nobs == 0) return (uint32_t)((uint64_t)npts * r / nranks);
+    uint64_t target = nobs * (uint64_t)r / (uint64_t)nranks;
+    return (uint32_t)(std::lower_bound(pt_start.begin(), pt_start.begin() + npts, target) - pt_start.begin());
+  };
+  p0 = boundary(rank);
+  p1 = boundary(rank + 1);
+}
+
 apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   // ---- validation (same failures as the reference / oracle) ----
   int K = model_intr_dim(d->camera_model);
@@ -49,18 +67,8 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   for (int i = 0; i < 4; ++i) c.loss_p[i] = d->loss_params[i];
 
   // ---- landmark sharding: contiguous ranges balanced by observation count ----
-  std::vector<uint64_t> pt_start((size_t)c.npts + 1, 0);
-  for (uint64_t o = 0; o < nobs; ++o) pt_start[d->obs_pt[o] + 1]++;
-  for (uint32_t p = 0; p < c.npts; ++p) pt_start[p + 1] += pt_start[p];
-  auto boundary = [&](int r) -> uint32_t {
-    if (r <= 0) return 0;
-    if (r >= c.nranks) return c.npts;
-    if (nobs == 0) return (uint32_t)((uint64_t)c.npts * r / c.nranks);
-    uint64_t target = nobs * (uint64_t)r / (uint64_t)c.nranks;
-    return (uint32_t)(std::lower_bound(pt_start.begin(), pt_start.begin() + c.npts, target) - pt_start.begin());
-  };
-  c.p0 = boundary(c.rank);
-  c.p1 = boundary(c.rank + 1);
+  std::vector<uint64_t> pt_start;
+  shard_range(c.npts, nobs, d->obs_pt, c.nranks, c.rank, pt_start, c.p0, c.p1);
   c.npl = c.p1 - c.p0;
   c.nobs_local = pt_start[c.p1] - pt_start[c.p0];
 

@@ -658,6 +658,8 @@ apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_d
   if (want_timing) { if (!d_timing) cudaMalloc(&d_timing, 12 * sizeof(long long)); a.timing = d_timing; }
   const size_t smem = mv_smem_bytes(c.dc, n, priv);
   if (!priv) APEX_TRY(launch_hcc_apply(c, x, y, check_done));  // y starts as (H_cc + lambda I) x; the kernel reduces into it
+  cudaEvent_t* evp = (c.prof && c.nsuper) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
+  if (evp) cudaEventRecord(evp[0], c.stream);
   if (c.nsuper) {
     switch (c.dc) {
       case 6: APEX_TRY(launch_persist_dc<6>(c, a, priv, grid, smem)); break;
@@ -669,6 +671,7 @@ apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_d
     }
     c.launches++;
   }
+  if (evp) cudaEventRecord(evp[1], c.stream);
   if (priv) {
     schur_finalize_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(c.hcc.p, x, c.ypart.p, c.nsuper ? grid : 0u, y, c.state.p, n, c.dc,
                                                                  c.rank == 0 ? 1 : 0, check_done);

@@ -322,6 +322,26 @@ apex_status apex_lm_solve(apex_ctx* ctx, const apex_lm_config* cfg, apex_lm_resu
 /* Number of kernel launches issued by this context since creation (bench bookkeeping). */
 int64_t apex_kernel_launches(const apex_ctx* ctx);
 
+/* Device-side timing for bench.py (CUDA events on the context's own stream; the reference has no equivalent:
+ * its only timers are the wall-clock IterationStats of src/optimizer/mod.rs:375-398). With profiling on, every
+ * launch of the Schur-operator kernel inside a solve is bracketed by an event pair. apex_profile_read waits for
+ * the stream, returns the totals since the last read and resets them. */
+typedef struct apex_profile {
+  double lm_device_ms;        /* first-to-last kernel of the last apex_lm_solve, on the device timeline   */
+  double matvec_ms;           /* summed duration of the Schur-operator kernel launches                    */
+  int64_t matvec_launches;
+  double linearize_ms;        /* summed duration of apex_linearize's kernel group (K1+K2+K3)               */
+  int64_t linearize_launches;
+} apex_profile;
+apex_status apex_profile_enable(apex_ctx* ctx, int32_t on);
+apex_status apex_profile_read(apex_ctx* ctx, apex_profile* out);
+
+/* Host-only: the landmark range [p0,p1) and observation count rank `rank` of `nranks` owns for this observation
+ * list - the sharding rule apex_problem_upload applies (contiguous landmark ranges balanced by observations).
+ * Needs no device; lets multi-process host logic be tested without a GPU. */
+apex_status apex_shard_range(uint32_t npts, uint64_t nobs, const uint32_t* obs_pt, int32_t nranks, int32_t rank,
+                             uint32_t* p0, uint32_t* p1, uint64_t* nobs_local);
+
 #ifdef __cplusplus
 }
 #endif

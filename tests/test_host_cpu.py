@@ -1,0 +1,206 @@
+"""CPU-only tests (no GPU in this container): the C-ABI library loads and exports every symbol include/apex_gpu.h
+declares, fails loudly without a device (no CPU fallback), the host-side sharding logic, the synthetic generator,
+the oracle end to end on small BASELINE-shaped problems, and the N>1 decomposition over gloo (world_size 2)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from apex_solver_b200 import _ffi as F, synth
+from apex_solver_b200.context import BAProblem, GpuContext, shard_range
+from oracle_backend import OracleContext, oracle_lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAVE_GPU = F.load_library().apex_device_count() > 0
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "apex_gpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(apex_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 24
+    lib = C.CDLL(F.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/apex_gpu.h but not exported"
+    assert {"apex_" + n for n in F.SYMBOLS} == declared, "the ctypes table and the header disagree"
+    assert lib.apex_abi_version() == 100
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """ctypes mirrors vs the C compiler's view of include/apex_gpu.h (sizes and a few offsets)."""
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "apex_gpu.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                   "sizeof(apex_ctx_desc),sizeof(apex_problem_desc),sizeof(apex_lm_config),sizeof(apex_lm_result),sizeof(apex_iter_trace),"
+                   "sizeof(apex_dims),sizeof(apex_profile),offsetof(apex_problem_desc,loss_params),offsetof(apex_lm_config,cg_tolerance),"
+                   "offsetof(apex_lm_result,linear_iterations));return 0;}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    want = [C.sizeof(F.CtxDesc), C.sizeof(F.ProblemDesc), C.sizeof(F.LmConfig), C.sizeof(F.LmResult), C.sizeof(F.IterTrace), C.sizeof(F.Dims),
+            C.sizeof(F.Profile), F.ProblemDesc.loss_params.offset, F.LmConfig.cg_tolerance.offset, F.LmResult.linear_iterations.offset]
+    assert got == want
+
+
+def test_config_presets_match_reference():  # levenberg_marquardt.rs:319-359, 519-530
+    lib = F.load_library()
+    d, b = F.LmConfig(), F.LmConfig()
+    lib.apex_lm_config_default(C.byref(d))
+    lib.apex_lm_config_for_bundle_adjustment(C.byref(b))
+    assert (d.max_iterations, d.cost_tolerance, d.parameter_tolerance, d.gradient_tolerance) == (50, 1e-6, 1e-8, 1e-10)
+    assert (d.damping, d.damping_min, d.damping_max, d.damping_nu) == (1e-3, 1e-12, 1e12, 2.0)
+    assert d.schur_variant == F.SCHUR_EXPLICIT and np.isnan(d.min_cost_threshold)
+    assert (b.max_iterations, b.damping, b.schur_variant, b.schur_preconditioner) == (20, 1e-3, F.SCHUR_EXPLICIT_PCG, F.PRECOND_SCHUR_JACOBI)
+    assert (b.cg_max_iterations, b.cg_tolerance) == (200, 1e-6)  # explicit_schur.rs:211-212
+    # the oracle's presets are the same bytes
+    o = F.LmConfig()
+    oracle_lib().oracle_lm_config_for_bundle_adjustment(C.byref(o))
+    assert bytes(o)[:24] == bytes(b)[:24] and o.cg_tolerance == b.cg_tolerance
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="checks the behaviour WITHOUT a CUDA device")
+def test_no_device_means_error_not_fallback():
+    with pytest.raises(F.ApexError) as e:
+        GpuContext()
+    assert e.value.status == F.ERR_NO_DEVICE
+
+
+def test_shard_range_covers_and_balances():
+    prob = synth.make_problem(20, 3000, 5.0, seed=2)
+    for nranks in (1, 2, 3, 8):
+        parts = [shard_range(prob.obs_pt, prob.npts, nranks, r) for r in range(nranks)]
+        assert parts[0][0] == 0 and parts[-1][1] == prob.npts
+        for a, b in zip(parts, parts[1:]):
+            assert a[1] == b[0], "ranges are contiguous"
+        assert sum(p[2] for p in parts) == prob.nobs
+        cnt = np.bincount(prob.obs_pt, minlength=prob.npts)
+        for p0, p1, n in parts:
+            assert n == cnt[p0:p1].sum()
+            assert abs(n - prob.nobs / nranks) <= cnt.max() + 1, "balanced by observations up to one track"
+    with pytest.raises(F.ApexError):
+        shard_range(prob.obs_pt, prob.npts, 2, 2)
+
+
+def test_generator_is_deterministic_and_bal_shaped():
+    a, b = synth.make_shape("ladybug49"), synth.make_shape("ladybug49")
+    for x, y in ((a.pose, b.pose), (a.pt, b.pt), (a.obs_uv, b.obs_uv), (a.obs_cam, b.obs_cam)):
+        assert np.array_equal(x, y)
+    assert (a.ncam, a.npts) == (49, 7776) and 20000 < a.nobs < 40000
+    key = a.obs_pt.astype(np.int64) * a.ncam + a.obs_cam
+    assert len(np.unique(key)) == a.nobs, "one observation per (camera, landmark)"
+    assert a.pose_fixed[0] == 0x3F and not a.pose_fixed[1:].any()  # bin/bundle_adjustment.rs:294-298
+    assert np.allclose(np.linalg.norm(a.pose[:, 3:], axis=1), 1.0)
+    # every observation is in front of its camera at the initial values (BAL looks down -z)
+    R = synth.quat_to_matrix(a.meta["truth_pose"][:, 3:])
+    pc = np.einsum("nij,nj->ni", R[a.obs_cam], a.meta["truth_pt"][a.obs_pt]) + a.meta["truth_pose"][a.obs_cam, :3]
+    assert (pc[:, 2] < 0).all()
+
+
+@pytest.mark.parametrize("variant", [F.SCHUR_EXPLICIT, F.SCHUR_IMPLICIT, F.SCHUR_EXPLICIT_PCG], ids=["explicit", "implicit", "explicit_pcg"])
+def test_oracle_lm_converges_and_variants_agree(variant):
+    """Self-consistency of the restated oracle (SURVEY §8c iv): every Schur variant reduces the cost of a Ladybug-shaped
+    problem and they reach the same neighbourhood."""
+    prob = synth.make_problem(16, 600, 4.0, seed=7, self_calibration=False)
+    o = OracleContext().upload(prob)
+    cfg = o.default_config(True)
+    cfg.schur_variant = variant
+    cfg.max_iterations = 12
+    res, trace = o.lm_solve(cfg)
+    assert res.final_cost < 0.15 * res.initial_cost  # 2 % gross outliers keep a Huber floor
+    assert res.iterations == len(trace) and res.successful_steps + res.unsuccessful_steps == res.iterations
+    assert res.cost_evaluations == res.iterations + 1 and res.jacobian_evaluations == res.iterations
+    for a, b in zip(trace, trace[1:]):
+        assert b.cost <= a.cost + 1e-12, "accepted costs never increase"
+    ref = OracleContext().upload(prob)
+    cfg2 = ref.default_config(True)
+    cfg2.schur_variant = F.SCHUR_EXPLICIT
+    cfg2.max_iterations = 12
+    r2, _ = ref.lm_solve(cfg2)
+    assert abs(res.final_cost - r2.final_cost) <= 0.15 * r2.final_cost  # truncated PCG (200 its) lags the direct solve
+
+
+def test_oracle_linear_solve_matches_scipy():
+    """SURVEY §8c iii: the oracle's explicit Schur step solves (J^T J + lambda I) delta = -J^T r (checked densely)."""
+    import scipy.linalg
+    prob = synth.make_problem(6, 60, 4.0, seed=3)
+    o = OracleContext().upload(prob)
+    lam = 1e-2
+    o.linearize(lam)
+    r, jc, jp = o.get_linearization()
+    dc, ncam, npts = prob.dc, prob.ncam, prob.npts
+    n = ncam * dc + 3 * npts
+    J = np.zeros((2 * prob.nobs, n))
+    for i in range(prob.nobs):
+        c, p = int(prob.obs_cam[i]), int(prob.obs_pt[i])
+        J[2 * i:2 * i + 2, c * dc:(c + 1) * dc] = jc[i]
+        J[2 * i:2 * i + 2, ncam * dc + 3 * p:ncam * dc + 3 * p + 3] = jp[i]
+    H = J.T @ J + lam * np.eye(n)
+    g = J.T @ r.reshape(-1)
+    delta = scipy.linalg.cho_solve(scipy.linalg.cho_factor(H), -g)
+    sc, sp, gnorm, _ = o.solve_augmented(F.SCHUR_EXPLICIT, lam)
+    assert abs(gnorm - np.linalg.norm(g)) <= 1e-10 * gnorm
+    assert np.abs(sc.reshape(-1) - delta[:ncam * dc]).max() <= 1e-6 * np.abs(delta).max()
+    assert np.abs(sp.reshape(-1) - delta[ncam * dc:]).max() <= 1e-6 * np.abs(delta).max()
+    # and the matrix-free operator is the Schur complement of H
+    x = np.random.default_rng(0).standard_normal(ncam * dc)
+    Hcc, Hcp, Hpp = H[:ncam * dc, :ncam * dc], H[:ncam * dc, ncam * dc:], H[ncam * dc:, ncam * dc:]
+    S = Hcc - Hcp @ np.linalg.solve(Hpp, Hcp.T)
+    assert np.abs(o.schur_matvec(x) - S @ x).max() <= 1e-9 * np.abs(S @ x).max()
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` prints one JSON line with the contract's keys (runs the oracle on a bounded sample)."""
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--scale", "0.05"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "LM iterations/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+# ---- N > 1: observation/landmark sharding with replicated camera blocks, over gloo, world_size 2 ---------------
+GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+from apex_solver_b200 import synth
+from apex_solver_b200.context import shard_range
+from oracle_backend import OracleContext
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+prob = synth.make_problem(10, 400, 4.0, seed=5)
+o = OracleContext().upload(prob)
+lam = 1e-3
+o.linearize(lam)
+n = prob.ncam * prob.dc
+x = np.random.default_rng(1).standard_normal(n)
+p0, p1, nloc = shard_range(prob.obs_pt, prob.npts, world, rank)
+# what one rank of the GPU path computes: the H_cc term once (rank 0) + its landmarks' part of -H_cp Hpp^-1 H_cp^T x
+y = torch.from_numpy(o.schur_matvec_partial(x, p0, p1, rank == 0).copy())
+dist.all_reduce(y)            # the single exchange step of the operator (ncam*dc doubles)
+full = o.schur_matvec(x)
+err = float(np.abs(y.numpy() - full).max() / np.abs(full).max())
+cnt = torch.tensor([nloc], dtype=torch.int64); dist.all_reduce(cnt)
+ok = err < 1e-12 and int(cnt.item()) == prob.nobs
+print("RANK", rank, "err", err, "ok", ok, flush=True)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+'''
+
+
+def test_sharded_operator_allreduce_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER.format(root=ROOT))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-2000:]
