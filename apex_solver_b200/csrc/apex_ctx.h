@@ -49,6 +49,13 @@ struct SuperDesc {
   uint32_t validB;
   uint32_t pad[2];
 };
+// Per-chunk descriptor of the ping-pong operator kernel (one 256-thread group processes one chunk at a time).
+struct ChunkDesc {
+  uint32_t pt0, npt;   // landmarks of the chunk (0 landmarks for a padding chunk)
+  uint32_t nseg;       // distinct cameras among its <=256 observations
+  uint32_t pad;
+};
+constexpr int CSEG_LD = TILE + 2;     // u16 entries per chunk in cseg_begin (sentinel + padding to a 4-byte multiple)
 constexpr int STILE = 2 * TILE;       // slots per supertile
 constexpr int MAX_TILE_PTS = 128;     // landmarks per normal tile (so a supertile stages <= 256 landmark inverses)
 
@@ -129,6 +136,11 @@ struct Ctx {
   DevBuf<uint32_t> pt_meta;          // per landmark: supertile-local first slot | count << 16
   DevBuf<uint32_t> seg_cam;          // [nsuper][512] camera of each camera-segment
   DevBuf<uint16_t> seg_begin;        // [nsuper][514] first sorted position of each segment (+ sentinel)
+  DevBuf<ChunkDesc> chunk_desc;      // [nnormal_chunks rounded up to even]
+  DevBuf<uint2> cslot_meta;          // per slot: {camera, chunk-local landmark | sorted position << 8 | segment << 16}
+  DevBuf<uint32_t> cpt_meta;         // per landmark: chunk-local first slot | count << 16
+  DevBuf<uint32_t> cseg_cam;         // [chunk][256]
+  DevBuf<uint16_t> cseg_begin;       // [chunk][CSEG_LD]
   DevBuf<double> xpad;               // operator input at an even per-camera stride
   DevBuf<double> ypart;              // [grid][ncam*dc] per-CTA private results of the persistent operator kernel
   DevBuf<double> slot_uv;            // [chunk][2][TILE]

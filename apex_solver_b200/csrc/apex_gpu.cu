@@ -147,7 +147,7 @@ void apex_ctx_destroy(apex_ctx* ctx) {
                            &c.sj, &c.pinv, &c.vb, &c.vx, &c.vr, &c.vz, &c.vp, &c.vy, &c.step_cam, &c.step_pt, &c.red_scratch, &c.S, &c.E,
                            &c.dvec, &c.l2flush};
   for (auto* b : dbl) b->release();
-  c.giant_tiles.release(); c.supers.release(); c.slot_meta.release(); c.pt_meta.release(); c.seg_cam.release(); c.seg_begin.release(); c.ypart.release(); c.xpad.release();
+  c.giant_tiles.release(); c.supers.release(); c.slot_meta.release(); c.pt_meta.release(); c.seg_cam.release(); c.seg_begin.release(); c.ypart.release(); c.xpad.release(); c.chunk_desc.release(); c.cslot_meta.release(); c.cpt_meta.release(); c.cseg_cam.release(); c.cseg_begin.release();
   c.tiles.release(); c.slot_cam.release(); c.slot_lp.release(); c.pt_slot0.release(); c.pt_cnt.release(); c.items.release();
   c.cam_item_start.release(); c.cm_lp.release(); c.pose_fixed.release(); c.pt_fixed.release(); c.intr_fixed.release();
   c.state.release(); c.trace.release();

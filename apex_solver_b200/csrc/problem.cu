@@ -204,6 +204,45 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
     }
   }
 
+  // ---- per-chunk camera-sorted segment structure (ping-pong operator kernel) ----
+  const uint32_t nchunk_even = (c.nnormal_chunks + 1) & ~1u;
+  std::vector<ChunkDesc> chunk_desc(nchunk_even, ChunkDesc{0, 0, 0, 0});
+  std::vector<uint2> cslot_meta((size_t)nchunk_even * TILE, make_uint2(PAD_CAM, 0));
+  std::vector<uint32_t> cpt_meta(c.npl, 0);
+  std::vector<uint32_t> cseg_cam((size_t)nchunk_even * TILE, 0);
+  std::vector<uint16_t> cseg_begin((size_t)nchunk_even * CSEG_LD, 0);
+  {
+    std::vector<std::pair<uint32_t, uint32_t>> order;
+    for (const TileDesc& t : tiles) {
+      if (t.nchunks != 1) continue;
+      const uint32_t ch = t.chunk0;
+      order.clear();
+      for (uint32_t i = 0; i < t.npt; ++i) {
+        const uint32_t lp = t.pt0 + i;
+        const uint32_t off = pt_slot0[lp] - ch * TILE;
+        cpt_meta[lp] = off | (pt_cnt[lp] << 16);
+        for (uint32_t k = 0; k < pt_cnt[lp]; ++k) {
+          const size_t slot = (size_t)pt_slot0[lp] + k;
+          cslot_meta[slot].x = slot_cam[slot];
+          cslot_meta[slot].y = i;
+          order.push_back({slot_cam[slot], off + k});
+        }
+      }
+      std::sort(order.begin(), order.end());
+      uint32_t nseg = 0;
+      for (size_t pos = 0; pos < order.size(); ++pos) {
+        if (pos == 0 || order[pos].first != order[pos - 1].first) {
+          cseg_cam[(size_t)ch * TILE + nseg] = order[pos].first;
+          cseg_begin[(size_t)ch * CSEG_LD + nseg] = (uint16_t)pos;
+          ++nseg;
+        }
+        cslot_meta[(size_t)ch * TILE + order[pos].second].y |= ((uint32_t)pos << 8) | ((nseg - 1) << 16);
+      }
+      cseg_begin[(size_t)ch * CSEG_LD + nseg] = (uint16_t)order.size();
+      chunk_desc[ch] = ChunkDesc{t.pt0, t.npt, nseg, 0};
+    }
+  }
+
   // ---- camera-major copy of the local observations + work items ----
   std::vector<uint32_t> cam_start((size_t)c.ncam + 1, 0);
   for (uint64_t q = 0; q < c.nobs_local; ++q) cam_start[d->obs_cam[pm[q]] + 1]++;
@@ -250,6 +289,11 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   APEX_CUDA_TRY(c, upload_vec(c.pt_meta, pt_meta, s));
   APEX_CUDA_TRY(c, upload_vec(c.seg_cam, seg_cam, s));
   APEX_CUDA_TRY(c, upload_vec(c.seg_begin, seg_begin, s));
+  APEX_CUDA_TRY(c, upload_vec(c.chunk_desc, chunk_desc, s));
+  APEX_CUDA_TRY(c, upload_vec(c.cslot_meta, cslot_meta, s));
+  APEX_CUDA_TRY(c, upload_vec(c.cpt_meta, cpt_meta, s));
+  APEX_CUDA_TRY(c, upload_vec(c.cseg_cam, cseg_cam, s));
+  APEX_CUDA_TRY(c, upload_vec(c.cseg_begin, cseg_begin, s));
   APEX_CUDA_TRY(c, upload_vec(c.slot_uv, slot_uv, s));
   APEX_CUDA_TRY(c, upload_vec(c.pt_slot0, pt_slot0, s));
   APEX_CUDA_TRY(c, upload_vec(c.pt_cnt, pt_cnt, s));

@@ -418,6 +418,246 @@ __global__ void __launch_bounds__(MV_THREADS, 1) schur_matvec_persist_kernel(MvA
   }
 }
 
+// ----------------------------------------------------------------------------------------------------
+// Ping-pong variant of the persistent operator kernel. The 512-thread CTA is split into two 256-thread groups
+// that each walk their own chunks (256 slots = whole landmarks) with named barriers (bar.sync 1/2), half a
+// period out of phase, so one group's barrier / latency stalls are filled by the other group's work. Both groups
+// add into the same CTA-private y; their phase 4 is serialised by a two-barrier turnstile (bar.arrive/bar.sync
+// 3 and 4) in the fixed order A0 B0 A1 B1 ..., which keeps the result bitwise reproducible. x is staged per
+// camera SEGMENT (one coalesced 80-byte read per distinct camera instead of one scattered read per
+// observation); segment tables are double-buffered and fetched one chunk ahead with cp.async.
+// ----------------------------------------------------------------------------------------------------
+struct PpArgs {
+  const ChunkDesc* chunk_desc;
+  const uint2* cslot_meta;
+  const uint32_t* cpt_meta;
+  const uint32_t* cseg_cam;
+  const uint16_t* cseg_begin;
+  const double* J;
+  const double* hinv;
+  const double* xpad;
+  double* y;
+  double* ypart;
+  uint32_t n, npl, npairs, nnormal_chunks;
+  int check_done;
+  const DevState* st;
+};
+
+constexpr int PP_PTS = MAX_TILE_PTS;  // landmarks per chunk
+constexpr int PP_CS_LD = TILE + 1;
+
+__device__ __forceinline__ void pp_group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(TILE) : "memory"); }
+__device__ __forceinline__ void pp_turn_wait(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(2 * TILE) : "memory"); }
+__device__ __forceinline__ void pp_turn_signal(int id) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(2 * TILE) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int DC>
+struct PpRegs {
+  double j[2 * (DC + 3)];
+  uint32_t cam, sp;
+  uint32_t pt0, npt, nseg;
+};
+
+template <int DC> __host__ __device__ constexpr int pp_region_doubles() { return (DC * PP_CS_LD > TILE * ((DC + 1) & ~1)) ? DC * PP_CS_LD : TILE * ((DC + 1) & ~1); }
+template <int DC> __host__ __device__ constexpr int pp_group_doubles() {
+  // cs/xs region | su[3][256] | sw[3][128] | shinv[6][128] | sptm u32[128] | seg_cam u32[2][256] | seg_begin u16[2][258]
+  return (pp_region_doubles<DC>() + 3 * TILE + 3 * PP_PTS + 6 * PP_PTS + PP_PTS / 2 + TILE + (2 * CSEG_LD * 2 + 7) / 8 + 1) & ~1;  // even: 16-byte aligned groups
+}
+
+template <int DC, int STAGE>
+__device__ __forceinline__ void pp_prefetch_stage(const PpArgs& a, uint32_t chunk, bool valid, int gt, PpRegs<DC>& r) {
+  constexpr int NP = 2 * (DC + 3), NPAIR = NP / 2;
+  constexpr int M0 = (NPAIR * STAGE) / 4, M1 = (NPAIR * (STAGE + 1)) / 4;
+  if (STAGE == 0) { r.cam = PAD_CAM; r.sp = 0; r.pt0 = 0; r.npt = 0; r.nseg = 0; }
+  if (!valid) return;
+  const double2* p = reinterpret_cast<const double2*>(a.J) + (size_t)chunk * NPAIR * TILE + gt;
+#pragma unroll
+  for (int m = M0; m < M1; ++m) {
+    const double2 v = ld_stream2(p + (size_t)m * TILE);
+    r.j[2 * m] = v.x;
+    r.j[2 * m + 1] = v.y;
+  }
+  if (STAGE == 3) {
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(a.chunk_desc + chunk));
+    const uint2 m = __ldg(a.cslot_meta + (size_t)chunk * TILE + gt);
+    r.cam = m.x; r.sp = m.y;
+    r.pt0 = d.x; r.npt = d.y; r.nseg = d.z;
+  }
+}
+
+template <int DC>
+__device__ __forceinline__ void pp_fetch_tables(const PpArgs& a, uint32_t chunk, bool valid, int gt, uint32_t* sseg_cam, uint16_t* sseg_begin) {
+  if (!valid) return;
+  cp_async4(sseg_cam + gt, a.cseg_cam + (size_t)chunk * TILE + gt);
+  if (gt < CSEG_LD / 2) cp_async4(reinterpret_cast<uint32_t*>(sseg_begin) + gt, reinterpret_cast<const uint32_t*>(a.cseg_begin + (size_t)chunk * CSEG_LD) + gt);
+}
+
+template <int DC, bool PRIVATE>
+__global__ void __launch_bounds__(2 * TILE, 1) schur_matvec_pingpong_kernel(PpArgs a) {
+  constexpr int XS = (DC + 1) & ~1;
+  extern __shared__ __align__(16) double pp_smem[];
+  if (a.check_done && a.st->pcg_done) return;
+  const int tid = threadIdx.x, g = tid >> 8, gt = tid & (TILE - 1);
+  const uint32_t ny = PRIVATE ? ((a.n + 1) & ~1u) : 0;
+  double* y_priv = pp_smem;
+  double* base = pp_smem + ny + (size_t)g * pp_group_doubles<DC>();
+  double* cs = base;                       // [DC][257]; aliased by the per-segment x staging xs[nseg][XS]
+  double* su = cs + pp_region_doubles<DC>();
+  double* sw = su + 3 * TILE;
+  double* shinv = sw + 3 * PP_PTS;
+  uint32_t* sptm = reinterpret_cast<uint32_t*>(shinv + 6 * PP_PTS);
+  uint32_t* sseg_cam = sptm + PP_PTS;                                    // [2][256]
+  uint16_t* sseg_begin = reinterpret_cast<uint16_t*>(sseg_cam + 2 * TILE);  // [2][CSEG_LD]
+  if (PRIVATE)
+    for (uint32_t i = tid; i < a.n; i += 2 * TILE) y_priv[i] = 0.0;
+
+  // this CTA's chunk pairs: pair = blockIdx.x + it*gridDim.x ; group g takes chunk 2*pair + g
+  const uint32_t niter = (a.npairs - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  PpRegs<DC> ra, rb;
+  {
+    const uint32_t chunk = 2 * blockIdx.x + g;
+    const bool valid = chunk < a.nnormal_chunks;
+    pp_prefetch_stage<DC, 0>(a, chunk, valid, gt, ra);
+    pp_prefetch_stage<DC, 1>(a, chunk, valid, gt, ra);
+    pp_prefetch_stage<DC, 2>(a, chunk, valid, gt, ra);
+    pp_prefetch_stage<DC, 3>(a, chunk, valid, gt, ra);
+    pp_fetch_tables<DC>(a, chunk, valid, gt, sseg_cam, sseg_begin);
+    cp_async_commit();
+    cp_async_wait0();
+  }
+  __syncthreads();
+
+#define PP_BODY(R, RN)                                                                                                   \
+  {                                                                                                                      \
+    const uint32_t pair_next = blockIdx.x + (it + 1) * gridDim.x;                                                        \
+    const uint32_t chunk_next = 2 * pair_next + g;                                                                       \
+    const bool valid_next = (it + 1 < niter) && chunk_next < a.nnormal_chunks;                                           \
+    const int buf = it & 1;                                                                                              \
+    const uint32_t* segc = sseg_cam + buf * TILE;                                                                        \
+    const uint16_t* segb = sseg_begin + buf * CSEG_LD;                                                                   \
+    /* stage this chunk's landmark inverses + the next chunk's segment tables */                                        \
+    if ((uint32_t)gt < R.npt) {                                                                                          \
+      const uint32_t lp = R.pt0 + gt;                                                                                    \
+      _Pragma("unroll") for (int k = 0; k < 6; ++k) cp_async8(shinv + k * PP_PTS + gt, a.hinv + (size_t)k * a.npl + lp); \
+      cp_async4(sptm + gt, a.cpt_meta + lp);                                                                             \
+    }                                                                                                                    \
+    pp_fetch_tables<DC>(a, chunk_next, valid_next, gt, sseg_cam + (buf ^ 1) * TILE, sseg_begin + (buf ^ 1) * CSEG_LD);   \
+    cp_async_commit();                                                                                                   \
+    /* S0: x of every distinct camera of the chunk -> shared memory (coalesced per segment) */                          \
+    {                                                                                                                    \
+      double2* xs2 = reinterpret_cast<double2*>(cs);                                                                     \
+      const uint32_t nld = R.nseg * (XS / 2);                                                                            \
+      for (uint32_t idx = gt; idx < nld; idx += TILE) {                                                                  \
+        const uint32_t sgi = idx / (XS / 2), m = idx - sgi * (XS / 2);                                                   \
+        xs2[idx] = __ldg(reinterpret_cast<const double2*>(a.xpad + (size_t)segc[sgi] * XS) + m);                         \
+      }                                                                                                                  \
+    }                                                                                                                    \
+    pp_prefetch_stage<DC, 0>(a, chunk_next, valid_next, gt, RN);                                                         \
+    pp_group_bar(g);                                                                                                     \
+    /* P1: u_o = Jp^T (Jc x_c) */                                                                                        \
+    {                                                                                                                    \
+      double u0 = 0.0, u1 = 0.0, u2 = 0.0;                                                                               \
+      if (R.cam != PAD_CAM) {                                                                                            \
+        const double2* xs2 = reinterpret_cast<const double2*>(cs) + (size_t)((R.sp >> 16) & 0xFFFFu) * (XS / 2);         \
+        double xv[XS];                                                                                                   \
+        _Pragma("unroll") for (int m = 0; m < XS / 2; ++m) { const double2 v = xs2[m]; xv[2 * m] = v.x; xv[2 * m + 1] = v.y; } \
+        double a0 = 0.0, a1 = 0.0;                                                                                       \
+        _Pragma("unroll") for (int k = 0; k < DC; ++k) { a0 = fma(R.j[k], xv[k], a0); a1 = fma(R.j[DC + k], xv[k], a1); } \
+        const double* jp = R.j + 2 * DC;                                                                                 \
+        u0 = fma(jp[0], a0, jp[3] * a1); u1 = fma(jp[1], a0, jp[4] * a1); u2 = fma(jp[2], a0, jp[5] * a1);               \
+      }                                                                                                                  \
+      su[gt] = u0; su[TILE + gt] = u1; su[2 * TILE + gt] = u2;                                                           \
+    }                                                                                                                    \
+    pp_prefetch_stage<DC, 1>(a, chunk_next, valid_next, gt, RN);                                                         \
+    cp_async_wait0();                                                                                                    \
+    pp_group_bar(g);                                                                                                     \
+    /* P2: t_p = sum over the landmark's observations, w_p = Hpp^-1 t_p */                                               \
+    if ((uint32_t)gt < R.npt) {                                                                                          \
+      const uint32_t mm = sptm[gt], off = mm & 0xFFFFu, cnt = mm >> 16;                                                  \
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0, e0 = 0.0, e1 = 0.0, e2 = 0.0;                                                 \
+      uint32_t q = 0;                                                                                                    \
+      for (; q + 1 < cnt; q += 2) {                                                                                      \
+        t0 += su[off + q]; t1 += su[TILE + off + q]; t2 += su[2 * TILE + off + q];                                       \
+        e0 += su[off + q + 1]; e1 += su[TILE + off + q + 1]; e2 += su[2 * TILE + off + q + 1];                           \
+      }                                                                                                                  \
+      if (q < cnt) { t0 += su[off + q]; t1 += su[TILE + off + q]; t2 += su[2 * TILE + off + q]; }                        \
+      t0 += e0; t1 += e1; t2 += e2;                                                                                      \
+      const double h00 = shinv[gt], h01 = shinv[PP_PTS + gt], h02 = shinv[2 * PP_PTS + gt];                              \
+      const double h11 = shinv[3 * PP_PTS + gt], h12 = shinv[4 * PP_PTS + gt], h22 = shinv[5 * PP_PTS + gt];             \
+      sw[gt] = h00 * t0 + h01 * t1 + h02 * t2;                                                                           \
+      sw[PP_PTS + gt] = h01 * t0 + h11 * t1 + h12 * t2;                                                                  \
+      sw[2 * PP_PTS + gt] = h02 * t0 + h12 * t1 + h22 * t2;                                                              \
+    }                                                                                                                    \
+    pp_prefetch_stage<DC, 2>(a, chunk_next, valid_next, gt, RN);                                                         \
+    pp_group_bar(g);                                                                                                     \
+    /* P3: c_o = -Jc^T (Jp w_p) at the observation's camera-sorted position (xs is dead: cs reuses the region) */       \
+    if (R.cam != PAD_CAM) {                                                                                              \
+      const uint32_t spt = R.sp & 0xFFu, pos = (R.sp >> 8) & 0xFFu;                                                      \
+      const double w0 = sw[spt], w1 = sw[PP_PTS + spt], w2 = sw[2 * PP_PTS + spt];                                       \
+      const double* jp = R.j + 2 * DC;                                                                                   \
+      const double b0 = fma(jp[0], w0, fma(jp[1], w1, jp[2] * w2));                                                      \
+      const double b1 = fma(jp[3], w0, fma(jp[4], w1, jp[5] * w2));                                                      \
+      _Pragma("unroll") for (int k = 0; k < DC; ++k) cs[k * PP_CS_LD + pos] = -fma(R.j[k], b0, R.j[DC + k] * b1);        \
+    }                                                                                                                    \
+    pp_prefetch_stage<DC, 3>(a, chunk_next, valid_next, gt, RN);                                                         \
+    pp_group_bar(g);                                                                                                     \
+    /* P4: one thread per (camera segment, dof); the two groups take turns on the private y */                          \
+    if (PRIVATE) { if (g == 0) { if (it > 0) pp_turn_wait(4); } else pp_turn_wait(3); }                                  \
+    {                                                                                                                    \
+      const uint32_t nwork = R.nseg * DC;                                                                                \
+      for (uint32_t idx = gt; idx < nwork; idx += TILE) {                                                                \
+        const uint32_t sgi = idx / DC, k = idx - sgi * DC;                                                               \
+        const uint32_t b = segb[sgi], e = segb[sgi + 1];                                                                 \
+        const double* c0 = cs + k * PP_CS_LD;                                                                            \
+        double v = 0.0;                                                                                                  \
+        for (uint32_t q = b; q < e; ++q) v += c0[q];                                                                     \
+        const uint32_t row = segc[sgi] * DC + k;                                                                         \
+        if (PRIVATE) y_priv[row] += v; else red_add(a.y + row, v);                                                       \
+      }                                                                                                                  \
+    }                                                                                                                    \
+    if (PRIVATE) { if (g == 0) pp_turn_signal(3); else if (it + 1 < niter) pp_turn_signal(4); }                          \
+    pp_group_bar(g); /* cs / tables of this parity are rewritten next iteration */                                       \
+  }
+
+  uint32_t it = 0;
+  while (it < niter) {
+    PP_BODY(ra, rb)
+    ++it;
+    if (it >= niter) break;
+    PP_BODY(rb, ra)
+    ++it;
+  }
+#undef PP_BODY
+  __syncthreads();
+  if (PRIVATE) {
+    double* out = a.ypart + (size_t)blockIdx.x * a.n;
+    for (uint32_t i = tid; i < a.n; i += 2 * TILE) out[i] = y_priv[i];
+  }
+}
+
+template <int DC>
+static size_t pp_smem_bytes(uint32_t n, bool priv) {
+  return ((priv ? ((n + 1) & ~1u) : 0) + 2 * (size_t)pp_group_doubles<DC>()) * 8 + 64;
+}
+
+template <int DC>
+static apex_status launch_pingpong_dc(Ctx& c, const PpArgs& a, bool priv, unsigned grid) {
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[priv ? 1 : 0]) {
+    if (priv) APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_matvec_pingpong_kernel<DC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MV_SMEM_MAX));
+    else APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_matvec_pingpong_kernel<DC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MV_SMEM_MAX));
+    attr_done[priv ? 1 : 0] = true;
+  }
+  const size_t smem = pp_smem_bytes<DC>(a.n, priv);
+  if (priv) schur_matvec_pingpong_kernel<DC, true><<<grid, 2 * TILE, smem, c.stream>>>(a);
+  else schur_matvec_pingpong_kernel<DC, false><<<grid, 2 * TILE, smem, c.stream>>>(a);
+  return APEX_OK;
+}
+
 // x (stride dc) -> x at an even stride (camera blocks 16-byte aligned for the 128-bit gathers)
 __global__ void pad_x_kernel(const double* __restrict__ x, double* __restrict__ xpad, uint32_t ncam, int dc, int xs, const DevState* st, int check_done) {
   if (check_done && st->pcg_done) return;
@@ -647,31 +887,65 @@ apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_d
     APEX_TRY(launch_hcc_apply(c, x, y, check_done));
     return launch_schur_tiles(c, MODE_MATVEC, x, y, check_done);
   }
-  const bool priv = mv_smem_bytes(c.dc, n, true) <= (size_t)MV_SMEM_MAX && !(force && force[0] == 'r');
-  const unsigned grid = (unsigned)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)c.num_sms, c.nsuper));
+  const bool use_v2 = force && force[0] == 'p' && force[1] == 'e';  // "persist": lock-step supertile kernel (second generation)
   const int xs = (c.dc + 1) & ~1;
   pad_x_kernel<<<(c.ncam * xs + 255) / 256, 256, 0, c.stream>>>(x, c.xpad.p, c.ncam, c.dc, xs, c.state.p, check_done);
   c.launches++;
-  MvArgs a{c.supers.p, c.slot_meta.p, c.pt_meta.p, c.seg_cam.p, c.seg_begin.p, c.J.p, c.hinv.p, c.xpad.p, y, c.ypart.p, n, c.npl, c.nsuper, c.nnormal_chunks, check_done, c.state.p, nullptr};
-  static long long* d_timing = nullptr;
+  bool priv;
+  unsigned grid;
   const bool want_timing = getenv("APEX_MV_TIMING") != nullptr;
-  if (want_timing) { if (!d_timing) cudaMalloc(&d_timing, 12 * sizeof(long long)); a.timing = d_timing; }
-  const size_t smem = mv_smem_bytes(c.dc, n, priv);
-  if (!priv) APEX_TRY(launch_hcc_apply(c, x, y, check_done));  // y starts as (H_cc + lambda I) x; the kernel reduces into it
-  cudaEvent_t* evp = (c.prof && c.nsuper) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
-  if (evp) cudaEventRecord(evp[0], c.stream);
-  if (c.nsuper) {
+  static long long* d_timing = nullptr;
+  if (use_v2) {
+    priv = mv_smem_bytes(c.dc, n, true) <= (size_t)MV_SMEM_MAX && !(force && force[0] == 'r');
+    grid = (unsigned)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)c.num_sms, c.nsuper));
+    MvArgs a{c.supers.p, c.slot_meta.p, c.pt_meta.p, c.seg_cam.p, c.seg_begin.p, c.J.p, c.hinv.p, c.xpad.p, y, c.ypart.p, n, c.npl, c.nsuper, c.nnormal_chunks, check_done, c.state.p, nullptr};
+    if (want_timing) { if (!d_timing) cudaMalloc(&d_timing, 12 * sizeof(long long)); a.timing = d_timing; }
+    const size_t smem = mv_smem_bytes(c.dc, n, priv);
+    if (!priv) APEX_TRY(launch_hcc_apply(c, x, y, check_done));  // y starts as (H_cc + lambda I) x; the kernel reduces into it
+    cudaEvent_t* evp = (c.prof && c.nsuper) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
+    if (evp) cudaEventRecord(evp[0], c.stream);
+    if (c.nsuper) {
+      switch (c.dc) {
+        case 6: APEX_TRY(launch_persist_dc<6>(c, a, priv, grid, smem)); break;
+        case 9: APEX_TRY(launch_persist_dc<9>(c, a, priv, grid, smem)); break;
+        case 10: APEX_TRY(launch_persist_dc<10>(c, a, priv, grid, smem)); break;
+        case 12: APEX_TRY(launch_persist_dc<12>(c, a, priv, grid, smem)); break;
+        case 14: APEX_TRY(launch_persist_dc<14>(c, a, priv, grid, smem)); break;
+        default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
+      }
+      c.launches++;
+    }
+    if (evp) cudaEventRecord(evp[1], c.stream);
+  } else {
+    const uint32_t npairs = c.nsuper;  // chunk pairs (2s, 2s+1)
+    size_t need = 0;
     switch (c.dc) {
-      case 6: APEX_TRY(launch_persist_dc<6>(c, a, priv, grid, smem)); break;
-      case 9: APEX_TRY(launch_persist_dc<9>(c, a, priv, grid, smem)); break;
-      case 10: APEX_TRY(launch_persist_dc<10>(c, a, priv, grid, smem)); break;
-      case 12: APEX_TRY(launch_persist_dc<12>(c, a, priv, grid, smem)); break;
-      case 14: APEX_TRY(launch_persist_dc<14>(c, a, priv, grid, smem)); break;
+      case 6: need = pp_smem_bytes<6>(n, true); break;
+      case 9: need = pp_smem_bytes<9>(n, true); break;
+      case 10: need = pp_smem_bytes<10>(n, true); break;
+      case 12: need = pp_smem_bytes<12>(n, true); break;
+      case 14: need = pp_smem_bytes<14>(n, true); break;
       default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
     }
-    c.launches++;
+    priv = need <= (size_t)MV_SMEM_MAX && !(force && force[0] == 'r');
+    grid = (unsigned)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)c.num_sms, npairs));
+    PpArgs a{c.chunk_desc.p, c.cslot_meta.p, c.cpt_meta.p, c.cseg_cam.p, c.cseg_begin.p, c.J.p, c.hinv.p, c.xpad.p, y, c.ypart.p,
+             n, c.npl, npairs, c.nnormal_chunks, check_done, c.state.p};
+    if (!priv) APEX_TRY(launch_hcc_apply(c, x, y, check_done));
+    cudaEvent_t* evp = (c.prof && npairs) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
+    if (evp) cudaEventRecord(evp[0], c.stream);
+    if (npairs) {
+      switch (c.dc) {
+        case 6: APEX_TRY(launch_pingpong_dc<6>(c, a, priv, grid)); break;
+        case 9: APEX_TRY(launch_pingpong_dc<9>(c, a, priv, grid)); break;
+        case 10: APEX_TRY(launch_pingpong_dc<10>(c, a, priv, grid)); break;
+        case 12: APEX_TRY(launch_pingpong_dc<12>(c, a, priv, grid)); break;
+        default: APEX_TRY(launch_pingpong_dc<14>(c, a, priv, grid)); break;
+      }
+      c.launches++;
+    }
+    if (evp) cudaEventRecord(evp[1], c.stream);
   }
-  if (evp) cudaEventRecord(evp[1], c.stream);
   if (priv) {
     schur_finalize_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(c.hcc.p, x, c.ypart.p, c.nsuper ? grid : 0u, y, c.state.p, n, c.dc,
                                                                  c.rank == 0 ? 1 : 0, check_done);
