@@ -213,6 +213,17 @@ def shard_range(obs_pt, npts: int, nranks: int, rank: int):
     return p0.value, p1.value, n.value
 
 
+def layout_stats(prob: BAProblem, nranks: int = 1, rank: int = 0) -> F.LayoutStats:
+    """Host-only: build (and self-check) the observation layout rank `rank` of `nranks` would upload."""
+    lib = F.load_library()
+    d = prob.desc()
+    out = F.LayoutStats()
+    st = lib.apex_layout_stats_compute(C.byref(d), int(nranks), int(rank), C.byref(out))
+    if st != F.OK:
+        raise F.ApexError(st, "layout_stats")
+    return out
+
+
 class GpuContext(Context):
     """Context on the product library csrc/libapex_gpu.so (sm_100a kernels). No CPU fallback."""
 

@@ -41,14 +41,6 @@ struct TileDesc {
   uint32_t nchunks;  // 1 for a normal tile; >1 only when npt == 1
 };
 
-// Two consecutive normal tiles (chunks 2s, 2s+1) processed together by the persistent Schur-operator kernel.
-struct SuperDesc {
-  uint32_t ptA0, nptA;   // landmarks of chunk 2s
-  uint32_t ptB0, nptB;   // landmarks of chunk 2s+1 (nptB = 0 and validB = 0 when there is none)
-  uint32_t nseg;         // distinct cameras among the <=512 observations
-  uint32_t validB;
-  uint32_t pad[2];
-};
 // Per-chunk descriptor of the ping-pong operator kernel (one 256-thread group processes one chunk at a time).
 struct ChunkDesc {
   uint32_t pt0, npt;   // landmarks of the chunk (0 landmarks for a padding chunk)
@@ -56,7 +48,6 @@ struct ChunkDesc {
   uint32_t pad;
 };
 constexpr int CSEG_LD = TILE + 2;     // u16 entries per chunk in cseg_begin (sentinel + padding to a 4-byte multiple)
-constexpr int STILE = 2 * TILE;       // slots per supertile
 constexpr int MAX_TILE_PTS = 128;     // landmarks per normal tile (so a supertile stages <= 256 landmark inverses)
 
 struct CamItem { uint32_t cam, begin, end, pad; };  // [begin,end) in the camera-major arrays
@@ -76,6 +67,8 @@ struct DevState {
   double cost2_local;                     // sum r~^2 of the local observations
   // PCG
   double rz_old, pcg_tol, b_norm, r_norm;
+  double pcg_alpha, pcg_beta;
+  uint32_t ticket_a, ticket_b;            // last-block-done counters of the multi-CTA PCG kernels
   int32_t pcg_iters, pcg_done, pcg_max, pad1;
   // errors
   int32_t singular_landmark;              // a landmark block could not be inverted
@@ -121,7 +114,7 @@ struct Ctx {
   uint32_t p0 = 0, p1 = 0, npl = 0;  // local landmark range
   uint64_t nobs_local = 0;
   uint32_t nchunks = 0, ntiles = 0, nitems = 0;
-  uint32_t nsuper = 0, ngiant = 0, nnormal_chunks = 0;
+  uint32_t npairs = 0, ngiant = 0, nnormal_chunks = 0;  // npairs: chunk pairs (2s, 2s+1) walked by the operator kernel
   size_t nslots = 0;
   std::vector<uint64_t> slot_obs;  // slot -> caller's observation index (UINT64_MAX for padding)
   std::vector<uint32_t> h_pt_cnt;
@@ -131,11 +124,6 @@ struct Ctx {
   DevBuf<uint32_t> slot_cam;
   DevBuf<uint16_t> slot_lp;
   DevBuf<TileDesc> giant_tiles;      // the tiles with nchunks > 1 (a landmark with more than 256 observations)
-  DevBuf<SuperDesc> supers;
-  DevBuf<uint2> slot_meta;           // per slot: {camera, supertile-local landmark | camera-sorted position << 16}
-  DevBuf<uint32_t> pt_meta;          // per landmark: supertile-local first slot | count << 16
-  DevBuf<uint32_t> seg_cam;          // [nsuper][512] camera of each camera-segment
-  DevBuf<uint16_t> seg_begin;        // [nsuper][514] first sorted position of each segment (+ sentinel)
   DevBuf<ChunkDesc> chunk_desc;      // [nnormal_chunks rounded up to even]
   DevBuf<uint2> cslot_meta;          // per slot: {camera, chunk-local landmark | sorted position << 8 | segment << 16}
   DevBuf<uint32_t> cpt_meta;         // per landmark: chunk-local first slot | count << 16
@@ -216,6 +204,7 @@ inline cudaEvent_t* prof_pair(std::vector<cudaEvent_t>& pool, size_t idx) {
 // ---- launchers (one per kernel group; defined in the .cu files) --------------------------------------
 // problem.cu
 apex_status problem_upload(Ctx& c, const apex_problem_desc* d);
+apex_status layout_stats(const apex_problem_desc* d, int nranks, int rank, apex_layout_stats* out, std::string& err);
 void shard_range(uint32_t npts, uint64_t nobs, const uint32_t* obs_pt, int nranks, int rank, std::vector<uint64_t>& pt_start, uint32_t& p0, uint32_t& p1);
 // linearize.cu
 apex_status launch_normalize_poses(Ctx& c);
@@ -226,8 +215,8 @@ apex_status launch_schur_jacobi_blocks(Ctx& c, int kind);   // K5 build: fills p
 enum TileMode { MODE_MATVEC = 0, MODE_RHS = 1, MODE_BACKSUB = 2 };
 apex_status launch_schur_tiles(Ctx& c, int mode, const double* x, double* y, int check_done);
 apex_status launch_hcc_apply(Ctx& c, const double* x, double* y, int check_done);  // y = (H_cc + lambda I) x on rank 0, else 0
-apex_status schur_operator(Ctx& c, const double* x, double* y, int check_done);    // y = S x, all-reduced
-apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_done);  // this rank's part
+apex_status schur_operator(Ctx& c, const double* x, double* y, int check_done, bool xpad_ready = false);    // y = S x, all-reduced
+apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_done, bool xpad_ready = false);  // this rank's part
 apex_status launch_reduced_gradient(Ctx& c, double* b);
 apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol);
 // explicit.cu

@@ -147,7 +147,7 @@ void apex_ctx_destroy(apex_ctx* ctx) {
                            &c.sj, &c.pinv, &c.vb, &c.vx, &c.vr, &c.vz, &c.vp, &c.vy, &c.step_cam, &c.step_pt, &c.red_scratch, &c.S, &c.E,
                            &c.dvec, &c.l2flush};
   for (auto* b : dbl) b->release();
-  c.giant_tiles.release(); c.supers.release(); c.slot_meta.release(); c.pt_meta.release(); c.seg_cam.release(); c.seg_begin.release(); c.ypart.release(); c.xpad.release(); c.chunk_desc.release(); c.cslot_meta.release(); c.cpt_meta.release(); c.cseg_cam.release(); c.cseg_begin.release();
+  c.giant_tiles.release(); c.ypart.release(); c.xpad.release(); c.chunk_desc.release(); c.cslot_meta.release(); c.cpt_meta.release(); c.cseg_cam.release(); c.cseg_begin.release();
   c.tiles.release(); c.slot_cam.release(); c.slot_lp.release(); c.pt_slot0.release(); c.pt_cnt.release(); c.items.release();
   c.cam_item_start.release(); c.cm_lp.release(); c.pose_fixed.release(); c.pt_fixed.release(); c.intr_fixed.release();
   c.state.release(); c.trace.release();
@@ -380,6 +380,13 @@ apex_status apex_profile_read(apex_ctx* ctx, apex_profile* out) {
     if (cudaEventElapsedTime(&t, c.ev_lm0, c.ev_lm1) == cudaSuccess) out->lm_device_ms = t; else cudaGetLastError();
   }
   return APEX_OK;
+}
+
+apex_status apex_layout_stats_compute(const apex_problem_desc* desc, int32_t nranks, int32_t rank, apex_layout_stats* out) {
+  if (!desc || !out || nranks < 1 || rank < 0 || rank >= nranks) return APEX_ERR_INVALID_INPUT;
+  std::memset(out, 0, sizeof(*out));
+  std::string err;
+  return layout_stats(desc, nranks, rank, out, err);
 }
 
 apex_status apex_shard_range(uint32_t npts, uint64_t nobs, const uint32_t* obs_pt, int32_t nranks, int32_t rank, uint32_t* p0, uint32_t* p1,

@@ -1,8 +1,10 @@
 // problem.cu — apex_problem_upload: replaces Problem construction + initialize_optimization_state
 // (src/core/problem.rs:518-808, src/optimizer/mod.rs:522-563) for the SoA factor graph of
 // bin/bundle_adjustment.rs:212-441. Builds the static observation structure described in apex_ctx.h:
-// landmark sharding across ranks, point-major tiles, camera-major work items.
+// landmark sharding across ranks, point-major tiles with per-chunk camera segments, camera-major work items.
+// build_layout() is pure host code (OpenMP over tiles) so it can be exercised without a device.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <numeric>
 
@@ -37,23 +39,239 @@ void shard_range(uint32_t npts, uint64_t nobs, const uint32_t* obs_pt, int nrank
   p1 = boundary(rank + 1);
 }
 
-apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
-  // ---- validation (same failures as the reference / oracle) ----
+apex_status validate_problem(const apex_problem_desc* d, std::string& err) {
   int K = model_intr_dim(d->camera_model);
-  if (K < 0) { c.err = "camera model not supported on the GPU path"; return APEX_ERR_UNSUPPORTED; }
-  if (d->intr_dim != K) { c.err = "intr_dim does not match camera model"; return APEX_ERR_INVALID_INPUT; }
+  if (K < 0) { err = "camera model not supported on the GPU path"; return APEX_ERR_UNSUPPORTED; }
+  if (d->intr_dim != K) { err = "intr_dim does not match camera model"; return APEX_ERR_INVALID_INPUT; }
   if ((d->opt_flags & (APEX_OPT_POSE | APEX_OPT_LANDMARK)) != (APEX_OPT_POSE | APEX_OPT_LANDMARK)) {
-    c.err = "only BundleAdjustment / SelfCalibration OptimizeParams are live (bin/bundle_adjustment.rs)";
+    err = "only BundleAdjustment / SelfCalibration OptimizeParams are live (bin/bundle_adjustment.rs)";
     return APEX_ERR_UNSUPPORTED;
   }
-  if (d->ncam == 0) { c.err = "No camera variables found"; return APEX_ERR_INVALID_INPUT; }    // explicit_schur.rs:278-282
-  if (d->npts == 0) { c.err = "No landmark variables found"; return APEX_ERR_INVALID_INPUT; }  // explicit_schur.rs:283-287
-  if (d->nobs > 0xFFFFFFF0ull) { c.err = "too many observations for u32 slots"; return APEX_ERR_UNSUPPORTED; }
-  if (d->loss_id < APEX_LOSS_NONE || d->loss_id > APEX_LOSS_T_DISTRIBUTION) { c.err = "unknown loss id"; return APEX_ERR_INVALID_INPUT; }
+  if (d->ncam == 0) { err = "No camera variables found"; return APEX_ERR_INVALID_INPUT; }    // explicit_schur.rs:278-282
+  if (d->npts == 0) { err = "No landmark variables found"; return APEX_ERR_INVALID_INPUT; }  // explicit_schur.rs:283-287
+  if (d->nobs > 0xFFFFFFF0ull) { err = "too many observations for u32 slots"; return APEX_ERR_UNSUPPORTED; }
+  if (d->loss_id < APEX_LOSS_NONE || d->loss_id > APEX_LOSS_T_DISTRIBUTION) { err = "unknown loss id"; return APEX_ERR_INVALID_INPUT; }
   const uint64_t nobs = d->nobs;
-  for (uint64_t o = 0; o < nobs; ++o)
-    if (d->obs_cam[o] >= d->ncam || d->obs_pt[o] >= d->npts) { c.err = "observation index out of range"; return APEX_ERR_INVALID_INPUT; }
+  int bad = 0;
+#pragma omp parallel for reduction(| : bad) schedule(static)
+  for (int64_t o = 0; o < (int64_t)nobs; ++o) bad |= (d->obs_cam[o] >= d->ncam || d->obs_pt[o] >= d->npts) ? 1 : 0;
+  if (bad) { err = "observation index out of range"; return APEX_ERR_INVALID_INPUT; }
+  return APEX_OK;
+}
 
+// The static structure of one rank's shard, on the host.
+struct HostLayout {
+  uint32_t p0 = 0, p1 = 0, npl = 0;
+  uint64_t nobs_local = 0;
+  uint32_t nnormal_chunks = 0, nchunks = 0, npairs = 0;
+  std::vector<TileDesc> tiles, giant_tiles;
+  std::vector<uint32_t> pt_slot0, pt_cnt;
+  std::vector<uint32_t> slot_cam;
+  std::vector<uint16_t> slot_lp;
+  std::vector<double> slot_uv;
+  std::vector<uint64_t> slot_obs;
+  std::vector<ChunkDesc> chunk_desc;
+  std::vector<uint2> cslot_meta;
+  std::vector<uint32_t> cpt_meta, cseg_cam;
+  std::vector<uint16_t> cseg_begin;
+  std::vector<double> cm_uv;
+  std::vector<uint32_t> cm_lp;
+  std::vector<CamItem> items;
+  std::vector<uint32_t> cam_item_start;
+};
+
+static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostLayout& L) {
+  const uint64_t nobs = d->nobs;
+  const uint32_t ncam = d->ncam;
+  // ---- landmark sharding ----
+  std::vector<uint64_t> pt_start;
+  shard_range(d->npts, nobs, d->obs_pt, nranks, rank, pt_start, L.p0, L.p1);
+  L.npl = L.p1 - L.p0;
+  L.nobs_local = pt_start[L.p1] - pt_start[L.p0];
+  const uint32_t npl = L.npl;
+
+  // ---- point-major order of the local observations (stable in the caller's insertion order) ----
+  std::vector<uint64_t> pm(L.nobs_local);
+  {
+    std::vector<uint64_t> cur(pt_start.begin() + L.p0, pt_start.begin() + L.p1);
+    const uint64_t base = pt_start[L.p0];
+    for (uint64_t o = 0; o < nobs; ++o) {
+      const uint32_t p = d->obs_pt[o];
+      if (p >= L.p0 && p < L.p1) pm[cur[p - L.p0]++ - base] = o;
+    }
+  }
+
+  // ---- tiles ----
+  // Normal tiles (<=256 observations, <=128 landmarks) get chunk ids 0..nn-1 in landmark order so that the
+  // operator kernel's two thread groups can take chunks (2s, 2s+1); landmarks with more than 256 observations get
+  // their chunks after those.
+  L.pt_slot0.assign(npl, 0);
+  L.pt_cnt.assign(npl, 0);
+  std::vector<uint64_t> tile_q0;  // first point-major observation of each tile
+  uint32_t chunk = 0;
+  {
+    uint32_t cur_pt0 = 0, cur_npt = 0, cur_obs = 0;
+    uint64_t q = 0, cur_q0 = 0;
+    auto flush = [&]() {
+      if (cur_npt == 0) return;
+      L.tiles.push_back({cur_pt0, cur_npt, chunk, 1});
+      tile_q0.push_back(cur_q0);
+      chunk += 1;
+      cur_npt = 0; cur_obs = 0;
+    };
+    for (uint32_t lp = 0; lp < npl; ++lp) {
+      const uint32_t k = (uint32_t)(pt_start[L.p0 + lp + 1] - pt_start[L.p0 + lp]);
+      L.pt_cnt[lp] = k;
+      if (k > (uint32_t)TILE) {
+        flush();
+        L.tiles.push_back({lp, 1, 0xFFFFFFFFu, (k + TILE - 1) / TILE});  // chunk0 assigned below
+        tile_q0.push_back(q);
+        q += k;
+        continue;
+      }
+      if (cur_npt > 0 && (cur_obs + k > (uint32_t)TILE || cur_npt >= (uint32_t)MAX_TILE_PTS)) flush();
+      if (cur_npt == 0) { cur_pt0 = lp; cur_q0 = q; }
+      L.pt_slot0[lp] = chunk * TILE + cur_obs;
+      cur_npt++;
+      cur_obs += k;
+      q += k;
+    }
+    flush();
+  }
+  L.nnormal_chunks = chunk;
+  for (TileDesc& t : L.tiles)
+    if (t.nchunks > 1) {
+      t.chunk0 = chunk;
+      L.pt_slot0[t.pt0] = chunk * TILE;
+      chunk += t.nchunks;
+      L.giant_tiles.push_back(t);
+    }
+  L.nchunks = chunk;
+  const size_t nslots = (size_t)chunk * TILE;
+  const uint32_t nchunk_even = (L.nnormal_chunks + 1) & ~1u;
+  L.npairs = nchunk_even / 2;
+
+  // ---- slot arrays + per-chunk camera-sorted segment structure (parallel over tiles) ----
+  L.slot_cam.assign(nslots, PAD_CAM);
+  L.slot_lp.assign(nslots, 0);
+  L.slot_uv.assign(nslots * 2, 0.0);
+  L.slot_obs.assign(nslots, UINT64_MAX);
+  L.chunk_desc.assign(nchunk_even, ChunkDesc{0, 0, 0, 0});
+  L.cslot_meta.assign((size_t)nchunk_even * TILE, make_uint2(PAD_CAM, 0));
+  L.cpt_meta.assign(npl, 0);
+  L.cseg_cam.assign((size_t)nchunk_even * TILE, 0);
+  L.cseg_begin.assign((size_t)nchunk_even * CSEG_LD, 0);
+  const int64_t ntiles = (int64_t)L.tiles.size();
+#pragma omp parallel
+  {
+    std::vector<std::pair<uint32_t, uint32_t>> order;  // (camera, chunk-local slot)
+#pragma omp for schedule(dynamic, 64)
+    for (int64_t ti = 0; ti < ntiles; ++ti) {
+      const TileDesc& t = L.tiles[ti];
+      uint64_t q = tile_q0[ti];
+      order.clear();
+      for (uint32_t i = 0; i < t.npt; ++i) {
+        const uint32_t lp = t.pt0 + i;
+        const uint32_t off = L.pt_slot0[lp] - t.chunk0 * TILE;
+        if (t.nchunks == 1) L.cpt_meta[lp] = off | (L.pt_cnt[lp] << 16);
+        for (uint32_t k = 0; k < L.pt_cnt[lp]; ++k, ++q) {
+          const size_t slot = (size_t)L.pt_slot0[lp] + k;
+          const uint64_t o = pm[q];
+          const uint32_t cam = d->obs_cam[o];
+          L.slot_cam[slot] = cam;
+          L.slot_lp[slot] = (uint16_t)i;
+          const size_t ch = slot / TILE, lane = slot % TILE;
+          L.slot_uv[(ch * 2 + 0) * TILE + lane] = d->obs_uv[2 * o];
+          L.slot_uv[(ch * 2 + 1) * TILE + lane] = d->obs_uv[2 * o + 1];
+          L.slot_obs[slot] = o;
+          if (t.nchunks == 1) {
+            L.cslot_meta[slot].x = cam;
+            L.cslot_meta[slot].y = i;
+            order.push_back({cam, off + k});
+          }
+        }
+      }
+      if (t.nchunks != 1) continue;
+      const uint32_t ch = t.chunk0;
+      std::sort(order.begin(), order.end());
+      uint32_t nseg = 0;
+      for (size_t pos = 0; pos < order.size(); ++pos) {
+        if (pos == 0 || order[pos].first != order[pos - 1].first) {
+          L.cseg_cam[(size_t)ch * TILE + nseg] = order[pos].first;
+          L.cseg_begin[(size_t)ch * CSEG_LD + nseg] = (uint16_t)pos;
+          ++nseg;
+        }
+        L.cslot_meta[(size_t)ch * TILE + order[pos].second].y |= ((uint32_t)pos << 8) | ((nseg - 1) << 16);
+      }
+      L.cseg_begin[(size_t)ch * CSEG_LD + nseg] = (uint16_t)order.size();
+      L.chunk_desc[ch] = ChunkDesc{t.pt0, t.npt, nseg, 0};
+    }
+  }
+
+  // ---- camera-major copy of the local observations + work items ----
+  std::vector<uint32_t> cam_start((size_t)ncam + 1, 0);
+  for (uint64_t q = 0; q < L.nobs_local; ++q) cam_start[d->obs_cam[pm[q]] + 1]++;
+  for (uint32_t k = 0; k < ncam; ++k) cam_start[k + 1] += cam_start[k];
+  L.cm_uv.resize(2 * (size_t)L.nobs_local);
+  L.cm_lp.resize(L.nobs_local);
+  {
+    std::vector<uint32_t> cur(cam_start.begin(), cam_start.end() - 1);
+    uint64_t q = 0;
+    for (uint32_t lp = 0; lp < npl; ++lp)
+      for (uint32_t k = 0; k < L.pt_cnt[lp]; ++k, ++q) {
+        const uint64_t o = pm[q];
+        const uint32_t pos = cur[d->obs_cam[o]]++;
+        L.cm_uv[pos] = d->obs_uv[2 * o];
+        L.cm_uv[(size_t)L.nobs_local + pos] = d->obs_uv[2 * o + 1];
+        L.cm_lp[pos] = lp;
+      }
+  }
+  L.cam_item_start.assign((size_t)ncam + 1, 0);
+  for (uint32_t k = 0; k < ncam; ++k) {
+    L.cam_item_start[k] = (uint32_t)L.items.size();
+    for (uint32_t b = cam_start[k]; b < cam_start[k + 1]; b += CAM_CHUNK)
+      L.items.push_back({k, b, std::min<uint32_t>(b + CAM_CHUNK, cam_start[k + 1]), 0});
+  }
+  L.cam_item_start[ncam] = (uint32_t)L.items.size();
+}
+
+apex_status layout_stats(const apex_problem_desc* d, int nranks, int rank, apex_layout_stats* out, std::string& err) {
+  APEX_TRY(validate_problem(d, err));
+  const auto t0 = std::chrono::steady_clock::now();
+  HostLayout L;
+  build_layout(d, nranks, rank, L);
+  out->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  out->p0 = L.p0; out->p1 = L.p1; out->nobs_local = L.nobs_local;
+  out->ntiles = (uint32_t)L.tiles.size(); out->nlong_tiles = (uint32_t)L.giant_tiles.size();
+  out->nchunks = L.nchunks; out->nnormal_chunks = L.nnormal_chunks; out->ncam_items = (uint32_t)L.items.size();
+  uint64_t nseg = 0, maxseg = 0, covered = 0;
+  for (const ChunkDesc& cd : L.chunk_desc) { nseg += cd.nseg; maxseg = std::max<uint64_t>(maxseg, cd.nseg); }
+  for (uint64_t o : L.slot_obs) covered += o != UINT64_MAX;
+  out->nsegments = nseg; out->max_segments_per_chunk = (uint32_t)maxseg; out->slots_used = covered;
+  // structural self-check: every local observation sits in exactly one slot, camera-sorted positions are a
+  // permutation of the chunk's observations and every segment is a run of one camera
+  out->consistent = covered == L.nobs_local ? 1 : 0;
+  for (const TileDesc& t : L.tiles) {
+    if (t.nchunks != 1) continue;
+    const size_t base = (size_t)t.chunk0 * TILE;
+    int seen[TILE] = {0};
+    uint32_t nobs_tile = 0;
+    for (uint32_t i = 0; i < t.npt; ++i) nobs_tile += L.pt_cnt[t.pt0 + i];
+    const ChunkDesc& cd = L.chunk_desc[t.chunk0];
+    for (uint32_t s = 0; s < nobs_tile; ++s) {
+      const uint2 m = L.cslot_meta[base + s];
+      const uint32_t pos = (m.y >> 8) & 0xFFu, seg = (m.y >> 16) & 0xFFFFu;
+      if (pos >= nobs_tile || seen[pos]++ || seg >= cd.nseg || L.cseg_cam[base + seg] != m.x) { out->consistent = 0; break; }
+      const uint32_t b = L.cseg_begin[(size_t)t.chunk0 * CSEG_LD + seg], e = L.cseg_begin[(size_t)t.chunk0 * CSEG_LD + seg + 1];
+      if (pos < b || pos >= e) { out->consistent = 0; break; }
+    }
+  }
+  return APEX_OK;
+}
+
+apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
+  APEX_TRY(validate_problem(d, c.err));
+  const int K = model_intr_dim(d->camera_model);
   c.have_problem = false;
   c.linearized = false;
   c.model = d->camera_model; c.K = K; c.opt = d->opt_flags;
@@ -61,215 +279,19 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   c.intr_vars = d->intr_vars_present != 0;
   c.dc = 6 + (c.opt_intr ? K : 0);
   c.np = 2 * (c.dc + 3);
-  c.ncam = d->ncam; c.npts = d->npts; c.nobs = nobs;
+  c.ncam = d->ncam; c.npts = d->npts; c.nobs = d->nobs;
   c.cam_dof_ref = (uint64_t)c.ncam * (6 + ((c.opt_intr || c.intr_vars) ? K : 0));
   c.loss_id = d->loss_id;
   for (int i = 0; i < 4; ++i) c.loss_p[i] = d->loss_params[i];
 
-  // ---- landmark sharding: contiguous ranges balanced by observation count ----
-  std::vector<uint64_t> pt_start;
-  shard_range(c.npts, nobs, d->obs_pt, c.nranks, c.rank, pt_start, c.p0, c.p1);
-  c.npl = c.p1 - c.p0;
-  c.nobs_local = pt_start[c.p1] - pt_start[c.p0];
-
-  // ---- point-major order of the local observations (stable in the caller's insertion order) ----
-  std::vector<uint64_t> pm(c.nobs_local);
-  {
-    std::vector<uint64_t> cur(pt_start.begin() + c.p0, pt_start.begin() + c.p1);
-    const uint64_t base = pt_start[c.p0];
-    for (uint64_t o = 0; o < nobs; ++o) {
-      uint32_t p = d->obs_pt[o];
-      if (p >= c.p0 && p < c.p1) pm[cur[p - c.p0]++ - base] = o;
-    }
-  }
-
-  // ---- tiles ----
-  // Normal tiles (<=256 observations, <=128 landmarks) get chunk ids 0..nn-1 in landmark order so that the
-  // persistent operator kernel can pair chunks (2s, 2s+1); landmarks with more than 256 observations get
-  // their chunks after those.
-  std::vector<TileDesc> tiles;
-  std::vector<uint32_t> pt_slot0(c.npl), pt_cnt(c.npl);
-  uint32_t chunk = 0;
-  {
-    uint32_t cur_pt0 = 0, cur_npt = 0, cur_obs = 0;
-    auto flush = [&]() {
-      if (cur_npt == 0) return;
-      tiles.push_back({cur_pt0, cur_npt, chunk, 1});
-      chunk += 1;
-      cur_npt = 0; cur_obs = 0;
-    };
-    for (uint32_t lp = 0; lp < c.npl; ++lp) {
-      uint64_t k64 = pt_start[c.p0 + lp + 1] - pt_start[c.p0 + lp];
-      uint32_t k = (uint32_t)k64;
-      pt_cnt[lp] = k;
-      if (k > (uint32_t)TILE) {
-        flush();
-        tiles.push_back({lp, 1, 0xFFFFFFFFu, (k + TILE - 1) / TILE});  // chunk0 assigned below
-        continue;
-      }
-      if (cur_npt > 0 && (cur_obs + k > (uint32_t)TILE || cur_npt >= (uint32_t)MAX_TILE_PTS)) flush();
-      if (cur_npt == 0) cur_pt0 = lp;
-      pt_slot0[lp] = chunk * TILE + cur_obs;
-      cur_npt++;
-      cur_obs += k;
-    }
-    flush();
-  }
-  c.nnormal_chunks = chunk;
-  std::vector<TileDesc> giant_tiles;
-  for (TileDesc& t : tiles)
-    if (t.nchunks > 1) {
-      t.chunk0 = chunk;
-      pt_slot0[t.pt0] = chunk * TILE;
-      chunk += t.nchunks;
-      giant_tiles.push_back(t);
-    }
-  c.ngiant = (uint32_t)giant_tiles.size();
-  c.ntiles = (uint32_t)tiles.size();
-  c.nchunks = chunk;
-  c.nslots = (size_t)chunk * TILE;
-  c.h_pt_cnt = pt_cnt;
-
-  // ---- slot arrays ----
-  std::vector<uint32_t> slot_cam(c.nslots, PAD_CAM);
-  std::vector<uint16_t> slot_lp(c.nslots, 0);
-  std::vector<double> slot_uv(c.nslots * 2, 0.0);
-  c.slot_obs.assign(c.nslots, UINT64_MAX);
-  {
-    uint64_t q = 0;
-    for (const TileDesc& t : tiles) {
-      for (uint32_t i = 0; i < t.npt; ++i) {
-        uint32_t lp = t.pt0 + i;
-        for (uint32_t k = 0; k < pt_cnt[lp]; ++k, ++q) {
-          size_t slot = (size_t)pt_slot0[lp] + k;
-          uint64_t o = pm[q];
-          slot_cam[slot] = d->obs_cam[o];
-          slot_lp[slot] = (uint16_t)i;
-          size_t ch = slot / TILE, lane = slot % TILE;
-          slot_uv[(ch * 2 + 0) * TILE + lane] = d->obs_uv[2 * o];
-          slot_uv[(ch * 2 + 1) * TILE + lane] = d->obs_uv[2 * o + 1];
-          c.slot_obs[slot] = o;
-        }
-      }
-    }
-  }
-
-  // ---- supertiles: camera-sorted segment structure over chunk pairs (2s, 2s+1) ----
-  c.nsuper = (c.nnormal_chunks + 1) / 2;
-  std::vector<SuperDesc> supers(c.nsuper);
-  std::vector<uint2> slot_meta(c.nslots, make_uint2(PAD_CAM, 0));
-  std::vector<uint32_t> pt_meta(c.npl, 0);
-  std::vector<uint32_t> seg_cam((size_t)c.nsuper * STILE, 0);
-  std::vector<uint16_t> seg_begin((size_t)c.nsuper * (STILE + 2), 0);
-  {
-    std::vector<const TileDesc*> by_chunk(c.nnormal_chunks, nullptr);
-    for (const TileDesc& t : tiles) if (t.nchunks == 1) by_chunk[t.chunk0] = &t;
-    std::vector<std::pair<uint32_t, uint32_t>> order;  // (camera, supertile-local slot)
-    for (uint32_t st = 0; st < c.nsuper; ++st) {
-      SuperDesc& d = supers[st];
-      const TileDesc* ta = by_chunk[2 * st];
-      const TileDesc* tb = 2 * st + 1 < c.nnormal_chunks ? by_chunk[2 * st + 1] : nullptr;
-      d = SuperDesc{ta->pt0, ta->npt, tb ? tb->pt0 : 0u, tb ? tb->npt : 0u, 0u, tb ? 1u : 0u, {0u, 0u}};
-      order.clear();
-      for (int h = 0; h < 2; ++h) {
-        const TileDesc* t = h == 0 ? ta : tb;
-        if (!t) continue;
-        const uint32_t spt0 = h == 0 ? 0 : ta->npt;
-        for (uint32_t i = 0; i < t->npt; ++i) {
-          const uint32_t lp = t->pt0 + i;
-          const uint32_t off = h * TILE + (pt_slot0[lp] - t->chunk0 * TILE);
-          pt_meta[lp] = off | (pt_cnt[lp] << 16);
-          for (uint32_t k = 0; k < pt_cnt[lp]; ++k) {
-            const size_t slot = (size_t)pt_slot0[lp] + k;
-            slot_meta[slot].x = slot_cam[slot];
-            slot_meta[slot].y = spt0 + i;  // position filled below
-            order.push_back({slot_cam[slot], off + k});
-          }
-        }
-      }
-      std::sort(order.begin(), order.end());
-      uint32_t nseg = 0;
-      for (size_t pos = 0; pos < order.size(); ++pos) {
-        if (pos == 0 || order[pos].first != order[pos - 1].first) {
-          seg_cam[(size_t)st * STILE + nseg] = order[pos].first;
-          seg_begin[(size_t)st * (STILE + 2) + nseg] = (uint16_t)pos;
-          ++nseg;
-        }
-        const uint32_t sl = order[pos].second;
-        const size_t slot = (size_t)(2 * st + sl / TILE) * TILE + sl % TILE;
-        slot_meta[slot].y |= (uint32_t)pos << 16;
-      }
-      seg_begin[(size_t)st * (STILE + 2) + nseg] = (uint16_t)order.size();
-      d.nseg = nseg;
-    }
-  }
-
-  // ---- per-chunk camera-sorted segment structure (ping-pong operator kernel) ----
-  const uint32_t nchunk_even = (c.nnormal_chunks + 1) & ~1u;
-  std::vector<ChunkDesc> chunk_desc(nchunk_even, ChunkDesc{0, 0, 0, 0});
-  std::vector<uint2> cslot_meta((size_t)nchunk_even * TILE, make_uint2(PAD_CAM, 0));
-  std::vector<uint32_t> cpt_meta(c.npl, 0);
-  std::vector<uint32_t> cseg_cam((size_t)nchunk_even * TILE, 0);
-  std::vector<uint16_t> cseg_begin((size_t)nchunk_even * CSEG_LD, 0);
-  {
-    std::vector<std::pair<uint32_t, uint32_t>> order;
-    for (const TileDesc& t : tiles) {
-      if (t.nchunks != 1) continue;
-      const uint32_t ch = t.chunk0;
-      order.clear();
-      for (uint32_t i = 0; i < t.npt; ++i) {
-        const uint32_t lp = t.pt0 + i;
-        const uint32_t off = pt_slot0[lp] - ch * TILE;
-        cpt_meta[lp] = off | (pt_cnt[lp] << 16);
-        for (uint32_t k = 0; k < pt_cnt[lp]; ++k) {
-          const size_t slot = (size_t)pt_slot0[lp] + k;
-          cslot_meta[slot].x = slot_cam[slot];
-          cslot_meta[slot].y = i;
-          order.push_back({slot_cam[slot], off + k});
-        }
-      }
-      std::sort(order.begin(), order.end());
-      uint32_t nseg = 0;
-      for (size_t pos = 0; pos < order.size(); ++pos) {
-        if (pos == 0 || order[pos].first != order[pos - 1].first) {
-          cseg_cam[(size_t)ch * TILE + nseg] = order[pos].first;
-          cseg_begin[(size_t)ch * CSEG_LD + nseg] = (uint16_t)pos;
-          ++nseg;
-        }
-        cslot_meta[(size_t)ch * TILE + order[pos].second].y |= ((uint32_t)pos << 8) | ((nseg - 1) << 16);
-      }
-      cseg_begin[(size_t)ch * CSEG_LD + nseg] = (uint16_t)order.size();
-      chunk_desc[ch] = ChunkDesc{t.pt0, t.npt, nseg, 0};
-    }
-  }
-
-  // ---- camera-major copy of the local observations + work items ----
-  std::vector<uint32_t> cam_start((size_t)c.ncam + 1, 0);
-  for (uint64_t q = 0; q < c.nobs_local; ++q) cam_start[d->obs_cam[pm[q]] + 1]++;
-  for (uint32_t k = 0; k < c.ncam; ++k) cam_start[k + 1] += cam_start[k];
-  std::vector<double> cm_uv(2 * (size_t)c.nobs_local);
-  std::vector<uint32_t> cm_lp(c.nobs_local);
-  {
-    std::vector<uint32_t> cur(cam_start.begin(), cam_start.end() - 1);
-    uint64_t q = 0;
-    for (uint32_t lp = 0; lp < c.npl; ++lp)
-      for (uint32_t k = 0; k < pt_cnt[lp]; ++k, ++q) {
-        uint64_t o = pm[q];
-        uint32_t pos = cur[d->obs_cam[o]]++;
-        cm_uv[pos] = d->obs_uv[2 * o];
-        cm_uv[(size_t)c.nobs_local + pos] = d->obs_uv[2 * o + 1];
-        cm_lp[pos] = lp;
-      }
-  }
-  std::vector<CamItem> items;
-  std::vector<uint32_t> cam_item_start((size_t)c.ncam + 1, 0);
-  for (uint32_t k = 0; k < c.ncam; ++k) {
-    cam_item_start[k] = (uint32_t)items.size();
-    for (uint32_t b = cam_start[k]; b < cam_start[k + 1]; b += CAM_CHUNK)
-      items.push_back({k, b, std::min<uint32_t>(b + CAM_CHUNK, cam_start[k + 1]), 0});
-  }
-  cam_item_start[c.ncam] = (uint32_t)items.size();
-  c.nitems = (uint32_t)items.size();
+  HostLayout L;
+  build_layout(d, c.nranks, c.rank, L);
+  c.p0 = L.p0; c.p1 = L.p1; c.npl = L.npl; c.nobs_local = L.nobs_local;
+  c.nnormal_chunks = L.nnormal_chunks; c.nchunks = L.nchunks; c.npairs = L.npairs;
+  c.ntiles = (uint32_t)L.tiles.size(); c.ngiant = (uint32_t)L.giant_tiles.size(); c.nitems = (uint32_t)L.items.size();
+  c.nslots = (size_t)L.nchunks * TILE;
+  c.slot_obs.swap(L.slot_obs);
+  c.h_pt_cnt = L.pt_cnt;
 
   // ---- fixed masks ----
   std::vector<uint8_t> pose_fixed(c.ncam, 0), pt_fixed(c.npl, 0);
@@ -280,27 +302,22 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
 
   // ---- to the device ----
   cudaStream_t s = c.stream;
-  APEX_CUDA_TRY(c, upload_vec(c.tiles, tiles, s));
-  APEX_CUDA_TRY(c, upload_vec(c.slot_cam, slot_cam, s));
-  APEX_CUDA_TRY(c, upload_vec(c.slot_lp, slot_lp, s));
-  APEX_CUDA_TRY(c, upload_vec(c.giant_tiles, giant_tiles, s));
-  APEX_CUDA_TRY(c, upload_vec(c.supers, supers, s));
-  APEX_CUDA_TRY(c, upload_vec(c.slot_meta, slot_meta, s));
-  APEX_CUDA_TRY(c, upload_vec(c.pt_meta, pt_meta, s));
-  APEX_CUDA_TRY(c, upload_vec(c.seg_cam, seg_cam, s));
-  APEX_CUDA_TRY(c, upload_vec(c.seg_begin, seg_begin, s));
-  APEX_CUDA_TRY(c, upload_vec(c.chunk_desc, chunk_desc, s));
-  APEX_CUDA_TRY(c, upload_vec(c.cslot_meta, cslot_meta, s));
-  APEX_CUDA_TRY(c, upload_vec(c.cpt_meta, cpt_meta, s));
-  APEX_CUDA_TRY(c, upload_vec(c.cseg_cam, cseg_cam, s));
-  APEX_CUDA_TRY(c, upload_vec(c.cseg_begin, cseg_begin, s));
-  APEX_CUDA_TRY(c, upload_vec(c.slot_uv, slot_uv, s));
-  APEX_CUDA_TRY(c, upload_vec(c.pt_slot0, pt_slot0, s));
-  APEX_CUDA_TRY(c, upload_vec(c.pt_cnt, pt_cnt, s));
-  APEX_CUDA_TRY(c, upload_vec(c.items, items, s));
-  APEX_CUDA_TRY(c, upload_vec(c.cam_item_start, cam_item_start, s));
-  APEX_CUDA_TRY(c, upload_vec(c.cm_uv, cm_uv, s));
-  APEX_CUDA_TRY(c, upload_vec(c.cm_lp, cm_lp, s));
+  APEX_CUDA_TRY(c, upload_vec(c.tiles, L.tiles, s));
+  APEX_CUDA_TRY(c, upload_vec(c.giant_tiles, L.giant_tiles, s));
+  APEX_CUDA_TRY(c, upload_vec(c.slot_cam, L.slot_cam, s));
+  APEX_CUDA_TRY(c, upload_vec(c.slot_lp, L.slot_lp, s));
+  APEX_CUDA_TRY(c, upload_vec(c.slot_uv, L.slot_uv, s));
+  APEX_CUDA_TRY(c, upload_vec(c.pt_slot0, L.pt_slot0, s));
+  APEX_CUDA_TRY(c, upload_vec(c.pt_cnt, L.pt_cnt, s));
+  APEX_CUDA_TRY(c, upload_vec(c.chunk_desc, L.chunk_desc, s));
+  APEX_CUDA_TRY(c, upload_vec(c.cslot_meta, L.cslot_meta, s));
+  APEX_CUDA_TRY(c, upload_vec(c.cpt_meta, L.cpt_meta, s));
+  APEX_CUDA_TRY(c, upload_vec(c.cseg_cam, L.cseg_cam, s));
+  APEX_CUDA_TRY(c, upload_vec(c.cseg_begin, L.cseg_begin, s));
+  APEX_CUDA_TRY(c, upload_vec(c.items, L.items, s));
+  APEX_CUDA_TRY(c, upload_vec(c.cam_item_start, L.cam_item_start, s));
+  APEX_CUDA_TRY(c, upload_vec(c.cm_uv, L.cm_uv, s));
+  APEX_CUDA_TRY(c, upload_vec(c.cm_lp, L.cm_lp, s));
   APEX_CUDA_TRY(c, upload_vec(c.pose_fixed, pose_fixed, s));
   APEX_CUDA_TRY(c, upload_vec(c.intr_fixed, intr_fixed, s));
   APEX_CUDA_TRY(c, upload_vec(c.pt_fixed, pt_fixed, s));

@@ -2,7 +2,8 @@
 // device-resident control.
 //
 // sm_100a equivalents of IterativeSchurSolver (src/linalg/sparse/implicit_schur.rs):
-//   apply_schur_operator_fast :163-251  -> hcc_apply_kernel + schur_tile_kernel<DC, MODE_MATVEC>
+//   apply_schur_operator_fast :163-251  -> schur_matvec_pingpong_kernel + schur_finalize_kernel (schur_tile_kernel<DC, MODE_MATVEC>
+//                                          for landmarks with more than 256 observations)
 //   reduced gradient          :863-880  -> schur_tile_kernel<DC, MODE_RHS>
 //   back-substitution         :923-932  -> schur_tile_kernel<DC, MODE_BACKSUB>
 //   apply_preconditioner      :409-443, solve_pcg_block :577-679 -> pcg_init_kernel / pcg_step_kernel
@@ -180,39 +181,6 @@ __global__ void __launch_bounds__(TILE) schur_tile_kernel(SchurArgs a) {
   }
 }
 
-// ----------------------------------------------------------------------------------------------------
-// Persistent Schur-operator kernel (the PCG hot loop). One 512-thread CTA per SM walks its share of the
-// "supertiles" (two 256-slot chunks = whole landmarks, <= 512 observations):
-//   * the Jacobian planes and slot metadata of the NEXT supertile are prefetched into registers while the
-//     current one is processed, so every SM keeps ~100 KB of HBM reads in flight;
-//   * landmark inverses / segment tables of the current supertile are staged with cp.async;
-//   * the camera-side scatter  y_c -= Jc^T (Jp w)  is first combined per camera inside the CTA, using the
-//     camera-sorted segment structure built at upload (one thread per (camera segment, dof), fixed order), and
-//     then added to a CTA-PRIVATE copy of y in shared memory (PRIVATE: ncam*dc doubles fit next to the
-//     staging buffers) - no global atomics at all, bitwise reproducible - or, when y does not fit, sent
-//     to global memory with one red.global.add.f64 per (segment, dof) instead of one per (observation, dof).
-// The private copies are summed in CTA order by schur_finalize_kernel, which also adds (H_cc + lambda I) x.
-// ----------------------------------------------------------------------------------------------------
-struct MvArgs {
-  const SuperDesc* supers;
-  const uint2* slot_meta;
-  const uint32_t* pt_meta;
-  const uint32_t* seg_cam;
-  const uint16_t* seg_begin;
-  const double* J;
-  const double* hinv;
-  const double* x;
-  double* y;       // global y (non-private mode)
-  double* ypart;   // [gridDim.x][n] (private mode)
-  uint32_t n;      // ncam * dc
-  uint32_t npl;
-  uint32_t nsuper;
-  uint32_t nnormal_chunks;
-  int check_done;
-  const DevState* st;
-  long long* timing;  // development probe: per-phase clock64 totals of CTA 0 (null in production)
-};
-
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
@@ -221,205 +189,17 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
-}
-
-constexpr int MV_THREADS = STILE;            // 512
 constexpr int MV_SMEM_MAX = 232448 - 512;    // 227 KB per CTA minus the static shared memory of the kernel
-constexpr int CS_LD = STILE + 1;             // padded plane stride of the contribution buffer
-
-template <int DC>
-struct MvRegs {
-  double j[2 * (DC + 3)];
-  uint32_t cam, sp;
-  SuperDesc d;
-};
-
-// Prefetch of supertile `st` into registers, issued in 4 stages that mv_process interleaves with its phases: a
-// warp that issues all 12 128-bit loads at once sits in the LSU queue (lg_throttle) instead of computing.
-// Every address is arithmetic in (st, tid): descriptor, slot metadata and the Jacobian planes are independent
-// loads (padding slots hold zeros, so they are loaded unconditionally).
-template <int DC, int STAGE>
-__device__ __forceinline__ void mv_prefetch_stage(const MvArgs& a, uint32_t st, int tid, MvRegs<DC>& r) {
-  constexpr int NP = 2 * (DC + 3), NPAIR = NP / 2;
-  constexpr int M0 = (NPAIR * STAGE) / 4, M1 = (NPAIR * (STAGE + 1)) / 4;
-  if (STAGE == 0) { r.cam = PAD_CAM; r.sp = 0; }
-  if (st >= a.nsuper) return;
-  const int half = tid >> 8, lane = tid & (TILE - 1);
-  const size_t chunk = 2 * (size_t)st + half;
-  const bool valid = chunk < a.nnormal_chunks;
-  if (valid) {
-    const double2* p = reinterpret_cast<const double2*>(a.J) + chunk * NPAIR * TILE + lane;
-#pragma unroll
-    for (int m = M0; m < M1; ++m) {
-      const double2 v = ld_stream2(p + (size_t)m * TILE);
-      r.j[2 * m] = v.x;
-      r.j[2 * m + 1] = v.y;
-    }
-  }
-  if (STAGE == 3) {
-    const uint4* dp = reinterpret_cast<const uint4*>(a.supers + st);
-    const uint4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
-    if (valid) {
-      const uint2 m = __ldg(a.slot_meta + chunk * TILE + lane);
-      r.cam = m.x;
-      r.sp = m.y;
-    }
-    r.d.ptA0 = d0.x; r.d.nptA = d0.y; r.d.ptB0 = d0.z; r.d.nptB = d0.w; r.d.nseg = d1.x; r.d.validB = d1.y;
-  }
-}
-
-template <int DC>
-__device__ __forceinline__ void mv_prefetch(const MvArgs& a, uint32_t st, int tid, MvRegs<DC>& r) {
-  mv_prefetch_stage<DC, 0>(a, st, tid, r);
-  mv_prefetch_stage<DC, 1>(a, st, tid, r);
-  mv_prefetch_stage<DC, 2>(a, st, tid, r);
-  mv_prefetch_stage<DC, 3>(a, st, tid, r);
-}
-
-template <int DC, bool PRIVATE>
-__device__ __forceinline__ void mv_process(const MvArgs& a, uint32_t st, uint32_t st_next, int tid, const MvRegs<DC>& r, MvRegs<DC>& rn, double* y_priv, double* cs, double* su,
-                                           double* sw, double* shinv, uint32_t* sptm, uint32_t* sseg_cam, uint16_t* sseg_begin, long long* tacc) {
-  const SuperDesc& d = r.d;
-  long long tk0 = 0;
-  if (tacc) tk0 = clock64();
-#define MV_TICK(i) if (tacc) { long long tk1 = clock64(); if (tid == 0) tacc[i] += tk1 - tk0; tk0 = tk1; }
-  const uint32_t npt = d.nptA + d.nptB;
-  // stage this supertile's landmark inverses and segment tables (arrive during phase 1)
-  if ((uint32_t)tid < npt) {
-    const uint32_t lp = (uint32_t)tid < d.nptA ? d.ptA0 + tid : d.ptB0 + (tid - d.nptA);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) cp_async8(shinv + k * TILE + tid, a.hinv + (size_t)k * a.npl + lp);
-    cp_async4(sptm + tid, a.pt_meta + lp);
-  }
-  if (tid < (STILE + 2) / 2) cp_async4(reinterpret_cast<uint32_t*>(sseg_begin) + tid, reinterpret_cast<const uint32_t*>(a.seg_begin + (size_t)st * (STILE + 2)) + tid);
-  if ((uint32_t)tid < d.nseg) cp_async4(sseg_cam + tid, a.seg_cam + (size_t)st * STILE + tid);
-  // phase 1: u_o = Jp^T (Jc x_c)
-  {
-    double u[3] = {0.0, 0.0, 0.0};
-    if (r.cam != PAD_CAM) obs_forward_padded<DC>(r.j, r.j + 2 * DC, a.x + (size_t)r.cam * ((DC + 1) & ~1), u);
-    su[tid] = u[0]; su[STILE + tid] = u[1]; su[2 * STILE + tid] = u[2];
-  }
-  MV_TICK(0)
-  mv_prefetch_stage<DC, 0>(a, st_next, tid, rn);
-  cp_async_commit_wait_all();
-  MV_TICK(1)
-  __syncthreads();
-  MV_TICK(2)
-  // phase 2: t_p = sum of u over the landmark's observations (fixed order), w_p = Hpp^-1 t_p
-  if ((uint32_t)tid < npt) {
-    const uint32_t m = sptm[tid], off = m & 0xFFFFu, cnt = m >> 16;
-    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-    {
-      double e0 = 0.0, e1 = 0.0, e2 = 0.0;  // two interleaved partial sums (fixed order => still deterministic)
-      uint32_t q = 0;
-      for (; q + 1 < cnt; q += 2) {
-        t0 += su[off + q]; t1 += su[STILE + off + q]; t2 += su[2 * STILE + off + q];
-        e0 += su[off + q + 1]; e1 += su[STILE + off + q + 1]; e2 += su[2 * STILE + off + q + 1];
-      }
-      if (q < cnt) { t0 += su[off + q]; t1 += su[STILE + off + q]; t2 += su[2 * STILE + off + q]; }
-      t0 += e0; t1 += e1; t2 += e2;
-    }
-    const double h00 = shinv[tid], h01 = shinv[TILE + tid], h02 = shinv[2 * TILE + tid];
-    const double h11 = shinv[3 * TILE + tid], h12 = shinv[4 * TILE + tid], h22 = shinv[5 * TILE + tid];
-    sw[tid] = h00 * t0 + h01 * t1 + h02 * t2;
-    sw[TILE + tid] = h01 * t0 + h11 * t1 + h12 * t2;
-    sw[2 * TILE + tid] = h02 * t0 + h12 * t1 + h22 * t2;
-  }
-  mv_prefetch_stage<DC, 1>(a, st_next, tid, rn);
-  MV_TICK(3)
-  __syncthreads();
-  MV_TICK(4)
-  // phase 3: c_o = -Jc^T (Jp w_p), written at the observation's camera-sorted position
-  if (r.cam != PAD_CAM) {
-    const uint32_t spt = r.sp & 0xFFFFu, pos = r.sp >> 16;
-    const double w0 = sw[spt], w1 = sw[TILE + spt], w2 = sw[2 * TILE + spt];
-    const double* jc = r.j;
-    const double* jp = r.j + 2 * DC;
-    const double b0 = fma(jp[0], w0, fma(jp[1], w1, jp[2] * w2));
-    const double b1 = fma(jp[3], w0, fma(jp[4], w1, jp[5] * w2));
-#pragma unroll
-    for (int k = 0; k < DC; ++k) cs[k * CS_LD + pos] = -fma(jc[k], b0, jc[DC + k] * b1);
-  }
-  mv_prefetch_stage<DC, 2>(a, st_next, tid, rn);
-  MV_TICK(5)
-  __syncthreads();
-  MV_TICK(6)
-  // phase 4: one thread per (camera segment, dof) sums its run and updates y
-  const uint32_t nwork = d.nseg * DC;
-  for (uint32_t idx0 = tid; idx0 < nwork; idx0 += 2 * MV_THREADS) {
-    // two independent work items per trip so their shared-memory latencies overlap
-    const uint32_t idx1 = idx0 + MV_THREADS;
-    const bool two = idx1 < nwork;
-    const uint32_t s0 = idx0 / DC, k0 = idx0 - s0 * DC;
-    const uint32_t s1 = two ? idx1 / DC : s0, k1 = two ? idx1 - s1 * DC : k0;
-    const uint32_t b0 = sseg_begin[s0], e0 = sseg_begin[s0 + 1];
-    const uint32_t b1 = sseg_begin[s1], e1 = two ? sseg_begin[s1 + 1] : b1;
-    const uint32_t row0 = sseg_cam[s0] * DC + k0, row1 = sseg_cam[s1] * DC + k1;
-    const double* c0 = cs + k0 * CS_LD;
-    const double* c1 = cs + k1 * CS_LD;
-    double v0 = 0.0, v1 = 0.0;
-    const uint32_t len0 = e0 - b0, len1 = e1 - b1, lmin = len0 < len1 ? len0 : len1;
-    uint32_t q = 0;
-    for (; q < lmin; ++q) { v0 += c0[b0 + q]; v1 += c1[b1 + q]; }
-    for (uint32_t q0 = q; q0 < len0; ++q0) v0 += c0[b0 + q0];
-    for (uint32_t q1 = q; q1 < len1; ++q1) v1 += c1[b1 + q1];
-    if (PRIVATE) {
-      y_priv[row0] += v0;
-      if (two) y_priv[row1] += v1;
-    } else {
-      red_add(a.y + row0, v0);
-      if (two) red_add(a.y + row1, v1);
-    }
-  }
-  mv_prefetch_stage<DC, 3>(a, st_next, tid, rn);
-  MV_TICK(7)
-  __syncthreads();  // the staging buffers are rewritten by the next supertile
-  MV_TICK(8)
-#undef MV_TICK
-}
-
-template <int DC, bool PRIVATE>
-__global__ void __launch_bounds__(MV_THREADS, 1) schur_matvec_persist_kernel(MvArgs a) {
-  extern __shared__ double mv_smem[];
-  if (a.check_done && a.st->pcg_done) return;
-  const int tid = threadIdx.x;
-  const uint32_t ny = PRIVATE ? ((a.n + 1) & ~1u) : 0;
-  double* y_priv = mv_smem;
-  double* cs = y_priv + ny;
-  double* su = cs + DC * CS_LD + 1;  // keep 16-byte alignment irrelevant: all accesses are 8-byte
-  double* sw = su + 3 * STILE;
-  double* shinv = sw + 3 * TILE;
-  uint32_t* sptm = reinterpret_cast<uint32_t*>(shinv + 6 * TILE);
-  uint32_t* sseg_cam = sptm + TILE;
-  uint16_t* sseg_begin = reinterpret_cast<uint16_t*>(sseg_cam + STILE);
-  if (PRIVATE) {
-    for (uint32_t i = tid; i < a.n; i += MV_THREADS) y_priv[i] = 0.0;
-  }
-  __syncthreads();
-  __shared__ long long tacc_s[12];
-  long long* tacc = (a.timing && blockIdx.x == 0) ? tacc_s : nullptr;
-  if (tacc && tid < 12) tacc_s[tid] = 0;
-  MvRegs<DC> ra, rb;
-  uint32_t st = blockIdx.x;
-  mv_prefetch<DC>(a, st, tid, ra);
-  while (st < a.nsuper) {
-    mv_process<DC, PRIVATE>(a, st, st + gridDim.x, tid, ra, rb, y_priv, cs, su, sw, shinv, sptm, sseg_cam, sseg_begin, tacc);
-    st += gridDim.x;
-    if (st >= a.nsuper) break;
-    mv_process<DC, PRIVATE>(a, st, st + gridDim.x, tid, rb, ra, y_priv, cs, su, sw, shinv, sptm, sseg_cam, sseg_begin, tacc);
-    st += gridDim.x;
-  }
-  if (tacc) { __syncthreads(); if (tid < 12) a.timing[tid] = tacc_s[tid]; }
-  if (PRIVATE) {
-    double* out = a.ypart + (size_t)blockIdx.x * a.n;
-    for (uint32_t i = tid; i < a.n; i += MV_THREADS) out[i] = y_priv[i];
-  }
-}
 
 // ----------------------------------------------------------------------------------------------------
-// Ping-pong variant of the persistent operator kernel. The 512-thread CTA is split into two 256-thread groups
+// Persistent Schur-operator kernel (the PCG hot loop), one 512-thread CTA per SM. The Jacobian planes of the NEXT
+// chunk are prefetched into registers in 4 stages interleaved with the compute phases; the camera-side scatter
+// y_c -= Jc^T (Jp w) is combined per camera inside the CTA (camera-sorted segment structure built at upload, one
+// thread per (segment, dof), fixed order) and added to a CTA-PRIVATE copy of y in shared memory (PRIVATE: ncam*dc
+// doubles fit next to the staging buffers; no global atomics, bitwise reproducible) or, when y does not fit,
+// sent to global memory with one red.global.add.f64 per (segment, dof). The private copies are summed in CTA
+// order by schur_finalize_kernel, which also adds (H_cc + lambda I) x.
+// The 512-thread CTA is split into two 256-thread groups
 // that each walk their own chunks (256 slots = whole landmarks) with named barriers (bar.sync 1/2), half a
 // period out of phase, so one group's barrier / latency stalls are filled by the other group's work. Both groups
 // add into the same CTA-private y; their phase 4 is serialised by a two-barrier turnstile (bar.arrive/bar.sync
@@ -667,11 +447,6 @@ __global__ void pad_x_kernel(const double* __restrict__ x, double* __restrict__ 
   xpad[i] = k < (uint32_t)dc ? x[(size_t)cam * dc + k] : 0.0;
 }
 
-static size_t mv_smem_bytes(int dc, uint32_t n, bool priv) {
-  size_t dbl = (priv ? ((n + 1) & ~1u) : 0) + (size_t)dc * CS_LD + 1 + 3 * STILE + 3 * TILE + 6 * TILE;
-  return dbl * 8 + (size_t)TILE * 4 + (size_t)STILE * 4 + (size_t)(STILE + 2) * 2 + 16;
-}
-
 // y[i] = [(H_cc + lambda I) x]_i (rank 0) + sum over the CTA-private partial results, in CTA order
 __global__ void schur_finalize_kernel(const double* __restrict__ hcc, const double* __restrict__ x, const double* __restrict__ ypart, uint32_t nblk,
                                       double* __restrict__ y, const DevState* st, uint32_t n, int dc, int add_hcc, int check_done) {
@@ -745,51 +520,120 @@ __global__ void __launch_bounds__(1024) pcg_init_kernel(const double* __restrict
     st->pcg_iters = 0;
     st->pcg_max = max_it;
     st->pcg_done = max_it <= 0 ? 1 : 0;
+    st->pcg_alpha = 0.0; st->pcg_beta = 0.0; st->ticket_a = 0; st->ticket_b = 0;
   }
 }
 
-// one PCG iteration after ap = S p is complete (implicit_schur.rs:604-676), single CTA, deterministic
-__global__ void __launch_bounds__(1024) pcg_step_kernel(const double* __restrict__ ap, const double* __restrict__ pinv, double* x, double* r,
-                                                        double* z, double* p, DevState* st, uint32_t n, int dc, int K) {
-  __shared__ double sh[1024];
+// ---- multi-CTA PCG iteration (solve_pcg_block, implicit_schur.rs:604-676) --------------------------------
+// Three short kernels per iteration instead of one 1024-thread CTA: every grid-wide dot product is a per-CTA
+// partial + "last CTA done" pass that sums the partials in index order (deterministic), and alpha / beta / the
+// break tests stay in DevState.
+constexpr int PCG_THREADS = 256;
+constexpr int PCG_CAMS = 16;  // cameras per CTA of the update kernel
+
+// p = z + beta p (beta = 0 right after pcg_init) and the padded copy the operator kernel gathers from
+__global__ void __launch_bounds__(PCG_THREADS) pcg_dir_kernel(const double* __restrict__ z, double* __restrict__ p, double* __restrict__ xpad,
+                                                              const DevState* st, uint32_t ncam, int dc, int xs) {
   if (st->pcg_done) return;
-  const int iters = st->pcg_iters + 1;
-  const double rz_old = st->rz_old, tol = st->pcg_tol;
-  const int max_it = st->pcg_max;
+  const uint32_t i = blockIdx.x * PCG_THREADS + threadIdx.x;
+  if (i >= ncam * (uint32_t)xs) return;
+  const uint32_t cam = i / xs, k = i % xs;
   double v = 0.0;
-  for (uint32_t i = threadIdx.x; i < n; i += 1024) v = fma(p[i], ap[i], v);
-  const double p_ap = block_reduce_sum(v, sh);
-  if (fabs(p_ap) < 1e-20) {
-    if (threadIdx.x == 0) { st->pcg_iters = iters; st->pcg_done = 1; }
-    return;
+  if (k < (uint32_t)dc) {
+    const size_t row = (size_t)cam * dc + k;
+    const double beta = st->pcg_beta;
+    v = beta == 0.0 ? z[row] : z[row] + beta * p[row];
+    p[row] = v;
   }
-  const double alpha = rz_old / p_ap;
-  v = 0.0;
-  for (uint32_t i = threadIdx.x; i < n; i += 1024) {
-    x[i] += alpha * p[i];
-    const double rv = r[i] - alpha * ap[i];
-    r[i] = rv;
-    v = fma(rv, rv, v);
-  }
-  const double r_norm = sqrt(block_reduce_sum(v, sh));  // also orders the r writes before the z reads
-  if (r_norm < tol) {
-    if (threadIdx.x == 0) { st->pcg_iters = iters; st->pcg_done = 1; st->r_norm = r_norm; }
-    return;
-  }
-  v = 0.0;
-  for (uint32_t i = threadIdx.x; i < n; i += 1024) { const double zv = precond_row(pinv, r, i, dc, K); z[i] = zv; v = fma(r[i], zv, v); }
-  const double rz_new = block_reduce_sum(v, sh);
-  if (fabs(rz_old) < 1e-30) {
-    if (threadIdx.x == 0) { st->pcg_iters = iters; st->pcg_done = 1; st->r_norm = r_norm; }
-    return;
-  }
-  const double beta = rz_new / rz_old;
-  for (uint32_t i = threadIdx.x; i < n; i += 1024) p[i] = z[i] + beta * p[i];
+  xpad[i] = v;
+}
+
+// pAp = p . (S p); last CTA: break test |pAp| < 1e-20, alpha = rz_old / pAp
+__global__ void __launch_bounds__(PCG_THREADS) pcg_pap_kernel(const double* __restrict__ p, const double* __restrict__ ap, double* part,
+                                                              DevState* st, uint32_t n) {
+  __shared__ double sh[PCG_THREADS];
+  __shared__ bool is_last;
+  if (st->pcg_done) return;
+  const uint32_t i = blockIdx.x * PCG_THREADS + threadIdx.x;
+  double v = i < n ? p[i] * ap[i] : 0.0;
+  v = block_reduce_sum(v, sh);
   if (threadIdx.x == 0) {
-    st->rz_old = rz_new;
-    st->r_norm = r_norm;
+    part[blockIdx.x] = v;
+    __threadfence();
+    is_last = atomicAdd(&st->ticket_a, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double s = 0.0;
+  for (uint32_t b = threadIdx.x; b < gridDim.x; b += PCG_THREADS) s += __ldcg(part + b);
+  s = block_reduce_sum(s, sh);
+  if (threadIdx.x == 0) {
+    st->ticket_a = 0;
+    if (fabs(s) < 1e-20) { st->pcg_iters = st->pcg_iters + 1; st->pcg_done = 1; }
+    else st->pcg_alpha = st->rz_old / s;
+  }
+}
+
+// x += alpha p ; r -= alpha Ap ; z = M^-1 r ; last CTA: ||r|| < tol, |rz_old| < 1e-30, beta, iteration count
+__global__ void __launch_bounds__(PCG_THREADS) pcg_update_kernel(const double* __restrict__ ap, const double* __restrict__ pinv,
+                                                                 const double* __restrict__ p, double* x, double* r, double* z, double* part,
+                                                                 DevState* st, uint32_t ncam, int dc, int K) {
+  __shared__ double sh[PCG_THREADS];
+  __shared__ double rs[PCG_CAMS * MAX_DC];
+  __shared__ bool is_last;
+  if (st->pcg_done) return;
+  const double alpha = st->pcg_alpha;
+  const uint32_t cam0 = blockIdx.x * PCG_CAMS;
+  const uint32_t nrow = min((uint32_t)PCG_CAMS, ncam - cam0) * dc;
+  const size_t row0 = (size_t)cam0 * dc;
+  double rr = 0.0, rz = 0.0;
+  if (threadIdx.x < nrow) {
+    const size_t row = row0 + threadIdx.x;
+    x[row] += alpha * p[row];
+    const double rv = r[row] - alpha * ap[row];
+    r[row] = rv;
+    rs[threadIdx.x] = rv;
+    rr = rv * rv;
+  }
+  __syncthreads();
+  if (threadIdx.x < nrow) {
+    const uint32_t lc = threadIdx.x / dc, a = threadIdx.x % dc;
+    const double* P = pinv + (size_t)(cam0 + lc) * (36 + K * K);
+    const double* rc = rs + lc * dc;
+    double s = 0.0;
+    if (a < 6) { for (int b = 0; b < 6; ++b) s += P[a * 6 + b] * rc[b]; }
+    else { const double* Q = P + 36 + (a - 6) * K; for (int b = 0; b < K; ++b) s += Q[b] * rc[6 + b]; }
+    z[row0 + threadIdx.x] = s;
+    rz = rs[threadIdx.x] * s;
+  }
+  rr = block_reduce_sum(rr, sh);
+  rz = block_reduce_sum(rz, sh);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = rr;
+    part[gridDim.x + blockIdx.x] = rz;
+    __threadfence();
+    is_last = atomicAdd(&st->ticket_b, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double s0 = 0.0, s1 = 0.0;
+  for (uint32_t b = threadIdx.x; b < gridDim.x; b += PCG_THREADS) { s0 += __ldcg(part + b); s1 += __ldcg(part + gridDim.x + b); }
+  s0 = block_reduce_sum(s0, sh);
+  s1 = block_reduce_sum(s1, sh);
+  if (threadIdx.x == 0) {
+    st->ticket_b = 0;
+    const int iters = st->pcg_iters + 1;
+    const double r_norm = sqrt(s0), rz_old = st->rz_old;
     st->pcg_iters = iters;
-    if (iters >= max_it) st->pcg_done = 1;
+    st->r_norm = r_norm;
+    if (r_norm < st->pcg_tol || fabs(rz_old) < 1e-30) st->pcg_done = 1;
+    else {
+      st->pcg_beta = s1 / rz_old;
+      st->rz_old = s1;
+      if (iters >= st->pcg_max) st->pcg_done = 1;
+    }
   }
 }
 
@@ -846,19 +690,6 @@ apex_status launch_hcc_apply(Ctx& c, const double* x, double* y, int check_done)
   return APEX_OK;
 }
 
-template <int DC>
-static apex_status launch_persist_dc(Ctx& c, const MvArgs& a, bool priv, unsigned grid, size_t smem) {
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[priv ? 1 : 0]) {
-    if (priv) APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_matvec_persist_kernel<DC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MV_SMEM_MAX));
-    else APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_matvec_persist_kernel<DC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MV_SMEM_MAX));
-    attr_done[priv ? 1 : 0] = true;
-  }
-  if (priv) schur_matvec_persist_kernel<DC, true><<<grid, MV_THREADS, smem, c.stream>>>(a);
-  else schur_matvec_persist_kernel<DC, false><<<grid, MV_THREADS, smem, c.stream>>>(a);
-  return APEX_OK;
-}
-
 // the tile kernel restricted to the landmarks with more than 256 observations
 static apex_status launch_giant_tiles(Ctx& c, const double* x, double* y, int check_done) {
   if (c.ngiant == 0) return APEX_OK;
@@ -880,90 +711,58 @@ static apex_status launch_giant_tiles(Ctx& c, const double* x, double* y, int ch
 }
 
 // this rank's part of y = S x, before the all-reduce: persistent kernel (+ finalize) + long-track tiles
-apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_done) {
+apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_done, bool xpad_ready) {
   const uint32_t n = c.ncam * c.dc;
-  const char* force = getenv("APEX_MATVEC_IMPL");  // development switch: "tile" = first-generation kernel
+  const char* force = getenv("APEX_MATVEC_IMPL");  // development switch: "tile" = first-generation kernel, "red" = no private y
   if (force && force[0] == 't') {
     APEX_TRY(launch_hcc_apply(c, x, y, check_done));
     return launch_schur_tiles(c, MODE_MATVEC, x, y, check_done);
   }
-  const bool use_v2 = force && force[0] == 'p' && force[1] == 'e';  // "persist": lock-step supertile kernel (second generation)
   const int xs = (c.dc + 1) & ~1;
-  pad_x_kernel<<<(c.ncam * xs + 255) / 256, 256, 0, c.stream>>>(x, c.xpad.p, c.ncam, c.dc, xs, c.state.p, check_done);
-  c.launches++;
-  bool priv;
-  unsigned grid;
-  const bool want_timing = getenv("APEX_MV_TIMING") != nullptr;
-  static long long* d_timing = nullptr;
-  if (use_v2) {
-    priv = mv_smem_bytes(c.dc, n, true) <= (size_t)MV_SMEM_MAX && !(force && force[0] == 'r');
-    grid = (unsigned)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)c.num_sms, c.nsuper));
-    MvArgs a{c.supers.p, c.slot_meta.p, c.pt_meta.p, c.seg_cam.p, c.seg_begin.p, c.J.p, c.hinv.p, c.xpad.p, y, c.ypart.p, n, c.npl, c.nsuper, c.nnormal_chunks, check_done, c.state.p, nullptr};
-    if (want_timing) { if (!d_timing) cudaMalloc(&d_timing, 12 * sizeof(long long)); a.timing = d_timing; }
-    const size_t smem = mv_smem_bytes(c.dc, n, priv);
-    if (!priv) APEX_TRY(launch_hcc_apply(c, x, y, check_done));  // y starts as (H_cc + lambda I) x; the kernel reduces into it
-    cudaEvent_t* evp = (c.prof && c.nsuper) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
-    if (evp) cudaEventRecord(evp[0], c.stream);
-    if (c.nsuper) {
-      switch (c.dc) {
-        case 6: APEX_TRY(launch_persist_dc<6>(c, a, priv, grid, smem)); break;
-        case 9: APEX_TRY(launch_persist_dc<9>(c, a, priv, grid, smem)); break;
-        case 10: APEX_TRY(launch_persist_dc<10>(c, a, priv, grid, smem)); break;
-        case 12: APEX_TRY(launch_persist_dc<12>(c, a, priv, grid, smem)); break;
-        case 14: APEX_TRY(launch_persist_dc<14>(c, a, priv, grid, smem)); break;
-        default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
-      }
-      c.launches++;
-    }
-    if (evp) cudaEventRecord(evp[1], c.stream);
-  } else {
-    const uint32_t npairs = c.nsuper;  // chunk pairs (2s, 2s+1)
-    size_t need = 0;
-    switch (c.dc) {
-      case 6: need = pp_smem_bytes<6>(n, true); break;
-      case 9: need = pp_smem_bytes<9>(n, true); break;
-      case 10: need = pp_smem_bytes<10>(n, true); break;
-      case 12: need = pp_smem_bytes<12>(n, true); break;
-      case 14: need = pp_smem_bytes<14>(n, true); break;
-      default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
-    }
-    priv = need <= (size_t)MV_SMEM_MAX && !(force && force[0] == 'r');
-    grid = (unsigned)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)c.num_sms, npairs));
-    PpArgs a{c.chunk_desc.p, c.cslot_meta.p, c.cpt_meta.p, c.cseg_cam.p, c.cseg_begin.p, c.J.p, c.hinv.p, c.xpad.p, y, c.ypart.p,
-             n, c.npl, npairs, c.nnormal_chunks, check_done, c.state.p};
-    if (!priv) APEX_TRY(launch_hcc_apply(c, x, y, check_done));
-    cudaEvent_t* evp = (c.prof && npairs) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
-    if (evp) cudaEventRecord(evp[0], c.stream);
-    if (npairs) {
-      switch (c.dc) {
-        case 6: APEX_TRY(launch_pingpong_dc<6>(c, a, priv, grid)); break;
-        case 9: APEX_TRY(launch_pingpong_dc<9>(c, a, priv, grid)); break;
-        case 10: APEX_TRY(launch_pingpong_dc<10>(c, a, priv, grid)); break;
-        case 12: APEX_TRY(launch_pingpong_dc<12>(c, a, priv, grid)); break;
-        default: APEX_TRY(launch_pingpong_dc<14>(c, a, priv, grid)); break;
-      }
-      c.launches++;
-    }
-    if (evp) cudaEventRecord(evp[1], c.stream);
+  if (!xpad_ready) {
+    pad_x_kernel<<<(c.ncam * xs + 255) / 256, 256, 0, c.stream>>>(x, c.xpad.p, c.ncam, c.dc, xs, c.state.p, check_done);
+    c.launches++;
   }
+  const uint32_t npairs = c.npairs;  // chunk pairs (2s, 2s+1)
+  size_t need = 0;
+  switch (c.dc) {
+    case 6: need = pp_smem_bytes<6>(n, true); break;
+    case 9: need = pp_smem_bytes<9>(n, true); break;
+    case 10: need = pp_smem_bytes<10>(n, true); break;
+    case 12: need = pp_smem_bytes<12>(n, true); break;
+    case 14: need = pp_smem_bytes<14>(n, true); break;
+    default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
+  }
+  const bool priv = need <= (size_t)MV_SMEM_MAX && !(force && force[0] == 'r');
+  const unsigned grid = (unsigned)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)c.num_sms, npairs));
+  PpArgs a{c.chunk_desc.p, c.cslot_meta.p, c.cpt_meta.p, c.cseg_cam.p, c.cseg_begin.p, c.J.p, c.hinv.p, c.xpad.p, y, c.ypart.p,
+           n, c.npl, npairs, c.nnormal_chunks, check_done, c.state.p};
+  if (!priv) APEX_TRY(launch_hcc_apply(c, x, y, check_done));  // y starts as (H_cc + lambda I) x; the kernel reduces into it
+  cudaEvent_t* evp = (c.prof && npairs) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
+  if (evp) cudaEventRecord(evp[0], c.stream);
+  if (npairs) {
+    switch (c.dc) {
+      case 6: APEX_TRY(launch_pingpong_dc<6>(c, a, priv, grid)); break;
+      case 9: APEX_TRY(launch_pingpong_dc<9>(c, a, priv, grid)); break;
+      case 10: APEX_TRY(launch_pingpong_dc<10>(c, a, priv, grid)); break;
+      case 12: APEX_TRY(launch_pingpong_dc<12>(c, a, priv, grid)); break;
+      default: APEX_TRY(launch_pingpong_dc<14>(c, a, priv, grid)); break;
+    }
+    c.launches++;
+  }
+  if (evp) cudaEventRecord(evp[1], c.stream);
   if (priv) {
-    schur_finalize_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(c.hcc.p, x, c.ypart.p, c.nsuper ? grid : 0u, y, c.state.p, n, c.dc,
+    schur_finalize_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(c.hcc.p, x, c.ypart.p, npairs ? grid : 0u, y, c.state.p, n, c.dc,
                                                                  c.rank == 0 ? 1 : 0, check_done);
     c.launches++;
   }
   APEX_CUDA_TRY(c, cudaGetLastError());
-  if (want_timing) {
-    long long h[12];
-    cudaStreamSynchronize(c.stream);
-    cudaMemcpy(h, d_timing, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[mv timing, CTA 0, cycles] p1 %lld cpwait %lld sync %lld | p2 %lld sync %lld | p3 %lld sync %lld | p4 %lld sync %lld | prefetch-issue %lld\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9]);
-  }
   return launch_giant_tiles(c, x, y, check_done);
 }
 
 // full operator y = S x (all ranks end with the same y)
-apex_status schur_operator(Ctx& c, const double* x, double* y, int check_done) {
-  APEX_TRY(schur_operator_local(c, x, y, check_done));
+apex_status schur_operator(Ctx& c, const double* x, double* y, int check_done, bool xpad_ready) {
+  APEX_TRY(schur_operator_local(c, x, y, check_done, xpad_ready));
   APEX_TRY(allreduce_sum(c, y, (size_t)c.ncam * c.dc));
   return APEX_OK;
 }
@@ -1000,9 +799,14 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
   while (enq < cg_max_it) {
     const int nb = std::min(BATCH, cg_max_it - enq);
     for (int i = 0; i < nb; ++i) {
-      APEX_TRY(schur_operator(c, c.vp.p, c.vy.p, 1));
-      pcg_step_kernel<<<1, 1024, 0, s>>>(c.vy.p, c.pinv.p, c.step_cam.p, c.vr.p, c.vz.p, c.vp.p, c.state.p, n, c.dc, c.K);
+      const int xs = (c.dc + 1) & ~1;
+      const unsigned gp = (n + PCG_THREADS - 1) / PCG_THREADS, gu = (c.ncam + PCG_CAMS - 1) / PCG_CAMS;
+      pcg_dir_kernel<<<(c.ncam * xs + PCG_THREADS - 1) / PCG_THREADS, PCG_THREADS, 0, s>>>(c.vz.p, c.vp.p, c.xpad.p, c.state.p, c.ncam, c.dc, xs);
       c.launches++;
+      APEX_TRY(schur_operator(c, c.vp.p, c.vy.p, 1, true));
+      pcg_pap_kernel<<<gp, PCG_THREADS, 0, s>>>(c.vp.p, c.vy.p, c.red_scratch.p, c.state.p, n);
+      pcg_update_kernel<<<gu, PCG_THREADS, 0, s>>>(c.vy.p, c.pinv.p, c.vp.p, c.step_cam.p, c.vr.p, c.vz.p, c.red_scratch.p, c.state.p, c.ncam, c.dc, c.K);
+      c.launches += 2;
     }
     APEX_CUDA_TRY(c, cudaGetLastError());
     enq += nb;

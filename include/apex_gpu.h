@@ -342,6 +342,23 @@ apex_status apex_profile_read(apex_ctx* ctx, apex_profile* out);
 apex_status apex_shard_range(uint32_t npts, uint64_t nobs, const uint32_t* obs_pt, int32_t nranks, int32_t rank,
                              uint32_t* p0, uint32_t* p1, uint64_t* nobs_local);
 
+/* Host-only: build the static observation layout apex_problem_upload would build for (nranks, rank) - landmark
+ * shard, 256-slot point-major chunks, per-chunk camera segments, camera-major work items - check its invariants
+ * and report its size. Needs no device. */
+typedef struct apex_layout_stats {
+  uint32_t p0, p1;                 /* landmark range of the rank                                  */
+  uint64_t nobs_local;
+  uint32_t ntiles, nlong_tiles;    /* tiles; tiles holding one landmark with more than 256 observations */
+  uint32_t nchunks, nnormal_chunks;
+  uint32_t ncam_items, max_segments_per_chunk;
+  uint64_t nsegments;              /* distinct (chunk, camera) pairs                              */
+  uint64_t slots_used;             /* = nobs_local when consistent                                 */
+  int32_t consistent;              /* 1 when every structural invariant holds                      */
+  int32_t reserved;
+  double build_ms;
+} apex_layout_stats;
+apex_status apex_layout_stats_compute(const apex_problem_desc* desc, int32_t nranks, int32_t rank, apex_layout_stats* out);
+
 #ifdef __cplusplus
 }
 #endif

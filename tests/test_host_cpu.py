@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from apex_solver_b200 import _ffi as F, synth
-from apex_solver_b200.context import BAProblem, GpuContext, shard_range
+from apex_solver_b200.context import BAProblem, GpuContext, layout_stats, shard_range
 from oracle_backend import OracleContext, oracle_lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -33,15 +33,15 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_the_header(tmp_path):
     """ctypes mirrors vs the C compiler's view of include/apex_gpu.h (sizes and a few offsets)."""
     src = tmp_path / "sizes.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "apex_gpu.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "apex_gpu.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(apex_ctx_desc),sizeof(apex_problem_desc),sizeof(apex_lm_config),sizeof(apex_lm_result),sizeof(apex_iter_trace),"
-                   "sizeof(apex_dims),sizeof(apex_profile),offsetof(apex_problem_desc,loss_params),offsetof(apex_lm_config,cg_tolerance),"
+                   "sizeof(apex_dims),sizeof(apex_profile),sizeof(apex_layout_stats),offsetof(apex_problem_desc,loss_params),offsetof(apex_lm_config,cg_tolerance),"
                    "offsetof(apex_lm_result,linear_iterations));return 0;}\n")
     exe = tmp_path / "sizes"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
     want = [C.sizeof(F.CtxDesc), C.sizeof(F.ProblemDesc), C.sizeof(F.LmConfig), C.sizeof(F.LmResult), C.sizeof(F.IterTrace), C.sizeof(F.Dims),
-            C.sizeof(F.Profile), F.ProblemDesc.loss_params.offset, F.LmConfig.cg_tolerance.offset, F.LmResult.linear_iterations.offset]
+            C.sizeof(F.Profile), C.sizeof(F.LayoutStats), F.ProblemDesc.loss_params.offset, F.LmConfig.cg_tolerance.offset, F.LmResult.linear_iterations.offset]
     assert got == want
 
 
@@ -82,6 +82,34 @@ def test_shard_range_covers_and_balances():
             assert abs(n - prob.nobs / nranks) <= cnt.max() + 1, "balanced by observations up to one track"
     with pytest.raises(F.ApexError):
         shard_range(prob.obs_pt, prob.npts, 2, 2)
+
+
+def test_layout_invariants_incl_long_tracks_and_unobserved_landmarks():
+    """The static structure apex_problem_upload builds (host-only entry point): every observation in exactly one slot,
+    landmarks never straddle a 256-slot chunk, a landmark with more than 256 observations gets its own chunks, and the
+    per-chunk camera segments are consistent - for every rank of a sharded problem."""
+    prob = synth.make_problem(300, 3000, 6.0, seed=11)
+    keep = (prob.obs_pt != 3) & (prob.obs_pt >= 2)        # landmarks 0,1 unobserved; landmark 3 rebuilt below
+    extra = np.arange(prob.ncam, dtype=np.uint32)          # landmark 3 seen by all 300 cameras (> one chunk)
+    p2 = BAProblem(camera_model=prob.camera_model, opt_flags=prob.opt_flags, pose=prob.pose, intr=prob.intr, pt=prob.pt,
+                   obs_cam=np.concatenate([prob.obs_cam[keep], extra]), obs_pt=np.concatenate([prob.obs_pt[keep], np.full(prob.ncam, 3, np.uint32)]),
+                   obs_uv=np.concatenate([prob.obs_uv[keep], np.zeros((prob.ncam, 2))]))
+    s = layout_stats(p2)
+    assert s.consistent == 1 and s.slots_used == s.nobs_local == p2.nobs
+    assert s.nlong_tiles == 1 and s.nchunks == s.nnormal_chunks + 2      # 300 observations -> 2 chunks
+    assert s.nobs_local / (s.nchunks * 256) > 0.9, "chunk fill"
+    total = 0
+    for r in range(4):
+        sr = layout_stats(p2, 4, r)
+        assert sr.consistent == 1
+        total += sr.nobs_local
+        assert (sr.p0, sr.p1, sr.nobs_local) == shard_range(p2.obs_pt, p2.npts, 4, r)
+    assert total == p2.nobs
+    bad = BAProblem(camera_model=prob.camera_model, opt_flags=prob.opt_flags, pose=prob.pose, intr=prob.intr, pt=prob.pt,
+                    obs_cam=np.array([999], np.uint32), obs_pt=np.array([0], np.uint32), obs_uv=np.zeros((1, 2)))
+    with pytest.raises(F.ApexError) as e:
+        layout_stats(bad)
+    assert e.value.status == F.ERR_INVALID_INPUT
 
 
 def test_generator_is_deterministic_and_bal_shaped():
