@@ -385,18 +385,31 @@ __global__ void __launch_bounds__(2 * TILE, 1) schur_matvec_pingpong_kernel(PpAr
     }                                                                                                                    \
     pp_prefetch_stage<DC, 3>(a, chunk_next, valid_next, gt, RN);                                                         \
     pp_group_bar(g);                                                                                                     \
-    /* P4: one thread per (camera segment, dof); the two groups take turns on the private y */                          \
+    /* P4: one thread per camera segment sums its run for all dofs; the two groups take turns on the private y */                          \
     if (PRIVATE) { if (g == 0) { if (it > 0) pp_turn_wait(4); } else pp_turn_wait(3); }                                  \
     {                                                                                                                    \
-      const uint32_t nwork = R.nseg * DC;                                                                                \
+      constexpr int KG = 3;                 /* dofs per work item: 3 independent accumulators per thread */              \
+      constexpr int NG = (DC + KG - 1) / KG;                                                                             \
+      const uint32_t nwork = R.nseg * NG;                                                                                \
       for (uint32_t idx = gt; idx < nwork; idx += TILE) {                                                                \
-        const uint32_t sgi = idx / DC, k = idx - sgi * DC;                                                               \
-        const uint32_t b = segb[sgi], e = segb[sgi + 1];                                                                 \
-        const double* c0 = cs + k * PP_CS_LD;                                                                            \
-        double v = 0.0;                                                                                                  \
-        for (uint32_t q = b; q < e; ++q) v += c0[q];                                                                     \
-        const uint32_t row = segc[sgi] * DC + k;                                                                         \
-        if (PRIVATE) y_priv[row] += v; else red_add(a.y + row, v);                                                       \
+        const uint32_t sgi = idx / NG, kg = (idx - sgi * NG) * KG;                                                       \
+        const uint32_t b = segb[sgi], e = segb[sgi + 1], row = segc[sgi] * DC + kg;                                      \
+        const double* c0 = cs + kg * PP_CS_LD;                                                                           \
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;                                                                             \
+        for (uint32_t q = b; q < e; ++q) {                                                                               \
+          v0 += c0[q];                                                                                                   \
+          if (kg + 1 < DC) v1 += c0[PP_CS_LD + q];                                                                       \
+          if (kg + 2 < DC) v2 += c0[2 * PP_CS_LD + q];                                                                   \
+        }                                                                                                                \
+        if (PRIVATE) {                                                                                                   \
+          y_priv[row] += v0;                                                                                             \
+          if (kg + 1 < DC) y_priv[row + 1] += v1;                                                                        \
+          if (kg + 2 < DC) y_priv[row + 2] += v2;                                                                        \
+        } else {                                                                                                         \
+          red_add(a.y + row, v0);                                                                                        \
+          if (kg + 1 < DC) red_add(a.y + row + 1, v1);                                                                   \
+          if (kg + 2 < DC) red_add(a.y + row + 2, v2);                                                                   \
+        }                                                                                                                \
       }                                                                                                                  \
     }                                                                                                                    \
     if (PRIVATE) { if (g == 0) pp_turn_signal(3); else if (it + 1 < niter) pp_turn_signal(4); }                          \
@@ -461,7 +474,16 @@ __global__ void schur_finalize_kernel(const double* __restrict__ hcc, const doub
     s = st->damping * xc[a];
     for (int b = 0; b < dc; ++b) s += H[b] * xc[b];
   }
-  for (uint32_t b = 0; b < nblk; ++b) s += ypart[(size_t)b * n + row];
+  // fixed CTA order; 8 independent loads in flight per trip
+  uint32_t b = 0;
+  for (; b + 8 <= nblk; b += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcg(ypart + (size_t)(b + u) * n + row);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+  }
+  for (; b < nblk; ++b) s += __ldcg(ypart + (size_t)b * n + row);
   y[row] = s;
 }
 

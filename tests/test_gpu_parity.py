@@ -277,6 +277,22 @@ def test_fixed_variables_are_zeroed_at_update_only():
     assert np.array_equal(pg[2][:10, 0], prob.pt[:10, 0]) and np.array_equal(pg[2][:10, 2], prob.pt[:10, 2])
 
 
+@pytest.mark.parametrize("impl", ["red", "tile"])
+def test_operator_fallback_paths(impl, monkeypatch):
+    """The operator paths used when the camera vector does not fit next to the staging buffers in shared memory
+    (e.g. Final-13682: 985 KB): per-(segment, dof) reductions into global memory ("red"), and the first-generation
+    tile kernel ("tile"). Selected here with the development switch APEX_MATVEC_IMPL."""
+    monkeypatch.setenv("APEX_MATVEC_IMPL", impl)
+    prob = small_problem(ncam=40, npts=3000, track=5.0)
+    g, o = pair(prob)
+    g.linearize(1e-3); o.linearize(1e-3)
+    x = np.random.default_rng(9).standard_normal(prob.ncam * prob.dc)
+    assert relerr(g.schur_matvec(x), o.schur_matvec(x)) < 1e-10
+    sg = g.solve_augmented(F.SCHUR_IMPLICIT, 1e-3, cg_max_iterations=500, cg_tolerance=1e-12)
+    so = o.solve_augmented(F.SCHUR_IMPLICIT, 1e-3, cg_max_iterations=500, cg_tolerance=1e-12)
+    assert relerr(sg[0], so[0]) < 1e-5 and relerr(sg[1], so[1]) < 1e-5
+
+
 def test_error_behaviour():
     g = GpuContext()
     with pytest.raises(F.ApexError) as e:
