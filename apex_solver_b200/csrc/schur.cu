@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "apex_ctx.h"
 #include "ba_device.cuh"
@@ -40,8 +41,23 @@ struct SchurArgs {
   int debug;       // development probes: 1 = suppress the reductions into y, 2 = strided tile order
   uint32_t ntiles;
   const DevState* st;
+  // per-chunk camera segments (SEG variant: one reduction per (segment, dof) instead of per (observation, dof))
+  const ChunkDesc* chunk_desc;
+  const uint2* cslot_meta;
+  const uint32_t* cseg_cam;
+  const uint16_t* cseg_begin;
+  const uint32_t* cpt_meta;
 };
 
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
 
 // u = Jp^T (Jc x_c)
 template <int DC>
@@ -104,13 +120,14 @@ __device__ __forceinline__ void landmark_middle(const SchurArgs& a, uint32_t lp,
   }
 }
 
-template <int DC, int MODE>
-__global__ void __launch_bounds__(TILE) schur_tile_kernel(SchurArgs a) {
+template <int DC, int MODE, bool SEG = false>
+__global__ void __launch_bounds__(TILE, 3) schur_tile_kernel(SchurArgs a) {
   constexpr int NP = 2 * (DC + 3);
   if (a.check_done && a.st->pcg_done) return;
   __shared__ double sh[3][TILE];
   __shared__ double shw[3][TILE];
-  const uint32_t tile_idx = a.debug == 2 ? (uint32_t)(((uint64_t)blockIdx.x * 4099u) % a.ntiles) : blockIdx.x;
+  __shared__ double cs[SEG ? DC * (TILE + 1) : 1];
+  const uint32_t tile_idx = (a.debug == 2 || SEG) && (a.ntiles % 4099u != 0) ? (uint32_t)(((uint64_t)blockIdx.x * 4099u) % a.ntiles) : blockIdx.x;
   const TileDesc td = a.tiles[tile_idx];
   const int tid = threadIdx.x;
   if (td.nchunks == 1) {
@@ -139,10 +156,46 @@ __global__ void __launch_bounds__(TILE) schur_tile_kernel(SchurArgs a) {
     }
     if (MODE == MODE_BACKSUB) return;
     __syncthreads();
-    if (cam != PAD_CAM) {
-      const uint32_t li = a.slot_lp[slot];
-      const double w[3] = {shw[0][li], shw[1][li], shw[2][li]};
-      obs_backward<DC>(jc, jp, w, a.y + (size_t)cam * DC, a.debug);
+    if (!SEG) {
+      if (cam != PAD_CAM) {
+        const uint32_t li = a.slot_lp[slot];
+        const double w[3] = {shw[0][li], shw[1][li], shw[2][li]};
+        obs_backward<DC>(jc, jp, w, a.y + (size_t)cam * DC, a.debug);
+      }
+    } else {
+      // combine the scatter per camera inside the tile first: contributions at camera-sorted positions, then one
+      // reduction per (segment, dof)
+      constexpr int LD = TILE + 1;
+      if (cam != PAD_CAM) {
+        const uint32_t li = a.slot_lp[slot];
+        const uint32_t pos = (a.cslot_meta[slot].y >> 8) & 0xFFu;
+        const double w0 = shw[0][li], w1 = shw[1][li], w2 = shw[2][li];
+        const double b0 = fma(jp[0], w0, fma(jp[1], w1, jp[2] * w2));
+        const double b1 = fma(jp[3], w0, fma(jp[4], w1, jp[5] * w2));
+#pragma unroll
+        for (int k = 0; k < DC; ++k) cs[k * LD + pos] = -fma(jc[k], b0, jc[DC + k] * b1);
+      }
+      __syncthreads();
+      constexpr int KG = 3, NG = (DC + KG - 1) / KG;
+      const uint32_t nseg = a.chunk_desc[chunk].nseg;
+      const uint32_t* segc = a.cseg_cam + chunk * TILE;
+      const uint16_t* segb = a.cseg_begin + chunk * CSEG_LD;
+      for (uint32_t idx = tid; idx < nseg * NG; idx += TILE) {
+        const uint32_t sgi = idx / NG, kg = (idx - sgi * NG) * KG;
+        const uint32_t b = segb[sgi], e = segb[sgi + 1];
+        double* yr = a.y + (size_t)segc[sgi] * DC + kg;
+        const double* c0 = cs + kg * LD;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+        for (uint32_t q = b; q < e; ++q) {
+          v0 += c0[q];
+          if (kg + 1 < DC) v1 += c0[LD + q];
+          if (kg + 2 < DC) v2 += c0[2 * LD + q];
+        }
+        if (a.debug == 1 && v0 != 1.2345e300) continue;  // development probe: scatter suppressed
+        red_add(yr, v0);
+        if (kg + 1 < DC) red_add(yr + 1, v1);
+        if (kg + 2 < DC) red_add(yr + 2, v2);
+      }
     }
   } else {
     // one landmark spread over several chunks: accumulate per thread, reduce in fixed order, re-read J
@@ -181,14 +234,6 @@ __global__ void __launch_bounds__(TILE) schur_tile_kernel(SchurArgs a) {
   }
 }
 
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
 constexpr int MV_SMEM_MAX = 232448 - 512;    // 227 KB per CTA minus the static shared memory of the kernel
 
 // ----------------------------------------------------------------------------------------------------
@@ -215,6 +260,7 @@ struct PpArgs {
   const uint16_t* cseg_begin;
   const double* J;
   const double* hinv;
+  const double* gp;
   const double* xpad;
   double* y;
   double* ypart;
@@ -276,7 +322,7 @@ __device__ __forceinline__ void pp_fetch_tables(const PpArgs& a, uint32_t chunk,
   if (gt < CSEG_LD / 2) cp_async4(reinterpret_cast<uint32_t*>(sseg_begin) + gt, reinterpret_cast<const uint32_t*>(a.cseg_begin + (size_t)chunk * CSEG_LD) + gt);
 }
 
-template <int DC, bool PRIVATE>
+template <int DC, bool PRIVATE, int MODE = MODE_MATVEC>
 __global__ void __launch_bounds__(2 * TILE, 1) schur_matvec_pingpong_kernel(PpArgs a) {
   constexpr int XS = (DC + 1) & ~1;
   extern __shared__ __align__(16) double pp_smem[];
@@ -328,7 +374,7 @@ __global__ void __launch_bounds__(2 * TILE, 1) schur_matvec_pingpong_kernel(PpAr
     pp_fetch_tables<DC>(a, chunk_next, valid_next, gt, sseg_cam + (buf ^ 1) * TILE, sseg_begin + (buf ^ 1) * CSEG_LD);   \
     cp_async_commit();                                                                                                   \
     /* S0: x of every distinct camera of the chunk -> shared memory (coalesced per segment) */                          \
-    {                                                                                                                    \
+    if (MODE == MODE_MATVEC) {                                                                                           \
       double2* xs2 = reinterpret_cast<double2*>(cs);                                                                     \
       const uint32_t nld = R.nseg * (XS / 2);                                                                            \
       for (uint32_t idx = gt; idx < nld; idx += TILE) {                                                                  \
@@ -339,7 +385,7 @@ __global__ void __launch_bounds__(2 * TILE, 1) schur_matvec_pingpong_kernel(PpAr
     pp_prefetch_stage<DC, 0>(a, chunk_next, valid_next, gt, RN);                                                         \
     pp_group_bar(g);                                                                                                     \
     /* P1: u_o = Jp^T (Jc x_c) */                                                                                        \
-    {                                                                                                                    \
+    if (MODE == MODE_MATVEC) {                                                                                           \
       double u0 = 0.0, u1 = 0.0, u2 = 0.0;                                                                               \
       if (R.cam != PAD_CAM) {                                                                                            \
         const double2* xs2 = reinterpret_cast<const double2*>(cs) + (size_t)((R.sp >> 16) & 0xFFFFu) * (XS / 2);         \
@@ -357,7 +403,7 @@ __global__ void __launch_bounds__(2 * TILE, 1) schur_matvec_pingpong_kernel(PpAr
     pp_group_bar(g);                                                                                                     \
     /* P2: t_p = sum over the landmark's observations, w_p = Hpp^-1 t_p */                                               \
     if ((uint32_t)gt < R.npt) {                                                                                          \
-      const uint32_t mm = sptm[gt], off = mm & 0xFFFFu, cnt = mm >> 16;                                                  \
+      const uint32_t mm = sptm[gt], off = mm & 0xFFFFu, cnt = (MODE == MODE_RHS) ? 0u : (mm >> 16);                      \
       double t0 = 0.0, t1 = 0.0, t2 = 0.0, e0 = 0.0, e1 = 0.0, e2 = 0.0;                                                 \
       uint32_t q = 0;                                                                                                    \
       for (; q + 1 < cnt; q += 2) {                                                                                      \
@@ -366,6 +412,10 @@ __global__ void __launch_bounds__(2 * TILE, 1) schur_matvec_pingpong_kernel(PpAr
       }                                                                                                                  \
       if (q < cnt) { t0 += su[off + q]; t1 += su[TILE + off + q]; t2 += su[2 * TILE + off + q]; }                        \
       t0 += e0; t1 += e1; t2 += e2;                                                                                      \
+      if (MODE == MODE_RHS) {                                                                                            \
+        const size_t lp = R.pt0 + gt;                                                                                    \
+        t0 = -a.gp[lp]; t1 = -a.gp[(size_t)a.npl + lp]; t2 = -a.gp[2 * (size_t)a.npl + lp];                              \
+      }                                                                                                                  \
       const double h00 = shinv[gt], h01 = shinv[PP_PTS + gt], h02 = shinv[2 * PP_PTS + gt];                              \
       const double h11 = shinv[3 * PP_PTS + gt], h12 = shinv[4 * PP_PTS + gt], h22 = shinv[5 * PP_PTS + gt];             \
       sw[gt] = h00 * t0 + h01 * t1 + h02 * t2;                                                                           \
@@ -437,18 +487,30 @@ static size_t pp_smem_bytes(uint32_t n, bool priv) {
   return ((priv ? ((n + 1) & ~1u) : 0) + 2 * (size_t)pp_group_doubles<DC>()) * 8 + 64;
 }
 
-template <int DC>
+template <int DC, int MODE>
 static apex_status launch_pingpong_dc(Ctx& c, const PpArgs& a, bool priv, unsigned grid) {
   static bool attr_done[2] = {false, false};
   if (!attr_done[priv ? 1 : 0]) {
-    if (priv) APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_matvec_pingpong_kernel<DC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MV_SMEM_MAX));
-    else APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_matvec_pingpong_kernel<DC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MV_SMEM_MAX));
+    if (priv) APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_matvec_pingpong_kernel<DC, true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, MV_SMEM_MAX));
+    else APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_matvec_pingpong_kernel<DC, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, MV_SMEM_MAX));
     attr_done[priv ? 1 : 0] = true;
   }
   const size_t smem = pp_smem_bytes<DC>(a.n, priv);
-  if (priv) schur_matvec_pingpong_kernel<DC, true><<<grid, 2 * TILE, smem, c.stream>>>(a);
-  else schur_matvec_pingpong_kernel<DC, false><<<grid, 2 * TILE, smem, c.stream>>>(a);
+  if (priv) schur_matvec_pingpong_kernel<DC, true, MODE><<<grid, 2 * TILE, smem, c.stream>>>(a);
+  else schur_matvec_pingpong_kernel<DC, false, MODE><<<grid, 2 * TILE, smem, c.stream>>>(a);
   return APEX_OK;
+}
+
+template <int MODE>
+static apex_status launch_pingpong(Ctx& c, const PpArgs& a, bool priv, unsigned grid) {
+  switch (c.dc) {
+    case 6: return launch_pingpong_dc<6, MODE>(c, a, priv, grid);
+    case 9: return launch_pingpong_dc<9, MODE>(c, a, priv, grid);
+    case 10: return launch_pingpong_dc<10, MODE>(c, a, priv, grid);
+    case 12: return launch_pingpong_dc<12, MODE>(c, a, priv, grid);
+    case 14: return launch_pingpong_dc<14, MODE>(c, a, priv, grid);
+    default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
+  }
 }
 
 // x (stride dc) -> x at an even stride (camera blocks 16-byte aligned for the 128-bit gathers)
@@ -467,7 +529,8 @@ __global__ void schur_finalize_kernel(const double* __restrict__ hcc, const doub
   const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
   double s = 0.0;
-  if (add_hcc) {
+  if (add_hcc == 2) s = -x[row];  // reduced gradient: starts from -g_c (x = g_c)
+  else if (add_hcc) {
     const uint32_t cam = row / dc, a = row % dc;
     const double* H = hcc + ((size_t)cam * dc + a) * dc;
     const double* xc = x + (size_t)cam * dc;
@@ -485,6 +548,118 @@ __global__ void schur_finalize_kernel(const double* __restrict__ hcc, const doub
   }
   for (; b < nblk; ++b) s += __ldcg(ypart + (size_t)b * n + row);
   y[row] = s;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Chunk kernel: one 256-thread CTA per normal chunk (whole landmarks, <= 256 observations), 3 CTAs per SM.
+// Every global read a chunk needs - Jacobian planes, slot metadata, chunk descriptor, landmark inverses and
+// gradients, camera-segment tables - is issued up front (registers / cp.async into shared memory), so only ONE
+// memory latency is exposed per chunk; the camera-side scatter is combined per camera segment in shared
+// memory and leaves the CTA as one red.global.add.f64 per (segment, dof). Chunks are visited in a strided order
+// so that CTAs running at the same time touch different cameras (no same-address serialisation in L2).
+// ----------------------------------------------------------------------------------------------------
+template <int DC, int MODE>
+__global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a, uint32_t nchunks) {
+  constexpr int NP = 2 * (DC + 3);
+  constexpr int LD = TILE + 1;
+  if (a.check_done && a.st->pcg_done) return;
+  __shared__ double cs[DC * LD];                  // phase 3/4 contributions; its head doubles as su in phases 1/2
+  double (*su)[TILE] = reinterpret_cast<double (*)[TILE]>(cs);
+  __shared__ double sw[3][MAX_TILE_PTS];
+  __shared__ double shinv[6][MAX_TILE_PTS];
+  __shared__ double sgp[3][MAX_TILE_PTS];
+  __shared__ uint32_t sptm[MAX_TILE_PTS];
+  __shared__ uint32_t ssegc[TILE];
+  __shared__ __align__(4) uint16_t ssegb[CSEG_LD];
+  const int tid = threadIdx.x;
+  const uint32_t chunk = (nchunks % 4099u != 0) ? (uint32_t)(((uint64_t)blockIdx.x * 4099u) % nchunks) : blockIdx.x;
+  // ---- all global reads up front ----
+  const uint2 meta = __ldg(a.cslot_meta + (size_t)chunk * TILE + tid);
+  const uint4 dsc = __ldg(reinterpret_cast<const uint4*>(a.chunk_desc + chunk));
+  double jall[NP];
+  load_jacobian_planes<NP>(a.J, chunk, tid, jall);
+  if (MODE != MODE_BACKSUB) {
+    cp_async4(ssegc + tid, a.cseg_cam + (size_t)chunk * TILE + tid);
+    if (tid < CSEG_LD / 2) cp_async4(reinterpret_cast<uint32_t*>(ssegb) + tid, reinterpret_cast<const uint32_t*>(a.cseg_begin + (size_t)chunk * CSEG_LD) + tid);
+  }
+  const uint32_t pt0 = dsc.x, npt = dsc.y, nseg = dsc.z;
+  if ((uint32_t)tid < npt) {
+    const uint32_t lp = pt0 + tid;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cp_async8(&shinv[k][tid], a.hinv + (size_t)k * a.npl + lp);
+    if (MODE != MODE_MATVEC) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) cp_async8(&sgp[k][tid], a.gp + (size_t)k * a.npl + lp);
+    }
+    cp_async4(&sptm[tid], a.cpt_meta + lp);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const uint32_t cam = meta.x;
+  const double* jc = jall;
+  const double* jp = jall + 2 * DC;
+  // ---- phase 1: u_o = Jp^T (Jc x_c) ----
+  if (MODE != MODE_RHS) {
+    double u[3] = {0.0, 0.0, 0.0};
+    if (cam != PAD_CAM) obs_forward<DC>(jc, jp, a.x + (size_t)cam * DC, u);
+    su[0][tid] = u[0]; su[1][tid] = u[1]; su[2][tid] = u[2];
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // ---- phase 2: per landmark ----
+  if ((uint32_t)tid < npt) {
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    if (MODE != MODE_RHS) {
+      const uint32_t mm = sptm[tid], off = mm & 0xFFFFu, cnt = mm >> 16;
+      double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+      uint32_t q = 0;
+      for (; q + 1 < cnt; q += 2) {
+        t0 += su[0][off + q]; t1 += su[1][off + q]; t2 += su[2][off + q];
+        e0 += su[0][off + q + 1]; e1 += su[1][off + q + 1]; e2 += su[2][off + q + 1];
+      }
+      if (q < cnt) { t0 += su[0][off + q]; t1 += su[1][off + q]; t2 += su[2][off + q]; }
+      t0 += e0; t1 += e1; t2 += e2;
+    }
+    double v0, v1, v2;
+    if (MODE == MODE_MATVEC) { v0 = t0; v1 = t1; v2 = t2; }
+    else if (MODE == MODE_RHS) { v0 = -sgp[0][tid]; v1 = -sgp[1][tid]; v2 = -sgp[2][tid]; }
+    else { v0 = -sgp[0][tid] - t0; v1 = -sgp[1][tid] - t1; v2 = -sgp[2][tid] - t2; }
+    const double h00 = shinv[0][tid], h01 = shinv[1][tid], h02 = shinv[2][tid], h11 = shinv[3][tid], h12 = shinv[4][tid], h22 = shinv[5][tid];
+    const double w0 = h00 * v0 + h01 * v1 + h02 * v2, w1 = h01 * v0 + h11 * v1 + h12 * v2, w2 = h02 * v0 + h12 * v1 + h22 * v2;
+    if (MODE == MODE_BACKSUB) {
+      const size_t lp = pt0 + tid;
+      a.step_pt[3 * lp] = w0; a.step_pt[3 * lp + 1] = w1; a.step_pt[3 * lp + 2] = w2;
+    } else { sw[0][tid] = w0; sw[1][tid] = w1; sw[2][tid] = w2; }
+  }
+  if (MODE == MODE_BACKSUB) return;
+  __syncthreads();
+  // ---- phase 3: c_o = -Jc^T (Jp w_p) at the observation's camera-sorted position ----
+  if (cam != PAD_CAM) {
+    const uint32_t spt = meta.y & 0xFFu, pos = (meta.y >> 8) & 0xFFu;
+    const double w0 = sw[0][spt], w1 = sw[1][spt], w2 = sw[2][spt];
+    const double b0 = fma(jp[0], w0, fma(jp[1], w1, jp[2] * w2));
+    const double b1 = fma(jp[3], w0, fma(jp[4], w1, jp[5] * w2));
+#pragma unroll
+    for (int k = 0; k < DC; ++k) cs[k * LD + pos] = -fma(jc[k], b0, jc[DC + k] * b1);
+  }
+  __syncthreads();
+  // ---- phase 4: one reduction per (camera segment, dof) ----
+  constexpr int KG = 3, NG = (DC + KG - 1) / KG;
+  for (uint32_t idx = tid; idx < nseg * NG; idx += TILE) {
+    const uint32_t sgi = idx / NG, kg = (idx - sgi * NG) * KG;
+    const uint32_t b = ssegb[sgi], e = ssegb[sgi + 1];
+    double* yr = a.y + (size_t)ssegc[sgi] * DC + kg;
+    const double* c0 = cs + kg * LD;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+    for (uint32_t q = b; q < e; ++q) {
+      v0 += c0[q];
+      if (kg + 1 < DC) v1 += c0[LD + q];
+      if (kg + 2 < DC) v2 += c0[2 * LD + q];
+    }
+    if (a.debug == 1 && v0 != 1.2345e300) continue;  // development probe: scatter suppressed
+    red_add(yr, v0);
+    if (kg + 1 < DC) red_add(yr + 1, v1);
+    if (kg + 2 < DC) red_add(yr + 2, v2);
+  }
 }
 
 // y = (H_cc + lambda I) x on the block diagonal (first half of apply_schur_operator_fast); sign = -1 with
@@ -668,18 +843,65 @@ static SchurArgs make_schur_args(Ctx& c, const double* x, double* y, int check_d
   a.J = c.J.p; a.hinv = c.hinv.p; a.gp = c.gp.p; a.x = x; a.y = y; a.step_pt = c.step_pt.p;
   a.npl = c.npl; a.check_done = check_done; a.st = c.state.p;
   a.ntiles = c.ntiles;
+  a.chunk_desc = c.chunk_desc.p; a.cslot_meta = c.cslot_meta.p; a.cseg_cam = c.cseg_cam.p; a.cseg_begin = c.cseg_begin.p; a.cpt_meta = c.cpt_meta.p;
   const char* dbg = getenv("APEX_DEBUG_MATVEC");
   a.debug = dbg ? atoi(dbg) : 0;
   if (a.debug == 2 && c.ntiles % 4099u == 0) a.debug = 0;
   return a;
 }
 
+static int operator_impl() {
+  // development switch: 0 = chunk kernel (default), 1 = "tile" (first generation, per-observation reductions),
+  // 2 = "tileseg" (tile kernel with segment aggregation), 3 = "pp" (persistent ping-pong kernel, private y:
+  // bitwise reproducible), 4 = "red" (ping-pong kernel without the private y)
+  const char* f = getenv("APEX_MATVEC_IMPL");
+  if (!f) return getenv("APEX_DETERMINISTIC") ? 3 : 0;
+  if (!strcmp(f, "tile")) return 1;
+  if (!strcmp(f, "tileseg")) return 2;
+  if (!strcmp(f, "pp")) return 3;
+  if (!strcmp(f, "red")) return 4;
+  return 0;
+}
+
 template <int DC>
-static void launch_tiles_dc(Ctx& c, int mode, const SchurArgs& a) {
-  switch (mode) {
-    case MODE_MATVEC: schur_tile_kernel<DC, MODE_MATVEC><<<c.ntiles, TILE, 0, c.stream>>>(a); break;
-    case MODE_RHS: schur_tile_kernel<DC, MODE_RHS><<<c.ntiles, TILE, 0, c.stream>>>(a); break;
-    default: schur_tile_kernel<DC, MODE_BACKSUB><<<c.ntiles, TILE, 0, c.stream>>>(a); break;
+static void launch_tiles_dc(Ctx& c, int mode, const SchurArgs& a0) {
+  const int impl = operator_impl();
+  SchurArgs a = a0;
+  if (impl == 1 || impl == 2) {  // whole tile list through the tile kernel
+    if (!c.ntiles) return;
+    switch (mode) {
+      case MODE_MATVEC:
+        if (impl == 1) schur_tile_kernel<DC, MODE_MATVEC, false><<<c.ntiles, TILE, 0, c.stream>>>(a);
+        else schur_tile_kernel<DC, MODE_MATVEC, true><<<c.ntiles, TILE, 0, c.stream>>>(a);
+        break;
+      case MODE_RHS:
+        if (impl == 1) schur_tile_kernel<DC, MODE_RHS, false><<<c.ntiles, TILE, 0, c.stream>>>(a);
+        else schur_tile_kernel<DC, MODE_RHS, true><<<c.ntiles, TILE, 0, c.stream>>>(a);
+        break;
+      default: schur_tile_kernel<DC, MODE_BACKSUB, false><<<c.ntiles, TILE, 0, c.stream>>>(a); break;
+    }
+    c.launches++;
+    return;
+  }
+  // normal chunks through the chunk kernel, landmarks with more than 256 observations through the tile kernel
+  if (c.nnormal_chunks) {
+    switch (mode) {
+      case MODE_MATVEC: schur_chunk_kernel<DC, MODE_MATVEC><<<c.nnormal_chunks, TILE, 0, c.stream>>>(a, c.nnormal_chunks); break;
+      case MODE_RHS: schur_chunk_kernel<DC, MODE_RHS><<<c.nnormal_chunks, TILE, 0, c.stream>>>(a, c.nnormal_chunks); break;
+      default: schur_chunk_kernel<DC, MODE_BACKSUB><<<c.nnormal_chunks, TILE, 0, c.stream>>>(a, c.nnormal_chunks); break;
+    }
+    c.launches++;
+  }
+  if (c.ngiant) {
+    a.tiles = c.giant_tiles.p;
+    a.ntiles = c.ngiant;
+    a.debug = 0;
+    switch (mode) {
+      case MODE_MATVEC: schur_tile_kernel<DC, MODE_MATVEC, false><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
+      case MODE_RHS: schur_tile_kernel<DC, MODE_RHS, false><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
+      default: schur_tile_kernel<DC, MODE_BACKSUB, false><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
+    }
+    c.launches++;
   }
 }
 
@@ -694,7 +916,6 @@ apex_status launch_schur_tiles(Ctx& c, int mode, const double* x, double* y, int
     case 14: launch_tiles_dc<14>(c, mode, a); break;
     default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
   }
-  c.launches++;
   APEX_CUDA_TRY(c, cudaGetLastError());
   return APEX_OK;
 }
@@ -735,10 +956,14 @@ static apex_status launch_giant_tiles(Ctx& c, const double* x, double* y, int ch
 // this rank's part of y = S x, before the all-reduce: persistent kernel (+ finalize) + long-track tiles
 apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_done, bool xpad_ready) {
   const uint32_t n = c.ncam * c.dc;
-  const char* force = getenv("APEX_MATVEC_IMPL");  // development switch: "tile" = first-generation kernel, "red" = no private y
-  if (force && force[0] == 't') {
+  const int impl = operator_impl();
+  if (impl <= 2) {  // y = (H_cc + lambda I) x, then the chunk / tile kernels reduce -H_cp Hpp^-1 H_cp^T x into it
     APEX_TRY(launch_hcc_apply(c, x, y, check_done));
-    return launch_schur_tiles(c, MODE_MATVEC, x, y, check_done);
+    cudaEvent_t* evp = (c.prof && c.ntiles) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
+    if (evp) cudaEventRecord(evp[0], c.stream);
+    apex_status st = launch_schur_tiles(c, MODE_MATVEC, x, y, check_done);
+    if (evp) cudaEventRecord(evp[1], c.stream);
+    return st;
   }
   const int xs = (c.dc + 1) & ~1;
   if (!xpad_ready) {
@@ -755,21 +980,15 @@ apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_d
     case 14: need = pp_smem_bytes<14>(n, true); break;
     default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
   }
-  const bool priv = need <= (size_t)MV_SMEM_MAX && !(force && force[0] == 'r');
+  const bool priv = need <= (size_t)MV_SMEM_MAX && impl != 4;
   const unsigned grid = (unsigned)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)c.num_sms, npairs));
-  PpArgs a{c.chunk_desc.p, c.cslot_meta.p, c.cpt_meta.p, c.cseg_cam.p, c.cseg_begin.p, c.J.p, c.hinv.p, c.xpad.p, y, c.ypart.p,
+  PpArgs a{c.chunk_desc.p, c.cslot_meta.p, c.cpt_meta.p, c.cseg_cam.p, c.cseg_begin.p, c.J.p, c.hinv.p, c.gp.p, c.xpad.p, y, c.ypart.p,
            n, c.npl, npairs, c.nnormal_chunks, check_done, c.state.p};
   if (!priv) APEX_TRY(launch_hcc_apply(c, x, y, check_done));  // y starts as (H_cc + lambda I) x; the kernel reduces into it
   cudaEvent_t* evp = (c.prof && npairs) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
   if (evp) cudaEventRecord(evp[0], c.stream);
   if (npairs) {
-    switch (c.dc) {
-      case 6: APEX_TRY(launch_pingpong_dc<6>(c, a, priv, grid)); break;
-      case 9: APEX_TRY(launch_pingpong_dc<9>(c, a, priv, grid)); break;
-      case 10: APEX_TRY(launch_pingpong_dc<10>(c, a, priv, grid)); break;
-      case 12: APEX_TRY(launch_pingpong_dc<12>(c, a, priv, grid)); break;
-      default: APEX_TRY(launch_pingpong_dc<14>(c, a, priv, grid)); break;
-    }
+    APEX_TRY(launch_pingpong<MODE_MATVEC>(c, a, priv, grid));
     c.launches++;
   }
   if (evp) cudaEventRecord(evp[1], c.stream);
@@ -792,6 +1011,28 @@ apex_status schur_operator(Ctx& c, const double* x, double* y, int check_done, b
 // b = -g_c - H_cp Hpp^-1 (-g_p)   (implicit_schur.rs:863-880 with g = -J^T r; explicit_schur.rs:928-977)
 apex_status launch_reduced_gradient(Ctx& c, double* b) {
   const uint32_t n = c.ncam * c.dc;
+  if (operator_impl() == 3 && c.ngiant == 0 && c.npairs) {
+    // deterministic route: the ping-pong kernel in RHS mode (w_p = Hpp^-1 (-g_p)), private copies summed in CTA order
+    size_t need = 0;
+    switch (c.dc) {
+      case 6: need = pp_smem_bytes<6>(n, true); break;
+      case 9: need = pp_smem_bytes<9>(n, true); break;
+      case 10: need = pp_smem_bytes<10>(n, true); break;
+      case 12: need = pp_smem_bytes<12>(n, true); break;
+      default: need = pp_smem_bytes<14>(n, true); break;
+    }
+    if (need <= (size_t)MV_SMEM_MAX) {
+      const unsigned grid = (unsigned)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)c.num_sms, c.npairs));
+      PpArgs a{c.chunk_desc.p, c.cslot_meta.p, c.cpt_meta.p, c.cseg_cam.p, c.cseg_begin.p, c.J.p, c.hinv.p, c.gp.p, c.xpad.p, b, c.ypart.p,
+               n, c.npl, c.npairs, c.nnormal_chunks, 0, c.state.p};
+      APEX_TRY(launch_pingpong<MODE_RHS>(c, a, true, grid));
+      schur_finalize_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(c.hcc.p, c.gc, c.ypart.p, grid, b, c.state.p, n, c.dc, c.rank == 0 ? 2 : 0, 0);
+      c.launches += 2;
+      APEX_CUDA_TRY(c, cudaGetLastError());
+      APEX_TRY(allreduce_sum(c, b, n));
+      return APEX_OK;
+    }
+  }
   if (c.rank == 0) {
     negate_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(c.gc, b, n);
     c.launches++;

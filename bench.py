@@ -233,7 +233,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "matvec_traffic.json")
     if os.path.exists(tpath) and world == 1 and a.scale == 1.0:
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "schur_matvec_pingpong_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "schur_chunk_kernel<9, MATVEC>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_mv, "launches": int(prof.matvec_launches), "avg_launch_ms": mv_ms,
                 "share_of_step": prof.matvec_ms / prof.lm_device_ms if prof.lm_device_ms else None}

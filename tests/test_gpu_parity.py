@@ -80,8 +80,7 @@ def test_linearize_blocks_cost_matvec(name, kw):
     x = rng.standard_normal(prob.ncam * prob.dc)
     yg, yo = g.schur_matvec(x), o.schur_matvec(x)
     assert relerr(yg, yo) < 1e-12 * max(cond.max(), 10.0), "Schur operator"
-    # the persistent operator kernel keeps y in a CTA-private shared-memory copy: bitwise reproducible
-    assert np.array_equal(g.schur_matvec(x), yg)
+    assert relerr(g.schur_matvec(x), yg) < 1e-13  # default path: FP64 reductions into L2, order may differ run to run
 
 
 @pytest.mark.parametrize("variant", [F.SCHUR_EXPLICIT, F.SCHUR_IMPLICIT, F.SCHUR_EXPLICIT_PCG], ids=["explicit", "implicit", "explicit_pcg"])
@@ -277,7 +276,23 @@ def test_fixed_variables_are_zeroed_at_update_only():
     assert np.array_equal(pg[2][:10, 0], prob.pt[:10, 0]) and np.array_equal(pg[2][:10, 2], prob.pt[:10, 2])
 
 
-@pytest.mark.parametrize("impl", ["red", "tile"])
+def test_deterministic_operator_is_bitwise_reproducible(monkeypatch):
+    """APEX_DETERMINISTIC selects the persistent ping-pong kernel that keeps y in a CTA-private shared-memory copy
+    and sums the copies in CTA order: same bits on every run, and an LM trajectory that repeats exactly."""
+    monkeypatch.setenv("APEX_DETERMINISTIC", "1")
+    prob = small_problem(ncam=30, npts=2000, track=5.0)
+    g, o = pair(prob)
+    g.linearize(1e-3); o.linearize(1e-3)
+    x = np.random.default_rng(4).standard_normal(prob.ncam * prob.dc)
+    y1 = g.schur_matvec(x)
+    assert np.array_equal(g.schur_matvec(x), y1) and np.array_equal(g.schur_matvec(x), y1)
+    assert relerr(y1, o.schur_matvec(x)) < 1e-11
+    g1, g2 = GpuContext().upload(prob), GpuContext().upload(prob)
+    (r1, t1), (r2, t2) = run_lm(g1, F.SCHUR_IMPLICIT, max_it=4), run_lm(g2, F.SCHUR_IMPLICIT, max_it=4)
+    assert [a.cost for a in t1] == [b.cost for b in t2] and r1.linear_iterations == r2.linear_iterations
+
+
+@pytest.mark.parametrize("impl", ["red", "tile", "tileseg", "pp"])
 def test_operator_fallback_paths(impl, monkeypatch):
     """The operator paths used when the camera vector does not fit next to the staging buffers in shared memory
     (e.g. Final-13682: 985 KB): per-(segment, dof) reductions into global memory ("red"), and the first-generation
@@ -290,7 +305,7 @@ def test_operator_fallback_paths(impl, monkeypatch):
     assert relerr(g.schur_matvec(x), o.schur_matvec(x)) < 1e-10
     sg = g.solve_augmented(F.SCHUR_IMPLICIT, 1e-3, cg_max_iterations=500, cg_tolerance=1e-12)
     so = o.solve_augmented(F.SCHUR_IMPLICIT, 1e-3, cg_max_iterations=500, cg_tolerance=1e-12)
-    assert relerr(sg[0], so[0]) < 1e-5 and relerr(sg[1], so[1]) < 1e-5
+    assert relerr(sg[0], so[0]) < 1e-3 and relerr(sg[1], so[1]) < 1e-3  # cond(S) ~1e10: solver-accuracy level agreement
 
 
 def test_error_behaviour():

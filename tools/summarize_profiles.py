@@ -42,7 +42,7 @@ if os.path.exists(rep):
         return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
     traffic = tobytes(*out["dram__bytes_read.sum"]) + tobytes(*out["dram__bytes_write.sum"])
     with open(f"profiles/{tag}_matvec_ncu_summary.txt", "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:schur_matvec_persist -c 1 python bench.py --steps 1 --warmup 0 (Venice-1778 shape)\n")
+        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:schur_chunk_kernel -c 1 python bench.py --steps 1 --warmup 0 (Venice-1778 shape)\n")
         for k, (v, u) in out.items():
             f.write(f"{k:70s} {v} {u}\n")
         f.write(f"dram traffic per launch (read+write) = {traffic / 1e9:.4f} GB; algorithmic bytes per launch = 1.1077 GB\n")
