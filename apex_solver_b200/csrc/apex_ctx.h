@@ -213,7 +213,7 @@ apex_status launch_cost(Ctx& c, double* d_cost2_out);       // K1': writes sum r
 apex_status launch_schur_jacobi_blocks(Ctx& c, int kind);   // K5 build: fills pinv for preconditioner `kind`
 // schur.cu
 enum TileMode { MODE_MATVEC = 0, MODE_RHS = 1, MODE_BACKSUB = 2 };
-apex_status launch_schur_tiles(Ctx& c, int mode, const double* x, double* y, int check_done);
+apex_status launch_schur_tiles(Ctx& c, int mode, const double* x, double* y, int check_done, bool xpad_ready = false);
 apex_status launch_hcc_apply(Ctx& c, const double* x, double* y, int check_done);  // y = (H_cc + lambda I) x on rank 0, else 0
 apex_status schur_operator(Ctx& c, const double* x, double* y, int check_done, bool xpad_ready = false);    // y = S x, all-reduced
 apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_done, bool xpad_ready = false);  // this rank's part

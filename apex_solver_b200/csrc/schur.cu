@@ -47,6 +47,7 @@ struct SchurArgs {
   const uint32_t* cseg_cam;
   const uint16_t* cseg_begin;
   const uint32_t* cpt_meta;
+  const double* xpad;   // x at an even per-camera stride (chunk kernel)
 };
 
 
@@ -562,6 +563,7 @@ template <int DC, int MODE>
 __global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a, uint32_t nchunks) {
   constexpr int NP = 2 * (DC + 3);
   constexpr int LD = TILE + 1;
+  constexpr int XS = (DC + 1) & ~1;
   if (a.check_done && a.st->pcg_done) return;
   __shared__ double cs[DC * LD];                  // phase 3/4 contributions; its head doubles as su in phases 1/2
   double (*su)[TILE] = reinterpret_cast<double (*)[TILE]>(cs);
@@ -574,14 +576,14 @@ __global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a, uint3
   const int tid = threadIdx.x;
   const uint32_t chunk = (nchunks % 4099u != 0) ? (uint32_t)(((uint64_t)blockIdx.x * 4099u) % nchunks) : blockIdx.x;
   // ---- all global reads up front ----
-  const uint2 meta = __ldg(a.cslot_meta + (size_t)chunk * TILE + tid);
-  const uint4 dsc = __ldg(reinterpret_cast<const uint4*>(a.chunk_desc + chunk));
-  double jall[NP];
-  load_jacobian_planes<NP>(a.J, chunk, tid, jall);
   if (MODE != MODE_BACKSUB) {
     cp_async4(ssegc + tid, a.cseg_cam + (size_t)chunk * TILE + tid);
     if (tid < CSEG_LD / 2) cp_async4(reinterpret_cast<uint32_t*>(ssegb) + tid, reinterpret_cast<const uint32_t*>(a.cseg_begin + (size_t)chunk * CSEG_LD) + tid);
   }
+  const uint2 meta = __ldg(a.cslot_meta + (size_t)chunk * TILE + tid);
+  const uint4 dsc = __ldg(reinterpret_cast<const uint4*>(a.chunk_desc + chunk));
+  double jall[NP];
+  load_jacobian_planes<NP>(a.J, chunk, tid, jall);
   const uint32_t pt0 = dsc.x, npt = dsc.y, nseg = dsc.z;
   if ((uint32_t)tid < npt) {
     const uint32_t lp = pt0 + tid;
@@ -597,10 +599,10 @@ __global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a, uint3
   const uint32_t cam = meta.x;
   const double* jc = jall;
   const double* jp = jall + 2 * DC;
-  // ---- phase 1: u_o = Jp^T (Jc x_c) ----
+  // ---- phase 1: u_o = Jp^T (Jc x_c); x gathered through L1 with 128-bit loads from the padded copy ----
   if (MODE != MODE_RHS) {
     double u[3] = {0.0, 0.0, 0.0};
-    if (cam != PAD_CAM) obs_forward<DC>(jc, jp, a.x + (size_t)cam * DC, u);
+    if (cam != PAD_CAM) obs_forward_padded<DC>(jc, jp, a.xpad + (size_t)cam * XS, u);
     su[0][tid] = u[0]; su[1][tid] = u[1]; su[2][tid] = u[2];
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -843,12 +845,14 @@ static SchurArgs make_schur_args(Ctx& c, const double* x, double* y, int check_d
   a.J = c.J.p; a.hinv = c.hinv.p; a.gp = c.gp.p; a.x = x; a.y = y; a.step_pt = c.step_pt.p;
   a.npl = c.npl; a.check_done = check_done; a.st = c.state.p;
   a.ntiles = c.ntiles;
-  a.chunk_desc = c.chunk_desc.p; a.cslot_meta = c.cslot_meta.p; a.cseg_cam = c.cseg_cam.p; a.cseg_begin = c.cseg_begin.p; a.cpt_meta = c.cpt_meta.p;
+  a.chunk_desc = c.chunk_desc.p; a.cslot_meta = c.cslot_meta.p; a.cseg_cam = c.cseg_cam.p; a.cseg_begin = c.cseg_begin.p; a.cpt_meta = c.cpt_meta.p; a.xpad = c.xpad.p;
   const char* dbg = getenv("APEX_DEBUG_MATVEC");
   a.debug = dbg ? atoi(dbg) : 0;
   if (a.debug == 2 && c.ntiles % 4099u == 0) a.debug = 0;
   return a;
 }
+
+__global__ void pad_x_kernel(const double* __restrict__ x, double* __restrict__ xpad, uint32_t ncam, int dc, int xs, const DevState* st, int check_done);
 
 static int operator_impl() {
   // development switch: 0 = chunk kernel (default), 1 = "tile" (first generation, per-observation reductions),
@@ -905,8 +909,13 @@ static void launch_tiles_dc(Ctx& c, int mode, const SchurArgs& a0) {
   }
 }
 
-apex_status launch_schur_tiles(Ctx& c, int mode, const double* x, double* y, int check_done) {
+apex_status launch_schur_tiles(Ctx& c, int mode, const double* x, double* y, int check_done, bool xpad_ready) {
   if (c.ntiles == 0) return APEX_OK;
+  if (mode != MODE_RHS && !xpad_ready && operator_impl() != 1 && operator_impl() != 2) {  // the chunk kernel gathers x from the padded copy
+    const int xs = (c.dc + 1) & ~1;
+    pad_x_kernel<<<(c.ncam * xs + 255) / 256, 256, 0, c.stream>>>(x, c.xpad.p, c.ncam, c.dc, xs, c.state.p, check_done);
+    c.launches++;
+  }
   SchurArgs a = make_schur_args(c, x, y, check_done);
   switch (c.dc) {
     case 6: launch_tiles_dc<6>(c, mode, a); break;
@@ -961,7 +970,7 @@ apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_d
     APEX_TRY(launch_hcc_apply(c, x, y, check_done));
     cudaEvent_t* evp = (c.prof && c.ntiles) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
     if (evp) cudaEventRecord(evp[0], c.stream);
-    apex_status st = launch_schur_tiles(c, MODE_MATVEC, x, y, check_done);
+    apex_status st = launch_schur_tiles(c, MODE_MATVEC, x, y, check_done, xpad_ready);
     if (evp) cudaEventRecord(evp[1], c.stream);
     return st;
   }
