@@ -599,11 +599,22 @@ __global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a, uint3
   const uint32_t cam = meta.x;
   const double* jc = jall;
   const double* jp = jall + 2 * DC;
-  // ---- phase 1: u_o = Jp^T (Jc x_c); x gathered through L1 with 128-bit loads from the padded copy ----
+  // ---- phase 1: u_o = Jp^T (Jc x_c); x gathered through L1 with 128-bit loads from the padded copy. The sum over a
+  // landmark's observations (consecutive lanes) starts as a segmented warp-shuffle reduction; only the first lane of
+  // each run writes its partial to shared memory ----
   if (MODE != MODE_RHS) {
     double u[3] = {0.0, 0.0, 0.0};
     if (cam != PAD_CAM) obs_forward_padded<DC>(jc, jp, a.xpad + (size_t)cam * XS, u);
-    su[0][tid] = u[0]; su[1][tid] = u[1]; su[2][tid] = u[2];
+    const uint32_t key = cam != PAD_CAM ? (meta.y & 0xFFu) : 0xFFFFu;  // chunk-local landmark
+    const int lane = tid & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double o0 = __shfl_down_sync(0xffffffffu, u[0], d), o1 = __shfl_down_sync(0xffffffffu, u[1], d), o2 = __shfl_down_sync(0xffffffffu, u[2], d);
+      const uint32_t ok = __shfl_down_sync(0xffffffffu, key, d);
+      if (lane + d < 32 && ok == key) { u[0] += o0; u[1] += o1; u[2] += o2; }
+    }
+    const uint32_t pk = __shfl_up_sync(0xffffffffu, key, 1);
+    if ((lane == 0 || pk != key) && cam != PAD_CAM) { su[0][tid] = u[0]; su[1][tid] = u[1]; su[2][tid] = u[2]; }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
@@ -612,14 +623,10 @@ __global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a, uint3
     double t0 = 0.0, t1 = 0.0, t2 = 0.0;
     if (MODE != MODE_RHS) {
       const uint32_t mm = sptm[tid], off = mm & 0xFFFFu, cnt = mm >> 16;
-      double e0 = 0.0, e1 = 0.0, e2 = 0.0;
-      uint32_t q = 0;
-      for (; q + 1 < cnt; q += 2) {
-        t0 += su[0][off + q]; t1 += su[1][off + q]; t2 += su[2][off + q];
-        e0 += su[0][off + q + 1]; e1 += su[1][off + q + 1]; e2 += su[2][off + q + 1];
+      if (cnt) {
+        t0 = su[0][off]; t1 = su[1][off]; t2 = su[2][off];
+        for (uint32_t b = (off & ~31u) + 32; b < off + cnt; b += 32) { t0 += su[0][b]; t1 += su[1][b]; t2 += su[2][b]; }  // runs continuing in the next warps
       }
-      if (q < cnt) { t0 += su[0][off + q]; t1 += su[1][off + q]; t2 += su[2][off + q]; }
-      t0 += e0; t1 += e1; t2 += e2;
     }
     double v0, v1, v2;
     if (MODE == MODE_MATVEC) { v0 = t0; v1 = t1; v2 = t2; }
@@ -634,7 +641,7 @@ __global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a, uint3
   }
   if (MODE == MODE_BACKSUB) return;
   __syncthreads();
-  // ---- phase 3: c_o = -Jc^T (Jp w_p) at the observation's camera-sorted position ----
+  // ---- phase 3: c_o = -Jc^T (Jp w_p) written at the observation's camera-sorted position ----
   if (cam != PAD_CAM) {
     const uint32_t spt = meta.y & 0xFFu, pos = (meta.y >> 8) & 0xFFu;
     const double w0 = sw[0][spt], w1 = sw[1][spt], w2 = sw[2][spt];
@@ -644,7 +651,7 @@ __global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a, uint3
     for (int k = 0; k < DC; ++k) cs[k * LD + pos] = -fma(jc[k], b0, jc[DC + k] * b1);
   }
   __syncthreads();
-  // ---- phase 4: one reduction per (camera segment, dof) ----
+  // ---- phase 4: one reduction per (camera segment, dof); a thread takes 3 dofs of one segment ----
   constexpr int KG = 3, NG = (DC + KG - 1) / KG;
   for (uint32_t idx = tid; idx < nseg * NG; idx += TILE) {
     const uint32_t sgi = idx / NG, kg = (idx - sgi * NG) * KG;
