@@ -168,6 +168,8 @@ struct Ctx {
   DevState* h_state = nullptr;            // pinned mirror
   DevBuf<apex_iter_trace> trace;
   int64_t last_pcg_iters = 0;
+  void* pcg_graph_exec = nullptr;       // cudaGraphExec_t of one batch of PCG iterations (rebuilt after every upload)
+  int64_t pcg_graph_launches = 0;       // kernel launches one replay stands for
 
   // ---- profiling (apex_profile_*) ----
   bool prof = false;

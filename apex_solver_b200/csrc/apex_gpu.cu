@@ -142,6 +142,7 @@ void apex_ctx_destroy(apex_ctx* ctx) {
   Ctx& c = ctx->c;
   cudaSetDevice(c.device);
   if (c.stream) cudaStreamSynchronize(c.stream);
+  if (c.pcg_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)c.pcg_graph_exec);
   if (c.nccl_comm) nccl_api().CommDestroy((NcclComm)c.nccl_comm);
   DevBuf<double>* dbl[] = {&c.slot_uv, &c.cm_uv, &c.pose, &c.intr, &c.pt, &c.pt_full, &c.J, &c.R, &c.hpp, &c.gp, &c.hinv, &c.hcc, &c.partial,
                            &c.sj, &c.pinv, &c.vb, &c.vx, &c.vr, &c.vz, &c.vp, &c.vy, &c.step_cam, &c.step_pt, &c.red_scratch, &c.S, &c.E,

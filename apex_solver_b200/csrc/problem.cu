@@ -274,6 +274,7 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   const int K = model_intr_dim(d->camera_model);
   c.have_problem = false;
   c.linearized = false;
+  if (c.pcg_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)c.pcg_graph_exec); c.pcg_graph_exec = nullptr; }
   c.model = d->camera_model; c.K = K; c.opt = d->opt_flags;
   c.opt_intr = (d->opt_flags & APEX_OPT_INTRINSIC) != 0;
   c.intr_vars = d->intr_vars_present != 0;

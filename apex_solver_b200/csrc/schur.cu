@@ -1071,24 +1071,51 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
   pcg_init_kernel<<<1, 1024, 0, s>>>(c.vb.p, c.pinv.p, c.step_cam.p, c.vr.p, c.vz.p, c.vp.p, c.state.p, n, c.dc, c.K, cg_max_it, cg_tol);
   c.launches++;
   APEX_CUDA_TRY(c, cudaGetLastError());
-  // PCG: iterations are enqueued in batches; every kernel of an iteration is a no-op once the device-side
-  // `pcg_done` flag is set, so the host only polls the flag between batches.
+  // PCG: iterations are enqueued in batches of BATCH; every kernel of an iteration is a no-op once the device-side
+  // `pcg_done` flag is set (also set at pcg_max), so the host only polls the flag between batches. A batch is
+  // captured once per uploaded problem into a CUDA graph (kernels + the NCCL all-reduce) and replayed with one
+  // launch: the inner loop is launch-bound on small shards (8 GPUs: ~35 us of kernels per iteration).
   const int BATCH = 10;
+  auto enqueue_iteration = [&]() -> apex_status {
+    const int xs = (c.dc + 1) & ~1;
+    const unsigned gp = (n + PCG_THREADS - 1) / PCG_THREADS, gu = (c.ncam + PCG_CAMS - 1) / PCG_CAMS;
+    pcg_dir_kernel<<<(c.ncam * xs + PCG_THREADS - 1) / PCG_THREADS, PCG_THREADS, 0, s>>>(c.vz.p, c.vp.p, c.xpad.p, c.state.p, c.ncam, c.dc, xs);
+    APEX_TRY(schur_operator(c, c.vp.p, c.vy.p, 1, true));
+    pcg_pap_kernel<<<gp, PCG_THREADS, 0, s>>>(c.vp.p, c.vy.p, c.red_scratch.p, c.state.p, n);
+    pcg_update_kernel<<<gu, PCG_THREADS, 0, s>>>(c.vy.p, c.pinv.p, c.vp.p, c.step_cam.p, c.vr.p, c.vz.p, c.red_scratch.p, c.state.p, c.ncam, c.dc, c.K);
+    c.launches += 3;
+    return APEX_OK;
+  };
+  const bool use_graph = !c.prof && operator_impl() == 0 && !getenv("APEX_NO_GRAPH") && cg_max_it > 0;
+  if (use_graph && !c.pcg_graph_exec) {
+    const int64_t l0 = c.launches;
+    cudaGraph_t graph = nullptr;
+    APEX_CUDA_TRY(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    apex_status st = APEX_OK;
+    for (int i = 0; i < BATCH && st == APEX_OK; ++i) st = enqueue_iteration();
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    c.pcg_graph_launches = c.launches - l0;
+    c.launches = l0;
+    if (st != APEX_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+    APEX_CUDA_TRY(c, ce);
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    APEX_CUDA_TRY(c, ce);
+    c.pcg_graph_exec = exec;
+  }
   int enq = 0;
   while (enq < cg_max_it) {
-    const int nb = std::min(BATCH, cg_max_it - enq);
-    for (int i = 0; i < nb; ++i) {
-      const int xs = (c.dc + 1) & ~1;
-      const unsigned gp = (n + PCG_THREADS - 1) / PCG_THREADS, gu = (c.ncam + PCG_CAMS - 1) / PCG_CAMS;
-      pcg_dir_kernel<<<(c.ncam * xs + PCG_THREADS - 1) / PCG_THREADS, PCG_THREADS, 0, s>>>(c.vz.p, c.vp.p, c.xpad.p, c.state.p, c.ncam, c.dc, xs);
-      c.launches++;
-      APEX_TRY(schur_operator(c, c.vp.p, c.vy.p, 1, true));
-      pcg_pap_kernel<<<gp, PCG_THREADS, 0, s>>>(c.vp.p, c.vy.p, c.red_scratch.p, c.state.p, n);
-      pcg_update_kernel<<<gu, PCG_THREADS, 0, s>>>(c.vy.p, c.pinv.p, c.vp.p, c.step_cam.p, c.vr.p, c.vz.p, c.red_scratch.p, c.state.p, c.ncam, c.dc, c.K);
-      c.launches += 2;
+    if (use_graph) {
+      APEX_CUDA_TRY(c, cudaGraphLaunch((cudaGraphExec_t)c.pcg_graph_exec, s));
+      c.launches += c.pcg_graph_launches;
+      enq += BATCH;
+    } else {
+      const int nb = std::min(BATCH, cg_max_it - enq);
+      for (int i = 0; i < nb; ++i) APEX_TRY(enqueue_iteration());
+      APEX_CUDA_TRY(c, cudaGetLastError());
+      enq += nb;
     }
-    APEX_CUDA_TRY(c, cudaGetLastError());
-    enq += nb;
     APEX_TRY(sync_state(c));
     if (c.h_state->pcg_done) break;
   }

@@ -186,21 +186,28 @@ def main():
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    ctx.profile_enable(True)
     n0 = ctx.kernel_launches()
     res, trace = ctx.lm_solve(lm_config(ctx, a.steps))
-    prof = ctx.profile_read()
+    timed = ctx.profile_read()          # lm_device_ms: CUDA events around the solve on the solver's stream
     launches = ctx.kernel_launches() - n0
     barrier()
     sampler.stop_flag.set()
     sampler.join(timeout=2)
-    ctx.profile_enable(False)
-    dev_ms = torch.tensor([prof.lm_device_ms], dtype=torch.float64)
+    dev_ms = torch.tensor([timed.lm_device_ms], dtype=torch.float64)
     if world > 1:
         dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
     dev_ms = float(dev_ms.item())
     steps_done = res.iterations
     value = steps_done / (dev_ms * 1e-3)
+
+    # ---- roofline pass: the same K steps again with an event pair around every launch of the operator kernel (this
+    # disables the CUDA-graph replay of the PCG batches, so it is kept out of the timed run above) ----
+    ctx.params_upload(pose0, intr0, pt0)
+    barrier()
+    ctx.profile_enable(True)
+    ctx.lm_solve(lm_config(ctx, a.steps))
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
 
     # ---- e2e: the call a user makes, from host buffers: upload + solve + download, wall clock, max over ranks ----
     h2d = sum(x.nbytes for x in (prob.pose, prob.intr, prob.pt, prob.obs_cam, prob.obs_pt, prob.obs_uv))
@@ -236,7 +243,8 @@ def main():
     roofline = {"bound": "hbm", "kernel": "schur_chunk_kernel<9, MATVEC>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_mv, "launches": int(prof.matvec_launches), "avg_launch_ms": mv_ms,
-                "share_of_step": prof.matvec_ms / prof.lm_device_ms if prof.lm_device_ms else None}
+                "share_of_step": prof.matvec_ms / prof.lm_device_ms if prof.lm_device_ms else None,
+                "measured": "second pass of the same K steps with a CUDA-event pair around every launch (PCG batches not graph-replayed)"}
 
     if rank == 0:
         cb = None
