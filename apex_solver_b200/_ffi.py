@@ -122,14 +122,14 @@ class Profile(C.Structure):
 
 
 class LayoutStats(C.Structure):
-    _fields_ = [("p0", C.c_uint32), ("p1", C.c_uint32), ("nobs_local", C.c_uint64), ("ntiles", C.c_uint32), ("nlong_tiles", C.c_uint32),
+    _fields_ = [("shard_block", C.c_uint32), ("npts_local", C.c_uint32), ("nobs_local", C.c_uint64), ("ntiles", C.c_uint32), ("nlong_tiles", C.c_uint32),
                 ("nchunks", C.c_uint32), ("nnormal_chunks", C.c_uint32), ("ncam_items", C.c_uint32), ("max_segments_per_chunk", C.c_uint32),
                 ("nsegments", C.c_uint64), ("slots_used", C.c_uint64), ("consistent", C.c_int32), ("reserved", C.c_int32), ("build_ms", C.c_double)]
 
 
 class Dims(C.Structure):
     _fields_ = [("ncam", C.c_uint32), ("npts", C.c_uint32), ("nobs", C.c_uint64), ("intr_dim", C.c_int32), ("dc", C.c_int32),
-                ("cam_dof", C.c_uint64), ("lm_dof", C.c_uint64), ("npts_local", C.c_uint32), ("reserved", C.c_uint32),
+                ("cam_dof", C.c_uint64), ("lm_dof", C.c_uint64), ("npts_local", C.c_uint32), ("flags", C.c_uint32),
                 ("nobs_local", C.c_uint64)]
 
 
@@ -162,10 +162,10 @@ SYMBOLS = {
     "profile_enable": (C.c_int32, [C.c_void_p, C.c_int32]),
     "profile_read": (C.c_int32, [C.c_void_p, P(Profile)]),
     "layout_stats_compute": (C.c_int32, [P(ProblemDesc), C.c_int32, C.c_int32, P(LayoutStats)]),
-    "shard_range": (C.c_int32, [C.c_uint32, C.c_uint64, C.c_void_p, C.c_int32, C.c_int32, P(C.c_uint32), P(C.c_uint32), P(C.c_uint64)]),
+    "shard_info": (C.c_int32, [C.c_uint32, C.c_uint64, C.c_void_p, C.c_int32, C.c_int32, P(C.c_uint32), P(C.c_uint32), P(C.c_uint64)]),
 }
 # entry points the oracle does not implement (GPU-only plumbing)
-GPU_ONLY = {"device_count", "nccl_unique_id", "schur_matvec_bench", "kernel_launches", "profile_enable", "profile_read", "shard_range", "layout_stats_compute"}
+GPU_ONLY = {"device_count", "nccl_unique_id", "schur_matvec_bench", "kernel_launches", "profile_enable", "profile_read", "shard_info", "layout_stats_compute"}
 
 
 def bind(lib: C.CDLL, prefix: str, skip=()) -> None:

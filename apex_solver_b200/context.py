@@ -202,15 +202,15 @@ class Context:
         return p
 
 
-def shard_range(obs_pt, npts: int, nranks: int, rank: int):
-    """Landmark range [p0,p1) and observation count owned by `rank` (host-only entry point of the product library)."""
+def shard_info(obs_pt, npts: int, nranks: int, rank: int):
+    """(block, npts_local, nobs_local): landmark p is owned by rank (p // block) % nranks (host-only entry point)."""
     lib = F.load_library()
     obs_pt = np.ascontiguousarray(obs_pt, dtype=np.uint32)
-    p0, p1, n = C.c_uint32(), C.c_uint32(), C.c_uint64()
-    st = lib.apex_shard_range(int(npts), int(obs_pt.shape[0]), F.ptr(obs_pt), int(nranks), int(rank), C.byref(p0), C.byref(p1), C.byref(n))
+    blk, npl, n = C.c_uint32(), C.c_uint32(), C.c_uint64()
+    st = lib.apex_shard_info(int(npts), int(obs_pt.shape[0]), F.ptr(obs_pt), int(nranks), int(rank), C.byref(blk), C.byref(npl), C.byref(n))
     if st != F.OK:
-        raise F.ApexError(st, "shard_range")
-    return p0.value, p1.value, n.value
+        raise F.ApexError(st, "shard_info")
+    return blk.value, npl.value, n.value
 
 
 def layout_stats(prob: BAProblem, nranks: int = 1, rank: int = 0) -> F.LayoutStats:

@@ -143,6 +143,8 @@ void apex_ctx_destroy(apex_ctx* ctx) {
   cudaSetDevice(c.device);
   if (c.stream) cudaStreamSynchronize(c.stream);
   if (c.pcg_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)c.pcg_graph_exec);
+  release_peer_allreduce(c);
+  c.arbuf.release(); c.arflags.release(); c.d_peer_buf.release(); c.d_peer_flags.release();
   if (c.nccl_comm) nccl_api().CommDestroy((NcclComm)c.nccl_comm);
   DevBuf<double>* dbl[] = {&c.slot_uv, &c.cm_uv, &c.pose, &c.intr, &c.pt, &c.pt_full, &c.J, &c.R, &c.hpp, &c.gp, &c.hinv, &c.hcc, &c.partial,
                            &c.sj, &c.pinv, &c.vb, &c.vx, &c.vr, &c.vz, &c.vp, &c.vy, &c.step_cam, &c.step_pt, &c.red_scratch, &c.S, &c.E,
@@ -172,7 +174,7 @@ apex_status apex_get_dims(const apex_ctx* ctx, apex_dims* out) {
   if (!ctx || !out) return APEX_ERR_INVALID_INPUT;
   const Ctx& c = ctx->c;
   out->ncam = c.ncam; out->npts = c.npts; out->nobs = c.nobs; out->intr_dim = c.K; out->dc = c.dc;
-  out->cam_dof = c.cam_dof_ref; out->lm_dof = 3 * (uint64_t)c.npts; out->npts_local = c.npl; out->reserved = 0; out->nobs_local = c.nobs_local;
+  out->cam_dof = c.cam_dof_ref; out->lm_dof = 3 * (uint64_t)c.npts; out->npts_local = c.npl; out->flags = c.p2p_ok ? 1u : 0u; out->nobs_local = c.nobs_local;
   return APEX_OK;
 }
 
@@ -182,10 +184,22 @@ apex_status apex_params_upload(apex_ctx* ctx, const double* pose, const double* 
   cudaStream_t s = c.stream;
   if (pose) APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pose.p, pose, 7 * (size_t)c.ncam * sizeof(double), cudaMemcpyHostToDevice, s));
   if (intr) APEX_CUDA_TRY(c, cudaMemcpyAsync(c.intr.p, intr, (size_t)c.K * c.ncam * sizeof(double), cudaMemcpyHostToDevice, s));
-  if (pt && c.npl) APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pt.p, pt + 3 * (size_t)c.p0, 3 * (size_t)c.npl * sizeof(double), cudaMemcpyHostToDevice, s));
+  std::vector<double> pt_local;
+  if (pt && c.npl) {
+    pt_local = gather_local_points(c, pt);
+    APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pt.p, pt_local.data(), 3 * (size_t)c.npl * sizeof(double), cudaMemcpyHostToDevice, s));
+  }
   APEX_CUDA_TRY(c, cudaStreamSynchronize(s));
   c.linearized = false;
   return APEX_OK;
+}
+
+// local landmark rows -> their global positions (block-cyclic ownership)
+__global__ void scatter_rows_kernel(const double* __restrict__ local, double* __restrict__ full, uint32_t npl, int w, ShardMap m) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)w * npl) return;
+  const uint32_t lp = (uint32_t)(i / w);
+  full[(size_t)m.to_global(lp) * w + i % w] = local[i];
 }
 
 // landmark-indexed device array of local rows [npl][w] -> host array of all rows [npts][w]
@@ -197,8 +211,10 @@ static apex_status gather_point_rows(Ctx& c, const double* dev_local, int w, dou
     const size_t total = (size_t)w * c.npts;
     APEX_CUDA_TRY(c, c.pt_full.alloc(total));
     APEX_CUDA_TRY(c, cudaMemsetAsync(c.pt_full.p, 0, total * sizeof(double), s));
-    if (c.npl)
-      APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pt_full.p + (size_t)w * c.p0, dev_local, (size_t)w * c.npl * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (c.npl) {
+      scatter_rows_kernel<<<(unsigned)(((size_t)w * c.npl + 255) / 256), 256, 0, s>>>(dev_local, c.pt_full.p, c.npl, w, c.shard);
+      c.launches++;
+    }
     APEX_TRY(allreduce_sum(c, c.pt_full.p, total));
     APEX_CUDA_TRY(c, cudaMemcpyAsync(host_full, c.pt_full.p, total * sizeof(double), cudaMemcpyDeviceToHost, s));
   }
@@ -390,17 +406,19 @@ apex_status apex_layout_stats_compute(const apex_problem_desc* desc, int32_t nra
   return layout_stats(desc, nranks, rank, out, err);
 }
 
-apex_status apex_shard_range(uint32_t npts, uint64_t nobs, const uint32_t* obs_pt, int32_t nranks, int32_t rank, uint32_t* p0, uint32_t* p1,
-                             uint64_t* nobs_local) {
+apex_status apex_shard_info(uint32_t npts, uint64_t nobs, const uint32_t* obs_pt, int32_t nranks, int32_t rank, uint32_t* block,
+                            uint32_t* npts_local, uint64_t* nobs_local) {
   if (!obs_pt && nobs) return APEX_ERR_INVALID_INPUT;
   if (nranks < 1 || rank < 0 || rank >= nranks) return APEX_ERR_INVALID_INPUT;
-  for (uint64_t o = 0; o < nobs; ++o) if (obs_pt[o] >= npts) return APEX_ERR_INVALID_INPUT;
-  std::vector<uint64_t> pt_start;
-  uint32_t a = 0, b = 0;
-  shard_range(npts, nobs, obs_pt, nranks, rank, pt_start, a, b);
-  if (p0) *p0 = a;
-  if (p1) *p1 = b;
-  if (nobs_local) *nobs_local = pt_start[b] - pt_start[a];
+  const ShardMap m{npts, (uint32_t)nranks, (uint32_t)rank};
+  uint64_t mine = 0;
+  for (uint64_t o = 0; o < nobs; ++o) {
+    if (obs_pt[o] >= npts) return APEX_ERR_INVALID_INPUT;
+    mine += m.owns(obs_pt[o]) ? 1 : 0;
+  }
+  if (block) *block = SHARD_BLOCK;
+  if (npts_local) *npts_local = m.count();
+  if (nobs_local) *nobs_local = mine;
   return APEX_OK;
 }
 

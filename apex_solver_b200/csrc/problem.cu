@@ -21,24 +21,6 @@ static cudaError_t upload_vec(DevBuf<T>& buf, const std::vector<T>& v, cudaStrea
   return cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
 }
 
-// Contiguous landmark ranges balanced by observation count; identical on every rank. pt_start receives the
-// exclusive prefix sum of the per-landmark observation counts.
-void shard_range(uint32_t npts, uint64_t nobs, const uint32_t* obs_pt, int nranks, int rank, std::vector<uint64_t>& pt_start, uint32_t& p0,
-                 uint32_t& p1) {
-  pt_start.assign((size_t)npts + 1, 0);
-  for (uint64_t o = 0; o < nobs; ++o) pt_start[obs_pt[o] + 1]++;
-  for (uint32_t p = 0; p < npts; ++p) pt_start[p + 1] += pt_start[p];
-  auto boundary = [&](int r) -> uint32_t {
-    if (r <= 0) return 0;
-    if (r >= nranks) return npts;
-    if (nobs == 0) return (uint32_t)((uint64_t)npts * r / nranks);
-    uint64_t target = nobs * (uint64_t)r / (uint64_t)nranks;
-    return (uint32_t)(std::lower_bound(pt_start.begin(), pt_start.begin() + npts, target) - pt_start.begin());
-  };
-  p0 = boundary(rank);
-  p1 = boundary(rank + 1);
-}
-
 apex_status validate_problem(const apex_problem_desc* d, std::string& err) {
   int K = model_intr_dim(d->camera_model);
   if (K < 0) { err = "camera model not supported on the GPU path"; return APEX_ERR_UNSUPPORTED; }
@@ -61,7 +43,8 @@ apex_status validate_problem(const apex_problem_desc* d, std::string& err) {
 
 // The static structure of one rank's shard, on the host.
 struct HostLayout {
-  uint32_t p0 = 0, p1 = 0, npl = 0;
+  ShardMap shard;
+  uint32_t npl = 0;
   uint64_t nobs_local = 0;
   uint32_t nnormal_chunks = 0, nchunks = 0, npairs = 0;
   std::vector<TileDesc> tiles, giant_tiles;
@@ -83,21 +66,24 @@ struct HostLayout {
 static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostLayout& L) {
   const uint64_t nobs = d->nobs;
   const uint32_t ncam = d->ncam;
-  // ---- landmark sharding ----
-  std::vector<uint64_t> pt_start;
-  shard_range(d->npts, nobs, d->obs_pt, nranks, rank, pt_start, L.p0, L.p1);
-  L.npl = L.p1 - L.p0;
-  L.nobs_local = pt_start[L.p1] - pt_start[L.p0];
+  // ---- landmark sharding (block-cyclic) + point-major order of the local observations (stable in the caller's
+  // insertion order) ----
+  L.shard = ShardMap{d->npts, (uint32_t)nranks, (uint32_t)rank};
+  L.npl = L.shard.count();
   const uint32_t npl = L.npl;
-
-  // ---- point-major order of the local observations (stable in the caller's insertion order) ----
+  std::vector<uint64_t> pt_start((size_t)npl + 1, 0);  // exclusive prefix of the LOCAL landmarks' observation counts
+  for (uint64_t o = 0; o < nobs; ++o) {
+    const uint32_t p = d->obs_pt[o];
+    if (L.shard.owns(p)) pt_start[L.shard.to_local(p) + 1]++;
+  }
+  for (uint32_t lp = 0; lp < npl; ++lp) pt_start[lp + 1] += pt_start[lp];
+  L.nobs_local = pt_start[npl];
   std::vector<uint64_t> pm(L.nobs_local);
   {
-    std::vector<uint64_t> cur(pt_start.begin() + L.p0, pt_start.begin() + L.p1);
-    const uint64_t base = pt_start[L.p0];
+    std::vector<uint64_t> cur(pt_start.begin(), pt_start.end() - 1);
     for (uint64_t o = 0; o < nobs; ++o) {
       const uint32_t p = d->obs_pt[o];
-      if (p >= L.p0 && p < L.p1) pm[cur[p - L.p0]++ - base] = o;
+      if (L.shard.owns(p)) pm[cur[L.shard.to_local(p)]++] = o;
     }
   }
 
@@ -120,7 +106,7 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
       cur_npt = 0; cur_obs = 0;
     };
     for (uint32_t lp = 0; lp < npl; ++lp) {
-      const uint32_t k = (uint32_t)(pt_start[L.p0 + lp + 1] - pt_start[L.p0 + lp]);
+      const uint32_t k = (uint32_t)(pt_start[lp + 1] - pt_start[lp]);
       L.pt_cnt[lp] = k;
       if (k > (uint32_t)TILE) {
         flush();
@@ -241,7 +227,7 @@ apex_status layout_stats(const apex_problem_desc* d, int nranks, int rank, apex_
   HostLayout L;
   build_layout(d, nranks, rank, L);
   out->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  out->p0 = L.p0; out->p1 = L.p1; out->nobs_local = L.nobs_local;
+  out->shard_block = SHARD_BLOCK; out->npts_local = L.npl; out->nobs_local = L.nobs_local;
   out->ntiles = (uint32_t)L.tiles.size(); out->nlong_tiles = (uint32_t)L.giant_tiles.size();
   out->nchunks = L.nchunks; out->nnormal_chunks = L.nnormal_chunks; out->ncam_items = (uint32_t)L.items.size();
   uint64_t nseg = 0, maxseg = 0, covered = 0;
@@ -269,6 +255,16 @@ apex_status layout_stats(const apex_problem_desc* d, int nranks, int rank, apex_
   return APEX_OK;
 }
 
+// rows of the owned landmarks out of a full [npts][3] host array
+std::vector<double> gather_local_points(const Ctx& c, const double* pt_full) {
+  std::vector<double> out((size_t)c.npl * 3);
+  for (uint32_t lp = 0; lp < c.npl; ++lp) {
+    const size_t g = c.shard.to_global(lp);
+    out[3 * (size_t)lp] = pt_full[3 * g]; out[3 * (size_t)lp + 1] = pt_full[3 * g + 1]; out[3 * (size_t)lp + 2] = pt_full[3 * g + 2];
+  }
+  return out;
+}
+
 apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   APEX_TRY(validate_problem(d, c.err));
   const int K = model_intr_dim(d->camera_model);
@@ -287,7 +283,7 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
 
   HostLayout L;
   build_layout(d, c.nranks, c.rank, L);
-  c.p0 = L.p0; c.p1 = L.p1; c.npl = L.npl; c.nobs_local = L.nobs_local;
+  c.shard = L.shard; c.npl = L.npl; c.nobs_local = L.nobs_local;
   c.nnormal_chunks = L.nnormal_chunks; c.nchunks = L.nchunks; c.npairs = L.npairs;
   c.ntiles = (uint32_t)L.tiles.size(); c.ngiant = (uint32_t)L.giant_tiles.size(); c.nitems = (uint32_t)L.items.size();
   c.nslots = (size_t)L.nchunks * TILE;
@@ -299,7 +295,7 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   std::vector<uint16_t> intr_fixed(c.ncam, 0);
   if (d->pose_fixed) std::copy(d->pose_fixed, d->pose_fixed + c.ncam, pose_fixed.begin());
   if (d->intr_fixed) std::copy(d->intr_fixed, d->intr_fixed + c.ncam, intr_fixed.begin());
-  if (d->pt_fixed) std::copy(d->pt_fixed + c.p0, d->pt_fixed + c.p1, pt_fixed.begin());
+  if (d->pt_fixed) for (uint32_t lp = 0; lp < c.npl; ++lp) pt_fixed[lp] = d->pt_fixed[c.shard.to_global(lp)];
 
   // ---- to the device ----
   cudaStream_t s = c.stream;
@@ -355,9 +351,10 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
 
   APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pose.p, d->pose, (size_t)c.ncam * 7 * sizeof(double), cudaMemcpyHostToDevice, s));
   APEX_CUDA_TRY(c, cudaMemcpyAsync(c.intr.p, d->intr, (size_t)c.ncam * K * sizeof(double), cudaMemcpyHostToDevice, s));
-  if (c.npl)
-    APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pt.p, d->pt + 3 * (size_t)c.p0, (size_t)c.npl * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+  std::vector<double> pt_local = gather_local_points(c, d->pt);
+  if (c.npl) APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pt.p, pt_local.data(), (size_t)c.npl * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
   APEX_CUDA_TRY(c, cudaStreamSynchronize(s));  // the host vectors above die with this scope
+  APEX_TRY(setup_peer_allreduce(c, ncd));
   c.have_problem = true;
   return APEX_OK;
 }

@@ -781,6 +781,104 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_pap_kernel(const double* __re
   }
 }
 
+// p = z + beta p, its padded copy, and the start value of the operator result y0 = (H_cc + lambda I) p (add_hcc) or 0,
+// one CTA per PCG_CAMS cameras (pcg_dir_kernel + hcc_apply_kernel in one launch)
+__global__ void __launch_bounds__(PCG_THREADS) pcg_dir_hcc_kernel(const double* __restrict__ z, double* __restrict__ p, double* __restrict__ xpad,
+                                                                  const double* __restrict__ hcc, double* __restrict__ y0, const DevState* st,
+                                                                  uint32_t ncam, int dc, int xs, int add_hcc) {
+  __shared__ double ps[PCG_CAMS * MAX_DC];
+  if (st->pcg_done) return;
+  const uint32_t cam0 = blockIdx.x * PCG_CAMS;
+  const uint32_t nrow = min((uint32_t)PCG_CAMS, ncam - cam0) * dc;
+  const size_t row0 = (size_t)cam0 * dc;
+  const double beta = st->pcg_beta;
+  if (threadIdx.x < nrow) {
+    const size_t row = row0 + threadIdx.x;
+    const double v = beta == 0.0 ? z[row] : z[row] + beta * p[row];
+    p[row] = v;
+    ps[threadIdx.x] = v;
+    const uint32_t lc = threadIdx.x / dc, k = threadIdx.x % dc;
+    xpad[(size_t)(cam0 + lc) * xs + k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < nrow) {
+    double s = 0.0;
+    if (add_hcc) {
+      const uint32_t lc = threadIdx.x / dc, a = threadIdx.x % dc;
+      const double* H = hcc + ((size_t)(cam0 + lc) * dc + a) * dc;
+      const double* pc = ps + lc * dc;
+      s = st->damping * pc[a];
+      for (int b = 0; b < dc; ++b) s += H[b] * pc[b];
+    }
+    y0[row0 + threadIdx.x] = s;
+  }
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Fused all-reduce + dot product over NVLink peer memory (comm.cu): publish "my partial operator result of this
+// iteration is complete" to every peer, wait for theirs, y = sum over ranks of their partial vectors (rank order:
+// bitwise identical everywhere), pAp = p . y with the last-CTA pass of pcg_pap_kernel. The spin is bounded: a peer that
+// never arrives raises st->ar_timeout instead of hanging the GPU.
+__global__ void __launch_bounds__(PCG_THREADS) ar_reduce_pap_kernel(double* const* __restrict__ peer_buf, unsigned long long* const* __restrict__ peer_flags,
+                                                                    const unsigned long long* flags, int par, int nranks, int rank,
+                                                                    const double* __restrict__ p, double* __restrict__ y, double* part, DevState* st,
+                                                                    uint32_t n) {
+  __shared__ double sh[PCG_THREADS];
+  __shared__ bool is_last;
+  if (st->pcg_done) return;
+  const unsigned long long seq = st->ar_seq + 1;  // every CTA reads it before the last CTA (by ticket) advances it
+  if (blockIdx.x == 0 && (int)threadIdx.x < nranks) {
+    __threadfence_system();
+    st_release_sys(peer_flags[threadIdx.x] + rank, seq);
+  }
+  if ((int)threadIdx.x < nranks) {
+    long long spins = 0;
+    while (ld_acquire_sys(flags + threadIdx.x) < seq) {
+      if (++spins > (1ll << 26)) { atomicExch(&st->ar_timeout, 1); break; }
+    }
+  }
+  __syncthreads();
+  const uint32_t i = blockIdx.x * PCG_THREADS + threadIdx.x;
+  double v = 0.0;
+  if (i < n) {
+    double s = 0.0;
+    for (int r = 0; r < nranks; ++r) s += ld_relaxed_sys(peer_buf[r] + (size_t)par * n + i);
+    y[i] = s;
+    v = p[i] * s;
+  }
+  v = block_reduce_sum(v, sh);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = v;
+    __threadfence();
+    is_last = atomicAdd(&st->ticket_a, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double s = 0.0;
+  for (uint32_t b = threadIdx.x; b < gridDim.x; b += PCG_THREADS) s += __ldcg(part + b);
+  s = block_reduce_sum(s, sh);
+  if (threadIdx.x == 0) {
+    st->ticket_a = 0;
+    st->ar_seq = seq;
+    if (fabs(s) < 1e-20) { st->pcg_iters = st->pcg_iters + 1; st->pcg_done = 1; }
+    else st->pcg_alpha = st->rz_old / s;
+  }
+}
+
 // x += alpha p ; r -= alpha Ap ; z = M^-1 r ; last CTA: ||r|| < tol, |rz_old| < 1e-30, beta, iteration count
 __global__ void __launch_bounds__(PCG_THREADS) pcg_update_kernel(const double* __restrict__ ap, const double* __restrict__ pinv,
                                                                  const double* __restrict__ p, double* x, double* r, double* z, double* part,
@@ -1076,14 +1174,36 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
   // captured once per uploaded problem into a CUDA graph (kernels + the NCCL all-reduce) and replayed with one
   // launch: the inner loop is launch-bound on small shards (8 GPUs: ~35 us of kernels per iteration).
   const int BATCH = 10;
+  int it_count = 0;  // iteration index within this solve: selects the half of the peer buffer (BATCH is even)
   auto enqueue_iteration = [&]() -> apex_status {
     const int xs = (c.dc + 1) & ~1;
     const unsigned gp = (n + PCG_THREADS - 1) / PCG_THREADS, gu = (c.ncam + PCG_CAMS - 1) / PCG_CAMS;
-    pcg_dir_kernel<<<(c.ncam * xs + PCG_THREADS - 1) / PCG_THREADS, PCG_THREADS, 0, s>>>(c.vz.p, c.vp.p, c.xpad.p, c.state.p, c.ncam, c.dc, xs);
-    APEX_TRY(schur_operator(c, c.vp.p, c.vy.p, 1, true));
-    pcg_pap_kernel<<<gp, PCG_THREADS, 0, s>>>(c.vp.p, c.vy.p, c.red_scratch.p, c.state.p, n);
+    const int par = it_count++ & 1;
+    if (operator_impl() == 0) {
+      // chunk-kernel path: p / y0 in one kernel, the operator reduces into y0, then (ranks > 1) the peer-memory
+      // all-reduce fused with p.Ap, or NCCL when peer mapping is unavailable
+      double* y0 = c.p2p_ok ? c.arbuf.p + (size_t)par * n : c.vy.p;
+      pcg_dir_hcc_kernel<<<gu, PCG_THREADS, 0, s>>>(c.vz.p, c.vp.p, c.xpad.p, c.hcc.p, y0, c.state.p, c.ncam, c.dc, xs, c.rank == 0 ? 1 : 0);
+      c.launches++;
+      cudaEvent_t* evp = (c.prof && c.ntiles) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
+      if (evp) cudaEventRecord(evp[0], s);
+      APEX_TRY(launch_schur_tiles(c, MODE_MATVEC, c.vp.p, y0, 1, true));
+      if (evp) cudaEventRecord(evp[1], s);
+      if (c.p2p_ok) {
+        ar_reduce_pap_kernel<<<gp, PCG_THREADS, 0, s>>>(c.d_peer_buf.p, c.d_peer_flags.p, c.arflags.p, par, c.nranks, c.rank, c.vp.p, c.vy.p,
+                                                        c.red_scratch.p, c.state.p, n);
+      } else {
+        APEX_TRY(allreduce_sum(c, c.vy.p, n));
+        pcg_pap_kernel<<<gp, PCG_THREADS, 0, s>>>(c.vp.p, c.vy.p, c.red_scratch.p, c.state.p, n);
+      }
+    } else {
+      pcg_dir_kernel<<<(c.ncam * xs + PCG_THREADS - 1) / PCG_THREADS, PCG_THREADS, 0, s>>>(c.vz.p, c.vp.p, c.xpad.p, c.state.p, c.ncam, c.dc, xs);
+      c.launches++;
+      APEX_TRY(schur_operator(c, c.vp.p, c.vy.p, 1, true));
+      pcg_pap_kernel<<<gp, PCG_THREADS, 0, s>>>(c.vp.p, c.vy.p, c.red_scratch.p, c.state.p, n);
+    }
     pcg_update_kernel<<<gu, PCG_THREADS, 0, s>>>(c.vy.p, c.pinv.p, c.vp.p, c.step_cam.p, c.vr.p, c.vz.p, c.red_scratch.p, c.state.p, c.ncam, c.dc, c.K);
-    c.launches += 3;
+    c.launches += 2;
     return APEX_OK;
   };
   const bool use_graph = !c.prof && operator_impl() == 0 && !getenv("APEX_NO_GRAPH") && cg_max_it > 0;
@@ -1093,6 +1213,7 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
     APEX_CUDA_TRY(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     apex_status st = APEX_OK;
     for (int i = 0; i < BATCH && st == APEX_OK; ++i) st = enqueue_iteration();
+    it_count = 0;
     cudaError_t ce = cudaStreamEndCapture(s, &graph);
     c.pcg_graph_launches = c.launches - l0;
     c.launches = l0;
@@ -1121,6 +1242,7 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
   }
   if (cg_max_it <= 0) APEX_TRY(sync_state(c));
   c.last_pcg_iters = c.h_state->pcg_iters;
+  if (c.h_state->ar_timeout) { c.err = "peer all-reduce: a rank never published its partial result"; return APEX_ERR_NCCL; }
   if (c.h_state->singular_landmark) { c.err = "Landmark block singular"; return APEX_ERR_SINGULAR_MATRIX; }
   APEX_TRY(launch_schur_tiles(c, MODE_BACKSUB, c.step_cam.p, nullptr, 0));
   return APEX_OK;

@@ -257,7 +257,7 @@ def main():
                                        f"for_bundle_adjustment preset (lambda0 1e-3), implicit Schur PCG (cg 200 / 1e-6, Schur-Jacobi), convergence tolerances zeroed "
                                        f"to run exactly K iterations",
                            "ncam": prob.ncam, "npts": prob.npts, "nobs": prob.nobs, "cam_dof": prob.ncam * dc,
-                           "parallelism": f"landmarks+observations sharded over {world} rank(s), camera blocks replicated, NCCL all-reduce",
+                           "parallelism": f"landmarks+observations sharded block-cyclically over {world} rank(s), camera blocks replicated; per PCG iteration: " + ("NVLink peer-memory all-reduce fused with p.Ap" if (int(ctx.dims.flags) & 1) else ("NCCL all-reduce" if world > 1 else "no exchange")),
                            "l2": "inputs larger than L2 (Jacobian planes 1.0 GB per operator application vs 126 MB L2), no explicit flush",
                            "pcg_iterations": int(res.linear_iterations), "final_cost": res.final_cost, "initial_cost": res.initial_cost,
                            "accepted_steps": int(res.successful_steps)},

@@ -250,7 +250,7 @@ typedef struct apex_dims {
   uint64_t cam_dof;    /* rows of S in the reference layout (includes unreferenced intr columns) */
   uint64_t lm_dof;     /* 3*npts                                                          */
   uint32_t npts_local; /* points owned by this rank                                        */
-  uint32_t reserved;
+  uint32_t flags;      /* bit 0: the NVLink peer-memory all-reduce is active (nranks > 1)  */
   uint64_t nobs_local;
 } apex_dims;
 
@@ -336,17 +336,17 @@ typedef struct apex_profile {
 apex_status apex_profile_enable(apex_ctx* ctx, int32_t on);
 apex_status apex_profile_read(apex_ctx* ctx, apex_profile* out);
 
-/* Host-only: the landmark range [p0,p1) and observation count rank `rank` of `nranks` owns for this observation
- * list - the sharding rule apex_problem_upload applies (contiguous landmark ranges balanced by observations).
- * Needs no device; lets multi-process host logic be tested without a GPU. */
-apex_status apex_shard_range(uint32_t npts, uint64_t nobs, const uint32_t* obs_pt, int32_t nranks, int32_t rank,
-                             uint32_t* p0, uint32_t* p1, uint64_t* nobs_local);
+/* Host-only: the sharding rule apex_problem_upload applies. Landmarks are owned block-cyclically: landmark p belongs to
+ * rank (p / block) % nranks (so every rank sees every camera neighbourhood of a locality-ordered reconstruction); every
+ * observation lives with its landmark. Returns the block size and what `rank` owns. Needs no device. */
+apex_status apex_shard_info(uint32_t npts, uint64_t nobs, const uint32_t* obs_pt, int32_t nranks, int32_t rank,
+                            uint32_t* block, uint32_t* npts_local, uint64_t* nobs_local);
 
 /* Host-only: build the static observation layout apex_problem_upload would build for (nranks, rank) - landmark
  * shard, 256-slot point-major chunks, per-chunk camera segments, camera-major work items - check its invariants
  * and report its size. Needs no device. */
 typedef struct apex_layout_stats {
-  uint32_t p0, p1;                 /* landmark range of the rank                                  */
+  uint32_t shard_block, npts_local; /* block-cyclic ownership: block size, landmarks owned by the rank */
   uint64_t nobs_local;
   uint32_t ntiles, nlong_tiles;    /* tiles; tiles holding one landmark with more than 256 observations */
   uint32_t nchunks, nnormal_chunks;

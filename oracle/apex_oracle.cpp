@@ -1578,7 +1578,7 @@ apex_status oracle_problem_upload(oracle_ctx* ctx, const apex_problem_desc* d) {
 apex_status oracle_get_dims(const oracle_ctx* ctx, apex_dims* out) {
   const Ctx& c = ctx->c;
   out->ncam = c.ncam; out->npts = c.npts; out->nobs = c.nobs; out->intr_dim = c.K; out->dc = c.dc;
-  out->cam_dof = c.cam_dof; out->lm_dof = c.lm_dof; out->npts_local = c.npts; out->reserved = 0; out->nobs_local = c.nobs;
+  out->cam_dof = c.cam_dof; out->lm_dof = c.lm_dof; out->npts_local = c.npts; out->flags = 0; out->nobs_local = c.nobs;
   return APEX_OK;
 }
 

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from apex_solver_b200 import _ffi as F, synth
-from apex_solver_b200.context import BAProblem, GpuContext, layout_stats, shard_range
+from apex_solver_b200.context import BAProblem, GpuContext, layout_stats, shard_info
 from oracle_backend import OracleContext, oracle_lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -68,20 +68,20 @@ def test_no_device_means_error_not_fallback():
     assert e.value.status == F.ERR_NO_DEVICE
 
 
-def test_shard_range_covers_and_balances():
+def test_block_cyclic_sharding_covers_and_balances():
     prob = synth.make_problem(20, 3000, 5.0, seed=2)
+    cnt = np.bincount(prob.obs_pt, minlength=prob.npts)
     for nranks in (1, 2, 3, 8):
-        parts = [shard_range(prob.obs_pt, prob.npts, nranks, r) for r in range(nranks)]
-        assert parts[0][0] == 0 and parts[-1][1] == prob.npts
-        for a, b in zip(parts, parts[1:]):
-            assert a[1] == b[0], "ranges are contiguous"
-        assert sum(p[2] for p in parts) == prob.nobs
-        cnt = np.bincount(prob.obs_pt, minlength=prob.npts)
-        for p0, p1, n in parts:
-            assert n == cnt[p0:p1].sum()
-            assert abs(n - prob.nobs / nranks) <= cnt.max() + 1, "balanced by observations up to one track"
+        parts = [shard_info(prob.obs_pt, prob.npts, nranks, r) for r in range(nranks)]
+        block = parts[0][0]
+        assert all(p[0] == block for p in parts) and block == 128
+        owner = (np.arange(prob.npts) // block) % nranks
+        assert sum(p[1] for p in parts) == prob.npts and sum(p[2] for p in parts) == prob.nobs
+        for r, (_, npl, n) in enumerate(parts):
+            assert npl == int((owner == r).sum()) and n == int(cnt[owner == r].sum())
+            assert abs(n - prob.nobs / nranks) <= 0.2 * prob.nobs / nranks + cnt.max() * block, "balanced by observations"
     with pytest.raises(F.ApexError):
-        shard_range(prob.obs_pt, prob.npts, 2, 2)
+        shard_info(prob.obs_pt, prob.npts, 2, 2)
 
 
 def test_layout_invariants_incl_long_tracks_and_unobserved_landmarks():
@@ -103,7 +103,7 @@ def test_layout_invariants_incl_long_tracks_and_unobserved_landmarks():
         sr = layout_stats(p2, 4, r)
         assert sr.consistent == 1
         total += sr.nobs_local
-        assert (sr.p0, sr.p1, sr.nobs_local) == shard_range(p2.obs_pt, p2.npts, 4, r)
+        assert (sr.shard_block, sr.npts_local, sr.nobs_local) == shard_info(p2.obs_pt, p2.npts, 4, r)
     assert total == p2.nobs
     bad = BAProblem(camera_model=prob.camera_model, opt_flags=prob.opt_flags, pose=prob.pose, intr=prob.intr, pt=prob.pt,
                     obs_cam=np.array([999], np.uint32), obs_pt=np.array([0], np.uint32), obs_uv=np.zeros((1, 2)))
@@ -198,7 +198,7 @@ import os, sys
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
 import numpy as np, torch, torch.distributed as dist
 from apex_solver_b200 import synth
-from apex_solver_b200.context import shard_range
+from apex_solver_b200.context import shard_info
 from oracle_backend import OracleContext
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -208,9 +208,16 @@ lam = 1e-3
 o.linearize(lam)
 n = prob.ncam * prob.dc
 x = np.random.default_rng(1).standard_normal(n)
-p0, p1, nloc = shard_range(prob.obs_pt, prob.npts, world, rank)
-# what one rank of the GPU path computes: the H_cc term once (rank 0) + its landmarks' part of -H_cp Hpp^-1 H_cp^T x
-y = torch.from_numpy(o.schur_matvec_partial(x, p0, p1, rank == 0).copy())
+block, npl, nloc = shard_info(prob.obs_pt, prob.npts, world, rank)
+# what one rank of the GPU path computes: the H_cc term once (rank 0) + its landmark blocks' part of -H_cp Hpp^-1 H_cp^T x
+ysum = np.zeros(n)
+first = True
+for b0 in range(rank * block, prob.npts, world * block):      # block-cyclic ownership
+    ysum += o.schur_matvec_partial(x, b0, min(b0 + block, prob.npts), first and rank == 0)
+    first = False
+if first and rank == 0:
+    ysum += o.schur_matvec_partial(x, 0, 0, True)
+y = torch.from_numpy(ysum.copy())
 dist.all_reduce(y)            # the single exchange step of the operator (ncam*dc doubles)
 full = o.schur_matvec(x)
 err = float(np.abs(y.numpy() - full).max() / np.abs(full).max())
