@@ -199,27 +199,19 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// trailing update A22 -= L21 L21^T on 64x64 tiles of the lower block triangle; 4 warps, each a 32x32
-// sub-tile = 4x4 DMMA.8x8x4 accumulators; the two 64x64 panel tiles are staged in shared memory.
-__global__ void __launch_bounds__(128) chol_syrk_kernel(double* A, size_t ld, uint32_t k0) {
+// Trailing update  A[r0+.., c0+..] -= L[.., k0..k0+kdepth) L[.., k0..k0+kdepth)^T  on 64x64 tiles of the lower block
+// triangle: tile (bi, bj) = rows r0+64*bi, columns r0+64*bj, bi >= bj, bj < ncol_tiles. 4 warps, each a 32x32 sub-tile =
+// 4x4 DMMA.8x8x4 accumulators kept in registers across the whole k depth (the C tile is read and written once per
+// call, which is what makes the two-level blocking of dense_cholesky pay); the two 64x64 panel tiles of each 64-wide
+// k slice are staged in shared memory.
+__global__ void __launch_bounds__(128) chol_syrk_kernel(double* A, size_t ld, uint32_t k0, uint32_t kdepth, uint32_t r0) {
   extern __shared__ double smem[];
   double* Pa = smem;
   double* Pb = smem + NB * PLD;
-  const uint32_t t = blockIdx.x;
-  uint32_t bi = (uint32_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-  while ((uint64_t)bi * (bi + 1) / 2 > t) --bi;
-  while ((uint64_t)(bi + 1) * (bi + 2) / 2 <= t) ++bi;
-  const uint32_t bj = t - (uint32_t)((uint64_t)bi * (bi + 1) / 2);
-  const size_t ri = (size_t)k0 + NB + (size_t)bi * NB, rj = (size_t)k0 + NB + (size_t)bj * NB;
+  const uint32_t bi = blockIdx.x, bj = blockIdx.y;
+  if (bi < bj) return;
+  const size_t ri = (size_t)r0 + (size_t)bi * NB, rj = (size_t)r0 + (size_t)bj * NB;
   const int tid = threadIdx.x;
-  for (int e = tid; e < NB * NB / 2; e += 128) {
-    const int r = e / (NB / 2), c2 = (e % (NB / 2)) * 2;
-    const double2 va = *reinterpret_cast<const double2*>(A + (ri + r) * ld + k0 + c2);
-    Pa[r * PLD + c2] = va.x; Pa[r * PLD + c2 + 1] = va.y;
-    const double2 vb = *reinterpret_cast<const double2*>(A + (rj + r) * ld + k0 + c2);
-    Pb[r * PLD + c2] = vb.x; Pb[r * PLD + c2 + 1] = vb.y;
-  }
-  __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
   const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
   const int lr = lane >> 2, lc = lane & 3;
@@ -228,17 +220,28 @@ __global__ void __launch_bounds__(128) chol_syrk_kernel(double* A, size_t ld, ui
   for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+  for (uint32_t kc = 0; kc < kdepth; kc += NB) {
+    if (kc) __syncthreads();
+    for (int e = tid; e < NB * NB / 2; e += 128) {
+      const int r = e / (NB / 2), c2 = (e % (NB / 2)) * 2;
+      const double2 va = *reinterpret_cast<const double2*>(A + (ri + r) * ld + k0 + kc + c2);
+      Pa[r * PLD + c2] = va.x; Pa[r * PLD + c2 + 1] = va.y;
+      const double2 vb = *reinterpret_cast<const double2*>(A + (rj + r) * ld + k0 + kc + c2);
+      Pb[r * PLD + c2] = vb.x; Pb[r * PLD + c2 + 1] = vb.y;
+    }
+    __syncthreads();
 #pragma unroll 4
-  for (int kk = 0; kk < NB; kk += 4) {
-    double af[4], bf[4];
+    for (int kk = 0; kk < NB; kk += 4) {
+      double af[4], bf[4];
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi) af[mi] = Pa[(wm + mi * 8 + lr) * PLD + kk + lc];
+      for (int mi = 0; mi < 4; ++mi) af[mi] = Pa[(wm + mi * 8 + lr) * PLD + kk + lc];
 #pragma unroll
-    for (int ni = 0; ni < 4; ++ni) bf[ni] = Pb[(wn + ni * 8 + lr) * PLD + kk + lc];
+      for (int ni = 0; ni < 4; ++ni) bf[ni] = Pb[(wn + ni * 8 + lr) * PLD + kk + lc];
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
+      for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        for (int ni = 0; ni < 4; ++ni) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+    }
   }
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi)
@@ -419,16 +422,32 @@ static apex_status dense_cholesky(Ctx& c, double* L, uint32_t npad) {
     APEX_CUDA_TRY(c, cudaFuncSetAttribute(chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_smem_bytes));
     attr_set = true;
   }
+  // Two-level right-looking blocking. Outer panels of NBO = 256 columns: inside a panel the 64-wide steps update only
+  // the panel's own remaining columns (all rows below); the matrix to the right of the panel is then updated ONCE with
+  // k depth 256, so every trailing tile is read and written n/256 times instead of n/64 times (the 64-deep update is
+  // bound by that HBM traffic, not by the FP64 tensor pipe).
+  const uint32_t NBO = 4 * NB;
   const uint32_t nblk = npad / NB;
-  for (uint32_t kb = 0; kb < nblk; ++kb) {
-    const uint32_t k0 = kb * NB;
-    chol_potrf_kernel<<<1, 256, 0, s>>>(L, ld, k0, c.state.p);
-    c.launches++;
-    const uint32_t rem = nblk - kb - 1;
-    if (rem == 0) break;
-    chol_trsm_kernel<<<rem, 256, trsm_smem_bytes, s>>>(L, ld, k0);
-    chol_syrk_kernel<<<tri_count(rem), 128, smem, s>>>(L, ld, k0);
-    c.launches += 2;
+  for (uint32_t ko = 0; ko < npad; ko += NBO) {
+    const uint32_t kend = std::min(ko + NBO, npad);
+    for (uint32_t k0 = ko; k0 < kend; k0 += NB) {
+      chol_potrf_kernel<<<1, 256, 0, s>>>(L, ld, k0, c.state.p);
+      c.launches++;
+      const uint32_t rem = nblk - k0 / NB - 1;  // 64-row blocks below the diagonal block
+      if (rem == 0) break;
+      chol_trsm_kernel<<<rem, 256, trsm_smem_bytes, s>>>(L, ld, k0);
+      c.launches++;
+      const uint32_t ncol = (kend - k0) / NB - 1;  // panel column tiles still to update
+      if (ncol) {
+        chol_syrk_kernel<<<dim3(rem, ncol), 128, smem, s>>>(L, ld, k0, NB, k0 + NB);
+        c.launches++;
+      }
+    }
+    if (kend < npad) {
+      const uint32_t rem = (npad - kend) / NB;
+      chol_syrk_kernel<<<dim3(rem, rem), 128, smem, s>>>(L, ld, ko, kend - ko, kend);
+      c.launches++;
+    }
   }
   APEX_CUDA_TRY(c, cudaGetLastError());
   return APEX_OK;
