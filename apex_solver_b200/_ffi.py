@@ -124,7 +124,8 @@ class Profile(C.Structure):
 class LayoutStats(C.Structure):
     _fields_ = [("shard_block", C.c_uint32), ("npts_local", C.c_uint32), ("nobs_local", C.c_uint64), ("ntiles", C.c_uint32), ("nlong_tiles", C.c_uint32),
                 ("nchunks", C.c_uint32), ("nnormal_chunks", C.c_uint32), ("ncam_items", C.c_uint32), ("max_segments_per_chunk", C.c_uint32),
-                ("nsegments", C.c_uint64), ("slots_used", C.c_uint64), ("consistent", C.c_int32), ("reserved", C.c_int32), ("build_ms", C.c_double)]
+                ("nsegments", C.c_uint64), ("slots_used", C.c_uint64), ("consistent", C.c_int32), ("reserved", C.c_int32), ("build_ms", C.c_double),
+                ("mv_group", C.c_uint32), ("mv_window", C.c_uint32), ("mv_ngroups", C.c_uint32), ("reserved2", C.c_uint32), ("nobs_in_window", C.c_uint64)]
 
 
 class Dims(C.Structure):

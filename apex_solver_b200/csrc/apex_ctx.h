@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -33,6 +34,8 @@ constexpr uint32_t PAD_CAM = 0xFFFFFFFFu;
 constexpr int CAM_THREADS = 128;     // CTA size of the camera-major accumulation kernels
 constexpr int CAM_CHUNK = 2048;      // observations per camera work item
 constexpr int MAX_DC = 14;
+// per-camera stride (doubles) of the padded copy of the operator input: 32-byte aligned blocks for 256-bit gathers
+__host__ __device__ constexpr int xpad_stride(int dc) { return (dc + 3) & ~3; }
 constexpr int MAX_K = 8;
 
 struct TileDesc {
@@ -66,8 +69,20 @@ struct ShardMap {
     return (mine - 1) * SHARD_BLOCK + last_size;
   }
 };
-constexpr int CSEG_LD = TILE + 2;     // u16 entries per chunk in cseg_begin (sentinel + padding to a 4-byte multiple)
+constexpr int CSEG_LD = TILE + 8;     // u16 entries per chunk in cseg_begin (sentinel + padding to a 16-byte multiple: bulk copies)
 constexpr int MAX_TILE_PTS = 128;     // landmarks per normal tile (so a supertile stages <= 256 landmark inverses)
+
+// Window kernel of the Schur operator (schur.cu): shared memory of one CTA besides the two camera windows, and the
+// window width that still lets three CTAs share an SM ((228 KB - 3 x 1 KB reserved) / 3 = 76 800 B each).
+inline size_t mv_window_base_bytes(int dc) {
+  return sizeof(double) * ((size_t)dc * (TILE + 1) + 9 * MAX_TILE_PTS) + 4 * MAX_TILE_PTS + 4 * TILE + ((2 * CSEG_LD + 15) & ~15);
+}
+inline uint32_t mv_window_cameras(int dc, uint32_t ncam) {
+  const size_t budget = 76800, base = mv_window_base_bytes(dc);
+  size_t w = base < budget ? (budget - base) / (16 * (size_t)dc) : 0;
+  w &= ~(size_t)7;
+  return (uint32_t)(w < ncam ? w : ncam);
+}
 
 struct CamItem { uint32_t cam, begin, end, pad; };  // [begin,end) in the camera-major arrays
 
@@ -96,6 +111,19 @@ struct DevState {
   int32_t chol_fail;                      // first failing column + 1 of the dense Cholesky
   int32_t pad2[2];
 };
+
+// Host vector whose resize() leaves trivially constructible elements uninitialised: the layout build fills the big
+// per-slot arrays from OpenMP workers (parallel first touch) instead of zero-filling 230 MB on one thread first.
+template <typename T>
+struct NoInitAlloc : std::allocator<T> {
+  template <typename U> struct rebind { using other = NoInitAlloc<U>; };
+  template <typename U, typename... A>
+  void construct(U* p, A&&... a) {
+    if constexpr (sizeof...(A) == 0) ::new (static_cast<void*>(p)) U;
+    else ::new (static_cast<void*>(p)) U(static_cast<A&&>(a)...);
+  }
+};
+template <typename T> using HostVec = std::vector<T, NoInitAlloc<T>>;
 
 template <typename T>
 struct DevBuf {
@@ -138,7 +166,7 @@ struct Ctx {
   uint32_t nchunks = 0, ntiles = 0, nitems = 0;
   uint32_t npairs = 0, ngiant = 0, nnormal_chunks = 0;  // npairs: chunk pairs (2s, 2s+1) walked by the operator kernel
   size_t nslots = 0;
-  std::vector<uint64_t> slot_obs;  // slot -> caller's observation index (UINT64_MAX for padding)
+  HostVec<uint64_t> slot_obs;      // slot -> caller's observation index (UINT64_MAX for padding)
   std::vector<uint32_t> h_pt_cnt;
 
   // ---- device: static structure ----
@@ -152,6 +180,8 @@ struct Ctx {
   DevBuf<uint32_t> cseg_cam;         // [chunk][256]
   DevBuf<uint16_t> cseg_begin;       // [chunk][CSEG_LD]
   DevBuf<double> xpad;               // operator input at an even per-camera stride
+  uint32_t mv_G = 0, mv_W = 0, mv_ngroups = 0;  // window kernel: chunks per group, cameras per window (0 = chunk kernel), groups
+  DevBuf<uint32_t> grp_win0;         // [mv_ngroups] first camera of each group's window
   DevBuf<double> ypart;              // [grid][ncam*dc] per-CTA private results of the persistent operator kernel
   DevBuf<double> slot_uv;            // [chunk][2][TILE]
   DevBuf<uint32_t> pt_slot0, pt_cnt; // per local landmark

@@ -5,16 +5,19 @@
 // build_layout() is pure host code (OpenMP over tiles) so it can be exercised without a device.
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <omp.h>
 
 #include "apex_ctx.h"
 #include "ba_device.cuh"
 
 namespace apex {
 
-template <typename T>
-static cudaError_t upload_vec(DevBuf<T>& buf, const std::vector<T>& v, cudaStream_t s) {
+template <typename T, typename A>
+static cudaError_t upload_vec(DevBuf<T>& buf, const std::vector<T, A>& v, cudaStream_t s) {
   cudaError_t e = buf.alloc(v.size());
   if (e != cudaSuccess) return e;
   if (v.empty()) return cudaSuccess;
@@ -49,21 +52,70 @@ struct HostLayout {
   uint32_t nnormal_chunks = 0, nchunks = 0, npairs = 0;
   std::vector<TileDesc> tiles, giant_tiles;
   std::vector<uint32_t> pt_slot0, pt_cnt;
-  std::vector<uint32_t> slot_cam;
-  std::vector<uint16_t> slot_lp;
-  std::vector<double> slot_uv;
-  std::vector<uint64_t> slot_obs;
+  HostVec<uint32_t> slot_cam;
+  HostVec<uint16_t> slot_lp;
+  HostVec<double> slot_uv;
+  HostVec<uint64_t> slot_obs;
   std::vector<ChunkDesc> chunk_desc;
-  std::vector<uint2> cslot_meta;
-  std::vector<uint32_t> cpt_meta, cseg_cam;
-  std::vector<uint16_t> cseg_begin;
-  std::vector<double> cm_uv;
-  std::vector<uint32_t> cm_lp;
+  HostVec<uint2> cslot_meta;
+  std::vector<uint32_t> cpt_meta;
+  HostVec<uint32_t> cseg_cam;
+  HostVec<uint16_t> cseg_begin;
+  HostVec<double> cm_uv;
+  HostVec<uint32_t> cm_lp;
   std::vector<CamItem> items;
   std::vector<uint32_t> cam_item_start;
+  uint32_t mv_G = 0, mv_W = 0;
+  std::vector<uint32_t> grp_win0;
 };
 
-static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostLayout& L) {
+// Camera window of every group of G consecutive normal chunks (window kernel of the Schur operator): the run of W
+// consecutive cameras, modulo ncam, that holds the most observations of the group.
+static void build_windows(HostLayout& L, uint32_t ncam, uint32_t G, uint32_t W) {
+  L.mv_G = G; L.mv_W = W;
+  L.grp_win0.clear();
+  if (!G || !W || !L.nnormal_chunks) { L.mv_G = L.mv_W = 0; return; }
+  const uint32_t ngroups = (L.nnormal_chunks + G - 1) / G;
+  L.grp_win0.assign(ngroups, 0);
+  if (W >= ncam) return;  // every camera fits: window = [0, ncam)
+#pragma omp parallel
+  {
+    std::vector<int64_t> off;
+#pragma omp for schedule(dynamic, 16)
+    for (int64_t g = 0; g < (int64_t)ngroups; ++g) {
+      const size_t s0 = (size_t)g * G * TILE, s1 = std::min<size_t>((size_t)(g + 1) * G, L.nnormal_chunks) * TILE;
+      off.clear();
+      int64_t ref = -1;
+      const int64_t half = ncam / 2;
+      for (size_t s = s0; s < s1; ++s) {
+        const uint32_t cam = L.cslot_meta[s].x;
+        if (cam == PAD_CAM) continue;
+        if (ref < 0) ref = cam;
+        off.push_back((((int64_t)cam - ref + half) % ncam + ncam) % ncam - half);  // circular offset in [-ncam/2, ncam/2)
+      }
+      if (off.empty()) continue;
+      std::sort(off.begin(), off.end());
+      size_t best = 0, best_i = 0, j = 0;
+      for (size_t i = 0; i < off.size(); ++i) {
+        if (i && off[i] == off[i - 1]) continue;
+        if (j < i) j = i;
+        while (j < off.size() && off[j] < off[i] + (int64_t)W) ++j;
+        if (j - i > best) { best = j - i; best_i = i; }
+      }
+      L.grp_win0[g] = (uint32_t)(((ref + off[best_i]) % ncam + ncam) % ncam);
+    }
+  }
+}
+
+static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostLayout& L, int dc) {
+  const bool timing = getenv("APEX_LAYOUT_TIMING") != nullptr;
+  auto tprev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[layout] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tprev).count());
+    tprev = now;
+  };
   const uint64_t nobs = d->nobs;
   const uint32_t ncam = d->ncam;
   // ---- landmark sharding (block-cyclic) + point-major order of the local observations (stable in the caller's
@@ -71,22 +123,53 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
   L.shard = ShardMap{d->npts, (uint32_t)nranks, (uint32_t)rank};
   L.npl = L.shard.count();
   const uint32_t npl = L.npl;
+  // Stable counting sort by local landmark, in parallel: the observation list is cut into T contiguous pieces, piece t
+  // counts its observations per landmark, a prefix over (landmark, piece) gives every piece its write cursor.
   std::vector<uint64_t> pt_start((size_t)npl + 1, 0);  // exclusive prefix of the LOCAL landmarks' observation counts
-  for (uint64_t o = 0; o < nobs; ++o) {
-    const uint32_t p = d->obs_pt[o];
-    if (L.shard.owns(p)) pt_start[L.shard.to_local(p) + 1]++;
-  }
-  for (uint32_t lp = 0; lp < npl; ++lp) pt_start[lp + 1] += pt_start[lp];
-  L.nobs_local = pt_start[npl];
-  std::vector<uint64_t> pm(L.nobs_local);
+  HostVec<uint64_t> pm;
   {
-    std::vector<uint64_t> cur(pt_start.begin(), pt_start.end() - 1);
-    for (uint64_t o = 0; o < nobs; ++o) {
-      const uint32_t p = d->obs_pt[o];
-      if (L.shard.owns(p)) pm[cur[L.shard.to_local(p)]++] = o;
+    int T = std::max(1, std::min(omp_get_max_threads(), 16));
+    while (T > 1 && (size_t)T * npl * sizeof(uint32_t) > ((size_t)1 << 30)) T /= 2;  // counters: at most 1 GiB
+    if (nobs < 100000) T = 1;
+    std::vector<HostVec<uint32_t>> cnt(T);
+    auto piece = [&](int t) { return std::make_pair(nobs * (uint64_t)t / T, nobs * (uint64_t)(t + 1) / T); };
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+    for (int t = 0; t < T; ++t) {
+      cnt[t].resize(npl);
+      std::fill(cnt[t].begin(), cnt[t].end(), 0u);
+      const auto [o0, o1] = piece(t);
+      for (uint64_t o = o0; o < o1; ++o) {
+        const uint32_t p = d->obs_pt[o];
+        if (L.shard.owns(p)) cnt[t][L.shard.to_local(p)]++;
+      }
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t lp = 0; lp < (int64_t)npl; ++lp) {
+      uint64_t k = 0;
+      for (int t = 0; t < T; ++t) k += cnt[t][lp];
+      pt_start[lp + 1] = k;
+    }
+    for (uint32_t lp = 0; lp < npl; ++lp) pt_start[lp + 1] += pt_start[lp];
+    L.nobs_local = pt_start[npl];
+    pm.resize(L.nobs_local);
+#pragma omp parallel for schedule(static)
+    for (int64_t lp = 0; lp < (int64_t)npl; ++lp) {  // counts -> cursors relative to pt_start (fits u32: nobs < 2^32)
+      uint32_t run = 0;
+      for (int t = 0; t < T; ++t) { const uint32_t k = cnt[t][lp]; cnt[t][lp] = run; run += k; }
+    }
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+    for (int t = 0; t < T; ++t) {
+      const auto [o0, o1] = piece(t);
+      for (uint64_t o = o0; o < o1; ++o) {
+        const uint32_t p = d->obs_pt[o];
+        if (!L.shard.owns(p)) continue;
+        const uint32_t lp = L.shard.to_local(p);
+        pm[pt_start[lp] + cnt[t][lp]++] = o;
+      }
     }
   }
 
+  lap("point-major order");
   // ---- tiles ----
   // Normal tiles (<=256 observations, <=128 landmarks) get chunk ids 0..nn-1 in landmark order so that the
   // operator kernel's two thread groups can take chunks (2s, 2s+1); landmarks with more than 256 observations get
@@ -137,17 +220,32 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
   const uint32_t nchunk_even = (L.nnormal_chunks + 1) & ~1u;
   L.npairs = nchunk_even / 2;
 
+  lap("tiles");
   // ---- slot arrays + per-chunk camera-sorted segment structure (parallel over tiles) ----
-  L.slot_cam.assign(nslots, PAD_CAM);
-  L.slot_lp.assign(nslots, 0);
-  L.slot_uv.assign(nslots * 2, 0.0);
-  L.slot_obs.assign(nslots, UINT64_MAX);
+  // (uninitialised here; every chunk is filled with its padding defaults by the worker that builds it)
+  L.slot_cam.resize(nslots);
+  L.slot_lp.resize(nslots);
+  L.slot_uv.resize(nslots * 2);
+  L.slot_obs.resize(nslots);
   L.chunk_desc.assign(nchunk_even, ChunkDesc{0, 0, 0, 0});
-  L.cslot_meta.assign((size_t)nchunk_even * TILE, make_uint2(PAD_CAM, 0));
+  L.cslot_meta.resize((size_t)nchunk_even * TILE);
   L.cpt_meta.assign(npl, 0);
-  L.cseg_cam.assign((size_t)nchunk_even * TILE, 0);
-  L.cseg_begin.assign((size_t)nchunk_even * CSEG_LD, 0);
+  L.cseg_cam.resize((size_t)nchunk_even * TILE);
+  L.cseg_begin.resize((size_t)nchunk_even * CSEG_LD);
+  auto clear_chunk = [&](size_t ch) {
+    std::fill_n(L.slot_cam.begin() + ch * TILE, TILE, PAD_CAM);
+    std::fill_n(L.slot_lp.begin() + ch * TILE, TILE, (uint16_t)0);
+    std::fill_n(L.slot_uv.begin() + ch * 2 * TILE, 2 * TILE, 0.0);
+    std::fill_n(L.slot_obs.begin() + ch * TILE, TILE, UINT64_MAX);
+  };
+  auto clear_tables = [&](size_t ch) {
+    std::fill_n(L.cslot_meta.begin() + ch * TILE, TILE, make_uint2(PAD_CAM, 0));
+    std::fill_n(L.cseg_cam.begin() + ch * TILE, TILE, 0u);
+    std::fill_n(L.cseg_begin.begin() + ch * CSEG_LD, CSEG_LD, (uint16_t)0);
+  };
+  for (size_t ch = L.nnormal_chunks; ch < nchunk_even; ++ch) clear_tables(ch);  // the odd chunk of the last pair
   const int64_t ntiles = (int64_t)L.tiles.size();
+  lap("slot array allocation");
 #pragma omp parallel
   {
     std::vector<std::pair<uint32_t, uint32_t>> order;  // (camera, chunk-local slot)
@@ -156,6 +254,8 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
       const TileDesc& t = L.tiles[ti];
       uint64_t q = tile_q0[ti];
       order.clear();
+      for (uint32_t ch = t.chunk0; ch < t.chunk0 + t.nchunks; ++ch) clear_chunk(ch);
+      if (t.nchunks == 1) clear_tables(t.chunk0);
       for (uint32_t i = 0; i < t.npt; ++i) {
         const uint32_t lp = t.pt0 + i;
         const uint32_t off = L.pt_slot0[lp] - t.chunk0 * TILE;
@@ -194,23 +294,50 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
     }
   }
 
+  lap("slots + segments");
+  // ---- camera windows of the operator's chunk groups ----
+  {
+    const char* eg = getenv("APEX_MV_GROUP");
+    const char* ew = getenv("APEX_MV_WINDOW");
+    const uint32_t G = eg ? (uint32_t)std::max(0, atoi(eg)) : 8u;
+    // opt-in (APEX_MV_WINDOW = cameras per window): measured slower than the chunk kernel
+    const uint32_t W = ew ? std::min<uint32_t>(mv_window_cameras(dc, ncam), (uint32_t)std::max(0, atoi(ew))) : 0u;
+    build_windows(L, ncam, G, W);
+  }
+
   // ---- camera-major copy of the local observations + work items ----
+  // Stable counting sort by camera of the point-major list, in parallel over contiguous pieces of that list.
   std::vector<uint32_t> cam_start((size_t)ncam + 1, 0);
-  for (uint64_t q = 0; q < L.nobs_local; ++q) cam_start[d->obs_cam[pm[q]] + 1]++;
-  for (uint32_t k = 0; k < ncam; ++k) cam_start[k + 1] += cam_start[k];
   L.cm_uv.resize(2 * (size_t)L.nobs_local);
   L.cm_lp.resize(L.nobs_local);
   {
-    std::vector<uint32_t> cur(cam_start.begin(), cam_start.end() - 1);
-    uint64_t q = 0;
-    for (uint32_t lp = 0; lp < npl; ++lp)
-      for (uint32_t k = 0; k < L.pt_cnt[lp]; ++k, ++q) {
-        const uint64_t o = pm[q];
-        const uint32_t pos = cur[d->obs_cam[o]]++;
-        L.cm_uv[pos] = d->obs_uv[2 * o];
-        L.cm_uv[(size_t)L.nobs_local + pos] = d->obs_uv[2 * o + 1];
-        L.cm_lp[pos] = lp;
-      }
+    const int T = L.nobs_local < 100000 ? 1 : std::max(1, std::min(omp_get_max_threads(), 64));
+    std::vector<std::vector<uint32_t>> cnt(T, std::vector<uint32_t>(ncam, 0));
+    std::vector<uint32_t> lp_cut(T + 1, npl);  // piece t = landmarks [lp_cut[t], lp_cut[t+1]), balanced by observations
+    lp_cut[0] = 0;
+    for (int t = 1; t < T; ++t)
+      lp_cut[t] = (uint32_t)(std::lower_bound(pt_start.begin(), pt_start.end(), L.nobs_local * (uint64_t)t / T) - pt_start.begin());
+    for (int t = 1; t <= T; ++t) lp_cut[t] = std::max(lp_cut[t], lp_cut[t - 1]);
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+    for (int t = 0; t < T; ++t)
+      for (uint64_t q = pt_start[lp_cut[t]]; q < pt_start[lp_cut[t + 1]]; ++q) cnt[t][d->obs_cam[pm[q]]]++;
+    for (uint32_t k = 0; k < ncam; ++k) {
+      uint32_t run = cam_start[k];
+      for (int t = 0; t < T; ++t) { const uint32_t n = cnt[t][k]; cnt[t][k] = run; run += n; }
+      cam_start[k + 1] = run;
+    }
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+    for (int t = 0; t < T; ++t) {
+      uint64_t q = pt_start[lp_cut[t]];
+      for (uint32_t lp = lp_cut[t]; lp < lp_cut[t + 1]; ++lp)
+        for (uint32_t k = 0; k < L.pt_cnt[lp]; ++k, ++q) {
+          const uint64_t o = pm[q];
+          const uint32_t pos = cnt[t][d->obs_cam[o]]++;
+          L.cm_uv[pos] = d->obs_uv[2 * o];
+          L.cm_uv[(size_t)L.nobs_local + pos] = d->obs_uv[2 * o + 1];
+          L.cm_lp[pos] = lp;
+        }
+    }
   }
   L.cam_item_start.assign((size_t)ncam + 1, 0);
   for (uint32_t k = 0; k < ncam; ++k) {
@@ -219,13 +346,15 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
       L.items.push_back({k, b, std::min<uint32_t>(b + CAM_CHUNK, cam_start[k + 1]), 0});
   }
   L.cam_item_start[ncam] = (uint32_t)L.items.size();
+  lap("camera-major copy");
 }
 
 apex_status layout_stats(const apex_problem_desc* d, int nranks, int rank, apex_layout_stats* out, std::string& err) {
   APEX_TRY(validate_problem(d, err));
   const auto t0 = std::chrono::steady_clock::now();
   HostLayout L;
-  build_layout(d, nranks, rank, L);
+  const int K = model_intr_dim(d->camera_model);
+  build_layout(d, nranks, rank, L, 6 + ((d->opt_flags & APEX_OPT_INTRINSIC) ? K : 0));
   out->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   out->shard_block = SHARD_BLOCK; out->npts_local = L.npl; out->nobs_local = L.nobs_local;
   out->ntiles = (uint32_t)L.tiles.size(); out->nlong_tiles = (uint32_t)L.giant_tiles.size();
@@ -246,12 +375,24 @@ apex_status layout_stats(const apex_problem_desc* d, int nranks, int rank, apex_
     const ChunkDesc& cd = L.chunk_desc[t.chunk0];
     for (uint32_t s = 0; s < nobs_tile; ++s) {
       const uint2 m = L.cslot_meta[base + s];
-      const uint32_t pos = (m.y >> 8) & 0xFFu, seg = (m.y >> 16) & 0xFFFFu;
+      const uint32_t pos = (m.y >> 8) & 0xFFu, seg = (m.y >> 16) & 0xFFu;
       if (pos >= nobs_tile || seen[pos]++ || seg >= cd.nseg || L.cseg_cam[base + seg] != m.x) { out->consistent = 0; break; }
       const uint32_t b = L.cseg_begin[(size_t)t.chunk0 * CSEG_LD + seg], e = L.cseg_begin[(size_t)t.chunk0 * CSEG_LD + seg + 1];
       if (pos < b || pos >= e) { out->consistent = 0; break; }
     }
   }
+  out->mv_group = L.mv_G; out->mv_window = L.mv_W; out->mv_ngroups = (uint32_t)L.grp_win0.size(); out->reserved2 = 0;
+  uint64_t inwin = 0;
+  if (L.mv_W)
+    for (size_t s = 0; s < (size_t)L.nnormal_chunks * TILE; ++s) {
+      const uint32_t cam = L.cslot_meta[s].x;
+      if (cam == PAD_CAM) continue;
+      const uint32_t w0 = L.grp_win0[s / ((size_t)L.mv_G * TILE)];
+      if (w0 >= d->ncam) { out->consistent = 0; break; }
+      const uint32_t l = cam >= w0 ? cam - w0 : cam + d->ncam - w0;
+      inwin += l < L.mv_W;
+    }
+  out->nobs_in_window = inwin;
   return APEX_OK;
 }
 
@@ -282,7 +423,8 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   for (int i = 0; i < 4; ++i) c.loss_p[i] = d->loss_params[i];
 
   HostLayout L;
-  build_layout(d, c.nranks, c.rank, L);
+  build_layout(d, c.nranks, c.rank, L, c.dc);
+  c.mv_G = L.mv_G; c.mv_W = L.mv_W; c.mv_ngroups = (uint32_t)L.grp_win0.size();
   c.shard = L.shard; c.npl = L.npl; c.nobs_local = L.nobs_local;
   c.nnormal_chunks = L.nnormal_chunks; c.nchunks = L.nchunks; c.npairs = L.npairs;
   c.ntiles = (uint32_t)L.tiles.size(); c.ngiant = (uint32_t)L.giant_tiles.size(); c.nitems = (uint32_t)L.items.size();
@@ -311,6 +453,7 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   APEX_CUDA_TRY(c, upload_vec(c.cpt_meta, L.cpt_meta, s));
   APEX_CUDA_TRY(c, upload_vec(c.cseg_cam, L.cseg_cam, s));
   APEX_CUDA_TRY(c, upload_vec(c.cseg_begin, L.cseg_begin, s));
+  APEX_CUDA_TRY(c, upload_vec(c.grp_win0, L.grp_win0, s));
   APEX_CUDA_TRY(c, upload_vec(c.items, L.items, s));
   APEX_CUDA_TRY(c, upload_vec(c.cam_item_start, L.cam_item_start, s));
   APEX_CUDA_TRY(c, upload_vec(c.cm_uv, L.cm_uv, s));
@@ -342,7 +485,7 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   APEX_CUDA_TRY(c, c.vp.alloc(ncd));
   APEX_CUDA_TRY(c, c.vy.alloc(ncd));
   APEX_CUDA_TRY(c, c.ypart.alloc((size_t)c.num_sms * ncd));
-  APEX_CUDA_TRY(c, c.xpad.alloc((size_t)c.ncam * (c.dc + 2)));
+  APEX_CUDA_TRY(c, c.xpad.alloc((size_t)c.ncam * xpad_stride(c.dc)));
   APEX_CUDA_TRY(c, c.step_cam.alloc(ncd));
   APEX_CUDA_TRY(c, c.step_pt.alloc((size_t)c.npl * 3));
   APEX_CUDA_TRY(c, c.red_scratch.alloc(8 * (size_t)std::max<uint32_t>(std::max<uint32_t>(c.nchunks, c.ncam), 1024u) + 64));

@@ -74,13 +74,21 @@ __device__ __forceinline__ void obs_forward(const double* jc, const double* jp, 
   for (int k = 0; k < 3; ++k) u[k] = fma(jp[k], a0, jp[3 + k] * a1);
 }
 
-// same with x stored at an even stride XS >= DC (16-byte aligned camera blocks, 128-bit loads)
+// same with x stored at the padded stride xpad_stride(DC) (32-byte aligned camera blocks). The gather costs one L1
+// wavefront per (lane, instruction) because every lane reads another camera's line, so the block is fetched with as
+// few instructions as possible: 256-bit loads (LDG.E.ENL2.256) plus one 64/128-bit load for the remainder.
+__device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
 template <int DC>
 __device__ __forceinline__ void obs_forward_padded(const double* jc, const double* jp, const double* __restrict__ xc, double u[3]) {
-  constexpr int XS = (DC + 1) & ~1;
-  double xv[XS];
+  constexpr int N4 = DC / 4, REM = DC % 4;
+  double xv[4 * N4 + 4];
 #pragma unroll
-  for (int m = 0; m < XS / 2; ++m) { const double2 v = __ldg(reinterpret_cast<const double2*>(xc) + m); xv[2 * m] = v.x; xv[2 * m + 1] = v.y; }
+  for (int m = 0; m < N4; ++m) ldg256(xc + 4 * m, xv[4 * m], xv[4 * m + 1], xv[4 * m + 2], xv[4 * m + 3]);
+  if (REM == 1) xv[4 * N4] = __ldg(xc + 4 * N4);
+  else if (REM == 2) { const double2 v = __ldg(reinterpret_cast<const double2*>(xc + 4 * N4)); xv[4 * N4] = v.x; xv[4 * N4 + 1] = v.y; }
+  else if (REM == 3) ldg256(xc + 4 * N4, xv[4 * N4], xv[4 * N4 + 1], xv[4 * N4 + 2], xv[4 * N4 + 3]);
   double a0 = 0.0, a1 = 0.0;
 #pragma unroll
   for (int k = 0; k < DC; ++k) { a0 = fma(jc[k], xv[k], a0); a1 = fma(jc[DC + k], xv[k], a1); }
@@ -380,7 +388,7 @@ __global__ void __launch_bounds__(2 * TILE, 1) schur_matvec_pingpong_kernel(PpAr
       const uint32_t nld = R.nseg * (XS / 2);                                                                            \
       for (uint32_t idx = gt; idx < nld; idx += TILE) {                                                                  \
         const uint32_t sgi = idx / (XS / 2), m = idx - sgi * (XS / 2);                                                   \
-        xs2[idx] = __ldg(reinterpret_cast<const double2*>(a.xpad + (size_t)segc[sgi] * XS) + m);                         \
+        xs2[idx] = __ldg(reinterpret_cast<const double2*>(a.xpad + (size_t)segc[sgi] * xpad_stride(DC)) + m);            \
       }                                                                                                                  \
     }                                                                                                                    \
     pp_prefetch_stage<DC, 0>(a, chunk_next, valid_next, gt, RN);                                                         \
@@ -389,7 +397,7 @@ __global__ void __launch_bounds__(2 * TILE, 1) schur_matvec_pingpong_kernel(PpAr
     if (MODE == MODE_MATVEC) {                                                                                           \
       double u0 = 0.0, u1 = 0.0, u2 = 0.0;                                                                               \
       if (R.cam != PAD_CAM) {                                                                                            \
-        const double2* xs2 = reinterpret_cast<const double2*>(cs) + (size_t)((R.sp >> 16) & 0xFFFFu) * (XS / 2);         \
+        const double2* xs2 = reinterpret_cast<const double2*>(cs) + (size_t)((R.sp >> 16) & 0xFFu) * (XS / 2);           \
         double xv[XS];                                                                                                   \
         _Pragma("unroll") for (int m = 0; m < XS / 2; ++m) { const double2 v = xs2[m]; xv[2 * m] = v.x; xv[2 * m + 1] = v.y; } \
         double a0 = 0.0, a1 = 0.0;                                                                                       \
@@ -563,7 +571,7 @@ template <int DC, int MODE>
 __global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a, uint32_t nchunks) {
   constexpr int NP = 2 * (DC + 3);
   constexpr int LD = TILE + 1;
-  constexpr int XS = (DC + 1) & ~1;
+  constexpr int XS = xpad_stride(DC);
   if (a.check_done && a.st->pcg_done) return;
   __shared__ double cs[DC * LD];                  // phase 3/4 contributions; its head doubles as su in phases 1/2
   double (*su)[TILE] = reinterpret_cast<double (*)[TILE]>(cs);
@@ -609,9 +617,11 @@ __global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a, uint3
     const int lane = tid & 31;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const double o0 = __shfl_down_sync(0xffffffffu, u[0], d), o1 = __shfl_down_sync(0xffffffffu, u[1], d), o2 = __shfl_down_sync(0xffffffffu, u[2], d);
       const uint32_t ok = __shfl_down_sync(0xffffffffu, key, d);
-      if (lane + d < 32 && ok == key) { u[0] += o0; u[1] += o1; u[2] += o2; }
+      const bool hit = lane + d < 32 && ok == key;
+      if (!__any_sync(0xffffffffu, hit)) break;  // runs are contiguous: no partner at distance d => none further away
+      const double o0 = __shfl_down_sync(0xffffffffu, u[0], d), o1 = __shfl_down_sync(0xffffffffu, u[1], d), o2 = __shfl_down_sync(0xffffffffu, u[2], d);
+      if (hit) { u[0] += o0; u[1] += o1; u[2] += o2; }
     }
     const uint32_t pk = __shfl_up_sync(0xffffffffu, key, 1);
     if ((lane == 0 || pk != key) && cam != PAD_CAM) { su[0][tid] = u[0]; su[1][tid] = u[1]; su[2][tid] = u[2]; }
@@ -668,6 +678,395 @@ __global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a, uint3
     red_add(yr, v0);
     if (kg + 1 < DC) red_add(yr + 1, v1);
     if (kg + 2 < DC) red_add(yr + 2, v2);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Window kernel (operator only): one 256-thread CTA walks a GROUP of G consecutive chunks. In a locality-ordered
+// reconstruction the landmarks of a group see a narrow band of cameras, so the CTA keeps a WINDOW of W consecutive
+// cameras (modulo ncam; start chosen per group at upload for maximal coverage) in shared memory:
+//   xw : the operator input of the window's cameras, loaded once per group with coalesced cp.async
+//        (replaces a 32-line L1 gather per warp instruction by LDS),
+//   yw : the window's share of the result, accumulated chunk after chunk with plain shared-memory read-modify-
+//        writes (one thread per (camera segment, 3 dofs); segments of a chunk are distinct cameras, chunks are
+//        separated by a barrier) and flushed with ONE coalesced red.global.add.f64 per (camera, dof) per group
+//        instead of one per (chunk, camera segment, dof).
+// Observations whose camera falls outside the window (2-3 % on the Venice shape at W = 320) take the chunk
+// kernel's route: 128-bit gather from the padded copy, reduction straight to global memory. The result is exact
+// for any input; only the speed depends on locality.
+// ----------------------------------------------------------------------------------------------------
+struct WinArgs {
+  const uint32_t* grp_win0;  // [ngroups] first camera of the group's window
+  uint32_t ngroups, G, W, ncam;
+};
+template <int DC>
+__host__ __device__ constexpr size_t win_base_bytes() {
+  return sizeof(double) * (DC * (TILE + 1) + 3 * MAX_TILE_PTS + 6 * MAX_TILE_PTS) + 4 * MAX_TILE_PTS + 4 * TILE + ((2 * CSEG_LD + 15) & ~15);
+}
+template <int DC>
+__global__ void __launch_bounds__(TILE, 3) schur_window_kernel(SchurArgs a, WinArgs wa, uint32_t nchunks) {
+  constexpr int NP = 2 * (DC + 3);
+  constexpr int LD = TILE + 1;
+  constexpr int XS = xpad_stride(DC);
+  if (a.check_done && a.st->pcg_done) return;
+  extern __shared__ __align__(16) unsigned char win_smem[];
+  double* cs = reinterpret_cast<double*>(win_smem);                  // [DC][LD]; head doubles as su in phases 1/2
+  double (*su)[TILE] = reinterpret_cast<double (*)[TILE]>(cs);
+  double (*sw)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(cs + DC * LD);
+  double (*shinv)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(cs + DC * LD + 3 * MAX_TILE_PTS);
+  double* xw = cs + DC * LD + 9 * MAX_TILE_PTS;
+  const uint32_t W = wa.W, ncam = wa.ncam;
+  double* yw = xw + (size_t)W * DC;
+  uint32_t* sptm = reinterpret_cast<uint32_t*>(yw + (size_t)W * DC);
+  uint32_t* ssegc = sptm + MAX_TILE_PTS;
+  uint16_t* ssegb = reinterpret_cast<uint16_t*>(ssegc + TILE);
+  const int tid = threadIdx.x;
+  const uint32_t grp = (wa.ngroups % 4099u != 0) ? (uint32_t)(((uint64_t)blockIdx.x * 4099u) % wa.ngroups) : blockIdx.x;
+  const uint32_t c_begin = grp * wa.G, c_end = min(c_begin + wa.G, nchunks);
+  const uint32_t win0 = __ldg(wa.grp_win0 + grp);
+  const uint32_t nw = W * DC, ntot = ncam * DC;
+  // window of x (cp.async, lands together with the first chunk's tables), zeroed window of y
+  for (uint32_t i = tid; i < nw; i += TILE) {
+    uint32_t gi = win0 * DC + i;
+    if (gi >= ntot) gi -= ntot;
+    cp_async8(xw + i, a.x + gi);
+    yw[i] = 0.0;
+  }
+  for (uint32_t chunk = c_begin; chunk < c_end; ++chunk) {
+    // ---- all global reads of the chunk up front ----
+    cp_async4(ssegc + tid, a.cseg_cam + (size_t)chunk * TILE + tid);
+    if (tid < CSEG_LD / 2) cp_async4(reinterpret_cast<uint32_t*>(ssegb) + tid, reinterpret_cast<const uint32_t*>(a.cseg_begin + (size_t)chunk * CSEG_LD) + tid);
+    const uint2 meta = __ldg(a.cslot_meta + (size_t)chunk * TILE + tid);
+    const uint4 dsc = __ldg(reinterpret_cast<const uint4*>(a.chunk_desc + chunk));
+    double jall[NP];
+    load_jacobian_planes<NP>(a.J, chunk, tid, jall);
+    const uint32_t pt0 = dsc.x, npt = dsc.y, nseg = dsc.z;
+    if ((uint32_t)tid < npt) {
+      const uint32_t lp = pt0 + tid;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) cp_async8(&shinv[k][tid], a.hinv + (size_t)k * a.npl + lp);
+      cp_async4(&sptm[tid], a.cpt_meta + lp);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const uint32_t cam = meta.x;
+    const double* jc = jall;
+    const double* jp = jall + 2 * DC;
+    if (chunk == c_begin) {  // the window has to be there before the first gather
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+    }
+    // ---- phase 1: u_o = Jp^T (Jc x_c), x from the window; segmented warp-shuffle sum over each landmark's run ----
+    {
+      double u[3] = {0.0, 0.0, 0.0};
+      if (cam != PAD_CAM) {
+        uint32_t l = cam - win0;
+        if (cam < win0) l += ncam;
+        if (l < W) {
+          const double* xc = xw + l * DC;
+          double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+          for (int k = 0; k < DC; ++k) { const double xv = xc[k]; a0 = fma(jc[k], xv, a0); a1 = fma(jc[DC + k], xv, a1); }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) u[k] = fma(jp[k], a0, jp[3 + k] * a1);
+        } else {
+          obs_forward_padded<DC>(jc, jp, a.xpad + (size_t)cam * XS, u);
+        }
+      }
+      const uint32_t key = cam != PAD_CAM ? (meta.y & 0xFFu) : 0xFFFFu;
+      const int lane = tid & 31;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double o0 = __shfl_down_sync(0xffffffffu, u[0], d), o1 = __shfl_down_sync(0xffffffffu, u[1], d), o2 = __shfl_down_sync(0xffffffffu, u[2], d);
+        const uint32_t ok = __shfl_down_sync(0xffffffffu, key, d);
+        if (lane + d < 32 && ok == key) { u[0] += o0; u[1] += o1; u[2] += o2; }
+      }
+      const uint32_t pk = __shfl_up_sync(0xffffffffu, key, 1);
+      if ((lane == 0 || pk != key) && cam != PAD_CAM) { su[0][tid] = u[0]; su[1][tid] = u[1]; su[2][tid] = u[2]; }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // ---- phase 2: per landmark ----
+    if ((uint32_t)tid < npt) {
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+      const uint32_t mm = sptm[tid], off = mm & 0xFFFFu, cnt = mm >> 16;
+      if (cnt) {
+        t0 = su[0][off]; t1 = su[1][off]; t2 = su[2][off];
+        for (uint32_t b = (off & ~31u) + 32; b < off + cnt; b += 32) { t0 += su[0][b]; t1 += su[1][b]; t2 += su[2][b]; }
+      }
+      const double h00 = shinv[0][tid], h01 = shinv[1][tid], h02 = shinv[2][tid], h11 = shinv[3][tid], h12 = shinv[4][tid], h22 = shinv[5][tid];
+      sw[0][tid] = h00 * t0 + h01 * t1 + h02 * t2;
+      sw[1][tid] = h01 * t0 + h11 * t1 + h12 * t2;
+      sw[2][tid] = h02 * t0 + h12 * t1 + h22 * t2;
+    }
+    __syncthreads();
+    // ---- phase 3: c_o = -Jc^T (Jp w_p) at the observation's camera-sorted position ----
+    if (cam != PAD_CAM) {
+      const uint32_t spt = meta.y & 0xFFu, pos = (meta.y >> 8) & 0xFFu;
+      const double w0 = sw[0][spt], w1 = sw[1][spt], w2 = sw[2][spt];
+      const double b0 = fma(jp[0], w0, fma(jp[1], w1, jp[2] * w2));
+      const double b1 = fma(jp[3], w0, fma(jp[4], w1, jp[5] * w2));
+#pragma unroll
+      for (int k = 0; k < DC; ++k) cs[k * LD + pos] = -fma(jc[k], b0, jc[DC + k] * b1);
+    }
+    __syncthreads();
+    // ---- phase 4: per (camera segment, 3 dofs): into the window, or straight to global memory outside it ----
+    constexpr int KG = 3, NG = (DC + KG - 1) / KG;
+    for (uint32_t idx = tid; idx < nseg * NG; idx += TILE) {
+      const uint32_t sgi = idx / NG, kg = (idx - sgi * NG) * KG;
+      const uint32_t b = ssegb[sgi], e = ssegb[sgi + 1];
+      const uint32_t cg = ssegc[sgi];
+      const double* c0 = cs + kg * LD;
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+      for (uint32_t q = b; q < e; ++q) {
+        v0 += c0[q];
+        if (kg + 1 < DC) v1 += c0[LD + q];
+        if (kg + 2 < DC) v2 += c0[2 * LD + q];
+      }
+      uint32_t l = cg - win0;
+      if (cg < win0) l += ncam;
+      if (l < W) {
+        double* yr = yw + l * DC + kg;
+        yr[0] += v0;
+        if (kg + 1 < DC) yr[1] += v1;
+        if (kg + 2 < DC) yr[2] += v2;
+      } else if (a.debug != 1) {
+        double* yr = a.y + (size_t)cg * DC + kg;
+        red_add(yr, v0);
+        if (kg + 1 < DC) red_add(yr + 1, v1);
+        if (kg + 2 < DC) red_add(yr + 2, v2);
+      }
+    }
+    __syncthreads();  // the next chunk overwrites the tables and su; the flush reads yw
+  }
+  // ---- flush the window: one coalesced reduction per touched (camera, dof) ----
+  if (a.debug == 1) return;
+  for (uint32_t i = tid; i < nw; i += TILE) {
+    const double v = yw[i];
+    if (v != 0.0) {
+      uint32_t gi = win0 * DC + i;
+      if (gi >= ntot) gi -= ntot;
+      red_add(a.y + gi, v);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Stream kernel (operator only, DC = 6 / 9): the chunk kernel is latency bound - a CTA asks for its 48 KB of
+// Jacobian planes, waits, computes through three barriers, and only the other two CTAs of the SM cover that, so
+// on average ~36 KB per SM are in flight where HBM needs ~70 KB. Here loads and compute are decoupled:
+//   * one persistent CTA per SM = 3 groups of 256 threads sharing a 2-stage shared-memory ring;
+//   * whole chunks - Jacobian planes (one 48 KB bulk copy), slot metadata, camera-segment tables, chunk descriptor -
+//     are streamed into the ring with cp.async.bulk (TMA), armed on an mbarrier per stage, so ~100 KB per SM are
+//     always in flight, independent of what the groups are computing;
+//   * a group waits for its stage, moves its chunk into registers (12 conflict-free LDS.128 per thread), releases
+//     the stage (mbarrier arrive; its first thread re-arms it with the chunk two ahead as soon as all 256 copies
+//     are out) and then runs the chunk kernel's four phases on named barriers
+//     (bar.sync g, 256); the three groups are at different phases, so the LSU / FP64 / barrier latencies of one
+//     overlap with the others;
+//   * the x gather is issued before the register copy (the metadata is already on chip) and uses 256-bit loads.
+// Chunks are dealt round-robin to the CTAs in the same strided order as the chunk kernel. Every wait is bounded
+// (trap instead of a hang).
+// ----------------------------------------------------------------------------------------------------
+constexpr int ST_GROUPS = 3, ST_STAGES = 2, ST_THREADS = ST_GROUPS * TILE;
+// "stage full" barriers: one per (stage, group) combination, i.e. chunk i of a CTA uses full[i % 6]. With one barrier per
+// stage, a group waiting for the NEXT BUT ONE fill of a stage would see the parity it waits for as "already
+// completed" while the fill in between has not landed (a parity wait cannot tell phase n from phase n + 2).
+constexpr int ST_FULL = ST_GROUPS * ST_STAGES;
+template <int DC> __host__ __device__ constexpr uint32_t st_j_bytes() { return 2 * (DC + 3) * 8 * TILE; }
+template <int DC> __host__ __device__ constexpr uint32_t st_stage_bytes() {
+  return (st_j_bytes<DC>() + 8 * TILE + 4 * TILE + 2 * CSEG_LD + 16 + 127) & ~127u;
+}
+template <int DC> __host__ __device__ constexpr uint32_t st_group_bytes() {
+  return 8 * (DC * (TILE + 1) + 3 * TILE + 9 * MAX_TILE_PTS) + 4 * MAX_TILE_PTS + 2 * (4 * TILE + 2 * CSEG_LD);
+}
+template <int DC> __host__ __device__ constexpr uint32_t st_smem_bytes() {
+  return ST_STAGES * st_stage_bytes<DC>() + ST_GROUPS * st_group_bytes<DC>() + 8 * (ST_FULL + ST_STAGES);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait on a phase parity: ~2 s of polling, then trap (an error the host sees) instead of a hang
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+
+template <int DC>
+__global__ void __launch_bounds__(ST_THREADS, 1) schur_stream_kernel(SchurArgs a, uint32_t nchunks) {
+  constexpr int NP = 2 * (DC + 3);
+  constexpr int LD = TILE + 1;
+  constexpr int XS = xpad_stride(DC);
+  constexpr uint32_t JB = st_j_bytes<DC>(), SB = st_stage_bytes<DC>(), GB = st_group_bytes<DC>();
+  constexpr uint32_t OFF_META = JB, OFF_SEGC = JB + 8 * TILE, OFF_SEGB = OFF_SEGC + 4 * TILE, OFF_DESC = OFF_SEGB + 2 * CSEG_LD;
+  static_assert((2 * CSEG_LD) % 16 == 0, "segment table rows must be 16-byte multiples for bulk copies");
+  if (a.check_done && a.st->pcg_done) return;
+  extern __shared__ __align__(128) unsigned char st_smem[];
+  unsigned char* stages = st_smem;
+  unsigned char* groups = st_smem + ST_STAGES * SB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(groups + ST_GROUPS * GB);  // full[ST_FULL], empty[ST_STAGES]
+  const int tid_all = threadIdx.x;
+  if (tid_all == 0) {
+    for (int s = 0; s < ST_FULL; ++s) mbar_init(smem_u32(bars + s), 1);
+    for (int s = 0; s < ST_STAGES; ++s) mbar_init(smem_u32(bars + ST_FULL + s), TILE);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // chunks of this CTA: j = blockIdx.x + i * gridDim.x, visited in the strided order
+  const uint32_t nmine = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const bool strided = nchunks % 4099u != 0;
+  // producer duty: whoever frees a stage refills it. issue(i) arms stage i % ST_STAGES and starts the bulk copies of this
+  // CTA's i-th chunk: Jacobian planes (one contiguous run), slot metadata, segment tables, chunk descriptor.
+  auto issue = [&](uint32_t i) {
+    const uint32_t s = i % ST_STAGES;
+    const uint32_t j = blockIdx.x + i * gridDim.x;
+    const uint32_t chunk = strided ? (uint32_t)(((uint64_t)j * 4099u) % nchunks) : j;
+    const uint32_t full = smem_u32(bars + i % ST_FULL), dst = smem_u32(stages + (size_t)s * SB);
+    mbar_expect_tx(full, JB + 8 * TILE + 4 * TILE + 2 * CSEG_LD + 16);
+    bulk_g2s(dst, a.J + (size_t)chunk * NP * TILE, JB, full);
+    bulk_g2s(dst + OFF_META, a.cslot_meta + (size_t)chunk * TILE, 8 * TILE, full);
+    bulk_g2s(dst + OFF_SEGC, a.cseg_cam + (size_t)chunk * TILE, 4 * TILE, full);
+    bulk_g2s(dst + OFF_SEGB, a.cseg_begin + (size_t)chunk * CSEG_LD, 2 * CSEG_LD, full);
+    bulk_g2s(dst + OFF_DESC, a.chunk_desc + chunk, 16, full);
+  };
+  if (tid_all == 0)
+    for (uint32_t i = 0; i < ST_STAGES && i < nmine; ++i) issue(i);
+  // ---------------- consumers ----------------
+  const int grp = tid_all / TILE, tid = tid_all % TILE, lane = tid & 31;
+  unsigned char* gb = groups + (size_t)grp * GB;
+  double* cs = reinterpret_cast<double*>(gb);                          // [DC][LD]
+  double (*su)[TILE] = reinterpret_cast<double (*)[TILE]>(cs + DC * LD);
+  double (*sw)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(cs + DC * LD + 3 * TILE);
+  double (*shinv)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(cs + DC * LD + 3 * TILE + 3 * MAX_TILE_PTS);
+  uint32_t* sptm = reinterpret_cast<uint32_t*>(cs + DC * LD + 3 * TILE + 9 * MAX_TILE_PTS);
+  unsigned char* segtab = reinterpret_cast<unsigned char*>(sptm + MAX_TILE_PTS);   // 2 x {segc u32[256], segb u16[CSEG_LD]}
+  uint32_t par = 0;  // parity of the group's segment-table buffer
+  for (uint32_t i = grp; i < nmine; i += ST_GROUPS, par ^= 1) {
+    const uint32_t s = i % ST_STAGES, use = i / ST_STAGES;
+    const unsigned char* stg = stages + (size_t)s * SB;
+    mbar_wait(smem_u32(bars + i % ST_FULL), (i / ST_FULL) & 1);
+    // ---- chunk -> registers / group-private tables; the x gather goes out first ----
+    const uint2 meta = reinterpret_cast<const uint2*>(stg + OFF_META)[tid];
+    const uint4 dsc = *reinterpret_cast<const uint4*>(stg + OFF_DESC);
+    const uint32_t cam = meta.x;
+    double xv[4 * (DC / 4) + 4];
+    if (cam != PAD_CAM) {
+      const double* xc = a.xpad + (size_t)cam * XS;
+#pragma unroll
+      for (int m = 0; m < DC / 4; ++m) ldg256(xc + 4 * m, xv[4 * m], xv[4 * m + 1], xv[4 * m + 2], xv[4 * m + 3]);
+      if (DC % 4 == 1) xv[4 * (DC / 4)] = __ldg(xc + 4 * (DC / 4));
+      else if (DC % 4 == 2) { const double2 v = __ldg(reinterpret_cast<const double2*>(xc + 4 * (DC / 4))); xv[4 * (DC / 4)] = v.x; xv[4 * (DC / 4) + 1] = v.y; }
+      else if (DC % 4 == 3) ldg256(xc + 4 * (DC / 4), xv[4 * (DC / 4)], xv[4 * (DC / 4) + 1], xv[4 * (DC / 4) + 2], xv[4 * (DC / 4) + 3]);
+    }
+    double jall[NP];
+    {
+      const double2* j2 = reinterpret_cast<const double2*>(stg) + tid;
+#pragma unroll
+      for (int m = 0; m < NP / 2; ++m) { const double2 v = j2[m * TILE]; jall[2 * m] = v.x; jall[2 * m + 1] = v.y; }
+    }
+    uint32_t* ssegc = reinterpret_cast<uint32_t*>(segtab + (size_t)par * (4 * TILE + 2 * CSEG_LD));
+    uint16_t* ssegb = reinterpret_cast<uint16_t*>(ssegc + TILE);
+    ssegc[tid] = reinterpret_cast<const uint32_t*>(stg + OFF_SEGC)[tid];
+    if (tid < CSEG_LD / 2) reinterpret_cast<uint32_t*>(ssegb)[tid] = reinterpret_cast<const uint32_t*>(stg + OFF_SEGB)[tid];
+    mbar_arrive(smem_u32(bars + ST_FULL + s));    // stage free as soon as all 256 copies are out
+    if (tid == 0 && i + ST_STAGES < nmine) {      // ... and refilled at once, while this group computes
+      mbar_wait(smem_u32(bars + ST_FULL + s), use & 1);
+      issue(i + ST_STAGES);
+    }
+    const uint32_t pt0 = dsc.x, npt = dsc.y, nseg = dsc.z;
+    if ((uint32_t)tid < npt) {
+      const uint32_t lp = pt0 + tid;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) cp_async8(&shinv[k][tid], a.hinv + (size_t)k * a.npl + lp);
+      cp_async4(&sptm[tid], a.cpt_meta + lp);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const double* jc = jall;
+    const double* jp = jall + 2 * DC;
+    // ---- phase 1 ----
+    {
+      double u[3] = {0.0, 0.0, 0.0};
+      if (cam != PAD_CAM) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < DC; ++k) { a0 = fma(jc[k], xv[k], a0); a1 = fma(jc[DC + k], xv[k], a1); }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) u[k] = fma(jp[k], a0, jp[3 + k] * a1);
+      }
+      const uint32_t key = cam != PAD_CAM ? (meta.y & 0xFFu) : 0xFFFFu;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t ok = __shfl_down_sync(0xffffffffu, key, d);
+        const bool hit = lane + d < 32 && ok == key;
+        if (!__any_sync(0xffffffffu, hit)) break;
+        const double o0 = __shfl_down_sync(0xffffffffu, u[0], d), o1 = __shfl_down_sync(0xffffffffu, u[1], d), o2 = __shfl_down_sync(0xffffffffu, u[2], d);
+        if (hit) { u[0] += o0; u[1] += o1; u[2] += o2; }
+      }
+      const uint32_t pk = __shfl_up_sync(0xffffffffu, key, 1);
+      if ((lane == 0 || pk != key) && cam != PAD_CAM) { su[0][tid] = u[0]; su[1][tid] = u[1]; su[2][tid] = u[2]; }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    group_bar(1 + grp);
+    // ---- phase 2: per landmark ----
+    if ((uint32_t)tid < npt) {
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+      const uint32_t mm = sptm[tid], off = mm & 0xFFFFu, cnt = mm >> 16;
+      if (cnt) {
+        t0 = su[0][off]; t1 = su[1][off]; t2 = su[2][off];
+        for (uint32_t b = (off & ~31u) + 32; b < off + cnt; b += 32) { t0 += su[0][b]; t1 += su[1][b]; t2 += su[2][b]; }
+      }
+      const double h00 = shinv[0][tid], h01 = shinv[1][tid], h02 = shinv[2][tid], h11 = shinv[3][tid], h12 = shinv[4][tid], h22 = shinv[5][tid];
+      sw[0][tid] = h00 * t0 + h01 * t1 + h02 * t2;
+      sw[1][tid] = h01 * t0 + h11 * t1 + h12 * t2;
+      sw[2][tid] = h02 * t0 + h12 * t1 + h22 * t2;
+    }
+    group_bar(1 + grp);
+    // ---- phase 3 ----
+    if (cam != PAD_CAM) {
+      const uint32_t spt = meta.y & 0xFFu, pos = (meta.y >> 8) & 0xFFu;
+      const double w0 = sw[0][spt], w1 = sw[1][spt], w2 = sw[2][spt];
+      const double b0 = fma(jp[0], w0, fma(jp[1], w1, jp[2] * w2));
+      const double b1 = fma(jp[3], w0, fma(jp[4], w1, jp[5] * w2));
+#pragma unroll
+      for (int k = 0; k < DC; ++k) cs[k * LD + pos] = -fma(jc[k], b0, jc[DC + k] * b1);
+    }
+    group_bar(1 + grp);
+    // ---- phase 4 ----
+    constexpr int KG = 3, NGK = (DC + KG - 1) / KG;
+    for (uint32_t idx = tid; idx < nseg * NGK; idx += TILE) {
+      const uint32_t sgi = idx / NGK, kg = (idx - sgi * NGK) * KG;
+      const uint32_t b = ssegb[sgi], e = ssegb[sgi + 1];
+      double* yr = a.y + (size_t)ssegc[sgi] * DC + kg;
+      const double* c0 = cs + kg * LD;
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+      for (uint32_t q = b; q < e; ++q) {
+        v0 += c0[q];
+        if (kg + 1 < DC) v1 += c0[LD + q];
+        if (kg + 2 < DC) v2 += c0[2 * LD + q];
+      }
+      if (a.debug == 1 && v0 != 1.2345e300) continue;
+      red_add(yr, v0);
+      if (kg + 1 < DC) red_add(yr + 1, v1);
+      if (kg + 2 < DC) red_add(yr + 2, v2);
+    }
+    // no trailing barrier: su is separate from cs, the segment tables alternate between two buffers, and every
+    // other shared array is rewritten only behind the next chunk's barriers
   }
 }
 
@@ -993,7 +1392,25 @@ static void launch_tiles_dc(Ctx& c, int mode, const SchurArgs& a0) {
     return;
   }
   // normal chunks through the chunk kernel, landmarks with more than 256 observations through the tile kernel
-  if (c.nnormal_chunks) {
+  const char* stream_env = getenv("APEX_MV_STREAM");
+  const int stream_on = stream_env ? atoi(stream_env) : 0;  // opt-in: measured slower than the chunk kernel
+  if (c.nnormal_chunks && mode == MODE_MATVEC && stream_on && (DC == 6 || DC == 9) && !(c.mv_W && c.mv_ngroups)) {
+    // operator: persistent stream kernel (TMA-fed ring, producer warp + 3 consumer groups)
+    constexpr int SDC = (DC == 6 || DC == 9) ? DC : 9;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(schur_stream_kernel<SDC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem_bytes<SDC>()); attr_set = true; }
+    const unsigned grid = std::min<uint32_t>((uint32_t)c.num_sms, c.nnormal_chunks);
+    schur_stream_kernel<SDC><<<grid, ST_THREADS, st_smem_bytes<SDC>(), c.stream>>>(a, c.nnormal_chunks);
+    c.launches++;
+  } else if (c.nnormal_chunks && mode == MODE_MATVEC && c.mv_W && c.mv_ngroups) {
+    // operator: window kernel (groups of chunks, camera window of x and y in shared memory)
+    const size_t smem = mv_window_base_bytes(DC) + 2 * sizeof(double) * (size_t)c.mv_W * DC;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(schur_window_kernel<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 76800); attr_set = true; }
+    WinArgs wa{c.grp_win0.p, c.mv_ngroups, c.mv_G, c.mv_W, c.ncam};
+    schur_window_kernel<DC><<<c.mv_ngroups, TILE, smem, c.stream>>>(a, wa, c.nnormal_chunks);
+    c.launches++;
+  } else if (c.nnormal_chunks) {
     switch (mode) {
       case MODE_MATVEC: schur_chunk_kernel<DC, MODE_MATVEC><<<c.nnormal_chunks, TILE, 0, c.stream>>>(a, c.nnormal_chunks); break;
       case MODE_RHS: schur_chunk_kernel<DC, MODE_RHS><<<c.nnormal_chunks, TILE, 0, c.stream>>>(a, c.nnormal_chunks); break;
@@ -1017,7 +1434,7 @@ static void launch_tiles_dc(Ctx& c, int mode, const SchurArgs& a0) {
 apex_status launch_schur_tiles(Ctx& c, int mode, const double* x, double* y, int check_done, bool xpad_ready) {
   if (c.ntiles == 0) return APEX_OK;
   if (mode != MODE_RHS && !xpad_ready && operator_impl() != 1 && operator_impl() != 2) {  // the chunk kernel gathers x from the padded copy
-    const int xs = (c.dc + 1) & ~1;
+    const int xs = xpad_stride(c.dc);
     pad_x_kernel<<<(c.ncam * xs + 255) / 256, 256, 0, c.stream>>>(x, c.xpad.p, c.ncam, c.dc, xs, c.state.p, check_done);
     c.launches++;
   }
@@ -1079,7 +1496,7 @@ apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_d
     if (evp) cudaEventRecord(evp[1], c.stream);
     return st;
   }
-  const int xs = (c.dc + 1) & ~1;
+  const int xs = xpad_stride(c.dc);
   if (!xpad_ready) {
     pad_x_kernel<<<(c.ncam * xs + 255) / 256, 256, 0, c.stream>>>(x, c.xpad.p, c.ncam, c.dc, xs, c.state.p, check_done);
     c.launches++;
@@ -1176,7 +1593,7 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
   const int BATCH = 10;
   int it_count = 0;  // iteration index within this solve: selects the half of the peer buffer (BATCH is even)
   auto enqueue_iteration = [&]() -> apex_status {
-    const int xs = (c.dc + 1) & ~1;
+    const int xs = xpad_stride(c.dc);
     const unsigned gp = (n + PCG_THREADS - 1) / PCG_THREADS, gu = (c.ncam + PCG_CAMS - 1) / PCG_CAMS;
     const int par = it_count++ & 1;
     if (operator_impl() == 0) {

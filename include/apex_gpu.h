@@ -356,6 +356,10 @@ typedef struct apex_layout_stats {
   int32_t consistent;              /* 1 when every structural invariant holds                      */
   int32_t reserved;
   double build_ms;
+  /* camera windows of the Schur operator's chunk groups (window kernel): chunks per group, cameras per window
+   * (0 = windows disabled), groups, and how many local observations fall inside their group's window */
+  uint32_t mv_group, mv_window, mv_ngroups, reserved2;
+  uint64_t nobs_in_window;
 } apex_layout_stats;
 apex_status apex_layout_stats_compute(const apex_problem_desc* desc, int32_t nranks, int32_t rank, apex_layout_stats* out);
 

@@ -308,6 +308,46 @@ def test_operator_fallback_paths(impl, monkeypatch):
     assert relerr(sg[0], so[0]) < 1e-3 and relerr(sg[1], so[1]) < 1e-3  # cond(S) ~1e10: solver-accuracy level agreement
 
 
+@pytest.mark.parametrize("window,group,dc_case", [("320", "8", "selfcal"), ("16", "2", "selfcal"), ("24", "3", "ba"), ("0", "8", "selfcal")])
+def test_operator_window_kernel(window, group, dc_case, monkeypatch):
+    """Window kernel of the operator: camera window of x / y in shared memory per group of chunks. Narrow windows force
+    the out-of-window route (global gather + direct reductions) and the wrap-around of the window on the camera ring;
+    window 0 selects the chunk kernel. Every setting must give the oracle's S x."""
+    monkeypatch.setenv("APEX_MV_WINDOW", window)
+    monkeypatch.setenv("APEX_MV_GROUP", group)
+    prob = small_problem(ncam=90, npts=6000, track=5.0, self_cal=dc_case == "selfcal", window_frac=0.08, seed=21)
+    g, o = pair(prob)
+    g.linearize(1e-3); o.linearize(1e-3)
+    rng = np.random.default_rng(12)
+    for _ in range(2):
+        x = rng.standard_normal(prob.ncam * prob.dc)
+        assert relerr(g.schur_matvec(x), o.schur_matvec(x)) < 1e-11
+    sg = g.solve_augmented(F.SCHUR_IMPLICIT, 1e-3, cg_max_iterations=500, cg_tolerance=1e-12)
+    so = o.solve_augmented(F.SCHUR_IMPLICIT, 1e-3, cg_max_iterations=500, cg_tolerance=1e-12)
+    assert relerr(sg[0], so[0]) < 1e-3 and relerr(sg[1], so[1]) < 1e-3
+
+
+@pytest.mark.parametrize("self_cal", [True, False])
+def test_operator_stream_kernel_ring_reuse(self_cal, monkeypatch):
+    """Stream kernel (persistent CTA per SM, TMA-fed 2-stage ring shared by three consumer groups): enough chunks that
+    every CTA goes round the ring several times (~1 400 chunks on 148 SMs), dc = 9 and dc = 6. Must give the oracle's
+    S x and agree with the chunk kernel (APEX_MV_STREAM=0) to summation-order level."""
+    monkeypatch.setenv("APEX_MV_STREAM", "1")
+    prob = small_problem(ncam=300, npts=70000, track=5.0, self_cal=self_cal, seed=33)
+    g, o = pair(prob)
+    g.linearize(1e-3); o.linearize(1e-3)
+    rng = np.random.default_rng(5)
+    xs = [rng.standard_normal(prob.ncam * prob.dc) for _ in range(2)]
+    ys = [g.schur_matvec(x) for x in xs]
+    for x, y in zip(xs, ys):
+        assert relerr(y, o.schur_matvec(x)) < 1e-11
+    monkeypatch.setenv("APEX_MV_STREAM", "0")
+    g2 = GpuContext().upload(prob)
+    g2.linearize(1e-3)
+    for x, y in zip(xs, ys):
+        assert relerr(g2.schur_matvec(x), y) < 1e-12
+
+
 def test_error_behaviour():
     g = GpuContext()
     with pytest.raises(F.ApexError) as e:

@@ -112,6 +112,28 @@ def test_layout_invariants_incl_long_tracks_and_unobserved_landmarks():
     assert e.value.status == F.ERR_INVALID_INPUT
 
 
+def test_operator_camera_windows(monkeypatch):
+    """Window kernel structure (host side): groups of APEX_MV_GROUP chunks, each with the run of W consecutive cameras
+    (modulo ncam) holding most of its observations. Ring-local tracks => nearly everything inside; ncam <= W => all."""
+    assert layout_stats(synth.make_problem(40, 2000, 4.0, seed=5)).mv_window == 0      # off unless asked for
+    monkeypatch.setenv("APEX_MV_WINDOW", "100000")                                      # "as wide as three CTAs per SM allow"
+    small = synth.make_problem(40, 2000, 4.0, seed=5)
+    s = layout_stats(small)
+    assert s.consistent == 1 and s.mv_window == 40 and s.nobs_in_window == s.nobs_local
+    assert s.mv_group == 8 and s.mv_ngroups == (s.nnormal_chunks + 7) // 8
+    big = synth.make_problem(1500, 30000, 5.0, seed=6)        # window_frac 0.04 -> sigma 60 cameras
+    sb = layout_stats(big)
+    assert sb.consistent == 1 and sb.mv_window == 320          # dc = 9: (76800 - base) / 144 rounded down to 8
+    assert sb.nobs_in_window / sb.nobs_local > 0.95
+    # the window wraps around the ring: a brute-force best window per group must not beat the builder
+    monkeypatch.setenv("APEX_MV_WINDOW", "64")
+    monkeypatch.setenv("APEX_MV_GROUP", "2")
+    s64 = layout_stats(big)
+    assert (s64.mv_window, s64.mv_group) == (64, 2) and 0.2 < s64.nobs_in_window / s64.nobs_local < 0.9
+    monkeypatch.setenv("APEX_MV_WINDOW", "0")
+    assert layout_stats(big).mv_window == 0                     # windows off -> chunk kernel
+
+
 def test_generator_is_deterministic_and_bal_shaped():
     a, b = synth.make_shape("ladybug49"), synth.make_shape("ladybug49")
     for x, y in ((a.pose, b.pose), (a.pt, b.pt), (a.obs_uv, b.obs_uv), (a.obs_cam, b.obs_cam)):
