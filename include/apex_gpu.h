@@ -49,6 +49,11 @@ typedef int32_t apex_status;
 #define APEX_ERR_NCCL (-21)        /* NCCL error                                 */
 #define APEX_ERR_NO_DEVICE (-22)   /* no CUDA device / library built without one */
 #define APEX_ERR_UNSUPPORTED (-23) /* valid in the reference, not on this path   */
+/* IoError (crates/apex-io/src/lib.rs:52-82), BAL loader */
+#define APEX_ERR_IO (-30)             /* IoError::Io (file cannot be read / written)            */
+#define APEX_ERR_PARSE (-31)          /* IoError::Parse{line,message}                           */
+#define APEX_ERR_INVALID_NUMBER (-32) /* IoError::InvalidNumber{line,value}                     */
+#define APEX_ERR_MISSING_FIELDS (-33) /* IoError::MissingFields{line}                           */
 
 /* ---- enums ---------------------------------------------------------------- */
 
@@ -362,6 +367,40 @@ typedef struct apex_layout_stats {
   uint64_t nobs_in_window;
 } apex_layout_stats;
 apex_status apex_layout_stats_compute(const apex_problem_desc* desc, int32_t nranks, int32_t rank, apex_layout_stats* out);
+
+/* ---- BAL files and the CLI's problem construction (host only, no device needed) --------------------
+ * apex_bal_load          <- BalLoader::load (crates/apex-io/src/bal.rs:138-400): blank lines skipped (:144-149),
+ *                           header "ncam npts nobs", nobs lines "cam pt x y", 9 lines per camera (rx ry rz tx ty tz
+ *                           f k1 k2), 3 lines per point; a focal length that is not positive and finite becomes
+ *                           500.0 (:99-113). Errors map on IoError; apex_bal_last_error() holds the reference's
+ *                           message text ("Parse error at line N: ...").
+ * apex_bal_build_problem <- run_bundle_adjustment / add_factors (bin/bundle_adjustment.rs:212-441): axis-angle ->
+ *                           quaternion (angle < 1e-10 -> identity, :200-208), pose storage [t, qw qx qy qz],
+ *                           intrinsics [f,k1,k2], landmarks 0..num_points-1, observations with
+ *                           point_index < num_points in file order, HuberLoss(1.0), pose_0000 fixed (6 DOF).
+ *                           optimization_type: 0 = bundle-adjustment (pose + landmarks), 1 = self-calibration; the
+ *                           CLI's other three types are not functional in the reference and give
+ *                           APEX_ERR_UNSUPPORTED. The arrays behind the returned desc belong to the dataset object
+ *                           and live until apex_bal_free / the next apex_bal_build_problem on it.
+ * apex_bal_write         writes the same format (17 significant digits: values round-trip bit-exactly). */
+typedef struct apex_bal_dataset apex_bal_dataset; /* opaque */
+typedef struct apex_bal_view {
+  uint32_t ncam, npts;
+  uint64_t nobs;
+  const double* cameras;   /* [ncam][9] rx ry rz tx ty tz f k1 k2 (f normalised)          */
+  const double* points;    /* [npts][3]                                                   */
+  const uint32_t* obs_cam; /* [nobs]                                                      */
+  const uint32_t* obs_pt;  /* [nobs]                                                      */
+  const double* obs_uv;    /* [nobs][2]                                                   */
+} apex_bal_view;
+apex_status apex_bal_load(const char* path, apex_bal_dataset** out);
+apex_status apex_bal_from_arrays(uint32_t ncam, uint32_t npts, uint64_t nobs, const double* cameras, const double* points,
+                                 const uint32_t* obs_cam, const uint32_t* obs_pt, const double* obs_uv, apex_bal_dataset** out);
+apex_status apex_bal_view_get(const apex_bal_dataset* ds, apex_bal_view* out);
+apex_status apex_bal_write(const apex_bal_dataset* ds, const char* path);
+apex_status apex_bal_build_problem(apex_bal_dataset* ds, uint64_t num_points, int32_t optimization_type, apex_problem_desc* out);
+void apex_bal_free(apex_bal_dataset* ds);
+const char* apex_bal_last_error(void);
 
 #ifdef __cplusplus
 }
