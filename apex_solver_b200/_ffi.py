@@ -30,6 +30,10 @@ ERR_CUDA = -20
 ERR_NCCL = -21
 ERR_NO_DEVICE = -22
 ERR_UNSUPPORTED = -23
+ERR_IO = -30
+ERR_PARSE = -31
+ERR_INVALID_NUMBER = -32
+ERR_MISSING_FIELDS = -33
 
 ERROR_NAMES = {
     ERR_FACTORIZATION_FAILED: "LinAlgError::FactorizationFailed",
@@ -45,6 +49,10 @@ ERROR_NAMES = {
     ERR_NCCL: "NCCL error",
     ERR_NO_DEVICE: "no CUDA device (there is no CPU fallback)",
     ERR_UNSUPPORTED: "unsupported on the GPU path",
+    ERR_IO: "IoError::Io",
+    ERR_PARSE: "IoError::Parse",
+    ERR_INVALID_NUMBER: "IoError::InvalidNumber",
+    ERR_MISSING_FIELDS: "IoError::MissingFields",
 }
 
 # ---- enums -----------------------------------------------------------------------------------
@@ -128,6 +136,11 @@ class LayoutStats(C.Structure):
                 ("mv_group", C.c_uint32), ("mv_window", C.c_uint32), ("mv_ngroups", C.c_uint32), ("reserved2", C.c_uint32), ("nobs_in_window", C.c_uint64)]
 
 
+class BalView(C.Structure):
+    _fields_ = [("ncam", C.c_uint32), ("npts", C.c_uint32), ("nobs", C.c_uint64), ("cameras", C.c_void_p), ("points", C.c_void_p),
+                ("obs_cam", C.c_void_p), ("obs_pt", C.c_void_p), ("obs_uv", C.c_void_p)]
+
+
 class Dims(C.Structure):
     _fields_ = [("ncam", C.c_uint32), ("npts", C.c_uint32), ("nobs", C.c_uint64), ("intr_dim", C.c_int32), ("dc", C.c_int32),
                 ("cam_dof", C.c_uint64), ("lm_dof", C.c_uint64), ("npts_local", C.c_uint32), ("flags", C.c_uint32),
@@ -163,10 +176,18 @@ SYMBOLS = {
     "profile_enable": (C.c_int32, [C.c_void_p, C.c_int32]),
     "profile_read": (C.c_int32, [C.c_void_p, P(Profile)]),
     "layout_stats_compute": (C.c_int32, [P(ProblemDesc), C.c_int32, C.c_int32, P(LayoutStats)]),
+    "bal_load": (C.c_int32, [C.c_char_p, P(C.c_void_p)]),
+    "bal_from_arrays": (C.c_int32, [C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_void_p)]),
+    "bal_view_get": (C.c_int32, [C.c_void_p, P(BalView)]),
+    "bal_write": (C.c_int32, [C.c_void_p, C.c_char_p]),
+    "bal_build_problem": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_int32, P(ProblemDesc)]),
+    "bal_free": (None, [C.c_void_p]),
+    "bal_last_error": (C.c_char_p, []),
     "shard_info": (C.c_int32, [C.c_uint32, C.c_uint64, C.c_void_p, C.c_int32, C.c_int32, P(C.c_uint32), P(C.c_uint32), P(C.c_uint64)]),
 }
 # entry points the oracle does not implement (GPU-only plumbing)
-GPU_ONLY = {"device_count", "nccl_unique_id", "schur_matvec_bench", "kernel_launches", "profile_enable", "profile_read", "shard_info", "layout_stats_compute"}
+GPU_ONLY = {"device_count", "nccl_unique_id", "schur_matvec_bench", "kernel_launches", "profile_enable", "profile_read", "shard_info", "layout_stats_compute",
+            "bal_load", "bal_from_arrays", "bal_view_get", "bal_write", "bal_build_problem", "bal_free", "bal_last_error"}
 
 
 def bind(lib: C.CDLL, prefix: str, skip=()) -> None:

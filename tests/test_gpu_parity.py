@@ -348,6 +348,28 @@ def test_operator_stream_kernel_ring_reuse(self_cal, monkeypatch):
         assert relerr(g2.schur_matvec(x), y) < 1e-12
 
 
+def test_bal_file_to_gpu_solve(tmp_path):
+    """Data format either side of the path: generator -> BAL text -> apex_bal_load -> apex_bal_build_problem (the CLI's
+    construction, bin/bundle_adjustment.rs:212-441) -> GPU LM, against the oracle on the same loaded problem; and the
+    CLI binary on the same file reports the same iteration count and costs."""
+    import os
+    import re
+    import subprocess
+    from apex_solver_b200.bal import dataset_from_problem, load_bal
+    path = str(tmp_path / "problem-12-400-pre.txt")
+    dataset_from_problem(small_problem(ncam=12, npts=400, seed=41)).write(path)
+    prob = load_bal(path).problem(optimization_type="bundle-adjustment")
+    g, o = pair(prob)
+    (rg, tg), (ro, to) = run_lm(g, F.SCHUR_IMPLICIT, max_it=20), run_lm(o, F.SCHUR_IMPLICIT, max_it=20)
+    assert (rg.status, rg.iterations) == (ro.status, ro.iterations)
+    assert abs(rg.final_cost - ro.final_cost) <= FINAL_RTOL * abs(ro.final_cost)
+    exe = os.path.join(os.path.dirname(F.LIB_PATH), "bundle_adjustment")
+    r = subprocess.run([exe, path, "-t", "bundle-adjustment", "-v"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert int(re.search(r"Iterations: (\d+)", r.stdout).group(1)) == rg.iterations
+    assert abs(float(re.search(r"Final cost: (\S+)", r.stdout).group(1)) - rg.final_cost) <= 1e-5 * abs(rg.final_cost)  # printed with 7 digits
+
+
 def test_error_behaviour():
     g = GpuContext()
     with pytest.raises(F.ApexError) as e:
