@@ -33,10 +33,10 @@ constexpr int TILE = 256;            // slots per chunk = threads per CTA of the
 constexpr uint32_t PAD_CAM = 0xFFFFFFFFu;
 constexpr int CAM_THREADS = 128;     // CTA size of the camera-major accumulation kernels
 constexpr int CAM_CHUNK = 2048;      // observations per camera work item
-constexpr int MAX_DC = 14;
+constexpr int MAX_DC = 15;
 // per-camera stride (doubles) of the padded copy of the operator input: 32-byte aligned blocks for 256-bit gathers
 __host__ __device__ constexpr int xpad_stride(int dc) { return (dc + 3) & ~3; }
-constexpr int MAX_K = 8;
+constexpr int MAX_K = 9;
 
 struct TileDesc {
   uint32_t pt0;      // first local landmark

@@ -132,6 +132,11 @@ template <> struct CamK<APEX_CAM_BAL> { static constexpr int K = 3; };
 template <> struct CamK<APEX_CAM_PINHOLE> { static constexpr int K = 4; };
 template <> struct CamK<APEX_CAM_KANNALA_BRANDT> { static constexpr int K = 8; };
 template <> struct CamK<APEX_CAM_DOUBLE_SPHERE> { static constexpr int K = 6; };
+template <> struct CamK<APEX_CAM_RADTAN> { static constexpr int K = 9; };
+template <> struct CamK<APEX_CAM_UCM> { static constexpr int K = 5; };
+template <> struct CamK<APEX_CAM_EUCM> { static constexpr int K = 6; };
+template <> struct CamK<APEX_CAM_FOV> { static constexpr int K = 5; };
+template <> struct CamK<APEX_CAM_FTHETA> { static constexpr int K = 6; };
 
 inline int model_intr_dim(int model) {
   switch (model) {
@@ -139,6 +144,11 @@ inline int model_intr_dim(int model) {
     case APEX_CAM_PINHOLE: return 4;
     case APEX_CAM_KANNALA_BRANDT: return 8;
     case APEX_CAM_DOUBLE_SPHERE: return 6;
+    case APEX_CAM_RADTAN: return 9;
+    case APEX_CAM_UCM: return 5;
+    case APEX_CAM_EUCM: return 6;
+    case APEX_CAM_FOV: return 5;
+    case APEX_CAM_FTHETA: return 6;
     default: return -1;
   }
 }
@@ -177,7 +187,64 @@ APEX_HD bool cam_project(const double* in, const V3& p, double uv[2]) {
     uv[0] = in[0] * thd * p.x * inv_r + in[2];
     uv[1] = in[1] * thd * p.y * inv_r + in[3];
     return true;
+  } else if constexpr (MODEL == APEX_CAM_RADTAN) {  // rad_tan.rs:351-385, :95-97
+    if (!(p.z >= GEOMETRIC_PRECISION)) return false;
+    double inv_z = 1.0 / p.z;
+    double xp = p.x * inv_z, yp = p.y * inv_z;
+    double r2 = xp * xp + yp * yp, r4 = r2 * r2, r6 = r4 * r2;
+    double k1 = in[4], k2 = in[5], p1 = in[6], p2 = in[7], k3 = in[8];
+    double radial = 1.0 + k1 * r2 + k2 * r4 + k3 * r6;
+    double xy = xp * yp;
+    double dx = 2.0 * p1 * xy + p2 * (r2 + 2.0 * xp * xp);
+    double dy = p1 * (r2 + 2.0 * yp * yp) + 2.0 * p2 * xy;
+    uv[0] = in[0] * (radial * xp + dx) + in[2];
+    uv[1] = in[1] * (radial * yp + dy) + in[3];
+    return true;
+  } else if constexpr (MODEL == APEX_CAM_UCM) {  // ucm.rs:326-356, :100-108
+    double alpha = in[4];
+    double d = sqrt(p.x * p.x + p.y * p.y + p.z * p.z);
+    double denom = alpha * d + (1.0 - alpha) * p.z;
+    double w = alpha <= 0.5 ? alpha / (1.0 - alpha) : (1.0 - alpha) / alpha;
+    if (!(p.z > -w * d)) return false;
+    if (denom < GEOMETRIC_PRECISION) return false;
+    uv[0] = in[0] * p.x / denom + in[2];
+    uv[1] = in[1] * p.y / denom + in[3];
+    return true;
+  } else if constexpr (MODEL == APEX_CAM_EUCM) {  // eucm.rs:346-376, :103-113
+    double alpha = in[4], beta = in[5];
+    double r2 = p.x * p.x + p.y * p.y;
+    double d = sqrt(beta * r2 + p.z * p.z);
+    double denom = alpha * d + (1.0 - alpha) * p.z;
+    if (denom < GEOMETRIC_PRECISION) return false;
+    if (alpha > 0.5) {
+      double c = (alpha - 1.0) / (2.0 * alpha - 1.0);
+      if (p.z < denom * c) return false;
+    }
+    uv[0] = in[0] * p.x / denom + in[2];
+    uv[1] = in[1] * p.y / denom + in[3];
+    return true;
+  } else if constexpr (MODEL == APEX_CAM_FOV) {  // fov.rs:312-340
+    if (p.z < 1.4901161193847656e-08) return false;  // f64::EPSILON.sqrt()
+    double r = sqrt(p.x * p.x + p.y * p.y);
+    double w = in[4];
+    double m2t = tan(w / 2.0) * 2.0;
+    double rd = r > GEOMETRIC_PRECISION ? atan(m2t * r / p.z) / (r * w) : m2t / w;
+    uv[0] = in[0] * (p.x * rd) + in[2];
+    uv[1] = in[1] * (p.y * rd) + in[3];
+    return true;
+  } else if constexpr (MODEL == APEX_CAM_FTHETA) {  // ftheta.rs:229-253, :140-143; intrinsics [cx,cy,k1..k4]
+    if (p.z < MIN_DEPTH) return false;
+    double d = sqrt(p.x * p.x + p.y * p.y + p.z * p.z);
+    double th = acos(fmin(fmax(p.z / d, -1.0), 1.0));
+    double f = th * (in[2] + th * (in[3] + th * (in[4] + th * in[5])));
+    double rp = sqrt(p.x * p.x + p.y * p.y);
+    if (rp < GEOMETRIC_PRECISION) { uv[0] = in[0]; uv[1] = in[1]; return true; }
+    double inv_rp = 1.0 / rp;
+    uv[0] = in[0] + f * p.x * inv_rp;
+    uv[1] = in[1] + f * p.y * inv_rp;
+    return true;
   } else {  // double_sphere.rs:361-392, :118-127
+    static_assert(MODEL == APEX_CAM_DOUBLE_SPHERE, "unknown camera model");
     double xi = in[4], alpha = in[5];
     double r2 = p.x * p.x + p.y * p.y;
     double d1 = sqrt(r2 + p.z * p.z);
@@ -240,6 +307,92 @@ APEX_HD void cam_jacobian_point(const double* in, const V3& p, double J[6]) {
     J[3] = fy * (dthd * dth_dx * y * inv_r - thd * x * y * inv_r2 * inv_r);
     J[4] = fy * (dthd * dth_dy * y * inv_r + thd * (inv_r - y * y * inv_r2 * inv_r));
     J[5] = fy * dthd * dth_dz * y * inv_r;
+  } else if constexpr (MODEL == APEX_CAM_RADTAN) {  // rad_tan.rs:630-680
+    double fx = in[0], fy = in[1], k1 = in[4], k2 = in[5], p1 = in[6], p2 = in[7], k3 = in[8];
+    double inv_z = 1.0 / p.z;
+    double xp = p.x * inv_z, yp = p.y * inv_z;
+    double r2 = xp * xp + yp * yp, r4 = r2 * r2, r6 = r4 * r2;
+    double radial = 1.0 + k1 * r2 + k2 * r4 + k3 * r6;
+    double drad = k1 + 2.0 * k2 * r2 + 3.0 * k3 * r4;
+    double dxx = radial + 2.0 * xp * xp * drad + 2.0 * p1 * yp + 6.0 * p2 * xp;
+    double dxy = 2.0 * xp * yp * drad + 2.0 * p1 * xp + 2.0 * p2 * yp;
+    double dyx = 2.0 * yp * xp * drad + 2.0 * p1 * xp + 2.0 * p2 * yp;
+    double dyy = radial + 2.0 * yp * yp * drad + 6.0 * p1 * yp + 2.0 * p2 * xp;
+    J[0] = fx * (dxx * inv_z);
+    J[1] = fx * (dxy * inv_z);
+    J[2] = fx * (dxx * (-xp * inv_z) + dxy * (-yp * inv_z));
+    J[3] = fy * (dyx * inv_z);
+    J[4] = fy * (dyy * inv_z);
+    J[5] = fy * (dyx * (-xp * inv_z) + dyy * (-yp * inv_z));
+  } else if constexpr (MODEL == APEX_CAM_UCM) {  // ucm.rs:458-503
+    double fx = in[0], fy = in[1], alpha = in[4];
+    double x = p.x, y = p.y, z = p.z;
+    double rho = sqrt(x * x + y * y + z * z);
+    double ddx = alpha * x / rho, ddy = alpha * y / rho, ddz = alpha * z / rho + (1.0 - alpha);
+    double denom = alpha * rho + (1.0 - alpha) * z;
+    double denom2 = denom * denom;
+    J[0] = fx * (denom - x * ddx) / denom2;
+    J[1] = fx * (-x * ddy) / denom2;
+    J[2] = fx * (-x * ddz) / denom2;
+    J[3] = fy * (-y * ddx) / denom2;
+    J[4] = fy * (denom - y * ddy) / denom2;
+    J[5] = fy * (-y * ddz) / denom2;
+  } else if constexpr (MODEL == APEX_CAM_EUCM) {  // eucm.rs:514-548
+    double fx = in[0], fy = in[1], alpha = in[4], beta = in[5];
+    double x = p.x, y = p.y, z = p.z;
+    double r2 = x * x + y * y;
+    double d = sqrt(beta * r2 + z * z);
+    double denom = alpha * d + (1.0 - alpha) * z;
+    double dd_dx = beta * x / d, dd_dy = beta * y / d, dd_dz = z / d;
+    double ddx = alpha * dd_dx, ddy = alpha * dd_dy, ddz = alpha * dd_dz + (1.0 - alpha);
+    double denom2 = denom * denom;
+    J[0] = fx * (denom - x * ddx) / denom2;
+    J[1] = fx * (-x * ddy) / denom2;
+    J[2] = fx * (-x * ddz) / denom2;
+    J[3] = fy * (-y * ddx) / denom2;
+    J[4] = fy * (denom - y * ddy) / denom2;
+    J[5] = fy * (-y * ddz) / denom2;
+  } else if constexpr (MODEL == APEX_CAM_FOV) {  // fov.rs:468-530
+    double fx = in[0], fy = in[1], w = in[4];
+    double x = p.x, y = p.y, z = p.z;
+    double r = sqrt(x * x + y * y);
+    double m2t = tan(w / 2.0) * 2.0;
+    if (r < GEOMETRIC_PRECISION) {
+      double rd = m2t / w;
+      J[0] = fx * rd; J[1] = 0; J[2] = 0; J[3] = 0; J[4] = fy * rd; J[5] = 0;
+      return;
+    }
+    double at = atan(m2t * r / z);
+    double rd = at / (r * w);
+    double datan_dr = m2t * z / (z * z + m2t * m2t * r * r);
+    double datan_dz = -m2t * r / (z * z + m2t * m2t * r * r);
+    double drd_dr = (datan_dr * r - at) / (r * r * w);
+    double drd_dz = datan_dz / (r * w);
+    double dr_dx = x / r, dr_dy = y / r;
+    J[0] = fx * (rd + x * drd_dr * dr_dx);
+    J[1] = fx * (x * drd_dr * dr_dy);
+    J[2] = fx * (x * drd_dz);
+    J[3] = fy * (y * drd_dr * dr_dx);
+    J[4] = fy * (rd + y * drd_dr * dr_dy);
+    J[5] = fy * (y * drd_dz);
+  } else if constexpr (MODEL == APEX_CAM_FTHETA) {  // ftheta.rs:295-327
+    double x = p.x, y = p.y, z = p.z;
+    double rp2 = x * x + y * y, d2 = rp2 + z * z;
+    double d = sqrt(d2), rp = sqrt(rp2);
+    if (rp < GEOMETRIC_PRECISION) {
+      J[0] = in[2] / z; J[1] = 0; J[2] = 0; J[3] = 0; J[4] = in[2] / z; J[5] = 0;
+      return;
+    }
+    double th = acos(fmin(fmax(z / d, -1.0), 1.0));
+    double f = th * (in[2] + th * (in[3] + th * (in[4] + th * in[5])));
+    double fp = in[2] + th * (2.0 * in[3] + th * (3.0 * in[4] + th * 4.0 * in[5]));
+    double a = fp * z / (rp2 * d2), b = f / (rp2 * rp);
+    J[0] = a * x * x + b * y * y;
+    J[1] = (a - b) * x * y;
+    J[2] = -fp * x / d2;
+    J[3] = J[1];
+    J[4] = a * y * y + b * x * x;
+    J[5] = -fp * y / d2;
   } else {  // double_sphere.rs:532-583
     double fx = in[0], fy = in[1], xi = in[4], alpha = in[5];
     double x = p.x, y = p.y, z = p.z;
@@ -296,6 +449,72 @@ APEX_HD void cam_jacobian_intrinsics(const double* in, const V3& p, double* J) {
     J[4] = fx * t3 * x * inv_r; J[5] = fx * t5 * x * inv_r; J[6] = fx * t7 * x * inv_r; J[7] = fx * t9 * x * inv_r;
     J[8] = 0; J[9] = y * thd * inv_r; J[10] = 0; J[11] = 1;
     J[12] = fy * t3 * y * inv_r; J[13] = fy * t5 * y * inv_r; J[14] = fy * t7 * y * inv_r; J[15] = fy * t9 * y * inv_r;
+  } else if constexpr (MODEL == APEX_CAM_RADTAN) {  // rad_tan.rs:783-851
+    double fx = in[0], fy = in[1], k1 = in[4], k2 = in[5], p1 = in[6], p2 = in[7], k3 = in[8];
+    double inv_z = 1.0 / p.z;
+    double xp = p.x * inv_z, yp = p.y * inv_z;
+    double r2 = xp * xp + yp * yp, r4 = r2 * r2, r6 = r4 * r2;
+    double radial = 1.0 + k1 * r2 + k2 * r4 + k3 * r6;
+    double xy = xp * yp;
+    double dx = 2.0 * p1 * xy + p2 * (r2 + 2.0 * xp * xp);
+    double dy = p1 * (r2 + 2.0 * yp * yp) + 2.0 * p2 * xy;
+    J[0] = radial * xp + dx; J[1] = 0; J[2] = 1; J[3] = 0;
+    J[4] = fx * xp * r2; J[5] = fx * xp * r4; J[6] = fx * 2.0 * xy; J[7] = fx * (r2 + 2.0 * xp * xp); J[8] = fx * xp * r6;
+    J[9] = 0; J[10] = radial * yp + dy; J[11] = 0; J[12] = 1;
+    J[13] = fy * yp * r2; J[14] = fy * yp * r4; J[15] = fy * (r2 + 2.0 * yp * yp); J[16] = fy * 2.0 * xy; J[17] = fy * yp * r6;
+  } else if constexpr (MODEL == APEX_CAM_UCM) {  // ucm.rs:549-598
+    double fx = in[0], fy = in[1], alpha = in[4];
+    double x = p.x, y = p.y, z = p.z;
+    double rho = sqrt(x * x + y * y + z * z);
+    double denom = alpha * rho + (1.0 - alpha) * z;
+    double xn = x / denom, yn = y / denom;
+    double ucx = fx * xn, vcy = fy * yn;
+    double dda = rho - z;
+    J[0] = xn; J[1] = 0; J[2] = 1; J[3] = 0; J[4] = -ucx * dda / denom;
+    J[5] = 0; J[6] = yn; J[7] = 0; J[8] = 1; J[9] = -vcy * dda / denom;
+  } else if constexpr (MODEL == APEX_CAM_EUCM) {  // eucm.rs:652-696
+    double fx = in[0], fy = in[1], alpha = in[4], beta = in[5];
+    double x = p.x, y = p.y, z = p.z;
+    double r2 = x * x + y * y;
+    double d = sqrt(beta * r2 + z * z);
+    double denom = alpha * d + (1.0 - alpha) * z;
+    double dda = d - z;
+    double ddb = alpha * (r2 / (2.0 * d));
+    J[0] = x / denom; J[1] = 0; J[2] = 1; J[3] = 0;
+    J[4] = -fx * x * dda / (denom * denom); J[5] = -fx * x * ddb / (denom * denom);
+    J[6] = 0; J[7] = y / denom; J[8] = 0; J[9] = 1;
+    J[10] = -fy * y * dda / (denom * denom); J[11] = -fy * y * ddb / (denom * denom);
+  } else if constexpr (MODEL == APEX_CAM_FOV) {  // fov.rs:647-708
+    double fx = in[0], fy = in[1], w = in[4];
+    double x = p.x, y = p.y, z = p.z;
+    double r = sqrt(x * x + y * y);
+    double t2 = tan(w / 2.0);
+    double m2t = t2 * 2.0;
+    double rd = r > GEOMETRIC_PRECISION ? atan(m2t * r / z) / (r * w) : m2t / w;
+    double sec2 = 1.0 + t2 * t2;
+    double drd_dw;
+    if (r > GEOMETRIC_PRECISION) {
+      double al = 2.0 * t2 * r / z;
+      double at = atan(al);
+      double dal_dw = sec2 * r / z;
+      double datan_dw = dal_dw / (1.0 + al * al);
+      drd_dw = (datan_dw * r * w - at * r) / (r * r * w * w);
+    } else {
+      drd_dw = (sec2 * w - 2.0 * t2) / (w * w);
+    }
+    J[0] = x * rd; J[1] = 0; J[2] = 1; J[3] = 0; J[4] = fx * x * drd_dw;
+    J[5] = 0; J[6] = y * rd; J[7] = 0; J[8] = 1; J[9] = fy * y * drd_dw;
+  } else if constexpr (MODEL == APEX_CAM_FTHETA) {  // ftheta.rs:329-356
+    double x = p.x, y = p.y, z = p.z;
+    double rp2 = x * x + y * y;
+    double rp = sqrt(rp2), d = sqrt(rp2 + z * z);
+    for (int a = 0; a < 12; ++a) J[a] = 0.0;
+    J[0] = 1.0; J[7] = 1.0;
+    if (rp < GEOMETRIC_PRECISION) return;
+    double th = acos(fmin(fmax(z / d, -1.0), 1.0));
+    double cphi = x / rp, sphi = y / rp;
+    double tp = th;
+    for (int col = 2; col < 6; ++col) { J[col] = tp * cphi; J[6 + col] = tp * sphi; tp *= th; }
   } else {  // double_sphere.rs:691-731
     double fx = in[0], fy = in[1], xi = in[4], alpha = in[5];
     double x = p.x, y = p.y, z = p.z;

@@ -494,7 +494,9 @@ apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol) {
       case 9: schur_form_kernel<9><<<c.ntiles, TILE, 0, s>>>(fa); break;
       case 10: schur_form_kernel<10><<<c.ntiles, TILE, 0, s>>>(fa); break;
       case 12: schur_form_kernel<12><<<c.ntiles, TILE, 0, s>>>(fa); break;
+      case 11: schur_form_kernel<11><<<c.ntiles, TILE, 0, s>>>(fa); break;
       case 14: schur_form_kernel<14><<<c.ntiles, TILE, 0, s>>>(fa); break;
+      case 15: schur_form_kernel<15><<<c.ntiles, TILE, 0, s>>>(fa); break;
       default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
     }
     c.launches++;

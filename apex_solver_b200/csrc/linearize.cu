@@ -425,6 +425,11 @@ static CamArgs make_cam_args(Ctx& c) {
     case APEX_CAM_PINHOLE: if ((c).opt_intr) { CALL(APEX_CAM_PINHOLE, true); } else { CALL(APEX_CAM_PINHOLE, false); } break; \
     case APEX_CAM_KANNALA_BRANDT: if ((c).opt_intr) { CALL(APEX_CAM_KANNALA_BRANDT, true); } else { CALL(APEX_CAM_KANNALA_BRANDT, false); } break; \
     case APEX_CAM_DOUBLE_SPHERE: if ((c).opt_intr) { CALL(APEX_CAM_DOUBLE_SPHERE, true); } else { CALL(APEX_CAM_DOUBLE_SPHERE, false); } break; \
+    case APEX_CAM_RADTAN: if ((c).opt_intr) { CALL(APEX_CAM_RADTAN, true); } else { CALL(APEX_CAM_RADTAN, false); } break; \
+    case APEX_CAM_UCM: if ((c).opt_intr) { CALL(APEX_CAM_UCM, true); } else { CALL(APEX_CAM_UCM, false); } break; \
+    case APEX_CAM_EUCM: if ((c).opt_intr) { CALL(APEX_CAM_EUCM, true); } else { CALL(APEX_CAM_EUCM, false); } break; \
+    case APEX_CAM_FOV: if ((c).opt_intr) { CALL(APEX_CAM_FOV, true); } else { CALL(APEX_CAM_FOV, false); } break; \
+    case APEX_CAM_FTHETA: if ((c).opt_intr) { CALL(APEX_CAM_FTHETA, true); } else { CALL(APEX_CAM_FTHETA, false); } break; \
     default: (c).err = "camera model not supported"; return APEX_ERR_UNSUPPORTED;           \
   }
 
@@ -455,7 +460,9 @@ apex_status launch_linearize(Ctx& c) {
       case 9: camera_finalize_hcc_kernel<9><<<grid, 256, 0, s>>>(ca); break;
       case 10: camera_finalize_hcc_kernel<10><<<grid, 256, 0, s>>>(ca); break;
       case 12: camera_finalize_hcc_kernel<12><<<grid, 256, 0, s>>>(ca); break;
+      case 11: camera_finalize_hcc_kernel<11><<<grid, 256, 0, s>>>(ca); break;
       case 14: camera_finalize_hcc_kernel<14><<<grid, 256, 0, s>>>(ca); break;
+      case 15: camera_finalize_hcc_kernel<15><<<grid, 256, 0, s>>>(ca); break;
       default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
     }
     c.launches++;
@@ -503,7 +510,9 @@ apex_status launch_schur_jacobi_blocks(Ctx& c, int kind) {
       case 3: CALLF(3); break;
       case 4: CALLF(4); break;
       case 6: CALLF(6); break;
+      case 5: CALLF(5); break;
       case 8: CALLF(8); break;
+      case 9: CALLF(9); break;
       default: c.err = "unsupported K"; return APEX_ERR_UNSUPPORTED;
     }
 #undef CALLF
@@ -516,7 +525,9 @@ apex_status launch_schur_jacobi_blocks(Ctx& c, int kind) {
     case 3: precond_invert_kernel<3><<<grid, 64, 0, s>>>(c.hcc.p, c.sj.p, c.pinv.p, c.state.p, c.ncam, c.dc, kind, c.opt_intr); break;
     case 4: precond_invert_kernel<4><<<grid, 64, 0, s>>>(c.hcc.p, c.sj.p, c.pinv.p, c.state.p, c.ncam, c.dc, kind, c.opt_intr); break;
     case 6: precond_invert_kernel<6><<<grid, 64, 0, s>>>(c.hcc.p, c.sj.p, c.pinv.p, c.state.p, c.ncam, c.dc, kind, c.opt_intr); break;
+    case 5: precond_invert_kernel<5><<<grid, 64, 0, s>>>(c.hcc.p, c.sj.p, c.pinv.p, c.state.p, c.ncam, c.dc, kind, c.opt_intr); break;
     case 8: precond_invert_kernel<8><<<grid, 64, 0, s>>>(c.hcc.p, c.sj.p, c.pinv.p, c.state.p, c.ncam, c.dc, kind, c.opt_intr); break;
+    case 9: precond_invert_kernel<9><<<grid, 64, 0, s>>>(c.hcc.p, c.sj.p, c.pinv.p, c.state.p, c.ncam, c.dc, kind, c.opt_intr); break;
     default: c.err = "unsupported K"; return APEX_ERR_UNSUPPORTED;
   }
   c.launches++;

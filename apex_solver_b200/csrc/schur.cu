@@ -517,7 +517,9 @@ static apex_status launch_pingpong(Ctx& c, const PpArgs& a, bool priv, unsigned 
     case 9: return launch_pingpong_dc<9, MODE>(c, a, priv, grid);
     case 10: return launch_pingpong_dc<10, MODE>(c, a, priv, grid);
     case 12: return launch_pingpong_dc<12, MODE>(c, a, priv, grid);
+    case 11: return launch_pingpong_dc<11, MODE>(c, a, priv, grid);
     case 14: return launch_pingpong_dc<14, MODE>(c, a, priv, grid);
+    case 15: return launch_pingpong_dc<15, MODE>(c, a, priv, grid);
     default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
   }
 }
@@ -1444,7 +1446,9 @@ apex_status launch_schur_tiles(Ctx& c, int mode, const double* x, double* y, int
     case 9: launch_tiles_dc<9>(c, mode, a); break;
     case 10: launch_tiles_dc<10>(c, mode, a); break;
     case 12: launch_tiles_dc<12>(c, mode, a); break;
+    case 11: launch_tiles_dc<11>(c, mode, a); break;
     case 14: launch_tiles_dc<14>(c, mode, a); break;
+    case 15: launch_tiles_dc<15>(c, mode, a); break;
     default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
   }
   APEX_CUDA_TRY(c, cudaGetLastError());
@@ -1476,7 +1480,9 @@ static apex_status launch_giant_tiles(Ctx& c, const double* x, double* y, int ch
     case 9: schur_tile_kernel<9, MODE_MATVEC><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
     case 10: schur_tile_kernel<10, MODE_MATVEC><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
     case 12: schur_tile_kernel<12, MODE_MATVEC><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
+    case 11: schur_tile_kernel<11, MODE_MATVEC><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
     case 14: schur_tile_kernel<14, MODE_MATVEC><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
+    case 15: schur_tile_kernel<15, MODE_MATVEC><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
     default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
   }
   c.launches++;
@@ -1508,7 +1514,9 @@ apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_d
     case 9: need = pp_smem_bytes<9>(n, true); break;
     case 10: need = pp_smem_bytes<10>(n, true); break;
     case 12: need = pp_smem_bytes<12>(n, true); break;
+    case 11: need = pp_smem_bytes<11>(n, true); break;
     case 14: need = pp_smem_bytes<14>(n, true); break;
+    case 15: need = pp_smem_bytes<15>(n, true); break;
     default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
   }
   const bool priv = need <= (size_t)MV_SMEM_MAX && impl != 4;

@@ -130,6 +130,47 @@ def project(model, intr, pc):
         valid = (z > -w2 * d1) & (den >= 1e-6)
         den = np.where(valid, den, 1.0)
         return np.stack([intr[:, 0] * x / den + intr[:, 2], intr[:, 1] * y / den + intr[:, 3]], 1), valid
+    if model == F.CAM_RADTAN:
+        valid = z >= 1e-6
+        zz = np.where(valid, z, 1.0)
+        xp, yp = x / zz, y / zz
+        r2 = xp * xp + yp * yp
+        k1, k2, p1, p2, k3 = (intr[:, i] for i in range(4, 9))
+        radial = 1 + k1 * r2 + k2 * r2 * r2 + k3 * r2 ** 3
+        dx = 2 * p1 * xp * yp + p2 * (r2 + 2 * xp * xp)
+        dy = p1 * (r2 + 2 * yp * yp) + 2 * p2 * xp * yp
+        return np.stack([intr[:, 0] * (radial * xp + dx) + intr[:, 2], intr[:, 1] * (radial * yp + dy) + intr[:, 3]], 1), valid
+    if model in (F.CAM_UCM, F.CAM_EUCM):
+        al = intr[:, 4]
+        beta = intr[:, 5] if model == F.CAM_EUCM else np.ones_like(al)
+        r2 = x * x + y * y
+        d = np.sqrt(beta * r2 + z * z)
+        den = al * d + (1 - al) * z
+        if model == F.CAM_UCM:
+            w = np.where(al <= 0.5, al / (1 - al), (1 - al) / al)
+            valid = (z > -w * d) & (den >= 1e-6)
+        else:
+            valid = (den >= 1e-6) & ~((al > 0.5) & (z < den * (al - 1) / np.where(al > 0.5, 2 * al - 1, 1.0)))
+        den = np.where(valid, den, 1.0)
+        return np.stack([intr[:, 0] * x / den + intr[:, 2], intr[:, 1] * y / den + intr[:, 3]], 1), valid
+    if model == F.CAM_FOV:
+        valid = z >= np.sqrt(np.finfo(np.float64).eps)
+        zz = np.where(valid, z, 1.0)
+        r = np.sqrt(x * x + y * y)
+        w = intr[:, 4]
+        m2t = 2 * np.tan(w / 2)
+        rr = np.where(r > 1e-6, r, 1.0)
+        rd = np.where(r > 1e-6, np.arctan(m2t * rr / zz) / (rr * w), m2t / w)
+        return np.stack([intr[:, 0] * x * rd + intr[:, 2], intr[:, 1] * y * rd + intr[:, 3]], 1), valid
+    if model == F.CAM_FTHETA:
+        valid = z >= 1e-6
+        d = np.sqrt(x * x + y * y + z * z)
+        th = np.arccos(np.clip(z / np.where(d > 0, d, 1.0), -1.0, 1.0))
+        f = th * (intr[:, 2] + th * (intr[:, 3] + th * (intr[:, 4] + th * intr[:, 5])))
+        rp = np.sqrt(x * x + y * y)
+        rr = np.where(rp < 1e-6, 1.0, rp)
+        s_ = np.where(rp < 1e-6, 0.0, f / rr)
+        return np.stack([intr[:, 0] + s_ * x, intr[:, 1] + s_ * y], 1), valid
     raise ValueError(f"camera model {model} not supported by the generator")
 
 
@@ -160,6 +201,16 @@ def _intrinsics(rng, ncam, model):
         return np.stack([j(200.0), j(200.0), j(300.0), j(200.0), j(0.5), j(0.1), 0.001 * rng.standard_normal(ncam), 0.0001 * rng.standard_normal(ncam)], 1)
     if model == F.CAM_DOUBLE_SPHERE:   # tests/camera_double_sphere_integration.rs:52-63
         return np.stack([j(200.0), j(200.0), j(300.0), j(200.0), j(0.5), j(0.5)], 1)
+    if model == F.CAM_RADTAN:          # rad_tan.rs:895-903 (test camera), focal scaled like the other +z models
+        return np.stack([j(200.0), j(200.0), j(300.0), j(200.0), j(0.1), j(0.01), j(0.001), j(0.002), j(0.001)], 1)
+    if model == F.CAM_UCM:             # ucm.rs:715-717
+        return np.stack([j(200.0), j(200.0), j(300.0), j(200.0), j(0.6)], 1)
+    if model == F.CAM_EUCM:            # eucm.rs:863-868
+        return np.stack([j(200.0), j(200.0), j(300.0), j(200.0), j(0.7), j(1.5)], 1)
+    if model == F.CAM_FOV:             # fov.rs:757-759
+        return np.stack([j(200.0), j(200.0), j(300.0), j(200.0), j(1.5)], 1)
+    if model == F.CAM_FTHETA:          # ftheta.rs:453-455, scaled to the same image size
+        return np.stack([j(300.0), j(200.0), j(200.0), j(-4.0), j(0.8), j(-0.04)], 1)
     raise ValueError(model)
 
 

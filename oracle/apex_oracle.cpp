@@ -163,6 +163,11 @@ int model_intr_dim(int model) {
     case APEX_CAM_PINHOLE: return 4;
     case APEX_CAM_KANNALA_BRANDT: return 8;
     case APEX_CAM_DOUBLE_SPHERE: return 6;
+    case APEX_CAM_RADTAN: return 9;   // rad_tan.rs:333
+    case APEX_CAM_UCM: return 5;      // ucm.rs:300
+    case APEX_CAM_EUCM: return 6;     // eucm.rs:320
+    case APEX_CAM_FOV: return 5;      // fov.rs:291
+    case APEX_CAM_FTHETA: return 6;   // ftheta.rs:224
     default: return -1;
   }
 }
@@ -218,6 +223,81 @@ bool cam_project(int model, const double* in, const V3& p, double uv[2]) {
       if (denom < GEOMETRIC_PRECISION) return false;
       uv[0] = in[0] * p.x / denom + in[2];
       uv[1] = in[1] * p.y / denom + in[3];
+      return true;
+    }
+    case APEX_CAM_RADTAN: {  // rad_tan.rs:351-385; check_projection_condition :95-97 (z >= GEOMETRIC_PRECISION)
+      if (!(p.z >= GEOMETRIC_PRECISION)) return false;
+      const double fx = in[0], fy = in[1], cx = in[2], cy = in[3], k1 = in[4], k2 = in[5], p1 = in[6], p2 = in[7], k3 = in[8];
+      const double inv_z = 1.0 / p.z;
+      const double x_prime = p.x * inv_z, y_prime = p.y * inv_z;
+      const double r2 = x_prime * x_prime + y_prime * y_prime;
+      const double r4 = r2 * r2;
+      const double r6 = r4 * r2;
+      const double radial = 1.0 + k1 * r2 + k2 * r4 + k3 * r6;
+      const double xy = x_prime * y_prime;
+      const double dx = 2.0 * p1 * xy + p2 * (r2 + 2.0 * x_prime * x_prime);
+      const double dy = p1 * (r2 + 2.0 * y_prime * y_prime) + 2.0 * p2 * xy;
+      const double x_distorted = radial * x_prime + dx, y_distorted = radial * y_prime + dy;
+      uv[0] = fx * x_distorted + cx;
+      uv[1] = fy * y_distorted + cy;
+      return true;
+    }
+    case APEX_CAM_UCM: {  // ucm.rs:326-356; check_projection_condition :100-108
+      const double alpha = in[4];
+      const double d = std::sqrt(p.x * p.x + p.y * p.y + p.z * p.z);
+      const double denom = alpha * d + (1.0 - alpha) * p.z;
+      const double w = alpha <= 0.5 ? alpha / (1.0 - alpha) : (1.0 - alpha) / alpha;
+      if (!(p.z > -w * d)) return false;           // PointBehindCamera
+      if (denom < GEOMETRIC_PRECISION) return false;  // DenominatorTooSmall
+      uv[0] = in[0] * p.x / denom + in[2];
+      uv[1] = in[1] * p.y / denom + in[3];
+      return true;
+    }
+    case APEX_CAM_EUCM: {  // eucm.rs:346-376; check_projection_condition :103-113
+      const double alpha = in[4], beta = in[5];
+      const double r2 = p.x * p.x + p.y * p.y;
+      const double d = std::sqrt(beta * r2 + p.z * p.z);
+      const double denom = alpha * d + (1.0 - alpha) * p.z;
+      if (denom < GEOMETRIC_PRECISION) return false;
+      bool condition = true;
+      if (alpha > 0.5) {
+        const double c = (alpha - 1.0) / (2.0 * alpha - 1.0);
+        if (p.z < denom * c) condition = false;
+      }
+      if (!condition) return false;
+      uv[0] = in[0] * p.x / denom + in[2];
+      uv[1] = in[1] * p.y / denom + in[3];
+      return true;
+    }
+    case APEX_CAM_FOV: {  // fov.rs:312-340
+      if (p.z < std::sqrt(F64_EPS)) return false;  // ProjectionOutOfBounds
+      const double r = std::sqrt(p.x * p.x + p.y * p.y);
+      const double w = in[4];
+      const double tan_w_2 = std::tan(w / 2.0);
+      const double mul2tanwby2 = tan_w_2 * 2.0;
+      double rd;
+      if (r > GEOMETRIC_PRECISION) {
+        const double atan_wrd = std::atan(mul2tanwby2 * r / p.z);
+        rd = atan_wrd / (r * w);
+      } else {
+        rd = mul2tanwby2 / w;
+      }
+      const double mx = p.x * rd, my = p.y * rd;
+      uv[0] = in[0] * mx + in[2];
+      uv[1] = in[1] * my + in[3];
+      return true;
+    }
+    case APEX_CAM_FTHETA: {  // ftheta.rs:229-253, poly_forward :140-143; intrinsics [cx, cy, k1, k2, k3, k4]
+      if (p.z < MIN_DEPTH) return false;
+      const double cx = in[0], cy = in[1], k1 = in[2], k2 = in[3], k3 = in[4], k4 = in[5];
+      const double d = std::sqrt(p.x * p.x + p.y * p.y + p.z * p.z);
+      const double theta = std::acos(std::min(std::max(p.z / d, -1.0), 1.0));
+      const double f_theta = theta * (k1 + theta * (k2 + theta * (k3 + theta * k4)));
+      const double r_p = std::sqrt(p.x * p.x + p.y * p.y);
+      if (r_p < GEOMETRIC_PRECISION) { uv[0] = cx; uv[1] = cy; return true; }
+      const double inv_rp = 1.0 / r_p;
+      uv[0] = cx + f_theta * p.x * inv_rp;
+      uv[1] = cy + f_theta * p.y * inv_rp;
       return true;
     }
   }
@@ -300,6 +380,104 @@ void cam_jacobian_point(int model, const double* in, const V3& p, double J[6]) {
       J[5] = fy * (-y * dn_dz) / denom2;
       return;
     }
+    case APEX_CAM_RADTAN: {  // rad_tan.rs:630-680
+      const double fx = in[0], fy = in[1], k1 = in[4], k2 = in[5], p1 = in[6], p2 = in[7], k3 = in[8];
+      const double inv_z = 1.0 / p.z;
+      const double x_prime = p.x * inv_z, y_prime = p.y * inv_z;
+      const double r2 = x_prime * x_prime + y_prime * y_prime;
+      const double r4 = r2 * r2;
+      const double r6 = r4 * r2;
+      const double radial = 1.0 + k1 * r2 + k2 * r4 + k3 * r6;
+      const double dradial_dr2 = k1 + 2.0 * k2 * r2 + 3.0 * k3 * r4;
+      const double dx_dist_dx_prime = radial + 2.0 * x_prime * x_prime * dradial_dr2 + 2.0 * p1 * y_prime + 6.0 * p2 * x_prime;
+      const double dx_dist_dy_prime = 2.0 * x_prime * y_prime * dradial_dr2 + 2.0 * p1 * x_prime + 2.0 * p2 * y_prime;
+      const double dy_dist_dx_prime = 2.0 * y_prime * x_prime * dradial_dr2 + 2.0 * p1 * x_prime + 2.0 * p2 * y_prime;
+      const double dy_dist_dy_prime = radial + 2.0 * y_prime * y_prime * dradial_dr2 + 6.0 * p1 * y_prime + 2.0 * p2 * x_prime;
+      J[0] = fx * (dx_dist_dx_prime * inv_z);
+      J[1] = fx * (dx_dist_dy_prime * inv_z);
+      J[2] = fx * (dx_dist_dx_prime * (-x_prime * inv_z) + dx_dist_dy_prime * (-y_prime * inv_z));
+      J[3] = fy * (dy_dist_dx_prime * inv_z);
+      J[4] = fy * (dy_dist_dy_prime * inv_z);
+      J[5] = fy * (dy_dist_dx_prime * (-x_prime * inv_z) + dy_dist_dy_prime * (-y_prime * inv_z));
+      return;
+    }
+    case APEX_CAM_UCM: {  // ucm.rs:458-503
+      const double fx = in[0], fy = in[1], alpha = in[4];
+      const double x = p.x, y = p.y, z = p.z;
+      const double rho = std::sqrt(x * x + y * y + z * z);
+      const double d_denom_dx = alpha * x / rho, d_denom_dy = alpha * y / rho, d_denom_dz = alpha * z / rho + (1.0 - alpha);
+      const double denom = alpha * rho + (1.0 - alpha) * z;
+      const double denom2 = denom * denom;
+      J[0] = fx * (denom - x * d_denom_dx) / denom2;
+      J[1] = fx * (-x * d_denom_dy) / denom2;
+      J[2] = fx * (-x * d_denom_dz) / denom2;
+      J[3] = fy * (-y * d_denom_dx) / denom2;
+      J[4] = fy * (denom - y * d_denom_dy) / denom2;
+      J[5] = fy * (-y * d_denom_dz) / denom2;
+      return;
+    }
+    case APEX_CAM_EUCM: {  // eucm.rs:514-548
+      const double fx = in[0], fy = in[1], alpha = in[4], beta = in[5];
+      const double x = p.x, y = p.y, z = p.z;
+      const double r2 = x * x + y * y;
+      const double d = std::sqrt(beta * r2 + z * z);
+      const double denom = alpha * d + (1.0 - alpha) * z;
+      const double dd_dx = beta * x / d, dd_dy = beta * y / d, dd_dz = z / d;
+      const double ddenom_dx = alpha * dd_dx, ddenom_dy = alpha * dd_dy, ddenom_dz = alpha * dd_dz + (1.0 - alpha);
+      const double denom2 = denom * denom;
+      J[0] = fx * (denom - x * ddenom_dx) / denom2;
+      J[1] = fx * (-x * ddenom_dy) / denom2;
+      J[2] = fx * (-x * ddenom_dz) / denom2;
+      J[3] = fy * (-y * ddenom_dx) / denom2;
+      J[4] = fy * (denom - y * ddenom_dy) / denom2;
+      J[5] = fy * (-y * ddenom_dz) / denom2;
+      return;
+    }
+    case APEX_CAM_FOV: {  // fov.rs:468-530
+      const double fx = in[0], fy = in[1], w = in[4];
+      const double x = p.x, y = p.y, z = p.z;
+      const double r = std::sqrt(x * x + y * y);
+      const double tan_w_2 = std::tan(w / 2.0);
+      const double mul2tanwby2 = tan_w_2 * 2.0;
+      if (r < GEOMETRIC_PRECISION) {
+        const double rd = mul2tanwby2 / w;
+        J[0] = fx * rd; J[1] = 0.0; J[2] = 0.0; J[3] = 0.0; J[4] = fy * rd; J[5] = 0.0;
+        return;
+      }
+      const double atan_wrd = std::atan(mul2tanwby2 * r / z);
+      const double rd = atan_wrd / (r * w);
+      const double datan_dr = mul2tanwby2 * z / (z * z + mul2tanwby2 * mul2tanwby2 * r * r);
+      const double datan_dz = -mul2tanwby2 * r / (z * z + mul2tanwby2 * mul2tanwby2 * r * r);
+      const double drd_dr = (datan_dr * r - atan_wrd) / (r * r * w);
+      const double drd_dz = datan_dz / (r * w);
+      const double dr_dx = x / r, dr_dy = y / r;
+      const double dmx_dx = rd + x * drd_dr * dr_dx, dmx_dy = x * drd_dr * dr_dy, dmx_dz = x * drd_dz;
+      const double dmy_dx = y * drd_dr * dr_dx, dmy_dy = rd + y * drd_dr * dr_dy, dmy_dz = y * drd_dz;
+      J[0] = fx * dmx_dx; J[1] = fx * dmx_dy; J[2] = fx * dmx_dz;
+      J[3] = fy * dmy_dx; J[4] = fy * dmy_dy; J[5] = fy * dmy_dz;
+      return;
+    }
+    case APEX_CAM_FTHETA: {  // ftheta.rs:295-327, poly_forward / poly_forward_deriv :140-150
+      const double k1 = in[2], k2 = in[3], k3 = in[4], k4 = in[5];
+      const double x = p.x, y = p.y, z = p.z;
+      const double r_p2 = x * x + y * y;
+      const double d2 = r_p2 + z * z;
+      const double d = std::sqrt(d2), r_p = std::sqrt(r_p2);
+      for (int a = 0; a < 6; ++a) J[a] = 0.0;
+      if (r_p < GEOMETRIC_PRECISION) { J[0] = k1 / z; J[4] = k1 / z; return; }
+      const double theta = std::acos(std::min(std::max(z / d, -1.0), 1.0));
+      const double f_val = theta * (k1 + theta * (k2 + theta * (k3 + theta * k4)));
+      const double f_prime = k1 + theta * (2.0 * k2 + theta * (3.0 * k3 + theta * 4.0 * k4));
+      const double a = f_prime * z / (r_p2 * d2);
+      const double b = f_val / (r_p2 * r_p);
+      J[0] = a * x * x + b * y * y;
+      J[1] = (a - b) * x * y;
+      J[2] = -f_prime * x / d2;
+      J[3] = J[1];
+      J[4] = a * y * y + b * x * x;
+      J[5] = -f_prime * y / d2;
+      return;
+    }
   }
 }
 
@@ -357,6 +535,96 @@ void cam_jacobian_intrinsics(int model, const double* in, const V3& p, double* J
       J[4] = -fx * x * dn_dxi * inv_denom2; J[5] = -fx * x * dn_dalpha * inv_denom2;
       J[6] = 0; J[7] = y * inv_denom; J[8] = 0; J[9] = 1;
       J[10] = -fy * y * dn_dxi * inv_denom2; J[11] = -fy * y * dn_dalpha * inv_denom2;
+      return;
+    }
+    case APEX_CAM_RADTAN: {  // rad_tan.rs:783-851; columns [fx, fy, cx, cy, k1, k2, p1, p2, k3]
+      const double fx = in[0], fy = in[1], k1 = in[4], k2 = in[5], p1 = in[6], p2 = in[7], k3 = in[8];
+      const double inv_z = 1.0 / p.z;
+      const double x_prime = p.x * inv_z, y_prime = p.y * inv_z;
+      const double r2 = x_prime * x_prime + y_prime * y_prime;
+      const double r4 = r2 * r2;
+      const double r6 = r4 * r2;
+      const double radial = 1.0 + k1 * r2 + k2 * r4 + k3 * r6;
+      const double xy = x_prime * y_prime;
+      const double dx = 2.0 * p1 * xy + p2 * (r2 + 2.0 * x_prime * x_prime);
+      const double dy = p1 * (r2 + 2.0 * y_prime * y_prime) + 2.0 * p2 * xy;
+      const double row0[9] = {radial * x_prime + dx, 0.0, 1.0, 0.0, fx * x_prime * r2, fx * x_prime * r4, fx * 2.0 * xy, fx * (r2 + 2.0 * x_prime * x_prime), fx * x_prime * r6};
+      const double row1[9] = {0.0, radial * y_prime + dy, 0.0, 1.0, fy * y_prime * r2, fy * y_prime * r4, fy * (r2 + 2.0 * y_prime * y_prime), fy * 2.0 * xy, fy * y_prime * r6};
+      for (int a = 0; a < 9; ++a) { J[a] = row0[a]; J[9 + a] = row1[a]; }
+      return;
+    }
+    case APEX_CAM_UCM: {  // ucm.rs:549-598; columns [fx, fy, cx, cy, alpha]
+      const double fx = in[0], fy = in[1], alpha = in[4];
+      const double x = p.x, y = p.y, z = p.z;
+      const double rho = std::sqrt(x * x + y * y + z * z);
+      const double denom = alpha * rho + (1.0 - alpha) * z;
+      const double x_norm = x / denom, y_norm = y / denom;
+      const double u_cx = fx * x_norm, v_cy = fy * y_norm;
+      const double d_denom_d_alpha = rho - z;
+      for (int a = 0; a < 10; ++a) J[a] = 0.0;
+      J[0] = x_norm; J[5 + 1] = y_norm; J[2] = 1.0; J[5 + 3] = 1.0;
+      J[4] = -u_cx * d_denom_d_alpha / denom;
+      J[5 + 4] = -v_cy * d_denom_d_alpha / denom;
+      return;
+    }
+    case APEX_CAM_EUCM: {  // eucm.rs:652-696; columns [fx, fy, cx, cy, alpha, beta]
+      const double fx = in[0], fy = in[1], alpha = in[4], beta = in[5];
+      const double x = p.x, y = p.y, z = p.z;
+      const double r2 = x * x + y * y;
+      const double d = std::sqrt(beta * r2 + z * z);
+      const double denom = alpha * d + (1.0 - alpha) * z;
+      const double x_norm = x / denom, y_norm = y / denom;
+      const double ddenom_dalpha = d - z;
+      const double dd_dbeta = r2 / (2.0 * d);
+      const double ddenom_dbeta = alpha * dd_dbeta;
+      const double du_dalpha = -fx * x * ddenom_dalpha / (denom * denom), dv_dalpha = -fy * y * ddenom_dalpha / (denom * denom);
+      const double du_dbeta = -fx * x * ddenom_dbeta / (denom * denom), dv_dbeta = -fy * y * ddenom_dbeta / (denom * denom);
+      const double rows[12] = {x_norm, 0.0, 1.0, 0.0, du_dalpha, du_dbeta, 0.0, y_norm, 0.0, 1.0, dv_dalpha, dv_dbeta};
+      for (int a = 0; a < 12; ++a) J[a] = rows[a];
+      return;
+    }
+    case APEX_CAM_FOV: {  // fov.rs:647-708; columns [fx, fy, cx, cy, w]
+      const double fx = in[0], fy = in[1], w = in[4];
+      const double x = p.x, y = p.y, z = p.z;
+      const double r = std::sqrt(x * x + y * y);
+      const double tan_w_2 = std::tan(w / 2.0);
+      const double mul2tanwby2 = tan_w_2 * 2.0;
+      double rd;
+      if (r > GEOMETRIC_PRECISION) rd = std::atan(mul2tanwby2 * r / z) / (r * w);
+      else rd = mul2tanwby2 / w;
+      const double mx = x * rd, my = y * rd;
+      double drd_dw;
+      if (r > GEOMETRIC_PRECISION) {
+        const double alpha = 2.0 * tan_w_2 * r / z;
+        const double atan_alpha = std::atan(alpha);
+        const double sec2_w_2 = 1.0 + tan_w_2 * tan_w_2;
+        const double dalpha_dw = sec2_w_2 * r / z;
+        const double datan_dw = dalpha_dw / (1.0 + alpha * alpha);
+        drd_dw = (datan_dw * r * w - atan_alpha * r) / (r * r * w * w);
+      } else {
+        const double sec2_w_2 = 1.0 + tan_w_2 * tan_w_2;
+        drd_dw = (sec2_w_2 * w - 2.0 * tan_w_2) / (w * w);
+      }
+      const double rows[10] = {mx, 0.0, 1.0, 0.0, fx * x * drd_dw, 0.0, my, 0.0, 1.0, fy * y * drd_dw};
+      for (int a = 0; a < 10; ++a) J[a] = rows[a];
+      return;
+    }
+    case APEX_CAM_FTHETA: {  // ftheta.rs:329-356; columns [cx, cy, k1, k2, k3, k4]
+      const double x = p.x, y = p.y, z = p.z;
+      const double r_p2 = x * x + y * y;
+      const double r_p = std::sqrt(r_p2);
+      const double d = std::sqrt(r_p2 + z * z);
+      for (int a = 0; a < 12; ++a) J[a] = 0.0;
+      J[0] = 1.0; J[6 + 1] = 1.0;
+      if (r_p < GEOMETRIC_PRECISION) return;
+      const double theta = std::acos(std::min(std::max(z / d, -1.0), 1.0));
+      const double cos_phi = x / r_p, sin_phi = y / r_p;
+      double theta_pow = theta;
+      for (int col = 2; col < 6; ++col) {
+        J[col] = theta_pow * cos_phi;
+        J[6 + col] = theta_pow * sin_phi;
+        theta_pow *= theta;
+      }
       return;
     }
   }

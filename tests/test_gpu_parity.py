@@ -57,6 +57,12 @@ CASES = [
     ("kb_selfcal_cauchy", dict(model=F.CAM_KANNALA_BRANDT, self_cal=True, loss=(F.LOSS_CAUCHY, 1.0))),
     ("ds_selfcal_cauchy", dict(model=F.CAM_DOUBLE_SPHERE, self_cal=True, loss=(F.LOSS_CAUCHY, 1.0))),
     ("kb_ba_huber", dict(model=F.CAM_KANNALA_BRANDT, self_cal=False, loss=(F.LOSS_HUBER, 2.0))),
+    ("radtan_selfcal_huber", dict(model=F.CAM_RADTAN, self_cal=True, loss=(F.LOSS_HUBER, 1.0))),      # dc = 15
+    ("ucm_selfcal_cauchy", dict(model=F.CAM_UCM, self_cal=True, loss=(F.LOSS_CAUCHY, 1.0))),          # dc = 11
+    ("eucm_selfcal_huber", dict(model=F.CAM_EUCM, self_cal=True, loss=(F.LOSS_HUBER, 1.0))),          # dc = 12
+    ("fov_selfcal_huber", dict(model=F.CAM_FOV, self_cal=True, loss=(F.LOSS_HUBER, 1.0))),            # dc = 11
+    ("ftheta_selfcal_cauchy", dict(model=F.CAM_FTHETA, self_cal=True, loss=(F.LOSS_CAUCHY, 1.0))),    # dc = 12
+    ("radtan_ba_huber", dict(model=F.CAM_RADTAN, self_cal=False, loss=(F.LOSS_HUBER, 1.0))),
     ("bal_selfcal_andrews", dict(model=F.CAM_BAL, self_cal=True, loss=(F.LOSS_ANDREWS, 3.0))),  # rho'' > 0: corrector 2nd branch
     ("bal_selfcal_tukey", dict(model=F.CAM_BAL, self_cal=True, loss=(F.LOSS_TUKEY, 4.0))),
     ("bal_shuffled", dict(model=F.CAM_BAL, self_cal=True, shuffle_obs=True)),
@@ -167,6 +173,11 @@ LM_CASES = [
     ("ds_selfcal_explicit", dict(model=F.CAM_DOUBLE_SPHERE, self_cal=True, loss=(F.LOSS_CAUCHY, 1.0)), F.SCHUR_EXPLICIT),
     ("ds_selfcal_implicit", dict(model=F.CAM_DOUBLE_SPHERE, self_cal=True, loss=(F.LOSS_CAUCHY, 1.0)), F.SCHUR_IMPLICIT),
     ("pinhole_selfcal_implicit", dict(model=F.CAM_PINHOLE, self_cal=True), F.SCHUR_IMPLICIT),
+    ("radtan_selfcal_explicit", dict(model=F.CAM_RADTAN, self_cal=True), F.SCHUR_EXPLICIT),
+    ("ucm_selfcal_implicit", dict(model=F.CAM_UCM, self_cal=True, loss=(F.LOSS_CAUCHY, 1.0)), F.SCHUR_IMPLICIT),
+    ("eucm_ba_implicit", dict(model=F.CAM_EUCM, self_cal=False), F.SCHUR_IMPLICIT),
+    ("fov_selfcal_explicit", dict(model=F.CAM_FOV, self_cal=True), F.SCHUR_EXPLICIT),
+    ("ftheta_selfcal_implicit", dict(model=F.CAM_FTHETA, self_cal=True), F.SCHUR_IMPLICIT),
 ]
 
 

@@ -287,7 +287,63 @@ CAMS = [
     (F.CAM_KANNALA_BRANDT, [300.0, 300.0, 320.0, 240.0, 0.1, 0.01, 0.001, 0.0001], [0.1, 0.2, 1.0]),
     (F.CAM_DOUBLE_SPHERE, [300.0, 300.0, 320.0, 240.0, -0.2, 0.6], [0.1, 0.2, 1.0]),
     (F.CAM_DOUBLE_SPHERE, [200.0, 200.0, 300.0, 200.0, 0.5, 0.5], [-0.4, 0.3, 1.5]),
+    # the reference's own test cameras: rad_tan.rs:895-903,:933-1021; ucm.rs:715-757; eucm.rs:777-861; fov.rs:783-856; ftheta.rs:453-455,:708-790
+    (F.CAM_RADTAN, [300.0, 300.0, 320.0, 240.0, 0.1, 0.01, 0.001, 0.002, 0.001], [0.1, 0.2, 1.0]),
+    (F.CAM_RADTAN, [410.0, 400.0, 310.0, 250.0, -0.2, 0.05, -0.003, 0.001, -0.01], [-0.6, 0.35, 1.7]),
+    (F.CAM_UCM, [300.0, 300.0, 320.0, 240.0, 0.6], [0.1, 0.2, 1.0]),
+    (F.CAM_UCM, [300.0, 300.0, 320.0, 240.0, 0.5], [-0.3, 0.1, 2.0]),
+    (F.CAM_EUCM, [300.0, 300.0, 320.0, 240.0, 0.5, 1.0], [0.1, 0.2, 1.0]),
+    (F.CAM_EUCM, [400.0, 410.0, 320.0, 240.0, 0.7, 1.5], [0.25, -0.4, 1.2]),
+    (F.CAM_FOV, [300.0, 300.0, 320.0, 240.0, 1.5], [0.1, 0.2, 1.0]),
+    (F.CAM_FOV, [400.0, 410.0, 320.0, 240.0, 1.8], [-0.5, 0.3, 2.0]),
+    (F.CAM_FTHETA, [320.0, 240.0, 500.0, -10.0, 2.0, -0.1], [0.3, 0.2, 1.5]),
+    (F.CAM_FTHETA, [320.0, 240.0, 500.0, -10.0, 2.0, -0.1], [0.3, 0.2, 1.0]),
 ]
+
+
+def test_radtan_ucm_eucm_fov_ftheta_kats():
+    """Known answers of the five remaining models: principal point for a point on the axis (rad_tan.rs:913-927,
+    eucm.rs:759-771, fov.rs:768-777, ftheta.rs:747-757), validity predicates (rad_tan.rs:95-97, ucm.rs:100-108,:868-872,
+    eucm.rs:103-113, fov.rs:317-319, ftheta.rs:232-237), closed forms, and the near-axis branches."""
+    radtan = [300.0, 300.0, 320.0, 240.0, 0.1, 0.01, 0.001, 0.002, 0.001]
+    ucm, eucm, fov = [300.0, 300.0, 320.0, 240.0, 0.5], [300.0, 300.0, 320.0, 240.0, 0.5, 1.0], [300.0, 300.0, 320.0, 240.0, 1.5]
+    fth = [320.0, 240.0, 500.0, -10.0, 2.0, -0.1]
+    for model, intr, tol in ((F.CAM_RADTAN, radtan, 1e-10), (F.CAM_UCM, ucm, 1e-10), (F.CAM_EUCM, eucm, 1e-10), (F.CAM_FOV, fov, 1e-4), (F.CAM_FTHETA, fth, 1e-10)):
+        ok, uv = project(model, intr, [0.0, 0.0, 1.0])
+        assert ok and np.allclose(uv, [320.0, 240.0], atol=tol), model
+        assert not project(model, intr, [0.0, 0.0, -1.0])[0], model          # behind the camera
+    # closed forms at (0.1, 0.2, 1.0)
+    d = np.sqrt(0.01 + 0.04 + 1.0)
+    ok, uv = project(F.CAM_UCM, ucm, [0.1, 0.2, 1.0])                          # denom = 0.5 d + 0.5 z
+    assert ok and np.allclose(uv, [300 * 0.1 / (0.5 * d + 0.5) + 320, 300 * 0.2 / (0.5 * d + 0.5) + 240], rtol=1e-14)
+    ok, uv2 = project(F.CAM_EUCM, eucm, [0.1, 0.2, 1.0])                       # beta = 1: EUCM == UCM
+    assert ok and np.allclose(uv2, uv, rtol=1e-14)
+    r2 = 0.05
+    radial = 1 + 0.1 * r2 + 0.01 * r2 ** 2 + 0.001 * r2 ** 3
+    ok, uv = project(F.CAM_RADTAN, radtan, [0.1, 0.2, 1.0])
+    assert ok and np.allclose(uv, [300 * (radial * 0.1 + 2 * 0.001 * 0.02 + 0.002 * (r2 + 0.02)) + 320,
+                                   300 * (radial * 0.2 + 0.001 * (r2 + 0.08) + 2 * 0.002 * 0.02) + 240], rtol=1e-14)
+    r = np.sqrt(0.05)
+    ok, uv = project(F.CAM_FOV, fov, [0.1, 0.2, 1.0])
+    rd = np.arctan(2 * np.tan(0.75) * r) / (r * 1.5)
+    assert ok and np.allclose(uv, [300 * 0.1 * rd + 320, 300 * 0.2 * rd + 240], rtol=1e-13)
+    ok, uv = project(F.CAM_FTHETA, [320.0, 240.0, 500.0, 0.0, 0.0, 0.0], [0.3, 0.2, 1.5])   # linear camera: r = k1 * theta (ftheta.rs:457-460)
+    th = np.arccos(1.5 / np.sqrt(0.09 + 0.04 + 2.25))
+    assert ok and np.allclose(np.hypot(uv[0] - 320, uv[1] - 240), 500 * th, rtol=1e-13)
+    # validity edges
+    assert not project(F.CAM_RADTAN, radtan, [0.1, 0.2, 0.5e-6])[0] and project(F.CAM_RADTAN, radtan, [0.0, 0.0, 1e-6])[0]
+    assert not project(F.CAM_FOV, fov, [0.1, 0.2, 1e-8])[0] and project(F.CAM_FOV, fov, [0.0, 0.0, 2e-8])[0]
+    assert not project(F.CAM_FTHETA, fth, [0.1, 0.2, 0.5e-6])[0]
+    assert not project(F.CAM_UCM, [300.0, 300.0, 320.0, 240.0, 0.6], [1.0, 0.0, -0.95])[0]    # z <= -w d, w = 0.4/0.6
+    assert project(F.CAM_UCM, [300.0, 300.0, 320.0, 240.0, 0.6], [1.0, 0.0, -0.5])[0]
+    assert not project(F.CAM_EUCM, [300.0, 300.0, 320.0, 240.0, 0.7, 1.0], [1.0, 0.0, -0.9])[0]
+    # near-axis branches
+    J = jac_point(F.CAM_FTHETA, fth, [1e-8, -1e-8, 2.0])                        # ftheta.rs:304-310: k1 / z on the diagonal
+    assert J[0, 0] == 250.0 and J[1, 1] == 250.0 and J[0, 1] == 0 and J[0, 2] == 0 and J[1, 2] == 0
+    Ji = jac_intr(F.CAM_FTHETA, fth, [1e-8, -1e-8, 2.0])
+    assert Ji[0, 0] == 1 and Ji[1, 1] == 1 and np.all(Ji[:, 2:] == 0)
+    J = jac_point(F.CAM_FOV, fov, [1e-8, 0.0, 2.0])                             # fov.rs:479-489: rd = 2 tan(w/2) / w
+    assert np.allclose([J[0, 0], J[1, 1]], 300 * 2 * np.tan(0.75) / 1.5, rtol=1e-15) and J[0, 2] == 0 and J[1, 2] == 0
 
 
 @pytest.mark.parametrize("model,intr,p", CAMS)
