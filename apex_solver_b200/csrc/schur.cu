@@ -13,6 +13,8 @@
 // shared memory, and each observation then sends  -Jc_o^T (Jp_o w_p)  to y_c with FP64 reductions into L2
 // (red.global.add.f64). H_cp = Jc^T Jp is never materialised: 2*(dc+3) doubles per observation are read
 // instead of 3*dc.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -1343,6 +1345,216 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_update_kernel(const double* _
 }
 
 // ----------------------------------------------------------------------------------------------------
+// Fused PCG tail: everything between two operator applications in ONE launch of one thread-block cluster.
+//   [peer all-reduce of the partial operator result over NVLink]  ->  pAp, alpha  ->  x += alpha p, r -= alpha Ap,
+//   z = M^-1 r  ->  ||r||, r.z, beta, break tests  ->  p = z + beta p, its padded copy, y0 = (H_cc + lambda I) p
+// The camera vectors are small (ncam*dc doubles: 128 KB on the Venice shape), so the three grid-wide dot products that
+// cost three kernels with "last CTA" passes become cluster-wide reductions through distributed shared memory: every CTA
+// of the cluster owns a contiguous range of cameras, keeps its rows of p / Ap / r / z in shared memory, publishes its
+// partial sums in its own shared memory, cluster.sync(), and every CTA adds the partials in CTA order (same bits
+// everywhere, and the same bits on every rank because every rank adds the same numbers in the same order). Two launches
+// per PCG iteration (operator + tail) instead of four. Opt-in (APEX_PCG_TAIL = cluster size): 16 CTAs pull H_cc and the
+// preconditioner blocks (1.8 MB on the Venice shape) through 16 SMs, which costs what the saved launches and "last CTA"
+// passes gain - measured 19.6 vs 19.7 LM it/s on one GPU and 35.4 vs 36.0 on two. Needs a CTA's rows to fit in shared
+// memory (TAIL_MAX_ROWS). Semantics of solve_pcg_block (implicit_schur.rs:604-676) as in pcg_pap / pcg_update / pcg_dir_hcc.
+// ----------------------------------------------------------------------------------------------------
+constexpr int TAIL_THREADS = 1024;
+constexpr int TAIL_MAX_ROWS = 4096;   // rows of one CTA: 3 x 32 KB of shared memory
+struct TailArgs {
+  double* const* peer_buf;               // null: `ysrc` already holds the complete operator result
+  unsigned long long* const* peer_flags;
+  const unsigned long long* flags;
+  int par, nranks, rank;
+  const double* ysrc;
+  double* y0_next;
+  double* p; double* x; double* r; double* z; double* xpad;
+  const double* pinv; const double* hcc;
+  DevState* st;
+  uint32_t ncam;
+  int dc, K, xs, add_hcc;
+};
+
+// sum of one shared-memory slot over the cluster, in CTA order
+__device__ __forceinline__ double cluster_sum(cooperative_groups::cluster_group& cl, double* slot) {
+  double s = 0.0;
+  for (unsigned c = 0; c < cl.num_blocks(); ++c) s += *cl.map_shared_rank(slot, c);
+  return s;
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) pcg_tail_kernel(TailArgs a) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  extern __shared__ double tail_sm[];
+  __shared__ double sh[TAIL_THREADS];
+  __shared__ double slot[4];
+  DevState* st = a.st;
+  if (st->pcg_done) return;  // same value in every CTA: it is only written behind two cluster barriers below
+  const int tid = threadIdx.x, dc = a.dc, K = a.K;
+  const uint32_t n = a.ncam * dc;
+  const uint32_t cpc = (a.ncam + cl.num_blocks() - 1) / cl.num_blocks();
+  const uint32_t cam0 = min(cl.block_rank() * cpc, a.ncam);
+  const uint32_t nrow = min(cpc, a.ncam - cam0) * dc;
+  const size_t row0 = (size_t)cam0 * dc;
+  double* ys = tail_sm;                   // Ap rows, later z rows
+  double* pp = tail_sm + TAIL_MAX_ROWS;   // p rows
+  double* rs = tail_sm + 2 * TAIL_MAX_ROWS;
+  const double rz_old = st->rz_old, tol = st->pcg_tol, damping = st->damping;
+  const int iters0 = st->pcg_iters, max_it = st->pcg_max;
+  const unsigned long long seq = st->ar_seq + 1;
+  // ---- the operator result of all ranks (peer memory, rank order) and pAp ----
+  if (a.peer_buf) {
+    if (cl.block_rank() == 0 && tid < a.nranks) {
+      __threadfence_system();
+      st_release_sys(a.peer_flags[tid] + a.rank, seq);
+    }
+    if (tid < a.nranks) {
+      long long spins = 0;
+      while (ld_acquire_sys(a.flags + tid) < seq) {
+        if (++spins > (1ll << 26)) { atomicExch(&st->ar_timeout, 1); break; }
+      }
+    }
+    __syncthreads();
+  }
+  double v = 0.0;
+  for (uint32_t i = tid; i < nrow; i += TAIL_THREADS) {
+    const size_t row = row0 + i;
+    double s = 0.0;
+    if (a.peer_buf) { for (int r = 0; r < a.nranks; ++r) s += ld_relaxed_sys(a.peer_buf[r] + (size_t)a.par * n + row); }
+    else s = a.ysrc[row];
+    const double pv = a.p[row];
+    ys[i] = s; pp[i] = pv;
+    v += pv * s;
+  }
+  v = block_reduce_sum(v, sh);
+  if (tid == 0) slot[0] = v;
+  cl.sync();
+  const double pap = cluster_sum(cl, &slot[0]);
+  if (fabs(pap) < 1e-20) {  // break before the update (implicit_schur.rs:626-629)
+    if (cl.block_rank() == 0 && tid == 0) { st->pcg_iters = iters0 + 1; st->pcg_done = 1; if (a.peer_buf) st->ar_seq = seq; }
+    cl.sync();  // nobody leaves while its shared memory may still be read
+    return;
+  }
+  const double alpha = rz_old / pap;
+  // ---- x, r, z = M^-1 r, ||r||^2, r.z ----
+  double rr = 0.0, rz = 0.0;
+  for (uint32_t i = tid; i < nrow; i += TAIL_THREADS) {
+    const size_t row = row0 + i;
+    a.x[row] += alpha * pp[i];
+    const double rv = a.r[row] - alpha * ys[i];
+    a.r[row] = rv;
+    rs[i] = rv;
+    rr += rv * rv;
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < nrow; i += TAIL_THREADS) {
+    const uint32_t lc = i / dc, q = i % dc;
+    const double* P = a.pinv + (size_t)(cam0 + lc) * (36 + K * K);
+    const double* rc = rs + lc * dc;
+    double s = 0.0;
+    if (q < 6) { for (int b = 0; b < 6; ++b) s += P[q * 6 + b] * rc[b]; }
+    else { const double* Q = P + 36 + (q - 6) * K; for (int b = 0; b < K; ++b) s += Q[b] * rc[6 + b]; }
+    a.z[row0 + i] = s;
+    ys[i] = s;  // z rows
+    rz += rs[i] * s;
+  }
+  rr = block_reduce_sum(rr, sh);
+  rz = block_reduce_sum(rz, sh);
+  if (tid == 0) { slot[1] = rr; slot[2] = rz; }
+  cl.sync();
+  const double rr_tot = cluster_sum(cl, &slot[1]), rz_tot = cluster_sum(cl, &slot[2]);
+  const int iters = iters0 + 1;
+  const double r_norm = sqrt(rr_tot);
+  bool done = r_norm < tol || fabs(rz_old) < 1e-30;
+  double beta = 0.0;
+  const bool have_beta = !done;
+  if (have_beta) { beta = rz_tot / rz_old; if (iters >= max_it) done = true; }
+  if (cl.block_rank() == 0 && tid == 0) {
+    st->pcg_iters = iters;
+    st->r_norm = r_norm;
+    st->pcg_alpha = alpha;
+    if (have_beta) { st->pcg_beta = beta; st->rz_old = rz_tot; }
+    if (done) st->pcg_done = 1;
+    if (a.peer_buf) st->ar_seq = seq;
+  }
+  // ---- next direction and the start value of the next operator result ----
+  if (!done) {
+    for (uint32_t i = tid; i < nrow; i += TAIL_THREADS) {
+      const double pv = beta == 0.0 ? ys[i] : ys[i] + beta * pp[i];
+      a.p[row0 + i] = pv;
+      pp[i] = pv;
+      a.xpad[(size_t)(cam0 + i / dc) * a.xs + i % dc] = pv;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < nrow; i += TAIL_THREADS) {
+      double s = 0.0;
+      if (a.add_hcc) {
+        const uint32_t lc = i / dc, q = i % dc;
+        const double* H = a.hcc + ((size_t)(cam0 + lc) * dc + q) * dc;
+        const double* pc = pp + lc * dc;
+        s = damping * pc[q];
+        for (int b = 0; b < dc; ++b) s += H[b] * pc[b];
+      }
+      a.y0_next[row0 + i] = s;
+    }
+  }
+  cl.sync();  // distributed shared memory stays alive until every CTA has read the partial sums
+}
+
+static apex_status launch_pcg_tail(Ctx& c, const TailArgs& a, int cluster) {
+  static bool attr_set = false;
+  const size_t smem = 3 * (size_t)TAIL_MAX_ROWS * sizeof(double);
+  if (!attr_set) {
+    APEX_CUDA_TRY(c, cudaFuncSetAttribute(pcg_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    APEX_CUDA_TRY(c, cudaFuncSetAttribute(pcg_tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)cluster);
+  cfg.blockDim = dim3(TAIL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c.stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  APEX_CUDA_TRY(c, cudaLaunchKernelEx(&cfg, pcg_tail_kernel, a));
+  c.launches++;
+  return APEX_OK;
+}
+
+// cluster size of the fused tail (0 = use the three-kernel path): the largest of 16 (non-portable) / 8 / 4 CTAs the device
+// can co-schedule with 96 KB of shared memory each, provided a CTA's camera rows fit in TAIL_MAX_ROWS
+static int pcg_tail_cluster(Ctx& c) {
+  static int device_max = -1;
+  if (device_max < 0) {
+    device_max = 0;
+    const size_t smem = 3 * (size_t)TAIL_MAX_ROWS * sizeof(double);
+    if (cudaFuncSetAttribute(pcg_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+        cudaFuncSetAttribute(pcg_tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      for (int cl : {16, 8, 4}) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)cl); cfg.blockDim = dim3(TAIL_THREADS); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, pcg_tail_kernel, &cfg) == cudaSuccess && nclusters > 0) { device_max = cl; break; }
+      }
+    }
+    cudaGetLastError();  // a failed probe must not poison the next launch check
+  }
+  const char* e = getenv("APEX_PCG_TAIL");
+  int want = e ? atoi(e) : 0;  // opt-in: measured no faster than the three-kernel path (19.6 vs 19.7 LM it/s at N=1, 35.4 vs 36.0 at N=2)
+  if (want <= 0 || device_max <= 0) return 0;
+  want = std::min(want, device_max);
+  const uint32_t rows = (uint32_t)((c.ncam + want - 1) / want) * c.dc;
+  if (rows > (uint32_t)TAIL_MAX_ROWS) return 0;
+  return want;
+}
+
+// ----------------------------------------------------------------------------------------------------
 // host launchers
 // ----------------------------------------------------------------------------------------------------
 static SchurArgs make_schur_args(Ctx& c, const double* x, double* y, int check_done) {
@@ -1600,10 +1812,37 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
   // launch: the inner loop is launch-bound on small shards (8 GPUs: ~35 us of kernels per iteration).
   const int BATCH = 10;
   int it_count = 0;  // iteration index within this solve: selects the half of the peer buffer (BATCH is even)
+  const int tail_cluster = operator_impl() == 0 ? pcg_tail_cluster(c) : 0;
+  if (tail_cluster && cg_max_it > 0) {  // first direction p = z and y0 = (H_cc + lambda I) p into half 0; later ones come from the tail
+    const int xs = xpad_stride(c.dc);
+    double* y0 = c.p2p_ok ? c.arbuf.p : c.vy.p;
+    pcg_dir_hcc_kernel<<<(c.ncam + PCG_CAMS - 1) / PCG_CAMS, PCG_THREADS, 0, s>>>(c.vz.p, c.vp.p, c.xpad.p, c.hcc.p, y0, c.state.p, c.ncam, c.dc, xs, c.rank == 0 ? 1 : 0);
+    c.launches++;
+    APEX_CUDA_TRY(c, cudaGetLastError());
+  }
   auto enqueue_iteration = [&]() -> apex_status {
     const int xs = xpad_stride(c.dc);
     const unsigned gp = (n + PCG_THREADS - 1) / PCG_THREADS, gu = (c.ncam + PCG_CAMS - 1) / PCG_CAMS;
     const int par = it_count++ & 1;
+    if (operator_impl() == 0 && tail_cluster) {
+      // fused path: [operator, tail] per iteration; the first direction / y0 were produced before the loop
+      double* y0 = c.p2p_ok ? c.arbuf.p + (size_t)par * n : c.vy.p;
+      cudaEvent_t* evp = (c.prof && c.ntiles) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
+      if (evp) cudaEventRecord(evp[0], s);
+      APEX_TRY(launch_schur_tiles(c, MODE_MATVEC, c.vp.p, y0, 1, true));
+      if (evp) cudaEventRecord(evp[1], s);
+      if (!c.p2p_ok) APEX_TRY(allreduce_sum(c, c.vy.p, n));
+      TailArgs ta{};
+      if (c.p2p_ok) { ta.peer_buf = c.d_peer_buf.p; ta.peer_flags = c.d_peer_flags.p; ta.flags = c.arflags.p; }
+      ta.par = par; ta.nranks = c.nranks; ta.rank = c.rank;
+      ta.ysrc = c.vy.p;
+      ta.y0_next = c.p2p_ok ? c.arbuf.p + (size_t)(par ^ 1) * n : c.vy.p;
+      ta.p = c.vp.p; ta.x = c.step_cam.p; ta.r = c.vr.p; ta.z = c.vz.p; ta.xpad = c.xpad.p;
+      ta.pinv = c.pinv.p; ta.hcc = c.hcc.p; ta.st = c.state.p;
+      ta.ncam = c.ncam; ta.dc = c.dc; ta.K = c.K; ta.xs = xs; ta.add_hcc = c.rank == 0 ? 1 : 0;
+      APEX_TRY(launch_pcg_tail(c, ta, tail_cluster));
+      return APEX_OK;
+    }
     if (operator_impl() == 0) {
       // chunk-kernel path: p / y0 in one kernel, the operator reduces into y0, then (ranks > 1) the peer-memory
       // all-reduce fused with p.Ap, or NCCL when peer mapping is unavailable
