@@ -702,6 +702,7 @@ __global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a, uint3
 struct WinArgs {
   const uint32_t* grp_win0;  // [ngroups] first camera of the group's window
   uint32_t ngroups, G, W, ncam;
+  uint32_t ywin;             // 1: window of y in shared memory too; 0: x only (results leave per chunk, as in the chunk kernel)
 };
 template <int DC>
 __host__ __device__ constexpr size_t win_base_bytes() {
@@ -721,7 +722,8 @@ __global__ void __launch_bounds__(TILE, 3) schur_window_kernel(SchurArgs a, WinA
   double* xw = cs + DC * LD + 9 * MAX_TILE_PTS;
   const uint32_t W = wa.W, ncam = wa.ncam;
   double* yw = xw + (size_t)W * DC;
-  uint32_t* sptm = reinterpret_cast<uint32_t*>(yw + (size_t)W * DC);
+  const bool ywin = wa.ywin != 0;
+  uint32_t* sptm = reinterpret_cast<uint32_t*>(yw + (ywin ? (size_t)W * DC : 0));
   uint32_t* ssegc = sptm + MAX_TILE_PTS;
   uint16_t* ssegb = reinterpret_cast<uint16_t*>(ssegc + TILE);
   const int tid = threadIdx.x;
@@ -734,7 +736,7 @@ __global__ void __launch_bounds__(TILE, 3) schur_window_kernel(SchurArgs a, WinA
     uint32_t gi = win0 * DC + i;
     if (gi >= ntot) gi -= ntot;
     cp_async8(xw + i, a.x + gi);
-    yw[i] = 0.0;
+    if (ywin) yw[i] = 0.0;
   }
   for (uint32_t chunk = c_begin; chunk < c_end; ++chunk) {
     // ---- all global reads of the chunk up front ----
@@ -828,7 +830,7 @@ __global__ void __launch_bounds__(TILE, 3) schur_window_kernel(SchurArgs a, WinA
       }
       uint32_t l = cg - win0;
       if (cg < win0) l += ncam;
-      if (l < W) {
+      if (ywin && l < W) {
         double* yr = yw + l * DC + kg;
         yr[0] += v0;
         if (kg + 1 < DC) yr[1] += v1;
@@ -843,7 +845,7 @@ __global__ void __launch_bounds__(TILE, 3) schur_window_kernel(SchurArgs a, WinA
     __syncthreads();  // the next chunk overwrites the tables and su; the flush reads yw
   }
   // ---- flush the window: one coalesced reduction per touched (camera, dof) ----
-  if (a.debug == 1) return;
+  if (a.debug == 1 || !ywin) return;
   for (uint32_t i = tid; i < nw; i += TILE) {
     const double v = yw[i];
     if (v != 0.0) {
@@ -1618,10 +1620,12 @@ static void launch_tiles_dc(Ctx& c, int mode, const SchurArgs& a0) {
     c.launches++;
   } else if (c.nnormal_chunks && mode == MODE_MATVEC && c.mv_W && c.mv_ngroups) {
     // operator: window kernel (groups of chunks, camera window of x and y in shared memory)
-    const size_t smem = mv_window_base_bytes(DC) + 2 * sizeof(double) * (size_t)c.mv_W * DC;
+    const char* ye = getenv("APEX_MV_YWIN");
+    const uint32_t ywin = ye ? (uint32_t)atoi(ye) : 1u;
+    const size_t smem = mv_window_base_bytes(DC) + (ywin ? 2 : 1) * sizeof(double) * (size_t)c.mv_W * DC;
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(schur_window_kernel<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 76800); attr_set = true; }
-    WinArgs wa{c.grp_win0.p, c.mv_ngroups, c.mv_G, c.mv_W, c.ncam};
+    WinArgs wa{c.grp_win0.p, c.mv_ngroups, c.mv_G, c.mv_W, c.ncam, ywin};
     schur_window_kernel<DC><<<c.mv_ngroups, TILE, smem, c.stream>>>(a, wa, c.nnormal_chunks);
     c.launches++;
   } else if (c.nnormal_chunks) {
