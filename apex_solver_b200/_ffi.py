@@ -176,6 +176,7 @@ SYMBOLS = {
     "profile_enable": (C.c_int32, [C.c_void_p, C.c_int32]),
     "profile_read": (C.c_int32, [C.c_void_p, P(Profile)]),
     "layout_stats_compute": (C.c_int32, [P(ProblemDesc), C.c_int32, C.c_int32, P(LayoutStats)]),
+    "dense_cholesky_bench": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_int32, P(C.c_double)]),
     "bal_load": (C.c_int32, [C.c_char_p, P(C.c_void_p)]),
     "bal_from_arrays": (C.c_int32, [C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_void_p)]),
     "bal_view_get": (C.c_int32, [C.c_void_p, P(BalView)]),
@@ -186,7 +187,7 @@ SYMBOLS = {
     "shard_info": (C.c_int32, [C.c_uint32, C.c_uint64, C.c_void_p, C.c_int32, C.c_int32, P(C.c_uint32), P(C.c_uint32), P(C.c_uint64)]),
 }
 # entry points the oracle does not implement (GPU-only plumbing)
-GPU_ONLY = {"device_count", "nccl_unique_id", "schur_matvec_bench", "kernel_launches", "profile_enable", "profile_read", "shard_info", "layout_stats_compute",
+GPU_ONLY = {"device_count", "nccl_unique_id", "schur_matvec_bench", "kernel_launches", "profile_enable", "profile_read", "shard_info", "layout_stats_compute", "dense_cholesky_bench",
             "bal_load", "bal_from_arrays", "bal_view_get", "bal_write", "bal_build_problem", "bal_free", "bal_last_error"}
 
 

@@ -169,6 +169,12 @@ class Context:
         self._check(self._fn("schur_matvec_bench")(self._h, int(reps), 1 if flush_l2 else 0, C.byref(ms)))
         return ms.value
 
+    def dense_cholesky_bench(self, n: int, reps: int = 3) -> float:
+        """Average milliseconds of the dense FP64 (DMMA) Cholesky of a synthetic n x n SPD matrix (measurement aid)."""
+        ms = C.c_double()
+        self._check(self._fn("dense_cholesky_bench")(self._h, int(n), int(reps), C.byref(ms)))
+        return ms.value
+
     def solve_augmented(self, variant: int, lam: float, precond: int = F.PRECOND_SCHUR_JACOBI, cg_max_iterations: int = 200,
                         cg_tolerance: float = 1e-6):
         p = self.problem

@@ -286,6 +286,7 @@ apex_status launch_reduced_gradient(Ctx& c, double* b);
 apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol);
 // explicit.cu
 apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol);
+apex_status dense_cholesky_bench(Ctx& c, uint32_t n, int reps, double* ms_out);
 // lm.cu
 apex_status launch_step_norms(Ctx& c);
 apex_status launch_apply_step(Ctx& c, double sign, bool only_if_rejected);

@@ -338,6 +338,12 @@ apex_status apex_schur_matvec_bench(apex_ctx* ctx, int32_t reps, int32_t flush_l
   return APEX_OK;
 }
 
+apex_status apex_dense_cholesky_bench(apex_ctx* ctx, uint32_t n, int32_t reps, double* ms_per_factorization) {
+  CTX_OR_FAIL(ctx);
+  if (n == 0 || n > 60000) { c.err = "n out of range"; return APEX_ERR_INVALID_INPUT; }
+  return dense_cholesky_bench(c, n, reps, ms_per_factorization);
+}
+
 apex_status apex_solve_augmented(apex_ctx* ctx, int32_t schur_variant, int32_t preconditioner, int32_t cg_max_iterations, double cg_tolerance,
                                  double lambda, double* step_cam, double* step_pt, double* grad_norm, int32_t* pcg_iters) {
   CTX_OR_FAIL(ctx);

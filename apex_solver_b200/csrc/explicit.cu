@@ -141,58 +141,76 @@ __global__ void symmetrize_drop_kernel(double* S, size_t ld, uint32_t nt) {
 // ----------------------------------------------------------------------------------------------------
 // K8: blocked right-looking Cholesky, lower, in place
 // ----------------------------------------------------------------------------------------------------
-// factor the NB x NB diagonal block at k0 (one CTA, 256 threads)
+// factor the NB x NB diagonal block at k0 (one CTA, 256 threads as 16 x 16; thread (ty, tx) owns the 4 x 4 elements
+// rows ty + 16 a, columns tx + 16 b of the block, so the trailing update of a column needs no index arithmetic and the
+// rows / columns still alive are spread over all threads). Two barriers per column: every thread takes the square root
+// of the pivot itself, the pivot's owner stores it, the threads of the column scale their entry.
 __global__ void __launch_bounds__(256) chol_potrf_kernel(double* A, size_t ld, uint32_t k0, DevState* st) {
   __shared__ double a[NB][NB + 1];
   __shared__ int bad;
   if (st->chol_fail) return;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   if (tid == 0) bad = 0;
-  for (int e = tid; e < NB * NB; e += 256) { const int r = e / NB, cidx = e % NB; a[r][cidx] = A[((size_t)k0 + r) * ld + k0 + cidx]; }
+  for (int e = tid; e < NB * NB; e += 256) { const int r = e >> 6, cidx = e & 63; a[r][cidx] = A[((size_t)k0 + r) * ld + k0 + cidx]; }
   __syncthreads();
   for (int j = 0; j < NB; ++j) {
-    if (tid == 0) {
-      const double d = a[j][j];
-      if (!(d > 0.0)) { bad = j + 1; a[j][j] = 1.0; } else a[j][j] = sqrt(d);
-    }
+    double d = a[j][j];
+    const bool ok = d > 0.0;
+    if (!ok) d = 1.0;
+    const double rs = rsqrt(d);   // the column is serial in (pivot -> scale -> update): 1/sqrt + multiplies instead of sqrt + divisions
+    __syncthreads();  // everybody has read the pivot
+    if (tid == j) { a[j][j] = d * rs; if (!ok) bad = j + 1; }
+    else if (tid > j && tid < NB) a[tid][j] *= rs;
     __syncthreads();
-    const double d = a[j][j];
-    if (tid > j && tid < NB) a[tid][j] /= d;
-    __syncthreads();
-    // trailing update of the lower triangle: rows i > j, cols j < k <= i
-    const int m = NB - 1 - j;
-    for (int e = tid; e < m * m; e += 256) {
-      const int i = j + 1 + e / m, k = j + 1 + e % m;
-      if (k <= i) a[i][k] -= a[i][j] * a[k][j];
+    // trailing update of the lower triangle: rows i > j, columns j < k <= i
+    double cj[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) cj[b] = a[tx + 16 * b][j];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = ty + 16 * r;
+      if (i <= j) continue;
+      const double ri = a[i][j];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int k = tx + 16 * b;
+        if (k > j && k <= i) a[i][k] -= ri * cj[b];
+      }
     }
+    // no barrier here: the next column's pivot read is behind the barrier at the top of the loop only after all updates
     __syncthreads();
   }
-  for (int e = tid; e < NB * NB; e += 256) { const int r = e / NB, cidx = e % NB; if (cidx <= r) A[((size_t)k0 + r) * ld + k0 + cidx] = a[r][cidx]; }
+  for (int e = tid; e < NB * NB; e += 256) { const int r = e >> 6, cidx = e & 63; if (cidx <= r) A[((size_t)k0 + r) * ld + k0 + cidx] = a[r][cidx]; }
   if (tid == 0 && bad) atomicCAS(&st->chol_fail, 0, (int)k0 + bad);
 }
 
-// panel: rows [r0 + 64*blockIdx.x, +64): X <- X * L11^-T, one thread per row (forward substitution)
+// panel: rows [r0 + 64*blockIdx.x, +64): X <- X * L11^-T by forward substitution, four threads per row (lanes 4r..4r+3 of
+// a warp): each takes every fourth term of the dot product, two shuffles add the partial sums
 __global__ void __launch_bounds__(256) chol_trsm_kernel(double* A, size_t ld, uint32_t k0) {
   extern __shared__ double trsm_smem[];
-  double (*l)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(trsm_smem);
-  double (*x)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(trsm_smem + NB * (NB + 1));
+  double (*l)[PLD] = reinterpret_cast<double (*)[PLD]>(trsm_smem);
+  double (*x)[PLD] = reinterpret_cast<double (*)[PLD]>(trsm_smem + NB * PLD);
   const int tid = threadIdx.x;
   const size_t r0 = (size_t)k0 + NB + (size_t)blockIdx.x * NB;
   for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e / NB, cidx = e % NB;
+    const int r = e >> 6, cidx = e & 63;
     l[r][cidx] = A[((size_t)k0 + r) * ld + k0 + cidx];
     x[r][cidx] = A[(r0 + r) * ld + k0 + cidx];
   }
   __syncthreads();
-  if (tid < NB) {
-    for (int j = 0; j < NB; ++j) {
-      double s = x[tid][j];
-      for (int k = 0; k < j; ++k) s = fma(-x[tid][k], l[j][k], s);
-      x[tid][j] = s / l[j][j];
-    }
+  if (tid < NB) l[tid][tid] = 1.0 / l[tid][tid];  // reciprocal pivots once, off the serial path
+  __syncthreads();
+  const int row = tid >> 2, q = tid & 3;
+  for (int j = 0; j < NB; ++j) {
+    double s = 0.0;
+    for (int k = q; k < j; k += 4) s = fma(x[row][k], l[j][k], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (q == 0) x[row][j] = (x[row][j] - s) * l[j][j];
+    __syncwarp();
   }
   __syncthreads();
-  for (int e = tid; e < NB * NB; e += 256) { const int r = e / NB, cidx = e % NB; A[(r0 + r) * ld + k0 + cidx] = x[r][cidx]; }
+  for (int e = tid; e < NB * NB; e += 256) { const int r = e >> 6, cidx = e & 63; A[(r0 + r) * ld + k0 + cidx] = x[r][cidx]; }
 }
 
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
@@ -247,6 +265,79 @@ __global__ void __launch_bounds__(128) chol_syrk_kernel(double* A, size_t ld, ui
   for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) {
+      double2* p = reinterpret_cast<double2*>(A + (ri + wm + mi * 8 + lr) * ld + rj + wn + ni * 8 + lc * 2);
+      double2 v = *p;
+      v.x -= acc[mi][ni][0];
+      v.y -= acc[mi][ni][1];
+      *p = v;
+    }
+}
+
+// The deep (k = 256) trailing update on 128x128 tiles: 64x64 tiles move 64 KB through L2 per 64-deep slice for 0.5 MFLOP
+// (8 flop/B - at the DMMA rate that is more than L2 delivers); a 128x128 tile doubles the intensity. 256 threads = 8
+// warps as 4 (rows) x 2 (columns), each warp a 32x64 sub-tile = 4x8 DMMA.8x8x4 accumulators (128 registers); the two
+// 128 x 32 panel slices of a k step are staged with cp.async (16-byte copies) into a double-buffered shared-memory ring
+// (stride 36 doubles: fragment loads hit 16 distinct 8-byte banks per half warp), so the loads of slice s+1 are in
+// flight while slice s feeds the tensor pipe.
+constexpr int SB = 128, SKC = 32, SPLD = SKC + 4;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__global__ void __launch_bounds__(256, 1) chol_syrk128_kernel(double* A, size_t ld, uint32_t k0, uint32_t kdepth, uint32_t r0) {
+  extern __shared__ __align__(16) double smem[];
+  const uint32_t bi = blockIdx.x, bj = blockIdx.y;
+  if (bi < bj) return;
+  const size_t ri = (size_t)r0 + (size_t)bi * SB, rj = (size_t)r0 + (size_t)bj * SB;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 64;
+  const int lr = lane >> 2, lc = lane & 3;
+  double acc[4][8][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+  auto stage = [&](int buf, uint32_t kc) {  // 2 panels x 128 rows x 32 doubles = 2 x 2048 16-byte copies
+    double* Pa = smem + (size_t)buf * 2 * SB * SPLD;
+    double* Pb = Pa + SB * SPLD;
+    for (int e = tid; e < SB * SKC / 2; e += 256) {
+      const int r = e / (SKC / 2), c2 = (e % (SKC / 2)) * 2;
+      cp_async16(Pa + r * SPLD + c2, A + (ri + r) * ld + k0 + kc + c2);
+      cp_async16(Pb + r * SPLD + c2, A + (rj + r) * ld + k0 + kc + c2);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int nslices = (int)(kdepth / SKC);
+  stage(0, 0);
+  for (int sidx = 0; sidx < nslices; ++sidx) {
+    if (sidx + 1 < nslices) {
+      stage((sidx + 1) & 1, (uint32_t)(sidx + 1) * SKC);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const double* Pa = smem + (size_t)(sidx & 1) * 2 * SB * SPLD;
+    const double* Pb = Pa + SB * SPLD;
+#pragma unroll 2
+    for (int kk = 0; kk < SKC; kk += 4) {
+      double af[4], bf[8];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) af[mi] = Pa[(wm + mi * 8 + lr) * SPLD + kk + lc];
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni) bf[ni] = Pb[(wn + ni * 8 + lr) * SPLD + kk + lc];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+    }
+    __syncthreads();  // the buffer just read is refilled by the next iteration's stage()
+  }
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni) {
       double2* p = reinterpret_cast<double2*>(A + (ri + wm + mi * 8 + lr) * ld + rj + wn + ni * 8 + lc * 2);
       double2 v = *p;
       v.x -= acc[mi][ni][0];
@@ -416,8 +507,10 @@ static apex_status dense_cholesky(Ctx& c, double* L, uint32_t npad) {
   const size_t ld = npad;
   static bool attr_set = false;
   const int smem = 2 * NB * PLD * (int)sizeof(double);
-  const int trsm_smem_bytes = 2 * NB * (NB + 1) * (int)sizeof(double);
+  const int trsm_smem_bytes = 2 * NB * PLD * (int)sizeof(double);
+  const int syrk128_smem = 2 * 2 * SB * SPLD * (int)sizeof(double);
   if (!attr_set) {
+    APEX_CUDA_TRY(c, cudaFuncSetAttribute(chol_syrk128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, syrk128_smem));
     APEX_CUDA_TRY(c, cudaFuncSetAttribute(chol_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     APEX_CUDA_TRY(c, cudaFuncSetAttribute(chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_smem_bytes));
     attr_set = true;
@@ -444,12 +537,53 @@ static apex_status dense_cholesky(Ctx& c, double* L, uint32_t npad) {
       }
     }
     if (kend < npad) {
-      const uint32_t rem = (npad - kend) / NB;
-      chol_syrk_kernel<<<dim3(rem, rem), 128, smem, s>>>(L, ld, ko, kend - ko, kend);
+      if ((npad - kend) % SB == 0 && (kend - ko) % SKC == 0 && !getenv("APEX_CHOL_SYRK64")) {
+        const uint32_t rem = (npad - kend) / SB;
+        chol_syrk128_kernel<<<dim3(rem, rem), 256, syrk128_smem, s>>>(L, ld, ko, kend - ko, kend);
+      } else {
+        const uint32_t rem = (npad - kend) / NB;
+        chol_syrk_kernel<<<dim3(rem, rem), 128, smem, s>>>(L, ld, ko, kend - ko, kend);
+      }
       c.launches++;
     }
   }
   APEX_CUDA_TRY(c, cudaGetLastError());
+  return APEX_OK;
+}
+
+// Measurement aid (apex_dense_cholesky_bench): factor a synthetic SPD matrix (symmetric hash noise in [-1, 1), diagonal n:
+// strictly diagonally dominant) `reps` times and report the average time of the factorisation alone.
+__global__ void chol_bench_fill_kernel(double* A, uint32_t n) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * n) return;
+  const uint32_t i = (uint32_t)(idx / n), j = (uint32_t)(idx % n);
+  const uint32_t lo = min(i, j), hi = max(i, j);
+  uint64_t h = ((uint64_t)hi << 32 | lo) * 0x9E3779B97F4A7C15ull;
+  h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+  A[idx] = i == j ? (double)n : (double)(h >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+apex_status dense_cholesky_bench(Ctx& c, uint32_t n, int reps, double* ms_out) {
+  const uint32_t npad = (n + 2 * NB - 1) / (2 * NB) * (2 * NB);  // multiple of 128: the deep trailing update works on 128x128 tiles
+  APEX_CUDA_TRY(c, c.S.alloc((size_t)npad * npad));
+  cudaEvent_t e0, e1;
+  APEX_CUDA_TRY(c, cudaEventCreate(&e0));
+  APEX_CUDA_TRY(c, cudaEventCreate(&e1));
+  double total = 0.0;
+  for (int r = -1; r < reps; ++r) {  // one warm-up
+    chol_bench_fill_kernel<<<(unsigned)(((size_t)npad * npad + 255) / 256), 256, 0, c.stream>>>(c.S.p, npad);
+    APEX_CUDA_TRY(c, cudaMemsetAsync(&c.state.p->chol_fail, 0, sizeof(int32_t), c.stream));
+    APEX_CUDA_TRY(c, cudaEventRecord(e0, c.stream));
+    APEX_TRY(dense_cholesky(c, c.S.p, npad));
+    APEX_CUDA_TRY(c, cudaEventRecord(e1, c.stream));
+    APEX_CUDA_TRY(c, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    APEX_CUDA_TRY(c, cudaEventElapsedTime(&ms, e0, e1));
+    if (r >= 0) total += ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  APEX_TRY(sync_state(c));
+  if (c.h_state->chol_fail) { c.err = "benchmark matrix not positive definite?"; return APEX_ERR_FACTORIZATION_FAILED; }
+  if (ms_out) *ms_out = total / std::max(reps, 1);
   return APEX_OK;
 }
 
@@ -479,7 +613,7 @@ static apex_status dense_cholesky_solve(Ctx& c, const double* L, uint32_t npad, 
 apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol) {
   cudaStream_t s = c.stream;
   const uint32_t n = c.ncam * c.dc;
-  const uint32_t npad = (n + NB - 1) / NB * NB;
+  const uint32_t npad = (n + 2 * NB - 1) / (2 * NB) * (2 * NB);  // multiple of 128: the deep trailing update works on 128x128 tiles
   const size_t ld = npad;
   const size_t nn = (size_t)npad * npad;
   APEX_CUDA_TRY(c, c.S.alloc(nn * (use_pcg ? 1 : 2)));  // [S | factor workspace]

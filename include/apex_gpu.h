@@ -338,6 +338,9 @@ typedef struct apex_profile {
   double linearize_ms;        /* summed duration of apex_linearize's kernel group (K1+K2+K3)               */
   int64_t linearize_launches;
 } apex_profile;
+/* Measurement aid for K8: factor a synthetic n x n SPD matrix with the dense FP64 tensor-core Cholesky of the explicit
+ * Schur path `reps` times (after one warm-up); average milliseconds of the factorisation alone. Needs no problem. */
+apex_status apex_dense_cholesky_bench(apex_ctx* ctx, uint32_t n, int32_t reps, double* ms_per_factorization);
 apex_status apex_profile_enable(apex_ctx* ctx, int32_t on);
 apex_status apex_profile_read(apex_ctx* ctx, apex_profile* out);
 
