@@ -407,7 +407,16 @@ std::vector<double> gather_local_points(const Ctx& c, const double* pt_full) {
 }
 
 apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
+  const bool timing = getenv("APEX_LAYOUT_TIMING") != nullptr;
+  auto tprev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[upload] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tprev).count());
+    tprev = now;
+  };
   APEX_TRY(validate_problem(d, c.err));
+  lap("validate");
   const int K = model_intr_dim(d->camera_model);
   c.have_problem = false;
   c.linearized = false;
@@ -431,6 +440,7 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   c.nslots = (size_t)L.nchunks * TILE;
   c.slot_obs.swap(L.slot_obs);
   c.h_pt_cnt = L.pt_cnt;
+  lap("build_layout");
 
   // ---- fixed masks ----
   std::vector<uint8_t> pose_fixed(c.ncam, 0), pt_fixed(c.npl, 0);
@@ -462,6 +472,7 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   APEX_CUDA_TRY(c, upload_vec(c.intr_fixed, intr_fixed, s));
   APEX_CUDA_TRY(c, upload_vec(c.pt_fixed, pt_fixed, s));
 
+  lap("H2D of the structure (enqueue)");
   const size_t ncd = (size_t)c.ncam * c.dc;
   const int pb = 36 + K * K;
   APEX_CUDA_TRY(c, c.pose.alloc((size_t)c.ncam * 7));
@@ -496,8 +507,11 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   APEX_CUDA_TRY(c, cudaMemcpyAsync(c.intr.p, d->intr, (size_t)c.ncam * K * sizeof(double), cudaMemcpyHostToDevice, s));
   std::vector<double> pt_local = gather_local_points(c, d->pt);
   if (c.npl) APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pt.p, pt_local.data(), (size_t)c.npl * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+  lap("allocations + parameters");
   APEX_CUDA_TRY(c, cudaStreamSynchronize(s));  // the host vectors above die with this scope
+  lap("stream sync");
   APEX_TRY(setup_peer_allreduce(c, ncd));
+  lap("peer setup");
   c.have_problem = true;
   return APEX_OK;
 }

@@ -423,6 +423,36 @@ def test_error_behaviour():
     assert e.value.status == F.ERR_UNSUPPORTED
 
 
+def test_empty_and_degenerate_problems():
+    """Edge cases of the reference's front door: a problem without residual blocks is OptimizerError::NoResidualBlocks
+    (src/optimizer/mod.rs:66-141), a single observation / a camera without observations / ragged last chunks solve."""
+    base = small_problem(ncam=5, npts=40)
+    empty = BAProblemLike(base, np.zeros(0, bool))
+    for ctx in (GpuContext().upload(empty), OracleContext().upload(empty)):
+        with pytest.raises(F.ApexError) as e:
+            run_lm(ctx, F.SCHUR_IMPLICIT)
+        assert e.value.status == F.ERR_NO_RESIDUAL_BLOCKS
+    keep = np.zeros(base.nobs, bool); keep[0] = True
+    one = BAProblemLike(base, keep)
+    (rg, tg), (ro, to) = run_lm(GpuContext().upload(one), F.SCHUR_EXPLICIT, max_it=3), run_lm(OracleContext().upload(one), F.SCHUR_EXPLICIT, max_it=3)
+    assert (rg.status, rg.iterations) == (ro.status, ro.iterations) and rg.final_cost < rg.initial_cost
+    assert abs(rg.initial_cost - ro.initial_cost) <= 1e-13 * ro.initial_cost
+    assert abs(rg.final_cost - ro.final_cost) <= 1e-3 * ro.final_cost   # 1 observation, 3 + 15 + 120 unknowns: everything but 2 directions is held by lambda alone
+    nocam = BAProblemLike(base, base.obs_cam != 3)          # camera 3 keeps its variables but sees nothing
+    g, o = pair(nocam)
+    g.linearize(1e-3); o.linearize(1e-3)
+    x = np.random.default_rng(2).standard_normal(nocam.ncam * nocam.dc)
+    assert relerr(g.schur_matvec(x), o.schur_matvec(x)) < 1e-11
+    (rg, tg), (ro, to) = run_lm(g, F.SCHUR_IMPLICIT, max_it=4), run_lm(o, F.SCHUR_IMPLICIT, max_it=4)
+    assert (rg.status, rg.iterations) == (ro.status, ro.iterations)
+
+
+def BAProblemLike(p, keep):
+    from apex_solver_b200.context import BAProblem
+    return BAProblem(camera_model=p.camera_model, opt_flags=p.opt_flags, pose=p.pose, intr=p.intr, pt=p.pt, obs_cam=p.obs_cam[keep], obs_pt=p.obs_pt[keep],
+                     obs_uv=p.obs_uv[keep], loss_id=p.loss_id, loss_params=p.loss_params, intr_vars_present=p.intr_vars_present, pose_fixed=p.pose_fixed)
+
+
 def test_kernels_ran_on_the_device():
     prob = small_problem(ncam=6, npts=60)
     g = GpuContext().upload(prob)
