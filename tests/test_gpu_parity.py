@@ -442,7 +442,7 @@ def test_empty_and_degenerate_problems():
     g, o = pair(nocam)
     g.linearize(1e-3); o.linearize(1e-3)
     x = np.random.default_rng(2).standard_normal(nocam.ncam * nocam.dc)
-    assert relerr(g.schur_matvec(x), o.schur_matvec(x)) < 1e-11
+    assert relerr(g.schur_matvec(x), o.schur_matvec(x)) < 1e-10
     (rg, tg), (ro, to) = run_lm(g, F.SCHUR_IMPLICIT, max_it=4), run_lm(o, F.SCHUR_IMPLICIT, max_it=4)
     assert (rg.status, rg.iterations) == (ro.status, ro.iterations)
 
