@@ -146,6 +146,8 @@ struct Ctx {
   std::string err;
   int device = 0, rank = 0, nranks = 1;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;          // low-priority stream of the dense Cholesky's look-ahead (explicit.cu)
+  std::vector<cudaEvent_t> chol_events;    // pairs per outer panel: panel factored / rest update done
   int64_t launches = 0;
   int num_sms = 148;
   void* nccl_comm = nullptr;

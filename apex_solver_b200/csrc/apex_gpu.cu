@@ -158,6 +158,8 @@ void apex_ctx_destroy(apex_ctx* ctx) {
   for (cudaEvent_t e : c.ev_lin) cudaEventDestroy(e);
   if (c.ev_lm0) { cudaEventDestroy(c.ev_lm0); cudaEventDestroy(c.ev_lm1); }
   if (c.h_state) cudaFreeHost(c.h_state);
+  for (cudaEvent_t e : c.chol_events) cudaEventDestroy(e);
+  if (c.stream2) cudaStreamDestroy(c.stream2);
   if (c.stream) cudaStreamDestroy(c.stream);
   delete ctx;
 }

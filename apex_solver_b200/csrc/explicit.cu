@@ -284,9 +284,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
-__global__ void __launch_bounds__(256, 1) chol_syrk128_kernel(double* A, size_t ld, uint32_t k0, uint32_t kdepth, uint32_t r0) {
+__global__ void __launch_bounds__(256, 1) chol_syrk128_kernel(double* A, size_t ld, uint32_t k0, uint32_t kdepth, uint32_t r0, uint32_t bj0) {
   extern __shared__ __align__(16) double smem[];
-  const uint32_t bi = blockIdx.x, bj = blockIdx.y;
+  const uint32_t bi = blockIdx.x, bj = blockIdx.y + bj0;  // column tiles [bj0, bj0 + gridDim.y) of the trailing matrix
   if (bi < bj) return;
   const size_t ri = (size_t)r0 + (size_t)bi * SB, rj = (size_t)r0 + (size_t)bj * SB;
   const int tid = threadIdx.x;
@@ -521,6 +521,8 @@ static apex_status dense_cholesky(Ctx& c, double* L, uint32_t npad) {
   // bound by that HBM traffic, not by the FP64 tensor pipe).
   const uint32_t NBO = 4 * NB;
   const uint32_t nblk = npad / NB;
+  cudaEvent_t last_rest = nullptr;
+  bool have_rest = false;
   for (uint32_t ko = 0; ko < npad; ko += NBO) {
     const uint32_t kend = std::min(ko + NBO, npad);
     for (uint32_t k0 = ko; k0 < kend; k0 += NB) {
@@ -538,8 +540,33 @@ static apex_status dense_cholesky(Ctx& c, double* L, uint32_t npad) {
     }
     if (kend < npad) {
       if ((npad - kend) % SB == 0 && (kend - ko) % SKC == 0 && !getenv("APEX_CHOL_SYRK64")) {
-        const uint32_t rem = (npad - kend) / SB;
-        chol_syrk128_kernel<<<dim3(rem, rem), 256, syrk128_smem, s>>>(L, ld, ko, kend - ko, kend);
+        // Look-ahead: the deep update is split by columns. The 256 columns of the NEXT panel are updated on the main
+        // stream, which then goes straight on to factor that panel (potrf / trsm are latency bound on a handful of
+        // CTAs); everything to the right is updated on a second, low-priority stream at the same time. Events keep the
+        // order: "rest" update j waits for panel j (E_j); the next panel's columns wait for the previous rest update (R_j-1).
+        const uint32_t rem = (npad - kend) / SB, head = std::min<uint32_t>(rem, NBO / SB);
+        const bool lookahead = !getenv("APEX_CHOL_NO_LOOKAHEAD") && rem > head;
+        if (lookahead) {
+          if (!c.stream2) {
+            int lo = 0, hi = 0;
+            APEX_CUDA_TRY(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            APEX_CUDA_TRY(c, cudaStreamCreateWithPriority(&c.stream2, cudaStreamNonBlocking, lo));
+          }
+          const size_t pj = ko / NBO;
+          while (c.chol_events.size() < 2 * (pj + 1)) { cudaEvent_t e = nullptr; APEX_CUDA_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.chol_events.push_back(e); }
+          cudaEvent_t Ej = c.chol_events[2 * pj], Rj = c.chol_events[2 * pj + 1];
+          APEX_CUDA_TRY(c, cudaEventRecord(Ej, s));
+          if (have_rest) APEX_CUDA_TRY(c, cudaStreamWaitEvent(s, last_rest, 0));
+          chol_syrk128_kernel<<<dim3(rem, head), 256, syrk128_smem, s>>>(L, ld, ko, kend - ko, kend, 0);
+          APEX_CUDA_TRY(c, cudaStreamWaitEvent(c.stream2, Ej, 0));
+          chol_syrk128_kernel<<<dim3(rem, rem - head), 256, syrk128_smem, c.stream2>>>(L, ld, ko, kend - ko, kend, head);
+          APEX_CUDA_TRY(c, cudaEventRecord(Rj, c.stream2));
+          last_rest = Rj; have_rest = true;
+          c.launches++;
+        } else {
+          if (have_rest) { APEX_CUDA_TRY(c, cudaStreamWaitEvent(s, last_rest, 0)); have_rest = false; }
+          chol_syrk128_kernel<<<dim3(rem, rem), 256, syrk128_smem, s>>>(L, ld, ko, kend - ko, kend, 0);
+        }
       } else {
         const uint32_t rem = (npad - kend) / NB;
         chol_syrk_kernel<<<dim3(rem, rem), 128, smem, s>>>(L, ld, ko, kend - ko, kend);
@@ -547,6 +574,7 @@ static apex_status dense_cholesky(Ctx& c, double* L, uint32_t npad) {
       c.launches++;
     }
   }
+  if (have_rest) APEX_CUDA_TRY(c, cudaStreamWaitEvent(s, last_rest, 0));  // the main stream continues behind the last rest update
   APEX_CUDA_TRY(c, cudaGetLastError());
   return APEX_OK;
 }
