@@ -505,8 +505,9 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
 
   APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pose.p, d->pose, (size_t)c.ncam * 7 * sizeof(double), cudaMemcpyHostToDevice, s));
   APEX_CUDA_TRY(c, cudaMemcpyAsync(c.intr.p, d->intr, (size_t)c.ncam * K * sizeof(double), cudaMemcpyHostToDevice, s));
-  std::vector<double> pt_local = gather_local_points(c, d->pt);
-  if (c.npl) APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pt.p, pt_local.data(), (size_t)c.npl * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+  std::vector<double> pt_local;  // one rank owns every landmark in the caller's order: no gather needed
+  if (c.nranks > 1) pt_local = gather_local_points(c, d->pt);
+  if (c.npl) APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pt.p, c.nranks > 1 ? pt_local.data() : d->pt, (size_t)c.npl * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
   lap("allocations + parameters");
   APEX_CUDA_TRY(c, cudaStreamSynchronize(s));  // the host vectors above die with this scope
   lap("stream sync");
