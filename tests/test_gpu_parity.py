@@ -447,6 +447,41 @@ def test_empty_and_degenerate_problems():
     assert (rg.status, rg.iterations) == (ro.status, ro.iterations)
 
 
+def test_high_degree_cameras_and_chunk_boundaries():
+    """Cameras with more observations than one camera work item holds (2 048): H_cc / g_c / Schur-Jacobi partial sums are
+    combined across work items; landmarks with exactly 1, 255, 256 and 257 observations sit on the chunk boundaries of the
+    point-major layout (257 is a multi-chunk landmark)."""
+    base = small_problem(ncam=4, npts=7000, track=3.0, seed=5)      # every camera sees ~5 000 landmarks
+    assert np.bincount(base.obs_cam).min() > 2048
+    g, o = pair(base)
+    g.linearize(1e-3); o.linearize(1e-3)
+    assert_blocks_close(g, o, base, 1e-3)
+    sg = g.solve_augmented(F.SCHUR_EXPLICIT, 1e-3)
+    so = o.solve_augmented(F.SCHUR_EXPLICIT, 1e-3)
+    assert relerr(sg[0], so[0]) < 1e-7 and relerr(sg[1], so[1]) < 1e-7
+    sg = g.solve_augmented(F.SCHUR_IMPLICIT, 1e-3, cg_max_iterations=500, cg_tolerance=1e-10)   # 36 camera dofs: PCG fights rounding, counts are not comparable
+    so = o.solve_augmented(F.SCHUR_IMPLICIT, 1e-3, cg_max_iterations=500, cg_tolerance=1e-10)
+    assert relerr(sg[0], so[0]) < 1e-4 and relerr(sg[1], so[1]) < 1e-4
+    # track lengths on the chunk boundaries: 300 cameras, landmarks 0..3 seen by exactly 1 / 255 / 256 / 257 of them
+    prob = small_problem(ncam=300, npts=400, track=4.0, seed=6)
+    keep = prob.obs_pt >= 4
+    cams, pts = [], []
+    for lp, k in enumerate((1, 255, 256, 257)):
+        cams.append(np.arange(k, dtype=np.uint32)); pts.append(np.full(k, lp, np.uint32))
+    extra_cam, extra_pt = np.concatenate(cams), np.concatenate(pts)
+    from apex_solver_b200.context import BAProblem
+    p2 = BAProblem(camera_model=prob.camera_model, opt_flags=prob.opt_flags, pose=prob.pose, intr=prob.intr, pt=prob.pt,
+                   obs_cam=np.concatenate([prob.obs_cam[keep], extra_cam]), obs_pt=np.concatenate([prob.obs_pt[keep], extra_pt]),
+                   obs_uv=np.concatenate([prob.obs_uv[keep], np.random.default_rng(1).uniform(-50, 50, (extra_cam.size, 2))]),
+                   loss_id=prob.loss_id, loss_params=prob.loss_params, pose_fixed=prob.pose_fixed)
+    g, o = pair(p2)
+    assert abs(g.cost() - o.cost()) <= 1e-13 * abs(o.cost())
+    g.linearize(1e-3); o.linearize(1e-3)
+    assert_blocks_close(g, o, p2, 1e-3)
+    x = np.random.default_rng(3).standard_normal(p2.ncam * p2.dc)
+    assert relerr(g.schur_matvec(x), o.schur_matvec(x)) < 1e-10
+
+
 def BAProblemLike(p, keep):
     from apex_solver_b200.context import BAProblem
     return BAProblem(camera_model=p.camera_model, opt_flags=p.opt_flags, pose=p.pose, intr=p.intr, pt=p.pt, obs_cam=p.obs_cam[keep], obs_pt=p.obs_pt[keep],
