@@ -16,6 +16,14 @@
 
 namespace apex {
 
+template <typename T>
+static cudaError_t upload_vec(DevBuf<T>& buf, const StageBuf<T>& v, cudaStream_t s) {
+  cudaError_t e = buf.alloc(v.size());
+  if (e != cudaSuccess) return e;
+  if (v.empty()) return cudaSuccess;
+  return cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
 template <typename T, typename A>
 static cudaError_t upload_vec(DevBuf<T>& buf, const std::vector<T, A>& v, cudaStream_t s) {
   cudaError_t e = buf.alloc(v.size());
@@ -52,17 +60,21 @@ struct HostLayout {
   uint32_t nnormal_chunks = 0, nchunks = 0, npairs = 0;
   std::vector<TileDesc> tiles, giant_tiles;
   std::vector<uint32_t> pt_slot0, pt_cnt;
-  HostVec<uint32_t> slot_cam;
-  HostVec<uint16_t> slot_lp;
-  HostVec<double> slot_uv;
+  StageBuf<uint32_t> slot_cam;
+  StageBuf<uint16_t> slot_lp;
+  StageBuf<double> slot_uv;
   HostVec<uint64_t> slot_obs;
   std::vector<ChunkDesc> chunk_desc;
-  HostVec<uint2> cslot_meta;
+  StageBuf<uint2> cslot_meta;
   std::vector<uint32_t> cpt_meta;
-  HostVec<uint32_t> cseg_cam;
-  HostVec<uint16_t> cseg_begin;
-  HostVec<double> cm_uv;
-  HostVec<uint32_t> cm_lp;
+  StageBuf<uint32_t> cseg_cam;
+  StageBuf<uint16_t> cseg_begin;
+  StageBuf<double> cm_uv;
+  StageBuf<uint32_t> cm_lp;
+  void set_pinned(bool on) {
+    slot_cam.pinned = slot_lp.pinned = slot_uv.pinned = cslot_meta.pinned = cseg_cam.pinned = cseg_begin.pinned = cm_uv.pinned = cm_lp.pinned = on;
+  }
+  void reset() { tiles.clear(); giant_tiles.clear(); items.clear(); grp_win0.clear(); }  // what build_layout appends to
   std::vector<CamItem> items;
   std::vector<uint32_t> cam_item_start;
   uint32_t mv_G = 0, mv_W = 0;
@@ -431,7 +443,13 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   c.loss_id = d->loss_id;
   for (int i = 0; i < 4; ++i) c.loss_p[i] = d->loss_params[i];
 
-  HostLayout L;
+  if (!c.staging) {
+    auto hl = std::make_shared<HostLayout>();
+    hl->set_pinned(getenv("APEX_NO_PINNED_STAGING") == nullptr);
+    c.staging = hl;
+  }
+  HostLayout& L = *static_cast<HostLayout*>(c.staging.get());
+  L.reset();
   build_layout(d, c.nranks, c.rank, L, c.dc);
   c.mv_G = L.mv_G; c.mv_W = L.mv_W; c.mv_ngroups = (uint32_t)L.grp_win0.size();
   c.shard = L.shard; c.npl = L.npl; c.nobs_local = L.nobs_local;
