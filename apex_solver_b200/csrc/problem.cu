@@ -428,8 +428,12 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
     tprev = now;
   };
   // One process per GPU on one node: every rank builds its layout at the same time, so each takes its share of the host
-  // cores instead of all of them (8 ranks x 16 OpenMP threads on 16 cores made the 8-GPU upload 3x slower than the 1-GPU one).
-  if (c.nranks > 1 && !getenv("OMP_NUM_THREADS")) omp_set_num_threads(std::max(1, omp_get_num_procs() / c.nranks));
+  // cores - not all of them, and not the single thread torchrun's default OMP_NUM_THREADS=1 would leave it (that made the
+  // 2-GPU upload 220 ms against 49 ms on one GPU). APEX_HOST_THREADS overrides; single-rank runs keep OpenMP's own setting.
+  const int omp_before = omp_get_max_threads();
+  if (const char* ht = getenv("APEX_HOST_THREADS")) omp_set_num_threads(std::max(1, atoi(ht)));
+  else if (c.nranks > 1) omp_set_num_threads(std::max(1, omp_get_num_procs() / c.nranks));
+  struct OmpRestore { int n; ~OmpRestore() { omp_set_num_threads(n); } } omp_restore{omp_before};
   APEX_TRY(validate_problem(d, c.err));
   lap("validate");
   const int K = model_intr_dim(d->camera_model);
