@@ -103,6 +103,7 @@ def cpu_reference_leg(shape, steps, warmup, full_nobs):
     from oracle_backend import OracleContext, oracle_lib
     prob = synth.make_shape(shape, scale=CPU_SAMPLE_SCALE)
     lib = oracle_lib()
+    lib.oracle_set_num_threads(int(os.cpu_count() or 1))   # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     cores = int(lib.oracle_num_threads())
     ctx = OracleContext().upload(prob)
     pose0, intr0, pt0 = prob.pose.copy(), prob.intr.copy(), prob.pt.copy()
