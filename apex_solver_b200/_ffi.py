@@ -126,7 +126,9 @@ class IterTrace(C.Structure):
 
 class Profile(C.Structure):
     _fields_ = [("lm_device_ms", C.c_double), ("matvec_ms", C.c_double), ("matvec_launches", C.c_int64),
-                ("linearize_ms", C.c_double), ("linearize_launches", C.c_int64)]
+                ("linearize_ms", C.c_double), ("linearize_launches", C.c_int64),
+                ("schur_form_ms", C.c_double), ("schur_forms", C.c_int64), ("cholesky_ms", C.c_double), ("cholesky_factorizations", C.c_int64),
+                ("cholesky_n", C.c_uint64), ("upload_h2d_bytes", C.c_uint64)]
 
 
 class LayoutStats(C.Structure):
@@ -171,6 +173,7 @@ SYMBOLS = {
     "schur_matvec_bench": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, P(C.c_double)]),
     "solve_augmented": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, _DBL, _DBL,
                                     P(C.c_double), P(C.c_int32)]),
+    "get_step": (C.c_int32, [C.c_void_p, _DBL, _DBL]),
     "lm_solve": (C.c_int32, [C.c_void_p, P(LmConfig), P(LmResult), P(IterTrace), C.c_int32]),
     "kernel_launches": (C.c_int64, [C.c_void_p]),
     "profile_enable": (C.c_int32, [C.c_void_p, C.c_int32]),

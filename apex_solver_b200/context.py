@@ -184,6 +184,13 @@ class Context:
                                                 C.byref(g), C.byref(it)))
         return sc, sp, g.value, it.value
 
+    def get_step(self):
+        """(step_cam [ncam,dc], step_pt [npts,3]) of the last solve / the last LM iteration (parity read-back)."""
+        p = self.problem
+        sc = np.empty((p.ncam, p.dc)); sp = np.empty((p.npts, 3))
+        self._check(self._fn("get_step")(self._h, F.ptr(sc), F.ptr(sp)))
+        return sc, sp
+
     def default_config(self, for_bundle_adjustment: bool = True) -> F.LmConfig:
         cfg = F.LmConfig()
         self._fn("lm_config_for_bundle_adjustment" if for_bundle_adjustment else "lm_config_default")(C.byref(cfg))

@@ -112,6 +112,9 @@ struct DevState {
   int32_t singular_landmark;              // a landmark block could not be inverted
   int32_t chol_fail;                      // first failing column + 1 of the dense Cholesky
   int32_t pad2[2];
+  // multi-rank agreement (agree_error_flags / the LM loop's timeout): every rank must take the same exit
+  double agree[2];                        // {singular_landmark, ar_timeout} summed over the ranks
+  double elapsed;                         // rank 0's wall clock, all-reduced, for the TIMEOUT test of check_convergence
 };
 
 // Host vector whose resize() leaves trivially constructible elements uninitialised: the layout build fills the big
@@ -253,6 +256,7 @@ struct Ctx {
   DevBuf<double> pinv;               // [ncam][36 + K*K] preconditioner block inverses
   bool linearized = false;
   double lin_lambda = 0.0;
+  bool have_step = false;            // step_cam / step_pt hold the step of a solve (apex_get_step)
 
   // ---- device: solve ----
   DevBuf<double> vb, vx, vr, vz, vp, vy;  // PCG vectors, ncam*dc each
@@ -285,6 +289,10 @@ struct Ctx {
   size_t ev_mv_used = 0;              // event pairs used by operator launches since the last read
   std::vector<cudaEvent_t> ev_lin;    // pairs around launch_linearize
   size_t ev_lin_used = 0;
+  std::vector<cudaEvent_t> ev_form, ev_chol;  // explicit variants: pairs around the formation of S / the dense factorisation
+  size_t ev_form_used = 0, ev_chol_used = 0;
+  uint64_t chol_n = 0;
+  uint64_t upload_h2d_bytes = 0;      // H2D bytes of the last problem upload
   cudaEvent_t ev_lm0 = nullptr, ev_lm1 = nullptr;
   bool lm_timed = false;
 };
@@ -344,5 +352,6 @@ void release_peer_allreduce(Ctx& c);
 // comm (apex_gpu.cu)
 apex_status allreduce_sum(Ctx& c, double* dev, size_t count);
 apex_status sync_state(Ctx& c);  // copy DevState to the pinned mirror and wait
+apex_status agree_error_flags(Ctx& c);  // nranks > 1: OR of the per-rank error flags (singular landmark block, peer all-reduce timeout) on every rank
 
 }  // namespace apex

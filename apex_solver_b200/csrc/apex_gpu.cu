@@ -29,6 +29,27 @@ apex_status sync_state(Ctx& c) {
   return APEX_OK;
 }
 
+// Error flags are raised per rank (a singular landmark block lives in one shard, a peer all-reduce times out on the rank
+// that waited), but every rank has to leave the LM loop through the same exit - a rank that returned an error while its
+// peers enter the next collective would leave them blocked in it. Sum the flags over the ranks and write them back.
+__global__ void pack_error_flags_kernel(DevState* st) {
+  st->agree[0] = st->singular_landmark ? 1.0 : 0.0;
+  st->agree[1] = st->ar_timeout ? 1.0 : 0.0;
+}
+__global__ void unpack_error_flags_kernel(DevState* st) {
+  if (st->agree[0] > 0.0) st->singular_landmark = 1;
+  if (st->agree[1] > 0.0) st->ar_timeout = 1;
+}
+apex_status agree_error_flags(Ctx& c) {
+  if (c.nranks <= 1) return APEX_OK;
+  pack_error_flags_kernel<<<1, 1, 0, c.stream>>>(c.state.p);
+  APEX_TRY(allreduce_sum(c, c.state.p->agree, 2));
+  unpack_error_flags_kernel<<<1, 1, 0, c.stream>>>(c.state.p);
+  c.launches += 2;
+  APEX_CUDA_TRY(c, cudaGetLastError());
+  return APEX_OK;
+}
+
 static apex_status set_damping(Ctx& c, double lambda) {
   APEX_CUDA_TRY(c, cudaMemcpyAsync(&c.state.p->damping, &lambda, sizeof(double), cudaMemcpyHostToDevice, c.stream));
   APEX_CUDA_TRY(c, cudaStreamSynchronize(c.stream));  // `lambda` is a stack variable
@@ -156,6 +177,8 @@ void apex_ctx_destroy(apex_ctx* ctx) {
   c.state.release(); c.trace.release();
   for (cudaEvent_t e : c.ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : c.ev_lin) cudaEventDestroy(e);
+  for (cudaEvent_t e : c.ev_form) cudaEventDestroy(e);
+  for (cudaEvent_t e : c.ev_chol) cudaEventDestroy(e);
   if (c.ev_lm0) { cudaEventDestroy(c.ev_lm0); cudaEventDestroy(c.ev_lm1); }
   if (c.h_state) cudaFreeHost(c.h_state);
   for (cudaEvent_t e : c.chol_events) cudaEventDestroy(e);
@@ -356,11 +379,24 @@ apex_status apex_solve_augmented(apex_ctx* ctx, int32_t schur_variant, int32_t p
   if (schur_variant == APEX_SCHUR_IMPLICIT) st = solve_implicit(c, preconditioner, cg_max_iterations, cg_tolerance);
   else st = solve_explicit(c, schur_variant == APEX_SCHUR_EXPLICIT_PCG, cg_max_iterations, cg_tolerance);
   if (st != APEX_OK) return st;
+  c.have_step = true;
   APEX_TRY(launch_step_norms(c));
   APEX_TRY(sync_state(c));
   if (c.h_state->singular_landmark) { c.err = "Landmark block singular"; return APEX_ERR_SINGULAR_MATRIX; }
   if (grad_norm) *grad_norm = std::sqrt(c.h_state->g2_cam + c.h_state->g2_pt);
   if (pcg_iters) *pcg_iters = (int32_t)c.last_pcg_iters;
+  if (step_cam) {
+    APEX_CUDA_TRY(c, cudaMemcpyAsync(step_cam, c.step_cam.p, (size_t)c.ncam * c.dc * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    APEX_CUDA_TRY(c, cudaStreamSynchronize(c.stream));
+  }
+  if (step_pt) APEX_TRY(gather_point_rows(c, c.step_pt.p, 3, step_pt));
+  return APEX_OK;
+}
+
+apex_status apex_get_step(apex_ctx* ctx, double* step_cam, double* step_pt) {
+  CTX_OR_FAIL(ctx);
+  NEED_PROBLEM();
+  if (!c.have_step) { c.err = "no step computed yet"; return APEX_ERR_INVALID_STATE; }
   if (step_cam) {
     APEX_CUDA_TRY(c, cudaMemcpyAsync(step_cam, c.step_cam.p, (size_t)c.ncam * c.dc * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     APEX_CUDA_TRY(c, cudaStreamSynchronize(c.stream));
@@ -382,6 +418,7 @@ apex_status apex_profile_enable(apex_ctx* ctx, int32_t on) {
   c.prof = on != 0;
   c.ev_mv_used = 0;
   c.ev_lin_used = 0;
+  c.ev_form_used = c.ev_chol_used = 0;
   return APEX_OK;
 }
 
@@ -398,8 +435,13 @@ apex_status apex_profile_read(apex_ctx* ctx, apex_profile* out) {
   };
   total(c.ev_pool, c.ev_mv_used, out->matvec_ms, out->matvec_launches);
   total(c.ev_lin, c.ev_lin_used, out->linearize_ms, out->linearize_launches);
+  total(c.ev_form, c.ev_form_used, out->schur_form_ms, out->schur_forms);
+  total(c.ev_chol, c.ev_chol_used, out->cholesky_ms, out->cholesky_factorizations);
+  out->cholesky_n = c.chol_n;
+  out->upload_h2d_bytes = c.upload_h2d_bytes;
   c.ev_mv_used = 0;
   c.ev_lin_used = 0;
+  c.ev_form_used = c.ev_chol_used = 0;
   if (c.lm_timed) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, c.ev_lm0, c.ev_lm1) == cudaSuccess) out->lm_device_ms = t; else cudaGetLastError();

@@ -27,7 +27,13 @@ static int usage(const char* msg) {
           "Usage: bundle_adjustment [OPTIONS] <FILE>\n\n"
           "Options:\n"
           "  -n, --num-points <N>            Limit number of points (for testing)\n"
-          "  -s, --solver <SOLVER>           explicit | implicit [default: implicit]\n"
+          "  -s, --solver <SOLVER>           explicit | implicit | matrix-free [default: implicit]\n"
+          "                                  explicit    = SchurVariant::Sparse: dense S + Cholesky\n"
+          "                                  implicit    = SchurVariant::Iterative AS THE REFERENCE DISPATCHES IT TODAY: explicit S +\n"
+          "                                                scalar-Jacobi PCG (explicit_schur.rs:1222-1225), same trajectory as the crate\n"
+          "                                  matrix-free = the math of IterativeSchurSolver (implicit_schur.rs): S never formed, block PCG\n"
+          "                                                with the Schur-Jacobi preconditioner (what bench.py times; another truncated-PCG\n"
+          "                                                trajectory than `implicit`)\n"
           "  -t, --optimization-type <TYPE>  bundle-adjustment | self-calibration | only-pose | only-landmarks | only-intrinsics\n"
           "                                  [default: self-calibration]\n"
           "  -v, --verbose                   Verbose output\n"
@@ -64,7 +70,8 @@ int main(int argc, char** argv) {
   if (file.empty()) return usage("the following required arguments were not provided: <FILE>");
   int variant;
   if (solver == "explicit") variant = APEX_SCHUR_EXPLICIT;       // SchurVariant::Sparse (:36-43)
-  else if (solver == "implicit") variant = APEX_SCHUR_IMPLICIT;  // SchurVariant::Iterative
+  else if (solver == "implicit") variant = APEX_SCHUR_EXPLICIT_PCG;  // SchurVariant::Iterative -> solve_with_pcg on the explicit S (explicit_schur.rs:1222-1225)
+  else if (solver == "matrix-free") variant = APEX_SCHUR_IMPLICIT;   // IterativeSchurSolver's matrix-free block PCG (not reachable from the reference CLI)
   else return usage(("invalid value '" + solver + "' for '--solver <SOLVER>'").c_str());
   int opt_type;
   if (type == "bundle-adjustment") opt_type = 0;

@@ -26,9 +26,16 @@ void release_peer_allreduce(Ctx& c) {
 
 // Collective over all ranks (called from apex_problem_upload). On any failure every rank falls back to NCCL.
 apex_status setup_peer_allreduce(Ctx& c, size_t n) {
+  const bool had_peers = c.p2p_ok;
   release_peer_allreduce(c);
   if (c.nranks <= 1 || getenv("APEX_NO_P2P")) return APEX_OK;
   cudaStream_t s = c.stream;
+  if (had_peers) {
+    // re-upload: every rank has closed its mappings of the peers' buffers above; nobody may free a buffer a peer still maps
+    // (CUDA IPC rule), so meet here - a one-element all-reduce and a stream sync - before the exported buffers are released
+    APEX_TRY(allreduce_sum(c, c.state.p->agree, 1));
+    APEX_CUDA_TRY(c, cudaStreamSynchronize(s));
+  }
   int ok = 1;
   // fresh allocations: an IPC handle refers to the allocation it was taken from
   c.arbuf.release();

@@ -649,6 +649,8 @@ apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol) {
   double* S = c.S.p;
   APEX_CUDA_TRY(c, cudaMemsetAsync(S, 0, nn * sizeof(double), s));
   // --- S ---
+  cudaEvent_t* evf = c.prof ? prof_pair(c.ev_form, c.ev_form_used++) : nullptr;
+  if (evf) cudaEventRecord(evf[0], s);
   if (c.ntiles) {
     FormArgs fa{c.tiles.p, c.slot_cam.p, c.slot_lp.p, c.pt_slot0.p, c.pt_cnt.p, c.J.p, c.hinv.p, S, ld, c.npl};
     switch (c.dc) {
@@ -675,6 +677,7 @@ apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol) {
     symmetrize_drop_kernel<<<tri_count(nt), dim3(32, 8), 0, s>>>(S, ld, nt);
     c.launches++;
   }
+  if (evf) cudaEventRecord(evf[1], s);
   // --- reduced gradient ---
   APEX_TRY(launch_reduced_gradient(c, c.vb.p));
   APEX_CUDA_TRY(c, cudaGetLastError());
@@ -699,7 +702,11 @@ apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol) {
       APEX_CUDA_TRY(c, cudaMemcpyAsync(L, S, nn * sizeof(double), cudaMemcpyDeviceToDevice, s));
       if (reg != 0.0) { add_diag_kernel<<<(n + 255) / 256, 256, 0, s>>>(L, ld, n, reg); c.launches++; }
       APEX_CUDA_TRY(c, cudaMemsetAsync(&c.state.p->chol_fail, 0, sizeof(int32_t), s));
+      cudaEvent_t* evc = c.prof ? prof_pair(c.ev_chol, c.ev_chol_used++) : nullptr;
+      if (evc) cudaEventRecord(evc[0], s);
       APEX_TRY(dense_cholesky(c, L, npad));
+      if (evc) cudaEventRecord(evc[1], s);
+      c.chol_n = npad;
       APEX_TRY(sync_state(c));
       if (c.h_state->singular_landmark) { c.err = "Landmark block singular"; return APEX_ERR_SINGULAR_MATRIX; }
       solved = c.h_state->chol_fail == 0;

@@ -476,6 +476,7 @@ apex_status launch_linearize(Ctx& c) {
   APEX_CUDA_TRY(c, cudaGetLastError());
   // camera-side blocks are sums over all ranks' observations
   APEX_TRY(allreduce_sum(c, c.hcc.p, (size_t)c.ncam * c.dc * (c.dc + 1)));
+  APEX_TRY(agree_error_flags(c));  // a singular landmark block in one shard is everybody's error
   return APEX_OK;
 }
 

@@ -195,6 +195,7 @@ __global__ void lm_eval_kernel(DevState* st, LmParams p) {
 
 // after accept/revert and the parameter norm: trace row + check_convergence (mod.rs:591-658)
 __global__ void lm_converge_kernel(DevState* st, LmParams p, apex_iter_trace* trace, int trace_cap, double elapsed, int pcg_iters_hint) {
+  if (elapsed < 0.0) elapsed = st->elapsed;  // nranks > 1: rank 0's clock, all-reduced, so that every rank takes the same decision
   const int iteration = st->iteration;
   const int accepted = st->accepted;
   const double new_cost = st->new_cost;
@@ -277,6 +278,7 @@ apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, ape
     if (cfg->schur_variant == APEX_SCHUR_IMPLICIT) st = solve_implicit(c, cfg->schur_preconditioner, cfg->cg_max_iterations, cfg->cg_tolerance);
     else st = solve_explicit(c, cfg->schur_variant == APEX_SCHUR_EXPLICIT_PCG, cfg->cg_max_iterations, cfg->cg_tolerance);
     if (st != APEX_OK) return (st == APEX_ERR_SINGULAR_MATRIX || st == APEX_ERR_FACTORIZATION_FAILED) ? APEX_ERR_LINEAR_SOLVE_FAILED : st;
+    c.have_step = true;
     const int pcg_it = (int)c.last_pcg_iters;
     lin_iters += pcg_it;
     APEX_TRY(launch_step_norms(c));
@@ -287,7 +289,16 @@ apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, ape
     c.launches++;
     APEX_TRY(launch_apply_step(c, -1.0, true));   // apply_negative_parameter_step when rejected (:804-808)
     APEX_TRY(launch_param_norm(c));
-    const double elapsed = now_seconds() - t0;
+    double elapsed = now_seconds() - t0;
+    if (c.nranks > 1 && p.timeout_seconds > 0.0) {
+      // the TIMEOUT test must not depend on each rank's own clock: a rank that returned TIMEOUT while its peers enter the
+      // next linearisation would leave them blocked in ncclAllReduce. Everybody uses rank 0's elapsed time.
+      const double mine = c.rank == 0 ? elapsed : 0.0;
+      APEX_CUDA_TRY(c, cudaMemcpyAsync(&c.state.p->elapsed, &mine, sizeof(double), cudaMemcpyHostToDevice, s));
+      APEX_CUDA_TRY(c, cudaStreamSynchronize(s));  // `mine` is a stack variable
+      APEX_TRY(allreduce_sum(c, &c.state.p->elapsed, 1));
+      elapsed = -1.0;
+    }
     lm_converge_kernel<<<1, 1, 0, s>>>(c.state.p, p, trace ? c.trace.p : nullptr, trace_cap, elapsed, pcg_it);
     c.launches++;
     APEX_CUDA_TRY(c, cudaGetLastError());

@@ -16,11 +16,14 @@
 
 namespace apex {
 
+static thread_local uint64_t g_h2d_bytes = 0;  // bytes enqueued by upload_vec since problem_upload reset it
+
 template <typename T>
 static cudaError_t upload_vec(DevBuf<T>& buf, const StageBuf<T>& v, cudaStream_t s) {
   cudaError_t e = buf.alloc(v.size());
   if (e != cudaSuccess) return e;
   if (v.empty()) return cudaSuccess;
+  g_h2d_bytes += v.size() * sizeof(T);
   return cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
 }
 
@@ -29,6 +32,7 @@ static cudaError_t upload_vec(DevBuf<T>& buf, const std::vector<T, A>& v, cudaSt
   cudaError_t e = buf.alloc(v.size());
   if (e != cudaSuccess) return e;
   if (v.empty()) return cudaSuccess;
+  g_h2d_bytes += v.size() * sizeof(T);
   return cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
 }
 
@@ -439,6 +443,7 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   const int K = model_intr_dim(d->camera_model);
   c.have_problem = false;
   c.linearized = false;
+  c.have_step = false;
   if (c.pcg_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)c.pcg_graph_exec); c.pcg_graph_exec = nullptr; }
   c.model = d->camera_model; c.K = K; c.opt = d->opt_flags;
   c.opt_intr = (d->opt_flags & APEX_OPT_INTRINSIC) != 0;
@@ -476,6 +481,7 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
 
   // ---- to the device ----
   cudaStream_t s = c.stream;
+  g_h2d_bytes = 0;
   APEX_CUDA_TRY(c, upload_vec(c.tiles, L.tiles, s));
   APEX_CUDA_TRY(c, upload_vec(c.giant_tiles, L.giant_tiles, s));
   APEX_CUDA_TRY(c, upload_vec(c.slot_cam, L.slot_cam, s));
@@ -533,6 +539,7 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   std::vector<double> pt_local;  // one rank owns every landmark in the caller's order: no gather needed
   if (c.nranks > 1) pt_local = gather_local_points(c, d->pt);
   if (c.npl) APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pt.p, c.nranks > 1 ? pt_local.data() : d->pt, (size_t)c.npl * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+  c.upload_h2d_bytes = g_h2d_bytes + ((size_t)c.ncam * (7 + K) + (size_t)c.npl * 3) * sizeof(double);
   lap("allocations + parameters");
   APEX_CUDA_TRY(c, cudaStreamSynchronize(s));  // the host vectors above die with this scope
   lap("stream sync");

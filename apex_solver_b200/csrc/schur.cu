@@ -1132,6 +1132,7 @@ __global__ void __launch_bounds__(1024) pcg_init_kernel(const double* __restrict
     st->pcg_max = max_it;
     st->pcg_done = max_it <= 0 ? 1 : 0;
     st->pcg_alpha = 0.0; st->pcg_beta = 0.0; st->ticket_a = 0; st->ticket_b = 0;
+    st->ar_timeout = 0;
   }
 }
 
@@ -1252,7 +1253,7 @@ __global__ void __launch_bounds__(PCG_THREADS) ar_reduce_pap_kernel(double* cons
   if ((int)threadIdx.x < nranks) {
     long long spins = 0;
     while (ld_acquire_sys(flags + threadIdx.x) < seq) {
-      if (++spins > (1ll << 26)) { atomicExch(&st->ar_timeout, 1); break; }
+      if (++spins > (1ll << 26)) { atomicExch(&st->ar_timeout, 1); atomicExch(&st->pcg_done, 1); break; }  // the rest of the batch becomes no-ops
     }
   }
   __syncthreads();
@@ -1412,7 +1413,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) pcg_tail_kernel(TailArgs a) {
     if (tid < a.nranks) {
       long long spins = 0;
       while (ld_acquire_sys(a.flags + tid) < seq) {
-        if (++spins > (1ll << 26)) { atomicExch(&st->ar_timeout, 1); break; }
+        if (++spins > (1ll << 26)) { atomicExch(&st->ar_timeout, 1); atomicExch(&st->pcg_done, 1); break; }  // seen by the NEXT launch (read at entry)
       }
     }
     __syncthreads();
@@ -1910,6 +1911,10 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
   }
   if (cg_max_it <= 0) APEX_TRY(sync_state(c));
   c.last_pcg_iters = c.h_state->pcg_iters;
+  if (c.nranks > 1) {  // a timed-out exchange on one rank ends the solve on all of them
+    APEX_TRY(agree_error_flags(c));
+    APEX_TRY(sync_state(c));
+  }
   if (c.h_state->ar_timeout) { c.err = "peer all-reduce: a rank never published its partial result"; return APEX_ERR_NCCL; }
   if (c.h_state->singular_landmark) { c.err = "Landmark block singular"; return APEX_ERR_SINGULAR_MATRIX; }
   APEX_TRY(launch_schur_tiles(c, MODE_BACKSUB, c.step_cam.p, nullptr, 0));

@@ -319,6 +319,12 @@ apex_status apex_solve_augmented(apex_ctx* ctx, int32_t schur_variant, int32_t p
                                  int32_t cg_max_iterations, double cg_tolerance, double lambda,
                                  double* step_cam, double* step_pt, double* grad_norm, int32_t* pcg_iters);
 
+/* Debug / parity read-back of the step the last solve produced (apex_solve_augmented, or the LAST iteration of
+ * apex_lm_solve: the `step` of levenberg_marquardt.rs:888-899 before apply_parameter_step): step_cam[ncam][dc],
+ * step_pt[npts][3] in the caller's landmark order. Either pointer may be NULL. Works on every rank of a sharded context
+ * (collective: all ranks must call it). */
+apex_status apex_get_step(apex_ctx* ctx, double* step_cam, double* step_pt);
+
 /* LevenbergMarquardt::optimize (levenberg_marquardt.rs:1034-1083 -> optimize_with_mode :823-1028):
  * the whole loop, device resident. `trace` (may be NULL) receives up to trace_cap rows. */
 apex_status apex_lm_solve(apex_ctx* ctx, const apex_lm_config* cfg, apex_lm_result* result,
@@ -337,6 +343,12 @@ typedef struct apex_profile {
   int64_t matvec_launches;
   double linearize_ms;        /* summed duration of apex_linearize's kernel group (K1+K2+K3)               */
   int64_t linearize_launches;
+  double schur_form_ms;       /* explicit variants: formation of the dense reduced camera system S (K7)    */
+  int64_t schur_forms;
+  double cholesky_ms;         /* explicit variant: dense FP64 tensor-core factorisations (K8), summed      */
+  int64_t cholesky_factorizations;
+  uint64_t cholesky_n;        /* order of the factored matrix (padded)                                     */
+  uint64_t upload_h2d_bytes;  /* host-to-device bytes of the last apex_problem_upload (structure + values) */
 } apex_profile;
 /* Measurement aid for K8: factor a synthetic n x n SPD matrix with the dense FP64 tensor-core Cholesky of the explicit
  * Schur path `reps` times (after one warm-up); average milliseconds of the factorisation alone. Needs no problem. */

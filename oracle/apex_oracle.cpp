@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -34,6 +35,12 @@ namespace {
 // arithmetic, different rounding: oracle-vs-reversed-oracle is the floor any reordered (parallel)
 // implementation of the reference, including rayon with another thread count, can be held to.
 int g_reverse_order = 0;
+// Measurement aid (bench.py --impl reference, the full-size parity tests): 1 = run the landmark sweeps of the matrix-free
+// solver (operator, reduced gradient, Schur-Jacobi build) on all OpenMP threads - contiguous landmark ranges with
+// thread-private camera vectors, added in thread order. The reference runs these sweeps on ONE thread
+// (apply_schur_operator_fast, implicit_schur.rs:163-251), which is what the default 0 restates; with 1 the CPU arm is a
+// FAVOURABLE stand-in for the crate (same arithmetic per landmark, another summation order across landmarks).
+int g_parallel_sweeps = 0;
 
 constexpr double F64_EPS = 2.220446049250313e-16;
 constexpr double F64_MIN = -1.7976931348623157e308;  // Rust f64::MIN (most negative finite)
@@ -1224,6 +1231,7 @@ struct Ctx {
   std::vector<double> hcc, gc, hpp, gp, hpp_inv_exp, hpp_inv_imp;  // per camera dc*dc, dc; per point 9,3,9,9
   bool inv_exp_ok = true, inv_imp_ok = true;
   int64_t last_pcg_iters = 0;
+  std::vector<double> last_step_cam, last_step_pt;  // step of the last solve (parity read-back, oracle_get_step)
 };
 
 std::string var_name(const char* prefix, int width, uint32_t idx) {
@@ -1368,6 +1376,39 @@ inline void obs_E(const Ctx& c, const BlockLin& b, double* E) {
     for (int k = 0; k < 3; ++k) E[a * 3 + k] = jc[a] * b.jpt[k] + jc[c.dc + a] * b.jpt[3 + k];
 }
 
+// Runs sweep(q0, q1, dst) over the landmarks [p0, p1): on the calling thread straight into `y` (the reference's way), or -
+// with g_parallel_sweeps - on all OpenMP threads over contiguous landmark ranges balanced by observation count, each into a
+// private zeroed vector of n doubles; the private vectors are then added to y in thread order (reversed with g_reverse_order).
+template <typename Sweep>
+void landmark_sweep(const Ctx& c, uint32_t p0, uint32_t p1, size_t n, double* y, Sweep&& sweep) {
+  int nt = 1;
+#ifdef _OPENMP
+  if (g_parallel_sweeps) nt = omp_get_max_threads();
+#endif
+  if (nt <= 1 || p1 - p0 < 512) { sweep(p0, p1, y); return; }
+  std::vector<double> part((size_t)nt * n);
+  std::vector<uint32_t> cut(nt + 1, p1);
+  cut[0] = p0;
+  const size_t o0 = c.pt_obs_start[p0], o1 = c.pt_obs_start[p1];
+  for (int t = 1; t < nt; ++t) {
+    const size_t target = o0 + (o1 - o0) * (size_t)t / nt;
+    cut[t] = (uint32_t)(std::lower_bound(c.pt_obs_start.begin() + p0, c.pt_obs_start.begin() + p1, target) - c.pt_obs_start.begin());
+    cut[t] = std::max(cut[t], cut[t - 1]);
+  }
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+  for (int t = 0; t < nt; ++t) {
+    double* dst = &part[(size_t)t * n];
+    std::fill(dst, dst + n, 0.0);
+    sweep(cut[t], cut[t + 1], dst);
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)n; ++i) {
+    double s = y[i];
+    for (int tt = 0; tt < nt; ++tt) s += part[(size_t)(g_reverse_order ? nt - 1 - tt : tt) * n + i];
+    y[i] = s;
+  }
+}
+
 // apply_schur_operator_fast (implicit_schur.rs:163-251) restricted to points [p0,p1): y (camera-major local layout
 // ncam*dc, pose|intr) += [H_cc x + lambda x if add_hcc] - H_cp Hpp^-1 H_cp^T x.
 void schur_matvec_local(const Ctx& c, const double* x, double* y, double lambda, uint32_t p0, uint32_t p1, bool add_hcc, const std::vector<double>& hinv) {
@@ -1382,25 +1423,28 @@ void schur_matvec_local(const Ctx& c, const double* x, double* y, double lambda,
       }
     }
   }
-  double E[(6 + MAXK) * 3];
-  for (uint32_t pp = p0; pp < p1; ++pp) {
-    const uint32_t p = g_reverse_order ? p0 + (p1 - 1 - pp) : pp;
-    double t[3] = {0, 0, 0};
-    for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
-      uint32_t o = c.pt_obs[q];
-      obs_E(c, c.lin[o], E);
-      const double* xc = &x[(size_t)c.obs_cam[o] * dc];
-      for (int a = 0; a < dc; ++a) for (int k = 0; k < 3; ++k) t[k] += E[a * 3 + k] * xc[a];
+  auto sweep = [&](uint32_t q0, uint32_t q1, double* yy) {
+    double E[(6 + MAXK) * 3];
+    for (uint32_t pp = q0; pp < q1; ++pp) {
+      const uint32_t p = g_reverse_order ? q0 + (q1 - 1 - pp) : pp;
+      double t[3] = {0, 0, 0};
+      for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
+        uint32_t o = c.pt_obs[q];
+        obs_E(c, c.lin[o], E);
+        const double* xc = &x[(size_t)c.obs_cam[o] * dc];
+        for (int a = 0; a < dc; ++a) for (int k = 0; k < 3; ++k) t[k] += E[a * 3 + k] * xc[a];
+      }
+      const double* hi = &hinv[(size_t)p * 9];
+      double w[3] = {hi[0] * t[0] + hi[1] * t[1] + hi[2] * t[2], hi[3] * t[0] + hi[4] * t[1] + hi[5] * t[2], hi[6] * t[0] + hi[7] * t[1] + hi[8] * t[2]};
+      for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
+        uint32_t o = c.pt_obs[q];
+        obs_E(c, c.lin[o], E);
+        double* yc = &yy[(size_t)c.obs_cam[o] * dc];
+        for (int a = 0; a < dc; ++a) yc[a] -= E[a * 3] * w[0] + E[a * 3 + 1] * w[1] + E[a * 3 + 2] * w[2];
+      }
     }
-    const double* hi = &hinv[(size_t)p * 9];
-    double w[3] = {hi[0] * t[0] + hi[1] * t[1] + hi[2] * t[2], hi[3] * t[0] + hi[4] * t[1] + hi[5] * t[2], hi[6] * t[0] + hi[7] * t[1] + hi[8] * t[2]};
-    for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
-      uint32_t o = c.pt_obs[q];
-      obs_E(c, c.lin[o], E);
-      double* yc = &y[(size_t)c.obs_cam[o] * dc];
-      for (int a = 0; a < dc; ++a) yc[a] -= E[a * 3] * w[0] + E[a * 3 + 1] * w[1] + E[a * 3 + 2] * w[2];
-    }
-  }
+  };
+  landmark_sweep(c, p0, p1, (size_t)c.ncam * dc, y, sweep);
 }
 
 // Camera "variable" blocks of the implicit solver: per camera a 6x6 pose block and (if present) a KxK
@@ -1420,21 +1464,40 @@ void build_preconditioner(const Ctx& c, int kind, double lambda, const std::vect
         sintr[(size_t)cam * K * K + a * K + b] = (c.opt_intr ? H[(6 + a) * dc + 6 + b] : 0.0) + (a == b ? lambda : 0.0);
   }
   if (kind == APEX_PRECOND_SCHUR_JACOBI) {
-    double E[(6 + MAXK) * 3], T[(6 + MAXK) * 3];
     // visibility lists are in landmark-block order (build_visibility_index :784-831)
-    for (uint32_t k = 0; k < c.npts; ++k) {
-      uint32_t p = c.lm_order[k];
-      if (p < p0 || p >= p1) continue;
-      const double* hi = &hinv[(size_t)p * 9];
-      for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
-        uint32_t o = c.pt_obs[q], cam = c.obs_cam[o];
-        obs_E(c, c.lin[o], E);
-        for (int a = 0; a < dc; ++a) for (int j = 0; j < 3; ++j) T[a * 3 + j] = E[a * 3] * hi[j] + E[a * 3 + 1] * hi[3 + j] + E[a * 3 + 2] * hi[6 + j];
-        for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b)
-          spose[(size_t)cam * 36 + a * 6 + b] -= T[a * 3] * E[b * 3] + T[a * 3 + 1] * E[b * 3 + 1] + T[a * 3 + 2] * E[b * 3 + 2];
-        if (c.opt_intr)
-          for (int a = 0; a < K; ++a) for (int b = 0; b < K; ++b)
-            sintr[(size_t)cam * K * K + a * K + b] -= T[(6 + a) * 3] * E[(6 + b) * 3] + T[(6 + a) * 3 + 1] * E[(6 + b) * 3 + 1] + T[(6 + a) * 3 + 2] * E[(6 + b) * 3 + 2];
+    auto sweep = [&](uint32_t k0, uint32_t k1, double* sp, double* si) {
+      double E[(6 + MAXK) * 3], T[(6 + MAXK) * 3];
+      for (uint32_t k = k0; k < k1; ++k) {
+        uint32_t p = c.lm_order[k];
+        if (p < p0 || p >= p1) continue;
+        const double* hi = &hinv[(size_t)p * 9];
+        for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
+          uint32_t o = c.pt_obs[q], cam = c.obs_cam[o];
+          obs_E(c, c.lin[o], E);
+          for (int a = 0; a < dc; ++a) for (int j = 0; j < 3; ++j) T[a * 3 + j] = E[a * 3] * hi[j] + E[a * 3 + 1] * hi[3 + j] + E[a * 3 + 2] * hi[6 + j];
+          for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b)
+            sp[(size_t)cam * 36 + a * 6 + b] -= T[a * 3] * E[b * 3] + T[a * 3 + 1] * E[b * 3 + 1] + T[a * 3 + 2] * E[b * 3 + 2];
+          if (c.opt_intr)
+            for (int a = 0; a < K; ++a) for (int b = 0; b < K; ++b)
+              si[(size_t)cam * K * K + a * K + b] -= T[(6 + a) * 3] * E[(6 + b) * 3] + T[(6 + a) * 3 + 1] * E[(6 + b) * 3 + 1] + T[(6 + a) * 3 + 2] * E[(6 + b) * 3 + 2];
+        }
+      }
+    };
+    int nt = 1;
+#ifdef _OPENMP
+    if (g_parallel_sweeps && c.npts >= 512) nt = omp_get_max_threads();
+#endif
+    if (nt <= 1) sweep(0, c.npts, spose.data(), sintr.data());
+    else {  // measurement aid, see g_parallel_sweeps: private subtrahends per thread, added in thread order
+      std::vector<std::vector<double>> pp(nt), pi(nt);
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+      for (int t = 0; t < nt; ++t) {
+        pp[t].assign(spose.size(), 0.0); pi[t].assign(sintr.size(), 0.0);
+        sweep((uint32_t)((uint64_t)c.npts * t / nt), (uint32_t)((uint64_t)c.npts * (t + 1) / nt), pp[t].data(), pi[t].data());
+      }
+      for (int t = 0; t < nt; ++t) {
+        for (size_t i = 0; i < spose.size(); ++i) spose[i] += pp[t][i];
+        for (size_t i = 0; i < sintr.size(); ++i) sintr[i] += pi[t][i];
       }
     }
   }
@@ -1559,19 +1622,21 @@ apex_status solve_implicit(Ctx& c, int precond_kind, int cg_max_it, double cg_to
   // g_red = g_c - H_cp Hpp^-1 g_p (:863-880) in local camera-major layout
   std::vector<double> b(n);
   for (size_t i = 0; i < n; ++i) b[i] = -c.gc[i];
-  double E[(6 + MAXK) * 3];
-  for (uint32_t pp = 0; pp < c.npts; ++pp) {
-    const uint32_t p = g_reverse_order ? c.npts - 1 - pp : pp;
-    const double* hi = &hinv[(size_t)p * 9];
-    double g[3] = {-c.gp[(size_t)p * 3], -c.gp[(size_t)p * 3 + 1], -c.gp[(size_t)p * 3 + 2]};
-    double t[3] = {hi[0] * g[0] + hi[1] * g[1] + hi[2] * g[2], hi[3] * g[0] + hi[4] * g[1] + hi[5] * g[2], hi[6] * g[0] + hi[7] * g[1] + hi[8] * g[2]};
-    for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
-      uint32_t o = c.pt_obs[q];
-      obs_E(c, c.lin[o], E);
-      double* bc = &b[(size_t)c.obs_cam[o] * dc];
-      for (int a = 0; a < dc; ++a) bc[a] -= E[a * 3] * t[0] + E[a * 3 + 1] * t[1] + E[a * 3 + 2] * t[2];
+  landmark_sweep(c, 0, c.npts, n, b.data(), [&](uint32_t q0, uint32_t q1, double* dst) {
+    double E[(6 + MAXK) * 3];
+    for (uint32_t pp = q0; pp < q1; ++pp) {
+      const uint32_t p = g_reverse_order ? q0 + (q1 - 1 - pp) : pp;
+      const double* hi = &hinv[(size_t)p * 9];
+      double g[3] = {-c.gp[(size_t)p * 3], -c.gp[(size_t)p * 3 + 1], -c.gp[(size_t)p * 3 + 2]};
+      double t[3] = {hi[0] * g[0] + hi[1] * g[1] + hi[2] * g[2], hi[3] * g[0] + hi[4] * g[1] + hi[5] * g[2], hi[6] * g[0] + hi[7] * g[1] + hi[8] * g[2]};
+      for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
+        uint32_t o = c.pt_obs[q];
+        obs_E(c, c.lin[o], E);
+        double* bc = &dst[(size_t)c.obs_cam[o] * dc];
+        for (int a = 0; a < dc; ++a) bc[a] -= E[a * 3] * t[0] + E[a * 3 + 1] * t[1] + E[a * 3 + 2] * t[2];
+      }
     }
-  }
+  });
   std::vector<double> pinv_pose, pinv_intr;
   build_preconditioner(c, precond_kind, lambda, hinv, 0, c.npts, pinv_pose, pinv_intr);
   auto apply_precond = [&](const std::vector<double>& r, std::vector<double>& z) {  // :409-443
@@ -1609,18 +1674,18 @@ apex_status solve_implicit(Ctx& c, int precond_kind, int cg_max_it, double cg_to
     schur_matvec_local(c, pvec.data(), ap.data(), lambda, 0, c.npts, true, hinv);
     double p_ap = 0.0;
     for (size_t i = 0; i < n; ++i) p_ap += pvec[i] * ap[i];
-    if (std::fabs(p_ap) < 1e-20) break;
+    if (std::fabs(p_ap) < 1e-20) { if (getenv("ORACLE_DEBUG_PCG")) fprintf(stderr, "[pcg] it %d: |pAp| = %g < 1e-20\n", it, p_ap); break; }
     double alpha = rz_old / p_ap;
     for (size_t i = 0; i < n; ++i) x[i] += alpha * pvec[i];
     for (size_t i = 0; i < n; ++i) r[i] -= alpha * ap[i];
     double r_norm = 0.0;
     for (size_t i = 0; i < n; ++i) r_norm += r[i] * r[i];
     r_norm = std::sqrt(r_norm);
-    if (r_norm < tol) break;
+    if (r_norm < tol) { if (getenv("ORACLE_DEBUG_PCG")) fprintf(stderr, "[pcg] it %d: r_norm %g < tol %g\n", it, r_norm, tol); break; }
     apply_precond(r, z);
     double rz_new = 0.0;
     for (size_t i = 0; i < n; ++i) rz_new += r[i] * z[i];
-    if (std::fabs(rz_old) < 1e-30) break;
+    if (std::fabs(rz_old) < 1e-30) { if (getenv("ORACLE_DEBUG_PCG")) fprintf(stderr, "[pcg] it %d: |rz_old| = %g < 1e-30\n", it, rz_old); break; }
     double beta = rz_new / rz_old;
     for (size_t i = 0; i < n; ++i) pvec[i] = z[i] + beta * pvec[i];
     rz_old = rz_new;
@@ -1663,6 +1728,8 @@ apex_status solve_augmented(Ctx& c, int variant, int precond, int cg_max_it, dou
   out.step_norm = std::sqrt(s2);
   out.step_dot_grad = sg;
   c.last_pcg_iters = out.pcg_iters;
+  c.last_step_cam = out.cam;
+  c.last_step_pt = out.pt;
   return APEX_OK;
 }
 
@@ -1794,6 +1861,7 @@ int32_t oracle_num_threads(void) {
 #endif
 }
 void oracle_set_reverse_order(int32_t on) { g_reverse_order = on ? 1 : 0; }
+void oracle_set_parallel_sweeps(int32_t on) { g_parallel_sweeps = on ? 1 : 0; }
 void oracle_set_num_threads(int32_t n) {
 #ifdef _OPENMP
   if (n > 0) omp_set_num_threads(n);
@@ -1923,6 +1991,47 @@ apex_status oracle_solve_augmented(oracle_ctx* ctx, int32_t variant, int32_t pre
   return APEX_OK;
 }
 
+// Parity read-back: the step of the last solve (oracle_solve_augmented or the last iteration of oracle_lm_solve).
+apex_status oracle_get_step(oracle_ctx* ctx, double* step_cam, double* step_pt) {
+  Ctx& c = ctx->c;
+  if (c.last_step_cam.empty()) { c.err = "no step computed yet"; return APEX_ERR_INVALID_STATE; }
+  if (step_cam) std::copy(c.last_step_cam.begin(), c.last_step_cam.end(), step_cam);
+  if (step_pt) std::copy(c.last_step_pt.begin(), c.last_step_pt.end(), step_pt);
+  return APEX_OK;
+}
+// Test aid: apply_parameter_step / apply_negative_parameter_step (optimizer/mod.rs:309-356) with a GIVEN step
+// (step_cam [ncam][dc], step_pt [npts][3]); unreferenced intrinsics variables get a zero step.
+apex_status oracle_apply_step(oracle_ctx* ctx, const double* step_cam, const double* step_pt, double sign) {
+  Ctx& c = ctx->c;
+  StepOut s;
+  s.cam.assign(step_cam, step_cam + (size_t)c.ncam * c.dc);
+  s.pt.assign(step_pt, step_pt + (size_t)c.npts * 3);
+  if (!c.opt_intr && c.intr_vars) s.intr_unref.assign((size_t)c.ncam * c.K, 0.0);
+  apply_step(c, s, sign);
+  c.linearized = false;
+  return APEX_OK;
+}
+// Test aid: back-substitution (implicit_schur.rs:923-932 / explicit_schur.rs:980-1029) of a GIVEN camera step on the
+// current linearization: dp = Hpp^-1 (-g_p - H_cp^T dc). `flavour` selects the guarded inverse (1 = implicit solver's).
+apex_status oracle_back_substitute(oracle_ctx* ctx, const double* step_cam, int32_t flavour, double* step_pt) {
+  Ctx& c = ctx->c;
+  if (!c.linearized) { c.err = "not linearized"; return APEX_ERR_INVALID_STATE; }
+  const int dc = c.dc;
+  const std::vector<double>& hinv = flavour ? c.hpp_inv_imp : c.hpp_inv_exp;
+  for (uint32_t p = 0; p < c.npts; ++p) {
+    double t[3] = {0, 0, 0}, E[(6 + MAXK) * 3];
+    for (size_t q = c.pt_obs_start[p]; q < c.pt_obs_start[p + 1]; ++q) {
+      uint32_t o = c.pt_obs[q];
+      obs_E(c, c.lin[o], E);
+      const double* xc = &step_cam[(size_t)c.obs_cam[o] * dc];
+      for (int a = 0; a < dc; ++a) for (int k = 0; k < 3; ++k) t[k] += E[a * 3 + k] * xc[a];
+    }
+    double rhs[3] = {-c.gp[(size_t)p * 3] - t[0], -c.gp[(size_t)p * 3 + 1] - t[1], -c.gp[(size_t)p * 3 + 2] - t[2]};
+    const double* hi = &hinv[(size_t)p * 9];
+    for (int a = 0; a < 3; ++a) step_pt[(size_t)p * 3 + a] = hi[a * 3] * rhs[0] + hi[a * 3 + 1] * rhs[1] + hi[a * 3 + 2] * rhs[2];
+  }
+  return APEX_OK;
+}
 apex_status oracle_lm_solve(oracle_ctx* ctx, const apex_lm_config* cfg, apex_lm_result* result, apex_iter_trace* trace, int32_t trace_cap) {
   return lm_solve(ctx->c, cfg, result, trace, trace_cap);
 }

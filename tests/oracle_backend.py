@@ -61,6 +61,9 @@ def oracle_lib():
             "oracle_get_column_layout": (I32, [VP, VP, VP, VP]),
             "oracle_set_num_threads": (None, [I32]),
             "oracle_set_reverse_order": (None, [I32]),
+            "oracle_set_parallel_sweeps": (None, [I32]),
+            "oracle_apply_step": (I32, [VP, VP, VP, DBL]),
+            "oracle_back_substitute": (I32, [VP, VP, I32, VP]),
         }
         for name, (res, args) in sigs.items():
             fn = getattr(lib, name)
@@ -76,6 +79,17 @@ class OracleContext(Context):
     def get_blocks(self, implicit_flavour=True):
         return super().get_blocks(1 if implicit_flavour else 0)
 
+    def apply_step(self, step_cam, step_pt, sign=1.0):
+        sc, sp = F.as_f64(step_cam), F.as_f64(step_pt)
+        self._check(self._lib.oracle_apply_step(self._h, F.ptr(sc), F.ptr(sp), float(sign)))
+
+    def back_substitute(self, step_cam, implicit_flavour=True):
+        import numpy as np
+        sc = F.as_f64(step_cam)
+        sp = np.empty((self.problem.npts, 3))
+        self._check(self._lib.oracle_back_substitute(self._h, F.ptr(sc), 1 if implicit_flavour else 0, F.ptr(sp)))
+        return sp
+
     def schur_matvec_partial(self, x, p0, p1, add_hcc):
         import numpy as np
         p = self.problem
@@ -83,3 +97,42 @@ class OracleContext(Context):
         y = np.empty_like(x)
         self._check(self._lib.oracle_schur_matvec_partial(self._h, F.ptr(x), F.ptr(y), int(p0), int(p1), 1 if add_hcc else 0))
         return y
+
+
+class OracleVariant(OracleContext):
+    """The oracle in another SUMMATION ORDER: same arithmetic per observation / landmark, block sums and landmark sweeps
+    accumulated in reverse order (`reverse`) and / or spread over `threads` OpenMP threads with thread-private partial
+    results added in thread order (`parallel`; the reference runs these sweeps on one thread, any rayon thread count
+    reorders its other sums the same way). oracle-vs-OracleVariant is the rounding yardstick of the parity tests: the
+    reference algorithm itself is only reproducible down to that floor. Also the CPU stand-in "device under test" that
+    exercises the parity harness without a GPU, and (parallel=True) the fast CPU arm of the full-size tests / bench.py."""
+
+    def __init__(self, reverse=False, parallel=False, threads=None):
+        super().__init__()
+        self._flags = (1 if reverse else 0, 1 if parallel else 0, threads)
+
+    def _wrap(name):
+        def call(self, *a, **kw):
+            lib = oracle_lib()
+            rev, par, threads = self._flags
+            before = lib.oracle_num_threads()
+            lib.oracle_set_reverse_order(rev)
+            lib.oracle_set_parallel_sweeps(par)
+            if threads:
+                lib.oracle_set_num_threads(int(threads))
+            try:
+                return getattr(OracleContext, name)(self, *a, **kw)
+            finally:
+                lib.oracle_set_reverse_order(0)
+                lib.oracle_set_parallel_sweeps(0)
+                if threads:
+                    lib.oracle_set_num_threads(before)
+        return call
+
+    get_step = OracleContext.get_step
+    linearize = _wrap("linearize")
+    cost = _wrap("cost")
+    schur_matvec = _wrap("schur_matvec")
+    solve_augmented = _wrap("solve_augmented")
+    lm_solve = _wrap("lm_solve")
+    del _wrap

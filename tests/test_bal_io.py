@@ -151,3 +151,17 @@ def test_cli_without_a_device_fails_loudly(tmp_path):
     assert subprocess.run([exe, path, "-s", "nope"], capture_output=True, text=True).returncode == 2
     assert subprocess.run([exe, str(tmp_path / "missing.txt")], capture_output=True, text=True).returncode == 1
     assert subprocess.run([exe], capture_output=True, text=True).returncode == 2
+
+
+def test_header_counts_larger_than_the_file_fail_cleanly(tmp_path):
+    """An untrusted header (4e9 observations / cameras / points in a 30-byte file) must end in the loader's end-of-file
+    errors, not in a 100 GB allocation or a C++ exception crossing the C ABI."""
+    from apex_solver_b200 import _ffi as F
+    from apex_solver_b200.bal import load_bal
+    for text, what in (("3 3 4000000000\n0 0 1.0 2.0\n", "observations section"), ("4000000000 1 1\n0 0 1.0 2.0\n1.0\n", "camera 0 parameter 1"),
+                       ("1 4000000000 0\n" + "1.0\n" * 9 + "2.0\n", "point 0 coordinate 1")):
+        path = tmp_path / "hostile.txt"
+        path.write_text(text)
+        with pytest.raises(F.ApexError) as e:
+            load_bal(str(path))
+        assert e.value.status == F.ERR_PARSE and "Unexpected end of file in " + what in str(e.value), str(e.value)

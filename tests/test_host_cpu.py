@@ -214,6 +214,20 @@ def test_bench_reference_arm_contract():
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_teacher_forced_parity_harness_on_cpu():
+    """The harness the `-m gpu` suite uses (tests/parity_helpers.py), exercised here with the oracle in another summation
+    order (reversed block sums, landmark sweeps spread over 8 threads) as the device under test: cost / gradient / backward
+    agreement of the steps / back-substitution / trial cost / rho / damping / accept flag / parameters at every iterate of
+    the oracle's trajectory."""
+    from oracle_backend import OracleVariant
+    from parity_helpers import teacher_forced_parity
+    prob = synth.make_problem(16, 600, 4.0, seed=7, self_calibration=True)
+    for variant, bw in ((F.SCHUR_IMPLICIT, 1e-9), (F.SCHUR_EXPLICIT, 1e-11)):
+        rows = teacher_forced_parity(prob, variant, OracleVariant(reverse=True, parallel=True, threads=8).upload(prob), OracleContext().upload(prob),
+                                     OracleContext().upload(prob), oracle_lib(), twin=OracleVariant(reverse=True).upload(prob), n_it=3)
+        assert len(rows) == 3 and all(r["backward"] < bw for r in rows)
+
+
 # ---- N > 1: observation/landmark sharding with replicated camera blocks, over gloo, world_size 2 ---------------
 GLOO_WORKER = r'''
 import os, sys
