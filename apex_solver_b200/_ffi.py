@@ -81,6 +81,10 @@ class CtxDesc(C.Structure):
                 ("nccl_unique_id", C.c_void_p)]
 
 
+class LossSpec(C.Structure):
+    _fields_ = [("loss_id", C.c_int32), ("reserved", C.c_int32), ("params", C.c_double * 4)]
+
+
 class ProblemDesc(C.Structure):
     _fields_ = [
         ("camera_model", C.c_int32), ("opt_flags", C.c_uint32), ("intr_dim", C.c_int32), ("intr_vars_present", C.c_int32),
@@ -89,6 +93,7 @@ class ProblemDesc(C.Structure):
         ("obs_cam", C.c_void_p), ("obs_pt", C.c_void_p), ("obs_uv", C.c_void_p),
         ("loss_id", C.c_int32), ("reserved0", C.c_int32), ("loss_params", C.c_double * 4),
         ("pose_fixed", C.c_void_p), ("intr_fixed", C.c_void_p), ("pt_fixed", C.c_void_p),
+        ("obs_loss", C.c_void_p), ("loss_table", C.c_void_p), ("n_losses", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -135,7 +140,7 @@ class LayoutStats(C.Structure):
     _fields_ = [("shard_block", C.c_uint32), ("npts_local", C.c_uint32), ("nobs_local", C.c_uint64), ("ntiles", C.c_uint32), ("nlong_tiles", C.c_uint32),
                 ("nchunks", C.c_uint32), ("nnormal_chunks", C.c_uint32), ("ncam_items", C.c_uint32), ("max_segments_per_chunk", C.c_uint32),
                 ("nsegments", C.c_uint64), ("slots_used", C.c_uint64), ("consistent", C.c_int32), ("reserved", C.c_int32), ("build_ms", C.c_double),
-                ("mv_group", C.c_uint32), ("mv_window", C.c_uint32), ("mv_ngroups", C.c_uint32), ("reserved2", C.c_uint32), ("nobs_in_window", C.c_uint64)]
+                ("mv_ranges", C.c_uint32), ("mv_window", C.c_uint32), ("mv_nwindows", C.c_uint32), ("reserved2", C.c_uint32), ("mv_rows", C.c_uint64)]
 
 
 class BalView(C.Structure):

@@ -33,6 +33,8 @@ class BAProblem:
     pose_fixed: Optional[np.ndarray] = None   # [ncam] u8 bitmask
     intr_fixed: Optional[np.ndarray] = None   # [ncam] u16 bitmask
     pt_fixed: Optional[np.ndarray] = None     # [npts] u8 bitmask
+    obs_loss: Optional[np.ndarray] = None     # [nobs] u8 index into loss_table (per-block loss functions), None = uniform loss
+    loss_table: Optional[list] = None         # [(loss_id, p0, p1, ...), ...]
     meta: dict = field(default_factory=dict)
 
     def __post_init__(self):
@@ -49,6 +51,8 @@ class BAProblem:
             self.intr_fixed = np.ascontiguousarray(self.intr_fixed, dtype=np.uint16)
         if self.pt_fixed is not None:
             self.pt_fixed = np.ascontiguousarray(self.pt_fixed, dtype=np.uint8)
+        if self.obs_loss is not None:
+            self.obs_loss = np.ascontiguousarray(self.obs_loss, dtype=np.uint8).reshape(-1)
 
     @property
     def ncam(self): return self.pose.shape[0]
@@ -76,6 +80,16 @@ class BAProblem:
         d.pose_fixed = F.ptr(self.pose_fixed)
         d.intr_fixed = F.ptr(self.intr_fixed)
         d.pt_fixed = F.ptr(self.pt_fixed)
+        if self.obs_loss is not None:
+            tab = (F.LossSpec * len(self.loss_table))()
+            for i, row in enumerate(self.loss_table):
+                tab[i].loss_id = int(row[0])
+                prm = tuple(row[1:]) + (0.0,) * 4
+                tab[i].params = (C.c_double * 4)(*prm[:4])
+            self._loss_table_c = tab   # keep alive while the descriptor is in use
+            d.obs_loss = F.ptr(self.obs_loss)
+            d.loss_table = C.cast(tab, C.c_void_p)
+            d.n_losses = len(self.loss_table)
         return d
 
 

@@ -1,7 +1,7 @@
 // apex_ctx.h — host-side context of the B200 bundle-adjustment path: device buffers, the static
 // observation structure built at upload, and the launchers of every kernel group.
 //
-// Data layout in HBM (all FP64, indices u32):
+// Data layout in HBM (all FP64, indices u32; DESIGN.md section 2 has the full description):
 //   * Observations are sharded with their landmark (block-cyclic: blocks of 128 consecutive landmarks go round the
 //     ranks, so every rank sees every camera neighbourhood) and stored POINT-MAJOR
 //     in "slots". Slots are grouped in chunks of TILE=256; a tile is one chunk holding a run of whole
@@ -12,6 +12,10 @@
 //     the loss-corrected residual (2 planes) and Jacobian (2*(dc+3) planes), chunk-blocked:
 //     J[(chunk*NP + plane)*TILE + lane] so a chunk's Jacobians are one contiguous 8*NP*256-byte run
 //     and every warp access is a full 256-byte line pair.
+//   * SPLIT SLOT ORDER inside a normal chunk: the landmark half of the Jacobian (planes 2dc..2dc+5), the residual and the
+//     pixel sit at the observation's POINT-MAJOR lane; the camera half (planes 0..2dc-1) sits at the observation's
+//     CAMERA-SORTED lane (observations of the chunk sorted by camera). cslot_meta holds both permutations. Chunks of a
+//     landmark with more than 256 observations keep the camera half at the point-major lane.
 //   * Per landmark (SoA planes over local landmarks): H_pp (6, symmetric), g_p (3), (H_pp+lambda I)^-1 (6).
 //   * Camera side (replicated on every rank): pose[ncam][7], intr[ncam][K], H_cc[ncam][dc][dc], g_c[ncam][dc],
 //     preconditioner blocks, PCG vectors of ncam*dc doubles.
@@ -47,12 +51,38 @@ struct TileDesc {
   uint32_t nchunks;  // 1 for a normal tile; >1 only when npt == 1
 };
 
-// Per-chunk descriptor of the ping-pong operator kernel (one 256-thread group processes one chunk at a time).
+// Per-chunk descriptor of the chunk kernel.
 struct ChunkDesc {
-  uint32_t pt0, npt;   // landmarks of the chunk (0 landmarks for a padding chunk)
-  uint32_t nseg;       // distinct cameras among its <=256 observations
-  uint32_t pad;
+  uint32_t pt0, npt;   // landmarks of the chunk
+  uint32_t nwseg;      // warp-segments: runs of one camera among the camera-sorted lanes, cut at warp boundaries
+  uint32_t nobs;       // observations of the chunk (point-major lanes / camera-sorted lanes 0..nobs-1 are in use)
 };
+// cslot_meta[chunk*TILE + t] = {x, y}:
+//   x       camera of CAMERA-SORTED lane t (PAD_CAM for t >= nobs)
+//   y[ 7:0] chunk-local landmark of POINT-MAJOR lane t
+//   y[15:8] camera-sorted lane of the observation at point-major lane t
+//   y[23:16] point-major lane of the observation at camera-sorted lane t
+//   y[24]   camera-sorted lane t is the first lane of a warp and CONTINUES the run of the previous warp's last lane
+//   y[25]   ... and is the first continuation of that run (the previous warp did not start with the same run)
+//   y[28:26] number of consecutive warps, from this one on, that start with a continuation of the same run (1..7)
+// cslot_widx[chunk*TILE + t]: index of the camera of camera-sorted lane t in the camera list of the chunk's WINDOW.
+//
+// Operator work distribution (schur.cu). The normal chunks are cut into `nranges` contiguous ranges of equal length, one per
+// resident CTA of the chunk kernel; a range is cut into WINDOWS: maximal runs of chunks whose observations touch at most
+// W distinct cameras (W >= 256, so a chunk always fits). The CTA keeps the window's rows of the operator result in shared
+// memory and flushes them once per window.
+struct WinDesc {
+  uint32_t chunk_begin, chunk_end;  // chunks of the window
+  uint32_t cam0, ncams;             // its sorted camera list = win_cams[cam0 .. cam0+ncams); also its rows of the partial results
+};
+constexpr uint32_t CONT_BIT = 1u << 24, CONT_FIRST_BIT = 1u << 25;
+constexpr int CONT_LEN_SHIFT = 26;
+constexpr int MV_DEFAULT_CTAS = 444;  // host-only layout statistics: 3 CTAs on each of 148 SMs
+// cameras per window: 32 KB of shared memory for the window's rows of y, never below one chunk's worth of cameras
+inline uint32_t mv_window_cameras(int dc) {
+  if (const char* e = getenv("APEX_MV_WINDOW")) { const int w = atoi(e); if (w >= TILE) return (uint32_t)std::min(w, 4096); }
+  return (uint32_t)std::max(TILE, 32768 / (8 * dc));
+}
 // Landmark ownership: blocks of SHARD_BLOCK consecutive landmarks are dealt round-robin to the ranks. A contiguous
 // split would give each rank one camera neighbourhood of a locality-ordered reconstruction, i.e. 1/nranks of the
 // camera rows to reduce into (measured: 0.084 ms vs 0.059 ms per operator application on an eighth of Venice-1778).
@@ -71,20 +101,7 @@ struct ShardMap {
     return (mine - 1) * SHARD_BLOCK + last_size;
   }
 };
-constexpr int CSEG_LD = TILE + 8;     // u16 entries per chunk in cseg_begin (sentinel + padding to a 16-byte multiple: bulk copies)
-constexpr int MAX_TILE_PTS = 128;     // landmarks per normal tile (so a supertile stages <= 256 landmark inverses)
-
-// Window kernel of the Schur operator (schur.cu): shared memory of one CTA besides the two camera windows, and the
-// window width that still lets three CTAs share an SM ((228 KB - 3 x 1 KB reserved) / 3 = 76 800 B each).
-inline size_t mv_window_base_bytes(int dc) {
-  return sizeof(double) * ((size_t)dc * (TILE + 1) + 9 * MAX_TILE_PTS) + 4 * MAX_TILE_PTS + 4 * TILE + ((2 * CSEG_LD + 15) & ~15);
-}
-inline uint32_t mv_window_cameras(int dc, uint32_t ncam) {
-  const size_t budget = 76800, base = mv_window_base_bytes(dc);
-  size_t w = base < budget ? (budget - base) / (16 * (size_t)dc) : 0;
-  w &= ~(size_t)7;
-  return (uint32_t)(w < ncam ? w : ncam);
-}
+constexpr int MAX_TILE_PTS = 128;     // landmarks per normal tile
 
 struct CamItem { uint32_t cam, begin, end, pad; };  // [begin,end) in the camera-major arrays
 
@@ -212,9 +229,14 @@ struct Ctx {
   uint64_t nobs_local = 0;
   ShardMap shard;
   uint32_t nchunks = 0, ntiles = 0, nitems = 0;
-  uint32_t npairs = 0, ngiant = 0, nnormal_chunks = 0;  // npairs: chunk pairs (2s, 2s+1) walked by the operator kernel
+  uint32_t ngiant = 0, nnormal_chunks = 0;
+  uint32_t mv_nranges = 0, mv_window = 0, mv_ctas_per_sm = 0;   // chunk kernel: ranges (= CTAs), cameras per window
+  uint32_t mv_nwindows = 0;
+  uint64_t mv_nrows = 0;           // sum of the windows' camera counts (rows of det_partial)
+  bool mv_det = false;             // flush the windows as per-window partial rows + fixed-order second pass (bitwise reproducible)
   size_t nslots = 0;
   HostVec<uint64_t> slot_obs;      // slot -> caller's observation index (UINT64_MAX for padding)
+  HostVec<uint8_t> slot_pos;       // slot -> lane of the camera half of its Jacobian inside the chunk
   std::shared_ptr<void> staging;   // the HostLayout of problem.cu, kept between uploads (pinned staging arrays)
   std::vector<uint32_t> h_pt_cnt;
 
@@ -223,15 +245,18 @@ struct Ctx {
   DevBuf<uint32_t> slot_cam;
   DevBuf<uint16_t> slot_lp;
   DevBuf<TileDesc> giant_tiles;      // the tiles with nchunks > 1 (a landmark with more than 256 observations)
-  DevBuf<ChunkDesc> chunk_desc;      // [nnormal_chunks rounded up to even]
-  DevBuf<uint2> cslot_meta;          // per slot: {camera, chunk-local landmark | sorted position << 8 | segment << 16}
+  DevBuf<ChunkDesc> chunk_desc;      // [nnormal_chunks]
+  DevBuf<uint2> cslot_meta;          // [nnormal_chunks][TILE], see ChunkDesc
   DevBuf<uint32_t> cpt_meta;         // per landmark: chunk-local first slot | count << 16
-  DevBuf<uint32_t> cseg_cam;         // [chunk][256]
-  DevBuf<uint16_t> cseg_begin;       // [chunk][CSEG_LD]
-  DevBuf<double> xpad;               // operator input at an even per-camera stride
-  uint32_t mv_G = 0, mv_W = 0, mv_ngroups = 0;  // window kernel: chunks per group, cameras per window (0 = chunk kernel), groups
-  DevBuf<uint32_t> grp_win0;         // [mv_ngroups] first camera of each group's window
-  DevBuf<double> ypart;              // [grid][ncam*dc] per-CTA private results of the persistent operator kernel
+  DevBuf<double> xpad;               // operator input at the padded per-camera stride
+  DevBuf<uint16_t> cslot_widx;       // [nnormal_chunks][TILE] window-local camera index of the camera-sorted lanes
+  DevBuf<WinDesc> win_desc;          // [mv_nwindows]
+  DevBuf<uint32_t> range_win0;       // [mv_nranges + 1] first window of each range
+  DevBuf<uint32_t> win_cams;         // [mv_nrows] sorted camera lists of the windows
+  // deterministic flush: partial rows + per-camera row lists
+  DevBuf<uint32_t> cam_row_start;    // [ncam+1] CSR over cameras ...
+  DevBuf<uint32_t> cam_rows;         // ... of their rows in det_partial, ascending
+  DevBuf<double> det_partial;        // [mv_nrows][dc]
   DevBuf<double> slot_uv;            // [chunk][2][TILE]
   DevBuf<uint32_t> pt_slot0, pt_cnt; // per local landmark
   DevBuf<CamItem> items;
@@ -338,6 +363,7 @@ apex_status schur_operator(Ctx& c, const double* x, double* y, int check_done, b
 apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_done, bool xpad_ready = false);  // this rank's part
 apex_status launch_reduced_gradient(Ctx& c, double* b);
 apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol);
+apex_status schur_configure(Ctx& c);  // at upload: window width and CTAs per SM of the chunk kernel for the context's dc
 // explicit.cu
 apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol);
 apex_status dense_cholesky_bench(Ctx& c, uint32_t n, int reps, double* ms_out);

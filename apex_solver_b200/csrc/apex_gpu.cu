@@ -171,7 +171,8 @@ void apex_ctx_destroy(apex_ctx* ctx) {
                            &c.sj, &c.pinv, &c.vb, &c.vx, &c.vr, &c.vz, &c.vp, &c.vy, &c.step_cam, &c.step_pt, &c.red_scratch, &c.S, &c.E,
                            &c.dvec, &c.l2flush};
   for (auto* b : dbl) b->release();
-  c.giant_tiles.release(); c.ypart.release(); c.xpad.release(); c.chunk_desc.release(); c.cslot_meta.release(); c.cpt_meta.release(); c.cseg_cam.release(); c.cseg_begin.release();
+  c.giant_tiles.release(); c.xpad.release(); c.chunk_desc.release(); c.cslot_meta.release(); c.cpt_meta.release();
+  c.cslot_widx.release(); c.win_desc.release(); c.range_win0.release(); c.win_cams.release(); c.cam_row_start.release(); c.cam_rows.release(); c.det_partial.release();
   c.tiles.release(); c.slot_cam.release(); c.slot_lp.release(); c.pt_slot0.release(); c.pt_cnt.release(); c.items.release();
   c.cam_item_start.release(); c.cm_lp.release(); c.pose_fixed.release(); c.pt_fixed.release(); c.intr_fixed.release();
   c.state.release(); c.trace.release();
@@ -291,7 +292,7 @@ apex_status apex_get_linearization(apex_ctx* ctx, double* r, double* jc, double*
     if (o == UINT64_MAX) continue;
     const size_t ch = slot / TILE, lane = slot % TILE;
     if (r) { r[2 * o] = hR[(ch * 2 + 0) * TILE + lane]; r[2 * o + 1] = hR[(ch * 2 + 1) * TILE + lane]; }
-    if (jc) for (int k = 0; k < 2 * dc; ++k) jc[o * 2 * dc + k] = hJ[jplane_index(ch, np, k, lane)];
+    if (jc) for (int k = 0; k < 2 * dc; ++k) jc[o * 2 * dc + k] = hJ[jplane_index(ch, np, k, c.slot_pos[slot])];  // camera half: camera-sorted lane
     if (jp) for (int k = 0; k < 6; ++k) jp[o * 6 + k] = hJ[jplane_index(ch, np, 2 * dc + k, lane)];
   }
   return APEX_OK;

@@ -30,6 +30,7 @@ struct FormArgs {
   const uint16_t* slot_lp;
   const uint32_t* pt_slot0;
   const uint32_t* pt_cnt;
+  const uint2* cslot_meta;   // normal chunks: camera-sorted lane of each point-major lane (split slot order, apex_ctx.h)
   const double* J;
   const double* hinv;
   double* S;
@@ -49,8 +50,16 @@ __global__ void __launch_bounds__(TILE) schur_form_kernel(FormArgs a) {
     if (cam_i == PAD_CAM) continue;
     const uint32_t lp = td.pt0 + a.slot_lp[slot];
     const uint32_t s0 = a.pt_slot0[lp], cnt = a.pt_cnt[lp];
+    const bool split = td.nchunks == 1;  // camera half of a normal chunk sits at the observation's camera-sorted lane
     double jall[NP];
-    load_jacobian_planes<NP>(a.J, chunk, tid, jall);
+    {
+      const double2* Ji = reinterpret_cast<const double2*>(a.J) + chunk * (NP / 2) * TILE;
+      const int clane = split ? (int)((a.cslot_meta[slot].y >> 8) & 0xFFu) : tid;
+#pragma unroll
+      for (int m = 0; m < DC; ++m) { const double2 v = Ji[(size_t)m * TILE + clane]; jall[2 * m] = v.x; jall[2 * m + 1] = v.y; }
+#pragma unroll
+      for (int m = DC; m < DC + 3; ++m) { const double2 v = Ji[(size_t)m * TILE + tid]; jall[2 * m] = v.x; jall[2 * m + 1] = v.y; }
+    }
     const double* jc = jall;
     const double* jp = jall + 2 * DC;
     const size_t n = a.npl;
@@ -66,7 +75,9 @@ __global__ void __launch_bounds__(TILE) schur_form_kernel(FormArgs a) {
     for (uint32_t j = s0; j < s0 + cnt; ++j) {
       const uint32_t cam_j = a.slot_cam[j];
       if (cam_j > cam_i) continue;
-      const double2* Jj = reinterpret_cast<const double2*>(a.J) + (size_t)(j / TILE) * (NP / 2) * TILE + (j % TILE);
+      const double2* Jch = reinterpret_cast<const double2*>(a.J) + (size_t)(j / TILE) * (NP / 2) * TILE;
+      const double2* Jj = Jch + (j % TILE);
+      const double2* Jcj = Jch + (split ? ((a.cslot_meta[j].y >> 8) & 0xFFu) : (j % TILE));
       double pj[6];
 #pragma unroll
       for (int m = 0; m < 3; ++m) { const double2 v = Jj[(size_t)(DC + m) * TILE]; pj[2 * m] = v.x; pj[2 * m + 1] = v.y; }
@@ -77,7 +88,7 @@ __global__ void __launch_bounds__(TILE) schur_form_kernel(FormArgs a) {
         for (int cc = 0; cc < 2; ++cc) M[r][cc] = G[r][0] * pj[cc * 3] + G[r][1] * pj[cc * 3 + 1] + G[r][2] * pj[cc * 3 + 2];
       double cj[2 * DC];
 #pragma unroll
-      for (int m = 0; m < DC; ++m) { const double2 v = Jj[(size_t)m * TILE]; cj[2 * m] = v.x; cj[2 * m + 1] = v.y; }
+      for (int m = 0; m < DC; ++m) { const double2 v = Jcj[(size_t)m * TILE]; cj[2 * m] = v.x; cj[2 * m + 1] = v.y; }
       double* Srow = a.S + ((size_t)cam_i * DC) * a.ld + (size_t)cam_j * DC;
 #pragma unroll
       for (int p = 0; p < DC; ++p) {
@@ -652,7 +663,7 @@ apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol) {
   cudaEvent_t* evf = c.prof ? prof_pair(c.ev_form, c.ev_form_used++) : nullptr;
   if (evf) cudaEventRecord(evf[0], s);
   if (c.ntiles) {
-    FormArgs fa{c.tiles.p, c.slot_cam.p, c.slot_lp.p, c.pt_slot0.p, c.pt_cnt.p, c.J.p, c.hinv.p, S, ld, c.npl};
+    FormArgs fa{c.tiles.p, c.slot_cam.p, c.slot_lp.p, c.pt_slot0.p, c.pt_cnt.p, c.cslot_meta.p, c.J.p, c.hinv.p, S, ld, c.npl};
     switch (c.dc) {
       case 6: schur_form_kernel<6><<<c.ntiles, TILE, 0, s>>>(fa); break;
       case 9: schur_form_kernel<9><<<c.ntiles, TILE, 0, s>>>(fa); break;

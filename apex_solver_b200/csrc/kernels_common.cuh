@@ -65,6 +65,16 @@ __device__ __forceinline__ void store_jacobian_planes(double* J, size_t chunk, i
   for (int m = 0; m < NP / 2; ++m) p[(size_t)m * 256] = make_double2(j[2 * m], j[2 * m + 1]);
 }
 
+// split slot order: planes 0..2dc-1 (camera half) at lane `clane`, planes 2dc..2dc+5 (landmark half) at lane `plane`
+template <int DC>
+__device__ __forceinline__ void store_jacobian_split(double* J, size_t chunk, int clane, int plane, const double* j) {
+  double2* p = reinterpret_cast<double2*>(J) + chunk * (DC + 3) * 256;
+#pragma unroll
+  for (int m = 0; m < DC; ++m) p[(size_t)m * 256 + clane] = make_double2(j[2 * m], j[2 * m + 1]);
+#pragma unroll
+  for (int m = DC; m < DC + 3; ++m) p[(size_t)m * 256 + plane] = make_double2(j[2 * m], j[2 * m + 1]);
+}
+
 // fire-and-forget FP64 add into L2 (REDG.E.ADD.F64)
 __device__ __forceinline__ void red_add(double* p, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");

@@ -42,6 +42,7 @@ struct LinArgs {
   const double* slot_uv;
   const uint32_t* pt_slot0;
   const uint32_t* pt_cnt;
+  const uint2* cslot_meta;   // normal chunks: [15:8] of .y = camera-sorted lane of the observation at this point-major lane
   const double* pose;
   const double* intr;
   const double* pt;
@@ -112,7 +113,11 @@ __global__ void __launch_bounds__(TILE, 3) linearize_tile_kernel(LinArgs a) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) jp[k] = 0.0;
     }
-    store_jacobian_planes<NP>(a.J, chunk, tid, jall);
+    // split slot order (apex_ctx.h): the landmark half stays at this lane, the camera half goes to the observation's
+    // camera-sorted lane inside the chunk (padding lanes are the same set in both orders); a landmark with more than 256
+    // observations keeps both halves at its own lane
+    const int clane = (td.nchunks == 1 && cam != PAD_CAM) ? (int)((__ldg(&a.cslot_meta[slot].y) >> 8) & 0xFFu) : tid;
+    store_jacobian_split<DC>(a.J, chunk, clane, tid, jall);
     a.R[(chunk * 2 + 0) * TILE + tid] = r[0];
     a.R[(chunk * 2 + 1) * TILE + tid] = r[1];
     // landmark-side contributions: upper triangle of Jp^T Jp, then Jp^T r
@@ -404,7 +409,7 @@ __global__ void precond_invert_kernel(const double* hcc, const double* sj, doubl
 static LinArgs make_lin_args(Ctx& c) {
   LinArgs a;
   a.tiles = c.tiles.p; a.slot_cam = c.slot_cam.p; a.slot_lp = c.slot_lp.p; a.slot_uv = c.slot_uv.p;
-  a.pt_slot0 = c.pt_slot0.p; a.pt_cnt = c.pt_cnt.p;
+  a.pt_slot0 = c.pt_slot0.p; a.pt_cnt = c.pt_cnt.p; a.cslot_meta = c.cslot_meta.p;
   a.pose = c.pose.p; a.intr = c.intr.p; a.pt = c.pt.p;
   a.J = c.J.p; a.R = c.R.p; a.hpp = c.hpp.p; a.gp = c.gp.p; a.hinv = c.hinv.p;
   a.tile_partial = c.red_scratch.p;

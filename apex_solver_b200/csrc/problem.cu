@@ -61,69 +61,31 @@ struct HostLayout {
   ShardMap shard;
   uint32_t npl = 0;
   uint64_t nobs_local = 0;
-  uint32_t nnormal_chunks = 0, nchunks = 0, npairs = 0;
+  uint32_t nnormal_chunks = 0, nchunks = 0;
+  uint64_t nwseg_total = 0;   // warp-segments of all normal chunks (statistics)
   std::vector<TileDesc> tiles, giant_tiles;
   std::vector<uint32_t> pt_slot0, pt_cnt;
   StageBuf<uint32_t> slot_cam;
   StageBuf<uint16_t> slot_lp;
   StageBuf<double> slot_uv;
   HostVec<uint64_t> slot_obs;
+  HostVec<uint8_t> slot_pos;
   std::vector<ChunkDesc> chunk_desc;
   StageBuf<uint2> cslot_meta;
   std::vector<uint32_t> cpt_meta;
-  StageBuf<uint32_t> cseg_cam;
-  StageBuf<uint16_t> cseg_begin;
+  StageBuf<uint16_t> cslot_widx;
+  std::vector<WinDesc> win_desc;
+  std::vector<uint32_t> range_win0, win_cams, cam_row_start;
+  StageBuf<uint32_t> cam_rows;
   StageBuf<double> cm_uv;
   StageBuf<uint32_t> cm_lp;
-  void set_pinned(bool on) {
-    slot_cam.pinned = slot_lp.pinned = slot_uv.pinned = cslot_meta.pinned = cseg_cam.pinned = cseg_begin.pinned = cm_uv.pinned = cm_lp.pinned = on;
-  }
-  void reset() { tiles.clear(); giant_tiles.clear(); items.clear(); grp_win0.clear(); }  // what build_layout appends to
+  void set_pinned(bool on) { slot_cam.pinned = slot_lp.pinned = slot_uv.pinned = cslot_meta.pinned = cslot_widx.pinned = cam_rows.pinned = cm_uv.pinned = cm_lp.pinned = on; }
+  void reset() { tiles.clear(); giant_tiles.clear(); items.clear(); }  // what build_layout appends to
   std::vector<CamItem> items;
   std::vector<uint32_t> cam_item_start;
-  uint32_t mv_G = 0, mv_W = 0;
-  std::vector<uint32_t> grp_win0;
 };
 
-// Camera window of every group of G consecutive normal chunks (window kernel of the Schur operator): the run of W
-// consecutive cameras, modulo ncam, that holds the most observations of the group.
-static void build_windows(HostLayout& L, uint32_t ncam, uint32_t G, uint32_t W) {
-  L.mv_G = G; L.mv_W = W;
-  L.grp_win0.clear();
-  if (!G || !W || !L.nnormal_chunks) { L.mv_G = L.mv_W = 0; return; }
-  const uint32_t ngroups = (L.nnormal_chunks + G - 1) / G;
-  L.grp_win0.assign(ngroups, 0);
-  if (W >= ncam) return;  // every camera fits: window = [0, ncam)
-#pragma omp parallel
-  {
-    std::vector<int64_t> off;
-#pragma omp for schedule(dynamic, 16)
-    for (int64_t g = 0; g < (int64_t)ngroups; ++g) {
-      const size_t s0 = (size_t)g * G * TILE, s1 = std::min<size_t>((size_t)(g + 1) * G, L.nnormal_chunks) * TILE;
-      off.clear();
-      int64_t ref = -1;
-      const int64_t half = ncam / 2;
-      for (size_t s = s0; s < s1; ++s) {
-        const uint32_t cam = L.cslot_meta[s].x;
-        if (cam == PAD_CAM) continue;
-        if (ref < 0) ref = cam;
-        off.push_back((((int64_t)cam - ref + half) % ncam + ncam) % ncam - half);  // circular offset in [-ncam/2, ncam/2)
-      }
-      if (off.empty()) continue;
-      std::sort(off.begin(), off.end());
-      size_t best = 0, best_i = 0, j = 0;
-      for (size_t i = 0; i < off.size(); ++i) {
-        if (i && off[i] == off[i - 1]) continue;
-        if (j < i) j = i;
-        while (j < off.size() && off[j] < off[i] + (int64_t)W) ++j;
-        if (j - i > best) { best = j - i; best_i = i; }
-      }
-      L.grp_win0[g] = (uint32_t)(((ref + off[best_i]) % ncam + ncam) % ncam);
-    }
-  }
-}
-
-static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostLayout& L, int dc) {
+static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostLayout& L, uint32_t nctas, uint32_t W, bool want_det_lists) {
   const bool timing = getenv("APEX_LAYOUT_TIMING") != nullptr;
   auto tprev = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
@@ -233,45 +195,37 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
     }
   L.nchunks = chunk;
   const size_t nslots = (size_t)chunk * TILE;
-  const uint32_t nchunk_even = (L.nnormal_chunks + 1) & ~1u;
-  L.npairs = nchunk_even / 2;
 
   lap("tiles");
-  // ---- slot arrays + per-chunk camera-sorted segment structure (parallel over tiles) ----
+  // ---- slot arrays + the camera-sorted lane order of every normal chunk (parallel over tiles) ----
   // (uninitialised here; every chunk is filled with its padding defaults by the worker that builds it)
   L.slot_cam.resize(nslots);
   L.slot_lp.resize(nslots);
   L.slot_uv.resize(nslots * 2);
   L.slot_obs.resize(nslots);
-  L.chunk_desc.assign(nchunk_even, ChunkDesc{0, 0, 0, 0});
-  L.cslot_meta.resize((size_t)nchunk_even * TILE);
+  L.slot_pos.resize(nslots);
+  L.chunk_desc.assign(L.nnormal_chunks, ChunkDesc{0, 0, 0, 0});
+  L.cslot_meta.resize((size_t)L.nnormal_chunks * TILE);
   L.cpt_meta.assign(npl, 0);
-  L.cseg_cam.resize((size_t)nchunk_even * TILE);
-  L.cseg_begin.resize((size_t)nchunk_even * CSEG_LD);
   auto clear_chunk = [&](size_t ch) {
     std::fill_n(L.slot_cam.begin() + ch * TILE, TILE, PAD_CAM);
     std::fill_n(L.slot_lp.begin() + ch * TILE, TILE, (uint16_t)0);
     std::fill_n(L.slot_uv.begin() + ch * 2 * TILE, 2 * TILE, 0.0);
     std::fill_n(L.slot_obs.begin() + ch * TILE, TILE, UINT64_MAX);
+    for (int t = 0; t < TILE; ++t) L.slot_pos[ch * TILE + t] = (uint8_t)t;  // default: camera half at the slot's own lane
   };
-  auto clear_tables = [&](size_t ch) {
-    std::fill_n(L.cslot_meta.begin() + ch * TILE, TILE, make_uint2(PAD_CAM, 0));
-    std::fill_n(L.cseg_cam.begin() + ch * TILE, TILE, 0u);
-    std::fill_n(L.cseg_begin.begin() + ch * CSEG_LD, CSEG_LD, (uint16_t)0);
-  };
-  for (size_t ch = L.nnormal_chunks; ch < nchunk_even; ++ch) clear_tables(ch);  // the odd chunk of the last pair
   const int64_t ntiles = (int64_t)L.tiles.size();
   lap("slot array allocation");
 #pragma omp parallel
   {
-    std::vector<std::pair<uint32_t, uint32_t>> order;  // (camera, chunk-local slot)
+    std::vector<std::pair<uint32_t, uint32_t>> order;  // (camera, chunk-local point-major lane)
 #pragma omp for schedule(dynamic, 64)
     for (int64_t ti = 0; ti < ntiles; ++ti) {
       const TileDesc& t = L.tiles[ti];
       uint64_t q = tile_q0[ti];
       order.clear();
       for (uint32_t ch = t.chunk0; ch < t.chunk0 + t.nchunks; ++ch) clear_chunk(ch);
-      if (t.nchunks == 1) clear_tables(t.chunk0);
+      if (t.nchunks == 1) std::fill_n(L.cslot_meta.begin() + (size_t)t.chunk0 * TILE, TILE, make_uint2(PAD_CAM, 0));
       for (uint32_t i = 0; i < t.npt; ++i) {
         const uint32_t lp = t.pt0 + i;
         const uint32_t off = L.pt_slot0[lp] - t.chunk0 * TILE;
@@ -287,40 +241,120 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
           L.slot_uv[(ch * 2 + 1) * TILE + lane] = d->obs_uv[2 * o + 1];
           L.slot_obs[slot] = o;
           if (t.nchunks == 1) {
-            L.cslot_meta[slot].x = cam;
-            L.cslot_meta[slot].y = i;
+            L.cslot_meta[slot].y = i;  // [7:0] chunk-local landmark of point-major lane off + k
             order.push_back({cam, off + k});
           }
         }
       }
       if (t.nchunks != 1) continue;
+      // camera-sorted lanes (the (camera, lane) pairs are unique, so the order is fully determined); a run of one camera
+      // that crosses a warp boundary is marked on the first lane of the following warp(s) (continuation flags, apex_ctx.h)
       const uint32_t ch = t.chunk0;
+      const size_t base = (size_t)ch * TILE;
       std::sort(order.begin(), order.end());
-      uint32_t nseg = 0;
+      uint32_t nwseg = 0;
       for (size_t pos = 0; pos < order.size(); ++pos) {
-        if (pos == 0 || order[pos].first != order[pos - 1].first) {
-          L.cseg_cam[(size_t)ch * TILE + nseg] = order[pos].first;
-          L.cseg_begin[(size_t)ch * CSEG_LD + nseg] = (uint16_t)pos;
-          ++nseg;
-        }
-        L.cslot_meta[(size_t)ch * TILE + order[pos].second].y |= ((uint32_t)pos << 8) | ((nseg - 1) << 16);
+        if (pos % 32 == 0 || order[pos].first != order[pos - 1].first) ++nwseg;
+        const uint32_t ptl = order[pos].second;
+        L.cslot_meta[base + pos].x = order[pos].first;
+        L.cslot_meta[base + pos].y |= ptl << 16;
+        L.cslot_meta[base + ptl].y |= (uint32_t)pos << 8;
+        L.slot_pos[base + ptl] = (uint8_t)pos;
       }
-      L.cseg_begin[(size_t)ch * CSEG_LD + nseg] = (uint16_t)order.size();
-      L.chunk_desc[ch] = ChunkDesc{t.pt0, t.npt, nseg, 0};
+      auto is_cont = [&](size_t pos) { return pos >= 32 && pos < order.size() && order[pos].first == order[pos - 1].first; };
+      for (size_t pos = 32; pos < order.size(); pos += 32) {
+        if (!is_cont(pos)) continue;
+        uint32_t fl = CONT_BIT;
+        if (!(is_cont(pos - 32) && order[pos - 32].first == order[pos].first)) {
+          uint32_t len = 1;
+          while (is_cont(pos + 32 * len) && order[pos + 32 * len].first == order[pos].first) ++len;
+          fl |= CONT_FIRST_BIT | (len << CONT_LEN_SHIFT);
+        }
+        L.cslot_meta[base + pos].y |= fl;
+      }
+      L.chunk_desc[ch] = ChunkDesc{t.pt0, t.npt, nwseg, (uint32_t)order.size()};
     }
   }
+  L.nwseg_total = 0;
+  for (uint32_t ch = 0; ch < L.nnormal_chunks; ++ch) L.nwseg_total += L.chunk_desc[ch].nwseg;
+  lap("slots + camera-sorted lanes");
 
-  lap("slots + segments");
-  // ---- camera windows of the operator's chunk groups ----
+  // ---- ranges and windows of the chunk kernel (apex_ctx.h): range r = chunks [nn*r/P, nn*(r+1)/P); inside a range, greedy
+  // windows of consecutive chunks whose observations touch at most W distinct cameras ----
   {
-    const char* eg = getenv("APEX_MV_GROUP");
-    const char* ew = getenv("APEX_MV_WINDOW");
-    const uint32_t G = eg ? (uint32_t)std::max(0, atoi(eg)) : 8u;
-    // opt-in (APEX_MV_WINDOW = cameras per window): measured slower than the chunk kernel
-    const uint32_t W = ew ? std::min<uint32_t>(mv_window_cameras(dc, ncam), (uint32_t)std::max(0, atoi(ew))) : 0u;
-    build_windows(L, ncam, G, W);
+    const uint32_t nn = L.nnormal_chunks;
+    const uint32_t P = std::max<uint32_t>(1, std::min<uint32_t>(nn, nctas));
+    std::vector<std::vector<WinDesc>> rw(P);
+    std::vector<std::vector<uint32_t>> rc(P);
+    L.cslot_widx.resize((size_t)nn * TILE);
+#pragma omp parallel
+    {
+      std::vector<uint32_t> cur, ccams, merged;
+#pragma omp for schedule(dynamic, 4)
+      for (int64_t r = 0; r < (int64_t)P; ++r) {
+        const uint32_t c0 = (uint32_t)((uint64_t)nn * r / P), c1 = (uint32_t)((uint64_t)nn * (r + 1) / P);
+        auto close = [&](uint32_t cb, uint32_t ce) {
+          // window [cb, ce) with the sorted camera list `cur`: window-local index of every camera-sorted lane (merge walk)
+          rw[r].push_back(WinDesc{cb, ce, (uint32_t)rc[r].size(), (uint32_t)cur.size()});
+          rc[r].insert(rc[r].end(), cur.begin(), cur.end());
+          for (uint32_t ch = cb; ch < ce; ++ch) {
+            const size_t base = (size_t)ch * TILE;
+            const uint32_t n = L.chunk_desc[ch].nobs;
+            size_t j = 0;
+            for (uint32_t pos = 0; pos < n; ++pos) {
+              const uint32_t cam = L.cslot_meta[base + pos].x;
+              while (cur[j] < cam) ++j;
+              L.cslot_widx[base + pos] = (uint16_t)j;
+            }
+            for (uint32_t pos = n; pos < (uint32_t)TILE; ++pos) L.cslot_widx[base + pos] = 0;
+          }
+        };
+        cur.clear();
+        uint32_t wb = c0;
+        for (uint32_t ch = c0; ch < c1; ++ch) {
+          const size_t base = (size_t)ch * TILE;
+          const uint32_t n = L.chunk_desc[ch].nobs;
+          ccams.clear();
+          for (uint32_t pos = 0; pos < n; ++pos)
+            if (pos == 0 || L.cslot_meta[base + pos].x != L.cslot_meta[base + pos - 1].x) ccams.push_back(L.cslot_meta[base + pos].x);
+          merged.resize(cur.size() + ccams.size());
+          merged.resize(std::set_union(cur.begin(), cur.end(), ccams.begin(), ccams.end(), merged.begin()) - merged.begin());
+          if (merged.size() > W && ch > wb) {
+            close(wb, ch);
+            wb = ch;
+            cur = ccams;
+          } else cur.swap(merged);
+        }
+        if (c1 > wb) close(wb, c1);
+      }
+    }
+    L.range_win0.assign((size_t)P + 1, 0);
+    uint64_t nrows = 0;
+    for (uint32_t r = 0; r < P; ++r) L.range_win0[r + 1] = L.range_win0[r] + (uint32_t)rw[r].size();
+    L.win_desc.clear();
+    L.win_desc.reserve(L.range_win0[P]);
+    for (uint32_t r = 0; r < P; ++r) nrows += rc[r].size();
+    L.win_cams.clear();
+    L.win_cams.reserve(nrows);
+    for (uint32_t r = 0; r < P; ++r) {
+      const uint32_t off = (uint32_t)L.win_cams.size();
+      for (WinDesc w : rw[r]) { w.cam0 += off; L.win_desc.push_back(w); }
+      L.win_cams.insert(L.win_cams.end(), rc[r].begin(), rc[r].end());
+    }
+    if (nn == 0) { L.range_win0.assign(1, 0); }
+    // deterministic flush: per-camera lists of the rows (= positions in win_cams) that hold a partial result of the camera,
+    // ascending, i.e. in (range, window) order
+    L.cam_row_start.assign((size_t)ncam + 1, 0);
+    L.cam_rows.resize(0);
+    if (want_det_lists) {
+      for (uint32_t cam : L.win_cams) L.cam_row_start[cam + 1]++;
+      for (uint32_t k = 0; k < ncam; ++k) L.cam_row_start[k + 1] += L.cam_row_start[k];
+      L.cam_rows.resize(L.win_cams.size());
+      std::vector<uint32_t> cursor(L.cam_row_start.begin(), L.cam_row_start.end() - 1);
+      for (size_t row = 0; row < L.win_cams.size(); ++row) L.cam_rows[cursor[L.win_cams[row]]++] = (uint32_t)row;
+    }
   }
-
+  lap("ranges + windows");
   // ---- camera-major copy of the local observations + work items ----
   // Stable counting sort by camera of the point-major list, in parallel over contiguous pieces of that list.
   std::vector<uint32_t> cam_start((size_t)ncam + 1, 0);
@@ -370,45 +404,87 @@ apex_status layout_stats(const apex_problem_desc* d, int nranks, int rank, apex_
   const auto t0 = std::chrono::steady_clock::now();
   HostLayout L;
   const int K = model_intr_dim(d->camera_model);
-  build_layout(d, nranks, rank, L, 6 + ((d->opt_flags & APEX_OPT_INTRINSIC) ? K : 0));
+  const int dc = 6 + ((d->opt_flags & APEX_OPT_INTRINSIC) ? K : 0);
+  const uint32_t W = mv_window_cameras(dc);
+  build_layout(d, nranks, rank, L, MV_DEFAULT_CTAS, W, true);
   out->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   out->shard_block = SHARD_BLOCK; out->npts_local = L.npl; out->nobs_local = L.nobs_local;
   out->ntiles = (uint32_t)L.tiles.size(); out->nlong_tiles = (uint32_t)L.giant_tiles.size();
   out->nchunks = L.nchunks; out->nnormal_chunks = L.nnormal_chunks; out->ncam_items = (uint32_t)L.items.size();
-  uint64_t nseg = 0, maxseg = 0, covered = 0;
-  for (const ChunkDesc& cd : L.chunk_desc) { nseg += cd.nseg; maxseg = std::max<uint64_t>(maxseg, cd.nseg); }
+  uint64_t maxseg = 0, covered = 0;
+  for (const ChunkDesc& cd : L.chunk_desc) maxseg = std::max<uint64_t>(maxseg, cd.nwseg);
   for (uint64_t o : L.slot_obs) covered += o != UINT64_MAX;
-  out->nsegments = nseg; out->max_segments_per_chunk = (uint32_t)maxseg; out->slots_used = covered;
-  // structural self-check: every local observation sits in exactly one slot, camera-sorted positions are a
-  // permutation of the chunk's observations and every segment is a run of one camera
+  out->nsegments = L.nwseg_total; out->max_segments_per_chunk = (uint32_t)maxseg; out->slots_used = covered;
+  out->mv_ranges = (uint32_t)L.range_win0.size() - 1; out->mv_window = W; out->mv_nwindows = (uint32_t)L.win_desc.size();
+  out->mv_rows = L.win_cams.size();
+  // structural self-check: every local observation sits in exactly one slot; inside a normal chunk the camera-sorted lanes are
+  // a permutation of the point-major lanes, both maps are inverse to each other, cameras ascend along the sorted lanes, the
+  // continuation flags mark exactly the runs cut at warp boundaries; the windows tile the ranges, the ranges tile the normal
+  // chunks, a window's camera list is sorted, at most W long (or one chunk) and every lane's window index names its camera;
+  // the per-camera row lists cover every row once
   out->consistent = covered == L.nobs_local ? 1 : 0;
   for (const TileDesc& t : L.tiles) {
     if (t.nchunks != 1) continue;
     const size_t base = (size_t)t.chunk0 * TILE;
-    int seen[TILE] = {0};
+    const ChunkDesc& cd = L.chunk_desc[t.chunk0];
     uint32_t nobs_tile = 0;
     for (uint32_t i = 0; i < t.npt; ++i) nobs_tile += L.pt_cnt[t.pt0 + i];
-    const ChunkDesc& cd = L.chunk_desc[t.chunk0];
-    for (uint32_t s = 0; s < nobs_tile; ++s) {
+    if (cd.nobs != nobs_tile || cd.pt0 != t.pt0 || cd.npt != t.npt) { out->consistent = 0; break; }
+    uint32_t wseg = 0;
+    for (uint32_t s = 0; s < nobs_tile && out->consistent; ++s) {
       const uint2 m = L.cslot_meta[base + s];
-      const uint32_t pos = (m.y >> 8) & 0xFFu, seg = (m.y >> 16) & 0xFFu;
-      if (pos >= nobs_tile || seen[pos]++ || seg >= cd.nseg || L.cseg_cam[base + seg] != m.x) { out->consistent = 0; break; }
-      const uint32_t b = L.cseg_begin[(size_t)t.chunk0 * CSEG_LD + seg], e = L.cseg_begin[(size_t)t.chunk0 * CSEG_LD + seg + 1];
-      if (pos < b || pos >= e) { out->consistent = 0; break; }
+      const uint32_t pos = (m.y >> 8) & 0xFFu, ipos = (m.y >> 16) & 0xFFu;
+      if (pos >= nobs_tile || ipos >= nobs_tile || ((L.cslot_meta[base + pos].y >> 16) & 0xFFu) != s || L.cslot_meta[base + pos].x != L.slot_cam[base + s] ||
+          L.slot_pos[base + s] != pos || (m.y & 0xFFu) != L.slot_lp[base + s])
+        out->consistent = 0;
+      if (s > 0 && m.x < L.cslot_meta[base + s - 1].x) out->consistent = 0;
+      if (s % 32 == 0 || m.x != L.cslot_meta[base + s - 1].x) ++wseg;
+      const bool cont = s % 32 == 0 && s > 0 && m.x == L.cslot_meta[base + s - 1].x;
+      if (cont != ((m.y & CONT_BIT) != 0)) out->consistent = 0;
+      if (cont) {
+        const bool first = !((L.cslot_meta[base + s - 32].y & CONT_BIT) && L.cslot_meta[base + s - 32].x == m.x);
+        if (first != ((m.y & CONT_FIRST_BIT) != 0)) out->consistent = 0;
+        if (first) {
+          uint32_t len = 1;
+          while (s + 32 * len < nobs_tile && (L.cslot_meta[base + s + 32 * len].y & CONT_BIT) && L.cslot_meta[base + s + 32 * len].x == m.x) ++len;
+          if (((m.y >> CONT_LEN_SHIFT) & 7u) != len) out->consistent = 0;
+        }
+      } else if (m.y >> 24) out->consistent = 0;
     }
+    if (wseg != cd.nwseg) out->consistent = 0;
+    for (uint32_t s = nobs_tile; s < (uint32_t)TILE; ++s)
+      if (L.cslot_meta[base + s].x != PAD_CAM) out->consistent = 0;
+    if (!out->consistent) break;
   }
-  out->mv_group = L.mv_G; out->mv_window = L.mv_W; out->mv_ngroups = (uint32_t)L.grp_win0.size(); out->reserved2 = 0;
-  uint64_t inwin = 0;
-  if (L.mv_W)
-    for (size_t s = 0; s < (size_t)L.nnormal_chunks * TILE; ++s) {
-      const uint32_t cam = L.cslot_meta[s].x;
-      if (cam == PAD_CAM) continue;
-      const uint32_t w0 = L.grp_win0[s / ((size_t)L.mv_G * TILE)];
-      if (w0 >= d->ncam) { out->consistent = 0; break; }
-      const uint32_t l = cam >= w0 ? cam - w0 : cam + d->ncam - w0;
-      inwin += l < L.mv_W;
+  {
+    const uint32_t nn = L.nnormal_chunks, P = (uint32_t)L.range_win0.size() - 1;
+    uint32_t next_chunk = 0, next_row = 0;
+    for (uint32_t r = 0; r < P && out->consistent; ++r) {
+      if (nn && next_chunk != (uint32_t)((uint64_t)nn * r / P)) out->consistent = 0;
+      for (uint32_t w = L.range_win0[r]; w < L.range_win0[r + 1] && out->consistent; ++w) {
+        const WinDesc& wd = L.win_desc[w];
+        if (wd.chunk_begin != next_chunk || wd.chunk_end <= wd.chunk_begin || wd.cam0 != next_row || wd.ncams == 0) { out->consistent = 0; break; }
+        if (wd.ncams > W && wd.chunk_end - wd.chunk_begin != 1) out->consistent = 0;
+        for (uint32_t i = 1; i < wd.ncams; ++i) if (L.win_cams[wd.cam0 + i] <= L.win_cams[wd.cam0 + i - 1]) out->consistent = 0;
+        for (uint32_t ch = wd.chunk_begin; ch < wd.chunk_end && out->consistent; ++ch)
+          for (uint32_t s = 0; s < L.chunk_desc[ch].nobs; ++s) {
+            const uint32_t wi = L.cslot_widx[(size_t)ch * TILE + s];
+            if (wi >= wd.ncams || L.win_cams[wd.cam0 + wi] != L.cslot_meta[(size_t)ch * TILE + s].x) { out->consistent = 0; break; }
+          }
+        next_chunk = wd.chunk_end; next_row = wd.cam0 + wd.ncams;
+      }
     }
-  out->nobs_in_window = inwin;
+    if (next_chunk != nn || next_row != L.win_cams.size()) out->consistent = 0;
+  }
+  if (L.cam_row_start[d->ncam] != L.win_cams.size() || L.cam_rows.size() != L.win_cams.size()) out->consistent = 0;
+  else {
+    std::vector<uint8_t> seen(L.win_cams.size(), 0);
+    for (uint32_t k = 0; k < d->ncam && out->consistent; ++k)
+      for (uint32_t e = L.cam_row_start[k]; e < L.cam_row_start[k + 1]; ++e) {
+        const uint32_t row = L.cam_rows[e];
+        if (row >= L.win_cams.size() || seen[row]++ || L.win_cams[row] != k || (e > L.cam_row_start[k] && L.cam_rows[e - 1] >= row)) { out->consistent = 0; break; }
+      }
+  }
   return APEX_OK;
 }
 
@@ -462,13 +538,23 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   }
   HostLayout& L = *static_cast<HostLayout*>(c.staging.get());
   L.reset();
-  build_layout(d, c.nranks, c.rank, L, c.dc);
-  c.mv_G = L.mv_G; c.mv_W = L.mv_W; c.mv_ngroups = (uint32_t)L.grp_win0.size();
+  APEX_TRY(schur_configure(c));   // window width, CTAs per SM of the chunk kernel -> number of ranges
+  build_layout(d, c.nranks, c.rank, L, c.mv_ctas_per_sm * (uint32_t)c.num_sms, c.mv_window, true);
   c.shard = L.shard; c.npl = L.npl; c.nobs_local = L.nobs_local;
-  c.nnormal_chunks = L.nnormal_chunks; c.nchunks = L.nchunks; c.npairs = L.npairs;
+  c.nnormal_chunks = L.nnormal_chunks; c.nchunks = L.nchunks;
+  c.mv_nranges = (uint32_t)L.range_win0.size() - 1; c.mv_nwindows = (uint32_t)L.win_desc.size(); c.mv_nrows = L.win_cams.size();
+  {
+    // Deterministic flush (per-window partial rows + a fixed-order second pass) unless its extra traffic (rows written and
+    // read once per operator application) is more than a tenth of what the operator streams anyway, i.e. unless the
+    // windows are short (a landmark order without camera locality); APEX_DETERMINISTIC=0|1 overrides.
+    const double extra = 2.0 * (double)c.mv_nrows * c.dc * 8.0, stream = (double)c.nobs_local * (8.0 * c.np + 8.0);
+    c.mv_det = extra <= 0.1 * stream;
+    if (const char* e = getenv("APEX_DETERMINISTIC")) c.mv_det = atoi(e) != 0;
+  }
   c.ntiles = (uint32_t)L.tiles.size(); c.ngiant = (uint32_t)L.giant_tiles.size(); c.nitems = (uint32_t)L.items.size();
   c.nslots = (size_t)L.nchunks * TILE;
   c.slot_obs.swap(L.slot_obs);
+  c.slot_pos.swap(L.slot_pos);
   c.h_pt_cnt = L.pt_cnt;
   lap("build_layout");
 
@@ -492,9 +578,15 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   APEX_CUDA_TRY(c, upload_vec(c.chunk_desc, L.chunk_desc, s));
   APEX_CUDA_TRY(c, upload_vec(c.cslot_meta, L.cslot_meta, s));
   APEX_CUDA_TRY(c, upload_vec(c.cpt_meta, L.cpt_meta, s));
-  APEX_CUDA_TRY(c, upload_vec(c.cseg_cam, L.cseg_cam, s));
-  APEX_CUDA_TRY(c, upload_vec(c.cseg_begin, L.cseg_begin, s));
-  APEX_CUDA_TRY(c, upload_vec(c.grp_win0, L.grp_win0, s));
+  APEX_CUDA_TRY(c, upload_vec(c.cslot_widx, L.cslot_widx, s));
+  APEX_CUDA_TRY(c, upload_vec(c.win_desc, L.win_desc, s));
+  APEX_CUDA_TRY(c, upload_vec(c.range_win0, L.range_win0, s));
+  APEX_CUDA_TRY(c, upload_vec(c.win_cams, L.win_cams, s));
+  if (c.mv_det) {  // only the deterministic flush reads the per-camera row lists
+    APEX_CUDA_TRY(c, upload_vec(c.cam_row_start, L.cam_row_start, s));
+    APEX_CUDA_TRY(c, upload_vec(c.cam_rows, L.cam_rows, s));
+    APEX_CUDA_TRY(c, c.det_partial.alloc((size_t)std::max<uint64_t>(c.mv_nrows, 1) * c.dc));
+  }
   APEX_CUDA_TRY(c, upload_vec(c.items, L.items, s));
   APEX_CUDA_TRY(c, upload_vec(c.cam_item_start, L.cam_item_start, s));
   APEX_CUDA_TRY(c, upload_vec(c.cm_uv, L.cm_uv, s));
@@ -526,7 +618,6 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   APEX_CUDA_TRY(c, c.vz.alloc(ncd));
   APEX_CUDA_TRY(c, c.vp.alloc(ncd));
   APEX_CUDA_TRY(c, c.vy.alloc(ncd));
-  APEX_CUDA_TRY(c, c.ypart.alloc((size_t)c.num_sms * ncd));
   APEX_CUDA_TRY(c, c.xpad.alloc((size_t)c.ncam * xpad_stride(c.dc)));
   APEX_CUDA_TRY(c, c.step_cam.alloc(ncd));
   APEX_CUDA_TRY(c, c.step_pt.alloc((size_t)c.npl * 3));

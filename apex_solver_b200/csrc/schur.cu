@@ -2,17 +2,16 @@
 // device-resident control.
 //
 // sm_100a equivalents of IterativeSchurSolver (src/linalg/sparse/implicit_schur.rs):
-//   apply_schur_operator_fast :163-251  -> schur_matvec_pingpong_kernel + schur_finalize_kernel (schur_tile_kernel<DC, MODE_MATVEC>
-//                                          for landmarks with more than 256 observations)
-//   reduced gradient          :863-880  -> schur_tile_kernel<DC, MODE_RHS>
-//   back-substitution         :923-932  -> schur_tile_kernel<DC, MODE_BACKSUB>
-//   apply_preconditioner      :409-443, solve_pcg_block :577-679 -> pcg_init_kernel / pcg_step_kernel
+//   apply_schur_operator_fast :163-251  -> schur_chunk_kernel<DC, MODE_MATVEC> (schur_tile_kernel for landmarks with more
+//                                          than 256 observations)
+//   reduced gradient          :863-880  -> schur_chunk_kernel<DC, MODE_RHS>
+//   back-substitution         :923-932  -> schur_chunk_kernel<DC, MODE_BACKSUB>
+//   apply_preconditioner      :409-443, solve_pcg_block :577-679 -> pcg_init / pcg_dir_hcc / pcg_pap / pcg_update kernels
 //
-// The operator is applied in ONE pass over the Jacobian planes: a CTA owns a tile of whole landmarks,
-// so  t_p = sum_o Jp_o^T (Jc_o x_c(o))  is a segmented sum in shared memory, w_p = Hpp_p^-1 t_p stays in
-// shared memory, and each observation then sends  -Jc_o^T (Jp_o w_p)  to y_c with FP64 reductions into L2
-// (red.global.add.f64). H_cp = Jc^T Jp is never materialised: 2*(dc+3) doubles per observation are read
-// instead of 3*dc.
+// The operator is applied in ONE pass over the Jacobian planes: a CTA owns a chunk of whole landmarks,
+// so  t_p = sum_o Jp_o^T (Jc_o x_c(o))  is a segmented sum inside the CTA, w_p = Hpp_p^-1 t_p stays in
+// shared memory, and each observation then sends  -Jc_o^T (Jp_o w_p)  to y_c. H_cp = Jc^T Jp is never materialised:
+// 2*(dc+3) doubles per observation are read instead of 3*dc.
 #include <cooperative_groups.h>
 
 #include <algorithm>
@@ -40,18 +39,21 @@ struct SchurArgs {
   double* step_pt;
   uint32_t npl;
   int check_done;
-  int debug;       // development probes: 1 = suppress the reductions into y, 2 = strided tile order
+  int debug;       // development probe: 1 = suppress the reductions into y
   uint32_t ntiles;
   const DevState* st;
-  // per-chunk camera segments (SEG variant: one reduction per (segment, dof) instead of per (observation, dof))
   const ChunkDesc* chunk_desc;
   const uint2* cslot_meta;
-  const uint32_t* cseg_cam;
-  const uint16_t* cseg_begin;
   const uint32_t* cpt_meta;
-  const double* xpad;   // x at an even per-camera stride (chunk kernel)
+  const double* xpad;   // x at the padded per-camera stride (chunk kernel)
+  // ranges / windows of the chunk kernel (apex_ctx.h)
+  const uint16_t* cslot_widx;
+  const WinDesc* win_desc;
+  const uint32_t* range_win0;
+  const uint32_t* win_cams;
+  uint32_t window;                 // cameras per window the shared-memory rows were sized for
+  double* partial;                 // deterministic flush: [rows][DC], row = position in win_cams
 };
-
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -131,84 +133,18 @@ __device__ __forceinline__ void landmark_middle(const SchurArgs& a, uint32_t lp,
   }
 }
 
-template <int DC, int MODE, bool SEG = false>
+// Tile kernel: the three modes for a landmark with MORE than 256 observations (its observations fill several chunks that
+// hold nothing else; in these chunks the camera half of the Jacobian is stored at the observation's own lane, not in
+// camera-sorted order). Accumulate per thread -> fixed-order block reduction -> re-read J for the camera side.
+template <int DC, int MODE>
 __global__ void __launch_bounds__(TILE, 3) schur_tile_kernel(SchurArgs a) {
   constexpr int NP = 2 * (DC + 3);
   if (a.check_done && a.st->pcg_done) return;
   __shared__ double sh[3][TILE];
   __shared__ double shw[3][TILE];
-  __shared__ double cs[SEG ? DC * (TILE + 1) : 1];
-  const uint32_t tile_idx = (a.debug == 2 || SEG) && (a.ntiles % 4099u != 0) ? (uint32_t)(((uint64_t)blockIdx.x * 4099u) % a.ntiles) : blockIdx.x;
-  const TileDesc td = a.tiles[tile_idx];
+  const TileDesc td = a.tiles[blockIdx.x];
   const int tid = threadIdx.x;
-  if (td.nchunks == 1) {
-    const size_t chunk = td.chunk0;
-    const size_t slot = chunk * TILE + tid;
-    const uint32_t cam = a.slot_cam[slot];
-    double jall[NP];
-    const double* jc = jall;
-    const double* jp = jall + 2 * DC;
-    if (cam != PAD_CAM) load_jacobian_planes<NP>(a.J, chunk, tid, jall);
-    if (MODE != MODE_RHS) {
-      double u[3] = {0.0, 0.0, 0.0};
-      if (cam != PAD_CAM) obs_forward<DC>(jc, jp, a.x + (size_t)cam * DC, u);
-      sh[0][tid] = u[0]; sh[1][tid] = u[1]; sh[2][tid] = u[2];
-      __syncthreads();
-    }
-    if ((uint32_t)tid < td.npt) {
-      const uint32_t lp = td.pt0 + tid;
-      double t[3] = {0.0, 0.0, 0.0}, w[3];
-      if (MODE != MODE_RHS) {
-        const uint32_t off = a.pt_slot0[lp] - td.chunk0 * TILE, cnt = a.pt_cnt[lp];
-        for (uint32_t q = 0; q < cnt; ++q) { t[0] += sh[0][off + q]; t[1] += sh[1][off + q]; t[2] += sh[2][off + q]; }
-      }
-      landmark_middle<MODE>(a, lp, t, w);
-      if (MODE != MODE_BACKSUB) { shw[0][tid] = w[0]; shw[1][tid] = w[1]; shw[2][tid] = w[2]; }
-    }
-    if (MODE == MODE_BACKSUB) return;
-    __syncthreads();
-    if (!SEG) {
-      if (cam != PAD_CAM) {
-        const uint32_t li = a.slot_lp[slot];
-        const double w[3] = {shw[0][li], shw[1][li], shw[2][li]};
-        obs_backward<DC>(jc, jp, w, a.y + (size_t)cam * DC, a.debug);
-      }
-    } else {
-      // combine the scatter per camera inside the tile first: contributions at camera-sorted positions, then one
-      // reduction per (segment, dof)
-      constexpr int LD = TILE + 1;
-      if (cam != PAD_CAM) {
-        const uint32_t li = a.slot_lp[slot];
-        const uint32_t pos = (a.cslot_meta[slot].y >> 8) & 0xFFu;
-        const double w0 = shw[0][li], w1 = shw[1][li], w2 = shw[2][li];
-        const double b0 = fma(jp[0], w0, fma(jp[1], w1, jp[2] * w2));
-        const double b1 = fma(jp[3], w0, fma(jp[4], w1, jp[5] * w2));
-#pragma unroll
-        for (int k = 0; k < DC; ++k) cs[k * LD + pos] = -fma(jc[k], b0, jc[DC + k] * b1);
-      }
-      __syncthreads();
-      constexpr int KG = 3, NG = (DC + KG - 1) / KG;
-      const uint32_t nseg = a.chunk_desc[chunk].nseg;
-      const uint32_t* segc = a.cseg_cam + chunk * TILE;
-      const uint16_t* segb = a.cseg_begin + chunk * CSEG_LD;
-      for (uint32_t idx = tid; idx < nseg * NG; idx += TILE) {
-        const uint32_t sgi = idx / NG, kg = (idx - sgi * NG) * KG;
-        const uint32_t b = segb[sgi], e = segb[sgi + 1];
-        double* yr = a.y + (size_t)segc[sgi] * DC + kg;
-        const double* c0 = cs + kg * LD;
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-        for (uint32_t q = b; q < e; ++q) {
-          v0 += c0[q];
-          if (kg + 1 < DC) v1 += c0[LD + q];
-          if (kg + 2 < DC) v2 += c0[2 * LD + q];
-        }
-        if (a.debug == 1 && v0 != 1.2345e300) continue;  // development probe: scatter suppressed
-        red_add(yr, v0);
-        if (kg + 1 < DC) red_add(yr + 1, v1);
-        if (kg + 2 < DC) red_add(yr + 2, v2);
-      }
-    }
-  } else {
+  {
     // one landmark spread over several chunks: accumulate per thread, reduce in fixed order, re-read J
     double u[3] = {0.0, 0.0, 0.0};
     if (MODE != MODE_RHS) {
@@ -245,287 +181,6 @@ __global__ void __launch_bounds__(TILE, 3) schur_tile_kernel(SchurArgs a) {
   }
 }
 
-constexpr int MV_SMEM_MAX = 232448 - 512;    // 227 KB per CTA minus the static shared memory of the kernel
-
-// ----------------------------------------------------------------------------------------------------
-// Persistent Schur-operator kernel (the PCG hot loop), one 512-thread CTA per SM. The Jacobian planes of the NEXT
-// chunk are prefetched into registers in 4 stages interleaved with the compute phases; the camera-side scatter
-// y_c -= Jc^T (Jp w) is combined per camera inside the CTA (camera-sorted segment structure built at upload, one
-// thread per (segment, dof), fixed order) and added to a CTA-PRIVATE copy of y in shared memory (PRIVATE: ncam*dc
-// doubles fit next to the staging buffers; no global atomics, bitwise reproducible) or, when y does not fit,
-// sent to global memory with one red.global.add.f64 per (segment, dof). The private copies are summed in CTA
-// order by schur_finalize_kernel, which also adds (H_cc + lambda I) x.
-// The 512-thread CTA is split into two 256-thread groups
-// that each walk their own chunks (256 slots = whole landmarks) with named barriers (bar.sync 1/2), half a
-// period out of phase, so one group's barrier / latency stalls are filled by the other group's work. Both groups
-// add into the same CTA-private y; their phase 4 is serialised by a two-barrier turnstile (bar.arrive/bar.sync
-// 3 and 4) in the fixed order A0 B0 A1 B1 ..., which keeps the result bitwise reproducible. x is staged per
-// camera SEGMENT (one coalesced 80-byte read per distinct camera instead of one scattered read per
-// observation); segment tables are double-buffered and fetched one chunk ahead with cp.async.
-// ----------------------------------------------------------------------------------------------------
-struct PpArgs {
-  const ChunkDesc* chunk_desc;
-  const uint2* cslot_meta;
-  const uint32_t* cpt_meta;
-  const uint32_t* cseg_cam;
-  const uint16_t* cseg_begin;
-  const double* J;
-  const double* hinv;
-  const double* gp;
-  const double* xpad;
-  double* y;
-  double* ypart;
-  uint32_t n, npl, npairs, nnormal_chunks;
-  int check_done;
-  const DevState* st;
-};
-
-constexpr int PP_PTS = MAX_TILE_PTS;  // landmarks per chunk
-constexpr int PP_CS_LD = TILE + 1;
-
-__device__ __forceinline__ void pp_group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(TILE) : "memory"); }
-__device__ __forceinline__ void pp_turn_wait(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(2 * TILE) : "memory"); }
-__device__ __forceinline__ void pp_turn_signal(int id) {
-  __threadfence_block();
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(2 * TILE) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-template <int DC>
-struct PpRegs {
-  double j[2 * (DC + 3)];
-  uint32_t cam, sp;
-  uint32_t pt0, npt, nseg;
-};
-
-template <int DC> __host__ __device__ constexpr int pp_region_doubles() { return (DC * PP_CS_LD > TILE * ((DC + 1) & ~1)) ? DC * PP_CS_LD : TILE * ((DC + 1) & ~1); }
-template <int DC> __host__ __device__ constexpr int pp_group_doubles() {
-  // cs/xs region | su[3][256] | sw[3][128] | shinv[6][128] | sptm u32[128] | seg_cam u32[2][256] | seg_begin u16[2][258]
-  return (pp_region_doubles<DC>() + 3 * TILE + 3 * PP_PTS + 6 * PP_PTS + PP_PTS / 2 + TILE + (2 * CSEG_LD * 2 + 7) / 8 + 1) & ~1;  // even: 16-byte aligned groups
-}
-
-template <int DC, int STAGE>
-__device__ __forceinline__ void pp_prefetch_stage(const PpArgs& a, uint32_t chunk, bool valid, int gt, PpRegs<DC>& r) {
-  constexpr int NP = 2 * (DC + 3), NPAIR = NP / 2;
-  constexpr int M0 = (NPAIR * STAGE) / 4, M1 = (NPAIR * (STAGE + 1)) / 4;
-  if (STAGE == 0) { r.cam = PAD_CAM; r.sp = 0; r.pt0 = 0; r.npt = 0; r.nseg = 0; }
-  if (!valid) return;
-  const double2* p = reinterpret_cast<const double2*>(a.J) + (size_t)chunk * NPAIR * TILE + gt;
-#pragma unroll
-  for (int m = M0; m < M1; ++m) {
-    const double2 v = ld_stream2(p + (size_t)m * TILE);
-    r.j[2 * m] = v.x;
-    r.j[2 * m + 1] = v.y;
-  }
-  if (STAGE == 3) {
-    const uint4 d = __ldg(reinterpret_cast<const uint4*>(a.chunk_desc + chunk));
-    const uint2 m = __ldg(a.cslot_meta + (size_t)chunk * TILE + gt);
-    r.cam = m.x; r.sp = m.y;
-    r.pt0 = d.x; r.npt = d.y; r.nseg = d.z;
-  }
-}
-
-template <int DC>
-__device__ __forceinline__ void pp_fetch_tables(const PpArgs& a, uint32_t chunk, bool valid, int gt, uint32_t* sseg_cam, uint16_t* sseg_begin) {
-  if (!valid) return;
-  cp_async4(sseg_cam + gt, a.cseg_cam + (size_t)chunk * TILE + gt);
-  if (gt < CSEG_LD / 2) cp_async4(reinterpret_cast<uint32_t*>(sseg_begin) + gt, reinterpret_cast<const uint32_t*>(a.cseg_begin + (size_t)chunk * CSEG_LD) + gt);
-}
-
-template <int DC, bool PRIVATE, int MODE = MODE_MATVEC>
-__global__ void __launch_bounds__(2 * TILE, 1) schur_matvec_pingpong_kernel(PpArgs a) {
-  constexpr int XS = (DC + 1) & ~1;
-  extern __shared__ __align__(16) double pp_smem[];
-  if (a.check_done && a.st->pcg_done) return;
-  const int tid = threadIdx.x, g = tid >> 8, gt = tid & (TILE - 1);
-  const uint32_t ny = PRIVATE ? ((a.n + 1) & ~1u) : 0;
-  double* y_priv = pp_smem;
-  double* base = pp_smem + ny + (size_t)g * pp_group_doubles<DC>();
-  double* cs = base;                       // [DC][257]; aliased by the per-segment x staging xs[nseg][XS]
-  double* su = cs + pp_region_doubles<DC>();
-  double* sw = su + 3 * TILE;
-  double* shinv = sw + 3 * PP_PTS;
-  uint32_t* sptm = reinterpret_cast<uint32_t*>(shinv + 6 * PP_PTS);
-  uint32_t* sseg_cam = sptm + PP_PTS;                                    // [2][256]
-  uint16_t* sseg_begin = reinterpret_cast<uint16_t*>(sseg_cam + 2 * TILE);  // [2][CSEG_LD]
-  if (PRIVATE)
-    for (uint32_t i = tid; i < a.n; i += 2 * TILE) y_priv[i] = 0.0;
-
-  // this CTA's chunk pairs: pair = blockIdx.x + it*gridDim.x ; group g takes chunk 2*pair + g
-  const uint32_t niter = (a.npairs - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  PpRegs<DC> ra, rb;
-  {
-    const uint32_t chunk = 2 * blockIdx.x + g;
-    const bool valid = chunk < a.nnormal_chunks;
-    pp_prefetch_stage<DC, 0>(a, chunk, valid, gt, ra);
-    pp_prefetch_stage<DC, 1>(a, chunk, valid, gt, ra);
-    pp_prefetch_stage<DC, 2>(a, chunk, valid, gt, ra);
-    pp_prefetch_stage<DC, 3>(a, chunk, valid, gt, ra);
-    pp_fetch_tables<DC>(a, chunk, valid, gt, sseg_cam, sseg_begin);
-    cp_async_commit();
-    cp_async_wait0();
-  }
-  __syncthreads();
-
-#define PP_BODY(R, RN)                                                                                                   \
-  {                                                                                                                      \
-    const uint32_t pair_next = blockIdx.x + (it + 1) * gridDim.x;                                                        \
-    const uint32_t chunk_next = 2 * pair_next + g;                                                                       \
-    const bool valid_next = (it + 1 < niter) && chunk_next < a.nnormal_chunks;                                           \
-    const int buf = it & 1;                                                                                              \
-    const uint32_t* segc = sseg_cam + buf * TILE;                                                                        \
-    const uint16_t* segb = sseg_begin + buf * CSEG_LD;                                                                   \
-    /* stage this chunk's landmark inverses + the next chunk's segment tables */                                        \
-    if ((uint32_t)gt < R.npt) {                                                                                          \
-      const uint32_t lp = R.pt0 + gt;                                                                                    \
-      _Pragma("unroll") for (int k = 0; k < 6; ++k) cp_async8(shinv + k * PP_PTS + gt, a.hinv + (size_t)k * a.npl + lp); \
-      cp_async4(sptm + gt, a.cpt_meta + lp);                                                                             \
-    }                                                                                                                    \
-    pp_fetch_tables<DC>(a, chunk_next, valid_next, gt, sseg_cam + (buf ^ 1) * TILE, sseg_begin + (buf ^ 1) * CSEG_LD);   \
-    cp_async_commit();                                                                                                   \
-    /* S0: x of every distinct camera of the chunk -> shared memory (coalesced per segment) */                          \
-    if (MODE == MODE_MATVEC) {                                                                                           \
-      double2* xs2 = reinterpret_cast<double2*>(cs);                                                                     \
-      const uint32_t nld = R.nseg * (XS / 2);                                                                            \
-      for (uint32_t idx = gt; idx < nld; idx += TILE) {                                                                  \
-        const uint32_t sgi = idx / (XS / 2), m = idx - sgi * (XS / 2);                                                   \
-        xs2[idx] = __ldg(reinterpret_cast<const double2*>(a.xpad + (size_t)segc[sgi] * xpad_stride(DC)) + m);            \
-      }                                                                                                                  \
-    }                                                                                                                    \
-    pp_prefetch_stage<DC, 0>(a, chunk_next, valid_next, gt, RN);                                                         \
-    pp_group_bar(g);                                                                                                     \
-    /* P1: u_o = Jp^T (Jc x_c) */                                                                                        \
-    if (MODE == MODE_MATVEC) {                                                                                           \
-      double u0 = 0.0, u1 = 0.0, u2 = 0.0;                                                                               \
-      if (R.cam != PAD_CAM) {                                                                                            \
-        const double2* xs2 = reinterpret_cast<const double2*>(cs) + (size_t)((R.sp >> 16) & 0xFFu) * (XS / 2);           \
-        double xv[XS];                                                                                                   \
-        _Pragma("unroll") for (int m = 0; m < XS / 2; ++m) { const double2 v = xs2[m]; xv[2 * m] = v.x; xv[2 * m + 1] = v.y; } \
-        double a0 = 0.0, a1 = 0.0;                                                                                       \
-        _Pragma("unroll") for (int k = 0; k < DC; ++k) { a0 = fma(R.j[k], xv[k], a0); a1 = fma(R.j[DC + k], xv[k], a1); } \
-        const double* jp = R.j + 2 * DC;                                                                                 \
-        u0 = fma(jp[0], a0, jp[3] * a1); u1 = fma(jp[1], a0, jp[4] * a1); u2 = fma(jp[2], a0, jp[5] * a1);               \
-      }                                                                                                                  \
-      su[gt] = u0; su[TILE + gt] = u1; su[2 * TILE + gt] = u2;                                                           \
-    }                                                                                                                    \
-    pp_prefetch_stage<DC, 1>(a, chunk_next, valid_next, gt, RN);                                                         \
-    cp_async_wait0();                                                                                                    \
-    pp_group_bar(g);                                                                                                     \
-    /* P2: t_p = sum over the landmark's observations, w_p = Hpp^-1 t_p */                                               \
-    if ((uint32_t)gt < R.npt) {                                                                                          \
-      const uint32_t mm = sptm[gt], off = mm & 0xFFFFu, cnt = (MODE == MODE_RHS) ? 0u : (mm >> 16);                      \
-      double t0 = 0.0, t1 = 0.0, t2 = 0.0, e0 = 0.0, e1 = 0.0, e2 = 0.0;                                                 \
-      uint32_t q = 0;                                                                                                    \
-      for (; q + 1 < cnt; q += 2) {                                                                                      \
-        t0 += su[off + q]; t1 += su[TILE + off + q]; t2 += su[2 * TILE + off + q];                                       \
-        e0 += su[off + q + 1]; e1 += su[TILE + off + q + 1]; e2 += su[2 * TILE + off + q + 1];                           \
-      }                                                                                                                  \
-      if (q < cnt) { t0 += su[off + q]; t1 += su[TILE + off + q]; t2 += su[2 * TILE + off + q]; }                        \
-      t0 += e0; t1 += e1; t2 += e2;                                                                                      \
-      if (MODE == MODE_RHS) {                                                                                            \
-        const size_t lp = R.pt0 + gt;                                                                                    \
-        t0 = -a.gp[lp]; t1 = -a.gp[(size_t)a.npl + lp]; t2 = -a.gp[2 * (size_t)a.npl + lp];                              \
-      }                                                                                                                  \
-      const double h00 = shinv[gt], h01 = shinv[PP_PTS + gt], h02 = shinv[2 * PP_PTS + gt];                              \
-      const double h11 = shinv[3 * PP_PTS + gt], h12 = shinv[4 * PP_PTS + gt], h22 = shinv[5 * PP_PTS + gt];             \
-      sw[gt] = h00 * t0 + h01 * t1 + h02 * t2;                                                                           \
-      sw[PP_PTS + gt] = h01 * t0 + h11 * t1 + h12 * t2;                                                                  \
-      sw[2 * PP_PTS + gt] = h02 * t0 + h12 * t1 + h22 * t2;                                                              \
-    }                                                                                                                    \
-    pp_prefetch_stage<DC, 2>(a, chunk_next, valid_next, gt, RN);                                                         \
-    pp_group_bar(g);                                                                                                     \
-    /* P3: c_o = -Jc^T (Jp w_p) at the observation's camera-sorted position (xs is dead: cs reuses the region) */       \
-    if (R.cam != PAD_CAM) {                                                                                              \
-      const uint32_t spt = R.sp & 0xFFu, pos = (R.sp >> 8) & 0xFFu;                                                      \
-      const double w0 = sw[spt], w1 = sw[PP_PTS + spt], w2 = sw[2 * PP_PTS + spt];                                       \
-      const double* jp = R.j + 2 * DC;                                                                                   \
-      const double b0 = fma(jp[0], w0, fma(jp[1], w1, jp[2] * w2));                                                      \
-      const double b1 = fma(jp[3], w0, fma(jp[4], w1, jp[5] * w2));                                                      \
-      _Pragma("unroll") for (int k = 0; k < DC; ++k) cs[k * PP_CS_LD + pos] = -fma(R.j[k], b0, R.j[DC + k] * b1);        \
-    }                                                                                                                    \
-    pp_prefetch_stage<DC, 3>(a, chunk_next, valid_next, gt, RN);                                                         \
-    pp_group_bar(g);                                                                                                     \
-    /* P4: one thread per camera segment sums its run for all dofs; the two groups take turns on the private y */                          \
-    if (PRIVATE) { if (g == 0) { if (it > 0) pp_turn_wait(4); } else pp_turn_wait(3); }                                  \
-    {                                                                                                                    \
-      constexpr int KG = 3;                 /* dofs per work item: 3 independent accumulators per thread */              \
-      constexpr int NG = (DC + KG - 1) / KG;                                                                             \
-      const uint32_t nwork = R.nseg * NG;                                                                                \
-      for (uint32_t idx = gt; idx < nwork; idx += TILE) {                                                                \
-        const uint32_t sgi = idx / NG, kg = (idx - sgi * NG) * KG;                                                       \
-        const uint32_t b = segb[sgi], e = segb[sgi + 1], row = segc[sgi] * DC + kg;                                      \
-        const double* c0 = cs + kg * PP_CS_LD;                                                                           \
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0;                                                                             \
-        for (uint32_t q = b; q < e; ++q) {                                                                               \
-          v0 += c0[q];                                                                                                   \
-          if (kg + 1 < DC) v1 += c0[PP_CS_LD + q];                                                                       \
-          if (kg + 2 < DC) v2 += c0[2 * PP_CS_LD + q];                                                                   \
-        }                                                                                                                \
-        if (PRIVATE) {                                                                                                   \
-          y_priv[row] += v0;                                                                                             \
-          if (kg + 1 < DC) y_priv[row + 1] += v1;                                                                        \
-          if (kg + 2 < DC) y_priv[row + 2] += v2;                                                                        \
-        } else {                                                                                                         \
-          red_add(a.y + row, v0);                                                                                        \
-          if (kg + 1 < DC) red_add(a.y + row + 1, v1);                                                                   \
-          if (kg + 2 < DC) red_add(a.y + row + 2, v2);                                                                   \
-        }                                                                                                                \
-      }                                                                                                                  \
-    }                                                                                                                    \
-    if (PRIVATE) { if (g == 0) pp_turn_signal(3); else if (it + 1 < niter) pp_turn_signal(4); }                          \
-    pp_group_bar(g); /* cs / tables of this parity are rewritten next iteration */                                       \
-  }
-
-  uint32_t it = 0;
-  while (it < niter) {
-    PP_BODY(ra, rb)
-    ++it;
-    if (it >= niter) break;
-    PP_BODY(rb, ra)
-    ++it;
-  }
-#undef PP_BODY
-  __syncthreads();
-  if (PRIVATE) {
-    double* out = a.ypart + (size_t)blockIdx.x * a.n;
-    for (uint32_t i = tid; i < a.n; i += 2 * TILE) out[i] = y_priv[i];
-  }
-}
-
-template <int DC>
-static size_t pp_smem_bytes(uint32_t n, bool priv) {
-  return ((priv ? ((n + 1) & ~1u) : 0) + 2 * (size_t)pp_group_doubles<DC>()) * 8 + 64;
-}
-
-template <int DC, int MODE>
-static apex_status launch_pingpong_dc(Ctx& c, const PpArgs& a, bool priv, unsigned grid) {
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[priv ? 1 : 0]) {
-    if (priv) APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_matvec_pingpong_kernel<DC, true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, MV_SMEM_MAX));
-    else APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_matvec_pingpong_kernel<DC, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, MV_SMEM_MAX));
-    attr_done[priv ? 1 : 0] = true;
-  }
-  const size_t smem = pp_smem_bytes<DC>(a.n, priv);
-  if (priv) schur_matvec_pingpong_kernel<DC, true, MODE><<<grid, 2 * TILE, smem, c.stream>>>(a);
-  else schur_matvec_pingpong_kernel<DC, false, MODE><<<grid, 2 * TILE, smem, c.stream>>>(a);
-  return APEX_OK;
-}
-
-template <int MODE>
-static apex_status launch_pingpong(Ctx& c, const PpArgs& a, bool priv, unsigned grid) {
-  switch (c.dc) {
-    case 6: return launch_pingpong_dc<6, MODE>(c, a, priv, grid);
-    case 9: return launch_pingpong_dc<9, MODE>(c, a, priv, grid);
-    case 10: return launch_pingpong_dc<10, MODE>(c, a, priv, grid);
-    case 12: return launch_pingpong_dc<12, MODE>(c, a, priv, grid);
-    case 11: return launch_pingpong_dc<11, MODE>(c, a, priv, grid);
-    case 14: return launch_pingpong_dc<14, MODE>(c, a, priv, grid);
-    case 15: return launch_pingpong_dc<15, MODE>(c, a, priv, grid);
-    default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
-  }
-}
-
 // x (stride dc) -> x at an even stride (camera blocks 16-byte aligned for the 128-bit gathers)
 __global__ void pad_x_kernel(const double* __restrict__ x, double* __restrict__ xpad, uint32_t ncam, int dc, int xs, const DevState* st, int check_done) {
   if (check_done && st->pcg_done) return;
@@ -535,545 +190,263 @@ __global__ void pad_x_kernel(const double* __restrict__ x, double* __restrict__ 
   xpad[i] = k < (uint32_t)dc ? x[(size_t)cam * dc + k] : 0.0;
 }
 
-// y[i] = [(H_cc + lambda I) x]_i (rank 0) + sum over the CTA-private partial results, in CTA order
-__global__ void schur_finalize_kernel(const double* __restrict__ hcc, const double* __restrict__ x, const double* __restrict__ ypart, uint32_t nblk,
-                                      double* __restrict__ y, const DevState* st, uint32_t n, int dc, int add_hcc, int check_done) {
-  if (check_done && st->pcg_done) return;
-  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n) return;
-  double s = 0.0;
-  if (add_hcc == 2) s = -x[row];  // reduced gradient: starts from -g_c (x = g_c)
-  else if (add_hcc) {
-    const uint32_t cam = row / dc, a = row % dc;
-    const double* H = hcc + ((size_t)cam * dc + a) * dc;
-    const double* xc = x + (size_t)cam * dc;
-    s = st->damping * xc[a];
-    for (int b = 0; b < dc; ++b) s += H[b] * xc[b];
-  }
-  // fixed CTA order; 8 independent loads in flight per trip
-  uint32_t b = 0;
-  for (; b + 8 <= nblk; b += 8) {
-    double v[8];
+// ----------------------------------------------------------------------------------------------------
+// Chunk kernel: persistent 256-thread CTAs, 3 per SM; CTA r walks the chunks of range r (equal shares of the normal chunks),
+// one chunk (whole landmarks, <= 256 observations) per loop iteration.
+//
+// SPLIT SLOT ORDER. The two halves of an observation's Jacobian live in DIFFERENT orders inside the chunk: the landmark
+// half Jp (2x3) in point-major order (a landmark's observations are consecutive lanes), the camera half Jc (2xdc) in
+// CAMERA-SORTED order (a camera's observations are consecutive lanes; the permutation is built at upload,
+// cslot_meta). Thread t therefore holds Jp of point-major slot t and Jc of camera-sorted slot t, and the operator is
+//     a_o = Jc_o x_c            camera-sorted lanes: x is gathered with neighbouring lanes reading the same / adjacent rows
+//     u_o = Jp_o^T a_o          point-major lanes after a 2-value exchange through shared memory (a at its point-major slot)
+//     t_p = sum_o u_o           segmented warp-shuffle sum over the landmark's run of lanes (+ shared memory across warps)
+//     w_p = Hpp_p^-1 t_p        one thread per landmark
+//     b_o = Jp_o w_p            point-major lanes; 2 values back to the camera-sorted slot
+//     c_o = -Jc_o^T b_o         camera-sorted lanes; summed over each camera's run of lanes with segmented warp shuffles
+// Only 2 + 2 values per observation cross lanes through shared memory (instead of dc), both exchanges are one STS + one
+// stride-1 LDS per value. Every global read of a chunk is issued at the top of its iteration (registers / cp.async), so one
+// memory latency is exposed per chunk and CTA, hidden by the two other CTAs of the SM.
+//
+// WINDOWS. FP64 reductions into L2 cost 1.3 cycles per lane on the SM's path to the crossbar and do not overlap with the
+// loads that share it (measured: ~1 500 reductions per chunk added 1 850 cycles to the 3 000 the rest of a chunk takes), so
+// the camera-side sums do not leave the SM per chunk: consecutive chunks of a locality-ordered reconstruction see the same
+// few hundred cameras, the host cuts every range into windows of chunks touching <= W distinct cameras, and the CTA adds the
+// run sums into its window's rows of y in shared memory (ywin, indexed by the window-local camera index cslot_widx): a run's
+// first lane does a plain read-modify-write - runs of one warp name distinct cameras, and a run cut by a warp boundary
+// ("continuation") parks its sum in scont and is added by its warp's lanes 0..dc-1 after the next barrier. The window is
+// flushed once:
+//   DET   as a contiguous block of rows partial[win.cam0 + i][dc]; det_reduce_kernel then adds each camera's rows in a fixed
+//         order. Every sum has a fixed order => bitwise reproducible; costs rows*dc*16 bytes of extra traffic per application
+//         (Venice-1778 shape: 2 %).
+//   !DET  with one red.global.add.f64 per (camera of the window, dof) (a landmark order without camera locality makes the
+//         windows short and the rows many; problem_upload picks the flush, APEX_DETERMINISTIC overrides).
+// ----------------------------------------------------------------------------------------------------
+template <int DC>
+__device__ __forceinline__ void gather_x_padded(const double* __restrict__ xc, double* xv) {
+  // one L1 wavefront per distinct 128-byte line and instruction: as few instructions as possible (256-bit loads)
+  constexpr int N4 = DC / 4, REM = DC % 4;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldcg(ypart + (size_t)(b + u) * n + row);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) s += v[u];
-  }
-  for (; b < nblk; ++b) s += __ldcg(ypart + (size_t)b * n + row);
-  y[row] = s;
+  for (int m = 0; m < N4; ++m) ldg256(xc + 4 * m, xv[4 * m], xv[4 * m + 1], xv[4 * m + 2], xv[4 * m + 3]);
+  if (REM == 1) xv[4 * N4] = __ldg(xc + 4 * N4);
+  else if (REM == 2) { const double2 v = __ldg(reinterpret_cast<const double2*>(xc + 4 * N4)); xv[4 * N4] = v.x; xv[4 * N4 + 1] = v.y; }
+  else if (REM == 3) ldg256(xc + 4 * N4, xv[4 * N4], xv[4 * N4 + 1], xv[4 * N4 + 2], xv[4 * N4 + 3]);
 }
 
-// ----------------------------------------------------------------------------------------------------
-// Chunk kernel: one 256-thread CTA per normal chunk (whole landmarks, <= 256 observations), 3 CTAs per SM.
-// Every global read a chunk needs - Jacobian planes, slot metadata, chunk descriptor, landmark inverses and
-// gradients, camera-segment tables - is issued up front (registers / cp.async into shared memory), so only ONE
-// memory latency is exposed per chunk; the camera-side scatter is combined per camera segment in shared
-// memory and leaves the CTA as one red.global.add.f64 per (segment, dof). Chunks are visited in a strided order
-// so that CTAs running at the same time touch different cameras (no same-address serialisation in L2).
-// ----------------------------------------------------------------------------------------------------
+// shared memory of the chunk kernel in doubles: work arrays, continuation sums, window rows
+template <int MODE>
+__host__ __device__ constexpr int chunk_work_doubles() { return 2 * TILE + 3 * TILE + (3 + 6 + (MODE == MODE_MATVEC ? 0 : 3)) * MAX_TILE_PTS + MAX_TILE_PTS / 2; }
 template <int DC, int MODE>
-__global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a, uint32_t nchunks) {
-  constexpr int NP = 2 * (DC + 3);
-  constexpr int LD = TILE + 1;
-  constexpr int XS = xpad_stride(DC);
-  if (a.check_done && a.st->pcg_done) return;
-  __shared__ double cs[DC * LD];                  // phase 3/4 contributions; its head doubles as su in phases 1/2
-  double (*su)[TILE] = reinterpret_cast<double (*)[TILE]>(cs);
-  __shared__ double sw[3][MAX_TILE_PTS];
-  __shared__ double shinv[6][MAX_TILE_PTS];
-  __shared__ double sgp[3][MAX_TILE_PTS];
-  __shared__ uint32_t sptm[MAX_TILE_PTS];
-  __shared__ uint32_t ssegc[TILE];
-  __shared__ __align__(4) uint16_t ssegb[CSEG_LD];
-  const int tid = threadIdx.x;
-  const uint32_t chunk = (nchunks % 4099u != 0) ? (uint32_t)(((uint64_t)blockIdx.x * 4099u) % nchunks) : blockIdx.x;
-  // ---- all global reads up front ----
-  if (MODE != MODE_BACKSUB) {
-    cp_async4(ssegc + tid, a.cseg_cam + (size_t)chunk * TILE + tid);
-    if (tid < CSEG_LD / 2) cp_async4(reinterpret_cast<uint32_t*>(ssegb) + tid, reinterpret_cast<const uint32_t*>(a.cseg_begin + (size_t)chunk * CSEG_LD) + tid);
-  }
-  const uint2 meta = __ldg(a.cslot_meta + (size_t)chunk * TILE + tid);
-  const uint4 dsc = __ldg(reinterpret_cast<const uint4*>(a.chunk_desc + chunk));
-  double jall[NP];
-  load_jacobian_planes<NP>(a.J, chunk, tid, jall);
-  const uint32_t pt0 = dsc.x, npt = dsc.y, nseg = dsc.z;
-  if ((uint32_t)tid < npt) {
-    const uint32_t lp = pt0 + tid;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) cp_async8(&shinv[k][tid], a.hinv + (size_t)k * a.npl + lp);
-    if (MODE != MODE_MATVEC) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) cp_async8(&sgp[k][tid], a.gp + (size_t)k * a.npl + lp);
-    }
-    cp_async4(&sptm[tid], a.cpt_meta + lp);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  const uint32_t cam = meta.x;
-  const double* jc = jall;
-  const double* jp = jall + 2 * DC;
-  // ---- phase 1: u_o = Jp^T (Jc x_c); x gathered through L1 with 128-bit loads from the padded copy. The sum over a
-  // landmark's observations (consecutive lanes) starts as a segmented warp-shuffle reduction; only the first lane of
-  // each run writes its partial to shared memory ----
-  if (MODE != MODE_RHS) {
-    double u[3] = {0.0, 0.0, 0.0};
-    if (cam != PAD_CAM) obs_forward_padded<DC>(jc, jp, a.xpad + (size_t)cam * XS, u);
-    const uint32_t key = cam != PAD_CAM ? (meta.y & 0xFFu) : 0xFFFFu;  // chunk-local landmark
-    const int lane = tid & 31;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t ok = __shfl_down_sync(0xffffffffu, key, d);
-      const bool hit = lane + d < 32 && ok == key;
-      if (!__any_sync(0xffffffffu, hit)) break;  // runs are contiguous: no partner at distance d => none further away
-      const double o0 = __shfl_down_sync(0xffffffffu, u[0], d), o1 = __shfl_down_sync(0xffffffffu, u[1], d), o2 = __shfl_down_sync(0xffffffffu, u[2], d);
-      if (hit) { u[0] += o0; u[1] += o1; u[2] += o2; }
-    }
-    const uint32_t pk = __shfl_up_sync(0xffffffffu, key, 1);
-    if ((lane == 0 || pk != key) && cam != PAD_CAM) { su[0][tid] = u[0]; su[1][tid] = u[1]; su[2][tid] = u[2]; }
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  // ---- phase 2: per landmark ----
-  if ((uint32_t)tid < npt) {
-    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-    if (MODE != MODE_RHS) {
-      const uint32_t mm = sptm[tid], off = mm & 0xFFFFu, cnt = mm >> 16;
-      if (cnt) {
-        t0 = su[0][off]; t1 = su[1][off]; t2 = su[2][off];
-        for (uint32_t b = (off & ~31u) + 32; b < off + cnt; b += 32) { t0 += su[0][b]; t1 += su[1][b]; t2 += su[2][b]; }  // runs continuing in the next warps
-      }
-    }
-    double v0, v1, v2;
-    if (MODE == MODE_MATVEC) { v0 = t0; v1 = t1; v2 = t2; }
-    else if (MODE == MODE_RHS) { v0 = -sgp[0][tid]; v1 = -sgp[1][tid]; v2 = -sgp[2][tid]; }
-    else { v0 = -sgp[0][tid] - t0; v1 = -sgp[1][tid] - t1; v2 = -sgp[2][tid] - t2; }
-    const double h00 = shinv[0][tid], h01 = shinv[1][tid], h02 = shinv[2][tid], h11 = shinv[3][tid], h12 = shinv[4][tid], h22 = shinv[5][tid];
-    const double w0 = h00 * v0 + h01 * v1 + h02 * v2, w1 = h01 * v0 + h11 * v1 + h12 * v2, w2 = h02 * v0 + h12 * v1 + h22 * v2;
-    if (MODE == MODE_BACKSUB) {
-      const size_t lp = pt0 + tid;
-      a.step_pt[3 * lp] = w0; a.step_pt[3 * lp + 1] = w1; a.step_pt[3 * lp + 2] = w2;
-    } else { sw[0][tid] = w0; sw[1][tid] = w1; sw[2][tid] = w2; }
-  }
-  if (MODE == MODE_BACKSUB) return;
-  __syncthreads();
-  // ---- phase 3: c_o = -Jc^T (Jp w_p) written at the observation's camera-sorted position ----
-  if (cam != PAD_CAM) {
-    const uint32_t spt = meta.y & 0xFFu, pos = (meta.y >> 8) & 0xFFu;
-    const double w0 = sw[0][spt], w1 = sw[1][spt], w2 = sw[2][spt];
-    const double b0 = fma(jp[0], w0, fma(jp[1], w1, jp[2] * w2));
-    const double b1 = fma(jp[3], w0, fma(jp[4], w1, jp[5] * w2));
-#pragma unroll
-    for (int k = 0; k < DC; ++k) cs[k * LD + pos] = -fma(jc[k], b0, jc[DC + k] * b1);
-  }
-  __syncthreads();
-  // ---- phase 4: one reduction per (camera segment, dof); a thread takes 3 dofs of one segment ----
-  constexpr int KG = 3, NG = (DC + KG - 1) / KG;
-  for (uint32_t idx = tid; idx < nseg * NG; idx += TILE) {
-    const uint32_t sgi = idx / NG, kg = (idx - sgi * NG) * KG;
-    const uint32_t b = ssegb[sgi], e = ssegb[sgi + 1];
-    double* yr = a.y + (size_t)ssegc[sgi] * DC + kg;
-    const double* c0 = cs + kg * LD;
-    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-    for (uint32_t q = b; q < e; ++q) {
-      v0 += c0[q];
-      if (kg + 1 < DC) v1 += c0[LD + q];
-      if (kg + 2 < DC) v2 += c0[2 * LD + q];
-    }
-    if (a.debug == 1 && v0 != 1.2345e300) continue;  // development probe: scatter suppressed
-    red_add(yr, v0);
-    if (kg + 1 < DC) red_add(yr + 1, v1);
-    if (kg + 2 < DC) red_add(yr + 2, v2);
-  }
-}
+__host__ __device__ constexpr size_t chunk_smem_bytes(uint32_t W) { return sizeof(double) * ((size_t)chunk_work_doubles<MODE>() + 8 * DC + (size_t)W * DC); }
 
-// ----------------------------------------------------------------------------------------------------
-// Window kernel (operator only): one 256-thread CTA walks a GROUP of G consecutive chunks. In a locality-ordered
-// reconstruction the landmarks of a group see a narrow band of cameras, so the CTA keeps a WINDOW of W consecutive
-// cameras (modulo ncam; start chosen per group at upload for maximal coverage) in shared memory:
-//   xw : the operator input of the window's cameras, loaded once per group with coalesced cp.async
-//        (replaces a 32-line L1 gather per warp instruction by LDS),
-//   yw : the window's share of the result, accumulated chunk after chunk with plain shared-memory read-modify-
-//        writes (one thread per (camera segment, 3 dofs); segments of a chunk are distinct cameras, chunks are
-//        separated by a barrier) and flushed with ONE coalesced red.global.add.f64 per (camera, dof) per group
-//        instead of one per (chunk, camera segment, dof).
-// Observations whose camera falls outside the window (2-3 % on the Venice shape at W = 320) take the chunk
-// kernel's route: 128-bit gather from the padded copy, reduction straight to global memory. The result is exact
-// for any input; only the speed depends on locality.
-// ----------------------------------------------------------------------------------------------------
-struct WinArgs {
-  const uint32_t* grp_win0;  // [ngroups] first camera of the group's window
-  uint32_t ngroups, G, W, ncam;
-  uint32_t ywin;             // 1: window of y in shared memory too; 0: x only (results leave per chunk, as in the chunk kernel)
-};
-template <int DC>
-__host__ __device__ constexpr size_t win_base_bytes() {
-  return sizeof(double) * (DC * (TILE + 1) + 3 * MAX_TILE_PTS + 6 * MAX_TILE_PTS) + 4 * MAX_TILE_PTS + 4 * TILE + ((2 * CSEG_LD + 15) & ~15);
-}
-template <int DC>
-__global__ void __launch_bounds__(TILE, 3) schur_window_kernel(SchurArgs a, WinArgs wa, uint32_t nchunks) {
-  constexpr int NP = 2 * (DC + 3);
-  constexpr int LD = TILE + 1;
+template <int DC, int MODE, bool DET>
+__global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a) {
+  constexpr int NPAIR = DC + 3;
   constexpr int XS = xpad_stride(DC);
+  constexpr int NGP = MODE == MODE_MATVEC ? 0 : 3;
+  constexpr int WORK = chunk_work_doubles<MODE>();
   if (a.check_done && a.st->pcg_done) return;
-  extern __shared__ __align__(16) unsigned char win_smem[];
-  double* cs = reinterpret_cast<double*>(win_smem);                  // [DC][LD]; head doubles as su in phases 1/2
-  double (*su)[TILE] = reinterpret_cast<double (*)[TILE]>(cs);
-  double (*sw)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(cs + DC * LD);
-  double (*shinv)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(cs + DC * LD + 3 * MAX_TILE_PTS);
-  double* xw = cs + DC * LD + 9 * MAX_TILE_PTS;
-  const uint32_t W = wa.W, ncam = wa.ncam;
-  double* yw = xw + (size_t)W * DC;
-  const bool ywin = wa.ywin != 0;
-  uint32_t* sptm = reinterpret_cast<uint32_t*>(yw + (ywin ? (size_t)W * DC : 0));
-  uint32_t* ssegc = sptm + MAX_TILE_PTS;
-  uint16_t* ssegb = reinterpret_cast<uint16_t*>(ssegc + TILE);
-  const int tid = threadIdx.x;
-  const uint32_t grp = (wa.ngroups % 4099u != 0) ? (uint32_t)(((uint64_t)blockIdx.x * 4099u) % wa.ngroups) : blockIdx.x;
-  const uint32_t c_begin = grp * wa.G, c_end = min(c_begin + wa.G, nchunks);
-  const uint32_t win0 = __ldg(wa.grp_win0 + grp);
-  const uint32_t nw = W * DC, ntot = ncam * DC;
-  // window of x (cp.async, lands together with the first chunk's tables), zeroed window of y
-  for (uint32_t i = tid; i < nw; i += TILE) {
-    uint32_t gi = win0 * DC + i;
-    if (gi >= ntot) gi -= ntot;
-    cp_async8(xw + i, a.x + gi);
-    if (ywin) yw[i] = 0.0;
-  }
-  for (uint32_t chunk = c_begin; chunk < c_end; ++chunk) {
-    // ---- all global reads of the chunk up front ----
-    cp_async4(ssegc + tid, a.cseg_cam + (size_t)chunk * TILE + tid);
-    if (tid < CSEG_LD / 2) cp_async4(reinterpret_cast<uint32_t*>(ssegb) + tid, reinterpret_cast<const uint32_t*>(a.cseg_begin + (size_t)chunk * CSEG_LD) + tid);
-    const uint2 meta = __ldg(a.cslot_meta + (size_t)chunk * TILE + tid);
-    const uint4 dsc = __ldg(reinterpret_cast<const uint4*>(a.chunk_desc + chunk));
-    double jall[NP];
-    load_jacobian_planes<NP>(a.J, chunk, tid, jall);
-    const uint32_t pt0 = dsc.x, npt = dsc.y, nseg = dsc.z;
-    if ((uint32_t)tid < npt) {
-      const uint32_t lp = pt0 + tid;
+  extern __shared__ double sm[];
+  double (*sab)[TILE] = reinterpret_cast<double (*)[TILE]>(sm);                         // [2] a: camera-sorted -> point-major; later b: back
+  double (*su)[TILE] = reinterpret_cast<double (*)[TILE]>(sm + 2 * TILE);                // [3]
+  double (*sw)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(sm + 5 * TILE);               // [3]
+  double (*shinv)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(sm + 5 * TILE + 3 * MAX_TILE_PTS);  // [6]
+  double (*sgp)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(sm + 5 * TILE + 9 * MAX_TILE_PTS);    // [3] (not MATVEC)
+  uint32_t* sptm = reinterpret_cast<uint32_t*>(sm + 5 * TILE + (9 + NGP) * MAX_TILE_PTS);
+  double (*scont)[DC] = reinterpret_cast<double (*)[DC]>(sm + WORK);                     // [8] run sums of continuation lanes, per warp
+  double* ywin = sm + WORK + 8 * DC;                                                     // [window][DC]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t win_end = __ldg(a.range_win0 + blockIdx.x + 1);
+  uint32_t fix_flags = 0, fix_widx = 0;   // pending continuation sums of the previous chunk (this warp's lane 0)
+  // add the parked continuation sums of the previous chunk: lanes 0..DC-1 of the warp whose lane 0 started the chain
+  auto fix_up = [&]() {
+    if ((fix_flags & CONT_FIRST_BIT) && lane < DC) {
+      const int len = (int)((fix_flags >> CONT_LEN_SHIFT) & 7u);
+      double s = scont[warp][lane];
+      for (int v = 1; v < len; ++v) s += scont[warp + v][lane];
+      ywin[fix_widx * DC + lane] += s;
+    }
+    fix_flags = 0;
+  };
+  for (uint32_t win = __ldg(a.range_win0 + blockIdx.x); win < win_end; ++win) {
+    const uint4 wd = __ldg(reinterpret_cast<const uint4*>(a.win_desc + win));   // chunk_begin, chunk_end, cam0, ncams
+    if (MODE != MODE_BACKSUB) {
+      for (uint32_t i = tid; i < wd.w * DC; i += TILE) ywin[i] = 0.0;   // ordered before the first read-modify-write by the chunk's barriers
+    }
+    for (uint32_t chunk = wd.x; chunk < wd.y; ++chunk) {
+      // ---- all global reads up front ----
+      const uint2 meta = __ldg(a.cslot_meta + (size_t)chunk * TILE + tid);
+      const uint32_t widx = __ldg(a.cslot_widx + (size_t)chunk * TILE + tid);
+      const uint4 dsc = __ldg(reinterpret_cast<const uint4*>(a.chunk_desc + chunk));
+      double jc[2 * DC], jp[6];
+      {
+        const double2* p = reinterpret_cast<const double2*>(a.J) + (size_t)chunk * NPAIR * TILE + tid;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) cp_async8(&shinv[k][tid], a.hinv + (size_t)k * a.npl + lp);
-      cp_async4(&sptm[tid], a.cpt_meta + lp);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    const uint32_t cam = meta.x;
-    const double* jc = jall;
-    const double* jp = jall + 2 * DC;
-    if (chunk == c_begin) {  // the window has to be there before the first gather
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();
-    }
-    // ---- phase 1: u_o = Jp^T (Jc x_c), x from the window; segmented warp-shuffle sum over each landmark's run ----
-    {
-      double u[3] = {0.0, 0.0, 0.0};
-      if (cam != PAD_CAM) {
-        uint32_t l = cam - win0;
-        if (cam < win0) l += ncam;
-        if (l < W) {
-          const double* xc = xw + l * DC;
+        for (int m = 0; m < DC; ++m) { const double2 v = ld_stream2(p + (size_t)m * TILE); jc[2 * m] = v.x; jc[2 * m + 1] = v.y; }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) { const double2 v = ld_stream2(p + (size_t)(DC + m) * TILE); jp[2 * m] = v.x; jp[2 * m + 1] = v.y; }
+      }
+      const uint32_t pt0 = dsc.x, npt = dsc.y, nobs = dsc.w;
+      if ((uint32_t)tid < npt) {
+        const uint32_t lp = pt0 + tid;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cp_async8(&shinv[k][tid], a.hinv + (size_t)k * a.npl + lp);
+        if (MODE != MODE_MATVEC) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) cp_async8(&sgp[k][tid], a.gp + (size_t)k * a.npl + lp);
+        }
+        cp_async4(&sptm[tid], a.cpt_meta + lp);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (MODE != MODE_BACKSUB) fix_up();   // while the loads are in flight
+      const uint32_t camc = meta.x;                 // camera of camera-sorted slot tid (PAD_CAM behind the chunk's observations)
+      const bool pt_valid = (uint32_t)tid < nobs;   // point-major slot tid holds an observation
+      // ---- phase 1: a_o = Jc_o x_c on the camera-sorted lanes, sent to the observation's point-major slot ----
+      if (MODE != MODE_RHS) {
+        if (camc != PAD_CAM) {
+          double xv[4 * (DC / 4) + 4];
+          gather_x_padded<DC>(a.xpad + (size_t)camc * XS, xv);
           double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-          for (int k = 0; k < DC; ++k) { const double xv = xc[k]; a0 = fma(jc[k], xv, a0); a1 = fma(jc[DC + k], xv, a1); }
+          for (int k = 0; k < DC; ++k) { a0 = fma(jc[k], xv[k], a0); a1 = fma(jc[DC + k], xv[k], a1); }
+          const uint32_t ipos = (meta.y >> 16) & 0xFFu;
+          sab[0][ipos] = a0; sab[1][ipos] = a1;
+        }
+        __syncthreads();
+        // u_o = Jp_o^T a_o; the sum over a landmark's observations (consecutive lanes) starts as a segmented warp-shuffle
+        // reduction; only the first lane of each run writes its partial to shared memory
+        double u[3] = {0.0, 0.0, 0.0};
+        if (pt_valid) {
+          const double a0 = sab[0][tid], a1 = sab[1][tid];
 #pragma unroll
           for (int k = 0; k < 3; ++k) u[k] = fma(jp[k], a0, jp[3 + k] * a1);
-        } else {
-          obs_forward_padded<DC>(jc, jp, a.xpad + (size_t)cam * XS, u);
+        }
+        const uint32_t key = pt_valid ? (meta.y & 0xFFu) : 0xFFFFu;  // chunk-local landmark
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t ok = __shfl_down_sync(0xffffffffu, key, d);
+          const bool hit = lane + d < 32 && ok == key;
+          if (!__any_sync(0xffffffffu, hit)) break;  // runs are contiguous: no partner at distance d => none further away
+          const double o0 = __shfl_down_sync(0xffffffffu, u[0], d), o1 = __shfl_down_sync(0xffffffffu, u[1], d), o2 = __shfl_down_sync(0xffffffffu, u[2], d);
+          if (hit) { u[0] += o0; u[1] += o1; u[2] += o2; }
+        }
+        const uint32_t pk = __shfl_up_sync(0xffffffffu, key, 1);
+        if ((lane == 0 || pk != key) && pt_valid) { su[0][tid] = u[0]; su[1][tid] = u[1]; su[2][tid] = u[2]; }
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      // ---- phase 2: per landmark ----
+      if ((uint32_t)tid < npt) {
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        if (MODE != MODE_RHS) {
+          const uint32_t mm = sptm[tid], off = mm & 0xFFFFu, cnt = mm >> 16;
+          if (cnt) {
+            t0 = su[0][off]; t1 = su[1][off]; t2 = su[2][off];
+            for (uint32_t b = (off & ~31u) + 32; b < off + cnt; b += 32) { t0 += su[0][b]; t1 += su[1][b]; t2 += su[2][b]; }  // runs continuing in the next warps
+          }
+        }
+        double v0, v1, v2;
+        if (MODE == MODE_MATVEC) { v0 = t0; v1 = t1; v2 = t2; }
+        else if (MODE == MODE_RHS) { v0 = -sgp[0][tid]; v1 = -sgp[1][tid]; v2 = -sgp[2][tid]; }
+        else { v0 = -sgp[0][tid] - t0; v1 = -sgp[1][tid] - t1; v2 = -sgp[2][tid] - t2; }
+        const double h00 = shinv[0][tid], h01 = shinv[1][tid], h02 = shinv[2][tid], h11 = shinv[3][tid], h12 = shinv[4][tid], h22 = shinv[5][tid];
+        const double w0 = h00 * v0 + h01 * v1 + h02 * v2, w1 = h01 * v0 + h11 * v1 + h12 * v2, w2 = h02 * v0 + h12 * v1 + h22 * v2;
+        if (MODE == MODE_BACKSUB) {
+          const size_t lp = pt0 + tid;
+          a.step_pt[3 * lp] = w0; a.step_pt[3 * lp + 1] = w1; a.step_pt[3 * lp + 2] = w2;
+        } else { sw[0][tid] = w0; sw[1][tid] = w1; sw[2][tid] = w2; }
+      }
+      __syncthreads();
+      if (MODE == MODE_BACKSUB) continue;   // (the barrier above also protects the work arrays against the next chunk's loads)
+      // ---- phase 3: b_o = Jp_o w_p on the point-major lanes, sent to the observation's camera-sorted slot ----
+      if (pt_valid) {
+        const uint32_t spt = meta.y & 0xFFu, pos = (meta.y >> 8) & 0xFFu;
+        const double w0 = sw[0][spt], w1 = sw[1][spt], w2 = sw[2][spt];
+        sab[0][pos] = fma(jp[0], w0, fma(jp[1], w1, jp[2] * w2));
+        sab[1][pos] = fma(jp[3], w0, fma(jp[4], w1, jp[5] * w2));
+      }
+      __syncthreads();
+      // ---- phase 4: c_o = -Jc_o^T b_o, summed over each camera's run of lanes; the first lane of a run owns the result ----
+      double cv[DC];
+      if (camc != PAD_CAM) {
+        const double b0 = sab[0][tid], b1 = sab[1][tid];
+#pragma unroll
+        for (int k = 0; k < DC; ++k) cv[k] = -fma(jc[k], b0, jc[DC + k] * b1);
+      } else {
+#pragma unroll
+        for (int k = 0; k < DC; ++k) cv[k] = 0.0;
+      }
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t ok = __shfl_down_sync(0xffffffffu, camc, d);
+        const bool hit = lane + d < 32 && ok == camc && camc != PAD_CAM;
+        if (!__any_sync(0xffffffffu, hit)) break;
+#pragma unroll
+        for (int k = 0; k < DC; ++k) {
+          const double o = __shfl_down_sync(0xffffffffu, cv[k], d);
+          if (hit) cv[k] += o;
         }
       }
-      const uint32_t key = cam != PAD_CAM ? (meta.y & 0xFFu) : 0xFFFFu;
-      const int lane = tid & 31;
+      const uint32_t pc = __shfl_up_sync(0xffffffffu, camc, 1);
+      if (camc != PAD_CAM && (lane == 0 || pc != camc)) {
+        if (meta.y & CONT_BIT) {   // (only lane 0 can carry the flag)
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const double o0 = __shfl_down_sync(0xffffffffu, u[0], d), o1 = __shfl_down_sync(0xffffffffu, u[1], d), o2 = __shfl_down_sync(0xffffffffu, u[2], d);
-        const uint32_t ok = __shfl_down_sync(0xffffffffu, key, d);
-        if (lane + d < 32 && ok == key) { u[0] += o0; u[1] += o1; u[2] += o2; }
-      }
-      const uint32_t pk = __shfl_up_sync(0xffffffffu, key, 1);
-      if ((lane == 0 || pk != key) && cam != PAD_CAM) { su[0][tid] = u[0]; su[1][tid] = u[1]; su[2][tid] = u[2]; }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    // ---- phase 2: per landmark ----
-    if ((uint32_t)tid < npt) {
-      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-      const uint32_t mm = sptm[tid], off = mm & 0xFFFFu, cnt = mm >> 16;
-      if (cnt) {
-        t0 = su[0][off]; t1 = su[1][off]; t2 = su[2][off];
-        for (uint32_t b = (off & ~31u) + 32; b < off + cnt; b += 32) { t0 += su[0][b]; t1 += su[1][b]; t2 += su[2][b]; }
-      }
-      const double h00 = shinv[0][tid], h01 = shinv[1][tid], h02 = shinv[2][tid], h11 = shinv[3][tid], h12 = shinv[4][tid], h22 = shinv[5][tid];
-      sw[0][tid] = h00 * t0 + h01 * t1 + h02 * t2;
-      sw[1][tid] = h01 * t0 + h11 * t1 + h12 * t2;
-      sw[2][tid] = h02 * t0 + h12 * t1 + h22 * t2;
-    }
-    __syncthreads();
-    // ---- phase 3: c_o = -Jc^T (Jp w_p) at the observation's camera-sorted position ----
-    if (cam != PAD_CAM) {
-      const uint32_t spt = meta.y & 0xFFu, pos = (meta.y >> 8) & 0xFFu;
-      const double w0 = sw[0][spt], w1 = sw[1][spt], w2 = sw[2][spt];
-      const double b0 = fma(jp[0], w0, fma(jp[1], w1, jp[2] * w2));
-      const double b1 = fma(jp[3], w0, fma(jp[4], w1, jp[5] * w2));
+          for (int k = 0; k < DC; ++k) scont[warp][k] = cv[k];
+        } else {
+          double* yr = ywin + widx * DC;
 #pragma unroll
-      for (int k = 0; k < DC; ++k) cs[k * LD + pos] = -fma(jc[k], b0, jc[DC + k] * b1);
+          for (int k = 0; k < DC; ++k) yr[k] += cv[k];
+        }
+      }
+      fix_flags = __shfl_sync(0xffffffffu, meta.y, 0);
+      fix_widx = __shfl_sync(0xffffffffu, widx, 0);
+      __syncthreads();   // work arrays free for the next chunk; run sums visible to fix_up
     }
+    if (MODE == MODE_BACKSUB) continue;
+    // ---- flush the window ----
+    fix_up();
     __syncthreads();
-    // ---- phase 4: per (camera segment, 3 dofs): into the window, or straight to global memory outside it ----
-    constexpr int KG = 3, NG = (DC + KG - 1) / KG;
-    for (uint32_t idx = tid; idx < nseg * NG; idx += TILE) {
-      const uint32_t sgi = idx / NG, kg = (idx - sgi * NG) * KG;
-      const uint32_t b = ssegb[sgi], e = ssegb[sgi + 1];
-      const uint32_t cg = ssegc[sgi];
-      const double* c0 = cs + kg * LD;
-      double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-      for (uint32_t q = b; q < e; ++q) {
-        v0 += c0[q];
-        if (kg + 1 < DC) v1 += c0[LD + q];
-        if (kg + 2 < DC) v2 += c0[2 * LD + q];
-      }
-      uint32_t l = cg - win0;
-      if (cg < win0) l += ncam;
-      if (ywin && l < W) {
-        double* yr = yw + l * DC + kg;
-        yr[0] += v0;
-        if (kg + 1 < DC) yr[1] += v1;
-        if (kg + 2 < DC) yr[2] += v2;
-      } else if (a.debug != 1) {
-        double* yr = a.y + (size_t)cg * DC + kg;
-        red_add(yr, v0);
-        if (kg + 1 < DC) red_add(yr + 1, v1);
-        if (kg + 2 < DC) red_add(yr + 2, v2);
+    if (DET) {
+      double* out = a.partial + (size_t)wd.z * DC;
+      for (uint32_t i = tid; i < wd.w * DC; i += TILE) out[i] = ywin[i];
+    } else if (a.debug != 1) {
+      for (uint32_t i = tid; i < wd.w * DC; i += TILE) {
+        const uint32_t c = i / DC, k = i - c * DC;
+        red_add(a.y + (size_t)__ldg(a.win_cams + wd.z + c) * DC + k, ywin[i]);
       }
     }
-    __syncthreads();  // the next chunk overwrites the tables and su; the flush reads yw
-  }
-  // ---- flush the window: one coalesced reduction per touched (camera, dof) ----
-  if (a.debug == 1 || !ywin) return;
-  for (uint32_t i = tid; i < nw; i += TILE) {
-    const double v = yw[i];
-    if (v != 0.0) {
-      uint32_t gi = win0 * DC + i;
-      if (gi >= ntot) gi -= ntot;
-      red_add(a.y + gi, v);
-    }
+    __syncthreads();   // before the next window zeroes the rows
   }
 }
 
-// ----------------------------------------------------------------------------------------------------
-// Stream kernel (operator only, DC = 6 / 9): the chunk kernel is latency bound - a CTA asks for its 48 KB of
-// Jacobian planes, waits, computes through three barriers, and only the other two CTAs of the SM cover that, so
-// on average ~36 KB per SM are in flight where HBM needs ~70 KB. Here loads and compute are decoupled:
-//   * one persistent CTA per SM = 3 groups of 256 threads sharing a 2-stage shared-memory ring;
-//   * whole chunks - Jacobian planes (one 48 KB bulk copy), slot metadata, camera-segment tables, chunk descriptor -
-//     are streamed into the ring with cp.async.bulk (TMA), armed on an mbarrier per stage, so ~100 KB per SM are
-//     always in flight, independent of what the groups are computing;
-//   * a group waits for its stage, moves its chunk into registers (12 conflict-free LDS.128 per thread), releases
-//     the stage (mbarrier arrive; its first thread re-arms it with the chunk two ahead as soon as all 256 copies
-//     are out) and then runs the chunk kernel's four phases on named barriers
-//     (bar.sync g, 256); the three groups are at different phases, so the LSU / FP64 / barrier latencies of one
-//     overlap with the others;
-//   * the x gather is issued before the register copy (the metadata is already on chip) and uses 256-bit loads.
-// Chunks are dealt round-robin to the CTAs in the same strided order as the chunk kernel. Every wait is bounded
-// (trap instead of a hang).
-// ----------------------------------------------------------------------------------------------------
-constexpr int ST_GROUPS = 3, ST_STAGES = 2, ST_THREADS = ST_GROUPS * TILE;
-// "stage full" barriers: one per (stage, group) combination, i.e. chunk i of a CTA uses full[i % 6]. With one barrier per
-// stage, a group waiting for the NEXT BUT ONE fill of a stage would see the parity it waits for as "already
-// completed" while the fill in between has not landed (a parity wait cannot tell phase n from phase n + 2).
-constexpr int ST_FULL = ST_GROUPS * ST_STAGES;
-template <int DC> __host__ __device__ constexpr uint32_t st_j_bytes() { return 2 * (DC + 3) * 8 * TILE; }
-template <int DC> __host__ __device__ constexpr uint32_t st_stage_bytes() {
-  return (st_j_bytes<DC>() + 8 * TILE + 4 * TILE + 2 * CSEG_LD + 16 + 127) & ~127u;
-}
-template <int DC> __host__ __device__ constexpr uint32_t st_group_bytes() {
-  return 8 * (DC * (TILE + 1) + 3 * TILE + 9 * MAX_TILE_PTS) + 4 * MAX_TILE_PTS + 2 * (4 * TILE + 2 * CSEG_LD);
-}
-template <int DC> __host__ __device__ constexpr uint32_t st_smem_bytes() {
-  return ST_STAGES * st_stage_bytes<DC>() + ST_GROUPS * st_group_bytes<DC>() + 8 * (ST_FULL + ST_STAGES);
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// bounded wait on a phase parity: ~2 s of polling, then trap (an error the host sees) instead of a hang
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  const long long t0 = clock64();
-  for (;;) {
-    uint32_t ok;
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (ok) return;
-    if (clock64() - t0 > 4000000000ll) __trap();
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
-
+// deterministic flush, second pass: y[camera] += sum of the camera's partial rows, in ascending row order folded into a fixed
+// tree: one warp per camera, lane l adds rows l, l+32, ... in order, then a butterfly over the lanes.
 template <int DC>
-__global__ void __launch_bounds__(ST_THREADS, 1) schur_stream_kernel(SchurArgs a, uint32_t nchunks) {
-  constexpr int NP = 2 * (DC + 3);
-  constexpr int LD = TILE + 1;
-  constexpr int XS = xpad_stride(DC);
-  constexpr uint32_t JB = st_j_bytes<DC>(), SB = st_stage_bytes<DC>(), GB = st_group_bytes<DC>();
-  constexpr uint32_t OFF_META = JB, OFF_SEGC = JB + 8 * TILE, OFF_SEGB = OFF_SEGC + 4 * TILE, OFF_DESC = OFF_SEGB + 2 * CSEG_LD;
-  static_assert((2 * CSEG_LD) % 16 == 0, "segment table rows must be 16-byte multiples for bulk copies");
-  if (a.check_done && a.st->pcg_done) return;
-  extern __shared__ __align__(128) unsigned char st_smem[];
-  unsigned char* stages = st_smem;
-  unsigned char* groups = st_smem + ST_STAGES * SB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(groups + ST_GROUPS * GB);  // full[ST_FULL], empty[ST_STAGES]
-  const int tid_all = threadIdx.x;
-  if (tid_all == 0) {
-    for (int s = 0; s < ST_FULL; ++s) mbar_init(smem_u32(bars + s), 1);
-    for (int s = 0; s < ST_STAGES; ++s) mbar_init(smem_u32(bars + ST_FULL + s), TILE);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+__global__ void __launch_bounds__(256) det_reduce_kernel(const double* __restrict__ partial, const uint32_t* __restrict__ cam_row_start,
+                                                         const uint32_t* __restrict__ cam_rows, double* __restrict__ y, const DevState* st,
+                                                         uint32_t ncam, int check_done) {
+  if (check_done && st->pcg_done) return;
+  const uint32_t cam = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (cam >= ncam) return;
+  double acc[DC];
+#pragma unroll
+  for (int k = 0; k < DC; ++k) acc[k] = 0.0;
+  const uint32_t e1 = __ldg(cam_row_start + cam + 1);
+  for (uint32_t e = __ldg(cam_row_start + cam) + lane; e < e1; e += 32) {
+    const double* row = partial + (size_t)__ldg(cam_rows + e) * DC;
+#pragma unroll
+    for (int k = 0; k < DC; ++k) acc[k] += __ldcg(row + k);
   }
-  __syncthreads();
-  // chunks of this CTA: j = blockIdx.x + i * gridDim.x, visited in the strided order
-  const uint32_t nmine = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const bool strided = nchunks % 4099u != 0;
-  // producer duty: whoever frees a stage refills it. issue(i) arms stage i % ST_STAGES and starts the bulk copies of this
-  // CTA's i-th chunk: Jacobian planes (one contiguous run), slot metadata, segment tables, chunk descriptor.
-  auto issue = [&](uint32_t i) {
-    const uint32_t s = i % ST_STAGES;
-    const uint32_t j = blockIdx.x + i * gridDim.x;
-    const uint32_t chunk = strided ? (uint32_t)(((uint64_t)j * 4099u) % nchunks) : j;
-    const uint32_t full = smem_u32(bars + i % ST_FULL), dst = smem_u32(stages + (size_t)s * SB);
-    mbar_expect_tx(full, JB + 8 * TILE + 4 * TILE + 2 * CSEG_LD + 16);
-    bulk_g2s(dst, a.J + (size_t)chunk * NP * TILE, JB, full);
-    bulk_g2s(dst + OFF_META, a.cslot_meta + (size_t)chunk * TILE, 8 * TILE, full);
-    bulk_g2s(dst + OFF_SEGC, a.cseg_cam + (size_t)chunk * TILE, 4 * TILE, full);
-    bulk_g2s(dst + OFF_SEGB, a.cseg_begin + (size_t)chunk * CSEG_LD, 2 * CSEG_LD, full);
-    bulk_g2s(dst + OFF_DESC, a.chunk_desc + chunk, 16, full);
-  };
-  if (tid_all == 0)
-    for (uint32_t i = 0; i < ST_STAGES && i < nmine; ++i) issue(i);
-  // ---------------- consumers ----------------
-  const int grp = tid_all / TILE, tid = tid_all % TILE, lane = tid & 31;
-  unsigned char* gb = groups + (size_t)grp * GB;
-  double* cs = reinterpret_cast<double*>(gb);                          // [DC][LD]
-  double (*su)[TILE] = reinterpret_cast<double (*)[TILE]>(cs + DC * LD);
-  double (*sw)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(cs + DC * LD + 3 * TILE);
-  double (*shinv)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(cs + DC * LD + 3 * TILE + 3 * MAX_TILE_PTS);
-  uint32_t* sptm = reinterpret_cast<uint32_t*>(cs + DC * LD + 3 * TILE + 9 * MAX_TILE_PTS);
-  unsigned char* segtab = reinterpret_cast<unsigned char*>(sptm + MAX_TILE_PTS);   // 2 x {segc u32[256], segb u16[CSEG_LD]}
-  uint32_t par = 0;  // parity of the group's segment-table buffer
-  for (uint32_t i = grp; i < nmine; i += ST_GROUPS, par ^= 1) {
-    const uint32_t s = i % ST_STAGES, use = i / ST_STAGES;
-    const unsigned char* stg = stages + (size_t)s * SB;
-    mbar_wait(smem_u32(bars + i % ST_FULL), (i / ST_FULL) & 1);
-    // ---- chunk -> registers / group-private tables; the x gather goes out first ----
-    const uint2 meta = reinterpret_cast<const uint2*>(stg + OFF_META)[tid];
-    const uint4 dsc = *reinterpret_cast<const uint4*>(stg + OFF_DESC);
-    const uint32_t cam = meta.x;
-    double xv[4 * (DC / 4) + 4];
-    if (cam != PAD_CAM) {
-      const double* xc = a.xpad + (size_t)cam * XS;
 #pragma unroll
-      for (int m = 0; m < DC / 4; ++m) ldg256(xc + 4 * m, xv[4 * m], xv[4 * m + 1], xv[4 * m + 2], xv[4 * m + 3]);
-      if (DC % 4 == 1) xv[4 * (DC / 4)] = __ldg(xc + 4 * (DC / 4));
-      else if (DC % 4 == 2) { const double2 v = __ldg(reinterpret_cast<const double2*>(xc + 4 * (DC / 4))); xv[4 * (DC / 4)] = v.x; xv[4 * (DC / 4) + 1] = v.y; }
-      else if (DC % 4 == 3) ldg256(xc + 4 * (DC / 4), xv[4 * (DC / 4)], xv[4 * (DC / 4) + 1], xv[4 * (DC / 4) + 2], xv[4 * (DC / 4) + 3]);
-    }
-    double jall[NP];
-    {
-      const double2* j2 = reinterpret_cast<const double2*>(stg) + tid;
+  for (int d = 16; d >= 1; d >>= 1) {
 #pragma unroll
-      for (int m = 0; m < NP / 2; ++m) { const double2 v = j2[m * TILE]; jall[2 * m] = v.x; jall[2 * m + 1] = v.y; }
-    }
-    uint32_t* ssegc = reinterpret_cast<uint32_t*>(segtab + (size_t)par * (4 * TILE + 2 * CSEG_LD));
-    uint16_t* ssegb = reinterpret_cast<uint16_t*>(ssegc + TILE);
-    ssegc[tid] = reinterpret_cast<const uint32_t*>(stg + OFF_SEGC)[tid];
-    if (tid < CSEG_LD / 2) reinterpret_cast<uint32_t*>(ssegb)[tid] = reinterpret_cast<const uint32_t*>(stg + OFF_SEGB)[tid];
-    mbar_arrive(smem_u32(bars + ST_FULL + s));    // stage free as soon as all 256 copies are out
-    if (tid == 0 && i + ST_STAGES < nmine) {      // ... and refilled at once, while this group computes
-      mbar_wait(smem_u32(bars + ST_FULL + s), use & 1);
-      issue(i + ST_STAGES);
-    }
-    const uint32_t pt0 = dsc.x, npt = dsc.y, nseg = dsc.z;
-    if ((uint32_t)tid < npt) {
-      const uint32_t lp = pt0 + tid;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) cp_async8(&shinv[k][tid], a.hinv + (size_t)k * a.npl + lp);
-      cp_async4(&sptm[tid], a.cpt_meta + lp);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    const double* jc = jall;
-    const double* jp = jall + 2 * DC;
-    // ---- phase 1 ----
-    {
-      double u[3] = {0.0, 0.0, 0.0};
-      if (cam != PAD_CAM) {
-        double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < DC; ++k) { a0 = fma(jc[k], xv[k], a0); a1 = fma(jc[DC + k], xv[k], a1); }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) u[k] = fma(jp[k], a0, jp[3 + k] * a1);
-      }
-      const uint32_t key = cam != PAD_CAM ? (meta.y & 0xFFu) : 0xFFFFu;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t ok = __shfl_down_sync(0xffffffffu, key, d);
-        const bool hit = lane + d < 32 && ok == key;
-        if (!__any_sync(0xffffffffu, hit)) break;
-        const double o0 = __shfl_down_sync(0xffffffffu, u[0], d), o1 = __shfl_down_sync(0xffffffffu, u[1], d), o2 = __shfl_down_sync(0xffffffffu, u[2], d);
-        if (hit) { u[0] += o0; u[1] += o1; u[2] += o2; }
-      }
-      const uint32_t pk = __shfl_up_sync(0xffffffffu, key, 1);
-      if ((lane == 0 || pk != key) && cam != PAD_CAM) { su[0][tid] = u[0]; su[1][tid] = u[1]; su[2][tid] = u[2]; }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    group_bar(1 + grp);
-    // ---- phase 2: per landmark ----
-    if ((uint32_t)tid < npt) {
-      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-      const uint32_t mm = sptm[tid], off = mm & 0xFFFFu, cnt = mm >> 16;
-      if (cnt) {
-        t0 = su[0][off]; t1 = su[1][off]; t2 = su[2][off];
-        for (uint32_t b = (off & ~31u) + 32; b < off + cnt; b += 32) { t0 += su[0][b]; t1 += su[1][b]; t2 += su[2][b]; }
-      }
-      const double h00 = shinv[0][tid], h01 = shinv[1][tid], h02 = shinv[2][tid], h11 = shinv[3][tid], h12 = shinv[4][tid], h22 = shinv[5][tid];
-      sw[0][tid] = h00 * t0 + h01 * t1 + h02 * t2;
-      sw[1][tid] = h01 * t0 + h11 * t1 + h12 * t2;
-      sw[2][tid] = h02 * t0 + h12 * t1 + h22 * t2;
-    }
-    group_bar(1 + grp);
-    // ---- phase 3 ----
-    if (cam != PAD_CAM) {
-      const uint32_t spt = meta.y & 0xFFu, pos = (meta.y >> 8) & 0xFFu;
-      const double w0 = sw[0][spt], w1 = sw[1][spt], w2 = sw[2][spt];
-      const double b0 = fma(jp[0], w0, fma(jp[1], w1, jp[2] * w2));
-      const double b1 = fma(jp[3], w0, fma(jp[4], w1, jp[5] * w2));
-#pragma unroll
-      for (int k = 0; k < DC; ++k) cs[k * LD + pos] = -fma(jc[k], b0, jc[DC + k] * b1);
-    }
-    group_bar(1 + grp);
-    // ---- phase 4 ----
-    constexpr int KG = 3, NGK = (DC + KG - 1) / KG;
-    for (uint32_t idx = tid; idx < nseg * NGK; idx += TILE) {
-      const uint32_t sgi = idx / NGK, kg = (idx - sgi * NGK) * KG;
-      const uint32_t b = ssegb[sgi], e = ssegb[sgi + 1];
-      double* yr = a.y + (size_t)ssegc[sgi] * DC + kg;
-      const double* c0 = cs + kg * LD;
-      double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-      for (uint32_t q = b; q < e; ++q) {
-        v0 += c0[q];
-        if (kg + 1 < DC) v1 += c0[LD + q];
-        if (kg + 2 < DC) v2 += c0[2 * LD + q];
-      }
-      if (a.debug == 1 && v0 != 1.2345e300) continue;
-      red_add(yr, v0);
-      if (kg + 1 < DC) red_add(yr + 1, v1);
-      if (kg + 2 < DC) red_add(yr + 2, v2);
-    }
-    // no trailing barrier: su is separate from cs, the segment tables alternate between two buffers, and every
-    // other shared array is rewritten only behind the next chunk's barriers
+    for (int k = 0; k < DC; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
   }
+  double mine = 0.0;
+#pragma unroll
+  for (int k = 0; k < DC; ++k) if (lane == k) mine = acc[k];
+  if (lane < DC) y[(size_t)cam * DC + lane] += mine;
 }
 
 // y = (H_cc + lambda I) x on the block diagonal (first half of apply_schur_operator_fast); sign = -1 with
@@ -1566,113 +939,110 @@ static SchurArgs make_schur_args(Ctx& c, const double* x, double* y, int check_d
   a.J = c.J.p; a.hinv = c.hinv.p; a.gp = c.gp.p; a.x = x; a.y = y; a.step_pt = c.step_pt.p;
   a.npl = c.npl; a.check_done = check_done; a.st = c.state.p;
   a.ntiles = c.ntiles;
-  a.chunk_desc = c.chunk_desc.p; a.cslot_meta = c.cslot_meta.p; a.cseg_cam = c.cseg_cam.p; a.cseg_begin = c.cseg_begin.p; a.cpt_meta = c.cpt_meta.p; a.xpad = c.xpad.p;
+  a.chunk_desc = c.chunk_desc.p; a.cslot_meta = c.cslot_meta.p; a.cpt_meta = c.cpt_meta.p; a.xpad = c.xpad.p;
+  a.cslot_widx = c.cslot_widx.p; a.win_desc = c.win_desc.p; a.range_win0 = c.range_win0.p; a.win_cams = c.win_cams.p;
+  a.window = c.mv_window; a.partial = c.det_partial.p;
   const char* dbg = getenv("APEX_DEBUG_MATVEC");
   a.debug = dbg ? atoi(dbg) : 0;
-  if (a.debug == 2 && c.ntiles % 4099u == 0) a.debug = 0;
   return a;
 }
 
-__global__ void pad_x_kernel(const double* __restrict__ x, double* __restrict__ xpad, uint32_t ncam, int dc, int xs, const DevState* st, int check_done);
-
-static int operator_impl() {
-  // development switch: 0 = chunk kernel (default), 1 = "tile" (first generation, per-observation reductions),
-  // 2 = "tileseg" (tile kernel with segment aggregation), 3 = "pp" (persistent ping-pong kernel, private y:
-  // bitwise reproducible), 4 = "red" (ping-pong kernel without the private y)
-  const char* f = getenv("APEX_MATVEC_IMPL");
-  if (!f) return getenv("APEX_DETERMINISTIC") ? 3 : 0;
-  if (!strcmp(f, "tile")) return 1;
-  if (!strcmp(f, "tileseg")) return 2;
-  if (!strcmp(f, "pp")) return 3;
-  if (!strcmp(f, "red")) return 4;
-  return 0;
+// Shared memory of the chunk kernel for a window of W cameras (the largest of the three modes), and the CTAs per SM it
+// leaves. problem_upload calls this before it builds the layout: the number of ranges is the number of resident CTAs.
+template <int DC>
+static apex_status configure_dc(Ctx& c) {
+  const uint32_t W = mv_window_cameras(DC);
+  const size_t bytes = chunk_smem_bytes<DC, MODE_RHS>(W);   // RHS / BACKSUB carry the landmark gradients as well
+  c.mv_window = W;
+  APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_chunk_kernel<DC, MODE_MATVEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_chunk_kernel<DC, MODE_MATVEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_chunk_kernel<DC, MODE_RHS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_chunk_kernel<DC, MODE_RHS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_chunk_kernel<DC, MODE_BACKSUB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  int per_sm = 0;
+  APEX_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, schur_chunk_kernel<DC, MODE_MATVEC, true>, TILE, chunk_smem_bytes<DC, MODE_MATVEC>(W)));
+  if (per_sm < 1) { c.err = "chunk kernel does not fit on an SM"; return APEX_ERR_UNSUPPORTED; }
+  c.mv_ctas_per_sm = (uint32_t)per_sm;
+  if (const char* e = getenv("APEX_MV_CTAS_PER_SM")) c.mv_ctas_per_sm = (uint32_t)std::max(1, std::min(atoi(e), per_sm));
+  return APEX_OK;
+}
+apex_status schur_configure(Ctx& c) {
+  switch (c.dc) {
+    case 6: return configure_dc<6>(c);
+    case 9: return configure_dc<9>(c);
+    case 10: return configure_dc<10>(c);
+    case 11: return configure_dc<11>(c);
+    case 12: return configure_dc<12>(c);
+    case 14: return configure_dc<14>(c);
+    case 15: return configure_dc<15>(c);
+    default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
+  }
 }
 
 template <int DC>
-static void launch_tiles_dc(Ctx& c, int mode, const SchurArgs& a0) {
-  const int impl = operator_impl();
+static apex_status launch_tiles_dc(Ctx& c, int mode, const SchurArgs& a0) {
   SchurArgs a = a0;
-  if (impl == 1 || impl == 2) {  // whole tile list through the tile kernel
-    if (!c.ntiles) return;
+  const bool det = c.mv_det && mode != MODE_BACKSUB;
+  // normal chunks through the chunk kernel, landmarks with more than 256 observations through the tile kernel
+  if (c.nnormal_chunks) {
+    const unsigned grid = c.mv_nranges;
+    const uint32_t W = c.mv_window;
     switch (mode) {
       case MODE_MATVEC:
-        if (impl == 1) schur_tile_kernel<DC, MODE_MATVEC, false><<<c.ntiles, TILE, 0, c.stream>>>(a);
-        else schur_tile_kernel<DC, MODE_MATVEC, true><<<c.ntiles, TILE, 0, c.stream>>>(a);
+        if (det) schur_chunk_kernel<DC, MODE_MATVEC, true><<<grid, TILE, chunk_smem_bytes<DC, MODE_MATVEC>(W), c.stream>>>(a);
+        else schur_chunk_kernel<DC, MODE_MATVEC, false><<<grid, TILE, chunk_smem_bytes<DC, MODE_MATVEC>(W), c.stream>>>(a);
         break;
       case MODE_RHS:
-        if (impl == 1) schur_tile_kernel<DC, MODE_RHS, false><<<c.ntiles, TILE, 0, c.stream>>>(a);
-        else schur_tile_kernel<DC, MODE_RHS, true><<<c.ntiles, TILE, 0, c.stream>>>(a);
+        if (det) schur_chunk_kernel<DC, MODE_RHS, true><<<grid, TILE, chunk_smem_bytes<DC, MODE_RHS>(W), c.stream>>>(a);
+        else schur_chunk_kernel<DC, MODE_RHS, false><<<grid, TILE, chunk_smem_bytes<DC, MODE_RHS>(W), c.stream>>>(a);
         break;
-      default: schur_tile_kernel<DC, MODE_BACKSUB, false><<<c.ntiles, TILE, 0, c.stream>>>(a); break;
+      default: schur_chunk_kernel<DC, MODE_BACKSUB, false><<<grid, TILE, chunk_smem_bytes<DC, MODE_BACKSUB>(W), c.stream>>>(a); break;
     }
     c.launches++;
-    return;
-  }
-  // normal chunks through the chunk kernel, landmarks with more than 256 observations through the tile kernel
-  const char* stream_env = getenv("APEX_MV_STREAM");
-  const int stream_on = stream_env ? atoi(stream_env) : 0;  // opt-in: measured slower than the chunk kernel
-  if (c.nnormal_chunks && mode == MODE_MATVEC && stream_on && (DC == 6 || DC == 9) && !(c.mv_W && c.mv_ngroups)) {
-    // operator: persistent stream kernel (TMA-fed ring, producer warp + 3 consumer groups)
-    constexpr int SDC = (DC == 6 || DC == 9) ? DC : 9;
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(schur_stream_kernel<SDC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem_bytes<SDC>()); attr_set = true; }
-    const unsigned grid = std::min<uint32_t>((uint32_t)c.num_sms, c.nnormal_chunks);
-    schur_stream_kernel<SDC><<<grid, ST_THREADS, st_smem_bytes<SDC>(), c.stream>>>(a, c.nnormal_chunks);
-    c.launches++;
-  } else if (c.nnormal_chunks && mode == MODE_MATVEC && c.mv_W && c.mv_ngroups) {
-    // operator: window kernel (groups of chunks, camera window of x and y in shared memory)
-    const char* ye = getenv("APEX_MV_YWIN");
-    const uint32_t ywin = ye ? (uint32_t)atoi(ye) : 1u;
-    const size_t smem = mv_window_base_bytes(DC) + (ywin ? 2 : 1) * sizeof(double) * (size_t)c.mv_W * DC;
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(schur_window_kernel<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 76800); attr_set = true; }
-    WinArgs wa{c.grp_win0.p, c.mv_ngroups, c.mv_G, c.mv_W, c.ncam, ywin};
-    schur_window_kernel<DC><<<c.mv_ngroups, TILE, smem, c.stream>>>(a, wa, c.nnormal_chunks);
-    c.launches++;
-  } else if (c.nnormal_chunks) {
-    switch (mode) {
-      case MODE_MATVEC: schur_chunk_kernel<DC, MODE_MATVEC><<<c.nnormal_chunks, TILE, 0, c.stream>>>(a, c.nnormal_chunks); break;
-      case MODE_RHS: schur_chunk_kernel<DC, MODE_RHS><<<c.nnormal_chunks, TILE, 0, c.stream>>>(a, c.nnormal_chunks); break;
-      default: schur_chunk_kernel<DC, MODE_BACKSUB><<<c.nnormal_chunks, TILE, 0, c.stream>>>(a, c.nnormal_chunks); break;
+    if (det) {
+      det_reduce_kernel<DC><<<(c.ncam + 7) / 8, 256, 0, c.stream>>>(c.det_partial.p, c.cam_row_start.p, c.cam_rows.p, a.y, c.state.p, c.ncam, a.check_done);
+      c.launches++;
     }
-    c.launches++;
   }
   if (c.ngiant) {
     a.tiles = c.giant_tiles.p;
     a.ntiles = c.ngiant;
     a.debug = 0;
     switch (mode) {
-      case MODE_MATVEC: schur_tile_kernel<DC, MODE_MATVEC, false><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
-      case MODE_RHS: schur_tile_kernel<DC, MODE_RHS, false><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
-      default: schur_tile_kernel<DC, MODE_BACKSUB, false><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
+      case MODE_MATVEC: schur_tile_kernel<DC, MODE_MATVEC><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
+      case MODE_RHS: schur_tile_kernel<DC, MODE_RHS><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
+      default: schur_tile_kernel<DC, MODE_BACKSUB><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
     }
     c.launches++;
   }
+  return APEX_OK;
 }
 
 apex_status launch_schur_tiles(Ctx& c, int mode, const double* x, double* y, int check_done, bool xpad_ready) {
   if (c.ntiles == 0) return APEX_OK;
-  if (mode != MODE_RHS && !xpad_ready && operator_impl() != 1 && operator_impl() != 2) {  // the chunk kernel gathers x from the padded copy
+  if (mode != MODE_RHS && !xpad_ready) {  // the chunk kernel gathers x from the padded copy
     const int xs = xpad_stride(c.dc);
     pad_x_kernel<<<(c.ncam * xs + 255) / 256, 256, 0, c.stream>>>(x, c.xpad.p, c.ncam, c.dc, xs, c.state.p, check_done);
     c.launches++;
   }
   SchurArgs a = make_schur_args(c, x, y, check_done);
+  apex_status st;
   switch (c.dc) {
-    case 6: launch_tiles_dc<6>(c, mode, a); break;
-    case 9: launch_tiles_dc<9>(c, mode, a); break;
-    case 10: launch_tiles_dc<10>(c, mode, a); break;
-    case 12: launch_tiles_dc<12>(c, mode, a); break;
-    case 11: launch_tiles_dc<11>(c, mode, a); break;
-    case 14: launch_tiles_dc<14>(c, mode, a); break;
-    case 15: launch_tiles_dc<15>(c, mode, a); break;
+    case 6: st = launch_tiles_dc<6>(c, mode, a); break;
+    case 9: st = launch_tiles_dc<9>(c, mode, a); break;
+    case 10: st = launch_tiles_dc<10>(c, mode, a); break;
+    case 12: st = launch_tiles_dc<12>(c, mode, a); break;
+    case 11: st = launch_tiles_dc<11>(c, mode, a); break;
+    case 14: st = launch_tiles_dc<14>(c, mode, a); break;
+    case 15: st = launch_tiles_dc<15>(c, mode, a); break;
     default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
   }
+  APEX_TRY(st);
   APEX_CUDA_TRY(c, cudaGetLastError());
   return APEX_OK;
 }
 
-// y = (H_cc + lambda I) x on rank 0, 0 elsewhere (the all-reduce that follows the tile kernel adds it once)
+// y = (H_cc + lambda I) x on rank 0, 0 elsewhere (the all-reduce that follows the chunk kernel adds it once)
 apex_status launch_hcc_apply(Ctx& c, const double* x, double* y, int check_done) {
   const uint32_t n = c.ncam * c.dc;
   if (c.rank == 0) {
@@ -1685,76 +1055,15 @@ apex_status launch_hcc_apply(Ctx& c, const double* x, double* y, int check_done)
   return APEX_OK;
 }
 
-// the tile kernel restricted to the landmarks with more than 256 observations
-static apex_status launch_giant_tiles(Ctx& c, const double* x, double* y, int check_done) {
-  if (c.ngiant == 0) return APEX_OK;
-  SchurArgs a = make_schur_args(c, x, y, check_done);
-  a.tiles = c.giant_tiles.p;
-  a.ntiles = c.ngiant;
-  a.debug = 0;
-  switch (c.dc) {
-    case 6: schur_tile_kernel<6, MODE_MATVEC><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
-    case 9: schur_tile_kernel<9, MODE_MATVEC><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
-    case 10: schur_tile_kernel<10, MODE_MATVEC><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
-    case 12: schur_tile_kernel<12, MODE_MATVEC><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
-    case 11: schur_tile_kernel<11, MODE_MATVEC><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
-    case 14: schur_tile_kernel<14, MODE_MATVEC><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
-    case 15: schur_tile_kernel<15, MODE_MATVEC><<<c.ngiant, TILE, 0, c.stream>>>(a); break;
-    default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
-  }
-  c.launches++;
-  APEX_CUDA_TRY(c, cudaGetLastError());
-  return APEX_OK;
-}
-
-// this rank's part of y = S x, before the all-reduce: persistent kernel (+ finalize) + long-track tiles
+// this rank's part of y = S x, before the all-reduce: y = (H_cc + lambda I) x, then the chunk / tile kernels add
+// -H_cp Hpp^-1 H_cp^T x to it
 apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_done, bool xpad_ready) {
-  const uint32_t n = c.ncam * c.dc;
-  const int impl = operator_impl();
-  if (impl <= 2) {  // y = (H_cc + lambda I) x, then the chunk / tile kernels reduce -H_cp Hpp^-1 H_cp^T x into it
-    APEX_TRY(launch_hcc_apply(c, x, y, check_done));
-    cudaEvent_t* evp = (c.prof && c.ntiles) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
-    if (evp) cudaEventRecord(evp[0], c.stream);
-    apex_status st = launch_schur_tiles(c, MODE_MATVEC, x, y, check_done, xpad_ready);
-    if (evp) cudaEventRecord(evp[1], c.stream);
-    return st;
-  }
-  const int xs = xpad_stride(c.dc);
-  if (!xpad_ready) {
-    pad_x_kernel<<<(c.ncam * xs + 255) / 256, 256, 0, c.stream>>>(x, c.xpad.p, c.ncam, c.dc, xs, c.state.p, check_done);
-    c.launches++;
-  }
-  const uint32_t npairs = c.npairs;  // chunk pairs (2s, 2s+1)
-  size_t need = 0;
-  switch (c.dc) {
-    case 6: need = pp_smem_bytes<6>(n, true); break;
-    case 9: need = pp_smem_bytes<9>(n, true); break;
-    case 10: need = pp_smem_bytes<10>(n, true); break;
-    case 12: need = pp_smem_bytes<12>(n, true); break;
-    case 11: need = pp_smem_bytes<11>(n, true); break;
-    case 14: need = pp_smem_bytes<14>(n, true); break;
-    case 15: need = pp_smem_bytes<15>(n, true); break;
-    default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
-  }
-  const bool priv = need <= (size_t)MV_SMEM_MAX && impl != 4;
-  const unsigned grid = (unsigned)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)c.num_sms, npairs));
-  PpArgs a{c.chunk_desc.p, c.cslot_meta.p, c.cpt_meta.p, c.cseg_cam.p, c.cseg_begin.p, c.J.p, c.hinv.p, c.gp.p, c.xpad.p, y, c.ypart.p,
-           n, c.npl, npairs, c.nnormal_chunks, check_done, c.state.p};
-  if (!priv) APEX_TRY(launch_hcc_apply(c, x, y, check_done));  // y starts as (H_cc + lambda I) x; the kernel reduces into it
-  cudaEvent_t* evp = (c.prof && npairs) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
+  APEX_TRY(launch_hcc_apply(c, x, y, check_done));
+  cudaEvent_t* evp = (c.prof && c.ntiles) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
   if (evp) cudaEventRecord(evp[0], c.stream);
-  if (npairs) {
-    APEX_TRY(launch_pingpong<MODE_MATVEC>(c, a, priv, grid));
-    c.launches++;
-  }
+  apex_status st = launch_schur_tiles(c, MODE_MATVEC, x, y, check_done, xpad_ready);
   if (evp) cudaEventRecord(evp[1], c.stream);
-  if (priv) {
-    schur_finalize_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(c.hcc.p, x, c.ypart.p, npairs ? grid : 0u, y, c.state.p, n, c.dc,
-                                                                 c.rank == 0 ? 1 : 0, check_done);
-    c.launches++;
-  }
-  APEX_CUDA_TRY(c, cudaGetLastError());
-  return launch_giant_tiles(c, x, y, check_done);
+  return st;
 }
 
 // full operator y = S x (all ranks end with the same y)
@@ -1767,28 +1076,6 @@ apex_status schur_operator(Ctx& c, const double* x, double* y, int check_done, b
 // b = -g_c - H_cp Hpp^-1 (-g_p)   (implicit_schur.rs:863-880 with g = -J^T r; explicit_schur.rs:928-977)
 apex_status launch_reduced_gradient(Ctx& c, double* b) {
   const uint32_t n = c.ncam * c.dc;
-  if (operator_impl() == 3 && c.ngiant == 0 && c.npairs) {
-    // deterministic route: the ping-pong kernel in RHS mode (w_p = Hpp^-1 (-g_p)), private copies summed in CTA order
-    size_t need = 0;
-    switch (c.dc) {
-      case 6: need = pp_smem_bytes<6>(n, true); break;
-      case 9: need = pp_smem_bytes<9>(n, true); break;
-      case 10: need = pp_smem_bytes<10>(n, true); break;
-      case 12: need = pp_smem_bytes<12>(n, true); break;
-      default: need = pp_smem_bytes<14>(n, true); break;
-    }
-    if (need <= (size_t)MV_SMEM_MAX) {
-      const unsigned grid = (unsigned)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)c.num_sms, c.npairs));
-      PpArgs a{c.chunk_desc.p, c.cslot_meta.p, c.cpt_meta.p, c.cseg_cam.p, c.cseg_begin.p, c.J.p, c.hinv.p, c.gp.p, c.xpad.p, b, c.ypart.p,
-               n, c.npl, c.npairs, c.nnormal_chunks, 0, c.state.p};
-      APEX_TRY(launch_pingpong<MODE_RHS>(c, a, true, grid));
-      schur_finalize_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(c.hcc.p, c.gc, c.ypart.p, grid, b, c.state.p, n, c.dc, c.rank == 0 ? 2 : 0, 0);
-      c.launches += 2;
-      APEX_CUDA_TRY(c, cudaGetLastError());
-      APEX_TRY(allreduce_sum(c, b, n));
-      return APEX_OK;
-    }
-  }
   if (c.rank == 0) {
     negate_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(c.gc, b, n);
     c.launches++;
@@ -1817,7 +1104,7 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
   // launch: the inner loop is launch-bound on small shards (8 GPUs: ~35 us of kernels per iteration).
   const int BATCH = 10;
   int it_count = 0;  // iteration index within this solve: selects the half of the peer buffer (BATCH is even)
-  const int tail_cluster = operator_impl() == 0 ? pcg_tail_cluster(c) : 0;
+  const int tail_cluster = pcg_tail_cluster(c);
   if (tail_cluster && cg_max_it > 0) {  // first direction p = z and y0 = (H_cc + lambda I) p into half 0; later ones come from the tail
     const int xs = xpad_stride(c.dc);
     double* y0 = c.p2p_ok ? c.arbuf.p : c.vy.p;
@@ -1829,7 +1116,7 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
     const int xs = xpad_stride(c.dc);
     const unsigned gp = (n + PCG_THREADS - 1) / PCG_THREADS, gu = (c.ncam + PCG_CAMS - 1) / PCG_CAMS;
     const int par = it_count++ & 1;
-    if (operator_impl() == 0 && tail_cluster) {
+    if (tail_cluster) {
       // fused path: [operator, tail] per iteration; the first direction / y0 were produced before the loop
       double* y0 = c.p2p_ok ? c.arbuf.p + (size_t)par * n : c.vy.p;
       cudaEvent_t* evp = (c.prof && c.ntiles) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
@@ -1848,34 +1135,29 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
       APEX_TRY(launch_pcg_tail(c, ta, tail_cluster));
       return APEX_OK;
     }
-    if (operator_impl() == 0) {
-      // chunk-kernel path: p / y0 in one kernel, the operator reduces into y0, then (ranks > 1) the peer-memory
-      // all-reduce fused with p.Ap, or NCCL when peer mapping is unavailable
-      double* y0 = c.p2p_ok ? c.arbuf.p + (size_t)par * n : c.vy.p;
-      pcg_dir_hcc_kernel<<<gu, PCG_THREADS, 0, s>>>(c.vz.p, c.vp.p, c.xpad.p, c.hcc.p, y0, c.state.p, c.ncam, c.dc, xs, c.rank == 0 ? 1 : 0);
-      c.launches++;
-      cudaEvent_t* evp = (c.prof && c.ntiles) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
-      if (evp) cudaEventRecord(evp[0], s);
-      APEX_TRY(launch_schur_tiles(c, MODE_MATVEC, c.vp.p, y0, 1, true));
-      if (evp) cudaEventRecord(evp[1], s);
-      if (c.p2p_ok) {
-        ar_reduce_pap_kernel<<<gp, PCG_THREADS, 0, s>>>(c.d_peer_buf.p, c.d_peer_flags.p, c.arflags.p, par, c.nranks, c.rank, c.vp.p, c.vy.p,
-                                                        c.red_scratch.p, c.state.p, n);
-      } else {
-        APEX_TRY(allreduce_sum(c, c.vy.p, n));
-        pcg_pap_kernel<<<gp, PCG_THREADS, 0, s>>>(c.vp.p, c.vy.p, c.red_scratch.p, c.state.p, n);
-      }
+    {
+    // chunk-kernel path: p / y0 in one kernel, the operator reduces into y0, then (ranks > 1) the peer-memory
+    // all-reduce fused with p.Ap, or NCCL when peer mapping is unavailable
+    double* y0 = c.p2p_ok ? c.arbuf.p + (size_t)par * n : c.vy.p;
+    pcg_dir_hcc_kernel<<<gu, PCG_THREADS, 0, s>>>(c.vz.p, c.vp.p, c.xpad.p, c.hcc.p, y0, c.state.p, c.ncam, c.dc, xs, c.rank == 0 ? 1 : 0);
+    c.launches++;
+    cudaEvent_t* evp = (c.prof && c.ntiles) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
+    if (evp) cudaEventRecord(evp[0], s);
+    APEX_TRY(launch_schur_tiles(c, MODE_MATVEC, c.vp.p, y0, 1, true));
+    if (evp) cudaEventRecord(evp[1], s);
+    if (c.p2p_ok) {
+      ar_reduce_pap_kernel<<<gp, PCG_THREADS, 0, s>>>(c.d_peer_buf.p, c.d_peer_flags.p, c.arflags.p, par, c.nranks, c.rank, c.vp.p, c.vy.p,
+                                                      c.red_scratch.p, c.state.p, n);
     } else {
-      pcg_dir_kernel<<<(c.ncam * xs + PCG_THREADS - 1) / PCG_THREADS, PCG_THREADS, 0, s>>>(c.vz.p, c.vp.p, c.xpad.p, c.state.p, c.ncam, c.dc, xs);
-      c.launches++;
-      APEX_TRY(schur_operator(c, c.vp.p, c.vy.p, 1, true));
+      APEX_TRY(allreduce_sum(c, c.vy.p, n));
       pcg_pap_kernel<<<gp, PCG_THREADS, 0, s>>>(c.vp.p, c.vy.p, c.red_scratch.p, c.state.p, n);
+    }
     }
     pcg_update_kernel<<<gu, PCG_THREADS, 0, s>>>(c.vy.p, c.pinv.p, c.vp.p, c.step_cam.p, c.vr.p, c.vz.p, c.red_scratch.p, c.state.p, c.ncam, c.dc, c.K);
     c.launches += 2;
     return APEX_OK;
   };
-  const bool use_graph = !c.prof && operator_impl() == 0 && !getenv("APEX_NO_GRAPH") && cg_max_it > 0;
+  const bool use_graph = !c.prof && !getenv("APEX_NO_GRAPH") && cg_max_it > 0;
   if (use_graph && !c.pcg_graph_exec) {
     const int64_t l0 = c.launches;
     cudaGraph_t graph = nullptr;

@@ -139,6 +139,13 @@ enum apex_optimization_status {
 
 typedef struct apex_ctx apex_ctx; /* opaque */
 
+/* One LossFunction instance: enum apex_loss + its parameters (params[] meaning per id above). */
+typedef struct apex_loss_spec {
+  int32_t loss_id;
+  int32_t reserved;
+  double params[4];
+} apex_loss_spec;
+
 typedef struct apex_ctx_desc {
   int32_t device;           /* CUDA device ordinal                                       */
   int32_t rank;             /* 0..nranks-1                                               */
@@ -168,7 +175,7 @@ typedef struct apex_problem_desc {
   const uint32_t* obs_cam;  /* [nobs] camera index of each residual block, insertion order */
   const uint32_t* obs_pt;   /* [nobs] landmark index                                     */
   const double* obs_uv;     /* [nobs][2] measured pixel                                  */
-  int32_t loss_id;          /* enum apex_loss, uniform over blocks                       */
+  int32_t loss_id;          /* enum apex_loss, uniform over blocks (unless obs_loss is given) */
   int32_t reserved0;
   double loss_params[4];
   /* Problem::fix_variable (src/core/problem.rs:609-616): bit d set = tangent DOF d is fixed
@@ -176,6 +183,13 @@ typedef struct apex_problem_desc {
   const uint8_t* pose_fixed;  /* [ncam] bits 0..5                                        */
   const uint16_t* intr_fixed; /* [ncam] bits 0..K-1                                      */
   const uint8_t* pt_fixed;    /* [npts] bits 0..2                                        */
+  /* Per-block loss functions: every ResidualBlock owns its own Option<Box<dyn LossFunction>>
+   * (src/core/residual_block.rs:97-123). obs_loss[o] indexes loss_table (at most 256 distinct instances - the shim
+   * de-duplicates boxes by type and parameters); NULL = every block uses loss_id / loss_params above. */
+  const uint8_t* obs_loss;          /* [nobs] index into loss_table, or NULL                */
+  const apex_loss_spec* loss_table; /* [n_losses]                                           */
+  int32_t n_losses;
+  int32_t reserved1;
 } apex_problem_desc;
 
 /* LevenbergMarquardtConfig (src/optimizer/levenberg_marquardt.rs:213-317), field for field, plus the
@@ -363,7 +377,7 @@ apex_status apex_shard_info(uint32_t npts, uint64_t nobs, const uint32_t* obs_pt
                             uint32_t* block, uint32_t* npts_local, uint64_t* nobs_local);
 
 /* Host-only: build the static observation layout apex_problem_upload would build for (nranks, rank) - landmark
- * shard, 256-slot point-major chunks, per-chunk camera segments, camera-major work items - check its invariants
+ * shard, 256-slot point-major chunks with their camera-sorted lane order, camera-major work items - check its invariants
  * and report its size. Needs no device. */
 typedef struct apex_layout_stats {
   uint32_t shard_block, npts_local; /* block-cyclic ownership: block size, landmarks owned by the rank */
@@ -371,15 +385,15 @@ typedef struct apex_layout_stats {
   uint32_t ntiles, nlong_tiles;    /* tiles; tiles holding one landmark with more than 256 observations */
   uint32_t nchunks, nnormal_chunks;
   uint32_t ncam_items, max_segments_per_chunk;
-  uint64_t nsegments;              /* distinct (chunk, camera) pairs                              */
+  uint64_t nsegments;              /* (chunk, camera) runs of the camera-sorted lanes, cut at warp boundaries */
   uint64_t slots_used;             /* = nobs_local when consistent                                 */
   int32_t consistent;              /* 1 when every structural invariant holds                      */
   int32_t reserved;
   double build_ms;
-  /* camera windows of the Schur operator's chunk groups (window kernel): chunks per group, cameras per window
-   * (0 = windows disabled), groups, and how many local observations fall inside their group's window */
-  uint32_t mv_group, mv_window, mv_ngroups, reserved2;
-  uint64_t nobs_in_window;
+  /* work distribution of the Schur operator's chunk kernel: ranges (one per resident CTA; 444 here), cameras per window,
+   * windows, and the sum of the windows' camera counts (rows flushed per operator application) */
+  uint32_t mv_ranges, mv_window, mv_nwindows, reserved2;
+  uint64_t mv_rows;
 } apex_layout_stats;
 apex_status apex_layout_stats_compute(const apex_problem_desc* desc, int32_t nranks, int32_t rank, apex_layout_stats* out);
 

@@ -185,7 +185,8 @@ def assert_lm_parity(rg, tg, ro, to, floor, strict=False):
 CONVERGED = dict(cg_it=3000, cg_tolerance=1e-12)
 LM_CASES = [
     ("bal_selfcal_explicit", dict(model=F.CAM_BAL, self_cal=True), F.SCHUR_EXPLICIT, {}),
-    ("bal_selfcal_implicit", dict(model=F.CAM_BAL, self_cal=True), F.SCHUR_IMPLICIT, {}),           # the headline mode, reference preset (cg 200 / 1e-6)
+    # the headline mode with the reference preset (cg 200 / 1e-6): 4 LM iterations - from the 5th on the oracle's own twins differ by 1.6e-6
+    ("bal_selfcal_implicit", dict(model=F.CAM_BAL, self_cal=True), F.SCHUR_IMPLICIT, dict(max_it=3)),
     ("bal_selfcal_explicit_pcg", dict(model=F.CAM_BAL, self_cal=True), F.SCHUR_EXPLICIT_PCG, CONVERGED),
     ("bal_ba_implicit_strict", dict(model=F.CAM_BAL, self_cal=False), F.SCHUR_IMPLICIT, {}),
     ("bal_ba_explicit", dict(model=F.CAM_BAL, self_cal=False), F.SCHUR_EXPLICIT, {}),
@@ -254,10 +255,10 @@ def test_lm_teacher_forced_final_sixtyfourth():
 
 
 @pytest.mark.parametrize("shape", ["kb2000", "ds2000"])
-def test_lm_teacher_forced_c4_twentieth(shape):
+def test_lm_teacher_forced_c4_tenth(shape):
     """configs[3] (C4: Kannala-Brandt / double-sphere, self-calibration, Cauchy, explicit Schur + dense FP64 Cholesky) at
-    1/20 scale: 100 cameras (dc = 14 / 12), 50k landmarks, 300k observations."""
-    teacher_forced(synth.make_shape(shape, scale=0.05), F.SCHUR_EXPLICIT, n_it=3)
+    1/10 scale: 200 cameras (dc = 14 / 12), 100k landmarks, ~490k observations."""
+    teacher_forced(synth.make_shape(shape, scale=0.1), F.SCHUR_EXPLICIT, n_it=3)
 
 
 def test_lm_ladybug49_shape_explicit():
@@ -352,75 +353,27 @@ def test_fixed_variables_are_zeroed_at_update_only():
 
 
 def test_deterministic_operator_is_bitwise_reproducible(monkeypatch):
-    """APEX_DETERMINISTIC selects the persistent ping-pong kernel that keeps y in a CTA-private shared-memory copy
-    and sums the copies in CTA order: same bits on every run, and an LM trajectory that repeats exactly."""
+    """APEX_DETERMINISTIC=1: the chunk kernel writes per-chunk partial sums (one row per camera run) instead of reducing into L2,
+    and a second kernel adds each camera's rows in a fixed order: same bits on every run, an LM trajectory that repeats exactly,
+    and the same operator as the default path to summation-order level. Several camera models (dc = 6, 9, 14, 15)."""
     monkeypatch.setenv("APEX_DETERMINISTIC", "1")
+    for kw in (dict(), dict(self_cal=False), dict(model=F.CAM_KANNALA_BRANDT, loss=(F.LOSS_CAUCHY, 1.0)), dict(model=F.CAM_RADTAN)):
+        prob = small_problem(ncam=30, npts=2000, track=5.0, **kw)
+        g, o = pair(prob)
+        g.linearize(1e-3); o.linearize(1e-3)
+        x = np.random.default_rng(4).standard_normal(prob.ncam * prob.dc)
+        y1 = g.schur_matvec(x)
+        assert np.array_equal(g.schur_matvec(x), y1) and np.array_equal(g.schur_matvec(x), y1)
+        assert relerr(y1, o.schur_matvec(x)) < 1e-11
     prob = small_problem(ncam=30, npts=2000, track=5.0)
-    g, o = pair(prob)
-    g.linearize(1e-3); o.linearize(1e-3)
-    x = np.random.default_rng(4).standard_normal(prob.ncam * prob.dc)
-    y1 = g.schur_matvec(x)
-    assert np.array_equal(g.schur_matvec(x), y1) and np.array_equal(g.schur_matvec(x), y1)
-    assert relerr(y1, o.schur_matvec(x)) < 1e-11
     g1, g2 = GpuContext().upload(prob), GpuContext().upload(prob)
     (r1, t1), (r2, t2) = run_lm(g1, F.SCHUR_IMPLICIT, max_it=4), run_lm(g2, F.SCHUR_IMPLICIT, max_it=4)
     assert [a.cost for a in t1] == [b.cost for b in t2] and r1.linear_iterations == r2.linear_iterations
-
-
-@pytest.mark.parametrize("impl", ["red", "tile", "tileseg", "pp"])
-def test_operator_fallback_paths(impl, monkeypatch):
-    """The operator paths used when the camera vector does not fit next to the staging buffers in shared memory
-    (e.g. Final-13682: 985 KB): per-(segment, dof) reductions into global memory ("red"), and the first-generation
-    tile kernel ("tile"). Selected here with the development switch APEX_MATVEC_IMPL."""
-    monkeypatch.setenv("APEX_MATVEC_IMPL", impl)
-    prob = small_problem(ncam=40, npts=3000, track=5.0)
-    g, o = pair(prob)
-    g.linearize(1e-3); o.linearize(1e-3)
-    x = np.random.default_rng(9).standard_normal(prob.ncam * prob.dc)
-    assert relerr(g.schur_matvec(x), o.schur_matvec(x)) < 1e-10
-    sg = g.solve_augmented(F.SCHUR_IMPLICIT, 1e-3, cg_max_iterations=500, cg_tolerance=1e-12)
-    so = o.solve_augmented(F.SCHUR_IMPLICIT, 1e-3, cg_max_iterations=500, cg_tolerance=1e-12)
-    assert relerr(sg[0], so[0]) < 1e-3 and relerr(sg[1], so[1]) < 1e-3  # cond(S) ~1e10: solver-accuracy level agreement
-
-
-@pytest.mark.parametrize("window,group,dc_case", [("320", "8", "selfcal"), ("16", "2", "selfcal"), ("24", "3", "ba"), ("0", "8", "selfcal")])
-def test_operator_window_kernel(window, group, dc_case, monkeypatch):
-    """Window kernel of the operator: camera window of x / y in shared memory per group of chunks. Narrow windows force
-    the out-of-window route (global gather + direct reductions) and the wrap-around of the window on the camera ring;
-    window 0 selects the chunk kernel. Every setting must give the oracle's S x."""
-    monkeypatch.setenv("APEX_MV_WINDOW", window)
-    monkeypatch.setenv("APEX_MV_GROUP", group)
-    prob = small_problem(ncam=90, npts=6000, track=5.0, self_cal=dc_case == "selfcal", window_frac=0.08, seed=21)
-    g, o = pair(prob)
-    g.linearize(1e-3); o.linearize(1e-3)
-    rng = np.random.default_rng(12)
-    for _ in range(2):
-        x = rng.standard_normal(prob.ncam * prob.dc)
-        assert relerr(g.schur_matvec(x), o.schur_matvec(x)) < 1e-11
-    sg = g.solve_augmented(F.SCHUR_IMPLICIT, 1e-3, cg_max_iterations=500, cg_tolerance=1e-12)
-    so = o.solve_augmented(F.SCHUR_IMPLICIT, 1e-3, cg_max_iterations=500, cg_tolerance=1e-12)
-    assert relerr(sg[0], so[0]) < 1e-3 and relerr(sg[1], so[1]) < 1e-3
-
-
-@pytest.mark.parametrize("self_cal", [True, False])
-def test_operator_stream_kernel_ring_reuse(self_cal, monkeypatch):
-    """Stream kernel (persistent CTA per SM, TMA-fed 2-stage ring shared by three consumer groups): enough chunks that
-    every CTA goes round the ring several times (~1 400 chunks on 148 SMs), dc = 9 and dc = 6. Must give the oracle's
-    S x and agree with the chunk kernel (APEX_MV_STREAM=0) to summation-order level."""
-    monkeypatch.setenv("APEX_MV_STREAM", "1")
-    prob = small_problem(ncam=300, npts=70000, track=5.0, self_cal=self_cal, seed=33)
-    g, o = pair(prob)
-    g.linearize(1e-3); o.linearize(1e-3)
-    rng = np.random.default_rng(5)
-    xs = [rng.standard_normal(prob.ncam * prob.dc) for _ in range(2)]
-    ys = [g.schur_matvec(x) for x in xs]
-    for x, y in zip(xs, ys):
-        assert relerr(y, o.schur_matvec(x)) < 1e-11
-    monkeypatch.setenv("APEX_MV_STREAM", "0")
-    g2 = GpuContext().upload(prob)
-    g2.linearize(1e-3)
-    for x, y in zip(xs, ys):
-        assert relerr(g2.schur_matvec(x), y) < 1e-12
+    assert all(np.array_equal(a, b) for a, b in zip(g1.params_download(), g2.params_download()))
+    monkeypatch.delenv("APEX_DETERMINISTIC")
+    g3 = GpuContext().upload(prob)
+    g3.linearize(1e-3); g1.linearize(1e-3)
+    assert relerr(g3.schur_matvec(x), g1.schur_matvec(x)) < 1e-12
 
 
 @pytest.mark.parametrize("tail", ["16", "4", "0"])
@@ -591,8 +544,8 @@ def test_schur_operator_properties_trafalgar_full():
 
 def test_operator_and_lm_properties_venice_full():
     """The bench workload (configs[2], Venice-1778 shape at full size: 1 778 cams / 994k pts / 5.3 M obs) is too large for
-    the oracle; checked through size-independent properties: S symmetric, positive definite, linear; the three operator
-    kernels (chunk / window / stream) agree; the reduced system solved by PCG satisfies S dx = b to the CG tolerance
+    the oracle; checked through size-independent properties: S symmetric, positive definite, linear; the default and the
+    deterministic operator agree; the reduced system solved by PCG satisfies S dx = b to the CG tolerance
     (recomputed with the operator); an accepted LM step lowers the cost, and the cost the LM loop reports equals the cost
     kernel's value at the downloaded parameters."""
     import os
@@ -607,16 +560,15 @@ def test_operator_and_lm_properties_venice_full():
     assert abs(y @ Sx - x @ Sy) <= 1e-10 * abs(y @ Sx), "symmetry"
     assert x @ Sx > 0 and y @ Sy > 0, "positive definite"
     assert relerr(g.schur_matvec(2.0 * x - 3.0 * y), 2.0 * Sx - 3.0 * Sy) < 1e-11, "linearity"
-    for env in ({"APEX_MV_STREAM": "1"}, {"APEX_MV_WINDOW": "320"}):
-        os.environ.update(env)
-        try:
-            g2 = GpuContext().upload(prob)
-            g2.linearize(lam)
-            assert relerr(g2.schur_matvec(x), Sx) < 1e-12, env
-            g2.close()
-        finally:
-            for k in env:
-                del os.environ[k]
+    os.environ["APEX_DETERMINISTIC"] = "1"   # the deterministic two-pass operator agrees with the default one
+    try:
+        g2 = GpuContext().upload(prob)
+        g2.linearize(lam)
+        y2 = g2.schur_matvec(x)
+        assert relerr(y2, Sx) < 1e-12 and np.array_equal(g2.schur_matvec(x), y2)
+        g2.close()
+    finally:
+        del os.environ["APEX_DETERMINISTIC"]
     cfg = g.default_config(True)
     cfg.schur_variant = F.SCHUR_IMPLICIT
     cfg.max_iterations = 6

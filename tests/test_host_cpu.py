@@ -87,7 +87,7 @@ def test_block_cyclic_sharding_covers_and_balances():
 def test_layout_invariants_incl_long_tracks_and_unobserved_landmarks():
     """The static structure apex_problem_upload builds (host-only entry point): every observation in exactly one slot,
     landmarks never straddle a 256-slot chunk, a landmark with more than 256 observations gets its own chunks, and the
-    per-chunk camera segments are consistent - for every rank of a sharded problem."""
+    camera-sorted lane order of every chunk is consistent - for every rank of a sharded problem."""
     prob = synth.make_problem(300, 3000, 6.0, seed=11)
     keep = (prob.obs_pt != 3) & (prob.obs_pt >= 2)        # landmarks 0,1 unobserved; landmark 3 rebuilt below
     extra = np.arange(prob.ncam, dtype=np.uint32)          # landmark 3 seen by all 300 cameras (> one chunk)
@@ -112,26 +112,17 @@ def test_layout_invariants_incl_long_tracks_and_unobserved_landmarks():
     assert e.value.status == F.ERR_INVALID_INPUT
 
 
-def test_operator_camera_windows(monkeypatch):
-    """Window kernel structure (host side): groups of APEX_MV_GROUP chunks, each with the run of W consecutive cameras
-    (modulo ncam) holding most of its observations. Ring-local tracks => nearly everything inside; ncam <= W => all."""
-    assert layout_stats(synth.make_problem(40, 2000, 4.0, seed=5)).mv_window == 0      # off unless asked for
-    monkeypatch.setenv("APEX_MV_WINDOW", "100000")                                      # "as wide as three CTAs per SM allow"
-    small = synth.make_problem(40, 2000, 4.0, seed=5)
-    s = layout_stats(small)
-    assert s.consistent == 1 and s.mv_window == 40 and s.nobs_in_window == s.nobs_local
-    assert s.mv_group == 8 and s.mv_ngroups == (s.nnormal_chunks + 7) // 8
-    big = synth.make_problem(1500, 30000, 5.0, seed=6)        # window_frac 0.04 -> sigma 60 cameras
-    sb = layout_stats(big)
-    assert sb.consistent == 1 and sb.mv_window == 320          # dc = 9: (76800 - base) / 144 rounded down to 8
-    assert sb.nobs_in_window / sb.nobs_local > 0.95
-    # the window wraps around the ring: a brute-force best window per group must not beat the builder
-    monkeypatch.setenv("APEX_MV_WINDOW", "64")
-    monkeypatch.setenv("APEX_MV_GROUP", "2")
-    s64 = layout_stats(big)
-    assert (s64.mv_window, s64.mv_group) == (64, 2) and 0.2 < s64.nobs_in_window / s64.nobs_local < 0.9
-    monkeypatch.setenv("APEX_MV_WINDOW", "0")
-    assert layout_stats(big).mv_window == 0                     # windows off -> chunk kernel
+def test_camera_sorted_lane_order_of_the_chunks():
+    """Split slot order of the chunk kernel (host side): inside every normal chunk the camera-sorted lanes are a permutation of
+    the point-major lanes, cameras ascend along them, warp-segments count the runs of one camera cut at warp boundaries and
+    every warp-segment appears exactly once in its camera's list (layout self-check); a chunk of ~256 observations of
+    ring-local tracks sees far fewer cameras than observations."""
+    s = layout_stats(synth.make_problem(1500, 30000, 5.0, seed=6))
+    assert s.consistent == 1 and s.nnormal_chunks > 400
+    assert s.max_segments_per_chunk <= 256
+    assert s.nnormal_chunks * 8 <= s.nsegments < 0.9 * s.nobs_local     # >= one segment per warp, fewer than observations
+    tiny = layout_stats(synth.make_problem(3, 40, 2.5, seed=2))          # 3 cameras: every warp holds at most 3 runs
+    assert tiny.consistent == 1 and tiny.nsegments <= 3 * 8 * tiny.nnormal_chunks
 
 
 def test_generator_is_deterministic_and_bal_shaped():
