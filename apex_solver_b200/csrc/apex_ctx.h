@@ -77,7 +77,6 @@ struct WinDesc {
 };
 constexpr uint32_t CONT_BIT = 1u << 24, CONT_FIRST_BIT = 1u << 25;
 constexpr int CONT_LEN_SHIFT = 26;
-constexpr int MV_DEFAULT_CTAS = 444;  // host-only layout statistics: 3 CTAs on each of 148 SMs
 // cameras per window: 32 KB of shared memory for the window's rows of y, never below one chunk's worth of cameras
 inline uint32_t mv_window_cameras(int dc) {
   if (const char* e = getenv("APEX_MV_WINDOW")) { const int w = atoi(e); if (w >= TILE) return (uint32_t)std::min(w, 4096); }
@@ -233,6 +232,7 @@ struct Ctx {
   uint32_t mv_nranges = 0, mv_window = 0, mv_ctas_per_sm = 0;   // chunk kernel: ranges (= CTAs), cameras per window
   uint32_t mv_nwindows = 0;
   uint64_t mv_nrows = 0;           // sum of the windows' camera counts (rows of det_partial)
+  bool mv_staged = false;          // operator kernel prefetches the Jacobian planes through a TMA-fed shared-memory stage
   bool mv_det = false;             // flush the windows as per-window partial rows + fixed-order second pass (bitwise reproducible)
   size_t nslots = 0;
   HostVec<uint64_t> slot_obs;      // slot -> caller's observation index (UINT64_MAX for padding)
@@ -363,6 +363,7 @@ apex_status schur_operator(Ctx& c, const double* x, double* y, int check_done, b
 apex_status schur_operator_local(Ctx& c, const double* x, double* y, int check_done, bool xpad_ready = false);  // this rank's part
 apex_status launch_reduced_gradient(Ctx& c, double* b);
 apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol);
+void schur_plan(int dc, uint32_t& W, bool& staged);  // host-only: window width / Jacobian staging for a camera block of dc
 apex_status schur_configure(Ctx& c);  // at upload: window width and CTAs per SM of the chunk kernel for the context's dc
 // explicit.cu
 apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol);

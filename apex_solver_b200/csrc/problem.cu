@@ -405,8 +405,9 @@ apex_status layout_stats(const apex_problem_desc* d, int nranks, int rank, apex_
   HostLayout L;
   const int K = model_intr_dim(d->camera_model);
   const int dc = 6 + ((d->opt_flags & APEX_OPT_INTRINSIC) ? K : 0);
-  const uint32_t W = mv_window_cameras(dc);
-  build_layout(d, nranks, rank, L, MV_DEFAULT_CTAS, W, true);
+  uint32_t W; bool staged;
+  schur_plan(dc, W, staged);
+  build_layout(d, nranks, rank, L, (staged ? 2 : 3) * 148, W, true);
   out->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   out->shard_block = SHARD_BLOCK; out->npts_local = L.npl; out->nobs_local = L.nobs_local;
   out->ntiles = (uint32_t)L.tiles.size(); out->nlong_tiles = (uint32_t)L.giant_tiles.size();

@@ -233,30 +233,109 @@ __device__ __forceinline__ void gather_x_padded(const double* __restrict__ xc, d
   else if (REM == 3) ldg256(xc + 4 * N4, xv[4 * N4], xv[4 * N4 + 1], xv[4 * N4 + 2], xv[4 * N4 + 3]);
 }
 
-// shared memory of the chunk kernel in doubles: work arrays, continuation sums, window rows
+// shared memory of the chunk kernel in doubles: [Jacobian stage] work arrays, continuation sums, mbarrier, window rows
 template <int MODE>
 __host__ __device__ constexpr int chunk_work_doubles() { return 2 * TILE + 3 * TILE + (3 + 6 + (MODE == MODE_MATVEC ? 0 : 3)) * MAX_TILE_PTS + MAX_TILE_PTS / 2; }
-template <int DC, int MODE>
-__host__ __device__ constexpr size_t chunk_smem_bytes(uint32_t W) { return sizeof(double) * ((size_t)chunk_work_doubles<MODE>() + 8 * DC + (size_t)W * DC); }
+template <int DC, bool STAGED>
+__host__ __device__ constexpr int chunk_stage_doubles() { return STAGED ? 2 * (DC + 3) * TILE : 0; }
+template <int DC, int MODE, bool STAGED>
+__host__ __device__ constexpr size_t chunk_smem_bytes(uint32_t W) {
+  return sizeof(double) * ((size_t)chunk_stage_doubles<DC, STAGED>() + chunk_work_doubles<MODE>() + 8 * DC + 2 + (size_t)W * DC);
+}
 
-template <int DC, int MODE, bool DET>
-__global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a) {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait on a phase parity: ~2 s of polling, then trap (an error the host sees) instead of a hang
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int DC, int MODE, bool DET, bool STAGED>
+__global__ void __launch_bounds__(TILE, STAGED ? 2 : 3) schur_chunk_kernel(SchurArgs a) {
   constexpr int NPAIR = DC + 3;
   constexpr int XS = xpad_stride(DC);
   constexpr int NGP = MODE == MODE_MATVEC ? 0 : 3;
   constexpr int WORK = chunk_work_doubles<MODE>();
+  constexpr int STG = chunk_stage_doubles<DC, STAGED>();
+  constexpr uint32_t JBYTES = 16u * NPAIR * TILE;   // one chunk's Jacobian planes, contiguous in HBM
   if (a.check_done && a.st->pcg_done) return;
-  extern __shared__ double sm[];
-  double (*sab)[TILE] = reinterpret_cast<double (*)[TILE]>(sm);                         // [2] a: camera-sorted -> point-major; later b: back
-  double (*su)[TILE] = reinterpret_cast<double (*)[TILE]>(sm + 2 * TILE);                // [3]
-  double (*sw)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(sm + 5 * TILE);               // [3]
-  double (*shinv)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(sm + 5 * TILE + 3 * MAX_TILE_PTS);  // [6]
-  double (*sgp)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(sm + 5 * TILE + 9 * MAX_TILE_PTS);    // [3] (not MATVEC)
-  uint32_t* sptm = reinterpret_cast<uint32_t*>(sm + 5 * TILE + (9 + NGP) * MAX_TILE_PTS);
-  double (*scont)[DC] = reinterpret_cast<double (*)[DC]>(sm + WORK);                     // [8] run sums of continuation lanes, per warp
-  double* ywin = sm + WORK + 8 * DC;                                                     // [window][DC]
+  extern __shared__ __align__(128) double sm[];
+  double* wk = sm + STG;
+  double (*sab)[TILE] = reinterpret_cast<double (*)[TILE]>(wk);                         // [2] a: camera-sorted -> point-major; later b: back
+  double (*su)[TILE] = reinterpret_cast<double (*)[TILE]>(wk + 2 * TILE);                // [3]
+  double (*sw)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(wk + 5 * TILE);               // [3]
+  double (*shinv)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(wk + 5 * TILE + 3 * MAX_TILE_PTS);  // [6]
+  double (*sgp)[MAX_TILE_PTS] = reinterpret_cast<double (*)[MAX_TILE_PTS]>(wk + 5 * TILE + 9 * MAX_TILE_PTS);    // [3] (not MATVEC)
+  uint32_t* sptm = reinterpret_cast<uint32_t*>(wk + 5 * TILE + (9 + NGP) * MAX_TILE_PTS);
+  double (*scont)[DC] = reinterpret_cast<double (*)[DC]>(wk + WORK);                     // [8] run sums of continuation lanes, per warp
+  const uint32_t bar = smem_u32(wk + WORK + 8 * DC);                                     // mbarrier of the Jacobian stage
+  double* ywin = wk + WORK + 8 * DC + 2;                                                 // [window][DC]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t win_end = __ldg(a.range_win0 + blockIdx.x + 1);
+  const uint32_t win_begin = __ldg(a.range_win0 + blockIdx.x), win_end = __ldg(a.range_win0 + blockIdx.x + 1);
+  if (win_begin == win_end) return;
+  // the chunks of a range are contiguous: everything a chunk needs is requested ONE CHUNK AHEAD -
+  //   Jacobian planes  STAGED: one cp.async.bulk (TMA) of the chunk's 16*(dc+3)*256 contiguous bytes into the stage, armed on an
+  //                    mbarrier; the threads move their 12 x 16 bytes from the stage into registers, and as soon as every
+  //                    thread has done so (the first barrier of the chunk) the stage is refilled with the next chunk, so the
+  //                    copy runs under the whole computation of the current chunk. Registers are the second pipeline stage.
+  //                    !STAGED: plain 128-bit loads at the top of the chunk's iteration (exposed once per chunk and CTA).
+  //   slot metadata, window indices, chunk descriptor: registers, loaded during the previous chunk
+  //   landmark inverses / gradients / run tables: cp.async into shared memory once the previous chunk's phase 2 has read its own
+  const uint32_t chunk_first = __ldg(&a.win_desc[win_begin].chunk_begin), chunk_last = __ldg(&a.win_desc[win_end - 1].chunk_end);
+  auto issue_stage = [&](uint32_t chunk) {
+    mbar_expect_tx(bar, JBYTES);
+    bulk_g2s(smem_u32(sm), a.J + (size_t)chunk * 2 * NPAIR * TILE, JBYTES, bar);
+  };
+  auto issue_landmarks = [&](const uint2& dsc) {   // {first landmark, landmarks} of the chunk
+    if ((uint32_t)tid < dsc.y) {
+      const uint32_t lp = dsc.x + tid;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) cp_async8(&shinv[k][tid], a.hinv + (size_t)k * a.npl + lp);
+      if (MODE != MODE_MATVEC) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) cp_async8(&sgp[k][tid], a.gp + (size_t)k * a.npl + lp);
+      }
+      cp_async4(&sptm[tid], a.cpt_meta + lp);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (STAGED) {
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) issue_stage(chunk_first);
+  }
+  uint2 meta_n = __ldg(a.cslot_meta + (size_t)chunk_first * TILE + tid);
+  uint32_t widx_n = __ldg(a.cslot_widx + (size_t)chunk_first * TILE + tid);
+  // (only the fields that are used: a 128-bit load of the descriptor leaves a dead destination register that the compiler
+  // reuses at once, and the write-after-write wait on it exposed the prefetch's whole latency)
+  uint2 dsc_n = __ldg(reinterpret_cast<const uint2*>(a.chunk_desc + chunk_first));
+  uint32_t nobs_n = __ldg(&a.chunk_desc[chunk_first].nobs);
+  issue_landmarks(dsc_n);
+  // x of the chunk's cameras, gathered one chunk ahead as well (into the registers the camera half of the previous chunk frees)
+  double xv[4 * (DC / 4) + 4];
+  // (only with the two-CTA register budget of the staged kernel; at 80 registers the gather stays at its use)
+  auto prefetch_x = [&](uint32_t cam) {
+    if (STAGED && MODE != MODE_RHS && cam != PAD_CAM) gather_x_padded<DC>(a.xpad + (size_t)cam * XS, xv);
+  };
+  prefetch_x(meta_n.x);
+  uint32_t stage_parity = 0;
   uint32_t fix_flags = 0, fix_widx = 0;   // pending continuation sums of the previous chunk (this warp's lane 0)
   // add the parked continuation sums of the previous chunk: lanes 0..DC-1 of the warp whose lane 0 started the chain
   auto fix_up = [&]() {
@@ -268,58 +347,76 @@ __global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a) {
     }
     fix_flags = 0;
   };
-  for (uint32_t win = __ldg(a.range_win0 + blockIdx.x); win < win_end; ++win) {
+  for (uint32_t win = win_begin; win < win_end; ++win) {
     const uint4 wd = __ldg(reinterpret_cast<const uint4*>(a.win_desc + win));   // chunk_begin, chunk_end, cam0, ncams
     if (MODE != MODE_BACKSUB) {
       for (uint32_t i = tid; i < wd.w * DC; i += TILE) ywin[i] = 0.0;   // ordered before the first read-modify-write by the chunk's barriers
     }
     for (uint32_t chunk = wd.x; chunk < wd.y; ++chunk) {
-      // ---- all global reads up front ----
-      const uint2 meta = __ldg(a.cslot_meta + (size_t)chunk * TILE + tid);
-      const uint32_t widx = __ldg(a.cslot_widx + (size_t)chunk * TILE + tid);
-      const uint4 dsc = __ldg(reinterpret_cast<const uint4*>(a.chunk_desc + chunk));
+      const uint2 meta = meta_n;
+      const uint32_t widx = widx_n;
+      const uint2 dsc = dsc_n;
+      const uint32_t nobs = nobs_n;
+      const bool has_next = chunk + 1 < chunk_last;
+      if (has_next) {
+        meta_n = __ldg(a.cslot_meta + (size_t)(chunk + 1) * TILE + tid);
+        widx_n = __ldg(a.cslot_widx + (size_t)(chunk + 1) * TILE + tid);
+        dsc_n = __ldg(reinterpret_cast<const uint2*>(a.chunk_desc + chunk + 1));
+        nobs_n = __ldg(&a.chunk_desc[chunk + 1].nobs);
+      }
       double jc[2 * DC], jp[6];
-      {
+      if (STAGED) {
+        if (MODE != MODE_BACKSUB) fix_up();
+        mbar_wait(bar, stage_parity);
+        stage_parity ^= 1u;
+        // landmark half first: shared-memory loads of a warp return in order, and phase 1 consumes the camera half before the
+        // barrier that lets the next copy overwrite the stage
+        const double2* p = reinterpret_cast<const double2*>(sm) + tid;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) { const double2 v = p[(DC + m) * TILE]; jp[2 * m] = v.x; jp[2 * m + 1] = v.y; }
+#pragma unroll
+        for (int m = 0; m < DC; ++m) { const double2 v = p[m * TILE]; jc[2 * m] = v.x; jc[2 * m + 1] = v.y; }
+      } else {
         const double2* p = reinterpret_cast<const double2*>(a.J) + (size_t)chunk * NPAIR * TILE + tid;
 #pragma unroll
         for (int m = 0; m < DC; ++m) { const double2 v = ld_stream2(p + (size_t)m * TILE); jc[2 * m] = v.x; jc[2 * m + 1] = v.y; }
 #pragma unroll
         for (int m = 0; m < 3; ++m) { const double2 v = ld_stream2(p + (size_t)(DC + m) * TILE); jp[2 * m] = v.x; jp[2 * m + 1] = v.y; }
+        if (MODE != MODE_BACKSUB) fix_up();   // while the loads are in flight
       }
-      const uint32_t pt0 = dsc.x, npt = dsc.y, nobs = dsc.w;
-      if ((uint32_t)tid < npt) {
-        const uint32_t lp = pt0 + tid;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) cp_async8(&shinv[k][tid], a.hinv + (size_t)k * a.npl + lp);
-        if (MODE != MODE_MATVEC) {
-#pragma unroll
-          for (int k = 0; k < 3; ++k) cp_async8(&sgp[k][tid], a.gp + (size_t)k * a.npl + lp);
-        }
-        cp_async4(&sptm[tid], a.cpt_meta + lp);
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (MODE != MODE_BACKSUB) fix_up();   // while the loads are in flight
+      const uint32_t npt = dsc.y;
       const uint32_t camc = meta.x;                 // camera of camera-sorted slot tid (PAD_CAM behind the chunk's observations)
       const bool pt_valid = (uint32_t)tid < nobs;   // point-major slot tid holds an observation
       // ---- phase 1: a_o = Jc_o x_c on the camera-sorted lanes, sent to the observation's point-major slot ----
       if (MODE != MODE_RHS) {
+        double a0 = 0.0, a1 = 0.0;
         if (camc != PAD_CAM) {
-          double xv[4 * (DC / 4) + 4];
-          gather_x_padded<DC>(a.xpad + (size_t)camc * XS, xv);
-          double a0 = 0.0, a1 = 0.0;
+          if (!STAGED) gather_x_padded<DC>(a.xpad + (size_t)camc * XS, xv);
+          double a0b = 0.0, a1b = 0.0;   // two chains per sum: four independent DFMA chains instead of two of length dc
 #pragma unroll
-          for (int k = 0; k < DC; ++k) { a0 = fma(jc[k], xv[k], a0); a1 = fma(jc[DC + k], xv[k], a1); }
+          for (int k = 0; k + 1 < DC; k += 2) {
+            a0 = fma(jc[k], xv[k], a0); a1 = fma(jc[DC + k], xv[k], a1);
+            a0b = fma(jc[k + 1], xv[k + 1], a0b); a1b = fma(jc[DC + k + 1], xv[k + 1], a1b);
+          }
+          if (DC & 1) { a0 = fma(jc[DC - 1], xv[DC - 1], a0); a1 = fma(jc[2 * DC - 1], xv[DC - 1], a1); }
+          a0 += a0b; a1 += a1b;
           const uint32_t ipos = (meta.y >> 16) & 0xFFu;
           sab[0][ipos] = a0; sab[1][ipos] = a1;
+        } else if (STAGED) {
+          // padding lanes consume their (zero) camera half as well: every thread has its stage reads behind it at the barrier
+#pragma unroll
+          for (int k = 0; k < 2 * DC; ++k) a0 += jc[k];
+          if (a0 != 0.0) sab[0][0] = a0;   // never taken
         }
         __syncthreads();
+        if (STAGED && tid == 0 && has_next) issue_stage(chunk + 1);
         // u_o = Jp_o^T a_o; the sum over a landmark's observations (consecutive lanes) starts as a segmented warp-shuffle
         // reduction; only the first lane of each run writes its partial to shared memory
         double u[3] = {0.0, 0.0, 0.0};
         if (pt_valid) {
-          const double a0 = sab[0][tid], a1 = sab[1][tid];
+          const double b0 = sab[0][tid], b1 = sab[1][tid];
 #pragma unroll
-          for (int k = 0; k < 3; ++k) u[k] = fma(jp[k], a0, jp[3 + k] * a1);
+          for (int k = 0; k < 3; ++k) u[k] = fma(jp[k], b0, jp[3 + k] * b1);
         }
         const uint32_t key = pt_valid ? (meta.y & 0xFFu) : 0xFFFFu;  // chunk-local landmark
 #pragma unroll
@@ -335,37 +432,44 @@ __global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a) {
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
-      // ---- phase 2: per landmark ----
-      if ((uint32_t)tid < npt) {
-        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-        if (MODE != MODE_RHS) {
+      if (MODE == MODE_BACKSUB) {
+        // ---- back-substitution: one thread per landmark, dp = Hpp^-1 (-g_p - t_p) ----
+        if ((uint32_t)tid < npt) {
+          double t0 = 0.0, t1 = 0.0, t2 = 0.0;
           const uint32_t mm = sptm[tid], off = mm & 0xFFFFu, cnt = mm >> 16;
           if (cnt) {
             t0 = su[0][off]; t1 = su[1][off]; t2 = su[2][off];
             for (uint32_t b = (off & ~31u) + 32; b < off + cnt; b += 32) { t0 += su[0][b]; t1 += su[1][b]; t2 += su[2][b]; }  // runs continuing in the next warps
           }
+          const double v0 = -sgp[0][tid] - t0, v1 = -sgp[1][tid] - t1, v2 = -sgp[2][tid] - t2;
+          const double h00 = shinv[0][tid], h01 = shinv[1][tid], h02 = shinv[2][tid], h11 = shinv[3][tid], h12 = shinv[4][tid], h22 = shinv[5][tid];
+          const size_t lp = dsc.x + tid;
+          a.step_pt[3 * lp] = h00 * v0 + h01 * v1 + h02 * v2;
+          a.step_pt[3 * lp + 1] = h01 * v0 + h11 * v1 + h12 * v2;
+          a.step_pt[3 * lp + 2] = h02 * v0 + h12 * v1 + h22 * v2;
         }
-        double v0, v1, v2;
-        if (MODE == MODE_MATVEC) { v0 = t0; v1 = t1; v2 = t2; }
-        else if (MODE == MODE_RHS) { v0 = -sgp[0][tid]; v1 = -sgp[1][tid]; v2 = -sgp[2][tid]; }
-        else { v0 = -sgp[0][tid] - t0; v1 = -sgp[1][tid] - t1; v2 = -sgp[2][tid] - t2; }
-        const double h00 = shinv[0][tid], h01 = shinv[1][tid], h02 = shinv[2][tid], h11 = shinv[3][tid], h12 = shinv[4][tid], h22 = shinv[5][tid];
-        const double w0 = h00 * v0 + h01 * v1 + h02 * v2, w1 = h01 * v0 + h11 * v1 + h12 * v2, w2 = h02 * v0 + h12 * v1 + h22 * v2;
-        if (MODE == MODE_BACKSUB) {
-          const size_t lp = pt0 + tid;
-          a.step_pt[3 * lp] = w0; a.step_pt[3 * lp + 1] = w1; a.step_pt[3 * lp + 2] = w2;
-        } else { sw[0][tid] = w0; sw[1][tid] = w1; sw[2][tid] = w2; }
+        __syncthreads();
+        if (has_next) { issue_landmarks(dsc_n); prefetch_x(meta_n.x); }
+        continue;
       }
-      __syncthreads();
-      if (MODE == MODE_BACKSUB) continue;   // (the barrier above also protects the work arrays against the next chunk's loads)
-      // ---- phase 3: b_o = Jp_o w_p on the point-major lanes, sent to the observation's camera-sorted slot ----
+      // ---- phases 2 + 3 on the point-major lanes: every observation computes its landmark's w_p = Hpp_p^-1 t_p itself (the lanes
+      // of a run read the same shared-memory words: broadcasts) instead of waiting for one thread per landmark behind another
+      // barrier; b_o = Jp_o w_p goes to the observation's camera-sorted slot ----
       if (pt_valid) {
         const uint32_t spt = meta.y & 0xFFu, pos = (meta.y >> 8) & 0xFFu;
-        const double w0 = sw[0][spt], w1 = sw[1][spt], w2 = sw[2][spt];
+        double v0, v1, v2;
+        if (MODE == MODE_MATVEC) {
+          const uint32_t mm = sptm[spt], off = mm & 0xFFFFu, cnt = mm >> 16;
+          v0 = su[0][off]; v1 = su[1][off]; v2 = su[2][off];
+          for (uint32_t b = (off & ~31u) + 32; b < off + cnt; b += 32) { v0 += su[0][b]; v1 += su[1][b]; v2 += su[2][b]; }  // runs continuing in the next warps
+        } else { v0 = -sgp[0][spt]; v1 = -sgp[1][spt]; v2 = -sgp[2][spt]; }
+        const double h00 = shinv[0][spt], h01 = shinv[1][spt], h02 = shinv[2][spt], h11 = shinv[3][spt], h12 = shinv[4][spt], h22 = shinv[5][spt];
+        const double w0 = h00 * v0 + h01 * v1 + h02 * v2, w1 = h01 * v0 + h11 * v1 + h12 * v2, w2 = h02 * v0 + h12 * v1 + h22 * v2;
         sab[0][pos] = fma(jp[0], w0, fma(jp[1], w1, jp[2] * w2));
         sab[1][pos] = fma(jp[3], w0, fma(jp[4], w1, jp[5] * w2));
       }
       __syncthreads();
+      if (has_next) issue_landmarks(dsc_n);   // every lane has read this chunk's landmark data
       // ---- phase 4: c_o = -Jc_o^T b_o, summed over each camera's run of lanes; the first lane of a run owns the result ----
       double cv[DC];
       if (camc != PAD_CAM) {
@@ -376,6 +480,7 @@ __global__ void __launch_bounds__(TILE, 3) schur_chunk_kernel(SchurArgs a) {
 #pragma unroll
         for (int k = 0; k < DC; ++k) cv[k] = 0.0;
       }
+      if (has_next) prefetch_x(meta_n.x);   // the camera half is dead from here on
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const uint32_t ok = __shfl_down_sync(0xffffffffu, camc, d);
@@ -947,20 +1052,57 @@ static SchurArgs make_schur_args(Ctx& c, const double* x, double* y, int check_d
   return a;
 }
 
-// Shared memory of the chunk kernel for a window of W cameras (the largest of the three modes), and the CTAs per SM it
-// leaves. problem_upload calls this before it builds the layout: the number of ranges is the number of resident CTAs.
+// Shared memory of the chunk kernel for a window of W cameras, and the CTAs per SM it leaves. problem_upload calls this
+// before it builds the layout: the number of ranges is the number of resident CTAs of the operator (MATVEC) instantiation.
+// The Jacobian stage (TMA prefetch) is used by the operator when a chunk's planes + the window leave room for two CTAs per SM
+// (dc <= 10); the once-per-iteration modes (reduced gradient, back-substitution) always load directly.
+template <int DC>
+constexpr bool mv_staged_fits() { return chunk_smem_bytes<DC, MODE_MATVEC, true>(TILE) <= 110 * 1024; }
+static bool mv_staged_wanted() { const char* e = getenv("APEX_MV_STAGED"); return !e || atoi(e) != 0; }
+
+template <int DC>
+static void plan_dc(uint32_t& W, bool& staged) {
+  W = mv_window_cameras(DC);
+  staged = mv_staged_fits<DC>() && mv_staged_wanted();
+  if (staged) {  // stage + window fill what two CTAs per SM can have (113 KB each): dc = 9 -> 616 cameras
+    if (!getenv("APEX_MV_WINDOW")) W = 2048;
+    while (W > (uint32_t)TILE && chunk_smem_bytes<DC, MODE_MATVEC, true>(W) > 113 * 1024) W -= 8;
+  }
+}
+// host-only: window width / staging the chunk kernel will use for a camera block of dc (also for apex_layout_stats_compute)
+void schur_plan(int dc, uint32_t& W, bool& staged) {
+  switch (dc) {
+    case 6: plan_dc<6>(W, staged); break;
+    case 9: plan_dc<9>(W, staged); break;
+    case 10: plan_dc<10>(W, staged); break;
+    case 11: plan_dc<11>(W, staged); break;
+    case 12: plan_dc<12>(W, staged); break;
+    case 14: plan_dc<14>(W, staged); break;
+    case 15: plan_dc<15>(W, staged); break;
+    default: W = mv_window_cameras(dc); staged = false;
+  }
+}
+
 template <int DC>
 static apex_status configure_dc(Ctx& c) {
-  const uint32_t W = mv_window_cameras(DC);
-  const size_t bytes = chunk_smem_bytes<DC, MODE_RHS>(W);   // RHS / BACKSUB carry the landmark gradients as well
+  uint32_t W;
+  plan_dc<DC>(W, c.mv_staged);
   c.mv_window = W;
-  APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_chunk_kernel<DC, MODE_MATVEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_chunk_kernel<DC, MODE_MATVEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_chunk_kernel<DC, MODE_RHS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_chunk_kernel<DC, MODE_RHS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  APEX_CUDA_TRY(c, cudaFuncSetAttribute(schur_chunk_kernel<DC, MODE_BACKSUB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  auto set = [&](const void* fn, size_t bytes) { return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); };
+  APEX_CUDA_TRY(c, set((const void*)schur_chunk_kernel<DC, MODE_MATVEC, true, false>, chunk_smem_bytes<DC, MODE_MATVEC, false>(W)));
+  APEX_CUDA_TRY(c, set((const void*)schur_chunk_kernel<DC, MODE_MATVEC, false, false>, chunk_smem_bytes<DC, MODE_MATVEC, false>(W)));
+  if constexpr (mv_staged_fits<DC>()) {
+    APEX_CUDA_TRY(c, set((const void*)schur_chunk_kernel<DC, MODE_MATVEC, true, true>, chunk_smem_bytes<DC, MODE_MATVEC, true>(W)));
+    APEX_CUDA_TRY(c, set((const void*)schur_chunk_kernel<DC, MODE_MATVEC, false, true>, chunk_smem_bytes<DC, MODE_MATVEC, true>(W)));
+  }
+  APEX_CUDA_TRY(c, set((const void*)schur_chunk_kernel<DC, MODE_RHS, true, false>, chunk_smem_bytes<DC, MODE_RHS, false>(W)));
+  APEX_CUDA_TRY(c, set((const void*)schur_chunk_kernel<DC, MODE_RHS, false, false>, chunk_smem_bytes<DC, MODE_RHS, false>(W)));
+  APEX_CUDA_TRY(c, set((const void*)schur_chunk_kernel<DC, MODE_BACKSUB, false, false>, chunk_smem_bytes<DC, MODE_BACKSUB, false>(W)));
   int per_sm = 0;
-  APEX_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, schur_chunk_kernel<DC, MODE_MATVEC, true>, TILE, chunk_smem_bytes<DC, MODE_MATVEC>(W)));
+  if constexpr (mv_staged_fits<DC>()) {
+    if (c.mv_staged) APEX_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, schur_chunk_kernel<DC, MODE_MATVEC, true, true>, TILE, chunk_smem_bytes<DC, MODE_MATVEC, true>(W)));
+  }
+  if (!c.mv_staged) APEX_CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, schur_chunk_kernel<DC, MODE_MATVEC, true, false>, TILE, chunk_smem_bytes<DC, MODE_MATVEC, false>(W)));
   if (per_sm < 1) { c.err = "chunk kernel does not fit on an SM"; return APEX_ERR_UNSUPPORTED; }
   c.mv_ctas_per_sm = (uint32_t)per_sm;
   if (const char* e = getenv("APEX_MV_CTAS_PER_SM")) c.mv_ctas_per_sm = (uint32_t)std::max(1, std::min(atoi(e), per_sm));
@@ -989,14 +1131,21 @@ static apex_status launch_tiles_dc(Ctx& c, int mode, const SchurArgs& a0) {
     const uint32_t W = c.mv_window;
     switch (mode) {
       case MODE_MATVEC:
-        if (det) schur_chunk_kernel<DC, MODE_MATVEC, true><<<grid, TILE, chunk_smem_bytes<DC, MODE_MATVEC>(W), c.stream>>>(a);
-        else schur_chunk_kernel<DC, MODE_MATVEC, false><<<grid, TILE, chunk_smem_bytes<DC, MODE_MATVEC>(W), c.stream>>>(a);
+        if constexpr (mv_staged_fits<DC>()) {
+          if (c.mv_staged) {
+            if (det) schur_chunk_kernel<DC, MODE_MATVEC, true, true><<<grid, TILE, chunk_smem_bytes<DC, MODE_MATVEC, true>(W), c.stream>>>(a);
+            else schur_chunk_kernel<DC, MODE_MATVEC, false, true><<<grid, TILE, chunk_smem_bytes<DC, MODE_MATVEC, true>(W), c.stream>>>(a);
+            break;
+          }
+        }
+        if (det) schur_chunk_kernel<DC, MODE_MATVEC, true, false><<<grid, TILE, chunk_smem_bytes<DC, MODE_MATVEC, false>(W), c.stream>>>(a);
+        else schur_chunk_kernel<DC, MODE_MATVEC, false, false><<<grid, TILE, chunk_smem_bytes<DC, MODE_MATVEC, false>(W), c.stream>>>(a);
         break;
       case MODE_RHS:
-        if (det) schur_chunk_kernel<DC, MODE_RHS, true><<<grid, TILE, chunk_smem_bytes<DC, MODE_RHS>(W), c.stream>>>(a);
-        else schur_chunk_kernel<DC, MODE_RHS, false><<<grid, TILE, chunk_smem_bytes<DC, MODE_RHS>(W), c.stream>>>(a);
+        if (det) schur_chunk_kernel<DC, MODE_RHS, true, false><<<grid, TILE, chunk_smem_bytes<DC, MODE_RHS, false>(W), c.stream>>>(a);
+        else schur_chunk_kernel<DC, MODE_RHS, false, false><<<grid, TILE, chunk_smem_bytes<DC, MODE_RHS, false>(W), c.stream>>>(a);
         break;
-      default: schur_chunk_kernel<DC, MODE_BACKSUB, false><<<grid, TILE, chunk_smem_bytes<DC, MODE_BACKSUB>(W), c.stream>>>(a); break;
+      default: schur_chunk_kernel<DC, MODE_BACKSUB, false, false><<<grid, TILE, chunk_smem_bytes<DC, MODE_BACKSUB, false>(W), c.stream>>>(a); break;
     }
     c.launches++;
     if (det) {

@@ -390,7 +390,7 @@ typedef struct apex_layout_stats {
   int32_t consistent;              /* 1 when every structural invariant holds                      */
   int32_t reserved;
   double build_ms;
-  /* work distribution of the Schur operator's chunk kernel: ranges (one per resident CTA; 444 here), cameras per window,
+  /* work distribution of the Schur operator's chunk kernel: ranges (one per resident CTA of a 148-SM device), cameras per window,
    * windows, and the sum of the windows' camera counts (rows flushed per operator application) */
   uint32_t mv_ranges, mv_window, mv_nwindows, reserved2;
   uint64_t mv_rows;

@@ -17,7 +17,10 @@ d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('reductions suppr
 for det in 0 1; do APEX_DETERMINISTIC=$det timeout 400 python tools/probe.py --shape venice1778 --iters 1 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('deterministic=$det:', {k: round(d[k],4) for k in d if k.startswith('matvec')})"; done
-for w in 256 320 640; do APEX_MV_WINDOW=$w timeout 400 python tools/probe.py --shape venice1778 --iters 1 2>/dev/null | python -c "
+for st in 0 1; do for det in 0 1; do APEX_MV_STAGED=$st APEX_DETERMINISTIC=$det timeout 400 python tools/probe.py --shape venice1778 --iters 1 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('staged=$st det=$det:', {k: round(d[k],4) for k in d if k.startswith('matvec')})"; done; done
+for w in 320 600; do APEX_MV_WINDOW=$w timeout 400 python tools/probe.py --shape venice1778 --iters 1 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('window=$w:', {k: round(d[k],4) for k in d if k.startswith('matvec')})"; done
 timeout 900 python bench.py --steps 10 --warmup 3 --cpu-baseline 0 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; python - <<PY
