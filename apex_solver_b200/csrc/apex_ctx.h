@@ -121,6 +121,7 @@ struct DevState {
   double rz_old, pcg_tol, b_norm, r_norm;
   double pcg_alpha, pcg_beta;
   uint32_t ticket_a, ticket_b;            // last-block-done counters of the multi-CTA PCG kernels
+  uint32_t tail_bar[4];                   // arrival counters of the fused PCG tail's grid barriers
   int32_t pcg_iters, pcg_done, pcg_max, pad1;
   // errors
   unsigned long long ar_seq;              // sequence number of the peer-memory all-reduce (comm.cu)
@@ -233,6 +234,7 @@ struct Ctx {
   uint32_t mv_nwindows = 0;
   uint64_t mv_nrows = 0;           // sum of the windows' camera counts (rows of det_partial)
   bool mv_staged = false;          // operator kernel prefetches the Jacobian planes through a TMA-fed shared-memory stage
+  bool mv_defer_reduce = false;    // the caller adds the partial rows itself (fused PCG tail)
   bool mv_det = false;             // flush the windows as per-window partial rows + fixed-order second pass (bitwise reproducible)
   size_t nslots = 0;
   HostVec<uint64_t> slot_obs;      // slot -> caller's observation index (UINT64_MAX for padding)
@@ -254,8 +256,8 @@ struct Ctx {
   DevBuf<uint32_t> range_win0;       // [mv_nranges + 1] first window of each range
   DevBuf<uint32_t> win_cams;         // [mv_nrows] sorted camera lists of the windows
   // deterministic flush: partial rows + per-camera row lists
-  DevBuf<uint32_t> cam_row_start;    // [ncam+1] CSR over cameras ...
-  DevBuf<uint32_t> cam_rows;         // ... of their rows in det_partial, ascending
+  DevBuf<uint32_t> cam_row_start;    // [ncam+1] camera-major rows of det_partial: camera c owns rows [start[c], start[c+1]) ...
+  DevBuf<uint32_t> win_dst;          // ... and entry i of win_cams flushes to row win_dst[i] (a camera's rows in (range, window) order)
   DevBuf<double> det_partial;        // [mv_nrows][dc]
   DevBuf<double> slot_uv;            // [chunk][2][TILE]
   DevBuf<uint32_t> pt_slot0, pt_cnt; // per local landmark

@@ -76,10 +76,10 @@ struct HostLayout {
   StageBuf<uint16_t> cslot_widx;
   std::vector<WinDesc> win_desc;
   std::vector<uint32_t> range_win0, win_cams, cam_row_start;
-  StageBuf<uint32_t> cam_rows;
+  StageBuf<uint32_t> win_dst;
   StageBuf<double> cm_uv;
   StageBuf<uint32_t> cm_lp;
-  void set_pinned(bool on) { slot_cam.pinned = slot_lp.pinned = slot_uv.pinned = cslot_meta.pinned = cslot_widx.pinned = cam_rows.pinned = cm_uv.pinned = cm_lp.pinned = on; }
+  void set_pinned(bool on) { slot_cam.pinned = slot_lp.pinned = slot_uv.pinned = cslot_meta.pinned = cslot_widx.pinned = win_dst.pinned = cm_uv.pinned = cm_lp.pinned = on; }
   void reset() { tiles.clear(); giant_tiles.clear(); items.clear(); }  // what build_layout appends to
   std::vector<CamItem> items;
   std::vector<uint32_t> cam_item_start;
@@ -342,16 +342,16 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
       L.win_cams.insert(L.win_cams.end(), rc[r].begin(), rc[r].end());
     }
     if (nn == 0) { L.range_win0.assign(1, 0); }
-    // deterministic flush: per-camera lists of the rows (= positions in win_cams) that hold a partial result of the camera,
-    // ascending, i.e. in (range, window) order
+    // deterministic flush: the partial results are stored camera-major - camera c owns rows [cam_row_start[c], cam_row_start[c+1]),
+    // one per window that touches it, in (range, window) order; win_dst maps every entry of win_cams to its row
     L.cam_row_start.assign((size_t)ncam + 1, 0);
-    L.cam_rows.resize(0);
+    L.win_dst.resize(0);
     if (want_det_lists) {
       for (uint32_t cam : L.win_cams) L.cam_row_start[cam + 1]++;
       for (uint32_t k = 0; k < ncam; ++k) L.cam_row_start[k + 1] += L.cam_row_start[k];
-      L.cam_rows.resize(L.win_cams.size());
+      L.win_dst.resize(L.win_cams.size());
       std::vector<uint32_t> cursor(L.cam_row_start.begin(), L.cam_row_start.end() - 1);
-      for (size_t row = 0; row < L.win_cams.size(); ++row) L.cam_rows[cursor[L.win_cams[row]]++] = (uint32_t)row;
+      for (size_t i = 0; i < L.win_cams.size(); ++i) L.win_dst[i] = cursor[L.win_cams[i]]++;
     }
   }
   lap("ranges + windows");
@@ -422,7 +422,7 @@ apex_status layout_stats(const apex_problem_desc* d, int nranks, int rank, apex_
   // a permutation of the point-major lanes, both maps are inverse to each other, cameras ascend along the sorted lanes, the
   // continuation flags mark exactly the runs cut at warp boundaries; the windows tile the ranges, the ranges tile the normal
   // chunks, a window's camera list is sorted, at most W long (or one chunk) and every lane's window index names its camera;
-  // the per-camera row lists cover every row once
+  // the camera-major rows of the deterministic flush cover every window entry once
   out->consistent = covered == L.nobs_local ? 1 : 0;
   for (const TileDesc& t : L.tiles) {
     if (t.nchunks != 1) continue;
@@ -477,14 +477,15 @@ apex_status layout_stats(const apex_problem_desc* d, int nranks, int rank, apex_
     }
     if (next_chunk != nn || next_row != L.win_cams.size()) out->consistent = 0;
   }
-  if (L.cam_row_start[d->ncam] != L.win_cams.size() || L.cam_rows.size() != L.win_cams.size()) out->consistent = 0;
+  if (L.cam_row_start[d->ncam] != L.win_cams.size() || L.win_dst.size() != L.win_cams.size()) out->consistent = 0;
   else {
     std::vector<uint8_t> seen(L.win_cams.size(), 0);
-    for (uint32_t k = 0; k < d->ncam && out->consistent; ++k)
-      for (uint32_t e = L.cam_row_start[k]; e < L.cam_row_start[k + 1]; ++e) {
-        const uint32_t row = L.cam_rows[e];
-        if (row >= L.win_cams.size() || seen[row]++ || L.win_cams[row] != k || (e > L.cam_row_start[k] && L.cam_rows[e - 1] >= row)) { out->consistent = 0; break; }
-      }
+    std::vector<uint32_t> last(d->ncam, 0);
+    for (size_t i = 0; i < L.win_cams.size() && out->consistent; ++i) {   // every row once, inside its camera's block, ascending with i
+      const uint32_t cam = L.win_cams[i], row = L.win_dst[i];
+      if (row < L.cam_row_start[cam] || row >= L.cam_row_start[cam + 1] || seen[row]++ || (last[cam] && row < last[cam])) out->consistent = 0;
+      last[cam] = row + 1;
+    }
   }
   return APEX_OK;
 }
@@ -585,7 +586,7 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   APEX_CUDA_TRY(c, upload_vec(c.win_cams, L.win_cams, s));
   if (c.mv_det) {  // only the deterministic flush reads the per-camera row lists
     APEX_CUDA_TRY(c, upload_vec(c.cam_row_start, L.cam_row_start, s));
-    APEX_CUDA_TRY(c, upload_vec(c.cam_rows, L.cam_rows, s));
+    APEX_CUDA_TRY(c, upload_vec(c.win_dst, L.win_dst, s));
     APEX_CUDA_TRY(c, c.det_partial.alloc((size_t)std::max<uint64_t>(c.mv_nrows, 1) * c.dc));
   }
   APEX_CUDA_TRY(c, upload_vec(c.items, L.items, s));

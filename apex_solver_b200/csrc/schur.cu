@@ -52,7 +52,8 @@ struct SchurArgs {
   const uint32_t* range_win0;
   const uint32_t* win_cams;
   uint32_t window;                 // cameras per window the shared-memory rows were sized for
-  double* partial;                 // deterministic flush: [rows][DC], row = position in win_cams
+  const uint32_t* win_dst;         // deterministic flush: row of partial[][DC] for every entry of win_cams (camera-major)
+  double* partial;
 };
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
@@ -238,9 +239,10 @@ template <int MODE>
 __host__ __device__ constexpr int chunk_work_doubles() { return 2 * TILE + 3 * TILE + (3 + 6 + (MODE == MODE_MATVEC ? 0 : 3)) * MAX_TILE_PTS + MAX_TILE_PTS / 2; }
 template <int DC, bool STAGED>
 __host__ __device__ constexpr int chunk_stage_doubles() { return STAGED ? 2 * (DC + 3) * TILE : 0; }
+__host__ __device__ constexpr int ywin_stride(int dc) { return (dc + 1) & ~1; }   // window rows padded to 16 bytes: 128-bit read-modify-write
 template <int DC, int MODE, bool STAGED>
 __host__ __device__ constexpr size_t chunk_smem_bytes(uint32_t W) {
-  return sizeof(double) * ((size_t)chunk_stage_doubles<DC, STAGED>() + chunk_work_doubles<MODE>() + 8 * DC + 2 + (size_t)W * DC);
+  return sizeof(double) * ((size_t)chunk_stage_doubles<DC, STAGED>() + chunk_work_doubles<MODE>() + 8 * DC + 2 + (size_t)W * ywin_stride(DC));
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -268,6 +270,7 @@ template <int DC, int MODE, bool DET, bool STAGED>
 __global__ void __launch_bounds__(TILE, STAGED ? 2 : 3) schur_chunk_kernel(SchurArgs a) {
   constexpr int NPAIR = DC + 3;
   constexpr int XS = xpad_stride(DC);
+  constexpr int DCP = ywin_stride(DC);
   constexpr int NGP = MODE == MODE_MATVEC ? 0 : 3;
   constexpr int WORK = chunk_work_doubles<MODE>();
   constexpr int STG = chunk_stage_doubles<DC, STAGED>();
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(TILE, STAGED ? 2 : 3) schur_chunk_kernel(Schur
   uint32_t* sptm = reinterpret_cast<uint32_t*>(wk + 5 * TILE + (9 + NGP) * MAX_TILE_PTS);
   double (*scont)[DC] = reinterpret_cast<double (*)[DC]>(wk + WORK);                     // [8] run sums of continuation lanes, per warp
   const uint32_t bar = smem_u32(wk + WORK + 8 * DC);                                     // mbarrier of the Jacobian stage
-  double* ywin = wk + WORK + 8 * DC + 2;                                                 // [window][DC]
+  double* ywin = wk + WORK + 8 * DC + 2;                                                 // [window][DCP], 16-byte aligned rows
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t win_begin = __ldg(a.range_win0 + blockIdx.x), win_end = __ldg(a.range_win0 + blockIdx.x + 1);
   if (win_begin == win_end) return;
@@ -343,14 +346,14 @@ __global__ void __launch_bounds__(TILE, STAGED ? 2 : 3) schur_chunk_kernel(Schur
       const int len = (int)((fix_flags >> CONT_LEN_SHIFT) & 7u);
       double s = scont[warp][lane];
       for (int v = 1; v < len; ++v) s += scont[warp + v][lane];
-      ywin[fix_widx * DC + lane] += s;
+      ywin[fix_widx * DCP + lane] += s;
     }
     fix_flags = 0;
   };
   for (uint32_t win = win_begin; win < win_end; ++win) {
     const uint4 wd = __ldg(reinterpret_cast<const uint4*>(a.win_desc + win));   // chunk_begin, chunk_end, cam0, ncams
     if (MODE != MODE_BACKSUB) {
-      for (uint32_t i = tid; i < wd.w * DC; i += TILE) ywin[i] = 0.0;   // ordered before the first read-modify-write by the chunk's barriers
+      for (uint32_t i = tid; i < wd.w * DCP; i += TILE) ywin[i] = 0.0;   // ordered before the first read-modify-write by the chunk's barriers
     }
     for (uint32_t chunk = wd.x; chunk < wd.y; ++chunk) {
       const uint2 meta = meta_n;
@@ -498,9 +501,14 @@ __global__ void __launch_bounds__(TILE, STAGED ? 2 : 3) schur_chunk_kernel(Schur
 #pragma unroll
           for (int k = 0; k < DC; ++k) scont[warp][k] = cv[k];
         } else {
-          double* yr = ywin + widx * DC;
+          double2* yr = reinterpret_cast<double2*>(ywin + widx * DCP);
 #pragma unroll
-          for (int k = 0; k < DC; ++k) yr[k] += cv[k];
+          for (int m = 0; m < DCP / 2; ++m) {
+            double2 v = yr[m];
+            v.x += cv[2 * m];
+            if (2 * m + 1 < DC) v.y += cv[2 * m + 1];
+            yr[m] = v;
+          }
         }
       }
       fix_flags = __shfl_sync(0xffffffffu, meta.y, 0);
@@ -511,25 +519,26 @@ __global__ void __launch_bounds__(TILE, STAGED ? 2 : 3) schur_chunk_kernel(Schur
     // ---- flush the window ----
     fix_up();
     __syncthreads();
-    if (DET) {
-      double* out = a.partial + (size_t)wd.z * DC;
-      for (uint32_t i = tid; i < wd.w * DC; i += TILE) out[i] = ywin[i];
+    if (DET) {   // the camera's row of partial results for this window (camera-major rows: the second pass reads them contiguously)
+      for (uint32_t i = tid; i < wd.w * DC; i += TILE) {
+        const uint32_t c = i / DC, k = i - c * DC;
+        a.partial[(size_t)__ldg(a.win_dst + wd.z + c) * DC + k] = ywin[c * DCP + k];
+      }
     } else if (a.debug != 1) {
       for (uint32_t i = tid; i < wd.w * DC; i += TILE) {
         const uint32_t c = i / DC, k = i - c * DC;
-        red_add(a.y + (size_t)__ldg(a.win_cams + wd.z + c) * DC + k, ywin[i]);
+        red_add(a.y + (size_t)__ldg(a.win_cams + wd.z + c) * DC + k, ywin[c * DCP + k]);
       }
     }
     __syncthreads();   // before the next window zeroes the rows
   }
 }
 
-// deterministic flush, second pass: y[camera] += sum of the camera's partial rows, in ascending row order folded into a fixed
-// tree: one warp per camera, lane l adds rows l, l+32, ... in order, then a butterfly over the lanes.
+// deterministic flush, second pass: y[camera] += sum of the camera's partial rows (contiguous, in (range, window) order) folded into a
+// fixed tree: one warp per camera, lane l adds rows l, l+32, ... in order, then a butterfly over the lanes.
 template <int DC>
 __global__ void __launch_bounds__(256) det_reduce_kernel(const double* __restrict__ partial, const uint32_t* __restrict__ cam_row_start,
-                                                         const uint32_t* __restrict__ cam_rows, double* __restrict__ y, const DevState* st,
-                                                         uint32_t ncam, int check_done) {
+                                                         double* __restrict__ y, const DevState* st, uint32_t ncam, int check_done) {
   if (check_done && st->pcg_done) return;
   const uint32_t cam = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -539,7 +548,7 @@ __global__ void __launch_bounds__(256) det_reduce_kernel(const double* __restric
   for (int k = 0; k < DC; ++k) acc[k] = 0.0;
   const uint32_t e1 = __ldg(cam_row_start + cam + 1);
   for (uint32_t e = __ldg(cam_row_start + cam) + lane; e < e1; e += 32) {
-    const double* row = partial + (size_t)__ldg(cam_rows + e) * DC;
+    const double* row = partial + (size_t)e * DC;
 #pragma unroll
     for (int k = 0; k < DC; ++k) acc[k] += __ldcg(row + k);
   }
@@ -611,6 +620,7 @@ __global__ void __launch_bounds__(1024) pcg_init_kernel(const double* __restrict
     st->pcg_done = max_it <= 0 ? 1 : 0;
     st->pcg_alpha = 0.0; st->pcg_beta = 0.0; st->ticket_a = 0; st->ticket_b = 0;
     st->ar_timeout = 0;
+    for (int j = 0; j < 4; ++j) st->tail_bar[j] = 0;
   }
 }
 
@@ -826,213 +836,242 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_update_kernel(const double* _
 }
 
 // ----------------------------------------------------------------------------------------------------
-// Fused PCG tail: everything between two operator applications in ONE launch of one thread-block cluster.
-//   [peer all-reduce of the partial operator result over NVLink]  ->  pAp, alpha  ->  x += alpha p, r -= alpha Ap,
-//   z = M^-1 r  ->  ||r||, r.z, beta, break tests  ->  p = z + beta p, its padded copy, y0 = (H_cc + lambda I) p
-// The camera vectors are small (ncam*dc doubles: 128 KB on the Venice shape), so the three grid-wide dot products that
-// cost three kernels with "last CTA" passes become cluster-wide reductions through distributed shared memory: every CTA
-// of the cluster owns a contiguous range of cameras, keeps its rows of p / Ap / r / z in shared memory, publishes its
-// partial sums in its own shared memory, cluster.sync(), and every CTA adds the partials in CTA order (same bits
-// everywhere, and the same bits on every rank because every rank adds the same numbers in the same order). Two launches
-// per PCG iteration (operator + tail) instead of four. Opt-in (APEX_PCG_TAIL = cluster size): 16 CTAs pull H_cc and the
-// preconditioner blocks (1.8 MB on the Venice shape) through 16 SMs, which costs what the saved launches and "last CTA"
-// passes gain - measured 19.6 vs 19.7 LM it/s on one GPU and 35.4 vs 36.0 on two. Needs a CTA's rows to fit in shared
-// memory (TAIL_MAX_ROWS). Semantics of solve_pcg_block (implicit_schur.rs:604-676) as in pcg_pap / pcg_update / pcg_dir_hcc.
+// Fused PCG tail: everything between two operator applications in ONE launch.
+//   second pass of the deterministic flush (y += the camera's partial rows)  ->  [all-reduce of the partial operator results
+//   over NVLink peer memory]  ->  pAp, alpha  ->  x += alpha p, r -= alpha Ap, z = M^-1 r  ->  ||r||, r.z, beta, break tests
+//   ->  p = z + beta p, its padded copy, y0 = (H_cc + lambda I) p
+// The camera vectors are small (ncam*dc doubles: 128 KB on the Venice shape) and the step is pure latency: as five kernels
+// (det_reduce, pcg_pap / ar_reduce_pap, pcg_update, pcg_dir_hcc) it cost ~25-35 us per PCG iteration next to an operator of
+// 260 us on one GPU and 40 us on an eighth of the problem. Here one warp owns a camera (lane q = row q of its blocks), the CTAs
+// of one launch are co-resident (grid <= 2 per SM, 256 threads, no dynamic shared memory) and meet at software grid barriers -
+// an arrival counter in DevState per barrier, reset by CTA 0 once the following barrier proves every CTA has left it - and
+// every grid-wide dot product is a per-CTA partial summed by every CTA in the same fixed order (same bits on every CTA and, with
+// the rank-ordered peer sum, on every rank). Two launches per PCG iteration (operator + tail).
+// Semantics of solve_pcg_block (implicit_schur.rs:604-676) as in pcg_pap / pcg_update / pcg_dir_hcc.
 // ----------------------------------------------------------------------------------------------------
-constexpr int TAIL_THREADS = 1024;
-constexpr int TAIL_MAX_ROWS = 4096;   // rows of one CTA: 3 x 32 KB of shared memory
+constexpr int TAIL_THREADS = 256;
+constexpr int TAIL_BARRIERS = 4;
+
 struct TailArgs {
-  double* const* peer_buf;               // null: `ysrc` already holds the complete operator result
+  double* const* peer_buf;               // null: single rank
   unsigned long long* const* peer_flags;
   const unsigned long long* flags;
   int par, nranks, rank;
-  const double* ysrc;
+  double* ylocal;                        // this rank's operator result: y0 + what the operator kernels reduced into it
+  const double* partial;                 // deterministic flush: camera-major partial rows ...
+  const uint32_t* cam_row_start;         // ... of camera c: [cam_row_start[c], cam_row_start[c+1]); null = nothing to add
+  double* y;                             // the complete operator result (kept for the update stage)
   double* y0_next;
   double* p; double* x; double* r; double* z; double* xpad;
   const double* pinv; const double* hcc;
+  double* part;                          // [3 * gridDim.x] per-CTA partial dot products
   DevState* st;
   uint32_t ncam;
-  int dc, K, xs, add_hcc;
+  int K, xs, add_hcc;
 };
 
-// sum of one shared-memory slot over the cluster, in CTA order
-__device__ __forceinline__ double cluster_sum(cooperative_groups::cluster_group& cl, double* slot) {
-  double s = 0.0;
-  for (unsigned c = 0; c < cl.num_blocks(); ++c) s += *cl.map_shared_rank(slot, c);
-  return s;
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// software grid barrier `j` of the tail kernel (all CTAs co-resident). CTA 0 resets the counter of barrier j-1 afterwards: every
+// CTA has arrived here, so none is still polling it. The last barrier of a launch is reset behind the first one of the next
+// launch; pcg_init_kernel clears all of them (a solve can end between two barriers).
+__device__ __forceinline__ void tail_grid_barrier(DevState* st, int j, int reset) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&st->tail_bar[j], 1u);
+    long long spins = 0;
+    while (ld_acquire_gpu_u32(&st->tail_bar[j]) < gridDim.x) {
+      if (++spins > (1ll << 28)) __trap();   // a CTA that never arrives (not co-resident): an error the host sees, not a hang
+    }
+    if (blockIdx.x == 0 && reset >= 0) st->tail_bar[reset] = 0;
+  }
+  __syncthreads();
+}
+// sum of part[0..n) in a fixed order, same bits in every thread of every CTA: warp 0 strides the array, butterfly, broadcast
+__device__ __forceinline__ double tail_total(const double* part, unsigned n, double* slot) {
+  if (threadIdx.x < 32) {
+    double s = 0.0;
+    for (unsigned b = threadIdx.x; b < n; b += 32) s += __ldcg(part + b);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (threadIdx.x == 0) *slot = s;
+  }
+  __syncthreads();
+  const double v = *slot;
+  __syncthreads();
+  return v;
 }
 
-__global__ void __launch_bounds__(TAIL_THREADS, 1) pcg_tail_kernel(TailArgs a) {
-  namespace cg = cooperative_groups;
-  cg::cluster_group cl = cg::this_cluster();
-  extern __shared__ double tail_sm[];
+template <int DC>
+__global__ void __launch_bounds__(TAIL_THREADS) pcg_tail_kernel(TailArgs a) {
   __shared__ double sh[TAIL_THREADS];
-  __shared__ double slot[4];
+  __shared__ double slot;
   DevState* st = a.st;
-  if (st->pcg_done) return;  // same value in every CTA: it is only written behind two cluster barriers below
-  const int tid = threadIdx.x, dc = a.dc, K = a.K;
-  const uint32_t n = a.ncam * dc;
-  const uint32_t cpc = (a.ncam + cl.num_blocks() - 1) / cl.num_blocks();
-  const uint32_t cam0 = min(cl.block_rank() * cpc, a.ncam);
-  const uint32_t nrow = min(cpc, a.ncam - cam0) * dc;
-  const size_t row0 = (size_t)cam0 * dc;
-  double* ys = tail_sm;                   // Ap rows, later z rows
-  double* pp = tail_sm + TAIL_MAX_ROWS;   // p rows
-  double* rs = tail_sm + 2 * TAIL_MAX_ROWS;
+  if (st->pcg_done) return;  // same value in every CTA: it is only written behind the last grid barrier of a launch
+  const int tid = threadIdx.x, lane = tid & 31, K = a.K;
+  const uint32_t n = a.ncam * DC;
+  const uint32_t gw = blockIdx.x * (TAIL_THREADS / 32) + (tid >> 5), nw = gridDim.x * (TAIL_THREADS / 32);
+  const unsigned G = gridDim.x;
   const double rz_old = st->rz_old, tol = st->pcg_tol, damping = st->damping;
   const int iters0 = st->pcg_iters, max_it = st->pcg_max;
   const unsigned long long seq = st->ar_seq + 1;
-  // ---- the operator result of all ranks (peer memory, rank order) and pAp ----
-  if (a.peer_buf) {
-    if (cl.block_rank() == 0 && tid < a.nranks) {
+  const bool multi = a.peer_buf != nullptr;
+  const int last_bar = multi ? 3 : 2;   // index of the last grid barrier of a full launch (reset behind the first one of the next)
+  double* ymine = multi ? a.peer_buf[a.rank] + (size_t)a.par * n : a.ylocal;
+  // ---- stage A: this rank's operator result (second pass of the deterministic flush) ----
+  if (a.cam_row_start) {
+    for (uint32_t cam = gw; cam < a.ncam; cam += nw) {
+      double acc[DC];
+#pragma unroll
+      for (int k = 0; k < DC; ++k) acc[k] = 0.0;
+      const uint32_t e1 = __ldg(a.cam_row_start + cam + 1);
+      for (uint32_t e = __ldg(a.cam_row_start + cam) + lane; e < e1; e += 32) {
+        const double* row = a.partial + (size_t)e * DC;
+#pragma unroll
+        for (int k = 0; k < DC; ++k) acc[k] += __ldcg(row + k);
+      }
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) {
+#pragma unroll
+        for (int k = 0; k < DC; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
+      }
+      double mine = 0.0;
+#pragma unroll
+      for (int k = 0; k < DC; ++k) if (lane == k) mine = acc[k];
+      if (lane < DC) ymine[(size_t)cam * DC + lane] += mine;
+    }
+  }
+  int nb = 0;   // grid barriers passed in this launch
+  if (multi) {
+    // ---- the operator result of all ranks: publish "my partial result is complete", wait for the peers, sum in rank order ----
+    __threadfence_system();
+    tail_grid_barrier(st, nb, nb == 0 ? last_bar : nb - 1); ++nb;
+    if (blockIdx.x == 0 && tid < a.nranks) {
       __threadfence_system();
       st_release_sys(a.peer_flags[tid] + a.rank, seq);
     }
     if (tid < a.nranks) {
       long long spins = 0;
       while (ld_acquire_sys(a.flags + tid) < seq) {
-        if (++spins > (1ll << 26)) { atomicExch(&st->ar_timeout, 1); atomicExch(&st->pcg_done, 1); break; }  // seen by the NEXT launch (read at entry)
+        if (++spins > (1ll << 26)) { atomicExch(&st->ar_timeout, 1); break; }  // the sums below are garbage; solve_implicit sees the flag
       }
     }
     __syncthreads();
   }
+  // ---- stage B: y (complete), pAp ----
   double v = 0.0;
-  for (uint32_t i = tid; i < nrow; i += TAIL_THREADS) {
-    const size_t row = row0 + i;
-    double s = 0.0;
-    if (a.peer_buf) { for (int r = 0; r < a.nranks; ++r) s += ld_relaxed_sys(a.peer_buf[r] + (size_t)a.par * n + row); }
-    else s = a.ysrc[row];
-    const double pv = a.p[row];
-    ys[i] = s; pp[i] = pv;
-    v += pv * s;
+  for (uint32_t cam = gw; cam < a.ncam; cam += nw) {
+    if (lane < DC) {
+      const size_t row = (size_t)cam * DC + lane;
+      double s;
+      if (multi) { s = 0.0; for (int r = 0; r < a.nranks; ++r) s += ld_relaxed_sys(a.peer_buf[r] + (size_t)a.par * n + row); }
+      else s = ymine[row];
+      a.y[row] = s;
+      v += a.p[row] * s;
+    }
   }
   v = block_reduce_sum(v, sh);
-  if (tid == 0) slot[0] = v;
-  cl.sync();
-  const double pap = cluster_sum(cl, &slot[0]);
-  if (fabs(pap) < 1e-20) {  // break before the update (implicit_schur.rs:626-629)
-    if (cl.block_rank() == 0 && tid == 0) { st->pcg_iters = iters0 + 1; st->pcg_done = 1; if (a.peer_buf) st->ar_seq = seq; }
-    cl.sync();  // nobody leaves while its shared memory may still be read
+  if (tid == 0) a.part[blockIdx.x] = v;
+  tail_grid_barrier(st, nb, nb == 0 ? last_bar : nb - 1); ++nb;
+  const double pap = tail_total(a.part, G, &slot);
+  if (fabs(pap) < 1e-20 || *reinterpret_cast<volatile int32_t*>(&st->ar_timeout)) {  // break before the update (implicit_schur.rs:626-629); every CTA takes the same branch
+    tail_grid_barrier(st, nb, nb - 1); ++nb;   // nobody may still read pcg_done at entry... (all CTAs are past their entry test here)
+    if (blockIdx.x == 0 && tid == 0) { st->pcg_iters = iters0 + 1; st->pcg_done = 1; if (multi) st->ar_seq = seq; }
     return;
   }
   const double alpha = rz_old / pap;
-  // ---- x, r, z = M^-1 r, ||r||^2, r.z ----
+  // ---- stage C: x, r, z = M^-1 r, ||r||^2, r.z ----
   double rr = 0.0, rz = 0.0;
-  for (uint32_t i = tid; i < nrow; i += TAIL_THREADS) {
-    const size_t row = row0 + i;
-    a.x[row] += alpha * pp[i];
-    const double rv = a.r[row] - alpha * ys[i];
-    a.r[row] = rv;
-    rs[i] = rv;
-    rr += rv * rv;
-  }
-  __syncthreads();
-  for (uint32_t i = tid; i < nrow; i += TAIL_THREADS) {
-    const uint32_t lc = i / dc, q = i % dc;
-    const double* P = a.pinv + (size_t)(cam0 + lc) * (36 + K * K);
-    const double* rc = rs + lc * dc;
+  for (uint32_t cam = gw; cam < a.ncam; cam += nw) {
+    const size_t row = (size_t)cam * DC + lane;
+    double rv = 0.0;
+    if (lane < DC) {
+      a.x[row] += alpha * a.p[row];
+      rv = a.r[row] - alpha * a.y[row];
+      a.r[row] = rv;
+      rr += rv * rv;
+    }
+    // z_q = sum_b P[q][b] r_b on the 6x6 pose block and the KxK intrinsics block (apply_preconditioner, implicit_schur.rs:409-443)
+    const double* P = a.pinv + (size_t)cam * (36 + K * K);
     double s = 0.0;
-    if (q < 6) { for (int b = 0; b < 6; ++b) s += P[q * 6 + b] * rc[b]; }
-    else { const double* Q = P + 36 + (q - 6) * K; for (int b = 0; b < K; ++b) s += Q[b] * rc[6 + b]; }
-    a.z[row0 + i] = s;
-    ys[i] = s;  // z rows
-    rz += rs[i] * s;
+#pragma unroll
+    for (int b = 0; b < DC; ++b) {
+      const double rb = __shfl_sync(0xffffffffu, rv, b);
+      if (lane < 6) { if (b < 6) s += __ldg(P + lane * 6 + b) * rb; }
+      else if (lane < DC) { if (b >= 6) s += __ldg(P + 36 + (lane - 6) * K + (b - 6)) * rb; }
+    }
+    if (lane < DC) { a.z[row] = s; rz += rv * s; }
   }
   rr = block_reduce_sum(rr, sh);
   rz = block_reduce_sum(rz, sh);
-  if (tid == 0) { slot[1] = rr; slot[2] = rz; }
-  cl.sync();
-  const double rr_tot = cluster_sum(cl, &slot[1]), rz_tot = cluster_sum(cl, &slot[2]);
+  if (tid == 0) { a.part[G + blockIdx.x] = rr; a.part[2 * G + blockIdx.x] = rz; }
+  tail_grid_barrier(st, nb, nb - 1); ++nb;
+  const double rr_tot = tail_total(a.part + G, G, &slot), rz_tot = tail_total(a.part + 2 * G, G, &slot);
   const int iters = iters0 + 1;
   const double r_norm = sqrt(rr_tot);
   bool done = r_norm < tol || fabs(rz_old) < 1e-30;
   double beta = 0.0;
   const bool have_beta = !done;
   if (have_beta) { beta = rz_tot / rz_old; if (iters >= max_it) done = true; }
-  if (cl.block_rank() == 0 && tid == 0) {
+  // ---- stage D: next direction and the start value of the next operator result ----
+  if (!done) {
+    for (uint32_t cam = gw; cam < a.ncam; cam += nw) {
+      const size_t row = (size_t)cam * DC + lane;
+      double pv = 0.0;
+      if (lane < DC) {
+        const double zv = a.z[row];
+        pv = beta == 0.0 ? zv : zv + beta * a.p[row];
+        a.p[row] = pv;
+        a.xpad[(size_t)cam * a.xs + lane] = pv;
+      }
+      double s = damping * pv;
+      const double* H = a.hcc + ((size_t)cam * DC + (lane < DC ? lane : 0)) * DC;
+#pragma unroll
+      for (int b = 0; b < DC; ++b) {
+        const double pb = __shfl_sync(0xffffffffu, pv, b);
+        if (a.add_hcc && lane < DC) s += __ldg(H + b) * pb;
+      }
+      if (lane < DC) a.y0_next[row] = a.add_hcc ? s : 0.0;
+    }
+  }
+  // pcg_done / the scalars the next launch reads at entry are written behind a barrier every CTA has passed its entry test before
+  tail_grid_barrier(st, nb, nb - 1); ++nb;
+  if (blockIdx.x == 0 && tid == 0) {
     st->pcg_iters = iters;
     st->r_norm = r_norm;
     st->pcg_alpha = alpha;
     if (have_beta) { st->pcg_beta = beta; st->rz_old = rz_tot; }
     if (done) st->pcg_done = 1;
-    if (a.peer_buf) st->ar_seq = seq;
+    if (multi) st->ar_seq = seq;
   }
-  // ---- next direction and the start value of the next operator result ----
-  if (!done) {
-    for (uint32_t i = tid; i < nrow; i += TAIL_THREADS) {
-      const double pv = beta == 0.0 ? ys[i] : ys[i] + beta * pp[i];
-      a.p[row0 + i] = pv;
-      pp[i] = pv;
-      a.xpad[(size_t)(cam0 + i / dc) * a.xs + i % dc] = pv;
-    }
-    __syncthreads();
-    for (uint32_t i = tid; i < nrow; i += TAIL_THREADS) {
-      double s = 0.0;
-      if (a.add_hcc) {
-        const uint32_t lc = i / dc, q = i % dc;
-        const double* H = a.hcc + ((size_t)(cam0 + lc) * dc + q) * dc;
-        const double* pc = pp + lc * dc;
-        s = damping * pc[q];
-        for (int b = 0; b < dc; ++b) s += H[b] * pc[b];
-      }
-      a.y0_next[row0 + i] = s;
-    }
-  }
-  cl.sync();  // distributed shared memory stays alive until every CTA has read the partial sums
 }
 
-static apex_status launch_pcg_tail(Ctx& c, const TailArgs& a, int cluster) {
-  static bool attr_set = false;
-  const size_t smem = 3 * (size_t)TAIL_MAX_ROWS * sizeof(double);
-  if (!attr_set) {
-    APEX_CUDA_TRY(c, cudaFuncSetAttribute(pcg_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    APEX_CUDA_TRY(c, cudaFuncSetAttribute(pcg_tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr_set = true;
+// CTAs of the fused tail (0 = the separate kernels): one warp per camera, at most two CTAs per SM so that all are co-resident
+static int pcg_tail_ctas(Ctx& c) {
+  const char* e = getenv("APEX_PCG_TAIL");
+  const int want = e ? atoi(e) : 2;
+  if (want <= 0) return 0;
+  const int per_sm = std::min(want, 4);
+  return (int)std::max<uint32_t>(1, std::min<uint32_t>((c.ncam + 7) / 8, (uint32_t)(per_sm * c.num_sms)));
+}
+
+static apex_status launch_pcg_tail(Ctx& c, const TailArgs& a, int ctas) {
+  switch (c.dc) {
+    case 6: pcg_tail_kernel<6><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
+    case 9: pcg_tail_kernel<9><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
+    case 10: pcg_tail_kernel<10><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
+    case 11: pcg_tail_kernel<11><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
+    case 12: pcg_tail_kernel<12><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
+    case 14: pcg_tail_kernel<14><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
+    case 15: pcg_tail_kernel<15><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
+    default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)cluster);
-  cfg.blockDim = dim3(TAIL_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = c.stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  APEX_CUDA_TRY(c, cudaLaunchKernelEx(&cfg, pcg_tail_kernel, a));
   c.launches++;
   return APEX_OK;
-}
-
-// cluster size of the fused tail (0 = use the three-kernel path): the largest of 16 (non-portable) / 8 / 4 CTAs the device
-// can co-schedule with 96 KB of shared memory each, provided a CTA's camera rows fit in TAIL_MAX_ROWS
-static int pcg_tail_cluster(Ctx& c) {
-  static int device_max = -1;
-  if (device_max < 0) {
-    device_max = 0;
-    const size_t smem = 3 * (size_t)TAIL_MAX_ROWS * sizeof(double);
-    if (cudaFuncSetAttribute(pcg_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
-        cudaFuncSetAttribute(pcg_tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
-      for (int cl : {16, 8, 4}) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)cl); cfg.blockDim = dim3(TAIL_THREADS); cfg.dynamicSmemBytes = smem;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        int nclusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&nclusters, pcg_tail_kernel, &cfg) == cudaSuccess && nclusters > 0) { device_max = cl; break; }
-      }
-    }
-    cudaGetLastError();  // a failed probe must not poison the next launch check
-  }
-  const char* e = getenv("APEX_PCG_TAIL");
-  int want = e ? atoi(e) : 0;  // opt-in: measured no faster than the three-kernel path (19.6 vs 19.7 LM it/s at N=1, 35.4 vs 36.0 at N=2)
-  if (want <= 0 || device_max <= 0) return 0;
-  want = std::min(want, device_max);
-  const uint32_t rows = (uint32_t)((c.ncam + want - 1) / want) * c.dc;
-  if (rows > (uint32_t)TAIL_MAX_ROWS) return 0;
-  return want;
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -1046,7 +1085,7 @@ static SchurArgs make_schur_args(Ctx& c, const double* x, double* y, int check_d
   a.ntiles = c.ntiles;
   a.chunk_desc = c.chunk_desc.p; a.cslot_meta = c.cslot_meta.p; a.cpt_meta = c.cpt_meta.p; a.xpad = c.xpad.p;
   a.cslot_widx = c.cslot_widx.p; a.win_desc = c.win_desc.p; a.range_win0 = c.range_win0.p; a.win_cams = c.win_cams.p;
-  a.window = c.mv_window; a.partial = c.det_partial.p;
+  a.window = c.mv_window; a.partial = c.det_partial.p; a.win_dst = c.win_dst.p;
   const char* dbg = getenv("APEX_DEBUG_MATVEC");
   a.debug = dbg ? atoi(dbg) : 0;
   return a;
@@ -1148,8 +1187,8 @@ static apex_status launch_tiles_dc(Ctx& c, int mode, const SchurArgs& a0) {
       default: schur_chunk_kernel<DC, MODE_BACKSUB, false, false><<<grid, TILE, chunk_smem_bytes<DC, MODE_BACKSUB, false>(W), c.stream>>>(a); break;
     }
     c.launches++;
-    if (det) {
-      det_reduce_kernel<DC><<<(c.ncam + 7) / 8, 256, 0, c.stream>>>(c.det_partial.p, c.cam_row_start.p, c.cam_rows.p, a.y, c.state.p, c.ncam, a.check_done);
+    if (det && !c.mv_defer_reduce) {
+      det_reduce_kernel<DC><<<(c.ncam + 7) / 8, 256, 0, c.stream>>>(c.det_partial.p, c.cam_row_start.p, a.y, c.state.p, c.ncam, a.check_done);
       c.launches++;
     }
   }
@@ -1253,8 +1292,8 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
   // launch: the inner loop is launch-bound on small shards (8 GPUs: ~35 us of kernels per iteration).
   const int BATCH = 10;
   int it_count = 0;  // iteration index within this solve: selects the half of the peer buffer (BATCH is even)
-  const int tail_cluster = pcg_tail_cluster(c);
-  if (tail_cluster && cg_max_it > 0) {  // first direction p = z and y0 = (H_cc + lambda I) p into half 0; later ones come from the tail
+  const int tail_ctas = (c.nranks == 1 || c.p2p_ok) ? pcg_tail_ctas(c) : 0;
+  if (tail_ctas && cg_max_it > 0) {  // first direction p = z and y0 = (H_cc + lambda I) p into half 0; later ones come from the tail
     const int xs = xpad_stride(c.dc);
     double* y0 = c.p2p_ok ? c.arbuf.p : c.vy.p;
     pcg_dir_hcc_kernel<<<(c.ncam + PCG_CAMS - 1) / PCG_CAMS, PCG_THREADS, 0, s>>>(c.vz.p, c.vp.p, c.xpad.p, c.hcc.p, y0, c.state.p, c.ncam, c.dc, xs, c.rank == 0 ? 1 : 0);
@@ -1265,23 +1304,28 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
     const int xs = xpad_stride(c.dc);
     const unsigned gp = (n + PCG_THREADS - 1) / PCG_THREADS, gu = (c.ncam + PCG_CAMS - 1) / PCG_CAMS;
     const int par = it_count++ & 1;
-    if (tail_cluster) {
-      // fused path: [operator, tail] per iteration; the first direction / y0 were produced before the loop
+    if (tail_ctas) {
+      // fused path: [operator, tail] per iteration; the first direction / y0 were produced before the loop; the second pass
+      // of the deterministic flush runs inside the tail
       double* y0 = c.p2p_ok ? c.arbuf.p + (size_t)par * n : c.vy.p;
       cudaEvent_t* evp = (c.prof && c.ntiles) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
       if (evp) cudaEventRecord(evp[0], s);
-      APEX_TRY(launch_schur_tiles(c, MODE_MATVEC, c.vp.p, y0, 1, true));
+      c.mv_defer_reduce = true;
+      apex_status ost = launch_schur_tiles(c, MODE_MATVEC, c.vp.p, y0, 1, true);
+      c.mv_defer_reduce = false;
+      APEX_TRY(ost);
       if (evp) cudaEventRecord(evp[1], s);
-      if (!c.p2p_ok) APEX_TRY(allreduce_sum(c, c.vy.p, n));
       TailArgs ta{};
       if (c.p2p_ok) { ta.peer_buf = c.d_peer_buf.p; ta.peer_flags = c.d_peer_flags.p; ta.flags = c.arflags.p; }
       ta.par = par; ta.nranks = c.nranks; ta.rank = c.rank;
-      ta.ysrc = c.vy.p;
+      ta.ylocal = y0;
+      if (c.mv_det && c.nnormal_chunks) { ta.partial = c.det_partial.p; ta.cam_row_start = c.cam_row_start.p; }
+      ta.y = c.vy.p;
       ta.y0_next = c.p2p_ok ? c.arbuf.p + (size_t)(par ^ 1) * n : c.vy.p;
       ta.p = c.vp.p; ta.x = c.step_cam.p; ta.r = c.vr.p; ta.z = c.vz.p; ta.xpad = c.xpad.p;
-      ta.pinv = c.pinv.p; ta.hcc = c.hcc.p; ta.st = c.state.p;
-      ta.ncam = c.ncam; ta.dc = c.dc; ta.K = c.K; ta.xs = xs; ta.add_hcc = c.rank == 0 ? 1 : 0;
-      APEX_TRY(launch_pcg_tail(c, ta, tail_cluster));
+      ta.pinv = c.pinv.p; ta.hcc = c.hcc.p; ta.part = c.red_scratch.p; ta.st = c.state.p;
+      ta.ncam = c.ncam; ta.K = c.K; ta.xs = xs; ta.add_hcc = c.rank == 0 ? 1 : 0;
+      APEX_TRY(launch_pcg_tail(c, ta, tail_ctas));
       return APEX_OK;
     }
     {

@@ -77,7 +77,7 @@ def normalized_poses(lib, pose):
     return out
 
 
-def teacher_forced_parity(prob, variant, dut, oracle, scratch, lib, twin=None, n_it=6, cg_it=3000, cg_tol=1e-12, lam0=1e-3, nu0=2.0, log=None):
+def teacher_forced_parity(prob, variant, dut, oracle, scratch, lib, twin=None, n_it=6, cg_it=3000, cg_tol=1e-12, lam0=1e-3, nu0=2.0, log=None, backward_tol=None):
     """dut / oracle / scratch (/ twin): contexts with `prob` uploaded; oracle walks its own LM trajectory, scratch (another
     oracle context) recomputes links 3-8 on the DUT's numbers, twin (the oracle in another summation order) gives the
     forward floor of link 9 for the direct solver and the backward floor of link 3 for PCG. lib = the oracle library (scalar LM functions).
@@ -104,7 +104,7 @@ def teacher_forced_parity(prob, variant, dut, oracle, scratch, lib, twin=None, n
         s_diff = scratch.schur_matvec((dca - dcb).ravel())
         s_ref = scratch.schur_matvec(dcb.ravel())
         backward = float(np.linalg.norm(s_diff) / max(np.linalg.norm(s_ref), 1e-300))
-        tol_backward = BACKWARD_TOL[variant]
+        tol_backward = BACKWARD_TOL[variant] if backward_tol is None else backward_tol
         f = None
         if twin is not None:
             _, f, _ = one_iteration(twin, variant, lam, nu, cg_it, cg_tol)
