@@ -850,7 +850,6 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_update_kernel(const double* _
 // Semantics of solve_pcg_block (implicit_schur.rs:604-676) as in pcg_pap / pcg_update / pcg_dir_hcc.
 // ----------------------------------------------------------------------------------------------------
 constexpr int TAIL_THREADS = 256;
-constexpr int TAIL_BARRIERS = 4;
 
 struct TailArgs {
   double* const* peer_buf;               // null: single rank
@@ -875,43 +874,74 @@ __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// software grid barrier `j` of the tail kernel (all CTAs co-resident). CTA 0 resets the counter of barrier j-1 afterwards: every
-// CTA has arrived here, so none is still polling it. The last barrier of a launch is reset behind the first one of the next
-// launch; pcg_init_kernel clears all of them (a solve can end between two barriers).
-__device__ __forceinline__ void tail_grid_barrier(DevState* st, int j, int reset) {
+// software grid barrier number k of a PCG solve (all CTAs co-resident; k counts on across the launches of the solve). Barrier k
+// uses counter k % 3; once CTA 0 has seen it complete it clears the counter of barrier k-1 (every CTA has arrived here, so none
+// still polls that one), and the counter barrier k+1 will use was cleared at barrier k-1. pcg_init_kernel clears all three.
+__device__ __forceinline__ void tail_grid_barrier(DevState* st, unsigned k) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    unsigned* ctr = &st->tail_bar[k % 3u];
     __threadfence();
-    atomicAdd(&st->tail_bar[j], 1u);
+    atomicAdd(ctr, 1u);
     long long spins = 0;
-    while (ld_acquire_gpu_u32(&st->tail_bar[j]) < gridDim.x) {
+    while (ld_acquire_gpu_u32(ctr) < gridDim.x) {
       if (++spins > (1ll << 28)) __trap();   // a CTA that never arrives (not co-resident): an error the host sees, not a hang
     }
-    if (blockIdx.x == 0 && reset >= 0) st->tail_bar[reset] = 0;
+    if (blockIdx.x == 0) st->tail_bar[(k + 2u) % 3u] = 0;
   }
   __syncthreads();
 }
-// sum of part[0..n) in a fixed order, same bits in every thread of every CTA: warp 0 strides the array, butterfly, broadcast
-__device__ __forceinline__ double tail_total(const double* part, unsigned n, double* slot) {
+// sums of part[0..n) and part2[0..n) in a fixed order, same bits in every thread of every CTA: warp 0 strides the arrays,
+// butterfly, broadcast through shared memory
+__device__ __forceinline__ void tail_totals(const double* part, const double* part2, unsigned n, double* slot, double& t0, double& t1) {
   if (threadIdx.x < 32) {
-    double s = 0.0;
-    for (unsigned b = threadIdx.x; b < n; b += 32) s += __ldcg(part + b);
+    double s = 0.0, q = 0.0;
+    for (unsigned b = threadIdx.x; b < n; b += 32) { s += __ldcg(part + b); if (part2) q += __ldcg(part2 + b); }
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if (threadIdx.x == 0) *slot = s;
+    for (int d = 16; d >= 1; d >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, d); q += __shfl_xor_sync(0xffffffffu, q, d); }
+    if (threadIdx.x == 0) { slot[0] = s; slot[1] = q; }
   }
   __syncthreads();
-  const double v = *slot;
+  t0 = slot[0]; t1 = slot[1];
   __syncthreads();
-  return v;
 }
 
-template <int DC>
-__global__ void __launch_bounds__(TAIL_THREADS) pcg_tail_kernel(TailArgs a) {
+// second pass of the deterministic flush for one camera: sum of its partial rows, every lane gets all DC sums
+template <int DC, int NF>
+__device__ __forceinline__ void tail_row_sums(const TailArgs& a, uint32_t cam, int lane, double acc[DC]) {
+#pragma unroll
+  for (int k = 0; k < DC; ++k) acc[k] = 0.0;
+  const uint32_t e1 = __ldg(a.cam_row_start + cam + 1);
+  for (uint32_t e = __ldg(a.cam_row_start + cam) + lane; e < e1; e += 32 * NF) {   // NF rows per lane in flight; added in row order
+    double v[NF][DC];
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+      const bool on = e + 32 * j < e1;
+      const double* row = a.partial + (size_t)(on ? e + 32 * j : e) * DC;
+#pragma unroll
+      for (int k = 0; k < DC; ++k) v[j][k] = on ? __ldcg(row + k) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+#pragma unroll
+      for (int k = 0; k < DC; ++k) acc[k] += v[j][k];
+    }
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+#pragma unroll
+    for (int k = 0; k < DC; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
+  }
+}
+
+// ONE: every warp owns at most one camera (gridDim.x * 8 >= ncam): its rows of p, r, x, the preconditioner and H_cc blocks are
+// loaded once at entry and stay in registers across the grid barriers, so no stage waits for memory behind a barrier.
+template <int DC, bool ONE>
+__global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
   __shared__ double sh[TAIL_THREADS];
-  __shared__ double slot;
+  __shared__ double slot[2];
   DevState* st = a.st;
-  if (st->pcg_done) return;  // same value in every CTA: it is only written behind the last grid barrier of a launch
+  if (st->pcg_done) return;  // same value in every CTA: it is only written once every CTA of the launch has passed a grid barrier
   const int tid = threadIdx.x, lane = tid & 31, K = a.K;
   const uint32_t n = a.ncam * DC;
   const uint32_t gw = blockIdx.x * (TAIL_THREADS / 32) + (tid >> 5), nw = gridDim.x * (TAIL_THREADS / 32);
@@ -920,36 +950,54 @@ __global__ void __launch_bounds__(TAIL_THREADS) pcg_tail_kernel(TailArgs a) {
   const int iters0 = st->pcg_iters, max_it = st->pcg_max;
   const unsigned long long seq = st->ar_seq + 1;
   const bool multi = a.peer_buf != nullptr;
-  const int last_bar = multi ? 3 : 2;   // index of the last grid barrier of a full launch (reset behind the first one of the next)
+  unsigned kbar = (unsigned)iters0 * (multi ? 3u : 2u);   // this launch's first grid barrier in the solve's numbering
   double* ymine = multi ? a.peer_buf[a.rank] + (size_t)a.par * n : a.ylocal;
-  // ---- stage A: this rank's operator result (second pass of the deterministic flush) ----
-  if (a.cam_row_start) {
-    for (uint32_t cam = gw; cam < a.ncam; cam += nw) {
-      double acc[DC];
+  // ONE: this lane's row of everything
+  const bool act = ONE && gw < a.ncam && lane < DC;
+  const size_t myrow = (size_t)gw * DC + lane;
+  double pq = 0.0, rq = 0.0, xq = 0.0, yq = 0.0, Pq[DC > 6 ? (DC - 6 > 6 ? DC - 6 : 6) : 6], Hq[DC];
+  if (ONE) {
+    if (act) {
+      pq = a.p[myrow]; rq = a.r[myrow]; xq = a.x[myrow]; yq = ymine[myrow];
+      const double* P = a.pinv + (size_t)gw * (36 + K * K);
+      if (lane < 6) {
 #pragma unroll
-      for (int k = 0; k < DC; ++k) acc[k] = 0.0;
-      const uint32_t e1 = __ldg(a.cam_row_start + cam + 1);
-      for (uint32_t e = __ldg(a.cam_row_start + cam) + lane; e < e1; e += 32) {
-        const double* row = a.partial + (size_t)e * DC;
+        for (int b = 0; b < 6; ++b) Pq[b] = __ldg(P + lane * 6 + b);
+      } else {
 #pragma unroll
-        for (int k = 0; k < DC; ++k) acc[k] += __ldcg(row + k);
+        for (int b = 0; b < DC - 6; ++b) Pq[b] = __ldg(P + 36 + (lane - 6) * K + b);
       }
+      if (a.add_hcc) {
 #pragma unroll
-      for (int d = 16; d >= 1; d >>= 1) {
-#pragma unroll
-        for (int k = 0; k < DC; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
+        for (int b = 0; b < DC; ++b) Hq[b] = __ldg(a.hcc + myrow * DC + b);
       }
-      double mine = 0.0;
-#pragma unroll
-      for (int k = 0; k < DC; ++k) if (lane == k) mine = acc[k];
-      if (lane < DC) ymine[(size_t)cam * DC + lane] += mine;
     }
   }
-  int nb = 0;   // grid barriers passed in this launch
+  // ---- stage A: this rank's operator result (second pass of the deterministic flush) ----
+  if (a.cam_row_start) {
+    if (ONE) {
+      if (gw < a.ncam) {
+        double acc[DC];
+        tail_row_sums<DC, 2>(a, gw, lane, acc);
+#pragma unroll
+        for (int k = 0; k < DC; ++k) if (lane == k) yq += acc[k];
+        if (multi && act) ymine[myrow] = yq;
+      }
+    } else {
+      for (uint32_t cam = gw; cam < a.ncam; cam += nw) {
+        double acc[DC];
+        tail_row_sums<DC, 4>(a, cam, lane, acc);
+        double mine = 0.0;
+#pragma unroll
+        for (int k = 0; k < DC; ++k) if (lane == k) mine = acc[k];
+        if (lane < DC) ymine[(size_t)cam * DC + lane] += mine;
+      }
+    }
+  }
   if (multi) {
-    // ---- the operator result of all ranks: publish "my partial result is complete", wait for the peers, sum in rank order ----
-    __threadfence_system();
-    tail_grid_barrier(st, nb, nb == 0 ? last_bar : nb - 1); ++nb;
+    // ---- the operator result of all ranks: publish "my partial result is complete", wait for the peers, sum in rank order.
+    // (the rows written above are ordered before the flag by the grid barrier's fence + the publishing threads' system fence)
+    tail_grid_barrier(st, kbar++);
     if (blockIdx.x == 0 && tid < a.nranks) {
       __threadfence_system();
       st_release_sys(a.peer_flags[tid] + a.rank, seq);
@@ -964,53 +1012,79 @@ __global__ void __launch_bounds__(TAIL_THREADS) pcg_tail_kernel(TailArgs a) {
   }
   // ---- stage B: y (complete), pAp ----
   double v = 0.0;
-  for (uint32_t cam = gw; cam < a.ncam; cam += nw) {
-    if (lane < DC) {
-      const size_t row = (size_t)cam * DC + lane;
-      double s;
-      if (multi) { s = 0.0; for (int r = 0; r < a.nranks; ++r) s += ld_relaxed_sys(a.peer_buf[r] + (size_t)a.par * n + row); }
-      else s = ymine[row];
-      a.y[row] = s;
-      v += a.p[row] * s;
+  if (ONE) {
+    if (act) {
+      if (multi) { yq = 0.0; for (int r = 0; r < a.nranks; ++r) yq += ld_relaxed_sys(a.peer_buf[r] + (size_t)a.par * n + myrow); }
+      v = pq * yq;
+    }
+  } else {
+    for (uint32_t cam = gw; cam < a.ncam; cam += nw) {
+      if (lane < DC) {
+        const size_t row = (size_t)cam * DC + lane;
+        double s;
+        if (multi) { s = 0.0; for (int r = 0; r < a.nranks; ++r) s += ld_relaxed_sys(a.peer_buf[r] + (size_t)a.par * n + row); }
+        else s = ymine[row];
+        a.y[row] = s;
+        v += a.p[row] * s;
+      }
     }
   }
   v = block_reduce_sum(v, sh);
   if (tid == 0) a.part[blockIdx.x] = v;
-  tail_grid_barrier(st, nb, nb == 0 ? last_bar : nb - 1); ++nb;
-  const double pap = tail_total(a.part, G, &slot);
+  tail_grid_barrier(st, kbar++);
+  double pap, unused;
+  tail_totals(a.part, nullptr, G, slot, pap, unused);
   if (fabs(pap) < 1e-20 || *reinterpret_cast<volatile int32_t*>(&st->ar_timeout)) {  // break before the update (implicit_schur.rs:626-629); every CTA takes the same branch
-    tail_grid_barrier(st, nb, nb - 1); ++nb;   // nobody may still read pcg_done at entry... (all CTAs are past their entry test here)
+    // (every CTA has arrived at the barrier above, i.e. is past its entry reads of the scalars: they may be rewritten now)
     if (blockIdx.x == 0 && tid == 0) { st->pcg_iters = iters0 + 1; st->pcg_done = 1; if (multi) st->ar_seq = seq; }
     return;
   }
   const double alpha = rz_old / pap;
   // ---- stage C: x, r, z = M^-1 r, ||r||^2, r.z ----
-  double rr = 0.0, rz = 0.0;
-  for (uint32_t cam = gw; cam < a.ncam; cam += nw) {
-    const size_t row = (size_t)cam * DC + lane;
+  // z_q = sum_b P[q][b] r_b on the 6x6 pose block and the KxK intrinsics block (apply_preconditioner, implicit_schur.rs:409-443)
+  double rr = 0.0, rz = 0.0, zq = 0.0;
+  if (ONE) {
     double rv = 0.0;
-    if (lane < DC) {
-      a.x[row] += alpha * a.p[row];
-      rv = a.r[row] - alpha * a.y[row];
-      a.r[row] = rv;
-      rr += rv * rv;
+    if (act) {
+      a.x[myrow] = xq + alpha * pq;
+      rv = rq - alpha * yq;
+      a.r[myrow] = rv;
+      rr = rv * rv;
     }
-    // z_q = sum_b P[q][b] r_b on the 6x6 pose block and the KxK intrinsics block (apply_preconditioner, implicit_schur.rs:409-443)
-    const double* P = a.pinv + (size_t)cam * (36 + K * K);
-    double s = 0.0;
 #pragma unroll
     for (int b = 0; b < DC; ++b) {
       const double rb = __shfl_sync(0xffffffffu, rv, b);
-      if (lane < 6) { if (b < 6) s += __ldg(P + lane * 6 + b) * rb; }
-      else if (lane < DC) { if (b >= 6) s += __ldg(P + 36 + (lane - 6) * K + (b - 6)) * rb; }
+      if (lane < 6) { if (b < 6) zq += Pq[b] * rb; }
+      else if (lane < DC) { if (b >= 6) zq += Pq[b - 6 < 0 ? 0 : b - 6] * rb; }
     }
-    if (lane < DC) { a.z[row] = s; rz += rv * s; }
+    if (act) { a.z[myrow] = zq; rz = rv * zq; }
+  } else {
+    for (uint32_t cam = gw; cam < a.ncam; cam += nw) {
+      const size_t row = (size_t)cam * DC + lane;
+      double rv = 0.0;
+      if (lane < DC) {
+        a.x[row] += alpha * a.p[row];
+        rv = a.r[row] - alpha * a.y[row];
+        a.r[row] = rv;
+        rr += rv * rv;
+      }
+      const double* P = a.pinv + (size_t)cam * (36 + K * K);
+      double s = 0.0;
+#pragma unroll
+      for (int b = 0; b < DC; ++b) {
+        const double rb = __shfl_sync(0xffffffffu, rv, b);
+        if (lane < 6) { if (b < 6) s += __ldg(P + lane * 6 + b) * rb; }
+        else if (lane < DC) { if (b >= 6) s += __ldg(P + 36 + (lane - 6) * K + (b - 6)) * rb; }
+      }
+      if (lane < DC) { a.z[row] = s; rz += rv * s; }
+    }
   }
   rr = block_reduce_sum(rr, sh);
   rz = block_reduce_sum(rz, sh);
   if (tid == 0) { a.part[G + blockIdx.x] = rr; a.part[2 * G + blockIdx.x] = rz; }
-  tail_grid_barrier(st, nb, nb - 1); ++nb;
-  const double rr_tot = tail_total(a.part + G, G, &slot), rz_tot = tail_total(a.part + 2 * G, G, &slot);
+  tail_grid_barrier(st, kbar++);
+  double rr_tot, rz_tot;
+  tail_totals(a.part + G, a.part + 2 * G, G, slot, rr_tot, rz_tot);
   const int iters = iters0 + 1;
   const double r_norm = sqrt(rr_tot);
   bool done = r_norm < tol || fabs(rz_old) < 1e-30;
@@ -1019,27 +1093,42 @@ __global__ void __launch_bounds__(TAIL_THREADS) pcg_tail_kernel(TailArgs a) {
   if (have_beta) { beta = rz_tot / rz_old; if (iters >= max_it) done = true; }
   // ---- stage D: next direction and the start value of the next operator result ----
   if (!done) {
-    for (uint32_t cam = gw; cam < a.ncam; cam += nw) {
-      const size_t row = (size_t)cam * DC + lane;
+    if (ONE) {
       double pv = 0.0;
-      if (lane < DC) {
-        const double zv = a.z[row];
-        pv = beta == 0.0 ? zv : zv + beta * a.p[row];
-        a.p[row] = pv;
-        a.xpad[(size_t)cam * a.xs + lane] = pv;
+      if (act) {
+        pv = beta == 0.0 ? zq : zq + beta * pq;
+        a.p[myrow] = pv;
+        a.xpad[(size_t)gw * a.xs + lane] = pv;
       }
       double s = damping * pv;
-      const double* H = a.hcc + ((size_t)cam * DC + (lane < DC ? lane : 0)) * DC;
 #pragma unroll
       for (int b = 0; b < DC; ++b) {
         const double pb = __shfl_sync(0xffffffffu, pv, b);
-        if (a.add_hcc && lane < DC) s += __ldg(H + b) * pb;
+        if (a.add_hcc && act) s += Hq[b] * pb;
       }
-      if (lane < DC) a.y0_next[row] = a.add_hcc ? s : 0.0;
+      if (act) a.y0_next[myrow] = a.add_hcc ? s : 0.0;
+    } else {
+      for (uint32_t cam = gw; cam < a.ncam; cam += nw) {
+        const size_t row = (size_t)cam * DC + lane;
+        double pv = 0.0;
+        if (lane < DC) {
+          const double zv = a.z[row];
+          pv = beta == 0.0 ? zv : zv + beta * a.p[row];
+          a.p[row] = pv;
+          a.xpad[(size_t)cam * a.xs + lane] = pv;
+        }
+        double s = damping * pv;
+        const double* H = a.hcc + ((size_t)cam * DC + (lane < DC ? lane : 0)) * DC;
+#pragma unroll
+        for (int b = 0; b < DC; ++b) {
+          const double pb = __shfl_sync(0xffffffffu, pv, b);
+          if (a.add_hcc && lane < DC) s += __ldg(H + b) * pb;
+        }
+        if (lane < DC) a.y0_next[row] = a.add_hcc ? s : 0.0;
+      }
     }
   }
-  // pcg_done / the scalars the next launch reads at entry are written behind a barrier every CTA has passed its entry test before
-  tail_grid_barrier(st, nb, nb - 1); ++nb;
+  // (every CTA passed its entry reads of these scalars before it arrived at the last barrier)
   if (blockIdx.x == 0 && tid == 0) {
     st->pcg_iters = iters;
     st->r_norm = r_norm;
@@ -1050,24 +1139,46 @@ __global__ void __launch_bounds__(TAIL_THREADS) pcg_tail_kernel(TailArgs a) {
   }
 }
 
-// CTAs of the fused tail (0 = the separate kernels): one warp per camera, at most two CTAs per SM so that all are co-resident
-static int pcg_tail_ctas(Ctx& c) {
+// CTAs of the fused tail (0 = the separate kernels): one warp per camera when the device can keep that many CTAs resident at
+// once (occupancy of the instantiation x SMs, at most APEX_PCG_TAIL = 2 per SM), else the grid-stride variant on as many CTAs
+// as are co-resident. The grid barriers need every CTA of the launch on an SM at the same time.
+template <int DC>
+static int tail_plan_dc(Ctx& c, bool& one) {
   const char* e = getenv("APEX_PCG_TAIL");
   const int want = e ? atoi(e) : 2;
   if (want <= 0) return 0;
-  const int per_sm = std::min(want, 4);
-  return (int)std::max<uint32_t>(1, std::min<uint32_t>((c.ncam + 7) / 8, (uint32_t)(per_sm * c.num_sms)));
+  const int per_sm_want = std::min(want, 4);
+  const uint32_t need = (c.ncam + TAIL_THREADS / 32 - 1) / (TAIL_THREADS / 32);
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_tail_kernel<DC, true>, TAIL_THREADS, 0) == cudaSuccess && occ > 0 &&
+      need <= (uint32_t)(std::min(occ, per_sm_want) * c.num_sms)) { one = true; return (int)std::max<uint32_t>(need, 1); }
+  cudaGetLastError();
+  one = false;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_tail_kernel<DC, false>, TAIL_THREADS, 0) != cudaSuccess || occ <= 0) { cudaGetLastError(); return 0; }
+  return (int)std::max<uint32_t>(1, std::min<uint32_t>(need, (uint32_t)(std::min(occ, per_sm_want) * c.num_sms)));
+}
+static int pcg_tail_plan(Ctx& c, bool& one) {
+  switch (c.dc) {
+    case 6: return tail_plan_dc<6>(c, one);
+    case 9: return tail_plan_dc<9>(c, one);
+    case 10: return tail_plan_dc<10>(c, one);
+    case 11: return tail_plan_dc<11>(c, one);
+    case 12: return tail_plan_dc<12>(c, one);
+    case 14: return tail_plan_dc<14>(c, one);
+    case 15: return tail_plan_dc<15>(c, one);
+    default: return 0;
+  }
 }
 
-static apex_status launch_pcg_tail(Ctx& c, const TailArgs& a, int ctas) {
+static apex_status launch_pcg_tail(Ctx& c, const TailArgs& a, int ctas, bool one) {
   switch (c.dc) {
-    case 6: pcg_tail_kernel<6><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
-    case 9: pcg_tail_kernel<9><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
-    case 10: pcg_tail_kernel<10><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
-    case 11: pcg_tail_kernel<11><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
-    case 12: pcg_tail_kernel<12><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
-    case 14: pcg_tail_kernel<14><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
-    case 15: pcg_tail_kernel<15><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
+    case 6: if (one) pcg_tail_kernel<6, true><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); else pcg_tail_kernel<6, false><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
+    case 9: if (one) pcg_tail_kernel<9, true><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); else pcg_tail_kernel<9, false><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
+    case 10: if (one) pcg_tail_kernel<10, true><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); else pcg_tail_kernel<10, false><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
+    case 11: if (one) pcg_tail_kernel<11, true><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); else pcg_tail_kernel<11, false><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
+    case 12: if (one) pcg_tail_kernel<12, true><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); else pcg_tail_kernel<12, false><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
+    case 14: if (one) pcg_tail_kernel<14, true><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); else pcg_tail_kernel<14, false><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
+    case 15: if (one) pcg_tail_kernel<15, true><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); else pcg_tail_kernel<15, false><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
     default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
   }
   c.launches++;
@@ -1292,7 +1403,8 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
   // launch: the inner loop is launch-bound on small shards (8 GPUs: ~35 us of kernels per iteration).
   const int BATCH = 10;
   int it_count = 0;  // iteration index within this solve: selects the half of the peer buffer (BATCH is even)
-  const int tail_ctas = (c.nranks == 1 || c.p2p_ok) ? pcg_tail_ctas(c) : 0;
+  bool tail_one = false;
+  const int tail_ctas = (c.nranks == 1 || c.p2p_ok) ? pcg_tail_plan(c, tail_one) : 0;
   if (tail_ctas && cg_max_it > 0) {  // first direction p = z and y0 = (H_cc + lambda I) p into half 0; later ones come from the tail
     const int xs = xpad_stride(c.dc);
     double* y0 = c.p2p_ok ? c.arbuf.p : c.vy.p;
@@ -1325,7 +1437,7 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
       ta.p = c.vp.p; ta.x = c.step_cam.p; ta.r = c.vr.p; ta.z = c.vz.p; ta.xpad = c.xpad.p;
       ta.pinv = c.pinv.p; ta.hcc = c.hcc.p; ta.part = c.red_scratch.p; ta.st = c.state.p;
       ta.ncam = c.ncam; ta.K = c.K; ta.xs = xs; ta.add_hcc = c.rank == 0 ? 1 : 0;
-      APEX_TRY(launch_pcg_tail(c, ta, tail_ctas));
+      APEX_TRY(launch_pcg_tail(c, ta, tail_ctas, tail_one));
       return APEX_OK;
     }
     {
