@@ -102,7 +102,8 @@ struct ShardMap {
 };
 constexpr int MAX_TILE_PTS = 128;     // landmarks per normal tile
 
-struct CamItem { uint32_t cam, begin, end, pad; };  // [begin,end) in the camera-major arrays
+struct CamItem { uint32_t cam, begin, end, pad; };
+struct LossSpecPod { int id; double p0, p1; };   // layout of ba_device.cuh's LossSpec (one LossFunction instance on the device)  // [begin,end) in the camera-major arrays
 
 // Scalars that live on the device (LM bookkeeping, PCG control, norms, error flags).
 struct DevState {
@@ -225,6 +226,7 @@ struct Ctx {
   uint64_t cam_dof_ref = 0;  // reference-layout camera dof (includes unreferenced intr columns)
   int loss_id = 0;
   double loss_p[4] = {0, 0, 0, 0};
+  bool per_obs_loss = false;         // per-block loss functions (apex_problem_desc::obs_loss)
   uint32_t npl = 0;                  // landmarks owned by this rank (block-cyclic, see ShardMap)
   uint64_t nobs_local = 0;
   ShardMap shard;
@@ -260,6 +262,8 @@ struct Ctx {
   DevBuf<uint32_t> win_dst;          // ... and entry i of win_cams flushes to row win_dst[i] (a camera's rows in (range, window) order)
   DevBuf<double> det_partial;        // [mv_nrows][dc]
   DevBuf<double> slot_uv;            // [chunk][2][TILE]
+  DevBuf<uint8_t> slot_loss, cm_loss; // per-block loss index per slot / per camera-major observation (only with obs_loss)
+  DevBuf<LossSpecPod> loss_tab;      // {id, p0, p1} per entry of the caller's loss_table
   DevBuf<uint32_t> pt_slot0, pt_cnt; // per local landmark
   DevBuf<CamItem> items;
   DevBuf<uint32_t> cam_item_start;   // [ncam+1]

@@ -54,6 +54,8 @@ struct LinArgs {
   double* tile_partial;
   uint32_t npl;
   LossSpec loss;
+  const uint8_t* slot_loss;   // per-block loss functions: index into loss_tab per slot, or null (uniform `loss`)
+  const LossSpec* loss_tab;
   DevState* st;
 };
 
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(TILE, 3) linearize_tile_kernel(LinArgs a) {
       for (int k = 0; k < K; ++k) in[k] = a.intr[(size_t)cam * K + k];
       const V3 pw{a.pt[3 * (size_t)lp], a.pt[3 * (size_t)lp + 1], a.pt[3 * (size_t)lp + 2]};
       const double u = a.slot_uv[(chunk * 2 + 0) * TILE + tid], v = a.slot_uv[(chunk * 2 + 1) * TILE + tid];
-      linearize_obs<MODEL, OPT_INTR, true>(a.loss, pose, in, pw, u, v, r, jc, jp);
+      linearize_obs<MODEL, OPT_INTR, true>(a.slot_loss ? a.loss_tab[a.slot_loss[slot]] : a.loss, pose, in, pw, u, v, r, jc, jp);
     } else {
 #pragma unroll
       for (int k = 0; k < 2 * DC; ++k) jc[k] = 0.0;
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(TILE) cost_tile_kernel(LinArgs a) {
       const V3 pw{a.pt[3 * (size_t)lp], a.pt[3 * (size_t)lp + 1], a.pt[3 * (size_t)lp + 2]};
       const double u = a.slot_uv[(chunk * 2 + 0) * TILE + tid], v = a.slot_uv[(chunk * 2 + 1) * TILE + tid];
       double r[2];
-      linearize_obs<MODEL, OPT_INTR, false>(a.loss, pose, in, pw, u, v, r, nullptr, nullptr);
+      linearize_obs<MODEL, OPT_INTR, false>(a.slot_loss ? a.loss_tab[a.slot_loss[slot]] : a.loss, pose, in, pw, u, v, r, nullptr, nullptr);
       acc += r[0] * r[0] + r[1] * r[1];
     }
   }
@@ -216,6 +218,7 @@ __global__ void __launch_bounds__(TILE) cost_tile_kernel(LinArgs a) {
 //   WHAT = 1: sum_j H_cp[i,j] H_pp[j]^-1 H_cp[i,j]^T per camera VARIABLE block (pose 6x6, intrinsics KxK)
 //             (implicit_schur.rs:456-573)
 // ----------------------------------------------------------------------------------------------------
+static_assert(sizeof(LossSpec) == sizeof(LossSpecPod), "loss table entries are uploaded as LossSpecPod");
 struct CamArgs {
   const CamItem* items;
   const uint32_t* cam_item_start;
@@ -233,6 +236,8 @@ struct CamArgs {
   uint32_t ncam;
   uint64_t nobs_local;
   LossSpec loss;
+  const uint8_t* cm_loss;     // per-block loss functions, camera-major order, or null
+  const LossSpec* loss_tab;
 };
 
 template <int MODEL, bool OPT_INTR, int WHAT>
@@ -263,7 +268,7 @@ __global__ void __launch_bounds__(CAM_THREADS) camera_accum_kernel(CamArgs a) {
     const double u = a.cm_uv[o], v = a.cm_uv[a.nobs_local + o];
     const V3 pw{a.pt[3 * (size_t)lp], a.pt[3 * (size_t)lp + 1], a.pt[3 * (size_t)lp + 2]};
     double r[2], jc[2 * DC], jp[6];
-    linearize_obs<MODEL, OPT_INTR, true>(a.loss, pose, in, pw, u, v, r, jc, jp);
+    linearize_obs<MODEL, OPT_INTR, true>(a.cm_loss ? a.loss_tab[a.cm_loss[o]] : a.loss, pose, in, pw, u, v, r, jc, jp);
     if constexpr (WHAT == 0) {
       int idx = 0;
 #pragma unroll
@@ -415,6 +420,7 @@ static LinArgs make_lin_args(Ctx& c) {
   a.tile_partial = c.red_scratch.p;
   a.npl = c.npl;
   a.loss = {c.loss_id, c.loss_p[0], c.loss_p[1]};
+  a.slot_loss = c.per_obs_loss ? c.slot_loss.p : nullptr; a.loss_tab = reinterpret_cast<const LossSpec*>(c.loss_tab.p);
   a.st = c.state.p;
   return a;
 }
@@ -426,6 +432,7 @@ static CamArgs make_cam_args(Ctx& c) {
   a.partial = c.partial.p; a.hcc = c.hcc.p; a.gc = c.gc; a.sj = c.sj.p;
   a.npl = c.npl; a.ncam = c.ncam; a.nobs_local = c.nobs_local;
   a.loss = {c.loss_id, c.loss_p[0], c.loss_p[1]};
+  a.cm_loss = c.per_obs_loss ? c.cm_loss.p : nullptr; a.loss_tab = reinterpret_cast<const LossSpec*>(c.loss_tab.p);
   return a;
 }
 

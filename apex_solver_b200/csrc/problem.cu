@@ -49,10 +49,19 @@ apex_status validate_problem(const apex_problem_desc* d, std::string& err) {
   if (d->nobs > 0xFFFFFFF0ull) { err = "too many observations for u32 slots"; return APEX_ERR_UNSUPPORTED; }
   if (d->loss_id < APEX_LOSS_NONE || d->loss_id > APEX_LOSS_T_DISTRIBUTION) { err = "unknown loss id"; return APEX_ERR_INVALID_INPUT; }
   const uint64_t nobs = d->nobs;
-  int bad = 0;
-#pragma omp parallel for reduction(| : bad) schedule(static)
-  for (int64_t o = 0; o < (int64_t)nobs; ++o) bad |= (d->obs_cam[o] >= d->ncam || d->obs_pt[o] >= d->npts) ? 1 : 0;
+  if (d->obs_loss) {
+    if (!d->loss_table || d->n_losses < 1 || d->n_losses > 256) { err = "obs_loss needs a loss_table of 1..256 entries"; return APEX_ERR_INVALID_INPUT; }
+    for (int i = 0; i < d->n_losses; ++i)
+      if (d->loss_table[i].loss_id < APEX_LOSS_NONE || d->loss_table[i].loss_id > APEX_LOSS_T_DISTRIBUTION) { err = "unknown loss id in loss_table"; return APEX_ERR_INVALID_INPUT; }
+  }
+  int bad = 0, bad_loss = 0;
+#pragma omp parallel for reduction(| : bad, bad_loss) schedule(static)
+  for (int64_t o = 0; o < (int64_t)nobs; ++o) {
+    bad |= (d->obs_cam[o] >= d->ncam || d->obs_pt[o] >= d->npts) ? 1 : 0;
+    if (d->obs_loss) bad_loss |= d->obs_loss[o] >= d->n_losses ? 1 : 0;
+  }
   if (bad) { err = "observation index out of range"; return APEX_ERR_INVALID_INPUT; }
+  if (bad_loss) { err = "obs_loss index out of range"; return APEX_ERR_INVALID_INPUT; }
   return APEX_OK;
 }
 
@@ -68,6 +77,7 @@ struct HostLayout {
   StageBuf<uint32_t> slot_cam;
   StageBuf<uint16_t> slot_lp;
   StageBuf<double> slot_uv;
+  StageBuf<uint8_t> slot_loss, cm_loss;   // per-block loss indices (only when the problem has obs_loss)
   HostVec<uint64_t> slot_obs;
   HostVec<uint8_t> slot_pos;
   std::vector<ChunkDesc> chunk_desc;
@@ -204,6 +214,7 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
   L.slot_uv.resize(nslots * 2);
   L.slot_obs.resize(nslots);
   L.slot_pos.resize(nslots);
+  L.slot_loss.resize(d->obs_loss ? nslots : 0);
   L.chunk_desc.assign(L.nnormal_chunks, ChunkDesc{0, 0, 0, 0});
   L.cslot_meta.resize((size_t)L.nnormal_chunks * TILE);
   L.cpt_meta.assign(npl, 0);
@@ -212,6 +223,7 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
     std::fill_n(L.slot_lp.begin() + ch * TILE, TILE, (uint16_t)0);
     std::fill_n(L.slot_uv.begin() + ch * 2 * TILE, 2 * TILE, 0.0);
     std::fill_n(L.slot_obs.begin() + ch * TILE, TILE, UINT64_MAX);
+    if (d->obs_loss) std::fill_n(L.slot_loss.begin() + ch * TILE, TILE, (uint8_t)0);
     for (int t = 0; t < TILE; ++t) L.slot_pos[ch * TILE + t] = (uint8_t)t;  // default: camera half at the slot's own lane
   };
   const int64_t ntiles = (int64_t)L.tiles.size();
@@ -240,6 +252,7 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
           L.slot_uv[(ch * 2 + 0) * TILE + lane] = d->obs_uv[2 * o];
           L.slot_uv[(ch * 2 + 1) * TILE + lane] = d->obs_uv[2 * o + 1];
           L.slot_obs[slot] = o;
+          if (d->obs_loss) L.slot_loss[slot] = d->obs_loss[o];
           if (t.nchunks == 1) {
             L.cslot_meta[slot].y = i;  // [7:0] chunk-local landmark of point-major lane off + k
             order.push_back({cam, off + k});
@@ -360,6 +373,7 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
   std::vector<uint32_t> cam_start((size_t)ncam + 1, 0);
   L.cm_uv.resize(2 * (size_t)L.nobs_local);
   L.cm_lp.resize(L.nobs_local);
+  L.cm_loss.resize(d->obs_loss ? L.nobs_local : 0);
   {
     const int T = L.nobs_local < 100000 ? 1 : std::max(1, std::min(omp_get_max_threads(), 64));
     std::vector<std::vector<uint32_t>> cnt(T, std::vector<uint32_t>(ncam, 0));
@@ -386,6 +400,7 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
           L.cm_uv[pos] = d->obs_uv[2 * o];
           L.cm_uv[(size_t)L.nobs_local + pos] = d->obs_uv[2 * o + 1];
           L.cm_lp[pos] = lp;
+          if (d->obs_loss) L.cm_loss[pos] = d->obs_loss[o];
         }
     }
   }
@@ -532,6 +547,7 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   c.cam_dof_ref = (uint64_t)c.ncam * (6 + ((c.opt_intr || c.intr_vars) ? K : 0));
   c.loss_id = d->loss_id;
   for (int i = 0; i < 4; ++i) c.loss_p[i] = d->loss_params[i];
+  c.per_obs_loss = d->obs_loss != nullptr;
 
   if (!c.staging) {
     auto hl = std::make_shared<HostLayout>();
@@ -575,6 +591,14 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   APEX_CUDA_TRY(c, upload_vec(c.slot_cam, L.slot_cam, s));
   APEX_CUDA_TRY(c, upload_vec(c.slot_lp, L.slot_lp, s));
   APEX_CUDA_TRY(c, upload_vec(c.slot_uv, L.slot_uv, s));
+  if (c.per_obs_loss) {
+    std::vector<LossSpecPod> tab(d->n_losses);
+    for (int i = 0; i < d->n_losses; ++i) tab[i] = LossSpecPod{d->loss_table[i].loss_id, d->loss_table[i].params[0], d->loss_table[i].params[1]};
+    APEX_CUDA_TRY(c, upload_vec(c.slot_loss, L.slot_loss, s));
+    APEX_CUDA_TRY(c, upload_vec(c.cm_loss, L.cm_loss, s));
+    APEX_CUDA_TRY(c, upload_vec(c.loss_tab, tab, s));
+    APEX_CUDA_TRY(c, cudaStreamSynchronize(s));   // `tab` dies with this scope
+  }
   APEX_CUDA_TRY(c, upload_vec(c.pt_slot0, L.pt_slot0, s));
   APEX_CUDA_TRY(c, upload_vec(c.pt_cnt, L.pt_cnt, s));
   APEX_CUDA_TRY(c, upload_vec(c.chunk_desc, L.chunk_desc, s));

@@ -1217,6 +1217,10 @@ struct Ctx {
   std::vector<double> pose, intr, pt;  // current variable values
   std::vector<uint32_t> obs_cam, obs_pt; std::vector<double> uv;
   int loss_id = 0; double loss_prm[4] = {0, 0, 0, 0};
+  // per-block loss functions (ResidualBlock owns its own Option<Box<dyn LossFunction>>, src/core/residual_block.rs:97-123)
+  std::vector<uint8_t> obs_loss; std::vector<apex_loss_spec> loss_table;
+  int loss_id_of(uint64_t o) const { return obs_loss.empty() ? loss_id : loss_table[obs_loss[o]].loss_id; }
+  const double* loss_prm_of(uint64_t o) const { return obs_loss.empty() ? loss_prm : loss_table[obs_loss[o]].params; }
   std::vector<uint8_t> pose_fixed, pt_fixed; std::vector<uint16_t> intr_fixed;
   // derived structure
   bool opt_intr = false;
@@ -1303,7 +1307,7 @@ void linearize(Ctx& c, double lambda) {
     uint32_t cam = c.obs_cam[o], p = c.obs_pt[o];
     Pose pose = pose_from7(&c.pose[7 * (size_t)cam]);
     V3 pw{c.pt[3 * (size_t)p], c.pt[3 * (size_t)p + 1], c.pt[3 * (size_t)p + 2]};
-    linearize_obs(c.model, c.K, c.opt_intr, c.loss_id, c.loss_prm, pose, &c.intr[(size_t)c.K * cam], pw, &c.uv[2 * o], true, c.lin[o]);
+    linearize_obs(c.model, c.K, c.opt_intr, c.loss_id_of(o), c.loss_prm_of(o), pose, &c.intr[(size_t)c.K * cam], pw, &c.uv[2 * o], true, c.lin[o]);
   }
   const int dc = c.dc;
   c.hcc.assign((size_t)c.ncam * dc * dc, 0.0);
@@ -1362,7 +1366,7 @@ double cost_at(const Ctx& c, const std::vector<double>& pose, const std::vector<
     Pose ps = pose_from7(&pose[7 * (size_t)cam]);
     V3 pw{pt[3 * (size_t)p], pt[3 * (size_t)p + 1], pt[3 * (size_t)p + 2]};
     BlockLin b;
-    linearize_obs(c.model, c.K, c.opt_intr, c.loss_id, c.loss_prm, ps, &intr[(size_t)c.K * cam], pw, &c.uv[2 * o], false, b);
+    linearize_obs(c.model, c.K, c.opt_intr, c.loss_id_of(o), c.loss_prm_of(o), ps, &intr[(size_t)c.K * cam], pw, &c.uv[2 * o], false, b);
     r[2 * o] = b.r[0]; r[2 * o + 1] = b.r[1];
   }
   return compute_cost(r.data(), r.size());
@@ -1902,6 +1906,14 @@ apex_status oracle_problem_upload(oracle_ctx* ctx, const apex_problem_desc* d) {
     if (c.obs_cam[o] >= c.ncam || c.obs_pt[o] >= c.npts) { c.err = "observation index out of range"; return APEX_ERR_INVALID_INPUT; }
   c.loss_id = d->loss_id;
   for (int i = 0; i < 4; ++i) c.loss_prm[i] = d->loss_params[i];
+  c.obs_loss.clear(); c.loss_table.clear();
+  if (d->obs_loss) {
+    if (!d->loss_table || d->n_losses < 1 || d->n_losses > 256) { c.err = "obs_loss needs a loss_table of 1..256 entries"; return APEX_ERR_INVALID_INPUT; }
+    c.loss_table.assign(d->loss_table, d->loss_table + d->n_losses);
+    c.obs_loss.assign(d->obs_loss, d->obs_loss + c.nobs);
+    for (uint64_t o = 0; o < c.nobs; ++o)
+      if (c.obs_loss[o] >= d->n_losses) { c.err = "obs_loss index out of range"; return APEX_ERR_INVALID_INPUT; }
+  }
   c.pose_fixed.clear(); c.intr_fixed.clear(); c.pt_fixed.clear();
   if (d->pose_fixed) c.pose_fixed.assign(d->pose_fixed, d->pose_fixed + c.ncam);
   if (d->intr_fixed) c.intr_fixed.assign(d->intr_fixed, d->intr_fixed + c.ncam);

@@ -104,6 +104,27 @@ def test_linearize_blocks_cost_matvec(name, kw):
     assert relerr(g.schur_matvec(x), yg) < 1e-13  # default path: FP64 reductions into L2, order may differ run to run
 
 
+@pytest.mark.parametrize("model", [F.CAM_BAL, F.CAM_KANNALA_BRANDT], ids=["bal", "kb"])
+def test_per_block_loss_functions(model):
+    """apex_problem_desc::obs_loss / loss_table (every ResidualBlock owns its own loss, src/core/residual_block.rs:97-123): four
+    LossFunction instances drawn per observation. K1 (slot order), the cost kernel and the camera-major accumulations (which
+    re-evaluate the corrector) must all pick the block's own loss: residuals, Jacobians, blocks and an LM run against the oracle."""
+    import dataclasses
+    base = small_problem(model=model, ncam=14, npts=500)
+    table = [(F.LOSS_HUBER, 1.0), (F.LOSS_CAUCHY, 2.0), (F.LOSS_NONE,), (F.LOSS_TUKEY, 4.0)]
+    idx = np.random.default_rng(3).integers(0, len(table), base.nobs).astype(np.uint8)
+    prob = dataclasses.replace(base, obs_loss=idx, loss_table=table, meta={})
+    g, o = pair(prob)
+    assert abs(g.cost() - o.cost()) <= 1e-13 * abs(o.cost())
+    assert abs(g.cost() - GpuContext().upload(base).cost()) > 1e-6 * abs(o.cost()), "the table must matter"
+    g.linearize(1e-3); o.linearize(1e-3)
+    for a, b, what in zip(g.get_linearization(), o.get_linearization(), ("residuals", "camera Jacobians", "landmark Jacobians")):
+        assert relerr(a, b) < 1e-12, what
+    assert_blocks_close(g, o, prob, 1e-3)
+    teacher_forced(prob, F.SCHUR_EXPLICIT, n_it=4)
+    teacher_forced(prob, F.SCHUR_IMPLICIT, n_it=4)
+
+
 @pytest.mark.parametrize("variant", [F.SCHUR_EXPLICIT, F.SCHUR_IMPLICIT, F.SCHUR_EXPLICIT_PCG], ids=["explicit", "implicit", "explicit_pcg"])
 @pytest.mark.parametrize("self_cal", [True, False], ids=["selfcal", "ba"])
 def test_solve_augmented(variant, self_cal):

@@ -8,6 +8,8 @@ import subprocess
 import sys
 
 import numpy as np
+import dataclasses
+
 import pytest
 
 from apex_solver_b200 import _ffi as F, synth
@@ -190,6 +192,41 @@ def test_oracle_linear_solve_matches_scipy():
     Hcc, Hcp, Hpp = H[:ncam * dc, :ncam * dc], H[:ncam * dc, ncam * dc:], H[ncam * dc:, ncam * dc:]
     S = Hcc - Hcp @ np.linalg.solve(Hpp, Hcp.T)
     assert np.abs(o.schur_matvec(x) - S @ x).max() <= 1e-9 * np.abs(S @ x).max()
+
+
+def mixed_loss_problem(prob, seed=3):
+    """Per-block loss functions (src/core/residual_block.rs:97-123): every observation draws one of four LossFunction instances."""
+    table = [(F.LOSS_HUBER, 1.0), (F.LOSS_CAUCHY, 2.0), (F.LOSS_NONE,), (F.LOSS_TUKEY, 4.0)]
+    idx = np.random.default_rng(seed).integers(0, len(table), prob.nobs).astype(np.uint8)
+    return dataclasses.replace(prob, obs_loss=idx, loss_table=table, meta={}), table, idx
+
+
+def test_oracle_per_block_loss_is_the_sum_over_loss_classes():
+    """Oracle with a per-block loss table: the cost is the sum of the costs of the sub-problems that hold the observations of
+    one loss each (uniform-loss path), a table whose entries are all the same loss reproduces the uniform problem bit for bit,
+    and indices outside the table are rejected."""
+    base = synth.make_problem(10, 300, 4.0, seed=17)
+    prob, table, idx = mixed_loss_problem(base)
+    o = OracleContext().upload(prob)
+    total = 0.0
+    for k, spec in enumerate(table):
+        m = idx == k
+        lp = tuple(spec[1:]) + (0.0,) * 4
+        sub = dataclasses.replace(base, obs_cam=base.obs_cam[m], obs_pt=base.obs_pt[m], obs_uv=base.obs_uv[m], loss_id=spec[0], loss_params=lp[:4], meta={})
+        total += OracleContext().upload(sub).cost()
+    assert abs(o.cost() - total) <= 1e-12 * total
+    same = dataclasses.replace(base, obs_loss=np.zeros(base.nobs, np.uint8), loss_table=[(base.loss_id,) + tuple(base.loss_params)], meta={})
+    a, b = OracleContext().upload(same), OracleContext().upload(base)
+    assert a.cost() == b.cost()
+    a.linearize(1e-3); b.linearize(1e-3)
+    assert all(np.array_equal(x, y) for x, y in zip(a.get_blocks(), b.get_blocks()))
+    bad = dataclasses.replace(base, obs_loss=np.full(base.nobs, 7, np.uint8), loss_table=table, meta={})
+    with pytest.raises(F.ApexError) as e:
+        OracleContext().upload(bad)
+    assert e.value.status == F.ERR_INVALID_INPUT
+    with pytest.raises(F.ApexError) as e:
+        layout_stats(bad)
+    assert e.value.status == F.ERR_INVALID_INPUT
 
 
 def test_bench_reference_arm_contract():
