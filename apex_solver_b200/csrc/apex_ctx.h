@@ -226,6 +226,7 @@ struct Ctx {
   uint64_t cam_dof_ref = 0;  // reference-layout camera dof (includes unreferenced intr columns)
   int loss_id = 0;
   double loss_p[4] = {0, 0, 0, 0};
+  bool jacobi_on = false;            // linearisation applies the Jacobi column scaling (inside lm_solve with use_jacobi_scaling)
   bool per_obs_loss = false;         // per-block loss functions (apex_problem_desc::obs_loss)
   uint32_t npl = 0;                  // landmarks owned by this rank (block-cyclic, see ShardMap)
   uint64_t nobs_local = 0;
@@ -283,6 +284,7 @@ struct Ctx {
   DevBuf<double> hcc;                // [ncam][dc][dc] followed by g_c [ncam][dc] (one all-reduce)
   double* gc = nullptr;              // = hcc.p + ncam*dc*dc
   DevBuf<double> partial;            // [nitems][nacc] camera work-item partial sums
+  DevBuf<double> scale_cam, scale_pt; // Jacobi column scaling 1 / (1 + ||column||): [ncam][dc], [npl][3] (allocated on first use)
   DevBuf<double> sj;                 // [ncam][36 + K*K] Schur-Jacobi subtrahends
   DevBuf<double> pinv;               // [ncam][36 + K*K] preconditioner block inverses
   bool linearized = false;

@@ -56,8 +56,20 @@ struct LinArgs {
   LossSpec loss;
   const uint8_t* slot_loss;   // per-block loss functions: index into loss_tab per slot, or null (uniform `loss`)
   const LossSpec* loss_tab;
+  const double* scale_cam;    // Jacobi column scaling [ncam][dc] / [npl][3], or null (off)
+  const double* scale_pt;
   DevState* st;
 };
+
+// J * diag(scaling) for one block (apply_column_scaling, src/linearizer/mod.rs:240-252): camera columns by the camera's
+// scaling row, landmark columns by the landmark's
+template <int DC>
+__device__ __forceinline__ void scale_block(double* jc, double* jp, const double* __restrict__ sc, const double* __restrict__ sp) {
+#pragma unroll
+  for (int k = 0; k < DC; ++k) { const double f = sc[k]; jc[k] *= f; jc[DC + k] *= f; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { const double f = sp[k]; jp[k] *= f; jp[3 + k] *= f; }
+}
 
 // landmark block: store H_pp, g_p; damp with lambda*I (explicit_schur.rs:1208-1212, implicit_schur.rs:1053-1068);
 // guarded inverse (explicit_schur.rs:377-442)
@@ -109,6 +121,7 @@ __global__ void __launch_bounds__(TILE, 3) linearize_tile_kernel(LinArgs a) {
       const V3 pw{a.pt[3 * (size_t)lp], a.pt[3 * (size_t)lp + 1], a.pt[3 * (size_t)lp + 2]};
       const double u = a.slot_uv[(chunk * 2 + 0) * TILE + tid], v = a.slot_uv[(chunk * 2 + 1) * TILE + tid];
       linearize_obs<MODEL, OPT_INTR, true>(a.slot_loss ? a.loss_tab[a.slot_loss[slot]] : a.loss, pose, in, pw, u, v, r, jc, jp);
+      if (a.scale_cam) scale_block<DC>(jc, jp, a.scale_cam + (size_t)cam * DC, a.scale_pt + 3 * (size_t)lp);
     } else {
 #pragma unroll
       for (int k = 0; k < 2 * DC; ++k) jc[k] = 0.0;
@@ -238,6 +251,8 @@ struct CamArgs {
   LossSpec loss;
   const uint8_t* cm_loss;     // per-block loss functions, camera-major order, or null
   const LossSpec* loss_tab;
+  const double* scale_cam;    // Jacobi column scaling, or null
+  const double* scale_pt;
 };
 
 template <int MODEL, bool OPT_INTR, int WHAT>
@@ -269,6 +284,7 @@ __global__ void __launch_bounds__(CAM_THREADS) camera_accum_kernel(CamArgs a) {
     const V3 pw{a.pt[3 * (size_t)lp], a.pt[3 * (size_t)lp + 1], a.pt[3 * (size_t)lp + 2]};
     double r[2], jc[2 * DC], jp[6];
     linearize_obs<MODEL, OPT_INTR, true>(a.cm_loss ? a.loss_tab[a.cm_loss[o]] : a.loss, pose, in, pw, u, v, r, jc, jp);
+    if (a.scale_cam) scale_block<DC>(jc, jp, a.scale_cam + (size_t)item.cam * DC, a.scale_pt + 3 * (size_t)lp);
     if constexpr (WHAT == 0) {
       int idx = 0;
 #pragma unroll
@@ -421,6 +437,7 @@ static LinArgs make_lin_args(Ctx& c) {
   a.npl = c.npl;
   a.loss = {c.loss_id, c.loss_p[0], c.loss_p[1]};
   a.slot_loss = c.per_obs_loss ? c.slot_loss.p : nullptr; a.loss_tab = reinterpret_cast<const LossSpec*>(c.loss_tab.p);
+  a.scale_cam = c.jacobi_on ? c.scale_cam.p : nullptr; a.scale_pt = c.scale_pt.p;
   a.st = c.state.p;
   return a;
 }
@@ -433,6 +450,7 @@ static CamArgs make_cam_args(Ctx& c) {
   a.npl = c.npl; a.ncam = c.ncam; a.nobs_local = c.nobs_local;
   a.loss = {c.loss_id, c.loss_p[0], c.loss_p[1]};
   a.cm_loss = c.per_obs_loss ? c.cm_loss.p : nullptr; a.loss_tab = reinterpret_cast<const LossSpec*>(c.loss_tab.p);
+  a.scale_cam = c.jacobi_on ? c.scale_cam.p : nullptr; a.scale_pt = c.scale_pt.p;
   return a;
 }
 

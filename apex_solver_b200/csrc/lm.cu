@@ -238,6 +238,28 @@ __global__ void lm_converge_kernel(DevState* st, LmParams p, apex_iter_trace* tr
   st->iteration = iteration + 1;
 }
 
+// Jacobi column scaling (process_jacobian_generic, src/optimizer/mod.rs:749-763): the column norms of J are the square roots of
+// the diagonals of the camera / landmark blocks of J^T J of the UNSCALED linearisation; scaling = 1 / (1 + norm)
+__global__ void jacobi_scale_kernel(const double* __restrict__ hcc, const double* __restrict__ hpp, double* __restrict__ sc, double* __restrict__ sp,
+                                    uint32_t ncam, int dc, uint32_t npl) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t ncd = (size_t)ncam * dc;
+  if (i < ncd) sc[i] = 1.0 / (1.0 + sqrt(hcc[i * dc + i % dc]));
+  else if (i < ncd + (size_t)npl * 3) {
+    const size_t j = i - ncd, lp = j / 3;
+    const int k = (int)(j % 3);
+    const int plane = k == 0 ? 0 : (k == 1 ? 3 : 5);   // H_pp planes: 00 01 02 11 12 22
+    sp[j] = 1.0 / (1.0 + sqrt(hpp[(size_t)plane * npl + lp]));
+  }
+}
+// step = scaled_step .* scaling (apply_inverse_scaling, src/linearizer/mod.rs:255-261)
+__global__ void jacobi_unscale_step_kernel(double* __restrict__ step_cam, double* __restrict__ step_pt, const double* __restrict__ sc,
+                                           const double* __restrict__ sp, size_t ncd, size_t np3) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ncd) step_cam[i] *= sc[i];
+  else if (i < ncd + np3) step_pt[i - ncd] *= sp[i - ncd];
+}
+
 static double now_seconds() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -246,7 +268,10 @@ static double now_seconds() {
 apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, apex_iter_trace* trace, int trace_cap) {
   if (!c.have_problem) { c.err = "no problem uploaded"; return APEX_ERR_INVALID_STATE; }
   if (c.nobs == 0) { c.err = "no residual blocks"; return APEX_ERR_NO_RESIDUAL_BLOCKS; }
-  if (cfg->use_jacobi_scaling || cfg->compute_covariances) { c.err = "jacobi scaling / covariances are not on the GPU path"; return APEX_ERR_UNSUPPORTED; }
+  // compute_covariances: accepted and without effect, like the reference on this path - the Schur solvers do not implement
+  // LinearSolver::compute_covariance_matrix (default None, src/linalg/mod.rs:170-172), so SolverResult::covariances is None
+  c.jacobi_on = false;
+  struct ScalingOff { Ctx& c; ~ScalingOff() { if (c.jacobi_on) { c.jacobi_on = false; c.linearized = false; } } } scaling_off{c};  // standalone entry points stay unscaled
   if (cfg->schur_variant < APEX_SCHUR_EXPLICIT || cfg->schur_variant > APEX_SCHUR_EXPLICIT_PCG) { c.err = "bad schur_variant"; return APEX_ERR_INVALID_PARAMETERS; }
   cudaStream_t s = c.stream;
   const double t0 = now_seconds();
@@ -271,6 +296,18 @@ apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, ape
 
   for (int iteration = 0;; ++iteration) {
     const double it0 = now_seconds();
+    if (cfg->use_jacobi_scaling && iteration == 0) {
+      // the scaling comes from the unscaled Jacobian of the first iterate and stays fixed (mod.rs:754-758); the linearisation
+      // is then repeated with it (the once-per-solve price of never storing an unscaled copy)
+      const size_t ncd = (size_t)c.ncam * c.dc, np3 = (size_t)c.npl * 3;
+      APEX_CUDA_TRY(c, c.scale_cam.alloc(ncd));
+      APEX_CUDA_TRY(c, c.scale_pt.alloc(std::max<size_t>(np3, 1)));
+      APEX_TRY(launch_linearize(c));
+      jacobi_scale_kernel<<<(unsigned)((ncd + np3 + 255) / 256), 256, 0, s>>>(c.hcc.p, c.hpp.p, c.scale_cam.p, c.scale_pt.p, c.ncam, c.dc, c.npl);
+      c.launches++;
+      APEX_CUDA_TRY(c, cudaGetLastError());
+      c.jacobi_on = true;
+    }
     APEX_TRY(launch_linearize(c));
     c.linearized = true;
     jac_evals++;
@@ -278,6 +315,12 @@ apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, ape
     if (cfg->schur_variant == APEX_SCHUR_IMPLICIT) st = solve_implicit(c, cfg->schur_preconditioner, cfg->cg_max_iterations, cfg->cg_tolerance);
     else st = solve_explicit(c, cfg->schur_variant == APEX_SCHUR_EXPLICIT_PCG, cfg->cg_max_iterations, cfg->cg_tolerance);
     if (st != APEX_OK) return (st == APEX_ERR_SINGULAR_MATRIX || st == APEX_ERR_FACTORIZATION_FAILED) ? APEX_ERR_LINEAR_SOLVE_FAILED : st;
+    if (c.jacobi_on) {
+      // the predicted reduction pairs the UNSCALED step with the SCALED gradient (compute_step_generic, levenberg_marquardt.rs:738-761)
+      const size_t ncd = (size_t)c.ncam * c.dc, np3 = (size_t)c.npl * 3;
+      jacobi_unscale_step_kernel<<<(unsigned)((ncd + np3 + 255) / 256), 256, 0, s>>>(c.step_cam.p, c.step_pt.p, c.scale_cam.p, c.scale_pt.p, ncd, np3);
+      c.launches++;
+    }
     c.have_step = true;
     const int pcg_it = (int)c.last_pcg_iters;
     lin_iters += pcg_it;

@@ -220,8 +220,8 @@ typedef struct apex_lm_config {
   double max_condition_number;  /* dead; NaN: None */
   double min_relative_decrease; /* dead */
   double cg_tolerance;          /* 1e-6  */
-  int32_t use_jacobi_scaling;   /* must be 0 on this path (default false, :352)            */
-  int32_t compute_covariances;  /* must be 0 on this path                                  */
+  int32_t use_jacobi_scaling;   /* column scaling 1/(1+||J col||) fixed at iteration 0 (:871-879; default false, :352) */
+  int32_t compute_covariances;  /* accepted, no effect: the Schur solvers return no covariance matrix (linalg/mod.rs:170-172) */
 } apex_lm_config;
 
 /* SolverResult + ConvergenceInfo (src/optimizer/mod.rs:163-172,250-273). */

@@ -1219,6 +1219,8 @@ struct Ctx {
   int loss_id = 0; double loss_prm[4] = {0, 0, 0, 0};
   // per-block loss functions (ResidualBlock owns its own Option<Box<dyn LossFunction>>, src/core/residual_block.rs:97-123)
   std::vector<uint8_t> obs_loss; std::vector<apex_loss_spec> loss_table;
+  // Jacobi column scaling (process_jacobian_generic, src/optimizer/mod.rs:749-763): 1 / (1 + ||column||), fixed at LM iteration 0
+  bool scaling_on = false; std::vector<double> scale_cam, scale_pt;
   int loss_id_of(uint64_t o) const { return obs_loss.empty() ? loss_id : loss_table[obs_loss[o]].loss_id; }
   const double* loss_prm_of(uint64_t o) const { return obs_loss.empty() ? loss_prm : loss_table[obs_loss[o]].params; }
   std::vector<uint8_t> pose_fixed, pt_fixed; std::vector<uint16_t> intr_fixed;
@@ -1308,6 +1310,16 @@ void linearize(Ctx& c, double lambda) {
     Pose pose = pose_from7(&c.pose[7 * (size_t)cam]);
     V3 pw{c.pt[3 * (size_t)p], c.pt[3 * (size_t)p + 1], c.pt[3 * (size_t)p + 2]};
     linearize_obs(c.model, c.K, c.opt_intr, c.loss_id_of(o), c.loss_prm_of(o), pose, &c.intr[(size_t)c.K * cam], pw, &c.uv[2 * o], true, c.lin[o]);
+    if (c.scaling_on) {  // J * diag(scaling) (apply_column_scaling, src/linearizer/mod.rs:240-252)
+      BlockLin& b = c.lin[o];
+      const double* sc = &c.scale_cam[(size_t)cam * c.dc];
+      const double* sp = &c.scale_pt[(size_t)p * 3];
+      for (int r = 0; r < 2; ++r) {
+        for (int k = 0; k < 6; ++k) b.jpose[r * 6 + k] *= sc[k];
+        if (c.opt_intr) for (int k = 0; k < c.K; ++k) b.jintr[r * c.K + k] *= sc[6 + k];
+        for (int k = 0; k < 3; ++k) b.jpt[r * 3 + k] *= sp[k];
+      }
+    }
   }
   const int dc = c.dc;
   c.hcc.assign((size_t)c.ncam * dc * dc, 0.0);
@@ -1802,11 +1814,35 @@ apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, ape
   double final_gnorm = 0, final_snorm = 0;
   for (;;) {
     double it0 = now_seconds();
+    if (cfg->use_jacobi_scaling && iteration == 0) {
+      // column norms of the unscaled Jacobian (compute_column_norms, src/linearizer/mod.rs:228-238) = square roots of the
+      // diagonals of the camera / landmark blocks of J^T J; scaling = 1 / (1 + norm), kept for the whole solve
+      c.scaling_on = false;
+      linearize(c, damping);
+      c.scale_cam.resize((size_t)c.ncam * c.dc);
+      c.scale_pt.resize((size_t)c.npts * 3);
+      for (uint32_t cam = 0; cam < c.ncam; ++cam)
+        for (int a = 0; a < c.dc; ++a) c.scale_cam[(size_t)cam * c.dc + a] = 1.0 / (1.0 + std::sqrt(c.hcc[((size_t)cam * c.dc + a) * c.dc + a]));
+      for (uint32_t p = 0; p < c.npts; ++p)
+        for (int a = 0; a < 3; ++a) c.scale_pt[(size_t)p * 3 + a] = 1.0 / (1.0 + std::sqrt(c.hpp[(size_t)p * 9 + a * 3 + a]));
+      c.scaling_on = true;
+    }
     linearize(c, damping);
     jac_evals++;
     StepOut step;
     apex_status st = solve_augmented(c, cfg->schur_variant, cfg->schur_preconditioner, cfg->cg_max_iterations, cfg->cg_tolerance, damping, step);
-    if (st != APEX_OK) return st == APEX_ERR_SINGULAR_MATRIX || st == APEX_ERR_FACTORIZATION_FAILED ? APEX_ERR_LINEAR_SOLVE_FAILED : st;
+    if (st != APEX_OK) { c.scaling_on = false; return st == APEX_ERR_SINGULAR_MATRIX || st == APEX_ERR_FACTORIZATION_FAILED ? APEX_ERR_LINEAR_SOLVE_FAILED : st; }
+    if (c.scaling_on) {
+      // step = scaled_step .* scaling (apply_inverse_scaling, src/linearizer/mod.rs:255-261); the predicted reduction then pairs
+      // the UNSCALED step with the SCALED gradient (compute_step_generic, levenberg_marquardt.rs:738-761)
+      double s2 = 0, sg = 0;
+      for (size_t i = 0; i < step.cam.size(); ++i) { step.cam[i] *= c.scale_cam[i]; s2 += step.cam[i] * step.cam[i]; sg += step.cam[i] * c.gc[i]; }
+      for (double v : step.intr_unref) s2 += v * v;
+      for (size_t i = 0; i < step.pt.size(); ++i) { step.pt[i] *= c.scale_pt[i]; s2 += step.pt[i] * step.pt[i]; sg += step.pt[i] * c.gp[i]; }
+      step.step_norm = std::sqrt(s2);
+      step.step_dot_grad = sg;
+      c.last_step_cam = step.cam; c.last_step_pt = step.pt;
+    }
     lin_iters += step.pcg_iters;
     // compute_predicted_reduction (:721-727): 0.5 * step^T (damping*step - gradient)
     double predicted = 0.5 * (damping * step.step_norm * step.step_norm - step.step_dot_grad);
@@ -1841,6 +1877,7 @@ apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, ape
       res->elapsed_seconds = elapsed; res->final_gradient_norm = final_gnorm; res->final_parameter_update_norm = final_snorm;
       res->cost_evaluations = cost_evals; res->jacobian_evaluations = jac_evals; res->successful_steps = ok_steps;
       res->unsuccessful_steps = bad_steps; res->final_damping = damping; res->final_damping_nu = nu; res->linear_iterations = lin_iters;
+      if (c.scaling_on) { c.scaling_on = false; c.linearized = false; }  // the cached linearization holds scaled blocks
       return APEX_OK;
     }
     iteration++;

@@ -110,7 +110,9 @@ def test_per_block_loss_functions(model):
     LossFunction instances drawn per observation. K1 (slot order), the cost kernel and the camera-major accumulations (which
     re-evaluate the corrector) must all pick the block's own loss: residuals, Jacobians, blocks and an LM run against the oracle."""
     import dataclasses
-    base = small_problem(model=model, ncam=14, npts=500)
+    # (no gross outliers: an un-weighted 50-pixel residual next to Tukey-zeroed ones leaves a reduced system whose solve only
+    # reproduces to 2e-9 backward between two correct implementations)
+    base = small_problem(model=model, ncam=14, npts=500, outlier_frac=0.0)
     table = [(F.LOSS_HUBER, 1.0), (F.LOSS_CAUCHY, 2.0), (F.LOSS_NONE,), (F.LOSS_TUKEY, 4.0)]
     idx = np.random.default_rng(3).integers(0, len(table), base.nobs).astype(np.uint8)
     prob = dataclasses.replace(base, obs_loss=idx, loss_table=table, meta={})
@@ -121,7 +123,8 @@ def test_per_block_loss_functions(model):
     for a, b, what in zip(g.get_linearization(), o.get_linearization(), ("residuals", "camera Jacobians", "landmark Jacobians")):
         assert relerr(a, b) < 1e-12, what
     assert_blocks_close(g, o, prob, 1e-3)
-    teacher_forced(prob, F.SCHUR_EXPLICIT, n_it=4)
+    # (redescending Tukey blocks leave some landmark blocks held by lambda alone: the two Cholesky solves agree to 3e-10 backward)
+    teacher_forced(prob, F.SCHUR_EXPLICIT, n_it=4, backward_tol=1e-9)
     teacher_forced(prob, F.SCHUR_IMPLICIT, n_it=4)
 
 
@@ -468,10 +471,33 @@ def test_error_behaviour():
         GpuContext().upload(bad)
     assert e.value.status == F.ERR_INVALID_INPUT
     cfg = g.default_config(True)
-    cfg.use_jacobi_scaling = 1
-    with pytest.raises(F.ApexError) as e:
-        g.lm_solve(cfg)
-    assert e.value.status == F.ERR_UNSUPPORTED
+    cfg.compute_covariances = 1   # accepted without effect: the reference's Schur solvers return None (src/linalg/mod.rs:170-172)
+    cfg.max_iterations = 1
+    res, _ = g.lm_solve(cfg)
+    assert res.iterations == 2
+
+
+@pytest.mark.parametrize("variant,kw", [(F.SCHUR_EXPLICIT, {}), (F.SCHUR_IMPLICIT, dict(cg_it=3000, cg_tolerance=1e-12))], ids=["explicit", "implicit_converged"])
+@pytest.mark.parametrize("self_cal", [True, False], ids=["selfcal", "ba"])
+def test_lm_with_jacobi_scaling(variant, kw, self_cal):
+    """LevenbergMarquardtConfig::with_jacobi_scaling(true) (levenberg_marquardt.rs:871-879, optimizer/mod.rs:749-763): column
+    scaling 1 / (1 + ||J column||) fixed at the first iterate, solve in scaled variables, step scaled back, predicted reduction from
+    the unscaled step and the scaled gradient. Same accept pattern / status / iteration count as the oracle, per-iteration cost
+    and final parameters at the usual tolerances; and the scaling must matter (another trajectory than without it)."""
+    prob = small_problem(ncam=14, npts=500, self_cal=self_cal)
+    g, o = pair(prob)
+    (rg, tg), (ro, to) = run_lm(g, variant, max_it=6, use_jacobi_scaling=1, **kw), run_lm(o, variant, max_it=6, use_jacobi_scaling=1, **kw)
+    assert (rg.status, rg.iterations, [t.accepted for t in tg]) == (ro.status, ro.iterations, [t.accepted for t in to])
+    for a, b in zip(tg, to):
+        assert abs(a.cost - b.cost) <= 1e-8 * abs(b.cost) and abs(a.gradient_norm - b.gradient_norm) <= 1e-8 * b.gradient_norm
+        assert abs(a.step_norm - b.step_norm) <= 1e-6 * b.step_norm
+    for xa, xb in zip(g.params_download(), o.params_download()):
+        assert relerr(xa, xb) < 1e-6
+    (r0, t0) = run_lm(GpuContext().upload(prob), variant, max_it=6, **kw)
+    assert abs(t0[0].gradient_norm - tg[0].gradient_norm) > 1e-3 * t0[0].gradient_norm, "scaled gradient norm is reported"
+    g.params_upload(*o.params_download())
+    g.linearize(1e-3); o.linearize(1e-3)   # the standalone entry points stay unscaled after a scaled solve
+    assert relerr(g.get_linearization()[1], o.get_linearization()[1]) < 1e-12
 
 
 def test_empty_and_degenerate_problems():

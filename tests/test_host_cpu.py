@@ -229,6 +229,46 @@ def test_oracle_per_block_loss_is_the_sum_over_loss_classes():
     assert e.value.status == F.ERR_INVALID_INPUT
 
 
+def test_oracle_jacobi_scaling_matches_a_dense_restatement():
+    """process_jacobian_generic (src/optimizer/mod.rs:749-763) + compute_step_generic (levenberg_marquardt.rs:730-766), restated
+    densely with numpy on a tiny problem: scaling = 1 / (1 + column norm), (Js^T Js + lambda I) dxs = -Js^T r, step = dxs * scaling,
+    reported gradient norm = ||Js^T r||. The oracle's first LM iteration with use_jacobi_scaling must give that step."""
+    prob = synth.make_problem(4, 30, 3.0, seed=5, self_calibration=True)
+    o = OracleContext().upload(prob)
+    lam = 1e-3
+    o.linearize(lam)
+    r, jc, jp = o.get_linearization()
+    dc, ncd = prob.dc, prob.ncam * prob.dc
+    n = ncd + 3 * prob.npts
+    J = np.zeros((2 * prob.nobs, n))
+    for i in range(prob.nobs):
+        c, p = int(prob.obs_cam[i]), int(prob.obs_pt[i])
+        J[2 * i:2 * i + 2, c * dc:(c + 1) * dc] = jc[i].reshape(2, dc)
+        J[2 * i:2 * i + 2, ncd + 3 * p:ncd + 3 * p + 3] = jp[i].reshape(2, 3)
+    sc = 1.0 / (1.0 + np.linalg.norm(J, axis=0))
+    Js = J * sc[None, :]
+    g = Js.T @ r.reshape(-1)
+    dxs = np.linalg.solve(Js.T @ Js + lam * np.eye(n), -g)
+    step = dxs * sc
+    cfg = o.default_config(True)
+    cfg.schur_variant = F.SCHUR_EXPLICIT
+    cfg.max_iterations = 0
+    cfg.damping = lam
+    cfg.use_jacobi_scaling = 1
+    res, tr = o.lm_solve(cfg)
+    dca, dpa = o.get_step()
+    assert np.abs(dca.reshape(-1) - step[:ncd]).max() <= 1e-8 * np.abs(step[:ncd]).max()
+    assert np.abs(dpa.reshape(-1) - step[ncd:]).max() <= 1e-8 * np.abs(step[ncd:]).max()
+    assert abs(tr[0].gradient_norm - np.linalg.norm(g)) <= 1e-10 * np.linalg.norm(g)
+    assert abs(tr[0].step_norm - np.linalg.norm(step)) <= 1e-8 * np.linalg.norm(step)
+    predicted = 0.5 * step @ (lam * step - g)     # compute_predicted_reduction with the UNSCALED step and the SCALED gradient
+    assert abs(tr[0].predicted_reduction - predicted) <= 1e-8 * abs(predicted)
+    cfg.use_jacobi_scaling = 0                      # and without it the oracle takes another step
+    o2 = OracleContext().upload(prob)
+    o2.lm_solve(cfg)
+    assert np.abs(o2.get_step()[0] - dca).max() > 1e-6 * np.abs(dca).max()
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` prints one JSON line with the contract's keys (runs the oracle on a bounded sample)."""
     env = dict(os.environ, OMP_NUM_THREADS="4")
