@@ -167,13 +167,13 @@ struct StageBuf {
     p = nullptr; n = cap = 0;
   }
   void resize(size_t count) {  // contents are undefined after a resize (every user fills what it reads)
-    if (count > cap) {
+    if (count > cap || (pinned && !is_pinned_alloc && p && count > 0)) {   // (a buffer that became "pinned" is re-allocated page-locked)
       const bool want_pinned = pinned;
       release();
       const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
       if (want_pinned && cudaHostAlloc(reinterpret_cast<void**>(&p), bytes, cudaHostAllocDefault) == cudaSuccess) is_pinned_alloc = true;
       else { cudaGetLastError(); p = static_cast<T*>(malloc(bytes)); is_pinned_alloc = false; }
-      cap = p ? count : 0;
+      cap = p ? std::max(count, cap) : 0;
     }
     n = count <= cap ? count : 0;
   }
