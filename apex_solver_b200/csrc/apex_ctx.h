@@ -210,6 +210,7 @@ struct Ctx {
   std::string err;
   int device = 0, rank = 0, nranks = 1;
   cudaStream_t stream = nullptr;
+  bool chol_attr_set = false;              // dynamic shared-memory limits of the Cholesky kernels set on this context's device
   cudaStream_t stream2 = nullptr;          // low-priority stream of the dense Cholesky's look-ahead (explicit.cu)
   std::vector<cudaEvent_t> chol_events;    // pairs per outer panel: panel factored / rest update done
   int64_t launches = 0;

@@ -516,15 +516,14 @@ static uint32_t tri_count(uint32_t nb) { return (uint32_t)((uint64_t)nb * (nb + 
 static apex_status dense_cholesky(Ctx& c, double* L, uint32_t npad) {
   cudaStream_t s = c.stream;
   const size_t ld = npad;
-  static bool attr_set = false;
   const int smem = 2 * NB * PLD * (int)sizeof(double);
   const int trsm_smem_bytes = 2 * NB * PLD * (int)sizeof(double);
   const int syrk128_smem = 2 * 2 * SB * SPLD * (int)sizeof(double);
-  if (!attr_set) {
+  if (!c.chol_attr_set) {   // per context, i.e. per device (function attributes are per device)
     APEX_CUDA_TRY(c, cudaFuncSetAttribute(chol_syrk128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, syrk128_smem));
     APEX_CUDA_TRY(c, cudaFuncSetAttribute(chol_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     APEX_CUDA_TRY(c, cudaFuncSetAttribute(chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_smem_bytes));
-    attr_set = true;
+    c.chol_attr_set = true;
   }
   // Two-level right-looking blocking. Outer panels of NBO = 256 columns: inside a panel the 64-wide steps update only
   // the panel's own remaining columns (all rows below); the matrix to the right of the panel is then updated ONCE with
