@@ -383,6 +383,7 @@ apex_status launch_apply_step(Ctx& c, double sign, bool only_if_rejected);
 apex_status launch_param_norm(Ctx& c);
 apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, apex_iter_trace* trace, int trace_cap);
 // comm.cu
+constexpr size_t AR_CAPACITY = (size_t)1 << 19;   // camera dofs the peer buffers are mapped for at context creation (2 x 4 MB)
 apex_status setup_peer_allreduce(Ctx& c, size_t n);
 void release_peer_allreduce(Ctx& c);
 // comm (apex_gpu.cu)

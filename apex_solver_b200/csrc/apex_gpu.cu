@@ -153,6 +153,11 @@ apex_status apex_ctx_create(const apex_ctx_desc* desc, apex_ctx** out) {
     NcclComm comm = nullptr;
     if (api.CommInitRank(&comm, c.nranks, id, c.rank) != 0) { delete h; return APEX_ERR_NCCL; }
     c.nccl_comm = comm;
+    // Per-process communication setup belongs here, not into the first problem upload: the first collective on a new
+    // communicator establishes its channels and the first cudaIpcOpenMemHandle enables peer access (together ~300 ms measured at
+    // N=2), so the peer-memory buffers of the fused all-reduce are mapped now at a fixed capacity (AR_CAPACITY camera dofs; a
+    // problem with more re-maps them at upload).
+    if (setup_peer_allreduce(c, AR_CAPACITY) != APEX_OK) { cudaGetLastError(); c.p2p_ok = false; }
   }
   *out = h;
   return APEX_OK;

@@ -663,7 +663,9 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   lap("allocations + parameters");
   APEX_CUDA_TRY(c, cudaStreamSynchronize(s));  // the host vectors above die with this scope
   lap("stream sync");
-  APEX_TRY(setup_peer_allreduce(c, ncd));
+  // the peer-memory buffers of the fused all-reduce were mapped at context creation; only a larger camera vector re-maps them
+  // (collective: every rank sees the same ncd and the same capacity, so all take the same branch)
+  if (c.nranks > 1 && !(c.p2p_ok && ncd <= c.ar_n)) APEX_TRY(setup_peer_allreduce(c, std::max(ncd, AR_CAPACITY)));
   lap("peer setup");
   c.have_problem = true;
   return APEX_OK;
