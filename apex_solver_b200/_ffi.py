@@ -59,7 +59,7 @@ ERROR_NAMES = {
 CAM_BAL, CAM_PINHOLE, CAM_KANNALA_BRANDT, CAM_DOUBLE_SPHERE, CAM_RADTAN, CAM_UCM, CAM_EUCM, CAM_FOV, CAM_FTHETA = range(9)
 CAM_INTR_DIM = {CAM_BAL: 3, CAM_PINHOLE: 4, CAM_KANNALA_BRANDT: 8, CAM_DOUBLE_SPHERE: 6, CAM_RADTAN: 9,
                 CAM_UCM: 5, CAM_EUCM: 6, CAM_FOV: 5, CAM_FTHETA: 6}
-OPT_POSE, OPT_LANDMARK, OPT_INTRINSIC = 1, 2, 4
+OPT_POSE, OPT_LANDMARK, OPT_INTRINSIC, OPT_SHARED_INTRINSICS = 1, 2, 4, 8
 (LOSS_NONE, LOSS_L2, LOSS_L1, LOSS_HUBER, LOSS_CAUCHY, LOSS_FAIR, LOSS_GEMAN_MCCLURE, LOSS_WELSCH, LOSS_TUKEY,
  LOSS_ANDREWS, LOSS_RAMSAY_EA, LOSS_TRIMMED_MEAN, LOSS_LP_NORM, LOSS_BARRON, LOSS_T_DISTRIBUTION) = range(15)
 SCHUR_EXPLICIT, SCHUR_IMPLICIT, SCHUR_EXPLICIT_PCG = 0, 1, 2

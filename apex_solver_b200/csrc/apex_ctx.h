@@ -222,6 +222,7 @@ struct Ctx {
   int model = 0, K = 0, dc = 6, np = 18;  // np = 2*(dc+3) Jacobian planes
   uint32_t opt = 0;
   bool opt_intr = false, intr_vars = false;
+  bool shared_intr = false;          // one intrinsics variable for all cameras (APEX_OPT_SHARED_INTRINSICS)
   uint32_t ncam = 0, npts = 0;
   uint64_t nobs = 0;
   uint64_t cam_dof_ref = 0;  // reference-layout camera dof (includes unreferenced intr columns)
@@ -299,6 +300,7 @@ struct Ctx {
   DevBuf<double> S;                       // dense reduced camera system (explicit variants), n*n row-major
   DevBuf<double> E;                       // [chunk][3*dc][TILE] H_cp blocks for S formation
   DevBuf<double> dvec;                    // dense-solver work vectors
+  DevBuf<double> sh_vec;                  // shared intrinsics: [gradient | step] in the reduced layout [poses 6 each | intrinsics K]
   DevBuf<double> l2flush;                 // > L2 buffer for apex_schur_matvec_bench
   DevBuf<DevState> state;
   DevState* h_state = nullptr;            // pinned mirror

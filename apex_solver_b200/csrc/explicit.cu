@@ -508,6 +508,65 @@ __global__ void __launch_bounds__(1024) dense_pcg_step_kernel(const double* __re
 }
 
 // ----------------------------------------------------------------------------------------------------
+// Shared intrinsics (APEX_OPT_SHARED_INTRINSICS): the graph [pose_k, landmarks, intrinsics] of the reference's calibration tests is
+// the per-camera-intrinsics problem restricted to "every camera's copy is equal": x_un = P x_sh with P replicating the K
+// intrinsics columns, so J_sh = J_un P and, the landmark elimination not touching camera columns, the reduced system is the
+// Galerkin projection  S_sh = P^T (S_un - lambda I) P + lambda I,  b_sh = P^T b_un  (lambda I lives in the shared space). The
+// kernels above build S_un / b_un as always; these project, and the solved step is replicated back.
+// ----------------------------------------------------------------------------------------------------
+// one CTA per row of S_sh: pose rows copy their pose columns and sum the intrinsics columns over the cameras; intrinsics rows sum
+// over their cameras' rows as well. Writes the full symmetric matrix (identity on the padding).
+__global__ void __launch_bounds__(256) shared_project_matrix_kernel(const double* __restrict__ Sun, size_t ldu, double* __restrict__ Ssh, size_t lds,
+                                                                    uint32_t ncam, int dc, int K, uint32_t npad_sh, const DevState* st) {
+  __shared__ double sh[256];
+  const uint32_t np = 6 * ncam, nsh = np + (uint32_t)K, i = blockIdx.x;
+  const double lambda = st->damping;
+  if (i >= nsh) { for (uint32_t j = threadIdx.x; j < npad_sh; j += 256) Ssh[(size_t)i * lds + j] = i == j ? 1.0 : 0.0; return; }
+  if (i < np) {
+    const size_t ru = (size_t)(i / 6) * dc + i % 6;
+    for (uint32_t j = threadIdx.x; j < np; j += 256) Ssh[(size_t)i * lds + j] = Sun[ru * ldu + (size_t)(j / 6) * dc + j % 6];
+    for (int k = 0; k < K; ++k) {
+      double s = 0.0;
+      for (uint32_t c2 = threadIdx.x; c2 < ncam; c2 += 256) s += Sun[ru * ldu + (size_t)c2 * dc + 6 + k];
+      s = block_reduce_sum(s, sh);
+      if (threadIdx.x == 0) Ssh[(size_t)i * lds + np + k] = s;
+    }
+  } else {
+    const int k = (int)(i - np);
+    for (uint32_t j = threadIdx.x; j < np; j += 256) {   // column j of the pose part: sum over the cameras' intrinsics rows k
+      const size_t cu = (size_t)(j / 6) * dc + j % 6;
+      double s = 0.0;
+      for (uint32_t c1 = 0; c1 < ncam; ++c1) s += Sun[((size_t)c1 * dc + 6 + k) * ldu + cu];
+      Ssh[(size_t)i * lds + j] = s;
+    }
+    for (int l = 0; l < K; ++l) {
+      double s = 0.0;
+      for (uint32_t e = threadIdx.x; e < ncam * ncam; e += 256) s += Sun[((size_t)(e / ncam) * dc + 6 + k) * ldu + (size_t)(e % ncam) * dc + 6 + l];
+      s = block_reduce_sum(s, sh);
+      if (threadIdx.x == 0) Ssh[(size_t)i * lds + np + l] = s - (k == l ? (double)(ncam - 1) * lambda : 0.0);   // P^T (lambda I) P = ncam lambda there
+    }
+  }
+  for (uint32_t j = nsh + threadIdx.x; j < npad_sh; j += 256) Ssh[(size_t)i * lds + j] = 0.0;
+}
+// v_sh = P^T v_un (sign * v_un): pose entries copied, intrinsics entries summed over the cameras in camera order
+__global__ void shared_project_vector_kernel(const double* __restrict__ vun, double* __restrict__ vsh, uint32_t ncam, int dc, int K) {
+  const uint32_t np = 6 * ncam, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < np) vsh[i] = vun[(size_t)(i / 6) * dc + i % 6];
+  else if (i < np + (uint32_t)K) {
+    double s = 0.0;
+    for (uint32_t cam = 0; cam < ncam; ++cam) s += vun[(size_t)cam * dc + 6 + (i - np)];
+    vsh[i] = s;
+  }
+}
+// x_un = P x_sh
+__global__ void shared_expand_vector_kernel(const double* __restrict__ vsh, double* __restrict__ vun, uint32_t ncam, int dc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncam * (uint32_t)dc) return;
+  const uint32_t cam = i / dc, a = i % dc;
+  vun[i] = a < 6 ? vsh[6 * cam + a] : vsh[6 * ncam + (a - 6)];
+}
+
+// ----------------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------------
 static uint32_t tri_count(uint32_t nb) { return (uint32_t)((uint64_t)nb * (nb + 1) / 2); }
@@ -650,11 +709,11 @@ static apex_status dense_cholesky_solve(Ctx& c, const double* L, uint32_t npad, 
 // linearization. Leaves the camera step in c.step_cam and the landmark step in c.step_pt.
 apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol) {
   cudaStream_t s = c.stream;
-  const uint32_t n = c.ncam * c.dc;
-  const uint32_t npad = (n + 2 * NB - 1) / (2 * NB) * (2 * NB);  // multiple of 128: the deep trailing update works on 128x128 tiles
-  const size_t ld = npad;
-  const size_t nn = (size_t)npad * npad;
-  APEX_CUDA_TRY(c, c.S.alloc(nn * (use_pcg ? 1 : 2)));  // [S | factor workspace]
+  uint32_t n = c.ncam * c.dc;
+  uint32_t npad = (n + 2 * NB - 1) / (2 * NB) * (2 * NB);  // multiple of 128: the deep trailing update works on 128x128 tiles
+  size_t ld = npad;
+  size_t nn = (size_t)npad * npad;
+  APEX_CUDA_TRY(c, c.S.alloc(nn * ((use_pcg && !c.shared_intr) ? 1 : 2)));  // [S | factor workspace]
   APEX_CUDA_TRY(c, c.dvec.alloc((size_t)npad * 2 + 8));
   double* S = c.S.p;
   APEX_CUDA_TRY(c, cudaMemsetAsync(S, 0, nn * sizeof(double), s));
@@ -691,6 +750,21 @@ apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol) {
   // --- reduced gradient ---
   APEX_TRY(launch_reduced_gradient(c, c.vb.p));
   APEX_CUDA_TRY(c, cudaGetLastError());
+  const double* bsrc = c.vb.p;
+  if (c.shared_intr) {
+    // project the per-camera-intrinsics system onto the shared variable; from here on (n, npad, ld) are the shared system's
+    const uint32_t nsh = 6 * c.ncam + (uint32_t)c.K, npsh = (nsh + 2 * NB - 1) / (2 * NB) * (2 * NB);
+    double* tmp = S + nn;
+    shared_project_matrix_kernel<<<npsh, 256, 0, s>>>(S, ld, tmp, npsh, c.ncam, c.dc, c.K, npsh, c.state.p);
+    APEX_CUDA_TRY(c, cudaMemcpyAsync(S, tmp, (size_t)npsh * npsh * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    APEX_CUDA_TRY(c, c.sh_vec.alloc(2 * (size_t)nsh));
+    shared_project_vector_kernel<<<(nsh + 255) / 256, 256, 0, s>>>(c.vb.p, c.vr.p, c.ncam, c.dc, c.K);          // b_sh (vr is free: direct solve)
+    shared_project_vector_kernel<<<(nsh + 255) / 256, 256, 0, s>>>(c.gc, c.sh_vec.p, c.ncam, c.dc, c.K);        // gradient in the shared layout
+    c.launches += 3;
+    APEX_CUDA_TRY(c, cudaGetLastError());
+    bsrc = c.vr.p;
+    n = nsh; npad = npsh; ld = npsh; nn = (size_t)npsh * npsh;
+  }
 
   if (!use_pcg) {
     double* L = S + nn;
@@ -723,9 +797,13 @@ apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol) {
     }
     if (!solved) { c.err = "Schur complement singular after 5 regularization attempts"; return APEX_ERR_SINGULAR_MATRIX; }
     APEX_CUDA_TRY(c, cudaMemsetAsync(v, 0, (size_t)npad * sizeof(double), s));
-    APEX_CUDA_TRY(c, cudaMemcpyAsync(v, c.vb.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    APEX_CUDA_TRY(c, cudaMemcpyAsync(v, bsrc, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
     APEX_TRY(dense_cholesky_solve(c, L, npad, v));
-    APEX_CUDA_TRY(c, cudaMemcpyAsync(c.step_cam.p, v, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (c.shared_intr) {   // keep the shared step for the norms, replicate it into every camera's block
+      APEX_CUDA_TRY(c, cudaMemcpyAsync(c.sh_vec.p + n, v, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      shared_expand_vector_kernel<<<(c.ncam * c.dc + 255) / 256, 256, 0, s>>>(v, c.step_cam.p, c.ncam, c.dc);
+      c.launches++;
+    } else APEX_CUDA_TRY(c, cudaMemcpyAsync(c.step_cam.p, v, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
     c.last_pcg_iters = 0;
   } else {
     double* dinv = c.dvec.p;

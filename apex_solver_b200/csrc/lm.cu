@@ -51,7 +51,9 @@ __global__ void __launch_bounds__(1024) sum3_kernel(const double* __restrict__ p
 
 apex_status launch_step_norms(Ctx& c) {
   cudaStream_t s = c.stream;
-  cam_norms_kernel<<<1, 1024, 0, s>>>(c.gc, c.step_cam.p, c.ncam * c.dc, c.state.p);
+  // (shared intrinsics: gradient and step of the reduced layout [poses | one intrinsics block], left there by solve_explicit)
+  if (c.shared_intr) { const uint32_t nsh = 6 * c.ncam + (uint32_t)c.K; cam_norms_kernel<<<1, 1024, 0, s>>>(c.sh_vec.p, c.sh_vec.p + nsh, nsh, c.state.p); }
+  else cam_norms_kernel<<<1, 1024, 0, s>>>(c.gc, c.step_cam.p, c.ncam * c.dc, c.state.p);
   const uint32_t nb = (c.npl + 255) / 256;
   if (nb) pt_norms_kernel<<<nb, 256, 0, s>>>(c.gp.p, c.step_pt.p, c.npl, c.red_scratch.p, nb);
   sum3_kernel<<<1, 1024, 0, s>>>(c.red_scratch.p, nb, &c.state.p->g2_pt);
@@ -128,15 +130,15 @@ __global__ void __launch_bounds__(1024) cam_param_norm_kernel(const double* __re
   __shared__ double sh[1024];
   double s = 0.0;
   for (size_t i = threadIdx.x; i < 7 * (size_t)ncam; i += 1024) s += pose[i] * pose[i];
-  if (with_intr)
-    for (size_t i = threadIdx.x; i < (size_t)K * ncam; i += 1024) s += intr[i] * intr[i];
+  if (with_intr)   // with_intr == 2: one shared intrinsics variable (every camera holds a copy of it)
+    for (size_t i = threadIdx.x; i < (size_t)K * (with_intr == 2 ? 1 : ncam); i += 1024) s += intr[i] * intr[i];
   s = block_reduce_sum(s, sh);
   if (threadIdx.x == 0) st->pn2_cam = s;
 }
 
 apex_status launch_param_norm(Ctx& c) {
   cudaStream_t s = c.stream;
-  cam_param_norm_kernel<<<1, 1024, 0, s>>>(c.pose.p, c.intr.p, c.ncam, c.K, (c.opt_intr || c.intr_vars) ? 1 : 0, c.state.p);
+  cam_param_norm_kernel<<<1, 1024, 0, s>>>(c.pose.p, c.intr.p, c.ncam, c.K, c.shared_intr ? 2 : ((c.opt_intr || c.intr_vars) ? 1 : 0), c.state.p);
   const size_t n3 = 3 * (size_t)c.npl;
   const unsigned nb = (unsigned)std::min<size_t>((n3 + 255) / 256, 1024);
   if (nb) sumsq_partial_kernel<<<nb, 256, 0, s>>>(c.pt.p, n3, c.red_scratch.p);
@@ -273,6 +275,7 @@ apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, ape
   c.jacobi_on = false;
   struct ScalingOff { Ctx& c; ~ScalingOff() { if (c.jacobi_on) { c.jacobi_on = false; c.linearized = false; } } } scaling_off{c};  // standalone entry points stay unscaled
   if (cfg->schur_variant < APEX_SCHUR_EXPLICIT || cfg->schur_variant > APEX_SCHUR_EXPLICIT_PCG) { c.err = "bad schur_variant"; return APEX_ERR_INVALID_PARAMETERS; }
+  if (c.shared_intr && (cfg->schur_variant != APEX_SCHUR_EXPLICIT || cfg->use_jacobi_scaling)) { c.err = "shared intrinsics: explicit Schur + Cholesky without column scaling only"; return APEX_ERR_UNSUPPORTED; }
   cudaStream_t s = c.stream;
   const double t0 = now_seconds();
   LmParams p{cfg->max_iterations, cfg->cost_tolerance, cfg->parameter_tolerance, cfg->gradient_tolerance, cfg->timeout_seconds,

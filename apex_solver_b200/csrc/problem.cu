@@ -44,6 +44,10 @@ apex_status validate_problem(const apex_problem_desc* d, std::string& err) {
     err = "only BundleAdjustment / SelfCalibration OptimizeParams are live (bin/bundle_adjustment.rs)";
     return APEX_ERR_UNSUPPORTED;
   }
+  if ((d->opt_flags & APEX_OPT_SHARED_INTRINSICS) && (d->opt_flags & APEX_OPT_INTRINSIC)) {
+    if (d->loss_id != APEX_LOSS_NONE && d->loss_id != APEX_LOSS_L2) { err = "shared intrinsics: the loss must be NONE or L2"; return APEX_ERR_UNSUPPORTED; }
+    if (d->obs_loss) { err = "shared intrinsics: per-block losses are not supported"; return APEX_ERR_UNSUPPORTED; }
+  }
   if (d->ncam == 0) { err = "No camera variables found"; return APEX_ERR_INVALID_INPUT; }    // explicit_schur.rs:278-282
   if (d->npts == 0) { err = "No landmark variables found"; return APEX_ERR_INVALID_INPUT; }  // explicit_schur.rs:283-287
   if (d->nobs > 0xFFFFFFF0ull) { err = "too many observations for u32 slots"; return APEX_ERR_UNSUPPORTED; }
@@ -540,6 +544,7 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   if (c.pcg_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)c.pcg_graph_exec); c.pcg_graph_exec = nullptr; }
   c.model = d->camera_model; c.K = K; c.opt = d->opt_flags;
   c.opt_intr = (d->opt_flags & APEX_OPT_INTRINSIC) != 0;
+  c.shared_intr = c.opt_intr && (d->opt_flags & APEX_OPT_SHARED_INTRINSICS) != 0;
   c.intr_vars = d->intr_vars_present != 0;
   c.dc = 6 + (c.opt_intr ? K : 0);
   c.np = 2 * (c.dc + 3);
@@ -584,6 +589,7 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   std::vector<uint16_t> intr_fixed(c.ncam, 0);
   if (d->pose_fixed) std::copy(d->pose_fixed, d->pose_fixed + c.ncam, pose_fixed.begin());
   if (d->intr_fixed) std::copy(d->intr_fixed, d->intr_fixed + c.ncam, intr_fixed.begin());
+  if (c.shared_intr) std::fill(intr_fixed.begin(), intr_fixed.end(), intr_fixed[0]);   // one variable, one mask
   if (d->pt_fixed) for (uint32_t lp = 0; lp < c.npl; ++lp) pt_fixed[lp] = d->pt_fixed[c.shard.to_global(lp)];
 
   // ---- to the device ----
@@ -655,7 +661,12 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   APEX_CUDA_TRY(c, cudaMemsetAsync(c.step_pt.p, 0, std::max<size_t>((size_t)c.npl * 3, 1) * sizeof(double), s));
 
   APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pose.p, d->pose, (size_t)c.ncam * 7 * sizeof(double), cudaMemcpyHostToDevice, s));
-  APEX_CUDA_TRY(c, cudaMemcpyAsync(c.intr.p, d->intr, (size_t)c.ncam * K * sizeof(double), cudaMemcpyHostToDevice, s));
+  std::vector<double> intr_rep;   // shared intrinsics: row 0 is the value of every camera's copy (lives until the sync below)
+  if (c.shared_intr) {
+    intr_rep.resize((size_t)c.ncam * K);
+    for (uint32_t cam = 0; cam < c.ncam; ++cam) std::copy(d->intr, d->intr + K, intr_rep.begin() + (size_t)cam * K);
+  }
+  APEX_CUDA_TRY(c, cudaMemcpyAsync(c.intr.p, c.shared_intr ? intr_rep.data() : d->intr, (size_t)c.ncam * K * sizeof(double), cudaMemcpyHostToDevice, s));
   std::vector<double> pt_local;  // one rank owns every landmark in the caller's order: no gather needed
   if (c.nranks > 1) pt_local = gather_local_points(c, d->pt);
   if (c.npl) APEX_CUDA_TRY(c, cudaMemcpyAsync(c.pt.p, c.nranks > 1 ? pt_local.data() : d->pt, (size_t)c.npl * 3 * sizeof(double), cudaMemcpyHostToDevice, s));

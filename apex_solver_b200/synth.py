@@ -286,6 +286,47 @@ def make_problem(ncam, npts, mean_track, camera_model=F.CAM_BAL, loss=(F.LOSS_HU
                      meta={"seed": seed, "truth_pose": np.concatenate([t, q_true], 1), "truth_intr": intr, "truth_pt": pts})
 
 
+def make_calibration_scene(camera_model=F.CAM_KANNALA_BRANDT, ncam=5, grid=(20, 10), spacing=0.1, wall_z=3.0, arc_spread=0.8, seed=100,
+                           landmark_sigma=0.01, pose_sigma_t=0.02, pose_sigma_deg=1.0, intr_rel_sigma=0.02, scene="wall") -> BAProblem:
+    """The graph of the reference's camera calibration tests (tests/camera_kannala_brandt_integration.rs:45-225,
+    camera_double_sphere_integration.rs, tests/camera_test_utils.rs:215-285): a planar wall of grid[0] x grid[1] points at depth
+    wall_z, ncam cameras on a horizontal arc looking down +z (identity rotation), every camera sees every point, exact
+    projections; ONE ProjectionFactor with all its observations per camera over [pose_k, "landmarks", "intrinsics"] - i.e. one
+    intrinsics variable shared by all cameras (APEX_OPT_SHARED_INTRINSICS), SelfCalibration, no loss, pose_0 fixed. Initial
+    values = truth perturbed (1 cm, 2 cm / 1 deg, 2 %), own seeded noise."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    nx, ny = grid
+    ix, iy = np.meshgrid(np.arange(nx), np.arange(ny))
+    pts = np.stack([ix.ravel() * spacing - (nx - 1) * spacing / 2, iy.ravel() * spacing - (ny - 1) * spacing / 2, np.full(nx * ny, wall_z)], 1)
+    if scene == "hemisphere":   # generate_scene_points (tests/camera_test_utils.rs:24-43): index-driven points in front of the cameras
+        i = np.arange(nx * ny, dtype=np.float64)
+        a1, a2, depth = (i * 2.4) % (2 * np.pi), (i * 1.7) % np.pi, 2.0 + 3.0 * ((i * 0.17) % 1.0)
+        pts = np.stack([depth * np.sin(a2) * np.cos(a1), depth * np.sin(a2) * np.sin(a1), depth * np.abs(np.cos(a2)) + 2.0], 1)
+    tx = ((np.arange(ncam) / (ncam - 1)) - 0.5) * 2.0 * arc_spread if ncam > 1 else np.zeros(1)
+    t = np.stack([tx, np.zeros(ncam), np.zeros(ncam)], 1)
+    q_true = np.tile(np.array([1.0, 0.0, 0.0, 0.0]), (ncam, 1))
+    truth = {F.CAM_KANNALA_BRANDT: [200.0, 200.0, 300.0, 200.0, 0.5, 0.1, 0.0, 0.0],
+             F.CAM_DOUBLE_SPHERE: [200.0, 200.0, 300.0, 200.0, 0.5, 0.5],
+             F.CAM_PINHOLE: [500.0, 500.0, 320.0, 240.0]}[camera_model]
+    intr_true = np.tile(np.array(truth), (ncam, 1))
+    obs_cam = np.repeat(np.arange(ncam, dtype=np.uint32), pts.shape[0])
+    obs_pt = np.tile(np.arange(pts.shape[0], dtype=np.uint32), ncam)
+    pc = pts[obs_pt] + t[obs_cam]                       # identity rotation: p_cam = p_world + t
+    uv, valid = project(camera_model, intr_true[obs_cam], pc)
+    assert valid.all(), "every camera must see every calibration point"
+    pts0 = pts + landmark_sigma * rng.standard_normal(pts.shape)
+    dth = np.deg2rad(pose_sigma_deg) * rng.standard_normal((ncam, 3))
+    pose0 = np.concatenate([t + pose_sigma_t * rng.standard_normal((ncam, 3)), quat_mul(q_true, axis_angle_to_quat(dth))], 1)
+    pose0[0] = np.concatenate([t[0], q_true[0]])        # the anchor starts at the truth (it is fixed)
+    shared0 = np.array(truth) * (1.0 + intr_rel_sigma * rng.standard_normal(len(truth)))
+    pose_fixed = np.zeros(ncam, np.uint8)
+    pose_fixed[0] = 0x3F
+    return BAProblem(camera_model=camera_model, opt_flags=F.OPT_POSE | F.OPT_LANDMARK | F.OPT_INTRINSIC | F.OPT_SHARED_INTRINSICS, pose=pose0,
+                     intr=np.tile(shared0, (ncam, 1)), pt=pts0, obs_cam=obs_cam, obs_pt=obs_pt, obs_uv=uv, loss_id=F.LOSS_NONE, loss_params=(0.0,) * 4,
+                     intr_vars_present=True, pose_fixed=pose_fixed, intr_fixed=np.zeros(ncam, np.uint16),
+                     meta={"truth_intr": np.array(truth), "truth_pose": np.concatenate([t, q_true], 1), "truth_pt": pts})
+
+
 def make_shape(name: str, scale: float = 1.0, **kw) -> BAProblem:
     """One of the BASELINE.json configs (optionally scaled down for tests); seed = 0xA9E50000 + config#."""
     ncam, npts, mean_track, model, loss, cfg = SHAPES[name]

@@ -77,6 +77,12 @@ enum apex_camera_model {
 #define APEX_OPT_POSE 1u
 #define APEX_OPT_LANDMARK 2u
 #define APEX_OPT_INTRINSIC 4u
+/* With APEX_OPT_INTRINSIC: ALL cameras share ONE intrinsics variable - the graph of the reference's calibration tests
+ * (tests/camera_*_integration.rs: one multi-observation ProjectionFactor per camera over [pose_k, landmarks, intrinsics],
+ * src/factors/projection_factor.rs:184-364; an n-observation block is n rows of this SoA description). intr[0] is the shared
+ * value (rows 1.. are ignored on upload and returned equal to row 0); explicit Schur + Cholesky only, and the loss must be
+ * NONE or L2 (a robust loss on an n-observation block weighs the block's whole squared norm, not each observation). */
+#define APEX_OPT_SHARED_INTRINSICS 8u
 
 /* LossFunction implementations (src/core/loss_functions.rs). params[] meaning per id. */
 enum apex_loss {

@@ -1226,6 +1226,7 @@ struct Ctx {
   std::vector<uint8_t> pose_fixed, pt_fixed; std::vector<uint16_t> intr_fixed;
   // derived structure
   bool opt_intr = false;
+  bool shared_intr = false;            // one intrinsics variable for all cameras (APEX_OPT_SHARED_INTRINSICS)
   int dc = 6;                          // camera DOF inside the reduced system (pose6 [+K])
   size_t cam_dof = 0, lm_dof = 0;      // reference layout sizes
   std::vector<size_t> col_intr, col_pose, col_pt;  // reference (sorted-name) column offsets; cameras start at 0
@@ -1250,6 +1251,7 @@ std::string var_name(const char* prefix, int width, uint32_t idx) {
 // bin/bundle_adjustment.rs:240-253 names them pose_%04d / intr_%04d / pt_%05d.
 void build_structure(Ctx& c) {
   c.opt_intr = (c.opt & APEX_OPT_INTRINSIC) != 0;
+  c.shared_intr = c.opt_intr && (c.opt & APEX_OPT_SHARED_INTRINSICS) != 0;
   c.dc = 6 + (c.opt_intr ? c.K : 0);
   bool have_intr_vars = c.opt_intr || c.intr_vars;
   struct Var { std::string name; int kind; uint32_t idx; int size; };
@@ -1729,8 +1731,53 @@ apex_status solve_implicit(Ctx& c, int precond_kind, int cg_max_it, double cg_to
   return APEX_OK;
 }
 
+// Shared intrinsics (the reference's calibration graphs, tests/camera_*_integration.rs): [pose_k, landmarks, intrinsics] with ONE
+// intrinsics variable. The reference solves these with its default sparse Cholesky on the full normal equations
+// (SparseCholeskySolver::solve_augmented_equation, src/linalg/sparse/cholesky.rs:137-199: H = J^T J + lambda I, H dx = -J^T r);
+// restated densely: unknowns [poses 6 each | intrinsics K | landmarks 3 each].
+apex_status solve_shared_dense(Ctx& c, double lambda, StepOut& out) {
+  const int K = c.K, dc = c.dc;
+  const size_t np = 6 * (size_t)c.ncam, n = np + K + 3 * (size_t)c.npts;
+  std::vector<double> H(n * n, 0.0), g(n, 0.0), dx(n, 0.0);
+  std::vector<size_t> col(6 + K + 3);
+  for (uint64_t o = 0; o < c.nobs; ++o) {
+    const BlockLin& b = c.lin[o];
+    const size_t cam = c.obs_cam[o], p = c.obs_pt[o];
+    double J[2][6 + MAXK + 3];
+    int m = 0;
+    for (int k = 0; k < 6; ++k, ++m) { col[m] = 6 * cam + k; J[0][m] = b.jpose[k]; J[1][m] = b.jpose[6 + k]; }
+    for (int k = 0; k < K; ++k, ++m) { col[m] = np + k; J[0][m] = b.jintr[k]; J[1][m] = b.jintr[K + k]; }
+    for (int k = 0; k < 3; ++k, ++m) { col[m] = np + K + 3 * p + k; J[0][m] = b.jpt[k]; J[1][m] = b.jpt[3 + k]; }
+    for (int a = 0; a < m; ++a) {
+      g[col[a]] += J[0][a] * b.r[0] + J[1][a] * b.r[1];
+      for (int bb = 0; bb < m; ++bb) H[col[a] * n + col[bb]] += J[0][a] * J[0][bb] + J[1][a] * J[1][bb];
+    }
+  }
+  for (size_t i = 0; i < n; ++i) H[i * n + i] += lambda;
+  std::vector<double> rhs(n);
+  for (size_t i = 0; i < n; ++i) rhs[i] = -g[i];
+  if (!dense_cholesky(H.data(), n)) { c.err = "normal equations not positive definite"; return APEX_ERR_FACTORIZATION_FAILED; }
+  cholesky_solve(H.data(), n, rhs.data(), dx.data());
+  out.cam.assign((size_t)c.ncam * dc, 0.0);
+  for (uint32_t cam = 0; cam < c.ncam; ++cam) {
+    for (int k = 0; k < 6; ++k) out.cam[(size_t)cam * dc + k] = dx[6 * (size_t)cam + k];
+    for (int k = 0; k < K; ++k) out.cam[(size_t)cam * dc + 6 + k] = dx[np + k];   // every camera's copy moves by the shared step
+  }
+  out.intr_unref.clear();
+  out.pt.assign(dx.begin() + np + K, dx.end());
+  double g2 = 0, s2 = 0, sg = 0;
+  for (size_t i = 0; i < n; ++i) { g2 += g[i] * g[i]; s2 += dx[i] * dx[i]; sg += dx[i] * g[i]; }
+  out.grad_norm = std::sqrt(g2); out.step_norm = std::sqrt(s2); out.step_dot_grad = sg; out.pcg_iters = 0;
+  c.last_pcg_iters = 0; c.last_step_cam = out.cam; c.last_step_pt = out.pt;
+  return APEX_OK;
+}
+
 apex_status solve_augmented(Ctx& c, int variant, int precond, int cg_max_it, double cg_tol, double lambda, StepOut& out) {
   if (!c.linearized || c.lin_lambda != lambda) linearize(c, lambda);
+  if (c.shared_intr) {
+    if (variant != APEX_SCHUR_EXPLICIT) { c.err = "shared intrinsics: direct solve only"; return APEX_ERR_UNSUPPORTED; }
+    return solve_shared_dense(c, lambda, out);
+  }
   apex_status st;
   if (variant == APEX_SCHUR_IMPLICIT) st = solve_implicit(c, precond, cg_max_it, cg_tol, lambda, out);
   else st = solve_explicit(c, variant == APEX_SCHUR_EXPLICIT_PCG, cg_max_it, cg_tol, lambda, out);
@@ -1791,7 +1838,8 @@ void apply_step(Ctx& c, const StepOut& s, double sign) {
 double parameter_norm(const Ctx& c) {
   double s = 0;
   for (double v : c.pose) s += v * v;
-  if (c.opt_intr || c.intr_vars) for (double v : c.intr) s += v * v;
+  if (c.shared_intr) { for (int k = 0; k < c.K; ++k) s += c.intr[k] * c.intr[k]; }   // one variable
+  else if (c.opt_intr || c.intr_vars) for (double v : c.intr) s += v * v;
   for (double v : c.pt) s += v * v;
   return std::sqrt(s);
 }
@@ -1935,6 +1983,11 @@ apex_status oracle_problem_upload(oracle_ctx* ctx, const apex_problem_desc* d) {
   c.ncam = d->ncam; c.npts = d->npts; c.nobs = d->nobs;
   c.pose.assign(d->pose, d->pose + 7 * (size_t)c.ncam);
   c.intr.assign(d->intr, d->intr + (size_t)K * c.ncam);
+  if ((d->opt_flags & APEX_OPT_INTRINSIC) && (d->opt_flags & APEX_OPT_SHARED_INTRINSICS)) {
+    if (d->loss_id != APEX_LOSS_NONE && d->loss_id != APEX_LOSS_L2) { c.err = "shared intrinsics: the loss must be NONE or L2"; return APEX_ERR_UNSUPPORTED; }
+    if (d->obs_loss) { c.err = "shared intrinsics: per-block losses are not supported"; return APEX_ERR_UNSUPPORTED; }
+    for (uint32_t cam = 1; cam < c.ncam; ++cam) for (int k = 0; k < K; ++k) c.intr[(size_t)cam * K + k] = c.intr[k];
+  }
   c.pt.assign(d->pt, d->pt + 3 * (size_t)c.npts);
   c.obs_cam.assign(d->obs_cam, d->obs_cam + c.nobs);
   c.obs_pt.assign(d->obs_pt, d->obs_pt + c.nobs);

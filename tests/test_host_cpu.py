@@ -269,6 +269,58 @@ def test_oracle_jacobi_scaling_matches_a_dense_restatement():
     assert np.abs(o2.get_step()[0] - dca).max() > 1e-6 * np.abs(dca).max()
 
 
+def reference_calibration_problem(model):
+    """The reference's calibration test inputs, value for value: truth from synth.make_calibration_scene (wall for Kannala-Brandt,
+    generate_scene_points for double sphere), initial values from the reference's own index-driven Box-Muller noise
+    (tests/camera_test_utils.rs:53-150: landmarks 1 cm seed 100, poses 2 cm / 1 deg seed 200 + 10 i, intrinsics 2 % seed 300;
+    pose noise applied with SE3 right-plus)."""
+    def ref_normal(std, index):
+        u1 = ((index * 12345 + 67890) % 10000) / 10000.0
+        u2 = ((index * 54321 + 98765) % 10000) / 10000.0
+        return std * np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+    prob = synth.make_calibration_scene(model, scene="wall" if model == F.CAM_KANNALA_BRANDT else "hemisphere")
+    truth_pt, truth_pose, truth_intr = prob.meta["truth_pt"], prob.meta["truth_pose"], prob.meta["truth_intr"]
+    pt = truth_pt + np.array([[ref_normal(0.01, 100 + 3 * i + k) for k in range(3)] for i in range(truth_pt.shape[0])])
+    lib = oracle_lib()
+    pose = np.empty_like(truth_pose)
+    for i in range(truth_pose.shape[0]):
+        base = 200 + 10 * i
+        tau = np.array([ref_normal(0.02, base + k) for k in range(3)] + [ref_normal(np.deg2rad(1.0), base + 3 + k) for k in range(3)])
+        lib.oracle_se3_plus(F.ptr(np.ascontiguousarray(truth_pose[i])), F.ptr(tau), pose[i].ctypes.data)
+    intr0 = np.array([truth_intr[i] * (1.0 + ref_normal(0.02, 300 + i)) for i in range(len(truth_intr))])
+    return dataclasses.replace(prob, pose=pose, pt=pt, intr=np.tile(intr0, (prob.ncam, 1)), meta=dict(prob.meta))
+
+
+@pytest.mark.parametrize("model,rel_tol,floor", [(F.CAM_KANNALA_BRANDT, [0.05, 0.05, 0.05, 0.05, 0.10, 0.20], 0.01), (F.CAM_DOUBLE_SPHERE, [0.05] * 4 + [0.10, 0.10], 0.1)],
+                         ids=["kannala_brandt", "double_sphere"])
+def test_oracle_calibration_scene_meets_the_reference_tests_criteria(model, rel_tol, floor):
+    """The reference's own acceptance criteria for its multi-observation / shared-intrinsics graphs, on its own inputs
+    (tests/camera_kannala_brandt_integration.rs:45-330, camera_double_sphere_integration.rs:38-310): LM (100 iterations, cost /
+    parameter / gradient tolerances 1e-8 / 1e-8 / 1e-10, damping 1e-3) on 5 cameras x 200 points with ONE intrinsics variable, every
+    pose_0 DOF fixed, must end in a converged status, reduce the cost by more than 85 %, reach a reprojection RMSE below 2 px and
+    recover the intrinsics within the tests' per-parameter tolerances."""
+    prob = reference_calibration_problem(model)
+    o = OracleContext().upload(prob)
+    cfg = o.default_config(False)
+    cfg.schur_variant = F.SCHUR_EXPLICIT
+    cfg.max_iterations, cfg.cost_tolerance, cfg.parameter_tolerance, cfg.gradient_tolerance, cfg.damping = 100, 1e-8, 1e-8, 1e-10, 1e-3
+    res, tr = o.lm_solve(cfg)
+    assert res.status in (0, 2, 3, 4)   # Converged | CostToleranceReached | ParameterToleranceReached | GradientToleranceReached (include/apex_gpu.h)
+    assert (res.initial_cost - res.final_cost) / res.initial_cost > 0.85
+    assert np.sqrt(res.final_cost / prob.nobs) < 2.0
+    pose, intr, pt = o.params_download()
+    assert np.array_equal(intr, np.tile(intr[0], (prob.ncam, 1))), "one intrinsics variable"
+    truth = prob.meta["truth_intr"]
+    for i, tol in enumerate(rel_tol):
+        assert abs(intr[0, i] - truth[i]) / max(abs(truth[i]), floor) < tol, (i, intr[0, i], truth[i])
+    for i in range(len(rel_tol), len(truth)):
+        assert abs(intr[0, i] - truth[i]) < 0.25
+    # the shared variable is not the per-camera problem: another trajectory
+    per_cam = dataclasses.replace(prob, opt_flags=prob.opt_flags & ~F.OPT_SHARED_INTRINSICS, meta={})
+    r2, _ = OracleContext().upload(per_cam).lm_solve(cfg)
+    assert abs(r2.final_cost - res.final_cost) > 1e-9 * max(res.final_cost, 1e-12) or r2.iterations != res.iterations
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` prints one JSON line with the contract's keys (runs the oracle on a bounded sample)."""
     env = dict(os.environ, OMP_NUM_THREADS="4")
