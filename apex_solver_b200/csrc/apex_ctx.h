@@ -103,6 +103,7 @@ struct ShardMap {
 constexpr int MAX_TILE_PTS = 128;     // landmarks per normal tile
 
 struct CamItem { uint32_t cam, begin, end, pad; };
+struct PairBlock { uint32_t cam_i, cam_j, begin, end; };   // block (cam_i >= cam_j) of the reduced camera system: its pairs [begin, end)
 struct LossSpecPod { int id; double p0, p1; };   // layout of ba_device.cuh's LossSpec (one LossFunction instance on the device)  // [begin,end) in the camera-major arrays
 
 // Scalars that live on the device (LM bookkeeping, PCG control, norms, error flags).
@@ -297,6 +298,13 @@ struct Ctx {
   DevBuf<double> vb, vx, vr, vz, vp, vy;  // PCG vectors, ncam*dc each
   DevBuf<double> step_cam, step_pt;       // [ncam][dc], [npl][3]
   DevBuf<double> red_scratch;             // block partials of the deterministic reductions
+  // formation of the explicit S by camera-pair blocks (built on the first explicit solve after an upload)
+  bool pairs_ready = false;
+  uint32_t npair_blocks = 0;
+  DevBuf<PairBlock> pair_blocks;          // sorted by (cam_i, cam_j)
+  DevBuf<uint2> pair_slots;               // {slot of observation i, slot of observation j} of the same landmark, cam_j <= cam_i
+  DevBuf<uint32_t> slot_lpg;              // slot -> local landmark
+  DevBuf<uint8_t> slot_cs8;               // slot -> lane of the camera half of its Jacobian inside its chunk
   DevBuf<double> S;                       // dense reduced camera system (explicit variants), n*n row-major
   DevBuf<double> E;                       // [chunk][3*dc][TILE] H_cp blocks for S formation
   DevBuf<double> dvec;                    // dense-solver work vectors
@@ -360,6 +368,7 @@ inline cudaEvent_t* prof_pair(std::vector<cudaEvent_t>& pool, size_t idx) {
 apex_status problem_upload(Ctx& c, const apex_problem_desc* d);
 std::vector<double> gather_local_points(const Ctx& c, const double* pt_full);
 apex_status layout_stats(const apex_problem_desc* d, int nranks, int rank, apex_layout_stats* out, std::string& err);
+apex_status build_schur_pairs(Ctx& c);   // camera-pair blocks of the explicit S from the host copy of the layout (lazy, once per upload)
 
 // linearize.cu
 apex_status launch_normalize_poses(Ctx& c);

@@ -101,6 +101,90 @@ __global__ void __launch_bounds__(TILE) schur_form_kernel(FormArgs a) {
   }
 }
 
+// K7 by camera-pair blocks (build_schur_pairs, problem.cu): one warp per block (cam_i >= cam_j) of the lower block triangle adds the
+// block's (observation i, observation j) pairs in their fixed order and stores the dc x dc block once - no reductions into memory,
+// bitwise reproducible. Lane l = g*DC + q owns column q and the rows p = g, g + G, ... (G = 32 / DC groups of lanes); per pair every lane
+// recomputes the 2x2 middle  Jp_i Hpp^-1 Jp_j^T  (broadcast loads), reads its two entries of Jc_j and the rows' entries of Jc_i.
+struct PairArgs {
+  const PairBlock* blocks;
+  const uint2* pairs;
+  const uint32_t* slot_lpg;
+  const uint8_t* slot_cs8;
+  const double* J;
+  const double* hinv;
+  double* S;
+  size_t ld;
+  uint32_t npl, nblocks;
+};
+
+template <int DC>
+__global__ void __launch_bounds__(256, 4) schur_form_pairs_kernel(PairArgs a) {
+  constexpr int NPAIR = DC + 3, G = 32 / DC, RPL = (DC + G - 1) / G;
+  const uint32_t b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= a.nblocks) return;
+  const int lane = threadIdx.x & 31, g = lane / DC, q = lane % DC;
+  const bool act = g < G;
+  const PairBlock blk = a.blocks[b];
+  double acc[RPL];
+#pragma unroll
+  for (int r = 0; r < RPL; ++r) acc[r] = 0.0;
+  const double2* J2 = reinterpret_cast<const double2*>(a.J);
+  const size_t n = a.npl;
+  // the pair's indices (pair -> slots -> landmark / camera-half lanes) are fetched one pair ahead: two of the three dependent
+  // memory round trips per pair are then off the critical path
+  uint32_t nsi = 0, nsj = 0, nlp = 0, ncsi = 0, ncsj = 0;
+  auto fetch = [&](uint32_t e) {
+    const uint2 pr = __ldg(a.pairs + e);
+    nsi = pr.x; nsj = pr.y;
+    nlp = __ldg(a.slot_lpg + nsi); ncsi = __ldg(a.slot_cs8 + nsi); ncsj = __ldg(a.slot_cs8 + nsj);
+  };
+  if (blk.begin < blk.end) fetch(blk.begin);
+  for (uint32_t e = blk.begin; e < blk.end; ++e) {
+    const uint32_t si = nsi, sj = nsj, lp = nlp, csi = ncsi, csj = ncsj;
+    if (e + 1 < blk.end) fetch(e + 1);
+    const size_t bi = (size_t)(si >> 8) * NPAIR * TILE, bj = (size_t)(sj >> 8) * NPAIR * TILE;
+    const uint32_t pmi = si & 255u, pmj = sj & 255u;
+    double pi[6], pj[6];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      const double2 u = __ldg(J2 + bi + (size_t)(DC + m) * TILE + pmi), v = __ldg(J2 + bj + (size_t)(DC + m) * TILE + pmj);
+      pi[2 * m] = u.x; pi[2 * m + 1] = u.y; pj[2 * m] = v.x; pj[2 * m + 1] = v.y;
+    }
+    const double h00 = __ldg(a.hinv + 0 * n + lp), h01 = __ldg(a.hinv + 1 * n + lp), h02 = __ldg(a.hinv + 2 * n + lp);
+    const double h11 = __ldg(a.hinv + 3 * n + lp), h12 = __ldg(a.hinv + 4 * n + lp), h22 = __ldg(a.hinv + 5 * n + lp);
+    double M[2][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const double g0 = pi[r * 3] * h00 + pi[r * 3 + 1] * h01 + pi[r * 3 + 2] * h02;
+      const double g1 = pi[r * 3] * h01 + pi[r * 3 + 1] * h11 + pi[r * 3 + 2] * h12;
+      const double g2 = pi[r * 3] * h02 + pi[r * 3 + 1] * h12 + pi[r * 3 + 2] * h22;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) M[r][cc] = g0 * pj[cc * 3] + g1 * pj[cc * 3 + 1] + g2 * pj[cc * 3 + 2];
+    }
+    if (!act) continue;
+    // element k of a camera half: plane k / 2, component k % 2
+    const double* Jci = a.J + 2 * (bi + csi), *Jcj = a.J + 2 * (bj + csj);
+    auto elem = [&](const double* base, int k) { return __ldg(base + 2 * (size_t)(k >> 1) * TILE + (k & 1)); };
+    const double cj0 = elem(Jcj, q), cj1 = elem(Jcj, DC + q);
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+      const int p = g + r * G;
+      if (p < DC) {
+        const double ci0 = elem(Jci, p), ci1 = elem(Jci, DC + p);
+        const double a0 = ci0 * M[0][0] + ci1 * M[1][0], a1 = ci0 * M[0][1] + ci1 * M[1][1];
+        acc[r] -= fma(a0, cj0, a1 * cj1);
+      }
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+      const int p = g + r * G;
+      if (p < DC) a.S[((size_t)blk.cam_i * DC + p) * a.ld + (size_t)blk.cam_j * DC + q] = acc[r];
+    }
+  }
+}
+
 // S diagonal blocks += H_cc + lambda I (explicit_schur.rs:1186-1205, :784-792); identity on the padded tail
 __global__ void schur_diag_kernel(double* S, size_t ld, const double* hcc, const DevState* st, uint32_t ncam, int dc, uint32_t n, uint32_t npad,
                                   int add_hcc) {
@@ -720,7 +804,25 @@ apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol) {
   // --- S ---
   cudaEvent_t* evf = c.prof ? prof_pair(c.ev_form, c.ev_form_used++) : nullptr;
   if (evf) cudaEventRecord(evf[0], s);
-  if (c.ntiles) {
+  const bool by_pairs = !getenv("APEX_SCHUR_FORM_ATOMIC");   // (the reduction-per-element kernel stays for A/B measurements)
+  if (c.ntiles && by_pairs) {
+    APEX_TRY(build_schur_pairs(c));
+    PairArgs pa{c.pair_blocks.p, c.pair_slots.p, c.slot_lpg.p, c.slot_cs8.p, c.J.p, c.hinv.p, S, ld, c.npl, c.npair_blocks};
+    const unsigned grid = (c.npair_blocks + 7) / 8;
+    if (grid) {
+      switch (c.dc) {
+        case 6: schur_form_pairs_kernel<6><<<grid, 256, 0, s>>>(pa); break;
+        case 9: schur_form_pairs_kernel<9><<<grid, 256, 0, s>>>(pa); break;
+        case 10: schur_form_pairs_kernel<10><<<grid, 256, 0, s>>>(pa); break;
+        case 11: schur_form_pairs_kernel<11><<<grid, 256, 0, s>>>(pa); break;
+        case 12: schur_form_pairs_kernel<12><<<grid, 256, 0, s>>>(pa); break;
+        case 14: schur_form_pairs_kernel<14><<<grid, 256, 0, s>>>(pa); break;
+        case 15: schur_form_pairs_kernel<15><<<grid, 256, 0, s>>>(pa); break;
+        default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
+      }
+      c.launches++;
+    }
+  } else if (c.ntiles) {
     FormArgs fa{c.tiles.p, c.slot_cam.p, c.slot_lp.p, c.pt_slot0.p, c.pt_cnt.p, c.cslot_meta.p, c.J.p, c.hinv.p, S, ld, c.npl};
     switch (c.dc) {
       case 6: schur_form_kernel<6><<<c.ntiles, TILE, 0, s>>>(fa); break;

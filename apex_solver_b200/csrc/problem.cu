@@ -509,6 +509,84 @@ apex_status layout_stats(const apex_problem_desc* d, int nranks, int rank, apex_
   return APEX_OK;
 }
 
+// Camera-pair blocks of the explicit reduced camera system (K7). S_(ci,cj) -= sum over the landmarks seen by both cameras of
+// (Jc_i^T Jp_i) Hpp^-1 (Jp_j^T Jc_j): the (observation i, observation j) pairs of one landmark with cam_j <= cam_i are grouped by
+// block here, once per upload and only when an explicit solve asks for it, so that the kernel adds each block's pairs in
+// registers, in a fixed order, and writes it once - instead of one FP64 reduction per element and pair. Parallel over cameras:
+// camera ci's pairs are collected through its slots and sorted (stably) by cam_j.
+apex_status build_schur_pairs(Ctx& c) {
+  if (c.pairs_ready) return APEX_OK;
+  if (!c.staging) { c.err = "no layout"; return APEX_ERR_INVALID_STATE; }
+  HostLayout& L = *static_cast<HostLayout*>(c.staging.get());
+  const size_t nslots = c.nslots;
+  const uint32_t ncam = c.ncam;
+  std::vector<uint32_t> slot_lpg(nslots, 0xFFFFFFFFu);
+  for (const TileDesc& t : L.tiles)
+    for (uint32_t ch = 0; ch < t.nchunks; ++ch)
+      for (int lane = 0; lane < TILE; ++lane) {
+        const size_t slot = ((size_t)t.chunk0 + ch) * TILE + lane;
+        if (L.slot_cam[slot] != PAD_CAM) slot_lpg[slot] = t.pt0 + L.slot_lp[slot];
+      }
+  std::vector<uint32_t> cam_start((size_t)ncam + 1, 0), cam_slots;
+  for (size_t sl = 0; sl < nslots; ++sl) if (L.slot_cam[sl] != PAD_CAM) cam_start[L.slot_cam[sl] + 1]++;
+  for (uint32_t k = 0; k < ncam; ++k) cam_start[k + 1] += cam_start[k];
+  cam_slots.resize(cam_start[ncam]);
+  {
+    std::vector<uint32_t> cur(cam_start.begin(), cam_start.end() - 1);
+    for (size_t sl = 0; sl < nslots; ++sl) if (L.slot_cam[sl] != PAD_CAM) cam_slots[cur[L.slot_cam[sl]]++] = (uint32_t)sl;
+  }
+  std::vector<uint64_t> pair_off((size_t)ncam + 1, 0);
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int64_t ci = 0; ci < (int64_t)ncam; ++ci) {
+    uint64_t np = 0;
+    for (uint32_t e = cam_start[ci]; e < cam_start[ci + 1]; ++e) {
+      const uint32_t lp = slot_lpg[cam_slots[e]];
+      for (uint32_t sj = L.pt_slot0[lp]; sj < L.pt_slot0[lp] + L.pt_cnt[lp]; ++sj) np += L.slot_cam[sj] <= (uint32_t)ci;
+    }
+    pair_off[ci + 1] = np;
+  }
+  for (uint32_t k = 0; k < ncam; ++k) pair_off[k + 1] += pair_off[k];
+  const uint64_t npairs = pair_off[ncam];
+  if (npairs > 0xFFFFFFF0ull) { c.err = "too many observation pairs for the explicit Schur complement"; return APEX_ERR_UNSUPPORTED; }
+  HostVec<uint2> pairs(npairs);
+  std::vector<std::vector<PairBlock>> blk(ncam);
+#pragma omp parallel
+  {
+    struct Ent { uint32_t cj, si, sj; };
+    std::vector<Ent> tmp;
+#pragma omp for schedule(dynamic, 16)
+    for (int64_t ci = 0; ci < (int64_t)ncam; ++ci) {
+      tmp.clear();
+      for (uint32_t e = cam_start[ci]; e < cam_start[ci + 1]; ++e) {
+        const uint32_t si = cam_slots[e], lp = slot_lpg[si];
+        for (uint32_t sj = L.pt_slot0[lp]; sj < L.pt_slot0[lp] + L.pt_cnt[lp]; ++sj)
+          if (L.slot_cam[sj] <= (uint32_t)ci) tmp.push_back({L.slot_cam[sj], si, sj});
+      }
+      std::stable_sort(tmp.begin(), tmp.end(), [](const Ent& a, const Ent& b) { return a.cj < b.cj; });
+      const uint64_t off = pair_off[ci];
+      for (size_t k = 0; k < tmp.size(); ++k) {
+        pairs[off + k] = make_uint2(tmp[k].si, tmp[k].sj);
+        if (k == 0 || tmp[k].cj != tmp[k - 1].cj) {
+          if (!blk[ci].empty()) blk[ci].back().end = (uint32_t)(off + k);
+          blk[ci].push_back(PairBlock{(uint32_t)ci, tmp[k].cj, (uint32_t)(off + k), 0});
+        }
+      }
+      if (!blk[ci].empty()) blk[ci].back().end = (uint32_t)(off + tmp.size());
+    }
+  }
+  std::vector<PairBlock> blocks;
+  for (uint32_t k = 0; k < ncam; ++k) blocks.insert(blocks.end(), blk[k].begin(), blk[k].end());
+  c.npair_blocks = (uint32_t)blocks.size();
+  cudaStream_t s = c.stream;
+  APEX_CUDA_TRY(c, upload_vec(c.pair_blocks, blocks, s));
+  APEX_CUDA_TRY(c, upload_vec(c.pair_slots, pairs, s));
+  APEX_CUDA_TRY(c, upload_vec(c.slot_lpg, slot_lpg, s));
+  APEX_CUDA_TRY(c, upload_vec(c.slot_cs8, c.slot_pos, s));
+  APEX_CUDA_TRY(c, cudaStreamSynchronize(s));   // the host vectors die with this scope
+  c.pairs_ready = true;
+  return APEX_OK;
+}
+
 // rows of the owned landmarks out of a full [npts][3] host array
 std::vector<double> gather_local_points(const Ctx& c, const double* pt_full) {
   std::vector<double> out((size_t)c.npl * 3);
@@ -539,6 +617,7 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   lap("validate");
   const int K = model_intr_dim(d->camera_model);
   c.have_problem = false;
+  c.pairs_ready = false;
   c.linearized = false;
   c.have_step = false;
   if (c.pcg_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)c.pcg_graph_exec); c.pcg_graph_exec = nullptr; }

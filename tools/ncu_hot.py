@@ -18,7 +18,7 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(src.splitlines()))
 h2, data = rows[1], rows[2:]
 iS, isrc = h2.index("# Samples"), h2.index("Source")
-cols = {k: h2.index(k) for k in ("stall_barrier", "stall_long_sb", "stall_short_sb", "stall_wait", "stall_mio", "stall_math", "stall_lg", "L1 Wavefronts Shared")}
+cols = {k: h2.index(k) for k in ("stall_barrier", "stall_long_sb", "stall_short_sb", "stall_wait", "stall_mio", "stall_math", "stall_lg", "L1 Wavefronts Shared") if k in h2}
 tot = sum(int(r[iS]) for r in data)
 print("samples", tot)
 for i, r in sorted(sorted(enumerate(data), key=lambda x: -int(x[1][iS]))[:ntop]):
