@@ -371,10 +371,10 @@ __global__ void __launch_bounds__(128) chol_syrk_kernel(double* A, size_t ld, ui
 // The deep (k = 256) trailing update on 128x128 tiles: 64x64 tiles move 64 KB through L2 per 64-deep slice for 0.5 MFLOP
 // (8 flop/B - at the DMMA rate that is more than L2 delivers); a 128x128 tile doubles the intensity. 256 threads = 8
 // warps as 4 (rows) x 2 (columns), each warp a 32x64 sub-tile = 4x8 DMMA.8x8x4 accumulators (128 registers); the two
-// 128 x 32 panel slices of a k step are staged with cp.async (16-byte copies) into a double-buffered shared-memory ring
+// 128 x 32 panel slices of a k step are staged with cp.async (16-byte copies) into a three-stage shared-memory ring
 // (stride 36 doubles: fragment loads hit 16 distinct 8-byte banks per half warp), so the loads of slice s+1 are in
 // flight while slice s feeds the tensor pipe.
-constexpr int SB = 128, SKC = 32, SPLD = SKC + 4;
+constexpr int SB = 128, SKC = 32, SPLD = SKC + 4, SYRK_STAGES = 3;
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
@@ -393,27 +393,30 @@ __global__ void __launch_bounds__(256, 1) chol_syrk128_kernel(double* A, size_t 
   for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
-  auto stage = [&](int buf, uint32_t kc) {  // 2 panels x 128 rows x 32 doubles = 2 x 2048 16-byte copies
-    double* Pa = smem + (size_t)buf * 2 * SB * SPLD;
-    double* Pb = Pa + SB * SPLD;
-    for (int e = tid; e < SB * SKC / 2; e += 256) {
-      const int r = e / (SKC / 2), c2 = (e % (SKC / 2)) * 2;
-      cp_async16(Pa + r * SPLD + c2, A + (ri + r) * ld + k0 + kc + c2);
-      cp_async16(Pb + r * SPLD + c2, A + (rj + r) * ld + k0 + kc + c2);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
   const int nslices = (int)(kdepth / SKC);
-  stage(0, 0);
-  for (int sidx = 0; sidx < nslices; ++sidx) {
-    if (sidx + 1 < nslices) {
-      stage((sidx + 1) & 1, (uint32_t)(sidx + 1) * SKC);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+  auto stage = [&](int sl) {  // slice sl -> buffer sl % 3: 2 panels x 128 rows x 32 doubles = 2 x 2048 16-byte copies (nothing past the end)
+    if (sl < nslices) {
+      double* Pa = smem + (size_t)(sl % SYRK_STAGES) * 2 * SB * SPLD;
+      double* Pb = Pa + SB * SPLD;
+      const uint32_t kc = (uint32_t)sl * SKC;
+      for (int e = tid; e < SB * SKC / 2; e += 256) {
+        const int r = e / (SKC / 2), c2 = (e % (SKC / 2)) * 2;
+        cp_async16(Pa + r * SPLD + c2, A + (ri + r) * ld + k0 + kc + c2);
+        cp_async16(Pb + r * SPLD + c2, A + (rj + r) * ld + k0 + kc + c2);
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // one group per call, empty or not: the wait below counts groups
+  };
+  // three-stage ring, ONE barrier per slice: at the top of iteration s the groups of slices 0..s+1 are committed, wait_group 1
+  // leaves only s+1 pending, the barrier makes slice s visible to everybody and proves that everybody is done with slice s-1,
+  // whose buffer then takes slice s+2
+  stage(0);
+  stage(1);
+  for (int sidx = 0; sidx < nslices; ++sidx) {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
-    const double* Pa = smem + (size_t)(sidx & 1) * 2 * SB * SPLD;
+    stage(sidx + 2);
+    const double* Pa = smem + (size_t)(sidx % SYRK_STAGES) * 2 * SB * SPLD;
     const double* Pb = Pa + SB * SPLD;
 #pragma unroll 2
     for (int kk = 0; kk < SKC; kk += 4) {
@@ -427,7 +430,6 @@ __global__ void __launch_bounds__(256, 1) chol_syrk128_kernel(double* A, size_t 
 #pragma unroll
         for (int ni = 0; ni < 8; ++ni) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
     }
-    __syncthreads();  // the buffer just read is refilled by the next iteration's stage()
   }
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi)
@@ -661,7 +663,7 @@ static apex_status dense_cholesky(Ctx& c, double* L, uint32_t npad) {
   const size_t ld = npad;
   const int smem = 2 * NB * PLD * (int)sizeof(double);
   const int trsm_smem_bytes = 2 * NB * PLD * (int)sizeof(double);
-  const int syrk128_smem = 2 * 2 * SB * SPLD * (int)sizeof(double);
+  const int syrk128_smem = SYRK_STAGES * 2 * SB * SPLD * (int)sizeof(double);
   if (!c.chol_attr_set) {   // per context, i.e. per device (function attributes are per device)
     APEX_CUDA_TRY(c, cudaFuncSetAttribute(chol_syrk128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, syrk128_smem));
     APEX_CUDA_TRY(c, cudaFuncSetAttribute(chol_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
