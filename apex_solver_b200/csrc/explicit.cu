@@ -369,37 +369,38 @@ __global__ void __launch_bounds__(128) chol_syrk_kernel(double* A, size_t ld, ui
 }
 
 // The deep (k = 256) trailing update on 128x128 tiles: 64x64 tiles move 64 KB through L2 per 64-deep slice for 0.5 MFLOP
-// (8 flop/B - at the DMMA rate that is more than L2 delivers); a 128x128 tile doubles the intensity. 256 threads = 8
-// warps as 4 (rows) x 2 (columns), each warp a 32x64 sub-tile = 4x8 DMMA.8x8x4 accumulators (128 registers); the two
+// (8 flop/B - at the DMMA rate that is more than L2 delivers); a 128x128 tile doubles the intensity. 512 threads = 16
+// warps as 4 x 4, each warp a 32x32 sub-tile = 4x4 DMMA.8x8x4 accumulators (four warps per scheduler: with two the tensor
+// pipe idled a quarter of the time on fixed-latency waits); the two
 // 128 x 32 panel slices of a k step are staged with cp.async (16-byte copies) into a three-stage shared-memory ring
 // (stride 36 doubles: fragment loads hit 16 distinct 8-byte banks per half warp), so the loads of slice s+1 are in
 // flight while slice s feeds the tensor pipe.
-constexpr int SB = 128, SKC = 32, SPLD = SKC + 4, SYRK_STAGES = 3;
+constexpr int SB = 128, SKC = 32, SPLD = SKC + 4, SYRK_STAGES = 3, SYRK_THREADS = 512;
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
-__global__ void __launch_bounds__(256, 1) chol_syrk128_kernel(double* A, size_t ld, uint32_t k0, uint32_t kdepth, uint32_t r0, uint32_t bj0) {
+__global__ void __launch_bounds__(SYRK_THREADS, 1) chol_syrk128_kernel(double* A, size_t ld, uint32_t k0, uint32_t kdepth, uint32_t r0, uint32_t bj0) {
   extern __shared__ __align__(16) double smem[];
   const uint32_t bi = blockIdx.x, bj = blockIdx.y + bj0;  // column tiles [bj0, bj0 + gridDim.y) of the trailing matrix
   if (bi < bj) return;
   const size_t ri = (size_t)r0 + (size_t)bi * SB, rj = (size_t)r0 + (size_t)bj * SB;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 64;
+  const int wm = (warp >> 2) * 32, wn = (warp & 3) * 32;   // 16 warps as 4 x 4, each a 32 x 32 sub-tile = 4 x 4 DMMA accumulators
   const int lr = lane >> 2, lc = lane & 3;
-  double acc[4][8][2];
+  double acc[4][4][2];
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-    for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+    for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
   const int nslices = (int)(kdepth / SKC);
   auto stage = [&](int sl) {  // slice sl -> buffer sl % 3: 2 panels x 128 rows x 32 doubles = 2 x 2048 16-byte copies (nothing past the end)
     if (sl < nslices) {
       double* Pa = smem + (size_t)(sl % SYRK_STAGES) * 2 * SB * SPLD;
       double* Pb = Pa + SB * SPLD;
       const uint32_t kc = (uint32_t)sl * SKC;
-      for (int e = tid; e < SB * SKC / 2; e += 256) {
+      for (int e = tid; e < SB * SKC / 2; e += SYRK_THREADS) {
         const int r = e / (SKC / 2), c2 = (e % (SKC / 2)) * 2;
         cp_async16(Pa + r * SPLD + c2, A + (ri + r) * ld + k0 + kc + c2);
         cp_async16(Pb + r * SPLD + c2, A + (rj + r) * ld + k0 + kc + c2);
@@ -420,21 +421,21 @@ __global__ void __launch_bounds__(256, 1) chol_syrk128_kernel(double* A, size_t 
     const double* Pb = Pa + SB * SPLD;
 #pragma unroll 2
     for (int kk = 0; kk < SKC; kk += 4) {
-      double af[4], bf[8];
+      double af[4], bf[4];
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi) af[mi] = Pa[(wm + mi * 8 + lr) * SPLD + kk + lc];
 #pragma unroll
-      for (int ni = 0; ni < 8; ++ni) bf[ni] = Pb[(wn + ni * 8 + lr) * SPLD + kk + lc];
+      for (int ni = 0; ni < 4; ++ni) bf[ni] = Pb[(wn + ni * 8 + lr) * SPLD + kk + lc];
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        for (int ni = 0; ni < 4; ++ni) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
     }
   }
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-    for (int ni = 0; ni < 8; ++ni) {
+    for (int ni = 0; ni < 4; ++ni) {
       double2* p = reinterpret_cast<double2*>(A + (ri + wm + mi * 8 + lr) * ld + rj + wn + ni * 8 + lc * 2);
       double2 v = *p;
       v.x -= acc[mi][ni][0];
@@ -712,15 +713,15 @@ static apex_status dense_cholesky(Ctx& c, double* L, uint32_t npad) {
           cudaEvent_t Ej = c.chol_events[2 * pj], Rj = c.chol_events[2 * pj + 1];
           APEX_CUDA_TRY(c, cudaEventRecord(Ej, s));
           if (have_rest) APEX_CUDA_TRY(c, cudaStreamWaitEvent(s, last_rest, 0));
-          chol_syrk128_kernel<<<dim3(rem, head), 256, syrk128_smem, s>>>(L, ld, ko, kend - ko, kend, 0);
+          chol_syrk128_kernel<<<dim3(rem, head), SYRK_THREADS, syrk128_smem, s>>>(L, ld, ko, kend - ko, kend, 0);
           APEX_CUDA_TRY(c, cudaStreamWaitEvent(c.stream2, Ej, 0));
-          chol_syrk128_kernel<<<dim3(rem, rem - head), 256, syrk128_smem, c.stream2>>>(L, ld, ko, kend - ko, kend, head);
+          chol_syrk128_kernel<<<dim3(rem, rem - head), SYRK_THREADS, syrk128_smem, c.stream2>>>(L, ld, ko, kend - ko, kend, head);
           APEX_CUDA_TRY(c, cudaEventRecord(Rj, c.stream2));
           last_rest = Rj; have_rest = true;
           c.launches++;
         } else {
           if (have_rest) { APEX_CUDA_TRY(c, cudaStreamWaitEvent(s, last_rest, 0)); have_rest = false; }
-          chol_syrk128_kernel<<<dim3(rem, rem), 256, syrk128_smem, s>>>(L, ld, ko, kend - ko, kend, 0);
+          chol_syrk128_kernel<<<dim3(rem, rem), SYRK_THREADS, syrk128_smem, s>>>(L, ld, ko, kend - ko, kend, 0);
         }
       } else {
         const uint32_t rem = (npad - kend) / NB;
