@@ -211,6 +211,11 @@ struct Ctx {
   std::string err;
   int device = 0, rank = 0, nranks = 1;
   cudaStream_t stream = nullptr;
+  // page-locked bounce ring of the upload (problem.cu): two buffers + the events of their last DMA
+  static constexpr size_t BOUNCE_BYTES = (size_t)16 << 20;
+  void* bounce[2] = {nullptr, nullptr};
+  cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
+  int bounce_next = 0;
   bool chol_attr_set = false;              // dynamic shared-memory limits of the Cholesky kernels set on this context's device
   cudaStream_t stream2 = nullptr;          // low-priority stream of the dense Cholesky's look-ahead (explicit.cu)
   std::vector<cudaEvent_t> chol_events;    // pairs per outer panel: panel factored / rest update done

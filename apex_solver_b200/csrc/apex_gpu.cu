@@ -145,6 +145,13 @@ apex_status apex_ctx_create(const apex_ctx_desc* desc, apex_ctx** out) {
   if (ok && cudaGetDeviceProperties(&prop, c.device) == cudaSuccess) c.num_sms = prop.multiProcessorCount;
   if (!ok) { cudaGetLastError(); delete h; return APEX_ERR_CUDA; }
   std::memset(c.h_state, 0, sizeof(DevState));
+  for (int k = 0; k < 2; ++k) {   // upload bounce ring; without it the upload falls back to plain pageable copies
+    if (cudaHostAlloc(&c.bounce[k], Ctx::BOUNCE_BYTES, cudaHostAllocDefault) != cudaSuccess || cudaEventCreateWithFlags(&c.bounce_ev[k], cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      for (int j = 0; j <= k; ++j) { if (c.bounce[j]) cudaFreeHost(c.bounce[j]); c.bounce[j] = nullptr; }
+      break;
+    }
+  }
   if (c.nranks > 1) {
     NcclApi& api = nccl_api();
     if (!api.ok() || !desc->nccl_unique_id) { delete h; return APEX_ERR_NCCL; }
@@ -187,6 +194,7 @@ void apex_ctx_destroy(apex_ctx* ctx) {
   for (cudaEvent_t e : c.ev_chol) cudaEventDestroy(e);
   if (c.ev_lm0) { cudaEventDestroy(c.ev_lm0); cudaEventDestroy(c.ev_lm1); }
   if (c.h_state) cudaFreeHost(c.h_state);
+  for (int k = 0; k < 2; ++k) { if (c.bounce[k]) cudaFreeHost(c.bounce[k]); if (c.bounce_ev[k]) cudaEventDestroy(c.bounce_ev[k]); }
   for (cudaEvent_t e : c.chol_events) cudaEventDestroy(e);
   if (c.stream2) cudaStreamDestroy(c.stream2);
   if (c.stream) cudaStreamDestroy(c.stream);

@@ -52,6 +52,7 @@ struct SchurArgs {
   const uint32_t* range_win0;
   const uint32_t* win_cams;
   uint32_t window;                 // cameras per window the shared-memory rows were sized for
+  uint32_t nnormal;                // normal chunks (the grid's ranges tile them)
   const uint32_t* win_dst;         // deterministic flush: row of partial[][DC] for every entry of win_cams (camera-major)
   double* partial;
 };
@@ -288,8 +289,7 @@ __global__ void __launch_bounds__(TILE, STAGED ? 2 : 3) schur_chunk_kernel(Schur
   const uint32_t bar = smem_u32(wk + WORK + 8 * DC);                                     // mbarrier of the Jacobian stage
   double* ywin = wk + WORK + 8 * DC + 2;                                                 // [window][DCP], 16-byte aligned rows
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t win_begin = __ldg(a.range_win0 + blockIdx.x), win_end = __ldg(a.range_win0 + blockIdx.x + 1);
-  if (win_begin == win_end) return;
+  const uint32_t win_begin = __ldg(a.range_win0 + blockIdx.x), win_end = __ldg(a.range_win0 + blockIdx.x + 1);   // consumed at the window loop
   // the chunks of a range are contiguous: everything a chunk needs is requested ONE CHUNK AHEAD -
   //   Jacobian planes  STAGED: one cp.async.bulk (TMA) of the chunk's 16*(dc+3)*256 contiguous bytes into the stage, armed on an
   //                    mbarrier; the threads move their 12 x 16 bytes from the stage into registers, and as soon as every
@@ -298,7 +298,9 @@ __global__ void __launch_bounds__(TILE, STAGED ? 2 : 3) schur_chunk_kernel(Schur
   //                    !STAGED: plain 128-bit loads at the top of the chunk's iteration (exposed once per chunk and CTA).
   //   slot metadata, window indices, chunk descriptor: registers, loaded during the previous chunk
   //   landmark inverses / gradients / run tables: cp.async into shared memory once the previous chunk's phase 2 has read its own
-  const uint32_t chunk_first = __ldg(&a.win_desc[win_begin].chunk_begin), chunk_last = __ldg(&a.win_desc[win_end - 1].chunk_end);
+  // (range r = chunks [nn r / P, nn (r+1) / P) like the host built it: no dependent load in front of the first requests)
+  const uint32_t chunk_first = (uint32_t)((uint64_t)a.nnormal * blockIdx.x / gridDim.x), chunk_last = (uint32_t)((uint64_t)a.nnormal * (blockIdx.x + 1) / gridDim.x);
+  if (chunk_first == chunk_last) return;
   auto issue_stage = [&](uint32_t chunk) {
     mbar_expect_tx(bar, JBYTES);
     bulk_g2s(smem_u32(sm), a.J + (size_t)chunk * 2 * NPAIR * TILE, JBYTES, bar);
@@ -1196,7 +1198,7 @@ static SchurArgs make_schur_args(Ctx& c, const double* x, double* y, int check_d
   a.ntiles = c.ntiles;
   a.chunk_desc = c.chunk_desc.p; a.cslot_meta = c.cslot_meta.p; a.cpt_meta = c.cpt_meta.p; a.xpad = c.xpad.p;
   a.cslot_widx = c.cslot_widx.p; a.win_desc = c.win_desc.p; a.range_win0 = c.range_win0.p; a.win_cams = c.win_cams.p;
-  a.window = c.mv_window; a.partial = c.det_partial.p; a.win_dst = c.win_dst.p;
+  a.window = c.mv_window; a.nnormal = c.nnormal_chunks; a.partial = c.det_partial.p; a.win_dst = c.win_dst.p;
   const char* dbg = getenv("APEX_DEBUG_MATVEC");
   a.debug = dbg ? atoi(dbg) : 0;
   return a;
