@@ -395,7 +395,8 @@ def main():
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": b_mv, "launches": int(prof.matvec_launches), "avg_launch_ms": mv_ms,
                     "share_of_step": prof.matvec_ms / prof.lm_device_ms if prof.lm_device_ms else None,
-                    "measured": "second pass of the same K steps with a CUDA-event pair around every launch (PCG batches not graph-replayed)"}
+                    "measured": "second pass of the same K steps with a CUDA-event pair around every launch of the operator kernel (PCG batches not graph-replayed); "
+                                "the second pass of the deterministic flush (the camera windows' partial rows, 2-3 % of the operator's bytes) runs inside the fused PCG tail kernel and is outside the pair"}
 
     if rank == 0:
         cb = None

@@ -12,8 +12,15 @@ ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--variant", type=int, default=F.SCHUR_IMPLICIT)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--pts-frac", type=float, default=1.0, help="keep all cameras, this fraction of the landmarks (what one of 1/frac ranks holds)")
 a = ap.parse_args()
-t = time.time(); prob = synth.make_shape(a.shape, scale=a.scale); tgen = time.time() - t
+t = time.time()
+if a.pts_frac != 1.0:
+    ncam, npts, track, model, loss, cfgi = synth.SHAPES[a.shape]
+    prob = synth.make_problem(ncam, int(npts * a.pts_frac), track, camera_model=model, loss=loss, seed=0xA9E50000 + cfgi)
+else:
+    prob = synth.make_shape(a.shape, scale=a.scale)
+tgen = time.time() - t
 t = time.time(); g = GpuContext().upload(prob); tup = time.time() - t
 dc = prob.dc
 bytes_mv = prob.nobs * (8 * 2 * (dc + 3) + 8) + prob.npts * 48 + prob.ncam * (8 * dc * dc + 16 * dc)
