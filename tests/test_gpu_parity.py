@@ -443,6 +443,29 @@ def test_deterministic_operator_is_bitwise_reproducible(monkeypatch):
     assert relerr(g3.schur_matvec(x), y_det) < 1e-12
 
 
+@pytest.mark.parametrize("flush", ["0", "1"], ids=["reductions", "rows"])
+def test_operator_windows_and_run_chains(flush, monkeypatch):
+    """Corners of the operator kernel's camera-side bookkeeping, with both flushes: (a) three cameras - every camera's run of
+    camera-sorted lanes covers several whole warps of a chunk, so the continuation chains (sums parked per warp and added after the
+    next barrier) are 2-3 warps long; (b) 1 500 cameras without track locality - a range touches far more cameras than a window
+    holds, so every CTA flushes and re-zeroes its window several times; (c) fewer chunks than resident CTAs."""
+    monkeypatch.setenv("APEX_DETERMINISTIC", flush)
+    cases = [small_problem(ncam=3, npts=3000, track=2.6, seed=5),
+             small_problem(ncam=1500, npts=60000, track=5.0, window_frac=0.45, seed=6),
+             small_problem(ncam=40, npts=900, track=4.0, seed=8)]
+    for prob in cases:
+        g, o = pair(prob)
+        g.linearize(1e-3); o.linearize(1e-3)
+        rng = np.random.default_rng(2)
+        for _ in range(2):
+            x = rng.standard_normal(prob.ncam * prob.dc)
+            yg, yo = g.schur_matvec(x), o.schur_matvec(x)
+            assert relerr(yg, yo) < 1e-11, (prob.ncam, relerr(yg, yo))
+        sg = g.solve_augmented(F.SCHUR_IMPLICIT, 1e-3, cg_max_iterations=30, cg_tolerance=1e-6)
+        so = o.solve_augmented(F.SCHUR_IMPLICIT, 1e-3, cg_max_iterations=30, cg_tolerance=1e-6)
+        assert sg[3] == so[3] and relerr(sg[0], so[0]) < 1e-5, "truncated PCG: same iteration count, same step"
+
+
 @pytest.mark.parametrize("tail", ["2", "1", "0"])
 def test_pcg_fused_tail_and_three_kernel_path(tail, monkeypatch):
     """PCG between two operator applications: the fused tail kernel (one warp per camera, software grid barriers, second pass of
