@@ -313,6 +313,7 @@ struct Ctx {
   DevBuf<double> S;                       // dense reduced camera system (explicit variants), n*n row-major
   DevBuf<double> E;                       // [chunk][3*dc][TILE] H_cp blocks for S formation
   DevBuf<double> dvec;                    // dense-solver work vectors
+  DevBuf<long long> tail_trace;           // development probe APEX_TAIL_TRACE (schur.cu)
   DevBuf<double> sh_vec;                  // shared intrinsics: [gradient | step] in the reduced layout [poses 6 each | intrinsics K]
   DevBuf<double> l2flush;                 // > L2 buffer for apex_schur_matvec_bench
   DevBuf<DevState> state;

@@ -184,7 +184,7 @@ void apex_ctx_destroy(apex_ctx* ctx) {
                            &c.dvec, &c.l2flush};
   for (auto* b : dbl) b->release();
   c.giant_tiles.release(); c.xpad.release(); c.chunk_desc.release(); c.cslot_meta.release(); c.cpt_meta.release();
-  c.cslot_widx.release(); c.win_desc.release(); c.range_win0.release(); c.win_cams.release(); c.cam_row_start.release(); c.win_dst.release(); c.pair_blocks.release(); c.pair_slots.release(); c.slot_lpg.release(); c.slot_cs8.release(); c.sh_vec.release(); c.scale_cam.release(); c.scale_pt.release(); c.slot_loss.release(); c.cm_loss.release(); c.loss_tab.release(); c.det_partial.release();
+  c.cslot_widx.release(); c.win_desc.release(); c.range_win0.release(); c.win_cams.release(); c.cam_row_start.release(); c.win_dst.release(); c.pair_blocks.release(); c.pair_slots.release(); c.slot_lpg.release(); c.slot_cs8.release(); c.sh_vec.release(); c.tail_trace.release(); c.scale_cam.release(); c.scale_pt.release(); c.slot_loss.release(); c.cm_loss.release(); c.loss_tab.release(); c.det_partial.release();
   c.tiles.release(); c.slot_cam.release(); c.slot_lp.release(); c.pt_slot0.release(); c.pt_cnt.release(); c.items.release();
   c.cam_item_start.release(); c.cm_lp.release(); c.pose_fixed.release(); c.pt_fixed.release(); c.intr_fixed.release();
   c.state.release(); c.trace.release();

@@ -723,6 +723,20 @@ __device__ __forceinline__ double ld_relaxed_sys(const double* p) {
   asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
+// sum over the ranks of element `off` of their peer-mapped buffers, in rank order (same bits on every rank). The loads of up to
+// eight peers are issued back to back before the first sum: a runtime-bounded "s += load" loop waits for one NVLink round trip
+// (~1.5-2 us) per rank, which was the larger part of the 35 us per PCG iteration the 8-rank solve spent outside its kernels' work.
+__device__ __forceinline__ double peer_sum(double* const* __restrict__ peer_buf, int nranks, size_t off) {
+  double s = 0.0;
+  for (int r0 = 0; r0 < nranks; r0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = r0 + j < nranks ? ld_relaxed_sys(peer_buf[r0 + j] + off) : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];   // (+ 0.0 past the last rank: exact)
+  }
+  return s;
+}
 
 // Fused all-reduce + dot product over NVLink peer memory (comm.cu): publish "my partial operator result of this
 // iteration is complete" to every peer, wait for theirs, y = sum over ranks of their partial vectors (rank order:
@@ -751,7 +765,7 @@ __global__ void __launch_bounds__(PCG_THREADS) ar_reduce_pap_kernel(double* cons
   double v = 0.0;
   if (i < n) {
     double s = 0.0;
-    for (int r = 0; r < nranks; ++r) s += ld_relaxed_sys(peer_buf[r] + (size_t)par * n + i);
+    s = peer_sum(peer_buf, nranks, (size_t)par * n + i);
     y[i] = s;
     v = p[i] * s;
   }
@@ -869,6 +883,7 @@ struct TailArgs {
   DevState* st;
   uint32_t ncam;
   int K, xs, add_hcc;
+  long long* trace;                      // development probe (APEX_TAIL_TRACE): %globaltimer stamps of CTA 0 per iteration, [4096][8]
 };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
@@ -938,6 +953,9 @@ __device__ __forceinline__ void tail_row_sums(const TailArgs& a, uint32_t cam, i
 
 // ONE: every warp owns at most one camera (gridDim.x * 8 >= ncam): its rows of p, r, x, the preconditioner and H_cc blocks are
 // loaded once at entry and stay in registers across the grid barriers, so no stage waits for memory behind a barrier.
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TAIL_STAMP(k) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[(size_t)(iters0 & 4095) * 8 + (k)] = global_ns(); } while (0)
+
 template <int DC, bool ONE>
 __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
   __shared__ double sh[TAIL_THREADS];
@@ -975,6 +993,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
       }
     }
   }
+  TAIL_STAMP(0);
   // ---- stage A: this rank's operator result (second pass of the deterministic flush) ----
   if (a.cam_row_start) {
     if (ONE) {
@@ -999,7 +1018,9 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
   if (multi) {
     // ---- the operator result of all ranks: publish "my partial result is complete", wait for the peers, sum in rank order.
     // (the rows written above are ordered before the flag by the grid barrier's fence + the publishing threads' system fence)
+    TAIL_STAMP(1);
     tail_grid_barrier(st, kbar++);
+    TAIL_STAMP(2);
     if (blockIdx.x == 0 && tid < a.nranks) {
       __threadfence_system();
       st_release_sys(a.peer_flags[tid] + a.rank, seq);
@@ -1011,12 +1032,13 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
       }
     }
     __syncthreads();
+    TAIL_STAMP(3);
   }
   // ---- stage B: y (complete), pAp ----
   double v = 0.0;
   if (ONE) {
     if (act) {
-      if (multi) { yq = 0.0; for (int r = 0; r < a.nranks; ++r) yq += ld_relaxed_sys(a.peer_buf[r] + (size_t)a.par * n + myrow); }
+      if (multi) yq = peer_sum(a.peer_buf, a.nranks, (size_t)a.par * n + myrow);
       v = pq * yq;
     }
   } else {
@@ -1024,7 +1046,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
       if (lane < DC) {
         const size_t row = (size_t)cam * DC + lane;
         double s;
-        if (multi) { s = 0.0; for (int r = 0; r < a.nranks; ++r) s += ld_relaxed_sys(a.peer_buf[r] + (size_t)a.par * n + row); }
+        if (multi) s = peer_sum(a.peer_buf, a.nranks, (size_t)a.par * n + row);
         else s = ymine[row];
         a.y[row] = s;
         v += a.p[row] * s;
@@ -1033,7 +1055,9 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
   }
   v = block_reduce_sum(v, sh);
   if (tid == 0) a.part[blockIdx.x] = v;
+  TAIL_STAMP(4);
   tail_grid_barrier(st, kbar++);
+  TAIL_STAMP(5);
   double pap, unused;
   tail_totals(a.part, nullptr, G, slot, pap, unused);
   if (fabs(pap) < 1e-20 || *reinterpret_cast<volatile int32_t*>(&st->ar_timeout)) {  // break before the update (implicit_schur.rs:626-629); every CTA takes the same branch
@@ -1085,6 +1109,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
   rz = block_reduce_sum(rz, sh);
   if (tid == 0) { a.part[G + blockIdx.x] = rr; a.part[2 * G + blockIdx.x] = rz; }
   tail_grid_barrier(st, kbar++);
+  TAIL_STAMP(6);
   double rr_tot, rz_tot;
   tail_totals(a.part + G, a.part + 2 * G, G, slot, rr_tot, rz_tot);
   const int iters = iters0 + 1;
@@ -1130,6 +1155,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
       }
     }
   }
+  TAIL_STAMP(7);
   // (every CTA passed its entry reads of these scalars before it arrived at the last barrier)
   if (blockIdx.x == 0 && tid == 0) {
     st->pcg_iters = iters;
@@ -1405,6 +1431,7 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
   // launch: the inner loop is launch-bound on small shards (8 GPUs: ~35 us of kernels per iteration).
   const int BATCH = 10;
   int it_count = 0;  // iteration index within this solve: selects the half of the peer buffer (BATCH is even)
+  if (getenv("APEX_TAIL_TRACE") && !c.tail_trace.p) { APEX_CUDA_TRY(c, c.tail_trace.alloc(4096 * 8)); APEX_CUDA_TRY(c, cudaMemsetAsync(c.tail_trace.p, 0, 4096 * 8 * sizeof(long long), s)); }
   bool tail_one = false;
   const int tail_ctas = (c.nranks == 1 || c.p2p_ok) ? pcg_tail_plan(c, tail_one) : 0;
   if (tail_ctas && cg_max_it > 0) {  // first direction p = z and y0 = (H_cc + lambda I) p into half 0; later ones come from the tail
@@ -1439,6 +1466,7 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
       ta.p = c.vp.p; ta.x = c.step_cam.p; ta.r = c.vr.p; ta.z = c.vz.p; ta.xpad = c.xpad.p;
       ta.pinv = c.pinv.p; ta.hcc = c.hcc.p; ta.part = c.red_scratch.p; ta.st = c.state.p;
       ta.ncam = c.ncam; ta.K = c.K; ta.xs = xs; ta.add_hcc = c.rank == 0 ? 1 : 0;
+      ta.trace = c.tail_trace.p;
       APEX_TRY(launch_pcg_tail(c, ta, tail_ctas, tail_one));
       return APEX_OK;
     }
@@ -1500,6 +1528,24 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
   }
   if (cg_max_it <= 0) APEX_TRY(sync_state(c));
   c.last_pcg_iters = c.h_state->pcg_iters;
+  if (c.tail_trace.p && c.last_pcg_iters > 20) {   // development probe: where a PCG iteration's time goes, from CTA 0's stamps
+    std::vector<long long> h(4096 * 8);
+    cudaMemcpy(h.data(), c.tail_trace.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    const int n1 = (int)std::min<int64_t>(c.last_pcg_iters - 1, 4000);
+    double d[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int cnt = 0;
+    for (int i = 10; i < n1; ++i) {
+      const long long* a0 = &h[(size_t)i * 8];
+      const long long* a1 = &h[(size_t)(i + 1) * 8];
+      if (!a0[0] || !a0[7] || !a1[0]) continue;
+      long long prev = a0[0];
+      for (int k = 1; k < 8; ++k) { if (a0[k]) { d[k] += (double)(a0[k] - prev); prev = a0[k]; } }
+      d[8] += (double)(a1[0] - a0[7]);   // end of this tail -> start of the next = operator + launch gaps
+      ++cnt;
+    }
+    if (cnt) fprintf(stderr, "[tail trace rank %d] per iteration (us, %d samples): A %.2f | barA %.2f | peers' flags %.2f | B+reduce %.2f | barB %.2f | C..barC %.2f | D %.2f || operator+gaps %.2f\n", c.rank, cnt,
+                     d[1] / cnt / 1e3, d[2] / cnt / 1e3, d[3] / cnt / 1e3, d[4] / cnt / 1e3, d[5] / cnt / 1e3, d[6] / cnt / 1e3, d[7] / cnt / 1e3, d[8] / cnt / 1e3);
+  }
   if (c.nranks > 1) {  // a timed-out exchange on one rank ends the solve on all of them
     APEX_TRY(agree_error_flags(c));
     APEX_TRY(sync_state(c));
