@@ -123,14 +123,15 @@ struct DevState {
   double rz_old, pcg_tol, b_norm, r_norm;
   double pcg_alpha, pcg_beta;
   uint32_t ticket_a, ticket_b;            // last-block-done counters of the multi-CTA PCG kernels
-  uint32_t tail_bar[4];                   // arrival counters of the fused PCG tail's grid barriers
+  uint32_t pad4[4];
   int32_t pcg_iters, pcg_done, pcg_max, pad1;
   // errors
   unsigned long long ar_seq;              // sequence number of the peer-memory all-reduce (comm.cu)
   int32_t ar_timeout, pad3;               // a peer never published its flag (bounded spin expired)
   int32_t singular_landmark;              // a landmark block could not be inverted
   int32_t chol_fail;                      // first failing column + 1 of the dense Cholesky
-  int32_t pad2[2];
+  uint32_t tail_tag;                      // tag of the fused PCG tail's last sum exchange in this solve (schur.cu, tail_publish / tail_gather)
+  int32_t pad2;
   // multi-rank agreement (agree_error_flags / the LM loop's timeout): every rank must take the same exit
   double agree[2];                        // {singular_landmark, ar_timeout} summed over the ranks
   double elapsed;                         // rank 0's wall clock, all-reduced, for the TIMEOUT test of check_convergence
@@ -246,6 +247,7 @@ struct Ctx {
   uint64_t mv_nrows = 0;           // sum of the windows' camera counts (rows of det_partial)
   bool mv_staged = false;          // operator kernel prefetches the Jacobian planes through a TMA-fed shared-memory stage
   bool mv_defer_reduce = false;    // the caller adds the partial rows itself (fused PCG tail)
+  bool mv_pdl = false;             // launch the operator as a programmatic dependent of the kernel in front of it (PCG loop, schur.cu)
   bool mv_det = false;             // flush the windows as per-window partial rows + fixed-order second pass (bitwise reproducible)
   size_t nslots = 0;
   HostVec<uint64_t> slot_obs;      // slot -> caller's observation index (UINT64_MAX for padding)

@@ -86,6 +86,11 @@ __device__ __forceinline__ void obs_forward(const double* jc, const double* jp, 
 __device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d) {
   asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
+// same through the coherent path (L1-cached): x of the PCG loop is rewritten by the tail kernel while CTAs of the next operator
+// launch may already be resident (programmatic dependent launch), which the read-only contract of ld.global.nc does not allow
+__device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.ca.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
 template <int DC>
 __device__ __forceinline__ void obs_forward_padded(const double* jc, const double* jp, const double* __restrict__ xc, double u[3]) {
   constexpr int N4 = DC / 4, REM = DC % 4;
@@ -229,10 +234,10 @@ __device__ __forceinline__ void gather_x_padded(const double* __restrict__ xc, d
   // one L1 wavefront per distinct 128-byte line and instruction: as few instructions as possible (256-bit loads)
   constexpr int N4 = DC / 4, REM = DC % 4;
 #pragma unroll
-  for (int m = 0; m < N4; ++m) ldg256(xc + 4 * m, xv[4 * m], xv[4 * m + 1], xv[4 * m + 2], xv[4 * m + 3]);
-  if (REM == 1) xv[4 * N4] = __ldg(xc + 4 * N4);
-  else if (REM == 2) { const double2 v = __ldg(reinterpret_cast<const double2*>(xc + 4 * N4)); xv[4 * N4] = v.x; xv[4 * N4 + 1] = v.y; }
-  else if (REM == 3) ldg256(xc + 4 * N4, xv[4 * N4], xv[4 * N4 + 1], xv[4 * N4 + 2], xv[4 * N4 + 3]);
+  for (int m = 0; m < N4; ++m) ld256(xc + 4 * m, xv[4 * m], xv[4 * m + 1], xv[4 * m + 2], xv[4 * m + 3]);
+  if (REM == 1) { asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(xv[4 * N4]) : "l"(xc + 4 * N4)); }
+  else if (REM == 2) { asm volatile("ld.global.ca.v2.f64 {%0, %1}, [%2];" : "=d"(xv[4 * N4]), "=d"(xv[4 * N4 + 1]) : "l"(xc + 4 * N4)); }
+  else if (REM == 3) ld256(xc + 4 * N4, xv[4 * N4], xv[4 * N4 + 1], xv[4 * N4 + 2], xv[4 * N4 + 3]);
 }
 
 // shared memory of the chunk kernel in doubles: [Jacobian stage] work arrays, continuation sums, mbarrier, window rows
@@ -246,6 +251,9 @@ __host__ __device__ constexpr size_t chunk_smem_bytes(uint32_t W) {
   return sizeof(double) * ((size_t)chunk_stage_doubles<DC, STAGED>() + chunk_work_doubles<MODE>() + 8 * DC + 2 + (size_t)W * ywin_stride(DC));
 }
 
+// programmatic dependent launch (see the note in front of pcg_tail_kernel)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -276,7 +284,6 @@ __global__ void __launch_bounds__(TILE, STAGED ? 2 : 3) schur_chunk_kernel(Schur
   constexpr int WORK = chunk_work_doubles<MODE>();
   constexpr int STG = chunk_stage_doubles<DC, STAGED>();
   constexpr uint32_t JBYTES = 16u * NPAIR * TILE;   // one chunk's Jacobian planes, contiguous in HBM
-  if (a.check_done && a.st->pcg_done) return;
   extern __shared__ __align__(128) double sm[];
   double* wk = sm + STG;
   double (*sab)[TILE] = reinterpret_cast<double (*)[TILE]>(wk);                         // [2] a: camera-sorted -> point-major; later b: back
@@ -333,6 +340,15 @@ __global__ void __launch_bounds__(TILE, STAGED ? 2 : 3) schur_chunk_kernel(Schur
   uint2 dsc_n = __ldg(reinterpret_cast<const uint2*>(a.chunk_desc + chunk_first));
   uint32_t nobs_n = __ldg(&a.chunk_desc[chunk_first].nobs);
   issue_landmarks(dsc_n);
+  // Everything above reads structure and linearisation data that no kernel of the PCG loop writes: as a programmatic dependent
+  // (see pcg_tail_kernel) the CTA has done it while the tail in front was still running. x, the done flag and every write follow.
+  pdl_wait();
+  if (a.check_done && __ldcg(&a.st->pcg_done)) {   // (the copies in flight land in this CTA's shared memory: wait for them)
+    if (STAGED) mbar_wait(bar, 0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    return;
+  }
+  pdl_trigger();
   // x of the chunk's cameras, gathered one chunk ahead as well (into the registers the camera half of the previous chunk frees)
   double xv[4 * (DC / 4) + 4];
   // (only with the two-CTA register budget of the staged kernel; at 80 registers the gather stays at its use)
@@ -602,8 +618,10 @@ __device__ __forceinline__ double precond_row(const double* __restrict__ pinv, c
 
 // solve_pcg_block set-up (implicit_schur.rs:577-600): x0 = 0, r = b, z = M^-1 r, p = z
 __global__ void __launch_bounds__(1024) pcg_init_kernel(const double* __restrict__ b, const double* __restrict__ pinv, double* x, double* r,
-                                                        double* z, double* p, DevState* st, uint32_t n, int dc, int K, int max_it, double cg_tol) {
+                                                        double* z, double* p, DevState* st, uint32_t n, int dc, int K, int max_it, double cg_tol,
+                                                        unsigned long long* tail_slots, uint32_t ntail_slots) {
   __shared__ double sh[1024];
+  for (uint32_t i = threadIdx.x; i < ntail_slots; i += 1024) tail_slots[i] = 0;   // exchange slots of the fused tail: tags restart at 1
   double bb = 0.0;
   for (uint32_t i = threadIdx.x; i < n; i += 1024) { const double v = b[i]; r[i] = v; x[i] = 0.0; bb += v * v; }
   __syncthreads();
@@ -622,7 +640,7 @@ __global__ void __launch_bounds__(1024) pcg_init_kernel(const double* __restrict
     st->pcg_done = max_it <= 0 ? 1 : 0;
     st->pcg_alpha = 0.0; st->pcg_beta = 0.0; st->ticket_a = 0; st->ticket_b = 0;
     st->ar_timeout = 0;
-    for (int j = 0; j < 4; ++j) st->tail_bar[j] = 0;
+    st->tail_tag = 0;
   }
 }
 
@@ -866,6 +884,7 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_update_kernel(const double* _
 // Semantics of solve_pcg_block (implicit_schur.rs:604-676) as in pcg_pap / pcg_update / pcg_dir_hcc.
 // ----------------------------------------------------------------------------------------------------
 constexpr int TAIL_THREADS = 256;
+constexpr unsigned TAIL_MAX_CTAS = 592;      // 4 per SM x 148: capacity of the exchange slots (in red_scratch)
 
 struct TailArgs {
   double* const* peer_buf;               // null: single rank
@@ -879,57 +898,103 @@ struct TailArgs {
   double* y0_next;
   double* p; double* x; double* r; double* z; double* xpad;
   const double* pinv; const double* hcc;
-  double* part;                          // [3 * gridDim.x] per-CTA partial dot products
+  unsigned long long* slots;             // [2][TAIL_MAX_CTAS][4] exchange slots of the grid-wide sums, then [TAIL_MAX_CTAS] "rows written" words (zeroed by pcg_init_kernel)
   DevState* st;
   uint32_t ncam;
   int K, xs, add_hcc;
   long long* trace;                      // development probe (APEX_TAIL_TRACE): %globaltimer stamps of CTA 0 per iteration, [4096][8]
 };
 
-__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+// ---- grid-wide sums of the tail: barrier and all-gather in one step ("flag in data") ----
+// A counter barrier followed by a read of the per-CTA partials costs three dependent L2 round trips (arrive, see the count,
+// fetch the partials) plus G atomics on one address. Here a CTA publishes each partial as two 64-bit words {half of the double,
+// 32-bit tag} (a 64-bit store is single-copy atomic, so a word with the right tag carries the right half), and one or two warps of
+// every CTA poll the G slots directly - four per lane in flight - until all carry the tag: one round trip after the last CTA's
+// store, and every CTA adds the partials in the same fixed order (same bits everywhere). Tags count the exchanges of the solve
+// (DevState::tail_tag, zeroed with the slots by pcg_init_kernel); exchange t uses slot set t & 1: a CTA can only be one exchange
+// ahead of the slowest one, because it cannot leave exchange t+1 before every CTA has published there, i.e. has finished reading t.
+__device__ __forceinline__ void tail_publish(unsigned long long* set, unsigned tag, double v0, double v1, bool two) {
+  unsigned long long* q = set + (size_t)blockIdx.x * 4;
+  const unsigned long long b0 = (unsigned long long)__double_as_longlong(v0);
+  const unsigned long long w0 = (b0 & 0xFFFFFFFF00000000ull) | tag, w1 = (b0 << 32) | tag;
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(q), "l"(w0), "l"(w1) : "memory");
+  if (two) {
+    const unsigned long long b1 = (unsigned long long)__double_as_longlong(v1);
+    const unsigned long long w2 = (b1 & 0xFFFFFFFF00000000ull) | tag, w3 = (b1 << 32) | tag;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(q + 2), "l"(w2), "l"(w3) : "memory");
+  }
 }
-// software grid barrier number k of a PCG solve (all CTAs co-resident; k counts on across the launches of the solve). Barrier k
-// uses counter k % 3; once CTA 0 has seen it complete it clears the counter of barrier k-1 (every CTA has arrived here, so none
-// still polls that one), and the counter barrier k+1 will use was cleared at barrier k-1. pcg_init_kernel clears all three.
-__device__ __forceinline__ void tail_grid_barrier(DevState* st, unsigned k) {
+__device__ __forceinline__ void ld_relaxed_gpu_v2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+template <bool TWO>
+__device__ __forceinline__ void tail_gather(const unsigned long long* set, unsigned G, unsigned tag, double* shg /* shared [16], this exchange's own */, double& t0, double& t1) {
+  // Few pollers: the slots are hot lines in L2 and every CTA reads all of them, so the polling traffic itself delays the
+  // exchange (measured: all 256 threads polling one slot each was 0.5-1 us slower per exchange than one warp polling them all).
+  // Warp w < ceil(G / 128) polls slots [128 w, 128 w + 128): four per lane, all in flight at once (G <= 256: one round).
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned npoll = (G + 127u) / 128u;
+  double s = 0.0, q = 0.0;
+  for (unsigned base = warp * 128u; base < G; base += (TAIL_THREADS / 32) * 128u) {
+    unsigned long long w[4][TWO ? 4 : 2];
+    long long spins = 0;
+    bool ok;
+    do {
+      ok = true;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned b = base + 32 * j + lane;
+        if (b < G) {
+          ld_relaxed_gpu_v2(set + (size_t)b * 4, w[j][0], w[j][1]);
+          if (TWO) ld_relaxed_gpu_v2(set + (size_t)b * 4 + 2, w[j][TWO ? 2 : 0], w[j][TWO ? 3 : 1]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (base + 32 * j + lane < G) {
+#pragma unroll
+          for (int m = 0; m < (TWO ? 4 : 2); ++m) ok = ok && (unsigned)w[j][m] == tag;
+        }
+      }
+      if (!ok && ++spins > (1ll << 26)) __trap();   // a CTA that never publishes (not co-resident): an error the host sees, not a hang
+    } while (!ok);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (base + 32 * j + lane < G) {
+        s += __longlong_as_double((long long)((w[j][0] & 0xFFFFFFFF00000000ull) | (w[j][1] >> 32)));
+        if (TWO) q += __longlong_as_double((long long)((w[j][TWO ? 2 : 0] & 0xFFFFFFFF00000000ull) | (w[j][TWO ? 3 : 1] >> 32)));
+      }
+    }
+  }
+  if (warp < npoll && warp < TAIL_THREADS / 32) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, d); if (TWO) q += __shfl_xor_sync(0xffffffffu, q, d); }
+    if (lane == 0) { shg[warp] = s; shg[8 + warp] = q; }
+  }
+  __syncthreads();
+  t0 = shg[0]; t1 = shg[8];
+  for (unsigned w2 = 1; w2 < npoll && w2 < TAIL_THREADS / 32; ++w2) { t0 += shg[w2]; t1 += shg[8 + w2]; }
+}
+// CTA sums of two values in a fixed order: butterfly inside the warps, then the eight warp sums in warp order (thread 0 holds them)
+__device__ __forceinline__ void tail_block_sums(double& a, double& b, double* sh /* [16] */) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sh[warp] = a; sh[8 + warp] = b; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned* ctr = &st->tail_bar[k % 3u];
-    __threadfence();
-    atomicAdd(ctr, 1u);
-    long long spins = 0;
-    while (ld_acquire_gpu_u32(ctr) < gridDim.x) {
-      if (++spins > (1ll << 28)) __trap();   // a CTA that never arrives (not co-resident): an error the host sees, not a hang
-    }
-    if (blockIdx.x == 0) st->tail_bar[(k + 2u) % 3u] = 0;
-  }
-  __syncthreads();
-}
-// sums of part[0..n) and part2[0..n) in a fixed order, same bits in every thread of every CTA: warp 0 strides the arrays,
-// butterfly, broadcast through shared memory
-__device__ __forceinline__ void tail_totals(const double* part, const double* part2, unsigned n, double* slot, double& t0, double& t1) {
-  if (threadIdx.x < 32) {
-    double s = 0.0, q = 0.0;
-    for (unsigned b = threadIdx.x; b < n; b += 32) { s += __ldcg(part + b); if (part2) q += __ldcg(part2 + b); }
+    a = sh[0]; b = sh[8];
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, d); q += __shfl_xor_sync(0xffffffffu, q, d); }
-    if (threadIdx.x == 0) { slot[0] = s; slot[1] = q; }
+    for (int w = 1; w < TAIL_THREADS / 32; ++w) { a += sh[w]; b += sh[8 + w]; }
   }
-  __syncthreads();
-  t0 = slot[0]; t1 = slot[1];
-  __syncthreads();
 }
 
 // second pass of the deterministic flush for one camera: sum of its partial rows, every lane gets all DC sums
 template <int DC, int NF>
-__device__ __forceinline__ void tail_row_sums(const TailArgs& a, uint32_t cam, int lane, double acc[DC]) {
+__device__ __forceinline__ void tail_row_sums(const TailArgs& a, uint32_t e0, uint32_t e1, int lane, double acc[DC]) {   // rows [e0, e1)
 #pragma unroll
   for (int k = 0; k < DC; ++k) acc[k] = 0.0;
-  const uint32_t e1 = __ldg(a.cam_row_start + cam + 1);
-  for (uint32_t e = __ldg(a.cam_row_start + cam) + lane; e < e1; e += 32 * NF) {   // NF rows per lane in flight; added in row order
+  for (uint32_t e = e0 + lane; e < e1; e += 32 * NF) {   // NF rows per lane in flight; added in row order
     double v[NF][DC];
 #pragma unroll
     for (int j = 0; j < NF; ++j) {
@@ -951,34 +1016,47 @@ __device__ __forceinline__ void tail_row_sums(const TailArgs& a, uint32_t cam, i
   }
 }
 
-// ONE: every warp owns at most one camera (gridDim.x * 8 >= ncam): its rows of p, r, x, the preconditioner and H_cc blocks are
-// loaded once at entry and stay in registers across the grid barriers, so no stage waits for memory behind a barrier.
 __device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define TAIL_STAMP(k) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[(size_t)(iters0 & 4095) * 8 + (k)] = global_ns(); } while (0)
 
+// PROGRAMMATIC DEPENDENT LAUNCH. Inside the PCG loop the operator and the tail are launched as programmatic dependents of each
+// other (cudaLaunchAttributeProgrammaticStreamSerialization, also inside the captured graph): a kernel's CTAs are scheduled as
+// soon as every CTA of the kernel in front of it has executed griddepcontrol.launch_dependents (or exited) and SM resources
+// are free, run their prologue - everything that does not depend on the kernel in front - and block in griddepcontrol.wait
+// until that grid has completed and its writes are visible. The launch latency, the CTA ramp and the first memory round trips
+// (operator: descriptors, the first chunk's Jacobian planes by TMA, the landmark inverses; tail: its rows of p, r, x and the
+// preconditioner / H_cc blocks) overlap with the kernel in front. Both kernels trigger only AFTER their own wait, so a kernel is
+// never scheduled before the kernel two in front of it has completed: what the tail reads before its wait (written by the
+// previous tail) is final. Everything a kernel in front may still be writing is read after the wait, and never through the
+// non-coherent path. Launched without the attribute (every use outside the loop) both instructions do nothing.
+
+// ONE: every warp owns at most one camera (gridDim.x * 8 >= ncam): its rows of p, r, x, the preconditioner and H_cc blocks are
+// loaded once at entry and stay in registers across the exchanges, so no stage waits for memory behind one.
 template <int DC, bool ONE>
 __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
-  __shared__ double sh[TAIL_THREADS];
-  __shared__ double slot[2];
+  __shared__ double sh[16];
+  __shared__ double tot_b[16], tot_c[16];
   DevState* st = a.st;
-  if (st->pcg_done) return;  // same value in every CTA: it is only written once every CTA of the launch has passed a grid barrier
+  // (L2 loads: with an early launch this SM's L1 may still hold the lines the previous tail read before it rewrote them)
+  if (__ldcg(&st->pcg_done)) return;  // same value in every CTA: it is only written once every CTA of the launch has left the last exchange
   const int tid = threadIdx.x, lane = tid & 31, K = a.K;
   const uint32_t n = a.ncam * DC;
   const uint32_t gw = blockIdx.x * (TAIL_THREADS / 32) + (tid >> 5), nw = gridDim.x * (TAIL_THREADS / 32);
   const unsigned G = gridDim.x;
-  const double rz_old = st->rz_old, tol = st->pcg_tol, damping = st->damping;
-  const int iters0 = st->pcg_iters, max_it = st->pcg_max;
-  const unsigned long long seq = st->ar_seq + 1;
+  const double rz_old = __ldcg(&st->rz_old), tol = __ldcg(&st->pcg_tol), damping = __ldcg(&st->damping);
+  const int iters0 = __ldcg(&st->pcg_iters), max_it = __ldcg(&st->pcg_max);
+  const unsigned tag0 = __ldcg(&st->tail_tag);
+  const unsigned long long seq = __ldcg(&st->ar_seq) + 1;
   const bool multi = a.peer_buf != nullptr;
-  unsigned kbar = (unsigned)iters0 * (multi ? 3u : 2u);   // this launch's first grid barrier in the solve's numbering
   double* ymine = multi ? a.peer_buf[a.rank] + (size_t)a.par * n : a.ylocal;
   // ONE: this lane's row of everything
   const bool act = ONE && gw < a.ncam && lane < DC;
   const size_t myrow = (size_t)gw * DC + lane;
   double pq = 0.0, rq = 0.0, xq = 0.0, yq = 0.0, Pq[DC > 6 ? (DC - 6 > 6 ? DC - 6 : 6) : 6], Hq[DC];
+  uint32_t row_e0 = 0, row_e1 = 0;   // this camera's partial rows of the deterministic flush (structure: read before the wait)
   if (ONE) {
     if (act) {
-      pq = a.p[myrow]; rq = a.r[myrow]; xq = a.x[myrow]; yq = ymine[myrow];
+      pq = __ldcg(a.p + myrow); rq = __ldcg(a.r + myrow); xq = __ldcg(a.x + myrow);
       const double* P = a.pinv + (size_t)gw * (36 + K * K);
       if (lane < 6) {
 #pragma unroll
@@ -992,14 +1070,18 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
         for (int b = 0; b < DC; ++b) Hq[b] = __ldg(a.hcc + myrow * DC + b);
       }
     }
+    if (a.cam_row_start && gw < a.ncam) { row_e0 = __ldg(a.cam_row_start + gw); row_e1 = __ldg(a.cam_row_start + gw + 1); }
   }
+  pdl_wait();      // the operator in front has completed: partial rows / reductions into y0 are visible
+  pdl_trigger();   // every CTA of this launch is resident: the next operator's CTAs may take free SM resources and run their prologue
+  if (ONE && act) yq = __ldcg(ymine + myrow);
   TAIL_STAMP(0);
   // ---- stage A: this rank's operator result (second pass of the deterministic flush) ----
   if (a.cam_row_start) {
     if (ONE) {
       if (gw < a.ncam) {
         double acc[DC];
-        tail_row_sums<DC, 2>(a, gw, lane, acc);
+        tail_row_sums<DC, 2>(a, row_e0, row_e1, lane, acc);
 #pragma unroll
         for (int k = 0; k < DC; ++k) if (lane == k) yq += acc[k];
         if (multi && act) ymine[myrow] = yq;
@@ -1007,7 +1089,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
     } else {
       for (uint32_t cam = gw; cam < a.ncam; cam += nw) {
         double acc[DC];
-        tail_row_sums<DC, 4>(a, cam, lane, acc);
+        tail_row_sums<DC, 4>(a, __ldg(a.cam_row_start + cam), __ldg(a.cam_row_start + cam + 1), lane, acc);
         double mine = 0.0;
 #pragma unroll
         for (int k = 0; k < DC; ++k) if (lane == k) mine = acc[k];
@@ -1017,25 +1099,45 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
   }
   if (multi) {
     // ---- the operator result of all ranks: publish "my partial result is complete", wait for the peers, sum in rank order.
-    // (the rows written above are ordered before the flag by the grid barrier's fence + the publishing threads' system fence)
     TAIL_STAMP(1);
-    tail_grid_barrier(st, kbar++);
-    TAIL_STAMP(2);
-    if (blockIdx.x == 0 && tid < a.nranks) {
-      __threadfence_system();
-      st_release_sys(a.peer_flags[tid] + a.rank, seq);
+    // No grid barrier: a CTA reads this rank's rows only for its own cameras (which it wrote itself); only the publisher has to
+    // know that every CTA's rows are complete. Every CTA leaves "my rows of exchange `seq` are written" in its word of `adone`
+    // (fence + relaxed store), CTA 0 alone polls the G words - one poller per word, so no polling traffic on hot lines - and then
+    // publishes the rank's flag to the peers behind a system fence.
+    // (Measured alternative, N=2: one flag per CTA at every peer - every rank runs the same camera -> warp map, so CTA b only
+    // needs the rows the peers' CTAs b wrote: 223 system fences + NVLink flag writes per rank and iteration instead of one, 12 us
+    // in the flag wait and CTAs leaving it up to 8 us apart; 38.3 -> 35.9 LM it/s.)
+    unsigned long long* adone = a.slots + 2 * (size_t)TAIL_MAX_CTAS * 4;
+    __syncthreads();
+    if (tid == 0) { __threadfence(); asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(adone + blockIdx.x), "l"(seq) : "memory"); }
+    if (blockIdx.x == 0) {
+      for (unsigned b = tid; b < G; b += TAIL_THREADS) {
+        long long spins = 0;
+        unsigned long long v;
+        do {
+          asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(adone + b) : "memory");
+          if (++spins > (1ll << 26)) __trap();   // a CTA that never arrives (not co-resident): an error the host sees, not a hang
+        } while (v < seq);
+      }
+      __threadfence();
+      __syncthreads();
+      TAIL_STAMP(2);
+      if (tid < a.nranks) {
+        __threadfence_system();
+        st_release_sys(a.peer_flags[tid] + a.rank, seq);
+      }
     }
     if (tid < a.nranks) {
       long long spins = 0;
       while (ld_acquire_sys(a.flags + tid) < seq) {
-        if (++spins > (1ll << 26)) { atomicExch(&st->ar_timeout, 1); break; }  // the sums below are garbage; solve_implicit sees the flag
+        if (++spins > (1ll << 26)) { atomicExch(&st->ar_timeout, 1); __threadfence(); break; }  // the sums below are garbage; solve_implicit sees the flag
       }
     }
     __syncthreads();
     TAIL_STAMP(3);
   }
   // ---- stage B: y (complete), pAp ----
-  double v = 0.0;
+  double v = 0.0, vdummy = 0.0;
   if (ONE) {
     if (act) {
       if (multi) yq = peer_sum(a.peer_buf, a.nranks, (size_t)a.par * n + myrow);
@@ -1047,22 +1149,24 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
         const size_t row = (size_t)cam * DC + lane;
         double s;
         if (multi) s = peer_sum(a.peer_buf, a.nranks, (size_t)a.par * n + row);
-        else s = ymine[row];
+        else s = __ldcg(ymine + row);
         a.y[row] = s;
-        v += a.p[row] * s;
+        v += __ldcg(a.p + row) * s;
       }
     }
   }
-  v = block_reduce_sum(v, sh);
-  if (tid == 0) a.part[blockIdx.x] = v;
+  tail_block_sums(v, vdummy, sh);
+  unsigned long long* set_b = a.slots + (size_t)((tag0 + 1u) & 1u) * TAIL_MAX_CTAS * 4;
+  if (tid == 0) tail_publish(set_b, tag0 + 1u, v, 0.0, false);
   TAIL_STAMP(4);
-  tail_grid_barrier(st, kbar++);
-  TAIL_STAMP(5);
   double pap, unused;
-  tail_totals(a.part, nullptr, G, slot, pap, unused);
-  if (fabs(pap) < 1e-20 || *reinterpret_cast<volatile int32_t*>(&st->ar_timeout)) {  // break before the update (implicit_schur.rs:626-629); every CTA takes the same branch
-    // (every CTA has arrived at the barrier above, i.e. is past its entry reads of the scalars: they may be rewritten now)
-    if (blockIdx.x == 0 && tid == 0) { st->pcg_iters = iters0 + 1; st->pcg_done = 1; if (multi) st->ar_seq = seq; }
+  tail_gather<false>(set_b, G, tag0 + 1u, tot_b, pap, unused);
+  TAIL_STAMP(5);
+  bool timed_out = false;
+  if (multi) { __threadfence(); timed_out = *reinterpret_cast<volatile int32_t*>(&st->ar_timeout) != 0; }   // (set and fenced before the CTA that saw it published)
+  if (fabs(pap) < 1e-20 || timed_out) {  // break before the update (implicit_schur.rs:626-629); every CTA takes the same branch
+    // (every CTA has published above, i.e. is past its entry reads of the scalars: they may be rewritten now)
+    if (blockIdx.x == 0 && tid == 0) { st->pcg_iters = iters0 + 1; st->pcg_done = 1; st->tail_tag = tag0 + 1u; if (multi) st->ar_seq = seq; }
     return;
   }
   const double alpha = rz_old / pap;
@@ -1089,8 +1193,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
       const size_t row = (size_t)cam * DC + lane;
       double rv = 0.0;
       if (lane < DC) {
-        a.x[row] += alpha * a.p[row];
-        rv = a.r[row] - alpha * a.y[row];
+        a.x[row] = __ldcg(a.x + row) + alpha * __ldcg(a.p + row);
+        rv = __ldcg(a.r + row) - alpha * a.y[row];
         a.r[row] = rv;
         rr += rv * rv;
       }
@@ -1105,13 +1209,12 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
       if (lane < DC) { a.z[row] = s; rz += rv * s; }
     }
   }
-  rr = block_reduce_sum(rr, sh);
-  rz = block_reduce_sum(rz, sh);
-  if (tid == 0) { a.part[G + blockIdx.x] = rr; a.part[2 * G + blockIdx.x] = rz; }
-  tail_grid_barrier(st, kbar++);
-  TAIL_STAMP(6);
+  tail_block_sums(rr, rz, sh);   // (thread 0 read the stage-B warp sums before it published: in front of the gather's barrier)
+  unsigned long long* set_c = a.slots + (size_t)((tag0 + 2u) & 1u) * TAIL_MAX_CTAS * 4;
+  if (tid == 0) tail_publish(set_c, tag0 + 2u, rr, rz, true);
   double rr_tot, rz_tot;
-  tail_totals(a.part + G, a.part + 2 * G, G, slot, rr_tot, rz_tot);
+  tail_gather<true>(set_c, G, tag0 + 2u, tot_c, rr_tot, rz_tot);
+  TAIL_STAMP(6);
   const int iters = iters0 + 1;
   const double r_norm = sqrt(rr_tot);
   bool done = r_norm < tol || fabs(rz_old) < 1e-30;
@@ -1140,7 +1243,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
         double pv = 0.0;
         if (lane < DC) {
           const double zv = a.z[row];
-          pv = beta == 0.0 ? zv : zv + beta * a.p[row];
+          pv = beta == 0.0 ? zv : zv + beta * __ldcg(a.p + row);
           a.p[row] = pv;
           a.xpad[(size_t)cam * a.xs + lane] = pv;
         }
@@ -1156,15 +1259,28 @@ __global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
     }
   }
   TAIL_STAMP(7);
-  // (every CTA passed its entry reads of these scalars before it arrived at the last barrier)
+  // (every CTA passed its entry reads of these scalars before it published into the last exchange)
   if (blockIdx.x == 0 && tid == 0) {
     st->pcg_iters = iters;
     st->r_norm = r_norm;
     st->pcg_alpha = alpha;
+    st->tail_tag = tag0 + 2u;
     if (have_beta) { st->pcg_beta = beta; st->rz_old = rz_tot; }
     if (done) st->pcg_done = 1;
     if (multi) st->ar_seq = seq;
   }
+}
+
+// launch with one argument struct, optionally as a programmatic dependent of the kernel in front of it on the stream
+template <typename A>
+static cudaError_t launch_dep(void (*kern)(A), unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool pdl, const A& arg) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, arg);
 }
 
 // CTAs of the fused tail (0 = the separate kernels): one warp per camera when the device can keep that many CTAs resident at
@@ -1175,7 +1291,8 @@ static int tail_plan_dc(Ctx& c, bool& one) {
   const char* e = getenv("APEX_PCG_TAIL");
   const int want = e ? atoi(e) : 2;
   if (want <= 0) return 0;
-  const int per_sm_want = std::min(want, 4);
+  const int per_sm_want = std::min(std::min(want, 4), (int)(TAIL_MAX_CTAS / (unsigned)std::max(c.num_sms, 1)));
+  if (per_sm_want < 1) return 0;
   const uint32_t need = (c.ncam + TAIL_THREADS / 32 - 1) / (TAIL_THREADS / 32);
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_tail_kernel<DC, true>, TAIL_THREADS, 0) == cudaSuccess && occ > 0 &&
@@ -1198,17 +1315,24 @@ static int pcg_tail_plan(Ctx& c, bool& one) {
   }
 }
 
-static apex_status launch_pcg_tail(Ctx& c, const TailArgs& a, int ctas, bool one) {
+template <int DC>
+static cudaError_t launch_tail_dc(Ctx& c, const TailArgs& a, int ctas, bool one, bool pdl) {
+  return one ? launch_dep(pcg_tail_kernel<DC, true>, (unsigned)ctas, TAIL_THREADS, 0, c.stream, pdl, a)
+             : launch_dep(pcg_tail_kernel<DC, false>, (unsigned)ctas, TAIL_THREADS, 0, c.stream, pdl, a);
+}
+static apex_status launch_pcg_tail(Ctx& c, const TailArgs& a, int ctas, bool one, bool pdl) {
+  cudaError_t e;
   switch (c.dc) {
-    case 6: if (one) pcg_tail_kernel<6, true><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); else pcg_tail_kernel<6, false><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
-    case 9: if (one) pcg_tail_kernel<9, true><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); else pcg_tail_kernel<9, false><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
-    case 10: if (one) pcg_tail_kernel<10, true><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); else pcg_tail_kernel<10, false><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
-    case 11: if (one) pcg_tail_kernel<11, true><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); else pcg_tail_kernel<11, false><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
-    case 12: if (one) pcg_tail_kernel<12, true><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); else pcg_tail_kernel<12, false><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
-    case 14: if (one) pcg_tail_kernel<14, true><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); else pcg_tail_kernel<14, false><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
-    case 15: if (one) pcg_tail_kernel<15, true><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); else pcg_tail_kernel<15, false><<<ctas, TAIL_THREADS, 0, c.stream>>>(a); break;
+    case 6: e = launch_tail_dc<6>(c, a, ctas, one, pdl); break;
+    case 9: e = launch_tail_dc<9>(c, a, ctas, one, pdl); break;
+    case 10: e = launch_tail_dc<10>(c, a, ctas, one, pdl); break;
+    case 11: e = launch_tail_dc<11>(c, a, ctas, one, pdl); break;
+    case 12: e = launch_tail_dc<12>(c, a, ctas, one, pdl); break;
+    case 14: e = launch_tail_dc<14>(c, a, ctas, one, pdl); break;
+    case 15: e = launch_tail_dc<15>(c, a, ctas, one, pdl); break;
     default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
   }
+  APEX_CUDA_TRY(c, e);
   c.launches++;
   return APEX_OK;
 }
@@ -1311,13 +1435,13 @@ static apex_status launch_tiles_dc(Ctx& c, int mode, const SchurArgs& a0) {
       case MODE_MATVEC:
         if constexpr (mv_staged_fits<DC>()) {
           if (c.mv_staged) {
-            if (det) schur_chunk_kernel<DC, MODE_MATVEC, true, true><<<grid, TILE, chunk_smem_bytes<DC, MODE_MATVEC, true>(W), c.stream>>>(a);
-            else schur_chunk_kernel<DC, MODE_MATVEC, false, true><<<grid, TILE, chunk_smem_bytes<DC, MODE_MATVEC, true>(W), c.stream>>>(a);
+            if (det) APEX_CUDA_TRY(c, launch_dep(schur_chunk_kernel<DC, MODE_MATVEC, true, true>, grid, TILE, chunk_smem_bytes<DC, MODE_MATVEC, true>(W), c.stream, c.mv_pdl, a));
+            else APEX_CUDA_TRY(c, launch_dep(schur_chunk_kernel<DC, MODE_MATVEC, false, true>, grid, TILE, chunk_smem_bytes<DC, MODE_MATVEC, true>(W), c.stream, c.mv_pdl, a));
             break;
           }
         }
-        if (det) schur_chunk_kernel<DC, MODE_MATVEC, true, false><<<grid, TILE, chunk_smem_bytes<DC, MODE_MATVEC, false>(W), c.stream>>>(a);
-        else schur_chunk_kernel<DC, MODE_MATVEC, false, false><<<grid, TILE, chunk_smem_bytes<DC, MODE_MATVEC, false>(W), c.stream>>>(a);
+        if (det) APEX_CUDA_TRY(c, launch_dep(schur_chunk_kernel<DC, MODE_MATVEC, true, false>, grid, TILE, chunk_smem_bytes<DC, MODE_MATVEC, false>(W), c.stream, c.mv_pdl, a));
+        else APEX_CUDA_TRY(c, launch_dep(schur_chunk_kernel<DC, MODE_MATVEC, false, false>, grid, TILE, chunk_smem_bytes<DC, MODE_MATVEC, false>(W), c.stream, c.mv_pdl, a));
         break;
       case MODE_RHS:
         if (det) schur_chunk_kernel<DC, MODE_RHS, true, false><<<grid, TILE, chunk_smem_bytes<DC, MODE_RHS, false>(W), c.stream>>>(a);
@@ -1422,7 +1546,9 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
   cudaStream_t s = c.stream;
   APEX_TRY(launch_reduced_gradient(c, c.vb.p));
   APEX_TRY(launch_schur_jacobi_blocks(c, precond));
-  pcg_init_kernel<<<1, 1024, 0, s>>>(c.vb.p, c.pinv.p, c.step_cam.p, c.vr.p, c.vz.p, c.vp.p, c.state.p, n, c.dc, c.K, cg_max_it, cg_tol);
+  static_assert(sizeof(unsigned long long) == sizeof(double), "exchange slots live in red_scratch");
+  pcg_init_kernel<<<1, 1024, 0, s>>>(c.vb.p, c.pinv.p, c.step_cam.p, c.vr.p, c.vz.p, c.vp.p, c.state.p, n, c.dc, c.K, cg_max_it, cg_tol,
+                                     reinterpret_cast<unsigned long long*>(c.red_scratch.p), 9u * TAIL_MAX_CTAS);   // (red_scratch holds >= 8 256 words)
   c.launches++;
   APEX_CUDA_TRY(c, cudaGetLastError());
   // PCG: iterations are enqueued in batches of BATCH; every kernel of an iteration is a no-op once the device-side
@@ -1434,6 +1560,9 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
   if (getenv("APEX_TAIL_TRACE") && !c.tail_trace.p) { APEX_CUDA_TRY(c, c.tail_trace.alloc(4096 * 8)); APEX_CUDA_TRY(c, cudaMemsetAsync(c.tail_trace.p, 0, 4096 * 8 * sizeof(long long), s)); }
   bool tail_one = false;
   const int tail_ctas = (c.nranks == 1 || c.p2p_ok) ? pcg_tail_plan(c, tail_one) : 0;
+  // operator and tail as programmatic dependents of each other (note in front of pcg_tail_kernel); APEX_PDL=0: plain stream order
+  const char* pdl_env = getenv("APEX_PDL");
+  const bool pdl = tail_ctas > 0 && !(pdl_env && atoi(pdl_env) == 0);
   if (tail_ctas && cg_max_it > 0) {  // first direction p = z and y0 = (H_cc + lambda I) p into half 0; later ones come from the tail
     const int xs = xpad_stride(c.dc);
     double* y0 = c.p2p_ok ? c.arbuf.p : c.vy.p;
@@ -1452,8 +1581,10 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
       cudaEvent_t* evp = (c.prof && c.ntiles) ? prof_pair(c.ev_pool, c.ev_mv_used++) : nullptr;
       if (evp) cudaEventRecord(evp[0], s);
       c.mv_defer_reduce = true;
+      c.mv_pdl = pdl;
       apex_status ost = launch_schur_tiles(c, MODE_MATVEC, c.vp.p, y0, 1, true);
       c.mv_defer_reduce = false;
+      c.mv_pdl = false;
       APEX_TRY(ost);
       if (evp) cudaEventRecord(evp[1], s);
       TailArgs ta{};
@@ -1464,10 +1595,10 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
       ta.y = c.vy.p;
       ta.y0_next = c.p2p_ok ? c.arbuf.p + (size_t)(par ^ 1) * n : c.vy.p;
       ta.p = c.vp.p; ta.x = c.step_cam.p; ta.r = c.vr.p; ta.z = c.vz.p; ta.xpad = c.xpad.p;
-      ta.pinv = c.pinv.p; ta.hcc = c.hcc.p; ta.part = c.red_scratch.p; ta.st = c.state.p;
+      ta.pinv = c.pinv.p; ta.hcc = c.hcc.p; ta.slots = reinterpret_cast<unsigned long long*>(c.red_scratch.p); ta.st = c.state.p;
       ta.ncam = c.ncam; ta.K = c.K; ta.xs = xs; ta.add_hcc = c.rank == 0 ? 1 : 0;
       ta.trace = c.tail_trace.p;
-      APEX_TRY(launch_pcg_tail(c, ta, tail_ctas, tail_one));
+      APEX_TRY(launch_pcg_tail(c, ta, tail_ctas, tail_one, pdl));
       return APEX_OK;
     }
     {
@@ -1543,7 +1674,7 @@ apex_status solve_implicit(Ctx& c, int precond, int cg_max_it, double cg_tol) {
       d[8] += (double)(a1[0] - a0[7]);   // end of this tail -> start of the next = operator + launch gaps
       ++cnt;
     }
-    if (cnt) fprintf(stderr, "[tail trace rank %d] per iteration (us, %d samples): A %.2f | barA %.2f | peers' flags %.2f | B+reduce %.2f | barB %.2f | C..barC %.2f | D %.2f || operator+gaps %.2f\n", c.rank, cnt,
+    if (cnt) fprintf(stderr, "[tail trace rank %d] per iteration (us, %d samples): A %.2f | (barrier A %.2f) | peers' flags %.2f | B + publish %.2f | gather B %.2f | C + gather C %.2f | D %.2f || end of tail -> next tail past its wait (operator + gaps) %.2f\n", c.rank, cnt,
                      d[1] / cnt / 1e3, d[2] / cnt / 1e3, d[3] / cnt / 1e3, d[4] / cnt / 1e3, d[5] / cnt / 1e3, d[6] / cnt / 1e3, d[7] / cnt / 1e3, d[8] / cnt / 1e3);
   }
   if (c.nranks > 1) {  // a timed-out exchange on one rank ends the solve on all of them
