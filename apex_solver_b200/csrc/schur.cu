@@ -883,7 +883,8 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_update_kernel(const double* _
 // the rank-ordered peer sum, on every rank). Two launches per PCG iteration (operator + tail).
 // Semantics of solve_pcg_block (implicit_schur.rs:604-676) as in pcg_pap / pcg_update / pcg_dir_hcc.
 // ----------------------------------------------------------------------------------------------------
-constexpr int TAIL_THREADS = 256;
+constexpr int TAIL_THREADS = 512;           // 16 warps = 16 cameras per CTA, one CTA per SM: the G x G polling traffic of the exchanges is a quarter of what 256-thread CTAs cost
+constexpr int TAIL_WARPS = TAIL_THREADS / 32;
 constexpr unsigned TAIL_MAX_CTAS = 592;      // 4 per SM x 148: capacity of the exchange slots (in red_scratch)
 
 struct TailArgs {
@@ -928,7 +929,7 @@ __device__ __forceinline__ void ld_relaxed_gpu_v2(const unsigned long long* p, u
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 template <bool TWO>
-__device__ __forceinline__ void tail_gather(const unsigned long long* set, unsigned G, unsigned tag, double* shg /* shared [16], this exchange's own */, double& t0, double& t1) {
+__device__ __forceinline__ void tail_gather(const unsigned long long* set, unsigned G, unsigned tag, double* shg /* shared [2 * TAIL_WARPS], this exchange's own */, double& t0, double& t1) {
   // Few pollers: the slots are hot lines in L2 and every CTA reads all of them, so the polling traffic itself delays the
   // exchange (measured: all 256 threads polling one slot each was 0.5-1 us slower per exchange than one warp polling them all).
   // Warp w < ceil(G / 128) polls slots [128 w, 128 w + 128): four per lane, all in flight at once (G <= 256: one round).
@@ -969,23 +970,23 @@ __device__ __forceinline__ void tail_gather(const unsigned long long* set, unsig
   if (warp < npoll && warp < TAIL_THREADS / 32) {
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, d); if (TWO) q += __shfl_xor_sync(0xffffffffu, q, d); }
-    if (lane == 0) { shg[warp] = s; shg[8 + warp] = q; }
+    if (lane == 0) { shg[warp] = s; shg[TAIL_WARPS + warp] = q; }
   }
   __syncthreads();
-  t0 = shg[0]; t1 = shg[8];
-  for (unsigned w2 = 1; w2 < npoll && w2 < TAIL_THREADS / 32; ++w2) { t0 += shg[w2]; t1 += shg[8 + w2]; }
+  t0 = shg[0]; t1 = shg[TAIL_WARPS];
+  for (unsigned w2 = 1; w2 < npoll && w2 < TAIL_WARPS; ++w2) { t0 += shg[w2]; t1 += shg[TAIL_WARPS + w2]; }
 }
-// CTA sums of two values in a fixed order: butterfly inside the warps, then the eight warp sums in warp order (thread 0 holds them)
-__device__ __forceinline__ void tail_block_sums(double& a, double& b, double* sh /* [16] */) {
+// CTA sums of two values in a fixed order: butterfly inside the warps, then the warp sums in warp order (thread 0 holds them)
+__device__ __forceinline__ void tail_block_sums(double& a, double& b, double* sh /* [2 * TAIL_WARPS] */) {
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { sh[warp] = a; sh[8 + warp] = b; }
+  if (lane == 0) { sh[warp] = a; sh[TAIL_WARPS + warp] = b; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    a = sh[0]; b = sh[8];
+    a = sh[0]; b = sh[TAIL_WARPS];
 #pragma unroll
-    for (int w = 1; w < TAIL_THREADS / 32; ++w) { a += sh[w]; b += sh[8 + w]; }
+    for (int w = 1; w < TAIL_WARPS; ++w) { a += sh[w]; b += sh[TAIL_WARPS + w]; }
   }
 }
 
@@ -1033,9 +1034,9 @@ __device__ __forceinline__ long long global_ns() { long long t; asm volatile("mo
 // ONE: every warp owns at most one camera (gridDim.x * 8 >= ncam): its rows of p, r, x, the preconditioner and H_cc blocks are
 // loaded once at entry and stay in registers across the exchanges, so no stage waits for memory behind one.
 template <int DC, bool ONE>
-__global__ void __launch_bounds__(TAIL_THREADS, 2) pcg_tail_kernel(TailArgs a) {
-  __shared__ double sh[16];
-  __shared__ double tot_b[16], tot_c[16];
+__global__ void __launch_bounds__(TAIL_THREADS, 1) pcg_tail_kernel(TailArgs a) {
+  __shared__ double sh[2 * TAIL_WARPS];
+  __shared__ double tot_b[2 * TAIL_WARPS], tot_c[2 * TAIL_WARPS];
   DevState* st = a.st;
   // (L2 loads: with an early launch this SM's L1 may still hold the lines the previous tail read before it rewrote them)
   if (__ldcg(&st->pcg_done)) return;  // same value in every CTA: it is only written once every CTA of the launch has left the last exchange
