@@ -154,6 +154,19 @@ class Dims(C.Structure):
                 ("nobs_local", C.c_uint64)]
 
 
+class ObserverMetrics(C.Structure):
+    _fields_ = [("iteration", C.c_int32), ("accepted", C.c_int32), ("cost", C.c_double), ("gradient_norm", C.c_double),
+                ("damping", C.c_double), ("step_norm", C.c_double), ("step_quality", C.c_double)]
+
+
+ON_STEP = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.POINTER(ObserverMetrics))
+ON_COMPLETE = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int32)
+
+
+class Observer(C.Structure):
+    _fields_ = [("on_step", ON_STEP), ("on_optimization_complete", ON_COMPLETE), ("user", C.c_void_p)]
+
+
 # Every symbol include/apex_gpu.h declares (without prefix): name -> (restype, argtypes)
 P = C.POINTER
 _DBL = C.c_void_p  # double* passed as raw addresses of numpy buffers
@@ -180,6 +193,8 @@ SYMBOLS = {
                                     P(C.c_double), P(C.c_int32)]),
     "get_step": (C.c_int32, [C.c_void_p, _DBL, _DBL]),
     "lm_solve": (C.c_int32, [C.c_void_p, P(LmConfig), P(LmResult), P(IterTrace), C.c_int32]),
+    "add_observer": (C.c_int32, [C.c_void_p, P(Observer)]),
+    "clear_observers": (C.c_int32, [C.c_void_p]),
     "kernel_launches": (C.c_int64, [C.c_void_p]),
     "profile_enable": (C.c_int32, [C.c_void_p, C.c_int32]),
     "profile_read": (C.c_int32, [C.c_void_p, P(Profile)]),

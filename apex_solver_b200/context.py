@@ -217,6 +217,22 @@ class Context:
         n = min(res.iterations, trace_cap)
         return res, [tr[i] for i in range(n)]
 
+    def add_observer(self, on_step=None, on_optimization_complete=None):
+        """OptObserver (src/observers/mod.rs:201-330): `on_step(ctx, metrics)` once per LM iteration with the tuple the reference's
+        notify_observers_generic passes (metrics: F.ObserverMetrics, valid during the call only; ctx: this context, whose
+        params_download may be called from inside), `on_optimization_complete(ctx, iterations)` once when a solve ends."""
+        step_cb = F.ON_STEP((lambda user, h, m: on_step(self, m.contents)) if on_step else 0)
+        done_cb = F.ON_COMPLETE((lambda user, h, n: on_optimization_complete(self, n)) if on_optimization_complete else 0)
+        obs = F.Observer(step_cb, done_cb, None)
+        self._observers = getattr(self, "_observers", []) + [(step_cb, done_cb)]   # keep the thunks alive while they are registered
+        self._check(self._fn("add_observer")(self._h, C.byref(obs)))
+        return self
+
+    def clear_observers(self):
+        self._check(self._fn("clear_observers")(self._h))
+        self._observers = []
+        return self
+
     def kernel_launches(self) -> int:
         return int(self._fn("kernel_launches")(self._h))
 

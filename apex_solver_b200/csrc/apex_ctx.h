@@ -325,6 +325,10 @@ struct Ctx {
   void* pcg_graph_exec = nullptr;       // cudaGraphExec_t of one batch of PCG iterations (rebuilt after every upload)
   int64_t pcg_graph_launches = 0;       // kernel launches one replay stands for
 
+  // ---- observers (apex_add_observer): fed by lm_solve once per iteration ----
+  std::vector<apex_observer> observers;
+  apex_ctx* self = nullptr;                      // the handle the callbacks receive
+
   // ---- NVLink peer-memory all-reduce of the operator result (comm.cu) ----
   bool p2p_ok = false;
   size_t ar_n = 0;

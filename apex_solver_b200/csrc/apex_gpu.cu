@@ -166,6 +166,7 @@ apex_status apex_ctx_create(const apex_ctx_desc* desc, apex_ctx** out) {
     // problem with more re-maps them at upload).
     if (setup_peer_allreduce(c, AR_CAPACITY) != APEX_OK) { cudaGetLastError(); c.p2p_ok = false; }
   }
+  c.self = h;
   *out = h;
   return APEX_OK;
 }
@@ -429,6 +430,18 @@ apex_status apex_lm_solve(apex_ctx* ctx, const apex_lm_config* cfg, apex_lm_resu
   CTX_OR_FAIL(ctx);
   if (!cfg || !result) { c.err = "null config/result"; return APEX_ERR_INVALID_INPUT; }
   return lm_solve(c, cfg, result, trace, trace_cap);
+}
+
+apex_status apex_add_observer(apex_ctx* ctx, const apex_observer* observer) {
+  CTX_OR_FAIL(ctx);
+  if (!observer) { c.err = "null observer"; return APEX_ERR_INVALID_INPUT; }
+  c.observers.push_back(*observer);
+  return APEX_OK;
+}
+apex_status apex_clear_observers(apex_ctx* ctx) {
+  CTX_OR_FAIL(ctx);
+  c.observers.clear();
+  return APEX_OK;
 }
 
 int64_t apex_kernel_launches(const apex_ctx* ctx) { return ctx ? ctx->c.launches : 0; }

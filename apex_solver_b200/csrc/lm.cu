@@ -352,6 +352,15 @@ apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, ape
     c.linearized = false;  // the variables moved (or lambda changed): the cached linearization is stale
     iter_ms.push_back((now_seconds() - it0) * 1e3);
     if (c.h_state->accepted) ok_steps++; else bad_steps++;
+    if (!c.observers.empty()) {
+      // notify_observers_generic (src/optimizer/mod.rs:728-743; levenberg_marquardt.rs:930-940): the metric tuple of the iteration
+      // just finished, after the accept / reject decision. The stream is idle here (sync_state), so a callback may read the
+      // variables with apex_params_download.
+      apex_observer_metrics m;
+      m.iteration = iteration; m.accepted = c.h_state->accepted; m.cost = c.h_state->current_cost; m.gradient_norm = c.h_state->grad_norm;
+      m.damping = c.h_state->damping; m.step_norm = c.h_state->step_norm; m.step_quality = c.h_state->rho;
+      for (size_t i = 0; i < c.observers.size(); ++i) { const apex_observer o = c.observers[i]; if (o.on_step) o.on_step(o.user, c.self, &m); }
+    }
     if (c.h_state->status >= 0) {
       cudaEventRecord(c.ev_lm1, s);
       c.lm_timed = true;
@@ -375,6 +384,8 @@ apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, ape
         APEX_CUDA_TRY(c, cudaStreamSynchronize(s));
         for (int i = 0; i < nrow; ++i) trace[i].iter_time_ms = iter_ms[i];
       }
+      // notify_complete(&final_parameters, iteration + 1) (levenberg_marquardt.rs:1010-1011)
+      for (size_t i = 0; i < c.observers.size(); ++i) { const apex_observer o = c.observers[i]; if (o.on_optimization_complete) o.on_optimization_complete(o.user, c.self, iteration + 1); }
       return APEX_OK;
     }
   }

@@ -350,6 +350,33 @@ apex_status apex_get_step(apex_ctx* ctx, double* step_cam, double* step_pt);
 apex_status apex_lm_solve(apex_ctx* ctx, const apex_lm_config* cfg, apex_lm_result* result,
                           apex_iter_trace* trace, int32_t trace_cap);
 
+/* Observers: the reference's OptObserver (src/observers/mod.rs:201-330). The LM loop feeds them once per iteration, after the
+ * accept / reject decision and before the convergence test, exactly like notify_observers_generic (src/optimizer/mod.rs:728-743,
+ * called at levenberg_marquardt.rs:930-940): set_iteration_metrics(cost, gradient_norm, Some(damping), step_norm, Some(rho)) and
+ * on_step(values, iteration) arrive here as ONE call of `on_step` with the metric tuple; the variable values of that moment are not
+ * pushed (they live on the device) - an observer that wants them calls apex_params_download from inside the callback (the loop
+ * is at a synchronisation point; on a sharded context that call is collective, so either every rank's observer downloads or
+ * none). set_matrix_data is not fed on this path (the reference's generic path skips it as well, mod.rs:740-741).
+ * `on_optimization_complete` is called once when the loop ends with a status, with iterations = the SolverResult's
+ * (notify_complete, levenberg_marquardt.rs:1010-1011); not on an error return. Either pointer may be NULL. Observers stay
+ * registered across solves and uploads until apex_clear_observers; callbacks run on the calling thread. */
+typedef struct apex_observer_metrics {
+  int32_t iteration;      /* index of the iteration just finished (0-based): the `iteration` of on_step */
+  int32_t accepted;       /* step_eval.accepted */
+  double cost;            /* state.current_cost after the decision */
+  double gradient_norm;   /* step_result.gradient_norm */
+  double damping;         /* Some(config.damping), already updated by update_damping */
+  double step_norm;
+  double step_quality;    /* Some(step_eval.rho) */
+} apex_observer_metrics;
+typedef struct apex_observer {
+  void (*on_step)(void* user, apex_ctx* ctx, const apex_observer_metrics* metrics);
+  void (*on_optimization_complete)(void* user, apex_ctx* ctx, int32_t iterations);
+  void* user;
+} apex_observer;
+apex_status apex_add_observer(apex_ctx* ctx, const apex_observer* observer);
+apex_status apex_clear_observers(apex_ctx* ctx);
+
 /* Number of kernel launches issued by this context since creation (bench bookkeeping). */
 int64_t apex_kernel_launches(const apex_ctx* ctx);
 

@@ -1214,6 +1214,7 @@ void lm_config_default(apex_lm_config* c) {  // levenberg_marquardt.rs:319-359
 // ------------------------------------------------------------------------------------------------
 struct Ctx {
   std::string err;
+  std::vector<apex_observer> observers; void* self = nullptr;   // oracle_add_observer; the handle the callbacks receive
   // problem
   int model = 0, K = 0; uint32_t opt = 0; bool intr_vars = false;
   uint32_t ncam = 0, npts = 0; uint64_t nobs = 0;
@@ -1918,6 +1919,12 @@ apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, ape
       t.predicted_reduction = predicted; t.parameter_norm = pnorm; t.iter_time_ms = (now_seconds() - it0) * 1e3;
     }
     previous_cost = current_cost;
+    {  // notify_observers_generic (src/optimizer/mod.rs:728-743; levenberg_marquardt.rs:930-940)
+      apex_observer_metrics m;
+      m.iteration = iteration; m.accepted = accepted; m.cost = current_cost; m.gradient_norm = step.grad_norm; m.damping = damping;
+      m.step_norm = step.step_norm; m.step_quality = rho;
+      for (size_t i = 0; i < c.observers.size(); ++i) { const apex_observer o = c.observers[i]; if (o.on_step) o.on_step(o.user, reinterpret_cast<apex_ctx*>(c.self), &m); }
+    }
     double cost_before = accepted ? current_cost + cost_reduction : current_cost;  // :946-950
     ConvergenceParams cp{iteration, cost_before, current_cost, pnorm, step.step_norm, step.grad_norm, elapsed, accepted,
                          cfg->max_iterations, cfg->gradient_tolerance, cfg->parameter_tolerance, cfg->cost_tolerance,
@@ -1929,6 +1936,8 @@ apex_status lm_solve(Ctx& c, const apex_lm_config* cfg, apex_lm_result* res, ape
       res->cost_evaluations = cost_evals; res->jacobian_evaluations = jac_evals; res->successful_steps = ok_steps;
       res->unsuccessful_steps = bad_steps; res->final_damping = damping; res->final_damping_nu = nu; res->linear_iterations = lin_iters;
       if (c.scaling_on) { c.scaling_on = false; c.linearized = false; }  // the cached linearization holds scaled blocks
+      // notify_complete(&final_parameters, iteration + 1) (levenberg_marquardt.rs:1010-1011)
+      for (size_t i = 0; i < c.observers.size(); ++i) { const apex_observer o = c.observers[i]; if (o.on_optimization_complete) o.on_optimization_complete(o.user, reinterpret_cast<apex_ctx*>(c.self), iteration + 1); }
       return APEX_OK;
     }
     iteration++;
@@ -1969,7 +1978,9 @@ void oracle_lm_config_for_bundle_adjustment(apex_lm_config* cfg) {  // levenberg
   cfg->damping = 1e-3; cfg->max_iterations = 20; cfg->cost_tolerance = 1e-6; cfg->parameter_tolerance = 1e-8; cfg->gradient_tolerance = 1e-10;
 }
 
-apex_status oracle_ctx_create(const apex_ctx_desc*, oracle_ctx** out) { *out = new oracle_ctx(); return APEX_OK; }
+apex_status oracle_ctx_create(const apex_ctx_desc*, oracle_ctx** out) { *out = new oracle_ctx(); (*out)->c.self = *out; return APEX_OK; }
+apex_status oracle_add_observer(oracle_ctx* ctx, const apex_observer* observer) { if (!observer) return APEX_ERR_INVALID_INPUT; ctx->c.observers.push_back(*observer); return APEX_OK; }
+apex_status oracle_clear_observers(oracle_ctx* ctx) { ctx->c.observers.clear(); return APEX_OK; }
 void oracle_ctx_destroy(oracle_ctx* ctx) { delete ctx; }
 const char* oracle_last_error(const oracle_ctx* ctx) { return ctx->c.err.c_str(); }
 

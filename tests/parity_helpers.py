@@ -164,3 +164,44 @@ def teacher_forced_parity(prob, variant, dut, oracle, scratch, lib, twin=None, n
             log(row)
         lam, nu = rb.final_damping, rb.final_damping_nu
     return report
+
+
+def check_observer_feed(ctx_factory, prob, variant=F.SCHUR_EXPLICIT, max_it=6):
+    """The observer contract of the LM loop (OptObserver, src/observers/mod.rs:201-330; fed at levenberg_marquardt.rs:930-940 and
+    :1010-1011), shared by the oracle test here and the GPU test: one on_step per iteration carrying the tuple of
+    notify_observers_generic - which is what the IterationStats row of that iteration holds (cost, gradient norm, tr_radius = damping,
+    step norm, tr_ratio = rho) -, iterations numbered from 0, the variables readable from inside the callback, exactly one
+    on_optimization_complete with SolverResult::iterations (levenberg_marquardt.rs:1642-1682), observers kept across solves until
+    cleared, several observers fed in registration order."""
+    ctx = ctx_factory().upload(prob)
+    steps, done, order, params_seen = [], [], [], []
+
+    def on_step(c, m):
+        steps.append((m.iteration, m.accepted, m.cost, m.gradient_norm, m.damping, m.step_norm, m.step_quality))
+        params_seen.append([a.copy() for a in c.params_download()])
+        order.append("a")
+
+    ctx.add_observer(on_step, lambda c, n: done.append(n))
+    ctx.add_observer(lambda c, m: order.append("b"))          # a second observer without a completion hook
+    cfg = ctx.default_config(True)
+    cfg.schur_variant = variant
+    cfg.max_iterations = max_it
+    res, trace = ctx.lm_solve(cfg)
+    assert done == [res.iterations], "on_optimization_complete exactly once, with the result's iteration count"
+    assert [s[0] for s in steps] == list(range(res.iterations))
+    assert order == ["a", "b"] * res.iterations
+    for s, t in zip(steps, trace):
+        assert (s[1], s[2], s[3], s[4], s[5], s[6]) == (t.accepted, t.cost, t.gradient_norm, t.tr_radius, t.step_norm, t.tr_ratio)
+    final = ctx.params_download()
+    for a, b in zip(params_seen[-1], final):
+        assert np.array_equal(a, b), "the values an observer reads at the last step are the result's"
+    if steps[0][1]:   # the first step was accepted: the observer already sees the moved variables (on_step comes after the update)
+        assert any(not np.array_equal(a, b) for a, b in zip(params_seen[0], (prob.pose, prob.intr, prob.pt)))
+    ctx.upload(prob)                                         # observers survive a new upload and a second solve ...
+    ctx.lm_solve(cfg)
+    assert len(done) == 2 and len(steps) == 2 * res.iterations
+    ctx.clear_observers()                                    # ... until they are cleared
+    ctx.upload(prob)
+    ctx.lm_solve(cfg)
+    assert len(done) == 2 and len(steps) == 2 * res.iterations
+    return steps[: res.iterations], res

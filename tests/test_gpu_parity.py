@@ -486,6 +486,20 @@ def test_pcg_fused_tail_and_three_kernel_path(tail, monkeypatch):
     assert (rg.status, rg.iterations, [t.accepted for t in tg]) == (ro.status, ro.iterations, [t.accepted for t in to])
 
 
+def test_observer_feed():
+    """f4: the observer feed of the LM loop (levenberg_marquardt.rs:930-940, :1010-1011) through the C ABI's callbacks, same contract as
+    the oracle's (parity_helpers.check_observer_feed); the first iteration's tuple against the oracle's at the LM tolerances."""
+    from parity_helpers import check_observer_feed, rel
+    prob = small_problem(ncam=10, npts=300, seed=11)
+    for variant in (F.SCHUR_EXPLICIT, F.SCHUR_IMPLICIT):
+        sg, rg = check_observer_feed(GpuContext, prob, variant)
+        so, ro = check_observer_feed(OracleContext, prob, variant)
+        assert (rg.status, rg.iterations) == (ro.status, ro.iterations)
+        assert [s[1] for s in sg] == [s[1] for s in so], "accept pattern"
+        g0, o0 = sg[0], so[0]
+        assert rel(g0[2], o0[2]) < 1e-7 and rel(g0[3], o0[3]) < 1e-11 and g0[4] == pytest.approx(o0[4], rel=1e-4) and rel(g0[5], o0[5]) < 1e-5
+
+
 def test_bal_file_to_gpu_solve(tmp_path):
     """Data format either side of the path: generator -> BAL text -> apex_bal_load -> apex_bal_build_problem (the CLI's
     construction, bin/bundle_adjustment.rs:212-441) -> GPU LM, against the oracle on the same loaded problem; and the

@@ -15,6 +15,7 @@ import pytest
 from apex_solver_b200 import _ffi as F, synth
 from apex_solver_b200.context import BAProblem, GpuContext, layout_stats, shard_info
 from oracle_backend import OracleContext, oracle_lib
+from parity_helpers import check_observer_feed
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HAVE_GPU = F.load_library().apex_device_count() > 0
@@ -35,15 +36,16 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_the_header(tmp_path):
     """ctypes mirrors vs the C compiler's view of include/apex_gpu.h (sizes and a few offsets)."""
     src = tmp_path / "sizes.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "apex_gpu.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "apex_gpu.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(apex_ctx_desc),sizeof(apex_problem_desc),sizeof(apex_lm_config),sizeof(apex_lm_result),sizeof(apex_iter_trace),"
                    "sizeof(apex_dims),sizeof(apex_profile),sizeof(apex_layout_stats),offsetof(apex_problem_desc,loss_params),offsetof(apex_lm_config,cg_tolerance),"
-                   "offsetof(apex_lm_result,linear_iterations));return 0;}\n")
+                   "offsetof(apex_lm_result,linear_iterations),sizeof(apex_observer_metrics),sizeof(apex_observer),offsetof(apex_observer_metrics,step_quality));return 0;}\n")
     exe = tmp_path / "sizes"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
     want = [C.sizeof(F.CtxDesc), C.sizeof(F.ProblemDesc), C.sizeof(F.LmConfig), C.sizeof(F.LmResult), C.sizeof(F.IterTrace), C.sizeof(F.Dims),
-            C.sizeof(F.Profile), C.sizeof(F.LayoutStats), F.ProblemDesc.loss_params.offset, F.LmConfig.cg_tolerance.offset, F.LmResult.linear_iterations.offset]
+            C.sizeof(F.Profile), C.sizeof(F.LayoutStats), F.ProblemDesc.loss_params.offset, F.LmConfig.cg_tolerance.offset, F.LmResult.linear_iterations.offset,
+            C.sizeof(F.ObserverMetrics), C.sizeof(F.Observer), F.ObserverMetrics.step_quality.offset]
     assert got == want
 
 
@@ -163,6 +165,11 @@ def test_oracle_lm_converges_and_variants_agree(variant):
     cfg2.max_iterations = 12
     r2, _ = ref.lm_solve(cfg2)
     assert abs(res.final_cost - r2.final_cost) <= 0.15 * r2.final_cost  # truncated PCG (200 its) lags the direct solve
+
+
+def test_oracle_observer_feed():
+    """OptObserver feed of the LM loop (parity_helpers.check_observer_feed) on the oracle; the GPU library runs the same check in -m gpu."""
+    check_observer_feed(OracleContext, synth.make_problem(10, 300, 4.0, seed=11, self_calibration=True))
 
 
 def test_oracle_linear_solve_matches_scipy():
