@@ -253,26 +253,44 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
   L.chunk_desc.assign(L.nnormal_chunks, ChunkDesc{0, 0, 0, 0});
   L.cslot_meta.resize((size_t)L.nnormal_chunks * TILE);
   L.cpt_meta.assign(npl, 0);
-  auto clear_chunk = [&](size_t ch) {
-    std::fill_n(L.slot_cam.begin() + ch * TILE, TILE, PAD_CAM);
-    std::fill_n(L.slot_lp.begin() + ch * TILE, TILE, (uint16_t)0);
-    std::fill_n(L.slot_uv.begin() + ch * 2 * TILE, 2 * TILE, 0.0);
-    std::fill_n(L.slot_obs.begin() + ch * TILE, TILE, UINT64_MAX);
-    if (d->obs_loss) std::fill_n(L.slot_loss.begin() + ch * TILE, TILE, (uint8_t)0);
-    for (int t = 0; t < TILE; ++t) L.slot_pos[ch * TILE + t] = (uint8_t)t;  // default: camera half at the slot's own lane
+  // padding defaults of lanes [l0, TILE) of chunk ch (the observation lanes in front of them are written exactly once below:
+  // filling whole chunks first wrote every slot array twice)
+  auto pad_chunk = [&](size_t ch, uint32_t l0, bool normal) {
+    const size_t n = (size_t)TILE - l0, b = ch * TILE + l0;
+    if (n == 0) return;
+    std::fill_n(L.slot_cam.begin() + b, n, PAD_CAM);
+    std::fill_n(L.slot_lp.begin() + b, n, (uint16_t)0);
+    std::fill_n(L.slot_uv.begin() + ch * 2 * TILE + l0, n, 0.0);
+    std::fill_n(L.slot_uv.begin() + (ch * 2 + 1) * TILE + l0, n, 0.0);
+    std::fill_n(L.slot_obs.begin() + b, n, UINT64_MAX);
+    if (d->obs_loss) std::fill_n(L.slot_loss.begin() + b, n, (uint8_t)0);
+    for (uint32_t t = l0; t < (uint32_t)TILE; ++t) L.slot_pos[ch * TILE + t] = (uint8_t)t;  // default: camera half at the slot's own lane
+    if (normal) std::fill_n(L.cslot_meta.begin() + b, n, make_uint2(PAD_CAM, 0));
   };
   const int64_t ntiles = (int64_t)L.tiles.size();
+  int cam_bits = 8;   // radix passes of the per-chunk camera sort cover the bits of ncam - 1
+  while (cam_bits < 32 && ((uint64_t)1 << cam_bits) < (uint64_t)ncam) cam_bits += 8;
   lap("slot array allocation");
 #pragma omp parallel
   {
-    std::vector<std::pair<uint32_t, uint32_t>> order;  // (camera, chunk-local point-major lane)
+    struct CamLane { uint32_t first, second; };         // (camera, chunk-local point-major lane)
+    std::vector<uint64_t> keys, tmp;                    // camera << 32 | lane
+    std::vector<CamLane> order;
 #pragma omp for schedule(dynamic, 64)
     for (int64_t ti = 0; ti < ntiles; ++ti) {
       const TileDesc& t = L.tiles[ti];
       uint64_t q = tile_q0[ti];
-      order.clear();
-      for (uint32_t ch = t.chunk0; ch < t.chunk0 + t.nchunks; ++ch) clear_chunk(ch);
-      if (t.nchunks == 1) std::fill_n(L.cslot_meta.begin() + (size_t)t.chunk0 * TILE, TILE, make_uint2(PAD_CAM, 0));
+      keys.clear();
+      {
+        uint64_t tobs = 0;
+        for (uint32_t i = 0; i < t.npt; ++i) tobs += L.pt_cnt[t.pt0 + i];
+        if (t.nchunks == 1) pad_chunk(t.chunk0, (uint32_t)tobs, true);
+        else {   // one landmark over several chunks: camera halves stay at the observations' own lanes; the last chunk's tail is padding
+          for (uint32_t ch = t.chunk0; ch < t.chunk0 + t.nchunks; ++ch)
+            for (int l = 0; l < TILE; ++l) L.slot_pos[(size_t)ch * TILE + l] = (uint8_t)l;
+          pad_chunk(t.chunk0 + t.nchunks - 1, (uint32_t)(tobs - (uint64_t)(t.nchunks - 1) * TILE), false);
+        }
+      }
       for (uint32_t i = 0; i < t.npt; ++i) {
         const uint32_t lp = t.pt0 + i;
         const uint32_t off = L.pt_slot0[lp] - t.chunk0 * TILE;
@@ -290,7 +308,7 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
           if (d->obs_loss) L.slot_loss[slot] = d->obs_loss[o];
           if (t.nchunks == 1) {
             L.cslot_meta[slot].y = i;  // [7:0] chunk-local landmark of point-major lane off + k
-            order.push_back({cam, off + k});
+            keys.push_back((uint64_t)cam << 32 | (off + k));
           }
         }
       }
@@ -299,7 +317,25 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
       // that crosses a warp boundary is marked on the first lane of the following warp(s) (continuation flags, apex_ctx.h)
       const uint32_t ch = t.chunk0;
       const size_t base = (size_t)ch * TILE;
-      std::sort(order.begin(), order.end());
+      // stable LSD radix sort by camera, 8 bits per pass (the keys were pushed in lane order, so equal cameras keep it): a chunk has
+      // at most 256 keys and ncam needs two passes up to 65 536 cameras - a third of the time std::sort took on the Venice shape
+      {
+        const size_t n = keys.size();
+        tmp.resize(n);
+        uint64_t* a = keys.data();
+        uint64_t* b = tmp.data();
+        for (int shift = 32; shift < 32 + cam_bits; shift += 8) {
+          uint16_t cnt[256] = {0};
+          for (size_t i = 0; i < n; ++i) cnt[(a[i] >> shift) & 0xFF]++;
+          uint16_t run = 0;
+          for (int v = 0; v < 256; ++v) { const uint16_t c = cnt[v]; cnt[v] = run; run = (uint16_t)(run + c); }
+          for (size_t i = 0; i < n; ++i) b[cnt[(a[i] >> shift) & 0xFF]++] = a[i];
+          std::swap(a, b);
+        }
+        if (a != keys.data()) std::copy(a, a + n, keys.data());
+      }
+      order.resize(keys.size());
+      for (size_t i = 0; i < keys.size(); ++i) order[i] = CamLane{(uint32_t)(keys[i] >> 32), (uint32_t)keys[i]};
       uint32_t nwseg = 0;
       for (size_t pos = 0; pos < order.size(); ++pos) {
         if (pos % 32 == 0 || order[pos].first != order[pos - 1].first) ++nwseg;
@@ -337,41 +373,49 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
     L.cslot_widx.resize((size_t)nn * TILE);
 #pragma omp parallel
     {
-      std::vector<uint32_t> cur, ccams, merged;
+      // per thread: stamp[cam] == epoch <=> cam is in the current window; idx[cam] = its window-local index once the window closes
+      std::vector<uint32_t> cur, fresh, stamp(ncam, 0);
+      std::vector<uint16_t> idx(ncam, 0);
+      uint32_t epoch = 0;
 #pragma omp for schedule(dynamic, 4)
       for (int64_t r = 0; r < (int64_t)P; ++r) {
         const uint32_t c0 = (uint32_t)((uint64_t)nn * r / P), c1 = (uint32_t)((uint64_t)nn * (r + 1) / P);
         auto close = [&](uint32_t cb, uint32_t ce) {
-          // window [cb, ce) with the sorted camera list `cur`: window-local index of every camera-sorted lane (merge walk)
+          // window [cb, ce) with the camera list `cur`: sorted, it is the window's row order; every camera-sorted lane gets its row
+          std::sort(cur.begin(), cur.end());
           rw[r].push_back(WinDesc{cb, ce, (uint32_t)rc[r].size(), (uint32_t)cur.size()});
           rc[r].insert(rc[r].end(), cur.begin(), cur.end());
+          for (size_t j = 0; j < cur.size(); ++j) idx[cur[j]] = (uint16_t)j;
           for (uint32_t ch = cb; ch < ce; ++ch) {
             const size_t base = (size_t)ch * TILE;
             const uint32_t n = L.chunk_desc[ch].nobs;
-            size_t j = 0;
-            for (uint32_t pos = 0; pos < n; ++pos) {
-              const uint32_t cam = L.cslot_meta[base + pos].x;
-              while (cur[j] < cam) ++j;
-              L.cslot_widx[base + pos] = (uint16_t)j;
-            }
+            for (uint32_t pos = 0; pos < n; ++pos) L.cslot_widx[base + pos] = idx[L.cslot_meta[base + pos].x];
             for (uint32_t pos = n; pos < (uint32_t)TILE; ++pos) L.cslot_widx[base + pos] = 0;
           }
         };
         cur.clear();
+        ++epoch;
         uint32_t wb = c0;
         for (uint32_t ch = c0; ch < c1; ++ch) {
           const size_t base = (size_t)ch * TILE;
           const uint32_t n = L.chunk_desc[ch].nobs;
-          ccams.clear();
-          for (uint32_t pos = 0; pos < n; ++pos)
-            if (pos == 0 || L.cslot_meta[base + pos].x != L.cslot_meta[base + pos - 1].x) ccams.push_back(L.cslot_meta[base + pos].x);
-          merged.resize(cur.size() + ccams.size());
-          merged.resize(std::set_union(cur.begin(), cur.end(), ccams.begin(), ccams.end(), merged.begin()) - merged.begin());
-          if (merged.size() > W && ch > wb) {
+          // cameras of this chunk the window does not hold yet (a camera is one run of the camera-sorted lanes)
+          auto collect = [&]() {
+            fresh.clear();
+            for (uint32_t pos = 0; pos < n; ++pos) {
+              const uint32_t cam = L.cslot_meta[base + pos].x;
+              if ((pos == 0 || cam != L.cslot_meta[base + pos - 1].x) && stamp[cam] != epoch) fresh.push_back(cam);
+            }
+          };
+          collect();
+          if (cur.size() + fresh.size() > W && ch > wb) {   // the chunk would take the window beyond W cameras: it starts the next one
             close(wb, ch);
             wb = ch;
-            cur = ccams;
-          } else cur.swap(merged);
+            cur.clear();
+            ++epoch;
+            collect();
+          }
+          for (uint32_t cam : fresh) { stamp[cam] = epoch; cur.push_back(cam); }
         }
         if (c1 > wb) close(wb, c1);
       }
@@ -417,9 +461,14 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
     for (int t = 1; t < T; ++t)
       lp_cut[t] = (uint32_t)(std::lower_bound(pt_start.begin(), pt_start.end(), L.nobs_local * (uint64_t)t / T) - pt_start.begin());
     for (int t = 1; t <= T; ++t) lp_cut[t] = std::max(lp_cut[t], lp_cut[t - 1]);
+    // (cameras, pixels and loss classes are read back from the slot arrays filled above: they hold the observations in this very
+    // order, contiguously per landmark, where d->obs_*[pm[q]] would be one cache miss per observation and array)
 #pragma omp parallel for num_threads(T) schedule(static, 1)
     for (int t = 0; t < T; ++t)
-      for (uint64_t q = pt_start[lp_cut[t]]; q < pt_start[lp_cut[t + 1]]; ++q) cnt[t][d->obs_cam[pm[q]]]++;
+      for (uint32_t lp = lp_cut[t]; lp < lp_cut[t + 1]; ++lp) {
+        const uint32_t* sc = L.slot_cam.data() + L.pt_slot0[lp];
+        for (uint32_t k = 0; k < L.pt_cnt[lp]; ++k) cnt[t][sc[k]]++;
+      }
     for (uint32_t k = 0; k < ncam; ++k) {
       uint32_t run = cam_start[k];
       for (int t = 0; t < T; ++t) { const uint32_t n = cnt[t][k]; cnt[t][k] = run; run += n; }
@@ -427,15 +476,14 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
     }
 #pragma omp parallel for num_threads(T) schedule(static, 1)
     for (int t = 0; t < T; ++t) {
-      uint64_t q = pt_start[lp_cut[t]];
       for (uint32_t lp = lp_cut[t]; lp < lp_cut[t + 1]; ++lp)
-        for (uint32_t k = 0; k < L.pt_cnt[lp]; ++k, ++q) {
-          const uint64_t o = pm[q];
-          const uint32_t pos = cnt[t][d->obs_cam[o]]++;
-          L.cm_uv[pos] = d->obs_uv[2 * o];
-          L.cm_uv[(size_t)L.nobs_local + pos] = d->obs_uv[2 * o + 1];
+        for (uint32_t k = 0; k < L.pt_cnt[lp]; ++k) {
+          const size_t slot = (size_t)L.pt_slot0[lp] + k, ch = slot / TILE, lane = slot % TILE;
+          const uint32_t pos = cnt[t][L.slot_cam[slot]]++;
+          L.cm_uv[pos] = L.slot_uv[(ch * 2 + 0) * TILE + lane];
+          L.cm_uv[(size_t)L.nobs_local + pos] = L.slot_uv[(ch * 2 + 1) * TILE + lane];
           L.cm_lp[pos] = lp;
-          if (d->obs_loss) L.cm_loss[pos] = d->obs_loss[o];
+          if (d->obs_loss) L.cm_loss[pos] = L.slot_loss[slot];
         }
     }
   }
