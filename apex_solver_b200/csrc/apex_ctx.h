@@ -350,6 +350,8 @@ struct Ctx {
   uint64_t chol_n = 0;
   uint64_t upload_h2d_bytes = 0;      // H2D bytes of the last problem upload
   cudaEvent_t ev_lm0 = nullptr, ev_lm1 = nullptr;
+  cudaEvent_t ev_batch[2] = {nullptr, nullptr};   // end of the PCG batches in flight (solve_implicit)
+  int32_t* h_batch_done = nullptr;                // pinned [2]: pcg_done as of the end of those batches
   bool lm_timed = false;
 };
 

@@ -195,6 +195,8 @@ void apex_ctx_destroy(apex_ctx* ctx) {
   for (cudaEvent_t e : c.ev_chol) cudaEventDestroy(e);
   if (c.ev_lm0) { cudaEventDestroy(c.ev_lm0); cudaEventDestroy(c.ev_lm1); }
   if (c.h_state) cudaFreeHost(c.h_state);
+  if (c.h_batch_done) cudaFreeHost(c.h_batch_done);
+  for (cudaEvent_t e : c.ev_batch) if (e) cudaEventDestroy(e);
   for (int k = 0; k < 2; ++k) { if (c.bounce[k]) cudaFreeHost(c.bounce[k]); if (c.bounce_ev[k]) cudaEventDestroy(c.bounce_ev[k]); }
   for (cudaEvent_t e : c.chol_events) cudaEventDestroy(e);
   if (c.stream2) cudaStreamDestroy(c.stream2);
