@@ -105,12 +105,29 @@ __global__ void __launch_bounds__(TILE) schur_form_kernel(FormArgs a) {
 // block's (observation i, observation j) pairs in their fixed order and stores the dc x dc block once - no reductions into memory,
 // bitwise reproducible. Lane l = g*DC + q owns column q and the rows p = g, g + G, ... (G = 32 / DC groups of lanes); per pair every lane
 // recomputes the 2x2 middle  Jp_i Hpp^-1 Jp_j^T  (broadcast loads), reads its two entries of Jc_j and the rows' entries of Jc_i.
+// The pairs of a block name observations anywhere in the problem: read from the chunk planes, the 2*dc + 6 doubles of one observation
+// sit in dc + 3 different 4 KB-apart planes, i.e. one 32-byte sector per 16 useful bytes and 2 x (dc + 3) sectors per pair (ncu on the
+// Kannala-Brandt 2 000-camera shape: 44.8 GB of DRAM reads for 1.7 GB of Jacobians, long scoreboard 73 % of the stall samples). So the
+// explicit solve first packs the linearisation observation-major - row `slot` = [camera half 2*dc | landmark half 6], contiguous -
+// and a pair reads two rows: (2*dc + 6) / 4 sectors each.
+template <int DC>
+__global__ void __launch_bounds__(TILE) pack_obs_major_kernel(const double* __restrict__ J, const uint8_t* __restrict__ slot_cs8, double* __restrict__ rows) {
+  constexpr int NPAIR = DC + 3, RS = 2 * DC + 6;
+  const size_t chunk = blockIdx.x, slot = chunk * TILE + threadIdx.x;
+  const uint32_t cs = slot_cs8[slot];   // lane of the camera half inside the chunk (split slot order)
+  const double2* J2 = reinterpret_cast<const double2*>(J) + chunk * NPAIR * TILE;
+  double2* row = reinterpret_cast<double2*>(rows + slot * RS);
+#pragma unroll
+  for (int m = 0; m < DC; ++m) row[m] = ld_stream2(J2 + (size_t)m * TILE + cs);
+#pragma unroll
+  for (int m = 0; m < 3; ++m) row[DC + m] = ld_stream2(J2 + (size_t)(DC + m) * TILE + threadIdx.x);
+}
+
 struct PairArgs {
   const PairBlock* blocks;
   const uint2* pairs;
   const uint32_t* slot_lpg;
-  const uint8_t* slot_cs8;
-  const double* J;
+  const double* rows;    // observation-major linearisation (pack_obs_major_kernel)
   const double* hinv;
   double* S;
   size_t ld;
@@ -119,7 +136,7 @@ struct PairArgs {
 
 template <int DC>
 __global__ void __launch_bounds__(256, 4) schur_form_pairs_kernel(PairArgs a) {
-  constexpr int NPAIR = DC + 3, G = 32 / DC, RPL = (DC + G - 1) / G;
+  constexpr int G = 32 / DC, RPL = (DC + G - 1) / G;
   const uint32_t b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= a.nblocks) return;
   const int lane = threadIdx.x & 31, g = lane / DC, q = lane % DC;
@@ -128,26 +145,25 @@ __global__ void __launch_bounds__(256, 4) schur_form_pairs_kernel(PairArgs a) {
   double acc[RPL];
 #pragma unroll
   for (int r = 0; r < RPL; ++r) acc[r] = 0.0;
-  const double2* J2 = reinterpret_cast<const double2*>(a.J);
+  constexpr int RS = 2 * DC + 6;
   const size_t n = a.npl;
-  // the pair's indices (pair -> slots -> landmark / camera-half lanes) are fetched one pair ahead: two of the three dependent
-  // memory round trips per pair are then off the critical path
-  uint32_t nsi = 0, nsj = 0, nlp = 0, ncsi = 0, ncsj = 0;
+  // the pair's indices (pair -> slots -> landmark) are fetched one pair ahead: one of the two dependent memory round trips per
+  // pair is then off the critical path
+  uint32_t nsi = 0, nsj = 0, nlp = 0;
   auto fetch = [&](uint32_t e) {
     const uint2 pr = __ldg(a.pairs + e);
     nsi = pr.x; nsj = pr.y;
-    nlp = __ldg(a.slot_lpg + nsi); ncsi = __ldg(a.slot_cs8 + nsi); ncsj = __ldg(a.slot_cs8 + nsj);
+    nlp = __ldg(a.slot_lpg + nsi);
   };
   if (blk.begin < blk.end) fetch(blk.begin);
   for (uint32_t e = blk.begin; e < blk.end; ++e) {
-    const uint32_t si = nsi, sj = nsj, lp = nlp, csi = ncsi, csj = ncsj;
+    const uint32_t si = nsi, sj = nsj, lp = nlp;
     if (e + 1 < blk.end) fetch(e + 1);
-    const size_t bi = (size_t)(si >> 8) * NPAIR * TILE, bj = (size_t)(sj >> 8) * NPAIR * TILE;
-    const uint32_t pmi = si & 255u, pmj = sj & 255u;
+    const double* Ri = a.rows + (size_t)si * RS, *Rj = a.rows + (size_t)sj * RS;
     double pi[6], pj[6];
 #pragma unroll
     for (int m = 0; m < 3; ++m) {
-      const double2 u = __ldg(J2 + bi + (size_t)(DC + m) * TILE + pmi), v = __ldg(J2 + bj + (size_t)(DC + m) * TILE + pmj);
+      const double2 u = __ldg(reinterpret_cast<const double2*>(Ri + 2 * DC) + m), v = __ldg(reinterpret_cast<const double2*>(Rj + 2 * DC) + m);
       pi[2 * m] = u.x; pi[2 * m + 1] = u.y; pj[2 * m] = v.x; pj[2 * m + 1] = v.y;
     }
     const double h00 = __ldg(a.hinv + 0 * n + lp), h01 = __ldg(a.hinv + 1 * n + lp), h02 = __ldg(a.hinv + 2 * n + lp);
@@ -162,15 +178,13 @@ __global__ void __launch_bounds__(256, 4) schur_form_pairs_kernel(PairArgs a) {
       for (int cc = 0; cc < 2; ++cc) M[r][cc] = g0 * pj[cc * 3] + g1 * pj[cc * 3 + 1] + g2 * pj[cc * 3 + 2];
     }
     if (!act) continue;
-    // element k of a camera half: plane k / 2, component k % 2
-    const double* Jci = a.J + 2 * (bi + csi), *Jcj = a.J + 2 * (bj + csj);
-    auto elem = [&](const double* base, int k) { return __ldg(base + 2 * (size_t)(k >> 1) * TILE + (k & 1)); };
-    const double cj0 = elem(Jcj, q), cj1 = elem(Jcj, DC + q);
+    // element k of a camera half: row 0 = 0..DC-1, row 1 = DC..2DC-1
+    const double cj0 = __ldg(Rj + q), cj1 = __ldg(Rj + DC + q);
 #pragma unroll
     for (int r = 0; r < RPL; ++r) {
       const int p = g + r * G;
       if (p < DC) {
-        const double ci0 = elem(Jci, p), ci1 = elem(Jci, DC + p);
+        const double ci0 = __ldg(Ri + p), ci1 = __ldg(Ri + DC + p);
         const double a0 = ci0 * M[0][0] + ci1 * M[1][0], a1 = ci0 * M[0][1] + ci1 * M[1][1];
         acc[r] -= fma(a0, cj0, a1 * cj1);
       }
@@ -810,9 +824,21 @@ apex_status solve_explicit(Ctx& c, bool use_pcg, int cg_max_it, double cg_tol) {
   const bool by_pairs = !getenv("APEX_SCHUR_FORM_ATOMIC");   // (the reduction-per-element kernel stays for A/B measurements)
   if (c.ntiles && by_pairs) {
     APEX_TRY(build_schur_pairs(c));
-    PairArgs pa{c.pair_blocks.p, c.pair_slots.p, c.slot_lpg.p, c.slot_cs8.p, c.J.p, c.hinv.p, S, ld, c.npl, c.npair_blocks};
     const unsigned grid = (c.npair_blocks + 7) / 8;
     if (grid) {
+      APEX_CUDA_TRY(c, c.E.alloc((size_t)c.nchunks * TILE * (2 * (size_t)c.dc + 6)));   // observation-major rows
+      switch (c.dc) {
+        case 6: pack_obs_major_kernel<6><<<c.nchunks, TILE, 0, s>>>(c.J.p, c.slot_cs8.p, c.E.p); break;
+        case 9: pack_obs_major_kernel<9><<<c.nchunks, TILE, 0, s>>>(c.J.p, c.slot_cs8.p, c.E.p); break;
+        case 10: pack_obs_major_kernel<10><<<c.nchunks, TILE, 0, s>>>(c.J.p, c.slot_cs8.p, c.E.p); break;
+        case 11: pack_obs_major_kernel<11><<<c.nchunks, TILE, 0, s>>>(c.J.p, c.slot_cs8.p, c.E.p); break;
+        case 12: pack_obs_major_kernel<12><<<c.nchunks, TILE, 0, s>>>(c.J.p, c.slot_cs8.p, c.E.p); break;
+        case 14: pack_obs_major_kernel<14><<<c.nchunks, TILE, 0, s>>>(c.J.p, c.slot_cs8.p, c.E.p); break;
+        case 15: pack_obs_major_kernel<15><<<c.nchunks, TILE, 0, s>>>(c.J.p, c.slot_cs8.p, c.E.p); break;
+        default: c.err = "unsupported dc"; return APEX_ERR_UNSUPPORTED;
+      }
+      c.launches++;
+      PairArgs pa{c.pair_blocks.p, c.pair_slots.p, c.slot_lpg.p, c.E.p, c.hinv.p, S, ld, c.npl, c.npair_blocks};
       switch (c.dc) {
         case 6: schur_form_pairs_kernel<6><<<grid, 256, 0, s>>>(pa); break;
         case 9: schur_form_pairs_kernel<9><<<grid, 256, 0, s>>>(pa); break;
