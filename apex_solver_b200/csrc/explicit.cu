@@ -685,31 +685,46 @@ static apex_status dense_cholesky(Ctx& c, double* L, uint32_t npad) {
     APEX_CUDA_TRY(c, cudaFuncSetAttribute(chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_smem_bytes));
     c.chol_attr_set = true;
   }
-  // Two-level right-looking blocking. Outer panels of NBO = 256 columns: inside a panel the 64-wide steps update only
-  // the panel's own remaining columns (all rows below); the matrix to the right of the panel is then updated ONCE with
-  // k depth 256, so every trailing tile is read and written n/256 times instead of n/64 times (the 64-deep update is
-  // bound by that HBM traffic, not by the FP64 tensor pipe).
-  const uint32_t NBO = 4 * NB;
+  // Three-level right-looking blocking: 64-column steps (potrf, trsm) inside inner panels of NBI = 256 columns inside outer panels
+  // of NBO columns (default 1024). A 64-wide step updates only its inner panel's remaining columns (all rows below, k depth 64:
+  // bound by HBM traffic, not by the tensor pipe); a finished inner panel updates the remaining columns of its OUTER panel with k
+  // depth 256 on the 128x128 tensor-pipe tiles; the matrix to the right of the outer panel is updated ONCE per outer panel with k
+  // depth NBO, so a trailing tile is read and written n/NBO times and the pipeline fill + C read-modify-write of a tile (3-4 us) is
+  // paid once per 2*128*128*NBO flops. Measured at n = 28 032 with two levels: NBO 256 / 512 / 768 = 295.6 / 280.3 / 277.0 ms (the
+  // 64-deep in-panel work grows with the panel: 1.5 NBO / n of the flops at a third of the rate); with the middle level the wide
+  // panel no longer pays that.
+  const uint32_t NBI = 4 * NB;
+  uint32_t NBO = 16 * NB;
+  if (const char* e = getenv("APEX_CHOL_PANEL")) { const int v = atoi(e); if (v >= 256 && v <= 4096 && v % 256 == 0) NBO = (uint32_t)v; }   // A/B: outer panel width
+  const bool deep128 = !getenv("APEX_CHOL_SYRK64");
+  if (!deep128) NBO = NBI;
   const uint32_t nblk = npad / NB;
   cudaEvent_t last_rest = nullptr;
   bool have_rest = false;
   for (uint32_t ko = 0; ko < npad; ko += NBO) {
     const uint32_t kend = std::min(ko + NBO, npad);
-    for (uint32_t k0 = ko; k0 < kend; k0 += NB) {
-      chol_potrf_kernel<<<1, 256, 0, s>>>(L, ld, k0, c.state.p);
-      c.launches++;
-      const uint32_t rem = nblk - k0 / NB - 1;  // 64-row blocks below the diagonal block
-      if (rem == 0) break;
-      chol_trsm_kernel<<<rem, 256, trsm_smem_bytes, s>>>(L, ld, k0);
-      c.launches++;
-      const uint32_t ncol = (kend - k0) / NB - 1;  // panel column tiles still to update
-      if (ncol) {
-        chol_syrk_kernel<<<dim3(rem, ncol), 128, smem, s>>>(L, ld, k0, NB, k0 + NB);
+    for (uint32_t ki = ko; ki < kend; ki += NBI) {
+      const uint32_t kiend = std::min(ki + NBI, kend);
+      for (uint32_t k0 = ki; k0 < kiend; k0 += NB) {
+        chol_potrf_kernel<<<1, 256, 0, s>>>(L, ld, k0, c.state.p);
+        c.launches++;
+        const uint32_t rem = nblk - k0 / NB - 1;  // 64-row blocks below the diagonal block
+        if (rem == 0) break;
+        chol_trsm_kernel<<<rem, 256, trsm_smem_bytes, s>>>(L, ld, k0);
+        c.launches++;
+        const uint32_t ncol = (kiend - k0) / NB - 1;  // inner-panel column tiles still to update
+        if (ncol) {
+          chol_syrk_kernel<<<dim3(rem, ncol), 128, smem, s>>>(L, ld, k0, NB, k0 + NB);
+          c.launches++;
+        }
+      }
+      if (kiend < kend) {   // the rest of the outer panel: k depth 256, rows from kiend down, column tiles [kiend, kend)
+        chol_syrk128_kernel<<<dim3((npad - kiend) / SB, (kend - kiend) / SB), SYRK_THREADS, syrk128_smem, s>>>(L, ld, ki, kiend - ki, kiend, 0);
         c.launches++;
       }
     }
     if (kend < npad) {
-      if ((npad - kend) % SB == 0 && (kend - ko) % SKC == 0 && !getenv("APEX_CHOL_SYRK64")) {
+      if ((npad - kend) % SB == 0 && (kend - ko) % SKC == 0 && deep128) {
         // Look-ahead: the deep update is split by columns. The 256 columns of the NEXT panel are updated on the main
         // stream, which then goes straight on to factor that panel (potrf / trsm are latency bound on a handful of
         // CTAs); everything to the right is updated on a second, low-priority stream at the same time. Events keep the
