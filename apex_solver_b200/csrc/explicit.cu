@@ -422,28 +422,43 @@ __global__ void __launch_bounds__(SYRK_THREADS, 1) chol_syrk128_kernel(double* A
     }
     asm volatile("cp.async.commit_group;" ::: "memory");   // one group per call, empty or not: the wait below counts groups
   };
-  // three-stage ring, ONE barrier per slice: at the top of iteration s the groups of slices 0..s+1 are committed, wait_group 1
-  // leaves only s+1 pending, the barrier makes slice s visible to everybody and proves that everybody is done with slice s-1,
-  // whose buffer then takes slice s+2
+  // Three-stage ring, ONE barrier per slice, placed in the MIDDLE of the slice's eight k steps: there every thread's copies of
+  // slice s+1 have landed (wait_group 0; they were issued a slice ago), the barrier makes them visible to everybody and proves
+  // that everybody is past slice s-1, whose buffer then takes slice s+2. The fragments of a k step are loaded one step ahead into
+  // a second register set - across the slice boundary as well, which the mid-slice barrier allows - so no warp starts a step
+  // with a shared-memory round trip in front of its first DMMA (with the barrier at the top of a slice all sixteen warps did so
+  // at the same moment and the tensor pipe idled).
+  const int fr = lr * SPLD + lc;
+  double af[2][4], bf[2][4];
+  auto load = [&](int buf, const double* Pa, const double* Pb, int kk) {
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) af[buf][mi] = Pa[(wm + mi * 8) * SPLD + fr + kk];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) bf[buf][ni] = Pb[(wn + ni * 8) * SPLD + fr + kk];
+  };
   stage(0);
   stage(1);
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
+  __syncthreads();
+  load(0, smem, smem + SB * SPLD, 0);
   for (int sidx = 0; sidx < nslices; ++sidx) {
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncthreads();
-    stage(sidx + 2);
     const double* Pa = smem + (size_t)(sidx % SYRK_STAGES) * 2 * SB * SPLD;
     const double* Pb = Pa + SB * SPLD;
-#pragma unroll 2
-    for (int kk = 0; kk < SKC; kk += 4) {
-      double af[4], bf[4];
+    const double* Na = smem + (size_t)((sidx + 1) % SYRK_STAGES) * 2 * SB * SPLD;
+    const double* Nb = Na + SB * SPLD;
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi) af[mi] = Pa[(wm + mi * 8 + lr) * SPLD + kk + lc];
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) bf[ni] = Pb[(wn + ni * 8 + lr) * SPLD + kk + lc];
+    for (int st = 0; st < SKC / 4; ++st) {
+      if (st == SKC / 8) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        stage(sidx + 2);
+      }
+      if (st + 1 < SKC / 4) load((st + 1) & 1, Pa, Pb, 4 * (st + 1));
+      else if (sidx + 1 < nslices) load((st + 1) & 1, Na, Nb, 0);
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        for (int ni = 0; ni < 4; ++ni) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[st & 1][mi], bf[st & 1][ni]);
     }
   }
 #pragma unroll
