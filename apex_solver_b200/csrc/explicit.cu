@@ -394,10 +394,27 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
-__global__ void __launch_bounds__(SYRK_THREADS, 1) chol_syrk128_kernel(double* A, size_t ld, uint32_t k0, uint32_t kdepth, uint32_t r0, uint32_t bj0) {
+// Tiles of the lower block triangle in column tiles [bj0, bj0 + ny) of a trailing matrix with `rem` row tiles, numbered column by
+// column: column c holds the R - c tiles on and below the diagonal (R = rem - bj0), so tile t lives in the column c with
+// c R - c (c - 1) / 2 <= t. (A rem x ny grid with an early return for the upper triangle launched nearly twice the CTAs, and with
+// one 221 KB CTA per SM an empty CTA holds its SM for a launch + exit.)
+__host__ __device__ inline uint32_t syrk128_tiles(uint32_t rem, uint32_t bj0, uint32_t ny) {
+  const uint64_t R = rem - bj0;
+  return (uint32_t)((uint64_t)ny * R - (uint64_t)ny * (ny - 1) / 2);
+}
+__global__ void __launch_bounds__(SYRK_THREADS, 1) chol_syrk128_kernel(double* A, size_t ld, uint32_t k0, uint32_t kdepth, uint32_t r0, uint32_t bj0, uint32_t rem) {
   extern __shared__ __align__(16) double smem[];
-  const uint32_t bi = blockIdx.x, bj = blockIdx.y + bj0;  // column tiles [bj0, bj0 + gridDim.y) of the trailing matrix
-  if (bi < bj) return;
+  uint32_t bi, bj;
+  {
+    const double R = (double)(rem - bj0), t = (double)blockIdx.x;
+    int64_t c = (int64_t)floor(((2.0 * R + 1.0) - sqrt((2.0 * R + 1.0) * (2.0 * R + 1.0) - 8.0 * t)) * 0.5);
+    const int64_t Ri = (int64_t)(rem - bj0), ti = (int64_t)blockIdx.x;
+    if (c < 0) c = 0;
+    while ((c + 1) * Ri - (c + 1) * c / 2 <= ti) ++c;
+    while (c * Ri - c * (c - 1) / 2 > ti) --c;
+    bj = bj0 + (uint32_t)c;
+    bi = bj + (uint32_t)(ti - (c * Ri - c * (c - 1) / 2));
+  }
   const size_t ri = (size_t)r0 + (size_t)bi * SB, rj = (size_t)r0 + (size_t)bj * SB;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -422,8 +439,8 @@ __global__ void __launch_bounds__(SYRK_THREADS, 1) chol_syrk128_kernel(double* A
     }
     asm volatile("cp.async.commit_group;" ::: "memory");   // one group per call, empty or not: the wait below counts groups
   };
-  // Three-stage ring, ONE barrier per slice, placed in the MIDDLE of the slice's eight k steps: there every thread's copies of
-  // slice s+1 have landed (wait_group 0; they were issued a slice ago), the barrier makes them visible to everybody and proves
+  // Three-stage ring, ONE barrier per slice, armed in the MIDDLE of the slice's eight k steps: there every thread's copies of
+  // slice s+1 have landed (wait_group 0; they were issued a slice ago); the barrier makes them visible to everybody and proves
   // that everybody is past slice s-1, whose buffer then takes slice s+2. The fragments of a k step are loaded one step ahead into
   // a second register set - across the slice boundary as well, which the mid-slice barrier allows - so no warp starts a step
   // with a shared-memory round trip in front of its first DMMA (with the barrier at the top of a slice all sixteen warps did so
@@ -436,11 +453,22 @@ __global__ void __launch_bounds__(SYRK_THREADS, 1) chol_syrk128_kernel(double* A
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) bf[buf][ni] = Pb[(wn + ni * 8) * SPLD + fr + kk];
   };
+  // The slice barrier is split (mbarrier, 512 arrivals per phase): a thread ARRIVES in the middle of slice s ("my copies of slice
+  // s+1 have landed and I am past slice s-1") and WAITS only at the slice's last step, in front of its first read of slice s+1 and
+  // of the copies that overwrite slice s-1's buffer: three k steps of slack, so the warps of a CTA drift against each other
+  // instead of meeting eight times per 256 k.
+  __shared__ __align__(8) unsigned long long slice_bar;
+  const uint32_t sbar = (uint32_t)__cvta_generic_to_shared(&slice_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sbar), "r"((uint32_t)SYRK_THREADS) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   stage(0);
   stage(1);
   asm volatile("cp.async.wait_group 1;" ::: "memory");
   __syncthreads();
   load(0, smem, smem + SB * SPLD, 0);
+  uint32_t phase = 0;
   for (int sidx = 0; sidx < nslices; ++sidx) {
     const double* Pa = smem + (size_t)(sidx % SYRK_STAGES) * 2 * SB * SPLD;
     const double* Pb = Pa + SB * SPLD;
@@ -450,11 +478,19 @@ __global__ void __launch_bounds__(SYRK_THREADS, 1) chol_syrk128_kernel(double* A
     for (int st = 0; st < SKC / 4; ++st) {
       if (st == SKC / 8) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        stage(sidx + 2);
+        asm volatile("{\n .reg .b64 t;\n mbarrier.arrive.shared::cta.b64 t, [%0];\n}" ::"r"(sbar) : "memory");
       }
       if (st + 1 < SKC / 4) load((st + 1) & 1, Pa, Pb, 4 * (st + 1));
-      else if (sidx + 1 < nslices) load((st + 1) & 1, Na, Nb, 0);
+      else {
+        for (;;) {   // every thread of the CTA has arrived for this slice
+          uint32_t ok;
+          asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(sbar), "r"(phase) : "memory");
+          if (ok) break;
+        }
+        phase ^= 1u;
+        stage(sidx + 2);
+        if (sidx + 1 < nslices) load((st + 1) & 1, Na, Nb, 0);
+      }
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -734,7 +770,8 @@ static apex_status dense_cholesky(Ctx& c, double* L, uint32_t npad) {
         }
       }
       if (kiend < kend) {   // the rest of the outer panel: k depth 256, rows from kiend down, column tiles [kiend, kend)
-        chol_syrk128_kernel<<<dim3((npad - kiend) / SB, (kend - kiend) / SB), SYRK_THREADS, syrk128_smem, s>>>(L, ld, ki, kiend - ki, kiend, 0);
+        const uint32_t remm = (npad - kiend) / SB, nym = (kend - kiend) / SB;
+        chol_syrk128_kernel<<<syrk128_tiles(remm, 0, nym), SYRK_THREADS, syrk128_smem, s>>>(L, ld, ki, kiend - ki, kiend, 0, remm);
         c.launches++;
       }
     }
@@ -757,15 +794,15 @@ static apex_status dense_cholesky(Ctx& c, double* L, uint32_t npad) {
           cudaEvent_t Ej = c.chol_events[2 * pj], Rj = c.chol_events[2 * pj + 1];
           APEX_CUDA_TRY(c, cudaEventRecord(Ej, s));
           if (have_rest) APEX_CUDA_TRY(c, cudaStreamWaitEvent(s, last_rest, 0));
-          chol_syrk128_kernel<<<dim3(rem, head), SYRK_THREADS, syrk128_smem, s>>>(L, ld, ko, kend - ko, kend, 0);
+          chol_syrk128_kernel<<<syrk128_tiles(rem, 0, head), SYRK_THREADS, syrk128_smem, s>>>(L, ld, ko, kend - ko, kend, 0, rem);
           APEX_CUDA_TRY(c, cudaStreamWaitEvent(c.stream2, Ej, 0));
-          chol_syrk128_kernel<<<dim3(rem, rem - head), SYRK_THREADS, syrk128_smem, c.stream2>>>(L, ld, ko, kend - ko, kend, head);
+          chol_syrk128_kernel<<<syrk128_tiles(rem, head, rem - head), SYRK_THREADS, syrk128_smem, c.stream2>>>(L, ld, ko, kend - ko, kend, head, rem);
           APEX_CUDA_TRY(c, cudaEventRecord(Rj, c.stream2));
           last_rest = Rj; have_rest = true;
           c.launches++;
         } else {
           if (have_rest) { APEX_CUDA_TRY(c, cudaStreamWaitEvent(s, last_rest, 0)); have_rest = false; }
-          chol_syrk128_kernel<<<dim3(rem, rem), SYRK_THREADS, syrk128_smem, s>>>(L, ld, ko, kend - ko, kend, 0);
+          chol_syrk128_kernel<<<syrk128_tiles(rem, 0, rem), SYRK_THREADS, syrk128_smem, s>>>(L, ld, ko, kend - ko, kend, 0, rem);
         }
       } else {
         const uint32_t rem = (npad - kend) / NB;
