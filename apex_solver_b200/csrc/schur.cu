@@ -877,10 +877,10 @@ __global__ void __launch_bounds__(PCG_THREADS) pcg_update_kernel(const double* _
 // The camera vectors are small (ncam*dc doubles: 128 KB on the Venice shape) and the step is pure latency: as five kernels
 // (det_reduce, pcg_pap / ar_reduce_pap, pcg_update, pcg_dir_hcc) it cost ~25-35 us per PCG iteration next to an operator of
 // 260 us on one GPU and 40 us on an eighth of the problem. Here one warp owns a camera (lane q = row q of its blocks), the CTAs
-// of one launch are co-resident (grid <= 2 per SM, 256 threads, no dynamic shared memory) and meet at software grid barriers -
-// an arrival counter in DevState per barrier, reset by CTA 0 once the following barrier proves every CTA has left it - and
-// every grid-wide dot product is a per-CTA partial summed by every CTA in the same fixed order (same bits on every CTA and, with
-// the rank-ordered peer sum, on every rank). Two launches per PCG iteration (operator + tail).
+// of one launch are co-resident (512 threads, one CTA per SM, no dynamic shared memory) and exchange their partial sums through
+// tagged slots (tail_publish / tail_gather below: barrier and gather in one step) - every grid-wide dot product is a per-CTA
+// partial summed by every CTA in the same fixed order (same bits on every CTA and, with the rank-ordered peer sum, on every
+// rank). Two launches per PCG iteration (operator + tail), each a programmatic dependent of the other.
 // Semantics of solve_pcg_block (implicit_schur.rs:604-676) as in pcg_pap / pcg_update / pcg_dir_hcc.
 // ----------------------------------------------------------------------------------------------------
 constexpr int TAIL_THREADS = 512;           // 16 warps = 16 cameras per CTA, one CTA per SM: the G x G polling traffic of the exchanges is a quarter of what 256-thread CTAs cost
