@@ -4,6 +4,8 @@
 // landmark sharding across ranks, point-major tiles with per-chunk camera segments, camera-major work items.
 // build_layout() is pure host code (OpenMP over tiles) so it can be exercised without a device.
 #include <algorithm>
+#include <functional>
+#include <thread>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -130,7 +132,10 @@ struct HostLayout {
   std::vector<uint32_t> cam_item_start;
 };
 
-static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostLayout& L, uint32_t nctas, uint32_t W, bool want_det_lists) {
+// `on_tiles(nchunks, nnormal_chunks, nobs_local, npl)`, if set, is called as soon as the chunk count is known (after the point-major
+// sort and the serial tile cut, about a third into the build): the caller starts its device allocations there.
+static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostLayout& L, uint32_t nctas, uint32_t W, bool want_det_lists,
+                         const std::function<void(uint32_t, uint32_t, uint64_t, uint32_t)>& on_tiles = nullptr) {
   const bool timing = getenv("APEX_LAYOUT_TIMING") != nullptr;
   auto tprev = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
@@ -242,6 +247,7 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
   const size_t nslots = (size_t)chunk * TILE;
 
   lap("tiles");
+  if (on_tiles) on_tiles(L.nchunks, L.nnormal_chunks, L.nobs_local, npl);
   // ---- slot arrays + the camera-sorted lane order of every normal chunk (parallel over tiles) ----
   // (uninitialised here; every chunk is filled with its padding defaults by the worker that builds it)
   L.slot_cam.resize(nslots);
@@ -723,7 +729,36 @@ apex_status problem_upload(Ctx& c, const apex_problem_desc* d) {
   HostLayout& L = *static_cast<HostLayout*>(c.staging.get());
   L.reset();
   APEX_TRY(schur_configure(c));   // window width, CTAs per SM of the chunk kernel -> number of ranges
-  build_layout(d, c.nranks, c.rank, L, c.mv_ctas_per_sm * (uint32_t)c.num_sms, c.mv_window, true);
+  // The device buffers whose sizes follow from the chunk count are allocated by a helper thread WHILE the rest of the layout is built
+  // (on a context that has never seen a problem cudaMalloc of ~1.6 GB costs 6-50 ms, sometimes more; the layout another ~25 ms from
+  // that point on). On a context that already holds large enough buffers every alloc() is a no-op.
+  std::thread alloc_thread;
+  cudaError_t alloc_err = cudaSuccess;
+  auto on_tiles = [&](uint32_t nchunks, uint32_t nnormal, uint64_t nobs_local, uint32_t npl) {
+    alloc_thread = std::thread([&c, &alloc_err, nchunks, nnormal, nobs_local, npl] {
+      auto A = [&](cudaError_t e) { if (alloc_err == cudaSuccess && e != cudaSuccess) alloc_err = e; };
+      A(cudaSetDevice(c.device));
+      const size_t nslots = (size_t)nchunks * TILE;
+      A(c.J.alloc((size_t)nchunks * c.np * TILE));
+      A(c.R.alloc((size_t)nchunks * 2 * TILE));
+      A(c.slot_cam.alloc(nslots));
+      A(c.slot_lp.alloc(nslots));
+      A(c.slot_uv.alloc(nslots * 2));
+      A(c.cslot_meta.alloc((size_t)nnormal * TILE));
+      A(c.cslot_widx.alloc((size_t)nnormal * TILE));
+      A(c.cm_uv.alloc(2 * (size_t)nobs_local));
+      A(c.cm_lp.alloc(nobs_local));
+      A(c.pt.alloc((size_t)npl * 3));
+      A(c.hpp.alloc((size_t)npl * 6));
+      A(c.gp.alloc((size_t)npl * 3));
+      A(c.hinv.alloc((size_t)npl * 6));
+      A(c.step_pt.alloc((size_t)npl * 3));
+    });
+  };
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{alloc_thread};
+  build_layout(d, c.nranks, c.rank, L, c.mv_ctas_per_sm * (uint32_t)c.num_sms, c.mv_window, true, on_tiles);
+  if (alloc_thread.joinable()) alloc_thread.join();
+  if (alloc_err != cudaSuccess) { c.err = std::string("device allocation: ") + cudaGetErrorString(alloc_err); cudaGetLastError(); return APEX_ERR_CUDA; }
   c.shard = L.shard; c.npl = L.npl; c.nobs_local = L.nobs_local;
   c.nnormal_chunks = L.nnormal_chunks; c.nchunks = L.nchunks;
   c.mv_nranges = (uint32_t)L.range_win0.size() - 1; c.mv_nwindows = (uint32_t)L.win_desc.size(); c.mv_nrows = L.win_cams.size();
