@@ -1296,12 +1296,15 @@ static int tail_plan_dc(Ctx& c, bool& one) {
   if (per_sm_want < 1) return 0;
   const uint32_t need = (c.ncam + TAIL_THREADS / 32 - 1) / (TAIL_THREADS / 32);
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_tail_kernel<DC, true>, TAIL_THREADS, 0) == cudaSuccess && occ > 0 &&
+  const char* gs = getenv("APEX_PCG_TAIL_STRIDE");   // test switch: the grid-stride variant also where one warp per camera would fit
+  const bool force_stride = gs && atoi(gs) != 0;
+  if (!force_stride && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_tail_kernel<DC, true>, TAIL_THREADS, 0) == cudaSuccess && occ > 0 &&
       need <= (uint32_t)(std::min(occ, per_sm_want) * c.num_sms)) { one = true; return (int)std::max<uint32_t>(need, 1); }
   cudaGetLastError();
   one = false;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_tail_kernel<DC, false>, TAIL_THREADS, 0) != cudaSuccess || occ <= 0) { cudaGetLastError(); return 0; }
-  return (int)std::max<uint32_t>(1, std::min<uint32_t>(need, (uint32_t)(std::min(occ, per_sm_want) * c.num_sms)));
+  const uint32_t cap = force_stride ? std::max<uint32_t>(1, need / 3) : (uint32_t)(std::min(occ, per_sm_want) * c.num_sms);   // (test switch: about three cameras per warp)
+  return (int)std::max<uint32_t>(1, std::min<uint32_t>(need, std::min<uint32_t>(cap, (uint32_t)(std::min(occ, per_sm_want) * c.num_sms))));
 }
 static int pcg_tail_plan(Ctx& c, bool& one) {
   switch (c.dc) {

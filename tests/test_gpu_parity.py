@@ -466,12 +466,19 @@ def test_operator_windows_and_run_chains(flush, monkeypatch):
         assert sg[3] == so[3] and relerr(sg[0], so[0]) < 1e-5, "truncated PCG: same iteration count, same step"
 
 
-@pytest.mark.parametrize("tail", ["2", "1", "0"])
+@pytest.mark.parametrize("tail", ["2", "1", "0", "stride", "stride-nopdl", "nopdl"])
 def test_pcg_fused_tail_and_three_kernel_path(tail, monkeypatch):
-    """PCG between two operator applications: the fused tail kernel (one warp per camera, software grid barriers, second pass of
-    the deterministic flush inside; APEX_PCG_TAIL = CTAs per SM, default 2) and the separate kernels (APEX_PCG_TAIL=0) take the
-    oracle's iteration count and agree with it on the step; ncam = 37 leaves warps of the last CTA without cameras."""
-    monkeypatch.setenv("APEX_PCG_TAIL", tail)
+    """PCG between two operator applications: the fused tail kernel (one warp per camera, tagged-slot sum exchanges, second pass of
+    the deterministic flush inside; APEX_PCG_TAIL = CTAs per SM), its grid-stride variant (the one problems with more cameras than
+    16 x SMs get - the Final-13682 shape -, forced here by APEX_PCG_TAIL_STRIDE with about three cameras per warp), both with and
+    without programmatic dependent launches (APEX_PDL=0), and the separate kernels (APEX_PCG_TAIL=0) take the oracle's iteration
+    count and agree with it on the step; ncam = 37 leaves warps of the last CTA without cameras."""
+    if tail.startswith("stride"):
+        monkeypatch.setenv("APEX_PCG_TAIL_STRIDE", "1")
+    if tail.endswith("nopdl"):
+        monkeypatch.setenv("APEX_PDL", "0")
+    if tail in ("2", "1", "0"):
+        monkeypatch.setenv("APEX_PCG_TAIL", tail)
     for ncam, npts in ((37, 1500), (10, 300)):
         prob = small_problem(ncam=ncam, npts=npts)
         g, o = pair(prob)
