@@ -420,6 +420,109 @@ def test_se3_plus_and_act_conventions():
     assert np.allclose(out[3:], qn, atol=1e-18)
 
 
+# ---- the reference's own SO3 / SE3 known-answer tests, on the operations the path uses (Exp through (+), act, rotation matrix) ----
+IDENT = [0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0]
+
+
+def quat_from_euler(roll, pitch, yaw):
+    """nalgebra UnitQuaternion::from_euler_angles(roll, pitch, yaw) = Rz(yaw) Ry(pitch) Rx(roll), as (w, x, y, z)."""
+    cr, sr, cp, sp, cy, sy = math.cos(roll / 2), math.sin(roll / 2), math.cos(pitch / 2), math.sin(pitch / 2), math.cos(yaw / 2), math.sin(yaw / 2)
+    return np.array([cr * cp * cy + sr * sp * sy, sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy])
+
+
+def so3_log(q):
+    """Independent numpy Log of a unit quaternion (w, x, y, z): rotation vector."""
+    q = np.asarray(q, dtype=np.float64)
+    if q[0] < 0:
+        q = -q
+    n = np.linalg.norm(q[1:])
+    if n < 1e-12:
+        return 2.0 * q[1:] / q[0]
+    return 2.0 * math.atan2(n, q[0]) * q[1:] / n
+
+
+def hat(v):
+    return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+
+
+def se3_log(pose):
+    """Independent numpy Log of [t, q]: (rho, theta) with t = J_l(theta) rho (Exp as se3.rs:569-586 defines it)."""
+    th = so3_log(pose[3:])
+    a = np.linalg.norm(th)
+    K = hat(th)
+    if a < 1e-7:
+        Jl = np.eye(3) + 0.5 * K
+    else:
+        Jl = np.eye(3) + (1 - math.cos(a)) / a ** 2 * K + (a - math.sin(a)) / a ** 3 * K @ K
+    return np.concatenate([np.linalg.solve(Jl, np.asarray(pose[:3])), th])
+
+
+def exp_se3(tau):
+    return se3_plus(IDENT, tau)
+
+
+def test_so3_reference_kats():
+    """crates/apex-manifolds/src/so3.rs tests: identity rotation / act (:842-860, :1020-1025), from_euler_angles(pi, pi/2, pi/4) acting on
+    (1,1,1) -> (0, -sqrt 2, -1) (:1027-1032), exp(0) = identity and exp(-v) = exp(v)^-1 (:965-983), quarter turns about x and z (:1143-1156),
+    exp/log round trips at 1e-8 (:1135-1140) and around the small-angle threshold 1e-6 .. 1e-3 (:1539-1553), 1000 composed small rotations
+    = Exp(1000 v) to 1e-6 (:1424-1439)."""
+    R = np.zeros(9)
+    L.oracle_rotation_matrix(F.ptr(arr(1.0, 0.0, 0.0, 0.0)), F.ptr(R))
+    assert np.array_equal(R.reshape(3, 3), np.eye(3))
+    assert np.allclose(se3_act(IDENT, [1.0, 1.0, 1.0]), [1.0, 1.0, 1.0], atol=1e-12)
+    q = quat_from_euler(math.pi, math.pi / 2, math.pi / 4)
+    out = se3_act(np.concatenate([np.zeros(3), q]), [1.0, 1.0, 1.0])
+    assert abs(out[0]) < 1e-12 and abs(out[1] + math.sqrt(2)) < 1e-10 and abs(out[2] + 1.0) < 1e-12
+    e0 = exp_se3(np.zeros(6))
+    assert np.array_equal(e0, IDENT)
+    ep, en = exp_se3([0, 0, 0, 0.1, 0.2, 0.3]), exp_se3([0, 0, 0, -0.1, -0.2, -0.3])
+    assert np.allclose(en[4:], -ep[4:], atol=1e-12) and abs(en[3] - ep[3]) < 1e-12
+    qx = exp_se3([0, 0, 0, math.pi / 2, 0, 0])          # from_axis_angle(x, pi/2) = Exp(pi/2 e_x)
+    assert np.allclose(se3_act(qx, [0.0, 1.0, 0.0]), [0.0, 0.0, 1.0], atol=1e-12)
+    qz = exp_se3([0, 0, 0, 0, 0, math.pi / 2])
+    assert np.allclose(se3_act(qz, [1.0, 0.0, 0.0]), [0.0, 1.0, 0.0], atol=1e-12)
+    v = np.array([1e-8, 2e-8, 3e-8])
+    assert np.linalg.norm(so3_log(exp_se3(np.concatenate([np.zeros(3), v]))[3:]) - v) < 1e-12
+    for angle in (1e-6, 1e-5, 1e-4, 1e-3):              # both sides of theta^2 = 1e-10 (so3.rs:558-577)
+        v = np.array([angle, 0.0, 0.0])
+        assert np.linalg.norm(so3_log(exp_se3(np.concatenate([np.zeros(3), v]))[3:]) - v) < 1e-10
+    small = np.array([0, 0, 0, 0.001, 0.002, -0.001])
+    acc = np.array(IDENT)
+    for _ in range(1000):
+        acc = se3_plus(acc, small)                       # compose(accumulated, Exp(small))
+    want = exp_se3(1000 * small)
+    assert np.linalg.norm(so3_log(acc[3:]) - so3_log(want[3:])) < 1e-6
+
+
+def test_se3_reference_kats():
+    """crates/apex-manifolds/src/se3.rs tests: act with the identity (:1007-1019), exp/log round trip of (0.1,0.2,0.3,0.01,0.02,0.03) to
+    1e-9 (:1035-1045), exp(0) = identity (:1048-1058), translation-only and roll-pi/2 poses acting on points (:1111-1134), the 1e-8 / 1e-9
+    small-angle pose (:1137-1149), ten odometry steps (1 m forward, 0.1 rad yaw) (:1492-1513; here against the closed form Exp(10 tau)
+    instead of the reference's 5.0 tolerance), 1 km translation with a 1e-6 rad rotation and a millimetre translation with a large
+    rotation through log -> exp (:1529-1555)."""
+    assert np.allclose(se3_act(IDENT, [1.0, 2.0, 3.0]), [1.0, 2.0, 3.0], atol=1e-9)
+    tau = np.array([0.1, 0.2, 0.3, 0.01, 0.02, 0.03])
+    assert np.linalg.norm(se3_log(exp_se3(tau)) - tau) < 1e-9
+    assert np.allclose(se3_act([1.0, 2.0, 3.0, 1.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0]), [1.0, 2.0, 3.0], atol=1e-9)
+    roll = np.concatenate([np.zeros(3), quat_from_euler(math.pi / 2, 0.0, 0.0)])
+    assert np.allclose(se3_act(roll, [0.0, 1.0, 0.0]), [0.0, 0.0, 1.0], atol=1e-9)
+    small = np.concatenate([[1e-8, 2e-8, 3e-8], quat_from_euler(1e-9, 2e-9, 3e-9)])
+    assert np.linalg.norm(se3_log(small) - np.array([1e-8, 2e-8, 3e-8, 1e-9, 2e-9, 3e-9])) < 1e-9
+    assert np.linalg.norm(se3_log(exp_se3([1e-8, 2e-8, 3e-8, 1e-9, 2e-9, 3e-9])) - np.array([1e-8, 2e-8, 3e-8, 1e-9, 2e-9, 3e-9])) < 1e-15
+    step = np.concatenate([[1.0, 0.0, 0.0], quat_from_euler(0.0, 0.0, 0.1)])
+    tau = se3_log(step)
+    pose = np.array(IDENT)
+    for _ in range(10):
+        pose = se3_plus(pose, tau)                       # compose(pose, step)
+    want = exp_se3(10 * tau)
+    assert np.allclose(pose[:3], want[:3], atol=1e-12) and np.allclose(pose[3:], want[3:], atol=1e-13)
+    assert abs(so3_log(pose[3:])[2] - 1.0) < 1e-12       # one radian of yaw in total
+    for t, th in (([1000.0, 2000.0, 500.0], [1e-6, 2e-6, 3e-6]), ([0.001, 0.002, -0.001], so3_log(quat_from_euler(1.5, 0.5, -1.2)))):
+        se3 = np.concatenate([t, exp_se3(np.concatenate([np.zeros(3), th]))[3:]])
+        back = exp_se3(se3_log(se3))
+        assert np.allclose(back[:3], se3[:3], rtol=0, atol=1e-9 * max(1.0, np.linalg.norm(t))) and np.allclose(back[3:], se3[3:], atol=1e-12)
+
+
 @pytest.mark.parametrize("model,intr,z", [(F.CAM_BAL, [500.0, 1e-2, 1e-3], -1), (F.CAM_KANNALA_BRANDT, [300.0, 300.0, 320.0, 240.0, 0.1, 0.01, 0.001, 0.0001], 1),
                                           (F.CAM_DOUBLE_SPHERE, [300.0, 300.0, 320.0, 240.0, -0.2, 0.6], 1), (F.CAM_PINHOLE, [500.0, 500.0, 320.0, 240.0], 1)])
 def test_projection_factor_jacobians_vs_central_differences_of_plus(model, intr, z):
