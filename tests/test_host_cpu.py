@@ -2,6 +2,7 @@
 declares, fails loudly without a device (no CPU fallback), the host-side sharding logic, the synthetic generator,
 the oracle end to end on small BASELINE-shaped problems, and the N>1 decomposition over gloo (world_size 2)."""
 import ctypes as C
+import math
 import os
 import re
 import subprocess
@@ -170,6 +171,47 @@ def test_oracle_lm_converges_and_variants_agree(variant):
 def test_oracle_observer_feed():
     """OptObserver feed of the LM loop (parity_helpers.check_observer_feed) on the oracle; the GPU library runs the same check in -m gpu."""
     check_observer_feed(OracleContext, synth.make_problem(10, 300, 4.0, seed=11, self_calibration=True))
+
+
+def test_oracle_step_application_and_parameter_norm_kats():
+    """src/optimizer/mod.rs:1123-1180 restated on BA variables: apply_parameter_step advances an Rn variable by the step (x = 0, step 3
+    -> 3) and apply_negative_parameter_step reverts it exactly on Rn (5 -> 7 -> 5); on SE3 the step goes through (+) (pose o Exp(step))
+    and the negative step returns to the start only to first order (the reference's revert, mod.rs:343-356); compute_parameter_norm is the
+    2-norm over the variables' storage (sqrt(3^2 + 4^2) = 5): 7 numbers per pose incl. the quaternion, intrinsics, landmarks; fixed
+    indices are zeroed at the update only (problem.rs:185-289)."""
+    prob = synth.make_problem(3, 12, 3.0, seed=5, self_calibration=True)
+    prob.pt[:] = 0.0
+    prob.pt[0] = [5.0, 0.0, 0.0]
+    prob.pt_fixed = np.zeros(prob.npts, dtype=np.uint8); prob.pt_fixed[1] = 0b010      # y of landmark 1 is fixed
+    o = OracleContext().upload(prob)
+    pose0, intr0, pt0 = [a.copy() for a in o.params_download()]
+    sc = np.zeros((prob.ncam, prob.dc)); sp = np.zeros((prob.npts, 3))
+    sp[0] = [2.0, 0.0, 0.0]; sp[1] = [1.0, 1.0, 1.0]; sp[2] = [3.0, 0.0, 0.0]
+    o.apply_step(sc, sp, +1.0)
+    _, _, pt1 = o.params_download()
+    assert pt1[0, 0] == 7.0 and pt1[2, 0] == 3.0 and list(pt1[1]) == [1.0, 0.0, 1.0]
+    o.apply_step(sc, sp, -1.0)
+    assert np.array_equal(o.params_download()[2], pt0), "Rn: the negative step is an exact revert"
+    sc[1, :6] = [0.01, -0.02, 0.03, 0.004, -0.005, 0.006]
+    sc[1, 6:] = 0.5
+    o.apply_step(sc, np.zeros_like(sp), +1.0)
+    pose1, intr1, _ = o.params_download()
+    assert np.array_equal(pose1[[0, 2]], pose0[[0, 2]]) and not np.array_equal(pose1[1], pose0[1])
+    assert np.allclose(intr1[1], intr0[1] + 0.5, rtol=0, atol=1e-12) and abs(np.linalg.norm(pose1[1, 3:]) - 1.0) < 1e-15
+    o.apply_step(sc, np.zeros_like(sp), -1.0)
+    pose2, intr2, _ = o.params_download()
+    assert np.allclose(pose2[1], pose0[1], atol=1e-3) and not np.array_equal(pose2[1], pose0[1]), "SE3: (x (+) d) (+) (-d) = x only to first order"
+    assert np.allclose(intr2[1], intr0[1], rtol=0, atol=1e-12)
+    # parameter norm: one LM iteration whose step is (almost) zero - damping 1e30 - reports the norm of the variables' storage
+    o = OracleContext().upload(prob)
+    cfg = o.default_config(True)
+    cfg.schur_variant = F.SCHUR_EXPLICIT
+    cfg.max_iterations = 0
+    cfg.damping, cfg.damping_max = 1e30, 1e32
+    _, tr = o.lm_solve(cfg)
+    pose, intr, pt = o.params_download()
+    want = math.sqrt((pose ** 2).sum() + (intr ** 2).sum() + (pt ** 2).sum())
+    assert abs(tr[0].parameter_norm - want) <= 1e-12 * want and tr[0].step_norm < 1e-20
 
 
 def test_oracle_linear_solve_matches_scipy():
