@@ -222,6 +222,72 @@ def test_loss_second_derivative_matches_numerical_derivative_of_first(lid, prm):
         assert abs(num - r0[2]) <= 1e-5 * max(1.0, abs(r0[2])), (lid, s, num, r0[2])
 
 
+def ref_numerical_derivative(lid, prm, s, h):
+    """numerical_derivative of the reference's own tests (src/core/loss_functions.rs:1591-1604): central differences of RHO."""
+    rp, rm, r0 = loss_eval(lid, prm, s + h)[0], loss_eval(lid, prm, s - h)[0], loss_eval(lid, prm, s)[0]
+    return (rp - rm) / (2 * h), (rp - 2 * r0 + rm) / (h * h)
+
+
+def test_loss_reference_unit_tests():
+    """The reference's per-loss unit tests (src/core/loss_functions.rs:1607-2005), assertion by assertion, with its constructor arguments
+    and its tolerances (EPSILON = 1e-6; derivative checks against numerical_derivative with h = 1e-5 at 1e-4 / 1e-3)."""
+    EPS = 1e-6
+    ev = loss_eval
+    assert list(ev(F.LOSS_L2, [], 0.0)) == [0.0, 1.0, 0.0] and list(ev(F.LOSS_L2, [], 4.0)) == [4.0, 1.0, 0.0]                     # :1607-1623
+    r = ev(F.LOSS_L1, [], 0.0)                                                                                                      # :1626-1641
+    assert r[0] == 0.0 and np.isfinite(r[1]) and np.isfinite(r[2])
+    r = ev(F.LOSS_L1, [], 4.0)
+    assert abs(r[0] - 4.0) < EPS and abs(r[1] - 0.5) < EPS
+    assert list(ev(F.LOSS_FAIR, [1.3999], 0.0)) == [0.0, 1.0, 0.0]                                                                  # :1644-1667
+    w1, w100, r4 = ev(F.LOSS_FAIR, [1.3999], 1.0)[1], ev(F.LOSS_FAIR, [1.3999], 100.0)[1], ev(F.LOSS_FAIR, [1.3999], 4.0)
+    assert 0.2 < w1 < 0.25 and w100 < w1 and np.isfinite(r4[1]) and r4[1] > 0 and np.isfinite(r4[2]) and r4[2] < 0
+    r = ev(F.LOSS_GEMAN_MCCLURE, [1.0], 0.0)                                                                                        # :1670-1692
+    assert r[0] == 0.0 and abs(r[1] - 1.0) < EPS
+    ws, wl = ev(F.LOSS_GEMAN_MCCLURE, [1.0], 1.0)[1], ev(F.LOSS_GEMAN_MCCLURE, [1.0], 100.0)[1]
+    assert wl < ws and wl < 0.1
+    for lid, prm, s0, tol2 in ((F.LOSS_GEMAN_MCCLURE, [1.0], 2.0, 1e-3), (F.LOSS_WELSCH, [2.9846], 5.0, 1e-3), (F.LOSS_RAMSAY_EA, [0.3], 4.0, 1e-3),
+                               (F.LOSS_LP_NORM, [1.5], 4.0, 1e-3), (F.LOSS_T_DISTRIBUTION, [5.0], 4.0, 1e-4)):
+        r = ev(lid, prm, s0)
+        n1, n2 = ref_numerical_derivative(lid, prm, s0, 1e-5)
+        assert abs(r[1] - n1) < 1e-4 and abs(r[2] - n2) < tol2, (lid, r, n1, n2)
+    r = ev(F.LOSS_WELSCH, [2.9846], 0.0)                                                                                            # :1695-1717
+    assert r[0] == 0.0 and abs(r[1] - 0.5) < EPS
+    w10, w100 = ev(F.LOSS_WELSCH, [2.9846], 10.0)[1], ev(F.LOSS_WELSCH, [2.9846], 100.0)[1]
+    assert w100 < w10 and w100 < 0.01
+    c2 = 4.6851 * 4.6851                                                                                                            # :1720-1743
+    r = ev(F.LOSS_TUKEY, [4.6851], 0.0)
+    assert r[0] == 0.0 and abs(r[1] - 0.5) < EPS
+    assert ev(F.LOSS_TUKEY, [4.6851], c2 * 0.5)[1] > 0.05 and ev(F.LOSS_TUKEY, [4.6851], c2 * 1.5)[1] == 0.0
+    r = ev(F.LOSS_TUKEY, [4.6851], 5.0)
+    assert np.isfinite(r[1]) and r[1] > 0 and np.isfinite(r[2]) and r[2] < 0
+    r = ev(F.LOSS_ANDREWS, [1.339], 0.0)                                                                                            # :1746-1769
+    assert r[0] == 0.0 and abs(r[1]) < EPS
+    r = ev(F.LOSS_ANDREWS, [1.339], 1.0)
+    assert 0.33 < r[1] < 0.35 and np.isfinite(r[2])
+    assert abs(ev(F.LOSS_ANDREWS, [1.339], (1.339 * math.pi + 0.1) ** 2)[1]) < 0.01
+    assert ev(F.LOSS_RAMSAY_EA, [0.3], 0.0)[0] == 0.0                                                                               # :1772-1792
+    assert ev(F.LOSS_RAMSAY_EA, [0.3], 100.0)[1] < ev(F.LOSS_RAMSAY_EA, [0.3], 1.0)[1]
+    r = ev(F.LOSS_TRIMMED_MEAN, [2.0], 2.0)                                                                                         # :1795-1812
+    assert abs(r[0] - 1.0) < EPS and abs(r[1] - 0.5) < EPS and r[2] == 0.0
+    r = ev(F.LOSS_TRIMMED_MEAN, [2.0], 10.0)
+    assert abs(r[0] - 2.0) < EPS and r[1] == 0.0 and r[2] == 0.0
+    assert abs(ev(F.LOSS_LP_NORM, [1.0], 4.0)[0] - 2.0) < EPS                                                                        # :1815-1842
+    r = ev(F.LOSS_LP_NORM, [2.0], 4.0)
+    assert abs(r[0] - 4.0) < EPS and abs(r[1] - 1.0) < EPS and r[2] == 0.0
+    assert ev(F.LOSS_LP_NORM, [0.5], 4.0)[1] < 1.0
+    assert ev(F.LOSS_BARRON, [0.0, 1.0], 100.0)[1] < ev(F.LOSS_BARRON, [0.0, 1.0], 1.0)[1]                                           # :1845-1872
+    r = ev(F.LOSS_BARRON, [2.0, 1.0], 4.0)
+    assert abs(r[0] - 4.0) < EPS and abs(r[1] - 1.0) < EPS and abs(r[2]) < EPS
+    assert 0.0 < ev(F.LOSS_BARRON, [1.0, 1.0], 4.0)[1] < 1.0
+    ws, wl = ev(F.LOSS_BARRON, [-2.0, 1.0], 1.0)[1], ev(F.LOSS_BARRON, [-2.0, 1.0], 100.0)[1]
+    assert wl < ws and wl < 0.1
+    r = ev(F.LOSS_T_DISTRIBUTION, [5.0], 0.0)                                                                                       # :1924-1948
+    assert r[0] == 0.0 and abs(r[1] - 0.6) < 0.01
+    ws, wl = ev(F.LOSS_T_DISTRIBUTION, [5.0], 1.0)[1], ev(F.LOSS_T_DISTRIBUTION, [5.0], 100.0)[1]
+    assert wl < ws and wl < 0.1
+    assert ev(F.LOSS_T_DISTRIBUTION, [3.0], 100.0)[1] < ev(F.LOSS_T_DISTRIBUTION, [10.0], 100.0)[1]                                  # :1951-1964
+
+
 def test_loss_exact_values():
     # closed forms straight from the reference bodies (loss_functions.rs:364-383, 497-509, 1132-1141, 848-869)
     assert np.allclose(loss_eval(F.LOSS_HUBER, [2.0], 9.0), [2 * 2 * 3 - 4, 2 / 3, -(2 / 3) / 18], rtol=0, atol=1e-15)
