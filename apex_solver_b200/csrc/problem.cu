@@ -154,7 +154,7 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
   // Stable counting sort by local landmark, in parallel: the observation list is cut into T contiguous pieces, piece t
   // counts its observations per landmark, a prefix over (landmark, piece) gives every piece its write cursor.
   std::vector<uint64_t> pt_start((size_t)npl + 1, 0);  // exclusive prefix of the LOCAL landmarks' observation counts
-  HostVec<uint64_t> pm;
+  HostVec<uint32_t> pm;   // point-major order: observation index (nobs < 2^32, validate_problem)
   {
     int T = std::max(1, std::min(omp_get_max_threads(), 16));
     while (T > 1 && (size_t)T * npl * sizeof(uint32_t) > ((size_t)1 << 30)) T /= 2;  // counters: at most 1 GiB
@@ -192,7 +192,7 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
         const uint32_t p = d->obs_pt[o];
         if (!L.shard.owns(p)) continue;
         const uint32_t lp = L.shard.to_local(p);
-        pm[pt_start[lp] + cnt[t][lp]++] = o;
+        pm[pt_start[lp] + cnt[t][lp]++] = (uint32_t)o;
       }
     }
   }
