@@ -161,6 +161,16 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
     if (nobs < 100000) T = 1;
     std::vector<HostVec<uint32_t>> cnt(T);
     auto piece = [&](int t) { return std::make_pair(nobs * (uint64_t)t / T, nobs * (uint64_t)(t + 1) / T); };
+    // ShardMap::owns / to_local per observation, twice: with a runtime rank count that is two integer divisions per call - most of
+    // this phase on a rank of several, which scans ALL observations. Powers of two (the usual rank counts) get shifts and masks.
+    static_assert((SHARD_BLOCK & (SHARD_BLOCK - 1)) == 0, "block size is a power of two");
+    const uint32_t nr = (uint32_t)nranks, rk = (uint32_t)rank;
+    const bool pow2 = (nr & (nr - 1)) == 0;
+    uint32_t rsh = 0, bsh = 0;
+    while ((1u << rsh) < nr) ++rsh;
+    while ((1u << bsh) < SHARD_BLOCK) ++bsh;
+    auto owns = [&](uint32_t p) { const uint32_t b = p >> bsh; return pow2 ? (b & (nr - 1)) == rk : b % nr == rk; };
+    auto to_local = [&](uint32_t p) { const uint32_t b = p >> bsh; return ((pow2 ? (b - rk) >> rsh : (b - rk) / nr) << bsh) | (p & (SHARD_BLOCK - 1)); };
 #pragma omp parallel for num_threads(T) schedule(static, 1)
     for (int t = 0; t < T; ++t) {
       cnt[t].resize(npl);
@@ -168,7 +178,7 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
       const auto [o0, o1] = piece(t);
       for (uint64_t o = o0; o < o1; ++o) {
         const uint32_t p = d->obs_pt[o];
-        if (L.shard.owns(p)) cnt[t][L.shard.to_local(p)]++;
+        if (owns(p)) cnt[t][to_local(p)]++;
       }
     }
 #pragma omp parallel for schedule(static)
@@ -190,8 +200,8 @@ static void build_layout(const apex_problem_desc* d, int nranks, int rank, HostL
       const auto [o0, o1] = piece(t);
       for (uint64_t o = o0; o < o1; ++o) {
         const uint32_t p = d->obs_pt[o];
-        if (!L.shard.owns(p)) continue;
-        const uint32_t lp = L.shard.to_local(p);
+        if (!owns(p)) continue;
+        const uint32_t lp = to_local(p);
         pm[pt_start[lp] + cnt[t][lp]++] = (uint32_t)o;
       }
     }
