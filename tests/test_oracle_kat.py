@@ -726,6 +726,48 @@ def test_solve_with_cholesky_and_pcg():  # explicit_schur.rs:1914-1938, 1942-195
     assert np.allclose(x, np.linalg.solve(A, b), rtol=1e-10, atol=1e-12)
 
 
+def test_reference_schur_fixture_through_the_dense_pipeline():
+    """The 2-camera / 3-landmark fixture of the reference's Schur solver tests (explicit_schur.rs:1299-1363 = implicit_schur.rs:1111-1164:
+    36 x 21 Jacobian with J[row_base + k, cam + k] = J[row_base + k, lm + k % 3] = 1, residuals (i % 5) / 10, H_cc = 3 I, H_pp = 4 I)
+    through steps 2-8 of solve_augmented_equation (:1162-1234) as the oracle restates them - damped 3x3 inverses, Schur complement,
+    reduced gradient, Cholesky or PCG on S, back-substitution - against a direct numpy solve of (J^T J + lambda I) delta = -J^T r,
+    for the lambdas the reference's tests use (:1712-1798: 0.1, 0.001, 100; different lambda => different update)."""
+    J = np.zeros((36, 21))
+    for ci, cam in enumerate((0, 6)):
+        for li, lm in enumerate((12, 15, 18)):
+            rb = (ci * 3 + li) * 6
+            for k in range(6):
+                J[rb + k, cam + k] = 1.0
+                J[rb + k, lm + k % 3] = 1.0
+    r = np.array([(i % 5) * 0.1 for i in range(36)])
+    H, g = J.T @ J, J.T @ r
+    assert np.array_equal(H[:12, :12], 3 * np.eye(12)) and np.array_equal(H[12:, 12:], 4 * np.eye(9))   # the fixture's own claim
+    steps = {}
+    for lam in (0.1, 0.001, 100.0):
+        hcc = np.ascontiguousarray(H[:12, :12] + lam * np.eye(12)); hcp = np.ascontiguousarray(H[:12, 12:])
+        hinv = np.zeros((3, 9))
+        for l in range(3):
+            blk = np.ascontiguousarray(H[12 + 3 * l:15 + 3 * l, 12 + 3 * l:15 + 3 * l] + lam * np.eye(3)).reshape(9)
+            assert L.oracle_invert_landmark_block(F.ptr(blk), C.c_double(lam), 0, F.ptr(hinv[l])) == 1
+        bc, bp = np.ascontiguousarray(-g[:12]), np.ascontiguousarray(-g[12:])
+        S = np.zeros((12, 12)); rhs = np.zeros(12)
+        L.oracle_schur_complement_dense(12, 3, F.ptr(hcc), F.ptr(hcp), F.ptr(hinv), F.ptr(S))
+        L.oracle_reduced_gradient_dense(12, 3, F.ptr(bc), F.ptr(bp), F.ptr(hcp), F.ptr(hinv), F.ptr(rhs))
+        want = np.linalg.solve(H + lam * np.eye(21), -g)
+        for variant in ("sparse", "iterative"):
+            dc = np.zeros(12); dp = np.zeros(9)
+            if variant == "sparse":
+                assert L.oracle_solve_cholesky_dense(12, F.ptr(S), F.ptr(rhs), F.ptr(dc)) == 0
+            else:
+                L.oracle_solve_pcg_dense(12, F.ptr(S), F.ptr(rhs), F.ptr(dc), 200, C.c_double(1e-6))
+            L.oracle_back_substitute_dense(12, 3, F.ptr(dc), F.ptr(bp), F.ptr(hcp), F.ptr(hinv), F.ptr(dp))
+            got = np.concatenate([dc, dp])
+            tol = 1e-11 if variant == "sparse" else 1e-5
+            assert np.abs(got - want).max() <= tol * max(1.0, np.abs(want).max()), (lam, variant)
+        steps[lam] = want
+    assert ((steps[0.001] - steps[100.0]) ** 2).sum() > 1e-10
+
+
 def test_inverse_n_matches_numpy():
     rng = np.random.default_rng(5)
     for n in (1, 2, 3, 4, 6, 8):
