@@ -50,6 +50,59 @@ def test_struct_layouts_match_the_header(tmp_path):
     assert got == want
 
 
+def test_plain_c_client_links_and_calls_the_host_side_of_the_abi(tmp_path):
+    """The boundary is a C ABI: a C99 translation unit (no C++, no Python) includes include/apex_gpu.h, links libapex_gpu.so and calls
+    the entry points that need no device - presets, the sharding rule, the BAL round trip (writer -> loader -> the CLI's problem
+    construction) and the layout build - the way the reference's Rust shim would through `extern "C"`. Without a device
+    apex_ctx_create must report APEX_ERR_NO_DEVICE (no CPU fallback); with one it must succeed."""
+    src = tmp_path / "client.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <string.h>
+#include "apex_gpu.h"
+int main(int argc, char** argv) {
+  if (apex_abi_version() != 100) return 10;
+  apex_lm_config cfg;
+  apex_lm_config_for_bundle_adjustment(&cfg);
+  if (cfg.max_iterations != 20 || cfg.damping != 1e-3) return 11;
+  /* 2 cameras, 3 points, 5 observations */
+  double cams[2 * 9] = {0.01, -0.02, 0.03, 0.1, 0.2, -0.3, 500.0, -1e-7, 1e-13,   -0.02, 0.01, 0.0, -0.1, 0.0, 0.2, 510.0, 2e-7, 0.0};
+  double pts[3 * 3] = {0.1, 0.2, -5.0, -0.3, 0.1, -6.0, 0.2, -0.2, -4.0};
+  unsigned obs_cam[5] = {0, 0, 0, 1, 1}, obs_pt[5] = {0, 1, 2, 0, 2};
+  double uv[5 * 2] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10};
+  apex_bal_dataset* ds = 0;
+  if (apex_bal_from_arrays(2, 3, 5, cams, pts, obs_cam, obs_pt, uv, &ds) != APEX_OK) return 12;
+  if (apex_bal_write(ds, argv[1]) != APEX_OK) return 13;
+  apex_bal_free(ds);
+  if (apex_bal_load(argv[1], &ds) != APEX_OK) { fprintf(stderr, "%s\n", apex_bal_last_error()); return 14; }
+  apex_bal_view v;
+  if (apex_bal_view_get(ds, &v) != APEX_OK || v.ncam != 2 || v.npts != 3 || v.nobs != 5) return 15;
+  if (memcmp(v.cameras, cams, sizeof cams) != 0 || memcmp(v.points, pts, sizeof pts) != 0) return 16;   /* 17 significant digits: bit-exact */
+  apex_problem_desc desc;
+  if (apex_bal_build_problem(ds, 3 /* -n: all points */, 1 /* SelfCalibration */, &desc) != APEX_OK) return 17;
+  if (desc.ncam != 2 || desc.npts != 3 || desc.nobs != 5 || desc.intr_dim != 3) return 18;
+  unsigned block = 0, npl = 0; unsigned long long nl = 0;
+  if (apex_shard_info(desc.npts, desc.nobs, desc.obs_pt, 2, 1, &block, &npl, (uint64_t*)&nl) != APEX_OK || block != 128 || npl != 0 || nl != 0) return 19;
+  apex_layout_stats st;
+  if (apex_layout_stats_compute(&desc, 1, 0, &st) != APEX_OK || st.consistent != 1 || st.nobs_local != 5 || st.nchunks != 1) return 20;
+  apex_ctx_desc cd; memset(&cd, 0, sizeof cd); cd.nranks = 1;
+  apex_ctx* ctx = 0;
+  apex_status s = apex_ctx_create(&cd, &ctx);
+  if (apex_device_count() > 0) { if (s != APEX_OK) return 21; apex_ctx_destroy(ctx); }
+  else if (s != APEX_ERR_NO_DEVICE) return 22;
+  apex_bal_free(ds);
+  printf("ok\n");
+  return 0;
+}
+""")
+    exe = tmp_path / "client"
+    libdir = os.path.dirname(F.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lapex_gpu", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe), str(tmp_path / "tiny.txt")], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", (out.returncode, out.stdout, out.stderr)
+
+
 def test_config_presets_match_reference():  # levenberg_marquardt.rs:319-359, 519-530
     lib = F.load_library()
     d, b = F.LmConfig(), F.LmConfig()
